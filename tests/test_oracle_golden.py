@@ -1,0 +1,111 @@
+"""The oracle restatement vs golden vectors recorded from the UNMODIFIED reference
+(baselines/her/her.py, replay_buffer.py) - bit exact.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import her_oracle, replay_oracle
+from oracle.reward_oracle import ModuleDistanceReward
+from tests.golden_util import GOLDEN, load_case, per_row_choices, sampler_cases
+
+
+def build_oracle_sampler(meta):
+    reward = ModuleDistanceReward(meta['tasks_ag_id'], meta['tasks_g_id'], meta['threshold'])
+    if meta['flat']:
+        s = her_oracle.make_sample_her_transitions(meta['goal_replay'], meta['her_replay_k'], reward,
+                                                   meta['task_replay'], tasks_ag_id=meta['tasks_ag_id'],
+                                                   tasks_g_id=meta['tasks_g_id'])
+    else:
+        s = her_oracle.make_sample_multi_task_her_transitions(
+            meta['goal_replay'], meta['her_replay_k'], meta['task_replay'], reward,
+            tasks_ag_id=meta['tasks_ag_id'], tasks_g_id=meta['tasks_g_id'])
+    return s, reward
+
+
+def run_oracle(meta, eps, stream=None):
+    sampler, reward = build_oracle_sampler(meta)
+    T = meta['T']
+    kw = {}
+    if not meta['flat']:
+        kw = dict(task_to_replay=meta['task_to_replay'], cp_proba=meta['cp_proba'])
+    if stream is not None:
+        kw['stream'] = stream
+    if meta['via_buffer']:
+        shapes = {k: v.shape[1:] for k, v in eps.items()}
+        buf = replay_oracle.ReplayBufferOracle(shapes, (meta['E'] + 3) * T, T, sampler)
+        buf.store_episode({k: v.copy() for k, v in eps.items()})
+        if stream is None:
+            np.random.seed(meta['seed'])
+            # the reference seeded before store_episode; storing E episodes in order draws nothing
+        out = buf.sample(meta['B'], **kw)
+    else:
+        batch = {k: v.copy() for k, v in eps.items()}
+        batch['o_2'] = batch['o'][:, 1:, :]
+        batch['ag_2'] = batch['ag'][:, 1:, :]
+        if stream is None:
+            np.random.seed(meta['seed'])
+        out = sampler(batch, meta['B'], **kw)
+    return out, sampler, reward
+
+
+@pytest.mark.parametrize('name', sampler_cases())
+def test_oracle_matches_reference_with_own_draws(name):
+    """Seeded like the reference run: same RNG consumption order, same outputs."""
+    meta, eps, stream, ref = load_case(name)
+    out, sampler, reward = run_oracle(meta, eps)
+    s = sampler.last_stream
+    assert np.array_equal(s.ep, stream['s_ep'])
+    assert np.array_equal(s.t, stream['s_t'])
+    assert np.array_equal(s.u_her, stream['s_uher'])
+    assert np.array_equal(s.u_off, stream['s_uoff'])
+    assert set(out.keys()) == set(ref.keys())
+    for k in ref:
+        assert out[k].shape == ref[k].shape, k
+        assert out[k].dtype == ref[k].dtype, k
+        assert np.array_equal(out[k], ref[k]), k
+    assert reward.n_calls == meta['reward_calls']
+    assert (reward.last_kwargs['task_descr'] is None) == meta['reward_td_none']
+
+
+@pytest.mark.parametrize('name', sampler_cases())
+def test_oracle_matches_reference_with_injected_stream(name):
+    meta, eps, stream, ref = load_case(name)
+    inj = her_oracle.HerStream(stream['s_ep'], stream['s_t'], stream['s_uher'], stream['s_uoff'],
+                               per_row_choices(meta, stream))
+    state = np.random.get_state()[1].copy()
+    out, _, _ = run_oracle(meta, eps, stream=inj)
+    assert np.array_equal(np.random.get_state()[1], state), "injected mode must not touch np.random"
+    for k in ref:
+        assert np.array_equal(out[k], ref[k]), k
+
+
+@pytest.mark.parametrize('name', ['storage_single', 'storage_batched'])
+def test_storage_index_policy(name):
+    z = np.load(os.path.join(GOLDEN, name + '.npz'))
+    meta = json.loads(str(z['meta']))
+    T = meta['T']
+    buf = replay_oracle.ReplayBufferOracle({'o': (T + 1, 2), 'u': (T, 1)}, meta['size_ep'] * T, T, None)
+    np.random.seed(meta['seed'])
+    for k, inc in enumerate(meta['increments']):
+        ep = {'o': np.full((inc, T + 1, 2), float(k)), 'u': np.full((inc, T, 1), float(k))}
+        idx = buf.store_episode(ep)
+        assert np.array_equal(np.atleast_1d(idx), z['idx_%d' % k]), k
+        assert buf.get_current_episode_size() == z['sizes'][k]
+        assert buf.get_transitions_stored() == z['stored'][k]
+    assert np.array_equal(buf.buffers['u'][:buf.current_size, 0, 0], z['final_u'])
+
+
+def test_invariants_on_golden():
+    """Hand-derived invariants: future_t in [t+1, T], td one-hot, g zero off-module."""
+    for name in sampler_cases():
+        meta, eps, stream, ref = load_case(name)
+        T = meta['T']
+        off = (stream['s_uoff'] * (T - stream['s_t'])).astype(int)
+        ft = stream['s_t'] + 1 + off
+        assert (ft >= stream['s_t'] + 1).all() and (ft <= T).all()
+        assert ref['r'].shape == (meta['B'], 1)
+        assert set(np.unique(ref['r'])) <= {-1.0, 0.0}
+        if not meta['flat']:
+            assert np.array_equal(ref['task_descr'].sum(1), np.ones(meta['B']))
