@@ -1,0 +1,432 @@
+"""bench.py - CURIOUS training hot path on B200 (contract: see the repository prompt / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+metric   HER-relabelled transitions/s (BASELINE.json), Arm4-shaped synthetic replay:
+         4 module buffers x 1e6 transitions (20 000 episodes x T=50, dimo=40, dimg=dimag=12, dimu=4, N=4).
+step     ONE launch of the fused HER relabel+gather+reward+clip kernel over ROWS_PER_STEP rows
+         (4096 batches of 256), LP-apportioned over the module buffers, Philox draws, producing the
+         staged training batch (o, g, u, task_descr, o_2, r).
+value    rows / device time (CUDA events), inputs resident in HBM, max over ranks, whole job.
+e2e      the reference's training cycle through the public plugin API with HOST episode buffers:
+         DDPG.store_episode(host episodes) + n_batches x DDPG.train() + DDPG.update_target_net()
+         + device->host read of the critic losses; transitions consumed per second.
+--impl reference   the oracle port of that same cycle on the host cores (the reference is pure Python;
+         TF1/mpi4py/gym_flowers are not installable), one process per core up to 19.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_MODULES = 4
+T = 50
+BUFFER_TRANSITIONS = 1000000
+BATCH = 256
+ROWS_PER_STEP = 1 << 20
+CP = [0.05, 0.2, 0.1, 0.0]
+EPS_TASK = 0.4
+N_BATCHES_E2E = 100            # config.py:72
+REF_UPDATES_PER_STEP = 10      # bounded sample of the cycle for the CPU arm
+
+
+def algorithmic_bytes_per_transition(dims, n_modules, g_len=3):
+    """reads o,o_2,u,td,g and the module slices of ag_2 / future ag; writes o,o_2,g,u,td,r."""
+    rd = 4 * (2 * dims['o'] + dims['u'] + n_modules + dims['g'] + 2 * g_len)
+    wr = 4 * (2 * dims['o'] + dims['g'] + dims['u'] + n_modules + 1)
+    return rd + wr
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.check_output(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                               '--format=csv,noheader,nounits'], timeout=5).decode().strip()
+                self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[2:]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------
+# workload construction
+# ------------------------------------------------------------------------------------------------
+def synth_dims():
+    from curious_b200 import synth
+    dims = synth.arm_dims(N_MODULES)
+    ag_ids, g_ids = synth.arm_task_ids(N_MODULES)
+    return dims, ag_ids, g_ids
+
+
+def fill_buffer_on_device(buf, dims, seed):
+    """Fill a ReplayBuffer to capacity with Arm-shaped synthetic episodes generated ON the device (same value
+    structure as curious_b200.synth.make_episodes; input generation only)."""
+    import torch
+    from curious_b200.replay_buffer import StagedEpisodes
+    g = torch.Generator(device=buf.device)
+    g.manual_seed(seed)
+    E, N = buf.size, dims['task_descr']
+    chunk = 2000
+    dev = buf.device
+    for e0 in range(0, E, chunk):
+        n = min(chunk, E - e0)
+        o = torch.randn((n, T + 1, dims['o']), generator=g, device=dev).clamp_(-5, 5)
+        ag0 = (torch.rand((n, 1, dims['ag']), generator=g, device=dev) - 0.5) * 0.3
+        moving = (torch.rand((n, N), generator=g, device=dev) >= 0.3).float().repeat_interleave(dims['ag'] // N, dim=1)
+        steps = torch.randn((n, T, dims['ag']), generator=g, device=dev) * 0.02 * moving[:, None, :]
+        ag = torch.cat([ag0, ag0 + torch.cumsum(steps, dim=1)], dim=1).contiguous()
+        task = torch.randint(0, N, (n,), generator=g, device=dev)
+        td = torch.nn.functional.one_hot(task, N).float()[:, None, :].expand(n, T, N).contiguous()
+        gv = (torch.rand((n, dims['g']), generator=g, device=dev) - 0.5) * 0.3
+        gmask = td[:, 0, :].repeat_interleave(dims['g'] // N, dim=1)
+        gg = (gv * gmask)[:, None, :].expand(n, T, dims['g']).contiguous()
+        u = torch.rand((n, T, dims['u']), generator=g, device=dev) * 2 - 1
+        change = ((ag[:, :1, :] - ag[:, 1:, :]).abs() > 1e-3).float().contiguous()
+        info = (torch.rand((n, T, 1), generator=g, device=dev) < 0.25).float()
+        staged = StagedEpisodes.from_device(dict(o=o.contiguous(), ag=ag, g=gg, u=u.contiguous(), task_descr=td,
+                                                 change=change, info=info), buf.layout)
+        staged.store([(i, buf.storage, e0 + i) for i in range(n)])
+        torch.cuda.synchronize()
+    buf.current_size = E
+    buf.n_transitions_stored = E * T
+
+
+def build_gpu_workload(device, seed):
+    from curious_b200 import her, synth
+    from curious_b200.ddpg import DDPG
+    from curious_b200.replay_buffer import ReplayBuffer
+    from curious_b200.reward import ModuleDistanceReward
+    dims, ag_ids, g_ids = synth_dims()
+    sampler = her.make_sample_multi_task_her_transitions('her', 4, 'replay_task_cp_buffer',
+                                                         ModuleDistanceReward(ag_ids, g_ids), tasks_ag_id=ag_ids,
+                                                         tasks_g_id=g_ids)
+    sampler.rng = 'philox'
+    sampler.seed = seed
+    shapes = synth.buffer_shapes(dims, T)
+    buffers = [ReplayBuffer(shapes, BUFFER_TRANSITIONS if i > 0 else T, T, sampler, device=device)
+               for i in range(N_MODULES + 1)]          # buffer 0 is never written by the reference (ddpg.py:191)
+    for i in range(1, N_MODULES + 1):
+        fill_buffer_on_device(buffers[i], dims, seed * 100 + i)
+    gamma = 1. - 1. / T
+    agent = DDPG(input_dims=dims, hidden=256, layers=3, network_class='baselines.her.actor_critic:MultiTaskActorCritic',
+                 polyak=0.95, batch_size=BATCH, Q_lr=0.001, pi_lr=0.001, norm_eps=0.01, norm_clip=5, max_u=1.,
+                 action_l2=1.0, clip_obs=200., scope='ddpg', T=T, rollout_batch_size=2,
+                 subtract_goals=lambda a, b: a - b, relative_goals=False, clip_pos_returns=True,
+                 clip_return=1. / (1. - gamma), normalize_obs=False, sample_transitions=sampler, gamma=gamma,
+                 buffers=buffers, tasks_ag_id=ag_ids, tasks_g_id=g_ids, task_replay='replay_task_cp_buffer',
+                 eps_task=EPS_TASK, structure='curious', her_rng='philox', seed=0, device=device)
+    agent.cp = np.array(CP)
+    return agent, sampler, buffers, dims, ag_ids, g_ids
+
+
+def her_step_segments(buffers, rows):
+    from curious_b200 import apportion
+    sizes = [b.current_size for b in buffers]
+    prop = apportion.proportions_curious(sizes, T, rows, 'replay_task_cp_buffer', np.array(CP), EPS_TASK)
+    return [(buffers[i].device_view(), int(prop[i]), i - 1) for i in range(1, len(buffers)) if prop[i] > 0]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) - used by cpu_baseline and by --impl reference
+# ------------------------------------------------------------------------------------------------
+def build_cpu_workload(seed, episodes_per_buffer):
+    from curious_b200 import synth
+    from oracle import ddpg_oracle, her_oracle, replay_oracle
+    from oracle.reward_oracle import ModuleDistanceReward
+    dims, ag_ids, g_ids = synth_dims()
+    sampler = her_oracle.make_sample_multi_task_her_transitions('her', 4, 'replay_task_cp_buffer',
+                                                                ModuleDistanceReward(ag_ids, g_ids),
+                                                                tasks_ag_id=ag_ids, tasks_g_id=g_ids)
+    shapes = synth.buffer_shapes(dims, T)
+    buffers = [replay_oracle.ReplayBufferOracle(shapes, (episodes_per_buffer if i > 0 else 1) * T, T, sampler)
+               for i in range(N_MODULES + 1)]
+    rng = np.random.RandomState(seed)
+    for i in range(1, N_MODULES + 1):
+        for e0 in range(0, episodes_per_buffer, 2000):
+            n = min(2000, episodes_per_buffer - e0)
+            buffers[i].store_episode(synth.make_episodes(rng, n, T, dims))
+    gamma = 1. - 1. / T
+    agent = ddpg_oracle.DDPGOracle(
+        input_dims=dims, hidden=256, layers=3, polyak=0.95, batch_size=BATCH, Q_lr=0.001, pi_lr=0.001, norm_eps=0.01,
+        norm_clip=5, max_u=1., action_l2=1.0, clip_obs=200., T=T, rollout_batch_size=2, relative_goals=False,
+        clip_pos_returns=True, clip_return=1. / (1. - gamma), normalize_obs=False, sample_transitions=sampler,
+        gamma=gamma, buffers=buffers, structure='curious', tasks_ag_id=ag_ids, tasks_g_id=g_ids,
+        task_replay='replay_task_cp_buffer', eps_task=EPS_TASK, weights_rng=np.random.RandomState(0))
+    agent.cp = np.array(CP)
+    return agent, dims
+
+
+def cpu_sampler_baseline(seconds=12.0):
+    """The oracle's DDPG.sample_batch (apportion + per-buffer HER sampler + concat + shuffle + preprocess) on one
+    core, full-size buffers: transitions/s.  kind = 'port' (restatement of her.py / replay_buffer.py / ddpg.py)."""
+    import contextlib
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=1)
+    except Exception:
+        ctx = contextlib.nullcontext()
+    with ctx:
+        agent, _ = build_cpu_workload(0, BUFFER_TRANSITIONS // T)
+        np.random.seed(0)
+        for _ in range(20):
+            agent.sample_batch()
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            agent.sample_batch()
+            n += 1
+        dt = time.perf_counter() - t0
+    return {'value': n * BATCH / dt, 'unit': 'transitions/s', 'cores': 1, 'kind': 'port',
+            'sample': '%d sample_batch calls x %d rows on 4 x 1e6-transition float64 buffers, 1 thread '
+                      '(oracle port of her.py/replay_buffer.py/ddpg.py sample_batch)' % (n, BATCH)}
+
+
+def _ref_worker(rank, n_steps, n_warm, updates, episodes_per_buffer, q):
+    os.environ['OMP_NUM_THREADS'] = '1'
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
+    agent, dims = build_cpu_workload(rank, episodes_per_buffer)
+    from curious_b200 import synth
+    rng = np.random.RandomState(1000 + rank)
+    np.random.seed(1000000 * rank)
+    q.put(('ready', rank))
+    times = []
+    for s in range(n_warm + n_steps):
+        ep = synth.make_episodes(rng, 2, T, dims, change_dtype=bool)
+        t0 = time.perf_counter()
+        agent.store_episode(ep, np.array(CP), 2 * (s + 1))
+        for _ in range(updates):
+            agent.train()
+        agent.update_target_net()
+        times.append(time.perf_counter() - t0)
+    q.put(('done', rank, times[n_warm:]))
+
+
+def run_reference_arm(args):
+    """The training cycle of the reference restated on the CPU (oracle port), one single-threaded process per
+    worker like the reference's `mpirun -np 19 --bind-to core` (train.py:221-231); no all-reduce is modelled, so
+    this over-estimates the CPU arm.  Each step is a bounded sample of the cycle: REF_UPDATES_PER_STEP updates."""
+    import multiprocessing as mp
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(19, cores))
+    episodes = BUFFER_TRANSITIONS // T
+    # bound memory: each worker owns 4 float64 buffers of 0.69 GB
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        procs = max(1, min(procs, int(avail * 0.6 // (4 * 0.7e9))))
+    except Exception:
+        pass
+    ctx = mp.get_context('fork')
+    q = ctx.Queue()
+    workers = [ctx.Process(target=_ref_worker, args=(r, args.steps, args.warmup, REF_UPDATES_PER_STEP, episodes, q))
+               for r in range(procs)]
+    for w in workers:
+        w.start()
+    done = {}
+    while len(done) < procs:
+        msg = q.get()
+        if msg[0] == 'done':
+            done[msg[1]] = msg[2]
+    for w in workers:
+        w.join()
+    per_step = np.max(np.array([done[r] for r in range(procs)]), axis=0)      # slowest worker per step
+    total = float(per_step.sum())
+    value = procs * REF_UPDATES_PER_STEP * BATCH * args.steps / total
+    dims, _, _ = synth_dims()
+    line = {
+        'impl': 'reference', 'metric': 'HER-relabelled transitions/s', 'value': value, 'unit': 'transitions/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'arm4-shaped: 4 module buffers x 1e6 transitions (T=50, dimo=40, dimg=12, dimu=4, N=4), '
+                               'batch 256, replay_task_cp_buffer; CPU arm = training cycle store_episode + %d x train + '
+                               'update_target_net per step' % REF_UPDATES_PER_STEP},
+        'cpu_baseline': {'value': value, 'unit': 'transitions/s', 'cores': procs, 'kind': 'port',
+                         'sample': '%d single-threaded worker processes x %d steps x %d updates of batch %d (oracle '
+                                   'NumPy port of her.py/replay_buffer.py/ddpg.py/mpi_adam.py; TF1 graph restated in '
+                                   'float32 NumPy/BLAS)' % (procs, args.steps, REF_UPDATES_PER_STEP, BATCH)},
+        'e2e': {'value': value, 'unit': 'transitions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'updates_per_s': procs * REF_UPDATES_PER_STEP * args.steps / total,
+        'host_cores': cores,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    from curious_b200 import _lib
+    _lib.load()
+    agent, sampler, buffers, dims, ag_ids, g_ids = build_gpu_workload(device, seed=1 + rank)
+    segs = her_step_segments(buffers, ROWS_PER_STEP)
+    want = ('o', 'g', 'u', 'td', 'o_2', 'r')
+    out = {}
+
+    def her_step():
+        return sampler.sample_device(segs, ROWS_PER_STEP, clip_obs=200.0, want=want, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        her_step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        her_step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    # ---- DDPG updates/s: device-timed train() (sample + grads + all-reduce + Adam) through the public API
+    for _ in range(5):
+        agent.train()
+    barrier()
+    n_upd = 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_upd):
+        agent.train()
+    e1.record()
+    barrier()
+    upd_ms = e0.elapsed_time(e1)
+    # ---- e2e: training cycles through the plugin API with host episode buffers
+    from curious_b200 import synth
+    rng = np.random.RandomState(99 + rank)
+    host_eps = [synth.make_episodes(rng, 2, T, dims, change_dtype=bool) for _ in range(8)]
+    h2d = sum(np.asarray(v).size * 4 for v in host_eps[0].values())
+
+    def cycle(i):
+        agent.store_episode({k: v for k, v in host_eps[i % len(host_eps)].items()}, np.array(CP), 2 * (i + 1))
+        losses = [agent.train()[0] for _ in range(N_BATCHES_E2E)]
+        agent.update_target_net()
+        return torch.stack([l.tensor for l in losses]).cpu().numpy()          # device->host read of the results
+
+    for i in range(3):
+        cycle(i)
+    barrier()
+    n_cyc = 10
+    t0 = time.perf_counter()
+    for i in range(n_cyc):
+        res = cycle(3 + i)
+    barrier()
+    cyc_s = time.perf_counter() - t0
+    clock_info = clocks.stop()
+    if world > 1:
+        tt = torch.tensor([ms, upd_ms, cyc_s], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, upd_ms, cyc_s = [float(x) for x in tt.cpu()]
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        bpt = algorithmic_bytes_per_transition(dims, N_MODULES)
+        kernel_ms = ms / args.steps                       # one step == one launch of the fused kernel
+        achieved = bpt * ROWS_PER_STEP / (kernel_ms * 1e-3) / 1e9
+        line = {
+            'metric': 'HER-relabelled transitions/s', 'value': world * ROWS_PER_STEP * args.steps / (ms * 1e-3),
+            'unit': 'transitions/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': kernel_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'arm4-shaped: 4 module buffers x 1e6 transitions (T=50, dimo=40, dimg=12, dimu=4, '
+                                   'N=4), LP-apportioned (replay_task_cp_buffer, cp=%s), %d rows per fused launch '
+                                   '(= %d batches of 256), Philox draws' % (CP, ROWS_PER_STEP, ROWS_PER_STEP // BATCH),
+                       'l2': 'inputs (1.44 GB of replay rows per rank) and outputs (0.42 GB) exceed the 126 MB L2',
+                       'rows_per_step': ROWS_PER_STEP, 'batch': BATCH},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_transition': bpt,
+                         'kernel': 'her_sample_kernel'},
+            'e2e': {'value': world * n_cyc * N_BATCHES_E2E * BATCH / cyc_s, 'unit': 'transitions/s',
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(res.nbytes),
+                    'what': 'DDPG.store_episode(host) + %d x DDPG.train() + update_target_net + loss readback per cycle'
+                            % N_BATCHES_E2E, 'cycle_ms': 1e3 * cyc_s / n_cyc,
+                    'updates_per_s': world * n_cyc * N_BATCHES_E2E / cyc_s},
+            'gpu_launches': args.steps,
+            'clocks': clock_info,
+            'updates_per_s': world * n_upd / (upd_ms * 1e-3),
+            'update_us': 1e3 * upd_ms / n_upd,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_sampler_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,522 @@
+// DDPG / UVFA actor-critic: forward, losses, backward into a flat GetFlat-ordered gradient (sm_100a).
+//
+// Replaces (reference flowersteam/curious):
+//   baselines/her/util.py:56-107           nn / nn_modular_her
+//   baselines/her/actor_critic.py:5-98     ActorCritic / MultiTaskActorCritic
+//   baselines/her/ddpg.py:412-449          losses + tf.gradients + flatten_grads
+//   baselines/her/ddpg.py:129-146          get_actions forward
+//
+// Schedule: the DDPG graph is cut into dependency levels; each level is ONE grouped-GEMM launch
+// (mlp_kernels.cuh) covering all independent nets of that level:
+//   fwd-1 : main.pi | target.pi | main.Q(o,g,u)        (L layers + output layer)
+//   fwd-2 : main.Q(o,g,pi) | target.Q(o2,g2,pi_t)      (L layers + output layer)
+//   loss  : target = clip(r + gamma*Q_t), Q_loss, pi_loss, dQ, dQ_pi
+//   bwd-1 : critic chain (dX + [dW;db]) | actor-through-Q chain (dX only)
+//   bwd-2 : actor chain (dX + [dW;db])
+// [dW;db] blocks are written straight into the flat gradient vector in GetFlat order, because
+// kernel [in,out] followed by bias [out] is exactly one contiguous (in+1) x out matrix there.
+#include <string.h>
+
+#include "mlp_kernels.cuh"
+
+namespace cur {
+
+struct NetLayout {
+  int modular, in_s, in_g, H, L, out;
+  int64_t off_W0, off_b0, off_W0g;
+  int64_t off_W[CUR_MAX_LAYERS], off_b[CUR_MAX_LAYERS];   // hidden layers 1..L-1
+  int64_t off_Wout, off_bout, total;
+};
+
+static NetLayout net_layout(const cur_net_desc& d, int which /*0 Q, 1 pi*/) {
+  NetLayout n;
+  n.modular = d.modular;
+  n.H = d.hidden;
+  n.L = d.layers;
+  const int act_in = (which == 0) ? d.dimu : 0;
+  if (d.modular) {
+    n.in_s = d.dimo + d.dimtd + act_in;
+    n.in_g = d.dimg;
+  } else {
+    n.in_s = d.dimo + d.dimg + act_in;
+    n.in_g = 0;
+  }
+  n.out = (which == 0) ? 1 : d.dimu;
+  int64_t o = 0;
+  n.off_W0 = o; o += (int64_t)n.in_s * n.H;
+  n.off_b0 = o; o += n.H;
+  n.off_W0g = o; o += (int64_t)n.in_g * n.H;
+  for (int l = 1; l < n.L; ++l) {
+    n.off_W[l] = o; o += (int64_t)n.H * n.H;
+    n.off_b[l] = o; o += n.H;
+  }
+  n.off_Wout = o; o += (int64_t)n.H * n.out;
+  n.off_bout = o; o += n.out;
+  n.total = o;
+  return n;
+}
+
+static inline int64_t r4(int64_t x) { return (x + 3) & ~(int64_t)3; }
+
+// Workspace carve-up (floats).  All leading dimensions are multiples of 4.
+struct Workspace {
+  int ld_spi, ld_sq, ld_g, H;
+  float *Xpi, *Xg, *XQu, *XQpi, *Xpi_t, *Xg_t, *XQ_t;
+  float *hp[CUR_MAX_LAYERS], *hq[CUR_MAX_LAYERS], *hqp[CUR_MAX_LAYERS], *ht[CUR_MAX_LAYERS], *htq[CUR_MAX_LAYERS];
+  float *Q, *Qt, *dQ, *dQpi, *dy;
+  float *dc[2], *da[2], *dp[2];
+  int64_t total;
+};
+
+static Workspace carve(const cur_net_desc& d, int64_t n, float* base) {
+  Workspace w;
+  const NetLayout q = net_layout(d, 0), p = net_layout(d, 1);
+  w.ld_spi = (int)r4(p.in_s);
+  w.ld_sq = (int)r4(q.in_s);
+  w.ld_g = (int)r4(d.modular ? d.dimg : 0);
+  w.H = d.hidden;
+  int64_t o = 0;
+  auto take = [&](int64_t floats) {
+    float* ptr = base ? base + o : nullptr;
+    o += r4(floats);
+    return ptr;
+  };
+  w.Xpi = take(n * w.ld_spi);
+  w.Xg = take(n * w.ld_g);
+  w.XQu = take(n * w.ld_sq);
+  w.XQpi = take(n * w.ld_sq);
+  w.Xpi_t = take(n * w.ld_spi);
+  w.Xg_t = take(n * w.ld_g);
+  w.XQ_t = take(n * w.ld_sq);
+  for (int l = 0; l < d.layers; ++l) {
+    w.hp[l] = take(n * w.H);
+    w.hq[l] = take(n * w.H);
+    w.hqp[l] = take(n * w.H);
+    w.ht[l] = take(n * w.H);
+    w.htq[l] = take(n * w.H);
+  }
+  w.Q = take(n);
+  w.Qt = take(n);
+  w.dQ = take(n);
+  w.dQpi = take(n);
+  w.dy = take(n * r4(d.dimu));
+  for (int i = 0; i < 2; ++i) {
+    w.dc[i] = take(n * w.H);
+    w.da[i] = take(n * w.H);
+    w.dp[i] = take(n * w.H);
+  }
+  w.total = o;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: build the first-layer input matrices (normalise/clip o,g; append task_descr and action)
+// ------------------------------------------------------------------------------------------------
+struct PrepParams {
+  cur_net_desc d;
+  const float *o, *g, *u, *td, *o_2, *g_2;
+  const float *ag;           // actions path only: relative goals g <- g - ag (ddpg.py:119-124)
+  float clip_obs;            // actions path only: clip o,g to +-clip_obs first (ddpg.py:125-126); <=0: off
+  const float *o_mean, *o_std, *g_mean, *g_std;
+  int64_t n;
+  int ld_spi, ld_sq, ld_g;
+  float *Xpi, *Xg, *XQu, *XQpi, *Xpi_t, *Xg_t, *XQ_t;   // any may be NULL
+};
+
+__device__ __forceinline__ float norm1(float x, const float* mean, const float* std, int k, float clip) {
+  float v = __fdiv_rn(__fsub_rn(x, mean[k]), std[k]);          // normalizer.py:72-77
+  return fminf(fmaxf(v, -clip), clip);
+}
+
+__global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepParams P) {
+  const cur_net_desc& d = P.d;
+  const int in_o = d.dimo;
+  const int in_spi = d.modular ? d.dimo + d.dimtd : d.dimo + d.dimg;
+  const int width = in_spi + d.dimu;   // columns of the widest matrix (XQ*)
+  const int64_t total = P.n * width;
+  const bool nrm = d.normalize_obs != 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / width;
+    const int k = (int)(i - r * width);
+    float v = 0.f, v2 = 0.f;   // main-side / target-side value of column k
+    if (k < in_o) {
+      v = P.o[r * d.dimo + k];
+      if (P.clip_obs > 0.f) v = fminf(fmaxf(v, -P.clip_obs), P.clip_obs);
+      if (nrm) v = norm1(v, P.o_mean, P.o_std, k, d.norm_clip);
+      if (P.o_2) {
+        v2 = P.o_2[r * d.dimo + k];
+        if (nrm) v2 = norm1(v2, P.o_mean, P.o_std, k, d.norm_clip);
+      }
+    } else if (k < in_spi) {
+      const int j = k - in_o;
+      if (d.modular) {
+        v = P.td[r * d.dimtd + j];      // task descriptor is never normalised (actor_critic.py:79,88)
+        v2 = v;
+      } else {
+        v = P.g[r * d.dimg + j];
+        if (P.ag) v = __fsub_rn(v, P.ag[r * d.dimg + j]);
+        if (P.clip_obs > 0.f) v = fminf(fmaxf(v, -P.clip_obs), P.clip_obs);
+        if (nrm) v = norm1(v, P.g_mean, P.g_std, j, d.norm_clip);
+        if (P.g_2) {
+          v2 = P.g_2[r * d.dimg + j];
+          if (nrm) v2 = norm1(v2, P.g_mean, P.g_std, j, d.norm_clip);
+        }
+      }
+    } else {
+      const int j = k - in_spi;
+      if (P.u && P.XQu) P.XQu[r * P.ld_sq + k] = __fdiv_rn(P.u[r * d.dimu + j], d.max_u);   // u / max_u
+      continue;
+    }
+    if (P.Xpi) P.Xpi[r * P.ld_spi + k] = v;
+    if (P.XQu) P.XQu[r * P.ld_sq + k] = v;
+    if (P.XQpi) P.XQpi[r * P.ld_sq + k] = v;
+    if (P.Xpi_t) P.Xpi_t[r * P.ld_spi + k] = v2;
+    if (P.XQ_t) P.XQ_t[r * P.ld_sq + k] = v2;
+  }
+  if (d.modular) {
+    const int64_t totg = P.n * d.dimg;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < totg;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / d.dimg;
+      const int j = (int)(i - r * d.dimg);
+      float v = P.g[i];
+      if (P.ag) v = __fsub_rn(v, P.ag[i]);
+      if (P.clip_obs > 0.f) v = fminf(fmaxf(v, -P.clip_obs), P.clip_obs);
+      if (nrm) v = norm1(v, P.g_mean, P.g_std, j, d.norm_clip);
+      if (P.Xg) P.Xg[r * P.ld_g + j] = v;
+      if (P.g_2 && P.Xg_t) {
+        float v2 = P.g_2[i];
+        if (nrm) v2 = norm1(v2, P.g_mean, P.g_std, j, d.norm_clip);
+        P.Xg_t[r * P.ld_g + j] = v2;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses (ddpg.py:436-441) + the two seeds of the backward pass.  One CTA.
+// ------------------------------------------------------------------------------------------------
+struct LossParams {
+  const float *r, *Q, *Qpi, *Qt, *th;
+  int ldth, dimu;
+  int64_t n;
+  float gamma, clip_return, action_l2;
+  int clip_pos;
+  float *dQ, *dQpi, *q_loss, *pi_loss;
+};
+
+__global__ void __launch_bounds__(1024) loss_kernel(const __grid_constant__ LossParams P) {
+  __shared__ float red[3][32];
+  float ssq = 0.f, sq = 0.f, sth = 0.f;
+  const float inv_n = 1.0f / (float)P.n;
+  const float hi = P.clip_pos ? 0.f : INFINITY;
+  for (int64_t i = threadIdx.x; i < P.n; i += blockDim.x) {
+    float tgt = fminf(fmaxf(P.r[i] + P.gamma * P.Qt[i], -P.clip_return), hi);   // ddpg.py:436-438
+    float diff = tgt - P.Q[i];
+    ssq += diff * diff;
+    sq += P.Qpi[i];
+    P.dQ[i] = -2.0f * inv_n * diff;      // d mean((tgt - Q)^2) / dQ
+    P.dQpi[i] = -inv_n;                  // d (-mean(Q_pi)) / dQ_pi
+  }
+  for (int64_t i = threadIdx.x; i < P.n * P.dimu; i += blockDim.x) {
+    int64_t r = i / P.dimu;
+    float t = P.th[r * P.ldth + (i - r * P.dimu)];
+    sth += t * t;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    sth += __shfl_xor_sync(0xffffffffu, sth, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = ssq; red[1][w] = sq; red[2][w] = sth; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    ssq = l < nw ? red[0][l] : 0.f;
+    sq = l < nw ? red[1][l] : 0.f;
+    sth = l < nw ? red[2][l] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) {
+      ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      sth += __shfl_xor_sync(0xffffffffu, sth, o);
+    }
+    if (l == 0) {
+      if (P.q_loss) *P.q_loss = ssq * inv_n;                                           // ddpg.py:439
+      if (P.pi_loss) *P.pi_loss = -sq * inv_n + P.action_l2 * sth / (float)(P.n * P.dimu);   // :440-441
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// problem builders
+// ------------------------------------------------------------------------------------------------
+static GemmProb zero_prob() {
+  GemmProb p;
+  memset(&p, 0, sizeof(p));
+  p.scale2 = 1.f;
+  return p;
+}
+
+// forward layer 0
+static GemmProb fwd0(const NetLayout& L, const float* th, const float* Xs, int ld_s, const float* Xg, int ld_g,
+                     float* out, int64_t n) {
+  GemmProb p = zero_prob();
+  p.A = Xs; p.lda = ld_s; p.B = th + L.off_W0; p.ldb = L.H; p.K = L.in_s;
+  if (L.in_g > 0) { p.A2 = Xg; p.lda2 = ld_g; p.B2 = th + L.off_W0g; p.ldb2 = L.H; p.K2 = L.in_g; }
+  p.bias = th + L.off_b0;
+  p.C = out; p.ldc = L.H; p.M = (int)n; p.N = L.H; p.epi = EPI_RELU;
+  return p;
+}
+static GemmProb fwdl(const NetLayout& L, const float* th, int l, const float* in, float* out, int64_t n) {
+  GemmProb p = zero_prob();
+  p.A = in; p.lda = L.H; p.B = th + L.off_W[l]; p.ldb = L.H; p.K = L.H;
+  p.bias = th + L.off_b[l];
+  p.C = out; p.ldc = L.H; p.M = (int)n; p.N = L.H; p.epi = EPI_RELU;
+  return p;
+}
+static GemmProb fwdout(const NetLayout& L, const float* th, const float* in, float* out, int ldc, int epi, int64_t n) {
+  GemmProb p = zero_prob();
+  p.A = in; p.lda = L.H; p.B = th + L.off_Wout; p.ldb = L.out; p.K = L.H;
+  p.bias = th + L.off_bout;
+  p.C = out; p.ldc = ldc; p.M = (int)n; p.N = L.out; p.epi = epi;
+  return p;
+}
+// dX = dY * W^T, gated by the sign of the activation feeding W
+static GemmProb bwd_dx(const float* dY, int lddy, const float* W, int n_in, int n_out, const float* act, int ldact,
+                       float* dX, int lddx, int64_t n) {
+  GemmProb p = zero_prob();
+  p.A = dY; p.lda = lddy; p.B = W; p.ldb = n_out; p.b_trans = 1; p.K = n_out;
+  p.C = dX; p.ldc = lddx; p.M = (int)n; p.N = n_in;
+  p.epi = act ? EPI_RELU_MASK : EPI_NONE; p.aux = act; p.ldaux = ldact;
+  return p;
+}
+// [dW;db] = [X|1]^T * dY  -> (n_in + 1) x n_out block of the flat gradient
+static GemmProb bwd_dw(const float* X, int ldx, int n_in, const float* dY, int lddy, int n_out, float* dWb,
+                       int with_bias, int64_t n) {
+  GemmProb p = zero_prob();
+  p.A = X; p.lda = ldx; p.a_trans = 1; p.a_ones = with_bias; p.K = (int)n;
+  p.B = dY; p.ldb = lddy;
+  p.C = dWb; p.ldc = n_out; p.M = n_in + (with_bias ? 1 : 0); p.N = n_out;
+  return p;
+}
+
+struct Batcher {
+  GemmBatch G;
+  cudaStream_t s;
+  explicit Batcher(cudaStream_t st) : s(st) { G.n = 0; G.total_tiles = 0; }
+  void add(const GemmProb& p) { G.p[G.n++] = p; }
+  int flush() {
+    int rc = launch_gemm_batch(G, s);
+    G.n = 0;
+    return rc;
+  }
+};
+
+#define CUR_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != CUR_OK) return _rc; \
+  } while (0)
+
+static int check_desc(const cur_net_desc* d) {
+  CUR_REQUIRE(d != nullptr, "net desc is NULL");
+  CUR_REQUIRE(d->dimo > 0 && d->dimg > 0 && d->dimu > 0, "bad input dims");
+  CUR_REQUIRE(d->hidden > 0 && (d->hidden % 4) == 0, "hidden must be a positive multiple of 4");
+  CUR_REQUIRE(d->layers >= 1 && d->layers <= CUR_MAX_LAYERS, "layers out of range");
+  CUR_REQUIRE(!d->modular || d->dimtd > 0, "modular net needs dimtd > 0");
+  CUR_REQUIRE(d->max_u > 0.f, "max_u must be > 0");
+  return CUR_OK;
+}
+
+static int grid_prep(int64_t work) {
+  int64_t b = (work + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 4;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace cur
+
+using namespace cur;
+
+extern "C" int64_t cur_net_param_count(const cur_net_desc* d, int which) {
+  if (check_desc(d) != CUR_OK || (which != 0 && which != 1)) return -1;
+  return net_layout(*d, which).total;
+}
+
+extern "C" int64_t cur_theta_pi_offset(const cur_net_desc* d, int64_t* total) {
+  if (check_desc(d) != CUR_OK) return -1;
+  const int64_t off = r4(net_layout(*d, 0).total);
+  if (total) *total = off + r4(net_layout(*d, 1).total);
+  return off;
+}
+
+extern "C" int64_t cur_ddpg_workspace_floats(const cur_net_desc* d, int64_t batch) {
+  if (check_desc(d) != CUR_OK || batch <= 0) return -1;
+  return carve(*d, batch, nullptr).total;
+}
+
+extern "C" int cur_ddpg_actions(void* stream, const cur_net_desc* d, const float* theta,
+                                const cur_norm_stats* stats, const float* o, const float* ag, const float* g,
+                                const float* td, int64_t n, float clip_obs, float* workspace, float* out_pi,
+                                float* out_q) {
+  CUR_TRY(check_desc(d));
+  CUR_REQUIRE(theta && o && g && workspace && out_pi, "NULL argument");
+  CUR_REQUIRE(!d->modular || td, "task_descr required for a modular net");
+  CUR_REQUIRE(n > 0 && n < (1 << 30), "bad batch");
+  if (d->normalize_obs)
+    CUR_REQUIRE(stats && stats->o_mean && stats->o_std && stats->g_mean && stats->g_std, "normalizer stats required");
+  cudaStream_t s = (cudaStream_t)stream;
+  const NetLayout LQ = net_layout(*d, 0), LP = net_layout(*d, 1);
+  const float* thQ = theta;
+  const float* thP = theta + r4(LQ.total);
+  Workspace w = carve(*d, n, workspace);
+
+  PrepParams P;
+  memset(&P, 0, sizeof(P));
+  P.d = *d; P.o = o; P.g = g; P.td = td; P.n = n;
+  P.ag = ag; P.clip_obs = clip_obs;
+  if (stats) { P.o_mean = stats->o_mean; P.o_std = stats->o_std; P.g_mean = stats->g_mean; P.g_std = stats->g_std; }
+  P.ld_spi = w.ld_spi; P.ld_sq = w.ld_sq; P.ld_g = w.ld_g;
+  P.Xpi = w.Xpi; P.Xg = w.Xg; P.XQpi = out_q ? w.XQpi : nullptr;
+  prep_kernel<<<grid_prep(n * (LQ.in_s)), 256, 0, s>>>(P);
+  CUR_CHECK_LAUNCH();
+
+  Batcher B(s);
+  B.add(fwd0(LP, thP, w.Xpi, w.ld_spi, w.Xg, w.ld_g, w.hp[0], n));
+  CUR_TRY(B.flush());
+  for (int l = 1; l < LP.L; ++l) {
+    B.add(fwdl(LP, thP, l, w.hp[l - 1], w.hp[l], n));
+    CUR_TRY(B.flush());
+  }
+  {
+    // th = tanh(.) goes into the action columns of the critic input; pi = max_u * th to the caller
+    GemmProb p = fwdout(LP, thP, w.hp[LP.L - 1], w.XQpi + LP.in_s, w.ld_sq, EPI_TANH, n);
+    p.C2 = out_pi; p.ldc2 = d->dimu; p.scale2 = d->max_u;
+    B.add(p);
+    CUR_TRY(B.flush());
+  }
+  if (out_q) {
+    B.add(fwd0(LQ, thQ, w.XQpi, w.ld_sq, w.Xg, w.ld_g, w.hqp[0], n));
+    CUR_TRY(B.flush());
+    for (int l = 1; l < LQ.L; ++l) {
+      B.add(fwdl(LQ, thQ, l, w.hqp[l - 1], w.hqp[l], n));
+      CUR_TRY(B.flush());
+    }
+    B.add(fwdout(LQ, thQ, w.hqp[LQ.L - 1], out_q, 1, EPI_NONE, n));
+    CUR_TRY(B.flush());
+  }
+  return CUR_OK;
+}
+
+extern "C" int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* theta_main,
+                              const float* theta_target, const cur_norm_stats* stats, const cur_batch* batch,
+                              const cur_ddpg_hyper* h, float* workspace, float* grads, float* q_loss,
+                              float* pi_loss, float* q_pi) {
+  CUR_TRY(check_desc(d));
+  CUR_REQUIRE(theta_main && theta_target && batch && h && workspace && grads && q_pi, "NULL argument");
+  CUR_REQUIRE(batch->o && batch->g && batch->u && batch->o_2 && batch->g_2 && batch->r, "NULL batch array");
+  CUR_REQUIRE(!d->modular || batch->td, "task_descr required for a modular net");
+  CUR_REQUIRE(batch->n > 0 && batch->n < (1 << 30), "bad batch");
+  if (d->normalize_obs)
+    CUR_REQUIRE(stats && stats->o_mean && stats->o_std && stats->g_mean && stats->g_std, "normalizer stats required");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = batch->n;
+  const NetLayout LQ = net_layout(*d, 0), LP = net_layout(*d, 1);
+  const int64_t offP = r4(LQ.total);
+  const float *mQ = theta_main, *mP = theta_main + offP, *tQ = theta_target, *tP = theta_target + offP;
+  float *gQ = grads, *gP = grads + offP;
+  Workspace w = carve(*d, n, workspace);
+  const int L = d->layers, H = d->hidden;
+
+  // ---- inputs
+  PrepParams P;
+  memset(&P, 0, sizeof(P));
+  P.d = *d; P.o = batch->o; P.g = batch->g; P.u = batch->u; P.td = batch->td; P.o_2 = batch->o_2; P.g_2 = batch->g_2;
+  P.n = n;
+  if (stats) { P.o_mean = stats->o_mean; P.o_std = stats->o_std; P.g_mean = stats->g_mean; P.g_std = stats->g_std; }
+  P.ld_spi = w.ld_spi; P.ld_sq = w.ld_sq; P.ld_g = w.ld_g;
+  P.Xpi = w.Xpi; P.Xg = w.Xg; P.XQu = w.XQu; P.XQpi = w.XQpi; P.Xpi_t = w.Xpi_t; P.Xg_t = w.Xg_t; P.XQ_t = w.XQ_t;
+  prep_kernel<<<grid_prep(n * LQ.in_s), 256, 0, s>>>(P);
+  CUR_CHECK_LAUNCH();
+
+  Batcher B(s);
+  // ---- fwd-1: main.pi | target.pi | main.Q(o,g,u)
+  B.add(fwd0(LP, mP, w.Xpi, w.ld_spi, w.Xg, w.ld_g, w.hp[0], n));
+  B.add(fwd0(LP, tP, w.Xpi_t, w.ld_spi, w.Xg_t, w.ld_g, w.ht[0], n));
+  B.add(fwd0(LQ, mQ, w.XQu, w.ld_sq, w.Xg, w.ld_g, w.hq[0], n));
+  CUR_TRY(B.flush());
+  for (int l = 1; l < L; ++l) {
+    B.add(fwdl(LP, mP, l, w.hp[l - 1], w.hp[l], n));
+    B.add(fwdl(LP, tP, l, w.ht[l - 1], w.ht[l], n));
+    B.add(fwdl(LQ, mQ, l, w.hq[l - 1], w.hq[l], n));
+    CUR_TRY(B.flush());
+  }
+  float* th = w.XQpi + LP.in_s;   // tanh output lives in the action columns of main.Q's input
+  B.add(fwdout(LP, mP, w.hp[L - 1], th, w.ld_sq, EPI_TANH, n));
+  B.add(fwdout(LP, tP, w.ht[L - 1], w.XQ_t + LP.in_s, w.ld_sq, EPI_TANH, n));
+  B.add(fwdout(LQ, mQ, w.hq[L - 1], w.Q, 1, EPI_NONE, n));
+  CUR_TRY(B.flush());
+  // ---- fwd-2: main.Q(o,g,pi) | target.Q(o2,g2,pi_t)   (same u and td for the target, ddpg.py:427-431)
+  B.add(fwd0(LQ, mQ, w.XQpi, w.ld_sq, w.Xg, w.ld_g, w.hqp[0], n));
+  B.add(fwd0(LQ, tQ, w.XQ_t, w.ld_sq, w.Xg_t, w.ld_g, w.htq[0], n));
+  CUR_TRY(B.flush());
+  for (int l = 1; l < L; ++l) {
+    B.add(fwdl(LQ, mQ, l, w.hqp[l - 1], w.hqp[l], n));
+    B.add(fwdl(LQ, tQ, l, w.htq[l - 1], w.htq[l], n));
+    CUR_TRY(B.flush());
+  }
+  B.add(fwdout(LQ, mQ, w.hqp[L - 1], q_pi, 1, EPI_NONE, n));
+  B.add(fwdout(LQ, tQ, w.htq[L - 1], w.Qt, 1, EPI_NONE, n));
+  CUR_TRY(B.flush());
+
+  // ---- losses and backward seeds
+  LossParams LPm;
+  LPm.r = batch->r; LPm.Q = w.Q; LPm.Qpi = q_pi; LPm.Qt = w.Qt; LPm.th = th; LPm.ldth = w.ld_sq; LPm.dimu = d->dimu;
+  LPm.n = n; LPm.gamma = h->gamma; LPm.clip_return = h->clip_return; LPm.action_l2 = h->action_l2;
+  LPm.clip_pos = h->clip_pos_returns; LPm.dQ = w.dQ; LPm.dQpi = w.dQpi; LPm.q_loss = q_loss; LPm.pi_loss = pi_loss;
+  loss_kernel<<<1, 1024, 0, s>>>(LPm);
+  CUR_CHECK_LAUNCH();
+
+  // ---- bwd-1: critic chain (weights grads of main/Q) | actor-through-Q chain (data grads only)
+  int cur = 0;
+  B.add(bwd_dx(w.dQ, 1, mQ + LQ.off_Wout, H, 1, w.hq[L - 1], H, w.dc[0], H, n));
+  B.add(bwd_dw(w.hq[L - 1], H, H, w.dQ, 1, 1, gQ + LQ.off_Wout, 1, n));
+  B.add(bwd_dx(w.dQpi, 1, mQ + LQ.off_Wout, H, 1, w.hqp[L - 1], H, w.da[0], H, n));
+  CUR_TRY(B.flush());
+  for (int l = L - 1; l >= 1; --l) {
+    B.add(bwd_dx(w.dc[cur], H, mQ + LQ.off_W[l], H, H, w.hq[l - 1], H, w.dc[cur ^ 1], H, n));
+    B.add(bwd_dw(w.hq[l - 1], H, H, w.dc[cur], H, H, gQ + LQ.off_W[l], 1, n));
+    B.add(bwd_dx(w.da[cur], H, mQ + LQ.off_W[l], H, H, w.hqp[l - 1], H, w.da[cur ^ 1], H, n));
+    CUR_TRY(B.flush());
+    cur ^= 1;
+  }
+  B.add(bwd_dw(w.XQu, w.ld_sq, LQ.in_s, w.dc[cur], H, H, gQ + LQ.off_W0, 1, n));
+  if (LQ.in_g > 0) B.add(bwd_dw(w.Xg, w.ld_g, LQ.in_g, w.dc[cur], H, H, gQ + LQ.off_W0g, 0, n));
+  {
+    // d pi_loss / d(pre-tanh) = (dL/d(pi/max_u) + action_l2 * 2/(B*dimu) * th) * (1 - th^2)
+    GemmProb p = bwd_dx(w.da[cur], H, mQ + LQ.off_W0 + (int64_t)LP.in_s * H, d->dimu, H, nullptr, 0, w.dy,
+                        (int)r4(d->dimu), n);
+    p.epi = EPI_ACTOR_DY; p.aux = th; p.ldaux = w.ld_sq;
+    p.coef = h->action_l2 * 2.0f / (float)(n * d->dimu);
+    B.add(p);
+  }
+  CUR_TRY(B.flush());
+  // ---- bwd-2: actor chain (weight grads of main/pi)
+  const int lddy = (int)r4(d->dimu);
+  cur = 0;
+  B.add(bwd_dx(w.dy, lddy, mP + LP.off_Wout, H, d->dimu, w.hp[L - 1], H, w.dp[0], H, n));
+  B.add(bwd_dw(w.hp[L - 1], H, H, w.dy, lddy, d->dimu, gP + LP.off_Wout, 1, n));
+  CUR_TRY(B.flush());
+  for (int l = L - 1; l >= 1; --l) {
+    B.add(bwd_dx(w.dp[cur], H, mP + LP.off_W[l], H, H, w.hp[l - 1], H, w.dp[cur ^ 1], H, n));
+    B.add(bwd_dw(w.hp[l - 1], H, H, w.dp[cur], H, H, gP + LP.off_W[l], 1, n));
+    CUR_TRY(B.flush());
+    cur ^= 1;
+  }
+  B.add(bwd_dw(w.Xpi, w.ld_spi, LP.in_s, w.dp[cur], H, H, gP + LP.off_W0, 1, n));
+  if (LP.in_g > 0) B.add(bwd_dw(w.Xg, w.ld_g, LP.in_g, w.dp[cur], H, H, gP + LP.off_W0g, 0, n));
+  CUR_TRY(B.flush());
+  return CUR_OK;
+}

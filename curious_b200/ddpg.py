@@ -1,0 +1,467 @@
+"""DDPG + HER agent on one B200 per rank - drop-in for reference baselines/her/ddpg.py:18-537.
+
+Same constructor arguments, same methods (get_actions / store_episode / sample_batch / stage_batch /
+train / update_target_net / get_current_buffer_size / clear_buffer / logs / save_weights / load_weights /
+pickling).  What moved to the device:
+  sample_batch      one fused kernel over all LP-apportioned module buffers     (csrc/her.cu)
+  _grads            grouped-GEMM forward/backward into a flat gradient          (csrc/ddpg.cu)
+  _update           NCCL all-reduce(SUM) + fused Adam on the flat arena         (csrc/norm_adam.cu)
+  update_target_net fused polyak on the flat arena
+  o_stats/g_stats   device normalisers, one packed all-reduce per store_episode
+Host keeps: the LP apportioning arithmetic (<= 9 integers, ddpg.py:255-286), buffer slot choice and
+the exploration noise of get_actions - they consume the caller's np.random stream in reference order.
+
+Extra keyword arguments (all optional): device, comm (torch.distributed group; default WORLD when
+initialised), her_rng ('philox' default | 'numpy' = replay the reference's np.random draws),
+seed (Xavier init seed; the reference uses TF's graph seed).
+"""
+import ctypes as C
+import pickle
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib, apportion
+from .her import HostDraws
+from .mpi_adam import MpiAdam, adam_step_scale
+from .normalizer import Normalizer, _world
+from .replay_buffer import StagedEpisodes, episodes_to_device
+from .util import LazyHost, dims_to_shapes, import_function, store_args, transitions_in_episode_batch
+
+
+class DDPG(object):
+    @store_args
+    def __init__(self, input_dims, hidden, layers, network_class, polyak, batch_size,
+                 Q_lr, pi_lr, norm_eps, norm_clip, max_u, action_l2, clip_obs, scope, T,
+                 rollout_batch_size, subtract_goals, relative_goals, clip_pos_returns, clip_return,
+                 normalize_obs, sample_transitions, gamma, buffers=None, reuse=False, tasks_ag_id=None,
+                 tasks_g_id=None, task_replay='', t_id=None, eps_task=None, **kwargs):
+        """See reference ddpg.py:25-60 for the meaning of every argument."""
+        if self.clip_return is None:
+            self.clip_return = np.inf
+        self.structure = kwargs.get('structure', getattr(self, 'structure', 'curious'))
+        self.device = kwargs.get('device') or torch.device('cuda', torch.cuda.current_device())
+        self.comm = kwargs.get('comm')
+        self.her_rng = kwargs.get('her_rng', 'philox')
+        self.seed = kwargs.get('seed', 0)
+        self.create_actor_critic = import_function(self.network_class)
+
+        self.dimo = self.input_dims['o']
+        self.dimg = self.input_dims['g']
+        self.dimag = self.input_dims['ag']
+        self.dimu = self.input_dims['u']
+        self.modular = self.structure in ('curious', 'task_experts')
+        if self.modular:
+            self.dimtd = self.input_dims['task_descr']
+        else:
+            self.dimtd = 0
+
+        # staged batch layout (ddpg.py:73-83)
+        input_shapes = dims_to_shapes(self.input_dims)
+        stage_shapes = OrderedDict()
+        for key in sorted(self.input_dims.keys()):
+            if key.startswith('info_'):
+                continue
+            stage_shapes[key] = (None, *input_shapes[key])
+        for key in ['o', 'g']:
+            stage_shapes[key + '_2'] = stage_shapes[key]
+        stage_shapes['r'] = (None, 1)
+        self.stage_shapes = stage_shapes
+
+        if t_id is not None:
+            self.scope += str(t_id)
+
+        if self.modular:
+            self.nb_tasks = len(tasks_g_id)
+        if buffers is not None:
+            self.buffer = buffers
+            if type(self.buffer) is list and len(self.buffer) > 5:
+                for i in range(6, len(self.buffer)):        # distractor buffers are one buffer (ddpg.py:104-110)
+                    self.buffer[i] = self.buffer[5]
+        self._create_network(reuse=reuse)
+        self.first = True
+        self.cp = None
+        self._staged = None
+
+    # ------------------------------------------------------------------------------------------
+    def _create_network(self, reuse=False):
+        dev = self.device
+        self.net = self.create_actor_critic(dimo=self.dimo, dimg=self.dimg, dimu=self.dimu, dimtd=self.dimtd,
+                                            max_u=self.max_u, hidden=self.hidden, layers=self.layers,
+                                            normalize_obs=self.normalize_obs, norm_clip=self.norm_clip)
+        if self.net.modular != self.modular:
+            raise ValueError('network_class %s does not fit structure %r' % (self.network_class, self.structure))
+        net = self.net
+        # running averages (ddpg.py:402-409)
+        self.o_stats = Normalizer(self.dimo, self.norm_eps, self.norm_clip, device=dev, comm=self.comm)
+        self.g_stats = Normalizer(self.dimg, self.norm_eps, self.norm_clip, device=dev, comm=self.comm)
+        self._stats = _lib.NormStats(self.o_stats.mean.data_ptr(), self.o_stats.std.data_ptr(),
+                                     self.g_stats.mean.data_ptr(), self.g_stats.std.data_ptr())
+        # flat arenas: [Q | pad | pi | pad]
+        self.theta_main = torch.zeros(net.arena, dtype=torch.float32, device=dev)
+        self.theta_target = torch.zeros(net.arena, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(net.arena, dtype=torch.float32, device=dev)
+        self._init_weights()
+        # optimisers (ddpg.py:451-453): separate Adam state and step counters for Q and pi
+        self.Q_adam = MpiAdam([self._view(self.theta_main, 'Q')], scale_grad_by_procs=False, comm=self.comm)
+        self.pi_adam = MpiAdam([self._view(self.theta_main, 'pi')], scale_grad_by_procs=False, comm=self.comm)
+        self._hyper = _lib.DdpgHyper(float(self.gamma), float(min(self.clip_return, 3.0e38)), float(self.action_l2),
+                                     1 if self.clip_pos_returns else 0)
+        self._ws = {}
+        self._sync_optimizers()
+        self._init_target_net()
+        self._q_loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._pi_loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._batch = None
+
+    def _view(self, arena, which):
+        net = self.net
+        return arena[:net.n_Q] if which == 'Q' else arena[net.pi_offset:net.pi_offset + net.n_pi]
+
+    def _init_weights(self):
+        """tf.contrib.layers.xavier_initializer() (uniform) kernels, zero biases (util.py:63), drawn on the
+        host in flat order main/Q then main/pi and uploaded."""
+        rng = np.random.RandomState(self.seed)
+        for which in ('Q', 'pi'):
+            chunks = []
+            for s in self.net.var_shapes(which):
+                if len(s) == 2:
+                    lim = np.sqrt(6.0 / (s[0] + s[1]))
+                    chunks.append(rng.uniform(-lim, lim, s).astype(np.float32).reshape(-1))
+                else:
+                    chunks.append(np.zeros(s, np.float32))
+            self.set_flat(which, np.concatenate(chunks))
+
+    # flat parameter access in GetFlat order (tf_util.py:221-244)
+    def get_flat(self, which, target=False):
+        return self._view(self.theta_target if target else self.theta_main, which).detach().cpu().numpy().copy()
+
+    def set_flat(self, which, values, target=False):
+        v = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float32))
+        self._view(self.theta_target if target else self.theta_main, which).copy_(v.to(self.device))
+
+    def _workspace(self, n):
+        if n not in self._ws:
+            floats = _lib.load().cur_ddpg_workspace_floats(C.byref(self.net.desc), n)
+            self._ws[n] = torch.empty(floats, dtype=torch.float32, device=self.device)
+        return self._ws[n]
+
+    # ------------------------------------------------------------------------------------------
+    def _random_action(self, n):
+        return np.random.uniform(low=-self.max_u, high=self.max_u, size=(n, self.dimu))
+
+    def _preprocess_og(self, o, ag, g):
+        """Host version kept for API parity (ddpg.py:118-127); the device paths fuse it into their kernels."""
+        if self.relative_goals:
+            g_shape = g.shape
+            g = g.reshape(-1, self.dimg)
+            ag = ag.reshape(-1, self.dimag)
+            g = self.subtract_goals(g, ag)
+            g = g.reshape(*g_shape)
+        o = np.clip(o, -self.clip_obs, self.clip_obs)
+        g = np.clip(g, -self.clip_obs, self.clip_obs)
+        return o, g
+
+    def get_actions(self, o, ag, g, task_descr=None, noise_eps=0., random_eps=0., use_target_net=False,
+                    compute_Q=False):
+        """ddpg.py:129-161.  One H2D blob, prep + MLP kernels, one D2H; exploration noise on the host RNG."""
+        o = np.asarray(o, np.float32).reshape(-1, self.dimo)
+        g = np.asarray(g, np.float32).reshape(-1, self.dimg)
+        n = o.shape[0]
+        parts = [o, g]
+        if self.relative_goals:
+            parts.append(np.asarray(ag, np.float32).reshape(-1, self.dimag))
+        if self.modular:
+            parts.append(np.asarray(task_descr, np.float32).reshape(-1, self.dimtd))
+        sizes = [p.size for p in parts]
+        host = torch.empty(sum(sizes), dtype=torch.float32, pin_memory=True)
+        hv = host.numpy()
+        k = 0
+        for p, s in zip(parts, sizes):
+            hv[k:k + s] = p.reshape(-1)
+            k += s
+        dev = host.to(self.device, non_blocking=True)
+        base, k = dev.data_ptr(), 0
+        ptrs = []
+        for s in sizes:
+            ptrs.append(base + 4 * k)
+            k += s
+        p_o, p_g = ptrs[0], ptrs[1]
+        idx = 2
+        p_ag = None
+        if self.relative_goals:
+            p_ag = ptrs[idx]
+            idx += 1
+        p_td = ptrs[idx] if self.modular else None
+        out = torch.empty(n * (self.dimu + 1), dtype=torch.float32, device=self.device)
+        theta = self.theta_target if use_target_net else self.theta_main
+        _lib.check(_lib.load().cur_ddpg_actions(
+            _lib.stream_ptr(), C.byref(self.net.desc), theta.data_ptr(), C.byref(self._stats), p_o, p_ag, p_g, p_td, n,
+            float(self.clip_obs), self._workspace(n).data_ptr(), out.data_ptr(),
+            out.data_ptr() + 4 * n * self.dimu if compute_Q else None), 'cur_ddpg_actions')
+        res = out.cpu().numpy()
+        ret = [res[:n * self.dimu].reshape(n, self.dimu).copy()]
+        if compute_Q:
+            ret.append(res[n * self.dimu:].reshape(n, 1).copy())
+        # action postprocessing (ddpg.py:147-155), host RNG in reference order
+        u = ret[0]
+        noise = noise_eps * self.max_u * np.random.randn(*u.shape)
+        u += noise
+        u = np.clip(u, -self.max_u, self.max_u)
+        u += np.random.binomial(1, random_eps, u.shape[0]).reshape(-1, 1) * (self._random_action(u.shape[0]) - u)
+        if u.shape[0] == 1:
+            u = u[0]
+        u = u.copy()
+        ret[0] = u
+        if len(ret) == 1:
+            return ret[0]
+        return ret
+
+    # ------------------------------------------------------------------------------------------
+    def _multi_buffer(self):
+        return 'buffer' in self.task_replay or self.task_replay == 'hand_designed'
+
+    def store_episode(self, episode_batch, cp, n_ep, update_stats=True):
+        """episode_batch: {key: [rollout_batch_size, T or T+1, dim]} (ddpg.py:163-223)."""
+        batch_size = episode_batch['ag'].shape[0]
+        self.cp = cp
+        self.n_episodes = n_ep
+        some_buffer = self.buffer[1] if type(self.buffer) is list else self.buffer
+        keys = list(some_buffer.buffer_shapes.keys())
+        staged = StagedEpisodes({k: episode_batch[k] for k in keys}, some_buffer.layout, some_buffer.info_keys,
+                                some_buffer.has_td, some_buffer.has_change, self.device)
+        copies = []
+        if self.modular:
+            change = np.asarray(episode_batch['change'])
+            for b in range(batch_size):
+                active_tasks = apportion.active_modules(change[b, -1], self.tasks_ag_id, self.tasks_g_id)
+                # (the reference all-reduces an unused counter here, ddpg.py:185 - dropped)
+                if self._multi_buffer():
+                    for task in active_tasks:                        # buffer[0] is never written (ddpg.py:191-195)
+                        copies.append(self.buffer[task + 1].store_staged(staged, b))
+                else:
+                    copies.append(self.buffer.store_staged(staged, b))
+        else:
+            for b in range(batch_size):
+                copies.append(self.buffer.store_staged(staged, b))
+        staged.store(copies)
+        self._staged = staged
+
+        if update_stats:
+            # HER-sample rollout_batch_size*T transitions of the fresh episodes and feed the preprocessed
+            # o,g to the normalisers (ddpg.py:206-223)
+            episode_batch['o_2'] = episode_batch['o'][:, 1:, :]
+            episode_batch['ag_2'] = episode_batch['ag'][:, 1:, :]
+            num = transitions_in_episode_batch(episode_batch)
+            epi = episodes_to_device({k: episode_batch[k] for k in keys}, self.device)
+            sampler = self.sample_transitions
+            draws = None
+            if self.her_rng == 'numpy':
+                d = HostDraws(epi.n_episodes, epi.layout.T, num)
+                d.draw_choices(sampler.mode, sampler.future_p, getattr(self, 'nb_tasks', 0), None)
+                draws = [d]
+            res = sampler.sample_device([(epi, num, None)], num, draws=draws, clip_obs=self.clip_obs,
+                                        relative_goals=self.relative_goals, want=('o', 'g'))
+            self.o_stats.update(res['o'])
+            self.g_stats.update(res['g'])
+            self.o_stats.recompute_stats()
+            self.g_stats.recompute_stats()
+
+    def get_current_buffer_size(self):
+        return sum([self.buffer[i].get_current_size() for i in range(self.nb_tasks)])
+
+    def _sync_optimizers(self):
+        self.Q_adam.sync()
+        self.pi_adam.sync()
+
+    # ------------------------------------------------------------------------------------------
+    def _proportions(self):
+        """LP-weighted apportioning of the batch over the module buffers (ddpg.py:255-286, 302-318)."""
+        sizes = [self.buffer[i].current_size for i in range(self.nb_tasks + 1)]
+        if self.structure == 'curious':
+            prop = apportion.proportions_curious(sizes, self.T, self.batch_size, self.task_replay, self.cp,
+                                                 self.eps_task)
+        else:
+            prop = apportion.proportions_task_expert(sizes, self.T, self.batch_size, self.t_id)
+        self.proportions = prop
+        return prop
+
+    def _sample_device(self, want, rng=None):
+        """Run the fused HER kernel for one batch; returns {key: float32 cuda tensor}."""
+        rng = rng or self.her_rng
+        sampler = self.sample_transitions
+        B = self.batch_size
+        cp_proba = None
+        perm = None
+        if self.modular and self._multi_buffer() and (
+                self.structure == 'curious' or self.task_replay == 'replay_current_task_buffer'):
+            prop = self._proportions()
+            segs = []
+            for i in range(self.nb_tasks + 1):
+                if prop[i] > 0:
+                    if self.structure == 'curious':
+                        ttr = i - 1 if i > 0 else None
+                    else:
+                        ttr = self.t_id
+                    assert self.buffer[i].current_size > 0
+                    segs.append((self.buffer[i].device_view(), int(prop[i]), ttr))
+            shuffle = True
+        else:
+            buf = self.buffer
+            assert buf.current_size > 0
+            if self.modular and self.structure == 'curious' and self.task_replay == 'replay_cp_task_transition':
+                cp_proba = apportion.cp_probabilities(self.cp, self.eps_task)       # ddpg.py:288-296
+            segs = [(buf.device_view(), B, None)]
+            shuffle = False
+        draws = None
+        if rng == 'numpy':
+            draws = []
+            for epi, count, ttr in segs:      # one sampler call per non-empty buffer, in buffer order
+                d = HostDraws(epi.n_episodes, epi.layout.T, count)
+                d.draw_choices(sampler.mode, sampler.future_p, getattr(self, 'nb_tasks', 0), cp_proba)
+                draws.append(d)
+            if shuffle:
+                perm = np.arange(B)
+                np.random.shuffle(perm)                                   # ddpg.py:338-339
+                self._last_perm = perm
+        return sampler.sample_device(segs, B, cp_proba=cp_proba, draws=draws, perm=perm, clip_obs=self.clip_obs,
+                                     relative_goals=self.relative_goals, want=want)
+
+    _STAGE_TO_KERNEL = {'ag': 'ag', 'g': 'g', 'o': 'o', 'task_descr': 'td', 'u': 'u', 'o_2': 'o_2', 'g_2': 'g_2',
+                        'r': 'r'}
+
+    def sample_batch(self):
+        """Returns the staged batch as a list of host arrays in stage_shapes order (ddpg.py:251-360)."""
+        want = tuple(self._STAGE_TO_KERNEL[k] for k in self.stage_shapes.keys())
+        res = self._sample_device(want)
+        torch.cuda.current_stream().synchronize()
+        return [res[self._STAGE_TO_KERNEL[k]].cpu().numpy().astype(np.float64) for k in self.stage_shapes.keys()]
+
+    def stage_batch(self, batch=None):
+        """ddpg.py:362-366.  With batch=None the batch is sampled on the device and never leaves it."""
+        if batch is None:
+            want = ('o', 'g', 'u', 'td', 'o_2', 'g_2', 'r') if self.modular else ('o', 'g', 'u', 'o_2', 'g_2', 'r')
+            self._batch = self._sample_device(want)
+            return
+        assert len(self.stage_shapes) == len(batch)
+        dev = {}
+        for key, arr in zip(self.stage_shapes.keys(), batch):
+            dev[self._STAGE_TO_KERNEL[key]] = torch.from_numpy(
+                np.ascontiguousarray(arr, dtype=np.float32)).to(self.device, non_blocking=True)
+        self._batch = dev
+
+    def _grads(self):
+        b = self._batch
+        n = b['o'].shape[0]
+        cb = _lib.Batch(b['o'].data_ptr(), b['g'].data_ptr(), b['u'].data_ptr(),
+                        b['td'].data_ptr() if self.modular else None, b['o_2'].data_ptr(), b['g_2'].data_ptr(),
+                        b['r'].data_ptr(), n)
+        q_pi = torch.empty((n, 1), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.load().cur_ddpg_grads(
+            _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
+            C.byref(self._stats), C.byref(cb), C.byref(self._hyper), self._workspace(n).data_ptr(),
+            self.grads.data_ptr(), self._q_loss.data_ptr(), self._pi_loss.data_ptr(), q_pi.data_ptr()),
+            'cur_ddpg_grads')
+        return self._q_loss, q_pi, self._view(self.grads, 'Q'), self._view(self.grads, 'pi')
+
+    def _update(self, Q_grad, pi_grad):
+        """Q_adam.update + pi_adam.update (ddpg.py:246-248).  Both vectors live in one arena, so the two
+        MPI all-reduces of the reference become ONE NCCL all-reduce, and when both nets share the step
+        size one fused Adam launch covers the arena."""
+        group, world = _world(self.comm)
+        if self.Q_adam.t % 100 == 0:
+            self.Q_adam.check_synced()
+            self.pi_adam.check_synced()
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)       # SUM, not mean (ddpg.py:452-453)
+        self.Q_adam.t += 1
+        self.pi_adam.t += 1
+        lib = _lib.load()
+        for adam, grad, lr in ((self.Q_adam, Q_grad, self.Q_lr), (self.pi_adam, pi_grad, self.pi_lr)):
+            a = adam_step_scale(lr, adam.beta1, adam.beta2, adam.t)
+            _lib.check(lib.cur_adam_step(_lib.stream_ptr(), adam.theta.data_ptr(), grad.data_ptr(),
+                                         adam.m.data_ptr(), adam.v.data_ptr(), adam.theta.numel(),
+                                         float(np.float32(-a)), adam.beta1, adam.beta2, adam.epsilon, 1.0),
+                       'cur_adam_step')
+
+    def train(self, stage=True):
+        if stage:
+            self.stage_batch()
+        critic_loss, actor_loss, Q_grad, pi_grad = self._grads()
+        self._update(Q_grad, pi_grad)
+        # like the reference, "actor_loss" is main.Q_pi, the whole [B,1] array (ddpg.py:237-243)
+        return LazyHost(critic_loss.clone().reshape(())), LazyHost(actor_loss)
+
+    def _init_target_net(self):
+        _lib.check(_lib.load().cur_polyak(_lib.stream_ptr(), self.theta_target.data_ptr(), self.theta_main.data_ptr(),
+                                          self.theta_main.numel(), 0.0), 'cur_polyak')
+
+    def update_target_net(self):
+        _lib.check(_lib.load().cur_polyak(_lib.stream_ptr(), self.theta_target.data_ptr(), self.theta_main.data_ptr(),
+                                          self.theta_main.numel(), float(self.polyak)), 'cur_polyak')
+
+    def clear_buffer(self):
+        for i in range(self.nb_tasks):
+            self.buffer[i].clear_buffer()
+
+    # ------------------------------------------------------------------------------------------
+    def logs(self, prefix=''):
+        logs = []
+        logs += [('stats_o/mean', float(self.o_stats.mean.mean().item()))]
+        logs += [('stats_o/std', float(self.o_stats.std.mean().item()))]
+        logs += [('stats_g/mean', float(self.g_stats.mean.mean().item()))]
+        logs += [('stats_g/std', float(self.g_stats.std.mean().item()))]
+        if prefix != '' and not prefix.endswith('/'):
+            return [(prefix + '/' + key, val) for key, val in logs]
+        return logs
+
+    def _vars_list(self, which, target=False):
+        flat = self.get_flat(which, target)
+        out, k = [], 0
+        for s in self.net.var_shapes(which):
+            n = int(np.prod(s))
+            out.append(flat[k:k + n].reshape(s).copy())
+            k += n
+        return out
+
+    def save_weights(self, path):
+        """<path>_weights.pkl = [main/Q, main/pi, target/Q, target/pi, o_stats, g_stats] as lists of arrays
+        (ddpg.py:481-497) - the reference's on-disk format."""
+        to_save = [self._vars_list('Q'), self._vars_list('pi'), self._vars_list('Q', True),
+                   self._vars_list('pi', True), self.o_stats.state_list(), self.g_stats.state_list()]
+        with open(path + '_weights.pkl', 'wb') as f:
+            pickle.dump(to_save, f)
+
+    def load_weights(self, path):
+        with open(path + '_weights.pkl', 'rb') as f:
+            weights = pickle.load(f)
+        for i, (which, target) in enumerate((('Q', False), ('pi', False), ('Q', True), ('pi', True))):
+            self.set_flat(which, np.concatenate([np.asarray(v, np.float32).reshape(-1) for v in weights[i]]), target)
+        self.o_stats.load_state_list(weights[4])
+        self.g_stats.load_state_list(weights[5])
+
+    def __getstate__(self):
+        """Policies can be pickled for playing; training state (Adam, buffers) is not saved (ddpg.py:511-521)."""
+        excluded_subnames = ['_tf', '_op', '_vars', '_adam', 'buffer', 'sess', '_stats', 'main', 'target', 'lock',
+                             'env', 'sample_transitions', 'stage_shapes', 'create_actor_critic', 'theta_', 'grads',
+                             '_ws', '_batch', '_staged', 'net', 'device', 'comm', '_hyper', '_q_loss', '_pi_loss',
+                             'kwargs']
+        state = {k: v for k, v in self.__dict__.items() if all([subname not in k for subname in excluded_subnames])}
+        state['weights'] = [self.get_flat('Q'), self.get_flat('pi'), self.get_flat('Q', True), self.get_flat('pi', True),
+                            self.o_stats.state_list(), self.g_stats.state_list()]
+        return state
+
+    def __setstate__(self, state):
+        if 'sample_transitions' not in state:
+            state['sample_transitions'] = None      # not needed for playing the policy
+        weights = state.pop('weights')
+        extra = {k: state.pop(k) for k in list(state.keys())
+                 if k not in DDPG.__init__.__wrapped__.__code__.co_varnames and k not in ('structure', 'her_rng', 'seed')}
+        self.__init__(**state)
+        self.__dict__.update(extra)
+        for i, (which, target) in enumerate((('Q', False), ('pi', False), ('Q', True), ('pi', True))):
+            self.set_flat(which, weights[i], target)
+        self.o_stats.load_state_list(weights[4])
+        self.g_stats.load_state_list(weights[5])

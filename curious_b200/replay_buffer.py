@@ -1,0 +1,248 @@
+"""Device-resident replay buffer - drop-in for reference baselines/her/replay_buffer.py:6-109.
+
+Storage is ONE float32 CUDA tensor of packed per-timestep rows (layout in include/curious_b200.h,
+`cur_layout`) instead of the reference's dict of float64 host arrays (replay_buffer.py:23-24).
+Everything the reference stores is float32-representable (rollout.py:50-52,194-195 build float32
+episodes; `change` is bool), so no information is lost; inputs that are not are rounded to float32.
+
+Slot selection (_get_storage_idx, replay_buffer.py:90-109) stays on the host and consumes the global
+np.random stream exactly like the reference, so a seeded run overwrites the same slots.
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from .her import DeviceEpisodes
+
+BASE_KEYS = ('o', 'ag', 'g', 'u')
+
+
+def split_keys(shapes_or_batch):
+    """Classify keys: returns (has_td, has_change, [(info_key, dim), ...] sorted)."""
+    keys = list(shapes_or_batch.keys())
+    info = sorted(k for k in keys if k.startswith('info_'))
+    known = set(BASE_KEYS) | {'task_descr', 'change', 'o_2', 'ag_2'} | set(info)
+    extra = [k for k in keys if k not in known]
+    if extra:
+        raise KeyError('unsupported replay keys: %s' % extra)
+    for k in BASE_KEYS:
+        if k not in shapes_or_batch:
+            raise KeyError('replay key %r is required' % k)
+    return 'task_descr' in shapes_or_batch, 'change' in shapes_or_batch, info
+
+
+def layout_from_shapes(buffer_shapes):
+    """buffer_shapes: {key: (T or T+1, dim)} as built by config.configure_buffer (config.py:200-208)."""
+    has_td, has_change, info = split_keys(buffer_shapes)
+    T = buffer_shapes['u'][0]
+    assert buffer_shapes['o'][0] == T + 1 and buffer_shapes['ag'][0] == T + 1
+    info_keys = [(k, int(buffer_shapes[k][-1])) for k in info]
+    L = _lib.make_layout(T, buffer_shapes['o'][-1], buffer_shapes['ag'][-1], buffer_shapes['g'][-1],
+                         buffer_shapes['u'][-1], buffer_shapes['task_descr'][-1] if has_td else 0,
+                         buffer_shapes['change'][-1] if has_change else 0, sum(d for _, d in info_keys))
+    return L, info_keys, has_td, has_change
+
+
+class StagedEpisodes:
+    """Key-major float32 episodes uploaded to the device in one blob (input of cur_store_episodes)."""
+
+    def __init__(self, episode_batch, layout, info_keys, has_td, has_change, device):
+        self.layout = layout
+        n = len(episode_batch['u'])
+        self.n = n
+        T = layout.T
+        parts = [('o', (T + 1) * layout.dimo), ('ag', (T + 1) * layout.dimag), ('g', T * layout.dimg),
+                 ('u', T * layout.dimu)]
+        if has_td:
+            parts.append(('task_descr', T * layout.dimtd))
+        if has_change:
+            parts.append(('change', T * layout.dimchange))
+        total = sum(sz for _, sz in parts) * n + n * T * layout.diminfo
+        host = torch.empty(total, dtype=torch.float32, pin_memory=True)
+        h = host.numpy()
+        offs, k0 = {}, 0
+        for key, sz in parts:
+            arr = np.asarray(episode_batch[key])
+            assert arr.shape[0] == n and arr[0].size == sz, 'bad shape for %s: %s' % (key, arr.shape)
+            h[k0:k0 + n * sz] = arr.reshape(-1)          # casts bool / float64 to float32
+            offs[key] = k0
+            k0 += n * sz
+        if info_keys:
+            info = np.concatenate([np.asarray(episode_batch[k], np.float32).reshape(n, T, d)
+                                   for k, d in info_keys], axis=2)
+            h[k0:k0 + info.size] = info.reshape(-1)
+            offs['info'] = k0
+            k0 += info.size
+        self.blob = host.to(device, non_blocking=True)
+        self._host = host
+        base = self.blob.data_ptr()
+        self.src = _lib.EpisodeSrc()
+        self.src.o = base + 4 * offs['o']
+        self.src.ag = base + 4 * offs['ag']
+        self.src.g = base + 4 * offs['g']
+        self.src.u = base + 4 * offs['u']
+        self.src.td = base + 4 * offs['task_descr'] if has_td else None
+        self.src.change = base + 4 * offs['change'] if has_change else None
+        self.src.info = base + 4 * offs['info'] if info_keys else None
+
+    @classmethod
+    def from_device(cls, tensors, layout):
+        """Episodes that already live on the device as key-major float32 tensors
+        {o, ag, g, u[, task_descr, change, info]} (synthetic fills, device-side env stepping)."""
+        self = cls.__new__(cls)
+        self.layout = layout
+        self.n = tensors['u'].shape[0]
+        self._keep = tensors
+        self.src = _lib.EpisodeSrc()
+        for key, field in (('o', 'o'), ('ag', 'ag'), ('g', 'g'), ('u', 'u'), ('task_descr', 'td'),
+                           ('change', 'change'), ('info', 'info')):
+            t = tensors.get(key)
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+            setattr(self.src, field, None if t is None else t.data_ptr())
+        return self
+
+    def store(self, copies, stream=None):
+        """copies: list of (src_episode, storage_tensor, slot)."""
+        n = len(copies)
+        if n == 0:
+            return
+        src = (C.c_int32 * n)(*[int(c[0]) for c in copies])
+        base = (C.c_void_p * n)(*[c[1].data_ptr() for c in copies])
+        slot = (C.c_int64 * n)(*[int(c[2]) for c in copies])
+        _lib.check(_lib.load().cur_store_episodes(_lib.stream_ptr(stream), C.byref(self.layout),
+                                                  C.byref(self.src), self.n, n, src, base, slot),
+                   'cur_store_episodes')
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise _lib.CuriousLibError('curious_b200 needs a CUDA device (no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def episodes_to_device(episode_batch, device=None):
+    """Pack a host episode batch {key: [n, T(+1), dim]} into a temporary device buffer and return the
+    DeviceEpisodes view the sampler consumes (used for the normaliser path, ddpg.py:209-215)."""
+    device = device or default_device()
+    shapes = {k: np.asarray(v).shape[1:] for k, v in episode_batch.items() if k not in ('o_2', 'ag_2')}
+    L, info_keys, has_td, has_change = layout_from_shapes(shapes)
+    n = len(episode_batch['u'])
+    storage = torch.empty(n * (L.T + 1) * L.row_stride, dtype=torch.float32, device=device)
+    staged = StagedEpisodes({k: v for k, v in episode_batch.items() if k not in ('o_2', 'ag_2')},
+                            L, info_keys, has_td, has_change, device)
+    staged.store([(e, storage, e) for e in range(n)])
+    epi = DeviceEpisodes(storage, n, L, info_keys, has_td, has_change)
+    epi._staged = staged
+    return epi
+
+
+class ReplayBuffer:
+    def __init__(self, buffer_shapes, size_in_transitions, T, sample_transitions, device=None):
+        """Same arguments as the reference (replay_buffer.py:7-16) + optional `device`."""
+        self.buffer_shapes = buffer_shapes
+        self.size = size_in_transitions // T                     # replay_buffer.py:18
+        self.T = T
+        self.sample_transitions = sample_transitions
+        self.device = device or default_device()
+        self.layout, self.info_keys, self.has_td, self.has_change = layout_from_shapes(buffer_shapes)
+        assert self.layout.T == T
+        self.storage = torch.empty(self.size * (T + 1) * self.layout.row_stride, dtype=torch.float32,
+                                   device=self.device)
+        self.current_size = 0
+        self.n_transitions_stored = 0
+        self.lock = threading.Lock()
+
+    @property
+    def full(self):
+        with self.lock:
+            return self.current_size == self.size
+
+    def device_view(self):
+        return DeviceEpisodes(self.storage, self.current_size, self.layout, self.info_keys, self.has_td,
+                              self.has_change)
+
+    def sample(self, batch_size, task_to_replay=None, cp_proba=None):
+        """Returns a dict {key: array(batch_size x shapes[key])} (replay_buffer.py:37-55)."""
+        with self.lock:
+            assert self.current_size > 0
+            view = self.device_view()
+        transitions = self.sample_transitions(view, batch_size, task_to_replay=task_to_replay,
+                                              cp_proba=cp_proba)
+        for key in (['r', 'o_2', 'ag_2'] + list(self.buffer_shapes.keys())):
+            assert key in transitions, "key %s missing from transitions" % key
+        return transitions
+
+    def store_episode(self, episode_batch):
+        """episode_batch: array(batch_size x (T or T+1) x dim_key) (replay_buffer.py:57-72)."""
+        batch_sizes = [len(episode_batch[key]) for key in episode_batch.keys()]
+        assert np.all(np.array(batch_sizes) == batch_sizes[0])
+        batch_size = batch_sizes[0]
+        with self.lock:
+            idxs = np.atleast_1d(self._get_storage_idx(batch_size))
+            staged = StagedEpisodes({k: episode_batch[k] for k in self.buffer_shapes.keys()}, self.layout,
+                                    self.info_keys, self.has_td, self.has_change, self.device)
+            staged.store([(e, self.storage, int(idxs[e])) for e in range(batch_size)])
+            self._last_staged = staged       # keep the pinned/device blobs alive until the copy ran
+            self.n_transitions_stored += batch_size * self.T
+
+    def store_staged(self, staged, src_episode):
+        """Store episode `src_episode` of an already uploaded batch (DDPG.store_episode duplicates one
+        episode into several module buffers, ddpg.py:194-195, with a single upload)."""
+        with self.lock:
+            idx = self._get_storage_idx(1)
+            self.n_transitions_stored += self.T
+        return (src_episode, self.storage, int(idx))
+
+    def get_current_episode_size(self):
+        with self.lock:
+            return self.current_size
+
+    def get_current_size(self):
+        with self.lock:
+            return self.current_size * self.T
+
+    def get_transitions_stored(self):
+        with self.lock:
+            return self.n_transitions_stored
+
+    def clear_buffer(self):
+        with self.lock:
+            self.current_size = 0
+
+    def _get_storage_idx(self, inc=None):
+        inc = inc or 1   # size increment
+        assert inc <= self.size, "Batch committed to replay is too large!"
+        # consecutive until the end is hit, then uniformly random slots (replay_buffer.py:94-102)
+        if self.current_size + inc <= self.size:
+            idx = np.arange(self.current_size, self.current_size + inc)
+        elif self.current_size < self.size:
+            overflow = inc - (self.size - self.current_size)
+            idx = np.concatenate([np.arange(self.current_size, self.size),
+                                  np.random.randint(0, self.current_size, overflow)])
+        else:
+            idx = np.random.randint(0, self.size, inc)
+        self.current_size = min(self.size, self.current_size + inc)
+        if inc == 1:
+            idx = idx[0]
+        return idx
+
+    @property
+    def buffers(self):
+        """Host copy in the reference's layout {key: float64 [size, T(+1), dim]} (debug / export only)."""
+        L, T = self.layout, self.T
+        rows = self.storage.view(self.size, T + 1, L.row_stride).cpu().numpy().astype(np.float64)
+        out = {'o': rows[:, :, L.off_o:L.off_o + L.dimo], 'ag': rows[:, :, L.off_ag:L.off_ag + L.dimag],
+               'g': rows[:, :T, L.off_g:L.off_g + L.dimg], 'u': rows[:, :T, L.off_u:L.off_u + L.dimu]}
+        if self.has_td:
+            out['task_descr'] = rows[:, :T, L.off_td:L.off_td + L.dimtd]
+        if self.has_change:
+            out['change'] = rows[:, :T, L.off_change:L.off_change + L.dimchange]
+        k0 = L.off_info
+        for key, d in self.info_keys:
+            out[key] = rows[:, :T, k0:k0 + d]
+            k0 += d
+        return out

@@ -48,7 +48,7 @@ def make_episodes(rng, n_ep, T, dims, walk_sigma=0.02, goal_span=0.15, still_pro
     `still_prob` of (episode, module) pairs does not move at all so that the
     `change`-mask routing of store_episode (reference ddpg.py:181) sees inactive modules.
     """
-    N = dims['task_descr']
+    N = dims.get('task_descr', 0)
     dimo, dimu, dimg, dimag = dims['o'], dims['u'], dims['g'], dims['ag']
     o = np.clip(rng.standard_normal((n_ep, T + 1, dimo)), -5, 5).astype(np.float32)
     ag0 = rng.uniform(-goal_span, goal_span, (n_ep, 1, dimag))

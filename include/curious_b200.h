@@ -1,0 +1,247 @@
+/*
+ * curious_b200 C ABI - the drop-in boundary of the B200-native CURIOUS training hot path.
+ *
+ * The reference (flowersteam/curious) has no FFI: its hot path is Python/NumPy/TF1 behind the
+ * duck-typed plugin surface wired by baselines/her/experiment/config.py:152-253.  This header is
+ * the C-ABI a maintainer binds (ctypes stub in INTEGRATION.md) so that surface runs on one B200 per
+ * rank.  Every entry point:
+ *   - is `extern "C"`, takes plain pointers / sizes / a `cudaStream_t` passed as `void*`;
+ *   - returns an int status (CUR_OK == 0); never throws; never allocates persistent memory;
+ *   - works on DEVICE pointers unless the parameter is documented as host;
+ *   - is asynchronous on `stream`.
+ * Each declaration cites the reference code it replaces (paths relative to the reference root).
+ */
+#ifndef CURIOUS_B200_H
+#define CURIOUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUR_ABI_VERSION 1
+
+#define CUR_OK 0
+#define CUR_ERR_INVALID 1   /* bad argument (dims, null pointer, table overflow)   */
+#define CUR_ERR_CUDA 2      /* a CUDA runtime call failed; see cur_last_error()    */
+#define CUR_ERR_UNSUPPORTED 3
+
+#define CUR_MAX_TASKS 16    /* modules (nb_tasks)                                   */
+#define CUR_MAX_SLICE 8     /* entries of one module's goal slice (tasks_g_id[m])   */
+#define CUR_MAX_SEGMENTS 17 /* per-module buffers + buffer 0 (ddpg.py:255)          */
+#define CUR_MAX_COPIES 64   /* (episode, destination) pairs per cur_store_episodes  */
+#define CUR_MAX_LAYERS 8
+
+int cur_abi_version(void);
+const char* cur_last_error(void);          /* message of the last CUR_ERR_CUDA on this thread */
+int cur_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Replay storage layout.  Replaces the float64 dict-of-arrays storage of
+ * baselines/her/replay_buffer.py:23-24 by ONE float32 array per buffer made of packed
+ * per-timestep rows   [ ag | o | g | u | task_descr | change | info ]   (each section padded to a
+ * multiple of 4 floats, so every section of every row is 16-byte aligned).  An episode is T+1
+ * consecutive rows (row T carries only ag,o).  (o_2, ag_2) of step t are the head of row t+1, so a
+ * transition is one contiguous read.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cur_layout {
+  int32_t T;
+  int32_t dimo, dimag, dimg, dimu, dimtd, dimchange, diminfo;
+  int32_t off_ag, off_o, off_g, off_u, off_td, off_change, off_info; /* floats */
+  int32_t row_stride;  /* floats per row, multiple of 4                                   */
+  int32_t next_prefix; /* floats of row t+1 holding [ag|o] (== off_g)                     */
+} cur_layout;
+
+/* Fills offsets/strides.  dimtd/dimchange/diminfo may be 0 (flat structure). */
+int cur_layout_init(cur_layout* L, int T, int dimo, int dimag, int dimg, int dimu, int dimtd,
+                    int dimchange, int diminfo);
+
+/* ------------------------------------------------------------------------------------------
+ * cur_store_episodes - ReplayBuffer.store_episode (replay_buffer.py:57-72) + the per-module
+ * duplication of DDPG.store_episode (ddpg.py:187-197).  Packs `n_ep` episodes given as key-major
+ * float32 device arrays ([n_ep,T+1,dimo], [n_ep,T+1,dimag], [n_ep,T,dim*]...) into rows and writes
+ * copy i of episode copy_src[i] to slot copy_slot[i] of the buffer at copy_base[i].
+ * Slot choice (_get_storage_idx, replay_buffer.py:90-109) stays on the host: it consumes the
+ * caller's np.random stream.  copy_* are HOST arrays of length n_copies <= CUR_MAX_COPIES.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cur_episode_src {
+  const float* o;      /* [n_ep, T+1, dimo]   */
+  const float* ag;     /* [n_ep, T+1, dimag]  */
+  const float* g;      /* [n_ep, T,   dimg]   */
+  const float* u;      /* [n_ep, T,   dimu]   */
+  const float* td;     /* [n_ep, T,   dimtd]     or NULL */
+  const float* change; /* [n_ep, T,   dimchange] or NULL */
+  const float* info;   /* [n_ep, T,   diminfo]   or NULL */
+} cur_episode_src;
+
+int cur_store_episodes(void* stream, const cur_layout* L, const cur_episode_src* src, int n_ep,
+                       int n_copies, const int32_t* copy_src, float* const* copy_base,
+                       const int64_t* copy_slot);
+
+/* ------------------------------------------------------------------------------------------
+ * cur_her_sample - ONE fused kernel for
+ *   _sample_her_transitions           (her.py:20-66 flat, her.py:99-183 multi-task)
+ *   + reward_fun / compute_reward     (config.py:158-159; restated rule)
+ *   + the per-buffer loop, concat and shuffle of DDPG.sample_batch (ddpg.py:325-345)
+ *   + DDPG._preprocess_og             (ddpg.py:118-127, 350-353)
+ * Row j of every output is concat-row c = perm ? perm[j] : j; concat rows are the segments'
+ * `count`s laid end to end (buffer order).  Per concat row:
+ *   draws (ep, t, u_her, u_off[, choice]) come from the injected arrays (bit-exact replay of the
+ *   reference's np.random stream) or, when inj_ep == NULL, from Philox4x32-10 keyed by `seed` with
+ *   counter (c, call_offset) - see DESIGN.md for the exact mapping;
+ *   her = u_her < future_p;  future_t = t + 1 + (int)(u_off * (T - t))  in float64 (her.py:115-118);
+ *   HER rows get g/task_descr relabelled per `mode` (her.py:129-164 / her.py:43-47);
+ *   r is recomputed for every row from (ag_2, relabelled g, task_descr) (her.py:174-176).
+ * Any output pointer may be NULL (not produced).  Outputs are float32 [batch, dim] row-major.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  CUR_MODE_BUFFER = 0,       /* 'buffer' in task_replay: module = segment.task_to_replay, or the
+                                row's own module when task_to_replay < 0      (her.py:131-136) */
+  CUR_MODE_RANDOM_TASK = 1,  /* replay_random_task_transition                 (her.py:138-139) */
+  CUR_MODE_CP_TASK = 2,      /* replay_cp_task_transition, p = cp_proba       (her.py:141-142) */
+  CUR_MODE_CURRENT_TASK = 3, /* replay_current_task_transition                (her.py:158-164) */
+  CUR_MODE_FLAT = 4          /* make_sample_her_transitions                   (her.py:43-47)   */
+};
+
+typedef struct cur_segment {
+  const float* base;      /* packed buffer                                                   */
+  int32_t n_episodes;     /* current_size: episodes are drawn from [0, n_episodes)            */
+  int32_t count;          /* rows sampled from this buffer (proportions[i], ddpg.py:326-336)  */
+  int32_t task_to_replay; /* module forced on HER rows, or -1 for None                        */
+  int32_t _pad;
+} cur_segment;
+
+typedef struct cur_task_table {
+  int32_t n_tasks;
+  int32_t reward_kind;               /* 0: module L2 distance > threshold -> -1 else 0        */
+  int32_t len[CUR_MAX_TASKS];        /* len(tasks_g_id[m])                                    */
+  int16_t g_idx[CUR_MAX_TASKS][CUR_MAX_SLICE];  /* tasks_g_id[m][k]                           */
+  int16_t ag_idx[CUR_MAX_TASKS][CUR_MAX_SLICE]; /* tasks_ag_id[m][k], truncated to len[m]     */
+  double threshold;
+  double cdf[CUR_MAX_TASKS];         /* CP_TASK: normalised cumsum(cp_proba) (np.random.choice) */
+} cur_task_table;
+
+typedef struct cur_her_args {
+  cur_layout L;
+  cur_task_table tasks;
+  int32_t mode;
+  int32_t n_segments;
+  cur_segment seg[CUR_MAX_SEGMENTS];
+  int64_t batch;          /* total rows == sum of seg[i].count                                */
+  double future_p;        /* 1 - 1/(1+k) or 0                            (her.py:86-89)       */
+  /* injected draws, indexed by CONCAT row; all NULL => Philox */
+  const int32_t* inj_ep;
+  const int32_t* inj_t;
+  const double* inj_u_her;
+  const double* inj_u_off;
+  const int32_t* inj_choice; /* resolved np.random.choice result per row, -1 if none; may be NULL */
+  uint64_t seed;
+  uint64_t call_offset;
+  const int32_t* perm;    /* shuffle_inds (ddpg.py:338-345) or NULL                           */
+  float clip_obs;         /* clip o,g,o_2,g_2 to +-clip_obs; <= 0 disables (raw sampler output) */
+  int32_t relative_goals; /* g <- g - ag (g_2 <- g - ag_2) before clipping                    */
+  float *o, *ag, *g, *u, *td, *change, *info, *o_2, *ag_2, *g_2, *r;
+  int32_t* idx_out;       /* optional [batch,4]: ep, t, future_t (-1 if not HER), module (-1) */
+} cur_her_args;
+
+int cur_her_sample(void* stream, const cur_her_args* args);
+
+/* ------------------------------------------------------------------------------------------
+ * Normalizer (baselines/her/normalizer.py:10-118).  State is float32 on the device.
+ * ------------------------------------------------------------------------------------------ */
+/* update(v): local_sum += v.sum(0); local_sumsq += (v*v).sum(0); local_count += n  (:64-70).
+ * `partial` = [sum(dim) | sumsq(dim) | count(1)] float32. */
+int cur_norm_accumulate(void* stream, const float* v, int64_t n, int dim, float* partial);
+/* recompute_stats (:96-118, :50-61): running += partial / world   (partial already SUMMED over
+ * ranks; `buf /= size`, :84-88); mean = sum/count; std = sqrt(max(eps^2, sumsq/count - mean^2));
+ * partial <- 0.  `running` = [sum | sumsq | count] (count initialised to 1 by the caller, :37-39). */
+int cur_norm_recompute(void* stream, float* running, float* partial, float world, float eps,
+                       int dim, float* mean, float* std);
+/* normalize(v) = clip((v-mean)/std, +-clip) (:72-77); denormalize (:79-82). In place allowed. */
+int cur_norm_apply(void* stream, const float* v, int64_t n, int dim, const float* mean,
+                   const float* std, float clip, float* out);
+int cur_norm_invert(void* stream, const float* v, int64_t n, int dim, const float* mean,
+                    const float* std, float* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Flat-vector optimiser pieces (baselines/common/mpi_adam.py:21-35, ddpg.py:456-462).
+ * ------------------------------------------------------------------------------------------ */
+/* m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; theta += neg_a*m/(sqrt(v)+eps).  Unfused IEEE
+ * float32 operations in NumPy's order (bit-exact with the float32 NumPy evaluation).
+ * neg_a = float32(-(stepsize*sqrt(1-b2^t)/(1-b1^t))) is computed by the caller in float64.
+ * grad_div: divide the (already all-reduced) gradient by this first (scale_grad_by_procs,
+ * mpi_adam.py:27-28); 1 = no division.  betas/eps are doubles so (1-beta) is rounded to float32
+ * from the exact python value, as NumPy does. */
+int cur_adam_step(void* stream, float* theta, const float* grad, float* m, float* v, int64_t n,
+                  float neg_a, double beta1, double beta2, double eps, float grad_div);
+/* Same, but the step scale is read from a device table indexed by a device step counter that the
+ * kernel increments (CUDA-graph friendly).  a_table[min(t, table_len-1)], t counted from 0. */
+int cur_adam_step_graph(void* stream, float* theta, const float* grad, float* m, float* v,
+                        int64_t n, const float* neg_a_table, int table_len, int32_t* step_counter,
+                        double beta1, double beta2, double eps, float grad_div);
+/* target = polyak*target + (1-polyak)*main (ddpg.py:461-462); polyak == 0 is the init copy. */
+int cur_polyak(void* stream, float* target, const float* main_, int64_t n, double polyak);
+/* Order-independent 64-bit checksum of a float32 vector (for check_synced, mpi_adam.py:42-50). */
+int cur_checksum(void* stream, const float* x, int64_t n, uint64_t* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Actor-critic networks (baselines/her/actor_critic.py:5-98, util.py:56-107) and the DDPG graph
+ * (ddpg.py:412-449).  Parameters live in flat float32 vectors in GetFlat order
+ * (util.py:49-53, tf_util.py:221-244):
+ *    modular net:  W0s[in_s,H] b0[H] W0g[dimg,H] W1[H,H] b1[H] ... Wout[H,out] bout[out]
+ *    flat net:     W0[in,H]    b0[H]             W1[H,H] b1[H] ... Wout[H,out] bout[out]
+ * `theta` = [Q | pi] (ddpg.py:456), same for target, grads and Adam state.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cur_net_desc {
+  int32_t modular;  /* 1: MultiTaskActorCritic / nn_modular_her; 0: ActorCritic / nn          */
+  int32_t dimo, dimg, dimu, dimtd;
+  int32_t hidden, layers; /* `layers` hidden layers of `hidden` units (+ the output layer)    */
+  float max_u;
+  int32_t normalize_obs;  /* apply o_stats/g_stats.normalize to o,g (actor_critic.py:31-36)   */
+  float norm_clip;
+} cur_net_desc;
+
+int64_t cur_net_param_count(const cur_net_desc* d, int which /*0: Q, 1: pi*/);
+/* Flat arena used by every theta-like vector (main, target, grads, Adam m/v):
+ *   [ Q params | zero pad to a multiple of 4 floats | pi params | zero pad ]
+ * so that both nets start 16-byte aligned and one elementwise launch / one all-reduce covers both.
+ * Returns the float offset of the pi block; *total (optional) receives the arena length. */
+int64_t cur_theta_pi_offset(const cur_net_desc* d, int64_t* total);
+/* floats of scratch needed by cur_ddpg_grads / cur_ddpg_actions for `batch` rows */
+int64_t cur_ddpg_workspace_floats(const cur_net_desc* d, int64_t batch);
+
+typedef struct cur_norm_stats {
+  const float *o_mean, *o_std, *g_mean, *g_std; /* may be NULL when normalize_obs == 0 */
+} cur_norm_stats;
+
+/* get_actions forward (ddpg.py:129-146) including _preprocess_og (ddpg.py:118-127):
+ * g <- g - ag if `ag` != NULL (relative goals); o,g clipped to +-clip_obs (if > 0); optional
+ * normalisation; pi = max_u*tanh(net(o,g,td)) and optionally Q(o,g,td,pi).
+ * The host-side exploration noise / eps-greedy (ddpg.py:148-152) stays with the caller's RNG. */
+int cur_ddpg_actions(void* stream, const cur_net_desc* d, const float* theta,
+                     const cur_norm_stats* stats, const float* o, const float* ag /* or NULL */,
+                     const float* g, const float* td, int64_t n, float clip_obs, float* workspace,
+                     float* out_pi, float* out_q /* or NULL */);
+
+typedef struct cur_batch {
+  const float *o, *g, *u, *td, *o_2, *g_2, *r; /* staged batch (ddpg.py:75-83); td NULL if flat */
+  int64_t n;
+} cur_batch;
+
+typedef struct cur_ddpg_hyper {
+  float gamma, clip_return, action_l2;
+  int32_t clip_pos_returns;
+} cur_ddpg_hyper;
+
+/* DDPG._grads (ddpg.py:235-243): writes grads = [Q_grad | pi_grad] (flat), Q_loss (1 float),
+ * pi_loss (1 float) and main.Q_pi [n,1]. */
+int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* theta_main,
+                   const float* theta_target, const cur_norm_stats* stats, const cur_batch* batch,
+                   const cur_ddpg_hyper* h, float* workspace, float* grads, float* q_loss,
+                   float* pi_loss, float* q_pi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURIOUS_B200_H */

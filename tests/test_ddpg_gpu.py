@@ -1,0 +1,225 @@
+"""GPU parity of the DDPG path (store_episode / sample_batch / train / update_target_net / get_actions,
+Normalizer, MpiAdam) against the CPU oracle.
+
+Tolerances (float32 path, summation order differs from NumPy/Eigen):
+  losses                 rel 1e-5
+  gradients              max-abs error <= 2e-5 * max|grad|   (per flat vector)
+  weights after a step   rel 1e-5 of max|theta| ... Adam's m/sqrt(v) normalisation can flip tiny gradients,
+                         so the step itself is additionally checked with the ORACLE's gradient (bit exact)
+"""
+import numpy as np
+import pytest
+
+from tests.ddpg_util import ddpg_kwargs, episode_stream, make_gpu_agent, make_oracle_agent, rel_err
+
+pytestmark = pytest.mark.gpu
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 2e-5
+
+
+def _fill(agent, episodes, cp):
+    n = 0
+    for ep in episodes:
+        n += ep['u'].shape[0]
+        agent.store_episode({k: v.copy() for k, v in ep.items()}, cp, n)
+
+
+@pytest.mark.parametrize('normalize_obs', [False, True])
+@pytest.mark.parametrize('n_modules', [4, 8])
+def test_store_sample_train_against_oracle(normalize_obs, n_modules):
+    """Same seeds on both sides: buffers, normaliser stats, sampled batch (bit exact), losses, gradients and
+    updated weights (tolerance) must agree over several updates."""
+    import torch
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(n_modules, normalize_obs=normalize_obs)
+    cp = np.linspace(0.0, 0.3, n_modules)
+    episodes = episode_stream(dims, kw['T'], 12)
+    ora = make_oracle_agent(kw, dims, ag_ids, g_ids)
+    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy')
+    np.random.seed(2024)
+    _fill(ora, episodes, cp)
+    np.random.seed(2024)
+    _fill(gpu, episodes, cp)
+    # routing + duplication + distractor aliasing (ddpg.py:107-110,181-195)
+    for i in range(n_modules + 1):
+        assert gpu.buffer[i].current_size == ora.buffer[i].current_size, i
+        if ora.buffer[i].current_size:
+            hb = gpu.buffer[i].buffers
+            for k in ('o', 'g', 'ag', 'u', 'task_descr', 'change'):
+                n = ora.buffer[i].current_size
+                assert np.array_equal(hb[k][:n], ora.buffer[i].buffers[k][:n]), (i, k)
+    assert gpu.buffer[0].current_size == 0
+    if n_modules == 8:
+        assert gpu.buffer[6] is gpu.buffer[5] and gpu.buffer[8] is gpu.buffer[5]
+    # normaliser statistics (fp32 accumulations in a different order)
+    for a, b in ((gpu.o_stats, ora.o_stats), (gpu.g_stats, ora.g_stats)):
+        assert np.allclose(a.mean.cpu().numpy(), b.mean, rtol=1e-5, atol=1e-6)
+        assert np.allclose(a.std.cpu().numpy(), b.std, rtol=1e-5, atol=1e-6)
+        assert float(a.count.cpu()[0]) == float(b.count[0])
+    # identical initial weights
+    assert np.array_equal(gpu.get_flat('Q'), ora.Q_adam.theta)
+    assert np.array_equal(gpu.get_flat('pi'), ora.pi_adam.theta)
+    # make the comparison independent of the tiny stats difference
+    if normalize_obs:
+        gpu.o_stats.load_state_list([ora.o_stats.sum, ora.o_stats.sumsq, ora.o_stats.count, ora.o_stats.mean,
+                                     ora.o_stats.std])
+        gpu.g_stats.load_state_list([ora.g_stats.sum, ora.g_stats.sumsq, ora.g_stats.count, ora.g_stats.mean,
+                                     ora.g_stats.std])
+    for step in range(4):
+        np.random.seed(100 + step)
+        ob = ora.sample_batch()
+        np.random.seed(100 + step)
+        gb = gpu.sample_batch()
+        assert list(gpu.stage_shapes.keys()) == ora.stage_keys
+        for key, x, y in zip(ora.stage_keys, gb, ob):
+            assert x.shape == y.shape, key
+            assert np.array_equal(x, np.asarray(y, np.float64)), key        # bit exact staged batch
+        assert np.array_equal(gpu.proportions, ora.proportions)
+        gpu.stage_batch(gb)
+        ql, qpi, gq, gp = gpu._grads()
+        ref = ora.grads(ob)
+        assert abs(float(ql) - ref['Q_loss']) <= LOSS_RTOL * abs(ref['Q_loss']) + 1e-7
+        assert abs(float(gpu._pi_loss) - ref['pi_loss']) <= LOSS_RTOL * abs(ref['pi_loss']) + 1e-7
+        assert rel_err(qpi.cpu().numpy(), ref['Q_pi']) <= 1e-5
+        assert rel_err(gq.cpu().numpy(), ref['Q_grad']) <= GRAD_RTOL
+        assert rel_err(gp.cpu().numpy(), ref['pi_grad']) <= GRAD_RTOL
+        # Adam with the oracle's own gradient: bit exact
+        gpu.grads.zero_()
+        gpu._view(gpu.grads, 'Q').copy_(torch.from_numpy(ref['Q_grad']).cuda())
+        gpu._view(gpu.grads, 'pi').copy_(torch.from_numpy(ref['pi_grad']).cuda())
+        gpu._update(gpu._view(gpu.grads, 'Q'), gpu._view(gpu.grads, 'pi'))
+        ora.train(ob)
+        assert np.array_equal(gpu.get_flat('Q'), ora.Q_adam.theta)
+        assert np.array_equal(gpu.get_flat('pi'), ora.pi_adam.theta)
+        assert np.array_equal(gpu.Q_adam.m.cpu().numpy(), ora.Q_adam.m)
+        assert np.array_equal(gpu.pi_adam.v.cpu().numpy(), ora.pi_adam.v)
+    gpu.update_target_net()
+    ora.update_target_net()
+    from oracle.ddpg_oracle import flatten
+    assert np.array_equal(gpu.get_flat('Q', target=True), flatten(ora.target_Q))      # polyak: bit exact
+    assert np.array_equal(gpu.get_flat('pi', target=True), flatten(ora.target_pi))
+
+
+@pytest.mark.parametrize('structure,task_replay', [('curious', 'replay_task_random_buffer'),
+                                                   ('curious', 'replay_cp_task_transition'),
+                                                   ('curious', 'replay_random_task_transition'),
+                                                   ('curious', 'replay_current_task_transition'),
+                                                   ('task_experts', 'replay_current_task_buffer'),
+                                                   ('flat', '')])
+def test_training_trajectory_all_options(structure, task_replay):
+    """train() end to end (own gradients) for every structure / task_replay option: weights after 5 updates
+    stay within tolerance of the oracle trajectory."""
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, structure=structure, task_replay=task_replay, hidden=64, batch_size=128)
+    if structure == 'task_experts':
+        kw['t_id'] = 1
+    cp = np.array([0.05, 0.2, 0.1, 0.0])
+    episodes = episode_stream(dims, kw['T'], 6, flat=structure == 'flat')
+    ora = make_oracle_agent(kw, dims, ag_ids, g_ids)
+    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy')
+    np.random.seed(7)
+    _fill(ora, episodes, cp)
+    np.random.seed(7)
+    _fill(gpu, episodes, cp)
+    np.random.seed(8)
+    for _ in range(5):
+        ql_o, qpi_o = ora.train()
+    ora.update_target_net()
+    np.random.seed(8)
+    for _ in range(5):
+        ql_g, qpi_g = gpu.train()
+    gpu.update_target_net()
+    assert abs(float(ql_g) - ql_o) <= 1e-4 * abs(ql_o) + 1e-6
+    assert np.asarray(qpi_g).shape == qpi_o.shape == (kw['batch_size'], 1)
+    # 5 Adam steps of size ~1e-3 each: compare against the size of the accumulated update
+    for which, adam in (('Q', ora.Q_adam), ('pi', ora.pi_adam)):
+        got = gpu.get_flat(which)
+        assert np.abs(got - adam.theta).max() <= 2e-4, which
+
+
+def test_get_actions_against_oracle():
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, normalize_obs=True)
+    ora = make_oracle_agent(kw, dims, ag_ids, g_ids)
+    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids)
+    episodes = episode_stream(dims, kw['T'], 3)
+    cp = np.zeros(4)
+    np.random.seed(1)
+    _fill(ora, episodes, cp)
+    np.random.seed(1)
+    _fill(gpu, episodes, cp)
+    gpu.o_stats.load_state_list([ora.o_stats.sum, ora.o_stats.sumsq, ora.o_stats.count, ora.o_stats.mean, ora.o_stats.std])
+    gpu.g_stats.load_state_list([ora.g_stats.sum, ora.g_stats.sumsq, ora.g_stats.count, ora.g_stats.mean, ora.g_stats.std])
+    rng = np.random.RandomState(5)
+    for n in (1, 2, 38):
+        o = rng.standard_normal((n, dims['o'])).astype(np.float32) * 100
+        g = rng.uniform(-1, 1, (n, dims['g'])).astype(np.float32)
+        ag = rng.uniform(-1, 1, (n, dims['ag'])).astype(np.float32)
+        td = np.eye(4, dtype=np.float32)[rng.randint(0, 4, n)]
+        for use_target in (False, True):
+            np.random.seed(9)
+            u_o, q_o = ora.get_actions(o, ag, g, task_descr=td, noise_eps=0.2, random_eps=0.3,
+                                       use_target_net=use_target, compute_Q=True)
+            np.random.seed(9)
+            u_g, q_g = gpu.get_actions(o, ag, g, task_descr=td, noise_eps=0.2, random_eps=0.3,
+                                       use_target_net=use_target, compute_Q=True)
+            assert u_g.shape == u_o.shape and (n > 1 or u_g.ndim == 1)
+            assert np.allclose(u_g, u_o, rtol=1e-5, atol=1e-6)
+            assert np.allclose(q_g, q_o, rtol=1e-5, atol=1e-6)
+        np.random.seed(10)
+        assert np.allclose(gpu.get_actions(o, ag, g, task_descr=td), ora.get_actions(o, ag, g, task_descr=td),
+                           rtol=1e-5, atol=1e-6)
+
+
+def test_normalizer_and_adam_primitives():
+    import torch
+    from curious_b200.mpi_adam import MpiAdam
+    from curious_b200.normalizer import Normalizer
+    from oracle.ddpg_oracle import MpiAdamOracle, NormalizerOracle
+    rng = np.random.RandomState(0)
+    for dim, rows in ((40, 100), (12, 100), (3, 7), (300, 5000)):
+        a, b = Normalizer(dim, 0.01, 5), NormalizerOracle(dim, 0.01, 5)
+        for _ in range(3):
+            v = (rng.standard_normal((rows, dim)) * 3 + 1).astype(np.float32)
+            a.update(v)
+            b.update(v)
+            a.recompute_stats()
+            b.recompute_stats()
+        assert np.allclose(a.mean.cpu().numpy(), b.mean, rtol=2e-6, atol=1e-6)
+        assert np.allclose(a.std.cpu().numpy(), b.std, rtol=2e-5, atol=1e-6)
+        x = rng.standard_normal((17, dim)).astype(np.float32) * 10
+        a.load_state_list([b.sum, b.sumsq, b.count, b.mean, b.std])
+        assert np.array_equal(a.normalize(x).cpu().numpy(), b.normalize(x))
+        assert np.array_equal(a.denormalize(x).cpu().numpy(), b.denormalize(x))
+    # Adam on the reference's own test problem: sum(a^2) + sum(sin(b))  (mpi_adam.py:54-63), bit exact
+    np.random.seed(0)
+    a0 = np.random.randn(3).astype('float32')
+    b0 = np.random.randn(2, 5).astype('float32')
+    theta0 = np.concatenate([a0, b0.reshape(-1)])
+    ora = MpiAdamOracle(theta0)
+    flat = torch.zeros(16, dtype=torch.float32, device='cuda')[:13]
+    flat.copy_(torch.from_numpy(theta0))
+    gpu = MpiAdam([flat])
+    for i in range(10):
+        th = ora.theta
+        grad = np.concatenate([2 * th[:3], np.cos(th[3:])]).astype(np.float32)
+        ora.update(grad, 1e-2)
+        gpu.update(grad, 1e-2)
+        assert np.array_equal(gpu.getflat(), ora.theta), i
+
+
+def test_save_load_weights_roundtrip(tmp_path):
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, hidden=64)
+    a = make_gpu_agent(kw, dims, ag_ids, g_ids, seed=1)
+    b = make_gpu_agent(kw, dims, ag_ids, g_ids, seed=2)
+    a.update_target_net()
+    path = str(tmp_path / 'policy')
+    a.save_weights(path)
+    import pickle
+    with open(path + '_weights.pkl', 'rb') as f:
+        w = pickle.load(f)
+    # reference layout: 4 lists of per-variable arrays + 2 normaliser lists (ddpg.py:481-497)
+    assert len(w) == 6 and [x.shape for x in w[0]] == [(48, 64), (64,), (12, 64), (64, 64), (64,), (64, 64), (64,),
+                                                      (64, 1), (1,)]
+    assert [x.shape for x in w[4]] == [(40,), (40,), (1,), (40,), (40,)]
+    b.load_weights(path)
+    for which in ('Q', 'pi'):
+        for tgt in (False, True):
+            assert np.array_equal(a.get_flat(which, tgt), b.get_flat(which, tgt))

@@ -1,0 +1,185 @@
+"""CPU-only tests: C-ABI library loads and exports every declared symbol, ctypes mirrors match the header,
+host apportioning logic equals the oracle, oracle backward pass equals torch autograd."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from curious_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'curious_b200.h')).read()
+    declared = set(re.findall(r'\b(cur_[a-z0-9_]+)\s*\(', header))
+    declared -= {'cur_layout', 'cur_segment'}
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), name
+        assert name in _lib.SIGNATURES, 'ctypes signature missing for ' + name
+    assert lib.cur_abi_version() == 1
+
+
+def test_ctypes_structs_match_header(tmp_path):
+    from curious_b200 import _lib
+    src = tmp_path / 'sz.cpp'
+    src.write_text('#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
+                   'sizeof(cur_layout),sizeof(cur_task_table),sizeof(cur_segment),sizeof(cur_her_args),'
+                   'sizeof(cur_net_desc),sizeof(cur_batch),sizeof(cur_ddpg_hyper),sizeof(cur_norm_stats),'
+                   'sizeof(cur_episode_src));}\n' % os.path.join(ROOT, 'include', 'curious_b200.h'))
+    exe = tmp_path / 'sz'
+    subprocess.check_call(['g++', str(src), '-o', str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(t) for t in (_lib.Layout, _lib.TaskTable, _lib.Segment, _lib.HerArgs, _lib.NetDesc, _lib.Batch,
+                                  _lib.DdpgHyper, _lib.NormStats, _lib.EpisodeSrc)]
+    assert got == want
+
+
+def test_layout_and_param_counts_without_gpu():
+    from curious_b200 import _lib
+    L = _lib.make_layout(50, 40, 12, 12, 4, 4, 12, 1)
+    assert (L.off_ag, L.off_o, L.off_g, L.off_u, L.off_td, L.off_change, L.off_info) == (0, 12, 52, 64, 68, 72, 84)
+    assert L.row_stride == 88 and L.next_prefix == 52
+    L = _lib.make_layout(10, 25, 3, 3, 4)          # unaligned dims get padded sections
+    assert L.off_o == 4 and L.off_g == 32 and L.row_stride % 4 == 0
+    lib = _lib.load()
+    d = _lib.NetDesc(1, 40, 12, 4, 4, 256, 3, 1.0, 0, 5.0)
+    assert lib.cur_net_param_count(C.byref(d), 0) == 147457
+    assert lib.cur_net_param_count(C.byref(d), 1) == 147204
+    bad = _lib.NetDesc(1, 40, 12, 4, 4, 250, 3, 1.0, 0, 5.0)
+    assert lib.cur_net_param_count(C.byref(bad), 0) == -1
+    with pytest.raises(_lib.CuriousLibError):
+        _lib.check(lib.cur_layout_init(C.byref(_lib.Layout()), 0, 1, 1, 1, 1, 0, 0, 0), 'cur_layout_init')
+
+
+def test_apportioning_equals_oracle():
+    from curious_b200 import apportion
+    from oracle import ddpg_oracle
+    rng = np.random.RandomState(0)
+    for _ in range(300):
+        N = rng.choice([2, 4, 8])
+        sizes = [0] + list(rng.randint(0, 6, N) * (rng.uniform(size=N) < 0.7))
+        if sum(sizes[1:]) == 0:
+            sizes[1 + rng.randint(N)] = 3
+        cp = rng.uniform(size=N) * (rng.uniform(size=N) < 0.6)
+        B = int(rng.choice([100, 256, 257]))
+        for tr in ('replay_task_random_buffer', 'replay_task_cp_buffer'):
+            a = apportion.proportions_curious(sizes, 50, B, tr, cp, 0.4)
+            b = ddpg_oracle.apportion_curious(sizes, 50, B, tr, cp, 0.4)
+            assert np.array_equal(a, b) and a.sum() == B and a[0] == 0
+            assert all(a[i] == 0 for i in range(1, N + 1) if sizes[i] == 0)
+        t_id = int(rng.randint(N))
+        a = apportion.proportions_task_expert(sizes, 50, B, t_id)
+        assert np.array_equal(a, ddpg_oracle.apportion_task_expert(sizes, 50, B, t_id))
+        assert a.sum() == B
+        if sizes[t_id + 1] > 0:
+            assert a[t_id + 1] == B
+    with pytest.raises(RuntimeError):
+        apportion.proportions_curious([0, 0, 0], 50, 256, 'replay_task_cp_buffer', np.zeros(2), 0.4)
+    with pytest.raises(NameError):
+        apportion.proportions_curious([0, 1, 0], 50, 256, 'hand_designed', np.zeros(2), 0.4)
+    p = apportion.cp_probabilities([0.05, 0.2, 0.1, 0.0], 0.4)
+    assert abs(p.sum() - 1) < 1e-15 and np.allclose(p, 0.1 + 0.6 * np.array([0.05, 0.2, 0.1, 0]) / 0.35)
+    ch = np.zeros(24, bool)
+    ch[[0, 16, 21]] = True
+    ids = [[3 * j, 3 * j + 1, 3 * j + 2] for j in range(8)]
+    assert apportion.active_modules(ch, ids, ids) == [0]          # modules 5 and 7 moved but j<5 only (ddpg.py:183)
+    assert apportion.active_modules(ch[:12], ids[:4], ids[:4]) == [0]
+
+
+@pytest.mark.parametrize('modular', [True, False])
+@pytest.mark.parametrize('normalize_obs', [False, True])
+def test_oracle_gradients_equal_torch_autograd(modular, normalize_obs):
+    """The hand-written NumPy backward pass of the oracle vs torch CPU autograd of the same graph
+    (ddpg.py:412-449)."""
+    import torch
+    from oracle import ddpg_oracle as D
+    rng = np.random.RandomState(1)
+    dimo, dimg, dimu, dimtd, H, L, B = 10, 6, 4, 2 if modular else 0, 32, 3, 64
+    o_stats, g_stats = D.NormalizerOracle(dimo, 0.01, 5), D.NormalizerOracle(dimg, 0.01, 5)
+    o_stats.update(rng.standard_normal((50, dimo)).astype(np.float32)); o_stats.recompute_stats()
+    g_stats.update(rng.standard_normal((50, dimg)).astype(np.float32)); g_stats.recompute_stats()
+    ac = D.ActorCriticOracle(modular, dimo, dimg, dimu, dimtd, H, L, 1.0, normalize_obs, o_stats, g_stats)
+    nets = [D.xavier_uniform_net(rng, s) for s in (ac.Q_shapes, ac.pi_shapes, ac.Q_shapes, ac.pi_shapes)]
+    for net in nets:     # non-zero biases so their gradients are exercised
+        for v in net:
+            if v.ndim == 1:
+                v += rng.standard_normal(v.shape).astype(np.float32) * 0.1
+    batch = dict(o=rng.standard_normal((B, dimo)), g=rng.standard_normal((B, dimg)), u=rng.uniform(-1, 1, (B, dimu)),
+                 o_2=rng.standard_normal((B, dimo)), g_2=rng.standard_normal((B, dimg)),
+                 r=-(rng.uniform(size=(B, 1)) < 0.5).astype(np.float64))
+    batch = {k: v.astype(np.float32) for k, v in batch.items()}
+    if modular:
+        batch['task_descr'] = np.eye(dimtd, dtype=np.float32)[rng.randint(0, dimtd, B)]
+    out = D.ddpg_losses_and_grads(ac, nets[0], nets[1], nets[2], nets[3], batch, 0.98, 50., True, 1.0)
+
+    t = lambda a: torch.tensor(a, dtype=torch.float64)
+    tn = [[t(v).requires_grad_(True) for v in net] for net in nets]
+
+    def norm(x, st):
+        return torch.clamp((x - t(st.mean)) / t(st.std), -5, 5) if normalize_obs else x
+
+    def mlp(net, xs, xg):
+        if modular:
+            h = torch.relu(xs @ net[0] + net[1] + xg @ net[2]); rest = net[3:]
+        else:
+            h = torch.relu(torch.cat([xs, xg], 1) @ net[0] + net[1]); rest = net[2:]
+        for i in range(len(rest) // 2):
+            h = h @ rest[2 * i] + rest[2 * i + 1]
+            if i < len(rest) // 2 - 1:
+                h = torch.relu(h)
+        return h
+
+    def pi_fn(net, o, g, td):
+        return torch.tanh(mlp(net, torch.cat([o, td], 1), g) if modular else mlp(net, o, g))
+
+    def q_fn(net, o, g, td, a):
+        if modular:
+            return mlp(net, torch.cat([o, td, a], 1), g)
+        return mlp(net, torch.cat([o, g, a], 1), torch.zeros(o.shape[0], 0, dtype=torch.float64))
+
+    o, g, o2, g2 = norm(t(batch['o']), o_stats), norm(t(batch['g']), g_stats), norm(t(batch['o_2']), o_stats), \
+        norm(t(batch['g_2']), g_stats)
+    td = t(batch['task_descr']) if modular else None
+    pi = pi_fn(tn[1], o, g, td)
+    Q_pi = q_fn(tn[0], o, g, td, pi)
+    Q = q_fn(tn[0], o, g, td, t(batch['u']))
+    with torch.no_grad():
+        tgt = torch.clamp(t(batch['r']) + 0.98 * q_fn(tn[2], o2, g2, td, pi_fn(tn[3], o2, g2, td)), -50., 0.)
+    Q_loss = ((tgt - Q) ** 2).mean()
+    pi_loss = -Q_pi.mean() + (pi ** 2).mean()
+    gQ = torch.autograd.grad(Q_loss, tn[0], retain_graph=True)
+    gP = torch.autograd.grad(pi_loss, tn[1])
+    flat = lambda gs: np.concatenate([x.numpy().reshape(-1) for x in gs])
+    assert abs(out['Q_loss'] - Q_loss.item()) < 1e-5 * abs(Q_loss.item())
+    assert abs(out['pi_loss'] - pi_loss.item()) < 1e-5 * abs(pi_loss.item()) + 1e-7
+    for got, want in ((out['Q_grad'], flat(gQ)), (out['pi_grad'], flat(gP))):
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_adam_oracle_on_reference_test_problem():
+    """The problem of the reference's print-only test_MpiAdam (mpi_adam.py:54-63): 10 steps on
+    sum(a^2)+sum(sin(b)) must track an independent float64 Adam (TF's epsilon-hat formulation)."""
+    from oracle.ddpg_oracle import MpiAdamOracle
+    np.random.seed(0)
+    a = np.random.randn(3).astype('float32')
+    b = np.random.randn(2, 5).astype('float32')
+    th0 = np.concatenate([a, b.reshape(-1)])
+    ora = MpiAdamOracle(th0)
+    th = th0.astype(np.float64)
+    m = np.zeros_like(th); v = np.zeros_like(th)
+    losses = []
+    for t in range(1, 11):
+        g = np.concatenate([2 * th[:3], np.cos(th[3:])])
+        losses.append((th[:3] ** 2).sum() + np.sin(th[3:]).sum())
+        m = 0.9 * m + 0.1 * g; v = 0.999 * v + 0.001 * g * g
+        th = th - 1e-2 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * m / (np.sqrt(v) + 1e-8)
+        g32 = np.concatenate([2 * ora.theta[:3], np.cos(ora.theta[3:])]).astype(np.float32)
+        ora.update(g32, 1e-2)
+        assert ora.theta.dtype == np.float32 and ora.m.dtype == np.float32
+        assert np.allclose(ora.theta, th, rtol=1e-5, atol=1e-6)
+    assert losses[-1] < losses[0]
