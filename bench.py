@@ -129,7 +129,7 @@ def fill_buffer_on_device(buf, dims, seed):
         info = (torch.rand((n, T, 1), generator=g, device=dev) < 0.25).float()
         staged = StagedEpisodes.from_device(dict(o=o.contiguous(), ag=ag, g=gg, u=u.contiguous(), task_descr=td,
                                                  change=change, info=info), buf.layout)
-        staged.store([(i, buf.storage, e0 + i) for i in range(n)])
+        staged.store([(i, buf.storage, buf.cold, e0 + i) for i in range(n)])
         torch.cuda.synchronize()
     buf.current_size = E
     buf.n_transitions_stored = E * T

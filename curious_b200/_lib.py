@@ -24,8 +24,8 @@ f32p = C.POINTER(C.c_float)
 class Layout(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'T', 'dimo', 'dimag', 'dimg', 'dimu', 'dimtd', 'dimchange', 'diminfo',
-        'off_ag', 'off_o', 'off_g', 'off_u', 'off_td', 'off_change', 'off_info',
-        'row_stride', 'next_prefix')]
+        'off_g', 'off_u', 'off_td', 'off_ag', 'off_o', 'row_stride',
+        'off_change', 'off_info', 'cold_stride')]
 
 
 class EpisodeSrc(C.Structure):
@@ -33,7 +33,7 @@ class EpisodeSrc(C.Structure):
 
 
 class Segment(C.Structure):
-    _fields_ = [('base', C.c_void_p), ('n_episodes', C.c_int32), ('count', C.c_int32),
+    _fields_ = [('base', C.c_void_p), ('cold', C.c_void_p), ('n_episodes', C.c_int32), ('count', C.c_int32),
                 ('task_to_replay', C.c_int32), ('_pad', C.c_int32)]
 
 
@@ -84,7 +84,8 @@ SIGNATURES = {
     'cur_device_info': (C.c_int, [C.POINTER(C.c_int)] * 3),
     'cur_layout_init': (C.c_int, [C.POINTER(Layout)] + [C.c_int] * 8),
     'cur_store_episodes': (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(EpisodeSrc), C.c_int, C.c_int,
-                                     C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_int64)]),
     'cur_her_sample': (C.c_int, [C.c_void_p, C.POINTER(HerArgs)]),
     'cur_norm_accumulate': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     'cur_norm_recompute': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int,

@@ -6,15 +6,16 @@
 //   baselines/her/ddpg.py:325-345, 350-353    per-buffer loop, concat, shuffle, _preprocess_og
 //   config.py:158-159 reward_fun              restated module-distance reward
 //
-// Kernel design (HBM bound, gather of ~0.5 KB per transition):
-//   * one CTA handles a tile of TILE consecutive OUTPUT rows;
-//   * the per-row draws are decoded by TILE threads (injected stream or Philox4x32-10);
-//   * each of those threads issues cp.async.bulk (TMA engine, SASS UBLKCP) copies of
-//       row t [+ head of row t+1]  and, for HER rows, the future achieved goal
-//     into shared memory, completion tracked by one mbarrier with expect_tx byte counts - no
-//     register staging, ~20 KB in flight per CTA, several CTAs per SM;
-//   * relabel (g, task_descr), float64 reward and clip are done out of shared memory and every
-//     output array is written as contiguous, fully coalesced 16-byte stores.
+// Kernel design (HBM bound, one ~0.5 KB gather per transition; ncu history in profiles/):
+//   * one CTA = TILE consecutive OUTPUT rows, 4 warps;
+//   * warp 0 decodes the per-row draws (injected stream or Philox4x32-10), one lane per row, and
+//     publishes three source addresses per row (main span, future achieved goal, cold row);
+//   * all warps then copy global -> shared with per-lane 16-byte cp.async (SASS LDGSTS, L2-only
+//     `.cg`): thanks to the shifted hot-row layout the whole transition is ONE contiguous span, so a
+//     single warp-wide LDGSTS moves an Arm4 transition (28 lanes span + 3 lanes future goal);
+//     no register staging, ~16 KB in flight per CTA, up to 14 CTAs per SM;
+//   * relabel (g, task_descr), the float64 reward and the clip are evaluated straight out of shared
+//     memory and every output array is written as contiguous, fully coalesced 16-byte stores.
 #include "common.cuh"
 
 namespace cur {
@@ -36,16 +37,17 @@ int sm_count() {
 
 constexpr int TILE = 32;         // transitions per CTA
 constexpr int HER_THREADS = 128;
+constexpr int HER_WARPS = HER_THREADS / 32;
 
 struct HerPlan {
-  // shared-memory image of one transition: [row t | head of row t+1] at the SAME float offsets as in
-  // global memory, followed by the future achieved goal.
-  int img_floats;   // row_stride + next_prefix
-  int fut_off;      // float offset of the future-ag copy inside the per-transition stage
+  // shared-memory image of one transition = global floats [row t + img_off, row t+1 end), then the
+  // future achieved goal, then (optionally) the cold row
+  int img_off;      // first float of row t that is copied (off_o, or off_ag when ag_t is needed)
+  int i0;           // image index where row t+1 starts (= row_stride - img_off)
+  int img4;         // 16-byte chunks of the image
+  int fut_off, fut4;
+  int cold_off, cold4;   // cold4 == 0 when change/info are not requested
   int stage_stride; // floats per transition in shared memory
-  int c1_off, c1_len;  // first bulk copy  (floats, relative to row t)
-  int c2_off, c2_len;  // second bulk copy (0 length if merged into the first)
-  int fut_len;         // floats of the future-ag copy (dimag padded to 4)
   int dimg_pad;
 };
 
@@ -54,47 +56,15 @@ struct HerKernelParams {
   HerPlan p;
 };
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers: mbarrier + bulk async copy (global -> shared::cta of this CTA)
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem)
                : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                         uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ float clipf(float x, float c) { return fminf(fmaxf(x, -c), c); }
@@ -127,6 +97,37 @@ __device__ __forceinline__ void emit(float* __restrict__ out, int dim, int64_t j
   }
 }
 
+// Two outputs of the same width sharing the index arithmetic (o/o_2, g/g_2, ag/ag_2).
+template <typename A4, typename B4, typename A1, typename B1>
+__device__ __forceinline__ void emit2(float* __restrict__ outa, float* __restrict__ outb, int dim, int64_t j0,
+                                      int nrows, A4 a4, B4 b4, A1 a1, B1 b1) {
+  if (outa == nullptr) { emit(outb, dim, j0, nrows, b4, b1); return; }
+  if (outb == nullptr) { emit(outa, dim, j0, nrows, a4, a1); return; }
+  if (dim <= 0) return;
+  float* da = outa + j0 * (int64_t)dim;
+  float* db = outb + j0 * (int64_t)dim;
+  if ((dim & 3) == 0) {
+    const int d4 = dim >> 2;
+    const float inv = 1.0f / (float)d4;
+    const int n4 = nrows * d4;
+    for (int i = threadIdx.x; i < n4; i += HER_THREADS) {
+      int tr = __float2int_rz(((float)i + 0.5f) * inv);
+      int k = (i - tr * d4) << 2;
+      reinterpret_cast<float4*>(da)[i] = a4(tr, k);
+      reinterpret_cast<float4*>(db)[i] = b4(tr, k);
+    }
+  } else {
+    const float inv = 1.0f / (float)dim;
+    const int n = nrows * dim;
+    for (int i = threadIdx.x; i < n; i += HER_THREADS) {
+      int tr = __float2int_rz(((float)i + 0.5f) * inv);
+      int k = i - tr * dim;
+      da[i] = a1(tr, k);
+      db[i] = b1(tr, k);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(HER_THREADS)
 her_sample_kernel(const __grid_constant__ HerKernelParams P) {
   const cur_her_args& a = P.a;
@@ -134,41 +135,26 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
   const HerPlan& pl = P.p;
   extern __shared__ __align__(128) unsigned char smem_raw[];
 
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);               // 16 bytes reserved
-  float* stage = reinterpret_cast<float*>(smem_raw + 16);             // TILE * stage_stride
-  float* gfin = stage + TILE * pl.stage_stride;                        // TILE * dimg_pad
-  float* rew = gfin + TILE * pl.dimg_pad;                              // TILE
-  int* m_her = reinterpret_cast<int*>(rew + TILE);                     // TILE: 1 if HER row
-  int* m_task = m_her + TILE;                                          // TILE: module written to td (-1: keep)
-  int* m_relab = m_task + TILE;                                        // TILE: module whose slice is relabelled
-  int16_t* gmap = reinterpret_cast<int16_t*>(m_relab + TILE);          // n_maps * dimg_pad
-  const int n_maps = (a.mode == CUR_MODE_FLAT) ? 1 : a.tasks.n_tasks;
+  float* stage = reinterpret_cast<float*>(smem_raw);                              // TILE * stage_stride
+  // per row: source address of [0] the main span, [1] the future achieved goal (NULL: not a HER
+  // row), [2] the cold row (NULL: not requested)
+  const float** m_src = reinterpret_cast<const float**>(stage + TILE * pl.stage_stride);    // TILE * 3
+  float* rew = reinterpret_cast<float*>(m_src + 3 * TILE);                        // TILE
+  int* m_task = reinterpret_cast<int*>(rew + TILE);        // module written to task_descr (-1: keep)
+  int* m_relab = m_task + TILE;                            // module whose goal slice is relabelled (-1: none)
 
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const int64_t j0 = (int64_t)blockIdx.x * TILE;
   const int nrows = (int)min((int64_t)TILE, a.batch - j0);
+  const int ss = pl.stage_stride;
 
-  // goal-column -> achieved-goal-column map per module (her.py:145-155); -1 = not in the slice
-  for (int i = tid; i < n_maps * pl.dimg_pad; i += HER_THREADS) gmap[i] = -1;
-  if (tid == 0) {
-    mbar_init(bar, TILE);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (a.mode == CUR_MODE_FLAT) {
-    for (int m = tid; m < a.tasks.n_tasks; m += HER_THREADS)
-      for (int k = 0; k < a.tasks.len[m]; ++k) gmap[a.tasks.g_idx[m][k]] = a.tasks.ag_idx[m][k];
-  } else {
-    for (int m = tid; m < a.tasks.n_tasks; m += HER_THREADS)
-      for (int k = 0; k < a.tasks.len[m]; ++k)
-        gmap[m * pl.dimg_pad + a.tasks.g_idx[m][k]] = a.tasks.ag_idx[m][k];
-  }
-
-  // ---------------------------------------------------------------- phase A: draws + bulk copies
+  // ---------------------------------------------------------------- phase A: draws (warp 0)
   int my_ft = -1, my_choice = -1, my_ep = 0, my_t = 0, my_ttr = -1;
-  if (tid < TILE) {
-    if (tid < nrows) {
-      const int64_t j = j0 + tid;
+  bool my_her = false;
+  if (warp == 0) {
+    if (lane < nrows) {
+      const int64_t j = j0 + lane;
       const int64_t c = a.perm ? (int64_t)a.perm[j] : j;
       // segment lookup: concat rows are the segments' counts laid end to end (ddpg.py:326-345)
       int s = 0;
@@ -210,105 +196,115 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
           }
         }
       }
-      const bool her = u_her < a.future_p;                         // her.py:115
-      if (her) my_ft = my_t + 1 + (int)(u_off * (double)(L.T - my_t));   // her.py:116-118
-      m_her[tid] = her ? 1 : 0;
-
-      const float* row = base + ((int64_t)my_ep * (L.T + 1) + my_t) * (int64_t)L.row_stride;
-      float* st = stage + tid * pl.stage_stride;
-      uint32_t bytes = (uint32_t)(pl.c1_len + pl.c2_len + (her ? pl.fut_len : 0)) * 4u;
-      mbar_arrive_expect_tx(bar, bytes);
-      bulk_g2s(st + pl.c1_off, row + pl.c1_off, (uint32_t)pl.c1_len * 4u, bar);
-      if (pl.c2_len > 0) bulk_g2s(st + pl.c2_off, row + pl.c2_off, (uint32_t)pl.c2_len * 4u, bar);
-      if (her) {
-        const float* frow = base + ((int64_t)my_ep * (L.T + 1) + my_ft) * (int64_t)L.row_stride;
-        bulk_g2s(st + pl.fut_off, frow + L.off_ag, (uint32_t)pl.fut_len * 4u, bar);
-      }
-    } else {
-      m_her[tid] = 0;
-      mbar_arrive(bar);
+      my_her = u_her < a.future_p;                                           // her.py:115
+      if (my_her) my_ft = my_t + 1 + (int)(u_off * (double)(L.T - my_t));    // her.py:116-118
+      const int64_t row = ((int64_t)my_ep * (L.T + 1) + my_t) * (int64_t)L.row_stride;
+      m_src[3 * lane + 0] = base + row + pl.img_off;
+      m_src[3 * lane + 1] = my_her ? base + ((int64_t)my_ep * (L.T + 1) + my_ft) * (int64_t)L.row_stride + L.off_ag
+                                   : nullptr;
+      m_src[3 * lane + 2] = (pl.cold4 > 0) ? a.seg[s].cold + ((int64_t)my_ep * L.T + my_t) * (int64_t)L.cold_stride
+                                           : nullptr;
     }
   }
-  __syncthreads();   // gmap + m_her visible; (copies still in flight)
-  mbar_wait(bar, 0);
+  __syncthreads();
 
-  // ---------------------------------------------------------------- phase A': module decisions
-  if (tid < nrows) {
-    const float* st = stage + tid * pl.stage_stride;
+  // ---------------------------------------------------------------- copies: global -> shared
+  // Each lane owns a fixed 16-byte chunk slot of the per-transition stage (region, index in region,
+  // destination offset are loop invariant); per row it only fetches the region's source address.
+  {
+    const int per_row = pl.img4 + pl.fut4 + pl.cold4;
+    const uint32_t stage_s = smem_u32(stage);
+    for (int c0 = 0; c0 < per_row; c0 += 32) {
+      const int c = c0 + lane;
+      int sel = 0, q = c, doff = 4 * c;
+      if (c >= pl.img4 + pl.fut4) { sel = 2; q = c - pl.img4 - pl.fut4; doff = pl.cold_off + 4 * q; }
+      else if (c >= pl.img4) { sel = 1; q = c - pl.img4; doff = pl.fut_off + 4 * q; }
+      const bool active = c < per_row;
+      uint32_t dst = stage_s + 4u * (uint32_t)(warp * ss + doff);
+      const uint32_t dstep = 4u * (uint32_t)(HER_WARPS * ss);
+      for (int r = warp; r < nrows; r += HER_WARPS, dst += dstep) {
+        const float* src = m_src[3 * r + sel];
+        if (active && src != nullptr)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * q) : "memory");
+      }
+    }
+    cp_async_wait_all();
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- module decisions + reward
+  // image indices: row t sections at (off - img_off); row t+1 sections at (i0 + off);
+  // g/u/td of step t live in row t+1 (shifted layout)
+  const int iG = pl.i0 + L.off_g, iU = pl.i0 + L.off_u, iTD = pl.i0 + L.off_td;
+  const int iAG2 = pl.i0 + L.off_ag, iO2 = pl.i0 + L.off_o;
+  const int iO = L.off_o - pl.img_off, iAG = L.off_ag - pl.img_off;   // iAG valid only if img_off <= off_ag
+  const bool wipe = (a.mode == CUR_MODE_BUFFER || a.mode == CUR_MODE_RANDOM_TASK || a.mode == CUR_MODE_CP_TASK);
+
+  if (warp == 0 && lane < nrows) {
+    float* st = stage + lane * ss;
     int own = -1;
     for (int k = 0; k < L.dimtd; ++k)
-      if (st[L.off_td + k] == 1.0f) { own = k; break; }            // argwhere(td == 1) (her.py:134)
+      if (st[iTD + k] == 1.0f) { own = k; break; }                 // argwhere(td == 1) (her.py:134)
     int relab = -1, newtd = -1;
-    if (m_her[tid]) {
+    if (my_her) {
       switch (a.mode) {
         case CUR_MODE_BUFFER: relab = (my_ttr >= 0) ? my_ttr : own; newtd = relab; break;
         case CUR_MODE_RANDOM_TASK:
         case CUR_MODE_CP_TASK: relab = my_choice; newtd = relab; break;
         case CUR_MODE_CURRENT_TASK: relab = own; newtd = -1; break;
-        default: relab = 0; newtd = -1; break;   // FLAT: single map
+        default: break;                          // FLAT handled below
+      }
+      // relabel IN PLACE in the staged image (this lane owns the row)
+      const float* fut = st + pl.fut_off;
+      if (a.mode == CUR_MODE_FLAT) {
+        for (int m = 0; m < a.tasks.n_tasks; ++m)                   // her.py:43-47
+          for (int k = 0; k < a.tasks.len[m]; ++k) st[iG + a.tasks.g_idx[m][k]] = fut[a.tasks.ag_idx[m][k]];
+      } else if (relab >= 0) {
+        if (wipe) {
+          for (int k = 0; k < L.dimg; ++k) st[iG + k] = 0.0f;       // her.py:151
+          for (int k = 0; k < L.dimtd; ++k) st[iTD + k] = (k == newtd) ? 1.0f : 0.0f;   // her.py:152,155
+        }
+        for (int k = 0; k < a.tasks.len[relab]; ++k)                // her.py:154 / 163
+          st[iG + a.tasks.g_idx[relab][k]] = fut[a.tasks.ag_idx[relab][k]];
+      } else if (wipe) {
+        // HER row whose module could not be determined (task_descr not one-hot): the reference would
+        // raise; clear like her.py:151-152 so the output is at least well defined
+        for (int k = 0; k < L.dimg; ++k) st[iG + k] = 0.0f;
+        for (int k = 0; k < L.dimtd; ++k) st[iTD + k] = 0.0f;
       }
     }
-    m_relab[tid] = relab;
-    m_task[tid] = newtd;
     if (a.idx_out) {
-      int32_t* io = a.idx_out + (j0 + tid) * 4;
-      io[0] = my_ep; io[1] = my_t; io[2] = my_ft; io[3] = m_her[tid] ? relab : -1;
+      int32_t* io = a.idx_out + (j0 + lane) * 4;
+      io[0] = my_ep; io[1] = my_t; io[2] = my_ft;
+      io[3] = my_her ? ((a.mode == CUR_MODE_FLAT) ? 0 : relab) : -1;
     }
-    // module used by the reward: relabelled module for HER rows that rewrite td, else the row's own
-    my_choice = (newtd >= 0) ? newtd : own;
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- phase B: relabelled goal
-  {
-    const int n = nrows * pl.dimg_pad;
-    const float inv = 1.0f / (float)pl.dimg_pad;
-    const bool wipe = (a.mode == CUR_MODE_BUFFER || a.mode == CUR_MODE_RANDOM_TASK ||
-                       a.mode == CUR_MODE_CP_TASK);
-    for (int i = tid; i < n; i += HER_THREADS) {
-      int tr = __float2int_rz(((float)i + 0.5f) * inv);
-      int k = i - tr * pl.dimg_pad;
-      const float* st = stage + tr * pl.stage_stride;
-      float v = (k < L.dimg) ? st[L.off_g + k] : 0.0f;
-      if (m_her[tr] && k < L.dimg) {
-        int relab = m_relab[tr];
-        int src = (relab >= 0) ? gmap[relab * pl.dimg_pad + k] : -1;
-        if (src >= 0) v = st[pl.fut_off + src];          // her.py:154 / 163 / 47
-        else if (wipe) v = 0.0f;                          // her.py:151
+    if (a.r != nullptr) {
+      // reward on (ag_2, relabelled g, final task_descr) in float64, NumPy's operation order
+      const float* ag2 = st + iAG2;
+      const float* gf = st + iG;
+      double d2 = 0.0;
+      if (a.mode == CUR_MODE_FLAT) {
+        for (int m = 0; m < a.tasks.n_tasks; ++m)
+          for (int k = 0; k < a.tasks.len[m]; ++k) {
+            double diff = (double)ag2[a.tasks.ag_idx[m][k]] - (double)gf[a.tasks.g_idx[m][k]];
+            d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+          }
+      } else {
+        const int m = (newtd >= 0) ? newtd : own;
+        if (m >= 0)
+          for (int k = 0; k < a.tasks.len[m]; ++k) {
+            double diff = (double)ag2[a.tasks.ag_idx[m][k]] - (double)gf[a.tasks.g_idx[m][k]];
+            d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+          }
       }
-      gfin[i] = v;
+      a.r[j0 + lane] = (sqrt(d2) > a.tasks.threshold) ? -1.0f : 0.0f;
     }
   }
   __syncthreads();
 
-  // ---------------------------------------------------------------- phase C: reward (float64)
-  if (tid < nrows && a.r != nullptr) {
-    const float* st = stage + tid * pl.stage_stride;
-    const float* ag2 = st + L.row_stride + L.off_ag;
-    const float* gf = gfin + tid * pl.dimg_pad;
-    double d2 = 0.0;
-    if (a.mode == CUR_MODE_FLAT) {
-      for (int m = 0; m < a.tasks.n_tasks; ++m)
-        for (int k = 0; k < a.tasks.len[m]; ++k) {
-          double diff = (double)ag2[a.tasks.ag_idx[m][k]] - (double)gf[a.tasks.g_idx[m][k]];
-          d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
-        }
-    } else {
-      int m = my_choice;
-      if (m >= 0)
-        for (int k = 0; k < a.tasks.len[m]; ++k) {
-          double diff = (double)ag2[a.tasks.ag_idx[m][k]] - (double)gf[a.tasks.g_idx[m][k]];
-          d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
-        }
-    }
-    rew[tid] = (sqrt(d2) > a.tasks.threshold) ? -1.0f : 0.0f;
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- phase D: coalesced outputs
+  // ---------------------------------------------------------------- coalesced outputs
   const float c = a.clip_obs;
   const bool do_clip = c > 0.0f;
-  const int ss = pl.stage_stride;
   auto ld4 = [&](int tr, int off) {
     return *reinterpret_cast<const float4*>(stage + tr * ss + off);
   };
@@ -317,130 +313,121 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
     return v;
   };
   auto clip1 = [&](float v) { return do_clip ? clipf(v, c) : v; };
+  auto sub4 = [&](float4 x, float4 y) { return make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w); };
 
-  emit(a.o, L.dimo, j0, nrows,
-       [&](int tr, int k) { return clip4(ld4(tr, L.off_o + k)); },
-       [&](int tr, int k) { return clip1(stage[tr * ss + L.off_o + k]); });
-  emit(a.o_2, L.dimo, j0, nrows,
-       [&](int tr, int k) { return clip4(ld4(tr, L.row_stride + L.off_o + k)); },
-       [&](int tr, int k) { return clip1(stage[tr * ss + L.row_stride + L.off_o + k]); });
+  emit2(a.o, a.o_2, L.dimo, j0, nrows,
+        [&](int tr, int k) { return clip4(ld4(tr, iO + k)); },
+        [&](int tr, int k) { return clip4(ld4(tr, iO2 + k)); },
+        [&](int tr, int k) { return clip1(stage[tr * ss + iO + k]); },
+        [&](int tr, int k) { return clip1(stage[tr * ss + iO2 + k]); });
   emit(a.u, L.dimu, j0, nrows,
-       [&](int tr, int k) { return ld4(tr, L.off_u + k); },
-       [&](int tr, int k) { return stage[tr * ss + L.off_u + k]; });
-  emit(a.ag, L.dimag, j0, nrows,
-       [&](int tr, int k) { return ld4(tr, L.off_ag + k); },
-       [&](int tr, int k) { return stage[tr * ss + L.off_ag + k]; });
-  emit(a.ag_2, L.dimag, j0, nrows,
-       [&](int tr, int k) { return ld4(tr, L.row_stride + L.off_ag + k); },
-       [&](int tr, int k) { return stage[tr * ss + L.row_stride + L.off_ag + k]; });
-  emit(a.change, L.dimchange, j0, nrows,
-       [&](int tr, int k) { return ld4(tr, L.off_change + k); },
-       [&](int tr, int k) { return stage[tr * ss + L.off_change + k]; });
-  emit(a.info, L.diminfo, j0, nrows,
-       [&](int tr, int k) { return ld4(tr, L.off_info + k); },
-       [&](int tr, int k) { return stage[tr * ss + L.off_info + k]; });
-  // task_descr: one-hot of the replayed module on HER rows that rewrite it (her.py:152,155)
-  auto td1 = [&](int tr, int k) {
-    int nt = m_task[tr];
-    return (nt >= 0) ? ((k == nt) ? 1.0f : 0.0f) : stage[tr * ss + L.off_td + k];
-  };
+       [&](int tr, int k) { return ld4(tr, iU + k); },
+       [&](int tr, int k) { return stage[tr * ss + iU + k]; });
   emit(a.td, L.dimtd, j0, nrows,
-       [&](int tr, int k) { return make_float4(td1(tr, k), td1(tr, k + 1), td1(tr, k + 2), td1(tr, k + 3)); },
-       td1);
+       [&](int tr, int k) { return ld4(tr, iTD + k); },
+       [&](int tr, int k) { return stage[tr * ss + iTD + k]; });
   // g / g_2 (ddpg.py:350-353): optional relative goals, then clip
-  auto g1 = [&](int tr, int k) {
-    float v = gfin[tr * pl.dimg_pad + k];
-    if (a.relative_goals) v = v - stage[tr * ss + L.off_ag + k];
-    return clip1(v);
-  };
-  auto g2_1 = [&](int tr, int k) {
-    float v = gfin[tr * pl.dimg_pad + k];
-    if (a.relative_goals) v = v - stage[tr * ss + L.row_stride + L.off_ag + k];
-    return clip1(v);
-  };
-  emit(a.g, L.dimg, j0, nrows,
-       [&](int tr, int k) { return make_float4(g1(tr, k), g1(tr, k + 1), g1(tr, k + 2), g1(tr, k + 3)); }, g1);
-  emit(a.g_2, L.dimg, j0, nrows,
-       [&](int tr, int k) { return make_float4(g2_1(tr, k), g2_1(tr, k + 1), g2_1(tr, k + 2), g2_1(tr, k + 3)); },
-       g2_1);
-  if (a.r != nullptr && tid < nrows) a.r[j0 + tid] = rew[tid];
+  if (a.relative_goals) {
+    emit2(a.g, a.g_2, L.dimg, j0, nrows,
+          [&](int tr, int k) { return clip4(sub4(ld4(tr, iG + k), ld4(tr, iAG + k))); },
+          [&](int tr, int k) { return clip4(sub4(ld4(tr, iG + k), ld4(tr, iAG2 + k))); },
+          [&](int tr, int k) { return clip1(stage[tr * ss + iG + k] - stage[tr * ss + iAG + k]); },
+          [&](int tr, int k) { return clip1(stage[tr * ss + iG + k] - stage[tr * ss + iAG2 + k]); });
+  } else {
+    emit2(a.g, a.g_2, L.dimg, j0, nrows,
+          [&](int tr, int k) { return clip4(ld4(tr, iG + k)); },
+          [&](int tr, int k) { return clip4(ld4(tr, iG + k)); },
+          [&](int tr, int k) { return clip1(stage[tr * ss + iG + k]); },
+          [&](int tr, int k) { return clip1(stage[tr * ss + iG + k]); });
+  }
+  emit2(a.ag, a.ag_2, L.dimag, j0, nrows,
+        [&](int tr, int k) { return ld4(tr, iAG + k); },
+        [&](int tr, int k) { return ld4(tr, iAG2 + k); },
+        [&](int tr, int k) { return stage[tr * ss + iAG + k]; },
+        [&](int tr, int k) { return stage[tr * ss + iAG2 + k]; });
+  emit(a.change, L.dimchange, j0, nrows,
+       [&](int tr, int k) { return ld4(tr, pl.cold_off + L.off_change + k); },
+       [&](int tr, int k) { return stage[tr * ss + pl.cold_off + L.off_change + k]; });
+  emit(a.info, L.diminfo, j0, nrows,
+       [&](int tr, int k) { return ld4(tr, pl.cold_off + L.off_info + k); },
+       [&](int tr, int k) { return stage[tr * ss + pl.cold_off + L.off_info + k]; });
 }
 
 // ------------------------------------------------------------------------------------------------
-// store: pack key-major episodes into rows, one CTA per (row, copy)
+// store: pack key-major episodes into hot/cold rows, one CTA per (row, copy)
 // ------------------------------------------------------------------------------------------------
 struct StoreParams {
   cur_layout L;
   cur_episode_src src;
   int n_copies;
   int32_t copy_src[CUR_MAX_COPIES];
-  float* copy_base[CUR_MAX_COPIES];
+  float* copy_hot[CUR_MAX_COPIES];
+  float* copy_cold[CUR_MAX_COPIES];
   int64_t copy_slot[CUR_MAX_COPIES];
 };
 
 __global__ void __launch_bounds__(128) store_episodes_kernel(const __grid_constant__ StoreParams S) {
   const cur_layout& L = S.L;
-  const int t = blockIdx.x;        // 0..T
+  const int r = blockIdx.x;        // hot row 0..T
   const int cpy = blockIdx.y;
   const int e = S.copy_src[cpy];
-  float* dst = S.copy_base[cpy] + (S.copy_slot[cpy] * (L.T + 1) + t) * (int64_t)L.row_stride;
-  const bool last = (t == L.T);
+  float* dst = S.copy_hot[cpy] + (S.copy_slot[cpy] * (L.T + 1) + r) * (int64_t)L.row_stride;
+  const int64_t rprev = (int64_t)e * L.T + (r - 1);        // step whose g/u/td live in this row
+  const int64_t rcur = (int64_t)e * (L.T + 1) + r;
   for (int k = threadIdx.x; k < L.row_stride; k += blockDim.x) {
     float v = 0.0f;
-    if (k < L.off_o) {
+    if (k < L.off_ag) {
+      if (r > 0) {
+        if (k < L.off_u) {
+          int j = k - L.off_g;
+          if (j < L.dimg) v = S.src.g[rprev * L.dimg + j];
+        } else if (k < L.off_td) {
+          int j = k - L.off_u;
+          if (j < L.dimu) v = S.src.u[rprev * L.dimu + j];
+        } else {
+          int j = k - L.off_td;
+          if (j < L.dimtd && S.src.td) v = S.src.td[rprev * L.dimtd + j];
+        }
+      }
+    } else if (k < L.off_o) {
       int j = k - L.off_ag;
-      if (j < L.dimag) v = S.src.ag[((int64_t)e * (L.T + 1) + t) * L.dimag + j];
-    } else if (k < L.off_g) {
+      if (j < L.dimag) v = S.src.ag[rcur * L.dimag + j];
+    } else {
       int j = k - L.off_o;
-      if (j < L.dimo) v = S.src.o[((int64_t)e * (L.T + 1) + t) * L.dimo + j];
-    } else if (!last) {
-      const int64_t rt = (int64_t)e * L.T + t;
-      if (k < L.off_u) {
-        int j = k - L.off_g;
-        if (j < L.dimg) v = S.src.g[rt * L.dimg + j];
-      } else if (k < L.off_td) {
-        int j = k - L.off_u;
-        if (j < L.dimu) v = S.src.u[rt * L.dimu + j];
-      } else if (k < L.off_change) {
-        int j = k - L.off_td;
-        if (j < L.dimtd && S.src.td) v = S.src.td[rt * L.dimtd + j];
-      } else if (k < L.off_info) {
+      if (j < L.dimo) v = S.src.o[rcur * L.dimo + j];
+    }
+    dst[k] = v;
+  }
+  if (r < L.T && L.cold_stride > 0 && S.copy_cold[cpy] != nullptr) {
+    float* cd = S.copy_cold[cpy] + (S.copy_slot[cpy] * L.T + r) * (int64_t)L.cold_stride;
+    const int64_t rt = (int64_t)e * L.T + r;
+    for (int k = threadIdx.x; k < L.cold_stride; k += blockDim.x) {
+      float v = 0.0f;
+      if (k < L.off_info) {
         int j = k - L.off_change;
         if (j < L.dimchange && S.src.change) v = S.src.change[rt * L.dimchange + j];
       } else {
         int j = k - L.off_info;
         if (j < L.diminfo && S.src.info) v = S.src.info[rt * L.diminfo + j];
       }
+      cd[k] = v;
     }
-    dst[k] = v;
   }
 }
 
 static int make_plan(const cur_her_args& a, HerPlan* p) {
   const cur_layout& L = a.L;
-  p->img_floats = L.row_stride + L.next_prefix;
-  p->fut_off = p->img_floats;
-  p->fut_len = round_up4(L.dimag);
-  p->stage_stride = p->img_floats + p->fut_len;
-  p->dimg_pad = round_up4(L.dimg);
   const bool need_ag_t = (a.ag != nullptr) || a.relative_goals;
-  const bool need_tail = (a.change != nullptr && L.dimchange > 0) || (a.info != nullptr && L.diminfo > 0);
-  const int start = need_ag_t ? 0 : L.off_o;
-  if (need_tail) {
-    p->c1_off = start;
-    p->c1_len = p->img_floats - start;
-    p->c2_off = 0;
-    p->c2_len = 0;
-  } else {
-    p->c1_off = start;
-    p->c1_len = L.off_change - start;
-    p->c2_off = L.row_stride;
-    p->c2_len = L.next_prefix;
-    if (p->c1_off + p->c1_len == p->c2_off) {  // nothing to skip: merge
-      p->c1_len += p->c2_len;
-      p->c2_len = 0;
-    }
-  }
+  const bool need_cold = (a.change != nullptr && L.dimchange > 0) || (a.info != nullptr && L.diminfo > 0);
+  p->img_off = need_ag_t ? L.off_ag : L.off_o;
+  p->i0 = L.row_stride - p->img_off;
+  p->img4 = (p->i0 + L.row_stride) / 4;
+  p->fut_off = p->i0 + L.row_stride;
+  p->fut4 = round_up4(L.dimag) / 4;
+  p->cold_off = p->fut_off + 4 * p->fut4;
+  p->cold4 = need_cold ? L.cold_stride / 4 : 0;
+  p->stage_stride = p->cold_off + 4 * p->cold4;
+  p->dimg_pad = round_up4(L.dimg);
   return CUR_OK;
 }
 
@@ -470,24 +457,26 @@ extern "C" int cur_layout_init(cur_layout* L, int T, int dimo, int dimag, int di
   L->dimo = dimo; L->dimag = dimag; L->dimg = dimg; L->dimu = dimu;
   L->dimtd = dimtd; L->dimchange = dimchange; L->diminfo = diminfo;
   int off = 0;
-  L->off_ag = off; off += round_up4(dimag);
-  L->off_o = off; off += round_up4(dimo);
-  L->next_prefix = off;
   L->off_g = off; off += round_up4(dimg);
   L->off_u = off; off += round_up4(dimu);
   L->off_td = off; off += round_up4(dimtd);
+  L->off_ag = off; off += round_up4(dimag);
+  L->off_o = off; off += round_up4(dimo);
+  L->row_stride = off;
+  off = 0;
   L->off_change = off; off += round_up4(dimchange);
   L->off_info = off; off += round_up4(diminfo);
-  L->row_stride = off;
+  L->cold_stride = off;
   return CUR_OK;
 }
 
 extern "C" int cur_store_episodes(void* stream, const cur_layout* L, const cur_episode_src* src, int n_ep,
-                                  int n_copies, const int32_t* copy_src, float* const* copy_base,
-                                  const int64_t* copy_slot) {
-  CUR_REQUIRE(L && src && copy_src && copy_base && copy_slot, "NULL argument");
+                                  int n_copies, const int32_t* copy_src, float* const* copy_hot,
+                                  float* const* copy_cold, const int64_t* copy_slot) {
+  CUR_REQUIRE(L && src && copy_src && copy_hot && copy_slot, "NULL argument");
   CUR_REQUIRE(src->o && src->ag && src->g && src->u, "o/ag/g/u sources are required");
   CUR_REQUIRE(n_copies >= 0 && n_ep > 0, "bad counts");
+  CUR_REQUIRE(L->cold_stride == 0 || copy_cold != nullptr, "cold destinations required");
   cudaStream_t s = (cudaStream_t)stream;
   for (int done = 0; done < n_copies; done += CUR_MAX_COPIES) {
     StoreParams S;
@@ -496,9 +485,10 @@ extern "C" int cur_store_episodes(void* stream, const cur_layout* L, const cur_e
     S.n_copies = (n_copies - done < CUR_MAX_COPIES) ? n_copies - done : CUR_MAX_COPIES;
     for (int i = 0; i < S.n_copies; ++i) {
       CUR_REQUIRE(copy_src[done + i] >= 0 && copy_src[done + i] < n_ep, "copy_src out of range");
-      CUR_REQUIRE(copy_base[done + i] != nullptr && copy_slot[done + i] >= 0, "bad destination");
+      CUR_REQUIRE(copy_hot[done + i] != nullptr && copy_slot[done + i] >= 0, "bad destination");
       S.copy_src[i] = copy_src[done + i];
-      S.copy_base[i] = copy_base[done + i];
+      S.copy_hot[i] = copy_hot[done + i];
+      S.copy_cold[i] = copy_cold ? copy_cold[done + i] : nullptr;
       S.copy_slot[i] = copy_slot[done + i];
     }
     dim3 grid(L->T + 1, S.n_copies);
@@ -543,9 +533,10 @@ extern "C" int cur_her_sample(void* stream, const cur_her_args* args) {
   HerKernelParams P;
   P.a = a;
   make_plan(a, &P.p);
-  const int n_maps = (a.mode == CUR_MODE_FLAT) ? 1 : a.tasks.n_tasks;
-  size_t smem = (size_t)TILE * P.p.stage_stride * 4 + (size_t)TILE * P.p.dimg_pad * 4 + TILE * 4 +
-                3 * TILE * 4 + (size_t)n_maps * P.p.dimg_pad * 2 + 16 + 16;
+  if (P.p.cold4 > 0)
+    for (int i = 0; i < a.n_segments; ++i)
+      CUR_REQUIRE(a.seg[i].count == 0 || a.seg[i].cold != nullptr, "change/info requested but segment has no cold rows");
+  size_t smem = (size_t)TILE * P.p.stage_stride * 4 + 3 * TILE * sizeof(void*) + 3 * TILE * 4 + 16;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     CUR_REQUIRE(smem <= 227 * 1024, "row too large for the shared-memory stage");

@@ -31,8 +31,8 @@ class DeviceEpisodes:
     """What ReplayBuffer.sample passes to the sampler instead of the reference's dict of views
     (replay_buffer.py:44-48): the packed device buffer and how many episodes are valid."""
 
-    def __init__(self, storage, n_episodes, layout, info_keys, has_td, has_change):
-        self.storage, self.n_episodes, self.layout = storage, n_episodes, layout
+    def __init__(self, storage, cold, n_episodes, layout, info_keys, has_td, has_change):
+        self.storage, self.cold, self.n_episodes, self.layout = storage, cold, n_episodes, layout
         self.info_keys, self.has_td, self.has_change = info_keys, has_td, has_change
 
 
@@ -153,6 +153,7 @@ class HerSampler:
             if count > 0 and epi.n_episodes <= 0:
                 raise AssertionError('sampling from an empty buffer')      # replay_buffer.py:43
             a.seg[i].base = epi.storage.data_ptr()
+            a.seg[i].cold = None if epi.cold is None else epi.cold.data_ptr()
             a.seg[i].n_episodes = int(epi.n_episodes)
             a.seg[i].count = int(count)
             a.seg[i].task_to_replay = -1 if ttr is None else int(ttr)

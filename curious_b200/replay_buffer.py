@@ -1,9 +1,10 @@
 """Device-resident replay buffer - drop-in for reference baselines/her/replay_buffer.py:6-109.
 
-Storage is ONE float32 CUDA tensor of packed per-timestep rows (layout in include/curious_b200.h,
-`cur_layout`) instead of the reference's dict of float64 host arrays (replay_buffer.py:23-24).
-Everything the reference stores is float32-representable (rollout.py:50-52,194-195 build float32
-episodes; `change` is bool), so no information is lost; inputs that are not are rounded to float32.
+Storage is two float32 CUDA tensors of packed per-timestep rows (layout in include/curious_b200.h,
+`cur_layout`: "hot" rows [g|u|task_descr|ag|o] and "cold" rows [change|info]) instead of the
+reference's dict of float64 host arrays (replay_buffer.py:23-24).  Everything the reference stores is
+float32-representable (rollout.py:50-52,194-195 build float32 episodes; `change` is bool), so no
+information is lost; inputs that are not are rounded to float32.
 
 Slot selection (_get_storage_idx, replay_buffer.py:90-109) stays on the host and consumes the global
 np.random stream exactly like the reference, so a seeded run overwrites the same slots.
@@ -21,7 +22,7 @@ BASE_KEYS = ('o', 'ag', 'g', 'u')
 
 
 def split_keys(shapes_or_batch):
-    """Classify keys: returns (has_td, has_change, [(info_key, dim), ...] sorted)."""
+    """Classify keys: returns (has_td, has_change, [info keys] sorted)."""
     keys = list(shapes_or_batch.keys())
     info = sorted(k for k in keys if k.startswith('info_'))
     known = set(BASE_KEYS) | {'task_descr', 'change', 'o_2', 'ag_2'} | set(info)
@@ -44,6 +45,15 @@ def layout_from_shapes(buffer_shapes):
                          buffer_shapes['u'][-1], buffer_shapes['task_descr'][-1] if has_td else 0,
                          buffer_shapes['change'][-1] if has_change else 0, sum(d for _, d in info_keys))
     return L, info_keys, has_td, has_change
+
+
+def alloc_storage(layout, n_episodes, device):
+    """(hot, cold) tensors for `n_episodes` episodes; cold is None when there is no change/info."""
+    hot = torch.empty(n_episodes * (layout.T + 1) * layout.row_stride, dtype=torch.float32, device=device)
+    cold = None
+    if layout.cold_stride > 0:
+        cold = torch.empty(n_episodes * layout.T * layout.cold_stride, dtype=torch.float32, device=device)
+    return hot, cold
 
 
 class StagedEpisodes:
@@ -106,15 +116,16 @@ class StagedEpisodes:
         return self
 
     def store(self, copies, stream=None):
-        """copies: list of (src_episode, storage_tensor, slot)."""
+        """copies: list of (src_episode, hot_tensor, cold_tensor_or_None, slot)."""
         n = len(copies)
         if n == 0:
             return
         src = (C.c_int32 * n)(*[int(c[0]) for c in copies])
-        base = (C.c_void_p * n)(*[c[1].data_ptr() for c in copies])
-        slot = (C.c_int64 * n)(*[int(c[2]) for c in copies])
+        hot = (C.c_void_p * n)(*[c[1].data_ptr() for c in copies])
+        cold = (C.c_void_p * n)(*[None if c[2] is None else c[2].data_ptr() for c in copies])
+        slot = (C.c_int64 * n)(*[int(c[3]) for c in copies])
         _lib.check(_lib.load().cur_store_episodes(_lib.stream_ptr(stream), C.byref(self.layout),
-                                                  C.byref(self.src), self.n, n, src, base, slot),
+                                                  C.byref(self.src), self.n, n, src, hot, cold, slot),
                    'cur_store_episodes')
 
 
@@ -128,14 +139,14 @@ def episodes_to_device(episode_batch, device=None):
     """Pack a host episode batch {key: [n, T(+1), dim]} into a temporary device buffer and return the
     DeviceEpisodes view the sampler consumes (used for the normaliser path, ddpg.py:209-215)."""
     device = device or default_device()
-    shapes = {k: np.asarray(v).shape[1:] for k, v in episode_batch.items() if k not in ('o_2', 'ag_2')}
+    batch = {k: v for k, v in episode_batch.items() if k not in ('o_2', 'ag_2')}
+    shapes = {k: np.asarray(v).shape[1:] for k, v in batch.items()}
     L, info_keys, has_td, has_change = layout_from_shapes(shapes)
-    n = len(episode_batch['u'])
-    storage = torch.empty(n * (L.T + 1) * L.row_stride, dtype=torch.float32, device=device)
-    staged = StagedEpisodes({k: v for k, v in episode_batch.items() if k not in ('o_2', 'ag_2')},
-                            L, info_keys, has_td, has_change, device)
-    staged.store([(e, storage, e) for e in range(n)])
-    epi = DeviceEpisodes(storage, n, L, info_keys, has_td, has_change)
+    n = len(batch['u'])
+    hot, cold = alloc_storage(L, n, device)
+    staged = StagedEpisodes(batch, L, info_keys, has_td, has_change, device)
+    staged.store([(e, hot, cold, e) for e in range(n)])
+    epi = DeviceEpisodes(hot, cold, n, L, info_keys, has_td, has_change)
     epi._staged = staged
     return epi
 
@@ -150,8 +161,7 @@ class ReplayBuffer:
         self.device = device or default_device()
         self.layout, self.info_keys, self.has_td, self.has_change = layout_from_shapes(buffer_shapes)
         assert self.layout.T == T
-        self.storage = torch.empty(self.size * (T + 1) * self.layout.row_stride, dtype=torch.float32,
-                                   device=self.device)
+        self.storage, self.cold = alloc_storage(self.layout, self.size, self.device)
         self.current_size = 0
         self.n_transitions_stored = 0
         self.lock = threading.Lock()
@@ -162,8 +172,8 @@ class ReplayBuffer:
             return self.current_size == self.size
 
     def device_view(self):
-        return DeviceEpisodes(self.storage, self.current_size, self.layout, self.info_keys, self.has_td,
-                              self.has_change)
+        return DeviceEpisodes(self.storage, self.cold, self.current_size, self.layout, self.info_keys,
+                              self.has_td, self.has_change)
 
     def sample(self, batch_size, task_to_replay=None, cp_proba=None):
         """Returns a dict {key: array(batch_size x shapes[key])} (replay_buffer.py:37-55)."""
@@ -185,17 +195,18 @@ class ReplayBuffer:
             idxs = np.atleast_1d(self._get_storage_idx(batch_size))
             staged = StagedEpisodes({k: episode_batch[k] for k in self.buffer_shapes.keys()}, self.layout,
                                     self.info_keys, self.has_td, self.has_change, self.device)
-            staged.store([(e, self.storage, int(idxs[e])) for e in range(batch_size)])
+            staged.store([(e, self.storage, self.cold, int(idxs[e])) for e in range(batch_size)])
             self._last_staged = staged       # keep the pinned/device blobs alive until the copy ran
             self.n_transitions_stored += batch_size * self.T
 
     def store_staged(self, staged, src_episode):
-        """Store episode `src_episode` of an already uploaded batch (DDPG.store_episode duplicates one
-        episode into several module buffers, ddpg.py:194-195, with a single upload)."""
+        """Reserve a slot for episode `src_episode` of an already uploaded batch and return the copy
+        descriptor (DDPG.store_episode duplicates one episode into several module buffers,
+        ddpg.py:194-195, with a single upload and a single kernel launch)."""
         with self.lock:
             idx = self._get_storage_idx(1)
             self.n_transitions_stored += self.T
-        return (src_episode, self.storage, int(idx))
+        return (src_episode, self.storage, self.cold, int(idx))
 
     def get_current_episode_size(self):
         with self.lock:
@@ -236,13 +247,16 @@ class ReplayBuffer:
         L, T = self.layout, self.T
         rows = self.storage.view(self.size, T + 1, L.row_stride).cpu().numpy().astype(np.float64)
         out = {'o': rows[:, :, L.off_o:L.off_o + L.dimo], 'ag': rows[:, :, L.off_ag:L.off_ag + L.dimag],
-               'g': rows[:, :T, L.off_g:L.off_g + L.dimg], 'u': rows[:, :T, L.off_u:L.off_u + L.dimu]}
+               # g/u/task_descr of step t are stored in hot row t+1 (shifted layout)
+               'g': rows[:, 1:, L.off_g:L.off_g + L.dimg], 'u': rows[:, 1:, L.off_u:L.off_u + L.dimu]}
         if self.has_td:
-            out['task_descr'] = rows[:, :T, L.off_td:L.off_td + L.dimtd]
-        if self.has_change:
-            out['change'] = rows[:, :T, L.off_change:L.off_change + L.dimchange]
-        k0 = L.off_info
-        for key, d in self.info_keys:
-            out[key] = rows[:, :T, k0:k0 + d]
-            k0 += d
+            out['task_descr'] = rows[:, 1:, L.off_td:L.off_td + L.dimtd]
+        if self.cold is not None:
+            cold = self.cold.view(self.size, T, L.cold_stride).cpu().numpy().astype(np.float64)
+            if self.has_change:
+                out['change'] = cold[:, :, L.off_change:L.off_change + L.dimchange]
+            k0 = L.off_info
+            for key, d in self.info_keys:
+                out[key] = cold[:, :, k0:k0 + d]
+                k0 += d
         return out

@@ -39,18 +39,24 @@ int cur_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ------------------------------------------------------------------------------------------
  * Replay storage layout.  Replaces the float64 dict-of-arrays storage of
- * baselines/her/replay_buffer.py:23-24 by ONE float32 array per buffer made of packed
- * per-timestep rows   [ ag | o | g | u | task_descr | change | info ]   (each section padded to a
- * multiple of 4 floats, so every section of every row is 16-byte aligned).  An episode is T+1
- * consecutive rows (row T carries only ag,o).  (o_2, ag_2) of step t are the head of row t+1, so a
- * transition is one contiguous read.
+ * baselines/her/replay_buffer.py:23-24 by TWO float32 arrays per buffer:
+ *
+ *   hot  [E][T+1][row_stride]   row r = [ g(r-1) | u(r-1) | task_descr(r-1) | ag(r) | o(r) ]
+ *   cold [E][T][cold_stride]    row t = [ change(t) | info(t) ]
+ *
+ * Sections are padded to multiples of 4 floats (16-byte aligned).  The per-step arrays g/u/task_descr
+ * are stored SHIFTED by one row (row 0 holds zeros there), so everything a training transition
+ * (o_t, g_t, u_t, td_t, o_{t+1}, ag_{t+1}) needs is ONE contiguous span: the tail [o] of row t
+ * followed by the whole row t+1.  `change`/`info` are only read by the API-parity sampler and the
+ * store-time routing; keeping them out of the hot rows keeps that span free of dead bytes.
  * ------------------------------------------------------------------------------------------ */
 typedef struct cur_layout {
   int32_t T;
   int32_t dimo, dimag, dimg, dimu, dimtd, dimchange, diminfo;
-  int32_t off_ag, off_o, off_g, off_u, off_td, off_change, off_info; /* floats */
-  int32_t row_stride;  /* floats per row, multiple of 4                                   */
-  int32_t next_prefix; /* floats of row t+1 holding [ag|o] (== off_g)                     */
+  int32_t off_g, off_u, off_td, off_ag, off_o; /* floats, inside a hot row  */
+  int32_t row_stride;                          /* floats per hot row, multiple of 4 */
+  int32_t off_change, off_info;                /* floats, inside a cold row */
+  int32_t cold_stride;                         /* floats per cold row (0 if no change/info) */
 } cur_layout;
 
 /* Fills offsets/strides.  dimtd/dimchange/diminfo may be 0 (flat structure). */
@@ -61,7 +67,7 @@ int cur_layout_init(cur_layout* L, int T, int dimo, int dimag, int dimg, int dim
  * cur_store_episodes - ReplayBuffer.store_episode (replay_buffer.py:57-72) + the per-module
  * duplication of DDPG.store_episode (ddpg.py:187-197).  Packs `n_ep` episodes given as key-major
  * float32 device arrays ([n_ep,T+1,dimo], [n_ep,T+1,dimag], [n_ep,T,dim*]...) into rows and writes
- * copy i of episode copy_src[i] to slot copy_slot[i] of the buffer at copy_base[i].
+ * copy i of episode copy_src[i] to slot copy_slot[i] of the buffer (copy_hot[i], copy_cold[i]).
  * Slot choice (_get_storage_idx, replay_buffer.py:90-109) stays on the host: it consumes the
  * caller's np.random stream.  copy_* are HOST arrays of length n_copies <= CUR_MAX_COPIES.
  * ------------------------------------------------------------------------------------------ */
@@ -76,7 +82,8 @@ typedef struct cur_episode_src {
 } cur_episode_src;
 
 int cur_store_episodes(void* stream, const cur_layout* L, const cur_episode_src* src, int n_ep,
-                       int n_copies, const int32_t* copy_src, float* const* copy_base,
+                       int n_copies, const int32_t* copy_src, float* const* copy_hot,
+                       float* const* copy_cold /* entries may be NULL when cold_stride == 0 */,
                        const int64_t* copy_slot);
 
 /* ------------------------------------------------------------------------------------------
@@ -105,7 +112,8 @@ enum {
 };
 
 typedef struct cur_segment {
-  const float* base;      /* packed buffer                                                   */
+  const float* base;      /* hot rows of the buffer                                          */
+  const float* cold;      /* cold rows (needed only when change/info outputs are requested)  */
   int32_t n_episodes;     /* current_size: episodes are drawn from [0, n_episodes)            */
   int32_t count;          /* rows sampled from this buffer (proportions[i], ddpg.py:326-336)  */
   int32_t task_to_replay; /* module forced on HER rows, or -1 for None                        */

@@ -213,5 +213,6 @@ def test_full_size_properties():
     # the row's ag_2 equals it; check the gather itself on a sample of rows instead
     host = buf.storage.view(buf.size, T + 1, buf.layout.row_stride)
     sel = np.where(her_rows)[0][:4096]
-    fut = host[torch.from_numpy(ep[sel]).long().cuda(), torch.from_numpy(ft[sel]).long().cuda()][:, :dims['ag']]
+    L = buf.layout
+    fut = host[torch.from_numpy(ep[sel]).long().cuda(), torch.from_numpy(ft[sel]).long().cuda()][:, L.off_ag:L.off_ag + dims['ag']]
     assert torch.equal(a['g'][torch.from_numpy(sel).cuda()][:, g_ids[2]], fut[:, ag_ids[2]])

@@ -42,10 +42,10 @@ def test_ctypes_structs_match_header(tmp_path):
 def test_layout_and_param_counts_without_gpu():
     from curious_b200 import _lib
     L = _lib.make_layout(50, 40, 12, 12, 4, 4, 12, 1)
-    assert (L.off_ag, L.off_o, L.off_g, L.off_u, L.off_td, L.off_change, L.off_info) == (0, 12, 52, 64, 68, 72, 84)
-    assert L.row_stride == 88 and L.next_prefix == 52
-    L = _lib.make_layout(10, 25, 3, 3, 4)          # unaligned dims get padded sections
-    assert L.off_o == 4 and L.off_g == 32 and L.row_stride % 4 == 0
+    assert (L.off_g, L.off_u, L.off_td, L.off_ag, L.off_o, L.row_stride) == (0, 12, 16, 20, 32, 72)
+    assert (L.off_change, L.off_info, L.cold_stride) == (0, 12, 16)
+    L = _lib.make_layout(10, 25, 3, 3, 4)          # unaligned dims get padded sections; flat: no cold rows
+    assert (L.off_g, L.off_u, L.off_td, L.off_ag, L.off_o, L.row_stride, L.cold_stride) == (0, 4, 8, 8, 12, 40, 0)
     lib = _lib.load()
     d = _lib.NetDesc(1, 40, 12, 4, 4, 256, 3, 1.0, 0, 5.0)
     assert lib.cur_net_param_count(C.byref(d), 0) == 147457
