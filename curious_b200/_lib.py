@@ -46,6 +46,11 @@ class TaskTable(C.Structure):
                 ('cdf', C.c_double * CUR_MAX_TASKS)]
 
 
+class HerDyn(C.Structure):
+    _fields_ = [('step', C.c_void_p), ('n_episodes', C.c_int32 * CUR_MAX_SEGMENTS),
+                ('count', C.c_int32 * CUR_MAX_SEGMENTS), ('cdf', C.c_double * CUR_MAX_TASKS)]
+
+
 class HerArgs(C.Structure):
     _fields_ = [('L', Layout), ('tasks', TaskTable), ('mode', C.c_int32), ('n_segments', C.c_int32),
                 ('seg', Segment * CUR_MAX_SEGMENTS), ('batch', C.c_int64), ('future_p', C.c_double),
@@ -55,7 +60,8 @@ class HerArgs(C.Structure):
                 ('clip_obs', C.c_float), ('relative_goals', C.c_int32),
                 ('o', C.c_void_p), ('ag', C.c_void_p), ('g', C.c_void_p), ('u', C.c_void_p),
                 ('td', C.c_void_p), ('change', C.c_void_p), ('info', C.c_void_p), ('o_2', C.c_void_p),
-                ('ag_2', C.c_void_p), ('g_2', C.c_void_p), ('r', C.c_void_p), ('idx_out', C.c_void_p)]
+                ('ag_2', C.c_void_p), ('g_2', C.c_void_p), ('r', C.c_void_p), ('idx_out', C.c_void_p),
+                ('dyn', C.c_void_p)]
 
 
 class NetDesc(C.Structure):
@@ -74,7 +80,8 @@ class Batch(C.Structure):
 
 class DdpgHyper(C.Structure):
     _fields_ = [('gamma', C.c_float), ('clip_return', C.c_float), ('action_l2', C.c_float),
-                ('clip_pos_returns', C.c_int32)]
+                ('clip_pos_returns', C.c_int32), ('step_counter', C.c_void_p), ('loss_ring', C.c_int32),
+                ('_pad', C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/curious_b200.h declares

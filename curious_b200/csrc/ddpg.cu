@@ -204,6 +204,8 @@ struct LossParams {
   float gamma, clip_return, action_l2;
   int clip_pos;
   float *dQ, *dQpi, *q_loss, *pi_loss;
+  int64_t* step_counter;   // optional: losses go to slot (*step % ring), then *step += 1
+  int ring;
 };
 
 __global__ void __launch_bounds__(1024) loss_kernel(const __grid_constant__ LossParams P) {
@@ -243,8 +245,14 @@ __global__ void __launch_bounds__(1024) loss_kernel(const __grid_constant__ Loss
       sth += __shfl_xor_sync(0xffffffffu, sth, o);
     }
     if (l == 0) {
-      if (P.q_loss) *P.q_loss = ssq * inv_n;                                           // ddpg.py:439
-      if (P.pi_loss) *P.pi_loss = -sq * inv_n + P.action_l2 * sth / (float)(P.n * P.dimu);   // :440-441
+      long long slot = 0;
+      if (P.step_counter) {
+        const long long st = *P.step_counter;
+        slot = P.ring > 0 ? st % P.ring : 0;
+        *P.step_counter = st + 1;
+      }
+      if (P.q_loss) P.q_loss[slot] = ssq * inv_n;                                           // ddpg.py:439
+      if (P.pi_loss) P.pi_loss[slot] = -sq * inv_n + P.action_l2 * sth / (float)(P.n * P.dimu);   // :440-441
     }
   }
 }
@@ -476,6 +484,7 @@ extern "C" int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* 
   LPm.r = batch->r; LPm.Q = w.Q; LPm.Qpi = q_pi; LPm.Qt = w.Qt; LPm.th = th; LPm.ldth = w.ld_sq; LPm.dimu = d->dimu;
   LPm.n = n; LPm.gamma = h->gamma; LPm.clip_return = h->clip_return; LPm.action_l2 = h->action_l2;
   LPm.clip_pos = h->clip_pos_returns; LPm.dQ = w.dQ; LPm.dQpi = w.dQpi; LPm.q_loss = q_loss; LPm.pi_loss = pi_loss;
+  LPm.step_counter = h->step_counter; LPm.ring = h->loss_ring;
   loss_kernel<<<1, 1024, 0, s>>>(LPm);
   CUR_CHECK_LAUNCH();
 

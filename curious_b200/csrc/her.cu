@@ -157,15 +157,20 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
       const int64_t j = j0 + lane;
       const int64_t c = a.perm ? (int64_t)a.perm[j] : j;
       // segment lookup: concat rows are the segments' counts laid end to end (ddpg.py:326-345)
+      // (with a device control block - CUDA-graph replays - counts / sizes / counter come from memory)
+      const cur_her_dyn* dyn = a.dyn;
       int s = 0;
       int64_t acc = 0;
-      while (s + 1 < a.n_segments && c >= acc + a.seg[s].count) {
-        acc += a.seg[s].count;
+      while (s + 1 < a.n_segments) {
+        const int cnt = dyn ? dyn->count[s] : a.seg[s].count;
+        if (c < acc + cnt) break;
+        acc += cnt;
         ++s;
       }
       const float* base = a.seg[s].base;
-      const int E = a.seg[s].n_episodes;
+      const int E = dyn ? dyn->n_episodes[s] : a.seg[s].n_episodes;
       my_ttr = a.seg[s].task_to_replay;
+      const uint64_t call_offset = a.call_offset + (dyn ? (uint64_t)*dyn->step : 0ull);
       double u_her, u_off;
       if (a.inj_ep != nullptr) {
         my_ep = a.inj_ep[c];
@@ -174,16 +179,16 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
         u_off = a.inj_u_off[c];
         if (a.inj_choice) my_choice = a.inj_choice[c];
       } else {
-        Philox x = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)a.call_offset,
-                                 (uint32_t)(a.call_offset >> 32), (uint32_t)a.seed,
+        Philox x = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)call_offset,
+                                 (uint32_t)(call_offset >> 32), (uint32_t)a.seed,
                                  (uint32_t)(a.seed >> 32));
         my_ep = (int)mulhi32(x.x[0], (uint32_t)E);
         my_t = (int)mulhi32(x.x[1], (uint32_t)L.T);
         u_her = u01_from_u32(x.x[2]);
         u_off = u01_from_u32(x.x[3]);
         if (a.mode == CUR_MODE_RANDOM_TASK || a.mode == CUR_MODE_CP_TASK) {
-          Philox y = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)a.call_offset,
-                                   (uint32_t)(a.call_offset >> 32) ^ 0x80000000u, (uint32_t)a.seed,
+          Philox y = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)call_offset,
+                                   (uint32_t)(call_offset >> 32) ^ 0x80000000u, (uint32_t)a.seed,
                                    (uint32_t)(a.seed >> 32));
           if (a.mode == CUR_MODE_RANDOM_TASK) {
             my_choice = (int)mulhi32(y.x[0], (uint32_t)a.tasks.n_tasks);
@@ -191,7 +196,7 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
             // np.random.choice(p=): cdf.searchsorted(u, side='right')
             double u = u01_from_u32(y.x[0]);
             int k = 0;
-            while (k < a.tasks.n_tasks - 1 && a.tasks.cdf[k] <= u) ++k;
+            while (k < a.tasks.n_tasks - 1 && (dyn ? dyn->cdf[k] : a.tasks.cdf[k]) <= u) ++k;
             my_choice = k;
           }
         }
@@ -511,14 +516,17 @@ extern "C" int cur_her_sample(void* stream, const cur_her_args* args) {
   int64_t total = 0;
   for (int i = 0; i < a.n_segments; ++i) {
     CUR_REQUIRE(a.seg[i].count >= 0, "negative segment count");
-    if (a.seg[i].count > 0) {
+    if (a.dyn != nullptr) {
+      CUR_REQUIRE(a.seg[i].base != nullptr, "segment base is NULL");
+    } else if (a.seg[i].count > 0) {
       CUR_REQUIRE(a.seg[i].base != nullptr, "segment base is NULL");
       CUR_REQUIRE(a.seg[i].n_episodes > 0, "sampling from an empty buffer (replay_buffer.py:43)");
       CUR_REQUIRE(a.seg[i].task_to_replay < a.tasks.n_tasks, "task_to_replay out of range");
     }
     total += a.seg[i].count;
   }
-  CUR_REQUIRE(total == a.batch, "segment counts must sum to batch (ddpg.py:323)");
+  CUR_REQUIRE(a.dyn != nullptr || total == a.batch, "segment counts must sum to batch (ddpg.py:323)");
+  CUR_REQUIRE(a.dyn == nullptr || a.inj_ep == nullptr, "a device control block implies Philox draws");
   for (int m = 0; m < a.tasks.n_tasks; ++m) {
     CUR_REQUIRE(a.tasks.len[m] >= 0 && a.tasks.len[m] <= CUR_MAX_SLICE, "module slice too long");
     for (int k = 0; k < a.tasks.len[m]; ++k) {

@@ -133,11 +133,12 @@ template <bool kTable>
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
             float* __restrict__ v, int64_t n, float neg_a, const float* __restrict__ table, int table_len,
-            const int32_t* __restrict__ step_counter, float b1, float omb1, float b2, float omb2, float eps,
+            const int64_t* __restrict__ step_counter, float b1, float omb1, float b2, float omb2, float eps,
             float grad_div) {
   if (kTable) {
-    int t = *step_counter;
-    neg_a = table[t < table_len ? t : table_len - 1];
+    long long t = *step_counter;                 // 1-based: already bumped for this step
+    if (t < 1) t = 1;
+    neg_a = table[(t <= table_len ? t : (long long)table_len) - 1];
   }
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -163,8 +164,6 @@ adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __
     theta[i] = T; m[i] = M; v[i] = V;
   }
 }
-
-__global__ void adam_counter_bump(int32_t* c) { *c += 1; }
 
 __global__ void __launch_bounds__(256)
 polyak_kernel(float* __restrict__ target, const float* __restrict__ main_, int64_t n, float p, float omp) {
@@ -262,8 +261,9 @@ extern "C" int cur_adam_step(void* stream, float* theta, const float* grad, floa
 }
 
 extern "C" int cur_adam_step_graph(void* stream, float* theta, const float* grad, float* m, float* v,
-                                   int64_t n, const float* neg_a_table, int table_len, int32_t* step_counter,
-                                   double beta1, double beta2, double eps, float grad_div) {
+                                   int64_t n, const float* neg_a_table, int table_len,
+                                   const int64_t* step_counter, double beta1, double beta2, double eps,
+                                   float grad_div) {
   CUR_REQUIRE(theta && grad && m && v && neg_a_table && step_counter, "NULL argument");
   CUR_REQUIRE(n >= 0 && table_len > 0, "bad sizes");
   if (n == 0) return CUR_OK;
@@ -273,8 +273,6 @@ extern "C" int cur_adam_step_graph(void* stream, float* theta, const float* grad
   adam_kernel<true><<<grid_for(n / 4 + 1, 256, 2), 256, 0, (cudaStream_t)stream>>>(
       theta, grad, m, v, n, 0.f, neg_a_table, table_len, step_counter, (float)beta1, omb1, (float)beta2, omb2,
       (float)eps, grad_div);
-  CUR_CHECK_LAUNCH();
-  adam_counter_bump<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter);
   CUR_CHECK_LAUNCH();
   return CUR_OK;
 }

@@ -30,6 +30,19 @@ from .replay_buffer import StagedEpisodes, episodes_to_device
 from .util import LazyHost, dims_to_shapes, import_function, store_args, transitions_in_episode_batch
 
 
+_ADAM_TABLES = {}
+
+
+def _adam_table(lr, beta1, beta2, n):
+    """float32(-a_t) for t = 1..n with a_t evaluated exactly like MpiAdam.update does it on the host
+    (python float pow, mpi_adam.py:31), so the graph path and the eager path step identically."""
+    key = (float(lr), float(beta1), float(beta2), int(n))
+    if key not in _ADAM_TABLES:
+        _ADAM_TABLES[key] = np.array([np.float32(-adam_step_scale(lr, beta1, beta2, t)) for t in range(1, n + 1)],
+                                     np.float32)
+    return _ADAM_TABLES[key]
+
+
 class DDPG(object):
     @store_args
     def __init__(self, input_dims, hidden, layers, network_class, polyak, batch_size,
@@ -45,6 +58,7 @@ class DDPG(object):
         self.comm = kwargs.get('comm')
         self.her_rng = kwargs.get('her_rng', 'philox')
         self.seed = kwargs.get('seed', 0)
+        self.use_cuda_graph = kwargs.get('use_cuda_graph', True)
         self.create_actor_critic = import_function(self.network_class)
 
         self.dimo = self.input_dims['o']
@@ -114,6 +128,11 @@ class DDPG(object):
         self._q_loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self._pi_loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self._batch = None
+        # shared device train-step counter (Philox counter of the HER kernel, Adam's t, loss ring slot)
+        self._step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._n_updates = 0
+        self._graph = None
+        self._graph_sig = None
 
     def _view(self, arena, which):
         net = self.net
@@ -386,12 +405,150 @@ class DDPG(object):
                                          float(np.float32(-a)), adam.beta1, adam.beta2, adam.epsilon, 1.0),
                        'cur_adam_step')
 
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph fast path: HER sample -> grads -> all-reduce -> Adam captured once, replayed per update.
+    # Everything that changes between updates lives in device memory (cur_her_dyn control block, the
+    # shared step counter, the Adam step-scale table), so the frozen kernel arguments stay valid.
+    LOSS_RING = 4096
+    ADAM_TABLE = 65536
+    GRAPH_STREAM_OFFSET = 1 << 40          # Philox call_offset base of the train-step stream
+
+    def _all_segments(self):
+        """Fixed segment table over every buffer (count 0 where nothing is sampled)."""
+        if self.modular and self._multi_buffer():
+            segs = []
+            for i in range(self.nb_tasks + 1):
+                ttr = (i - 1 if i > 0 else None) if self.structure == 'curious' else self.t_id
+                segs.append((self.buffer[i], ttr))
+            return segs
+        return [(self.buffer, None)]
+
+    def _dyn_signature(self):
+        segs = self._all_segments()
+        cp = None if self.cp is None else tuple(np.asarray(self.cp, np.float64).tolist())
+        return tuple(b.current_size for b, _ in segs), cp
+
+    def _refresh_dyn(self):
+        """Recompute the LP apportioning (ddpg.py:255-318) and push it to the device control block."""
+        sig = self._dyn_signature()
+        if sig == self._graph_sig:
+            return
+        segs = self._all_segments()
+        d = self._dyn_struct
+        if self.modular and self._multi_buffer():
+            prop = self._proportions()
+        else:
+            assert self.buffer.current_size > 0
+            prop = [self.batch_size]
+            if self.modular and self.structure == 'curious' and self.task_replay == 'replay_cp_task_transition':
+                _lib.set_cdf(d, apportion.cp_probabilities(self.cp, self.eps_task))
+            elif self.sample_transitions.mode == _lib.MODE_CP_TASK:
+                _lib.set_cdf(d, np.ones(self.nb_tasks) / self.nb_tasks)
+        for i, (buf, _) in enumerate(segs):
+            d.n_episodes[i] = int(buf.current_size)
+            d.count[i] = int(prop[i])
+        C.memmove(self._dyn_host.data_ptr(), C.addressof(d), C.sizeof(d))
+        self._dyn_dev.copy_(self._dyn_host, non_blocking=True)
+        self._graph_sig = sig
+
+    def _build_graph(self):
+        dev = self.device
+        B = self.batch_size
+        L = self._all_segments()[0][0].layout
+        self._dyn_struct = _lib.HerDyn()
+        self._dyn_struct.step = self._step.data_ptr()
+        nbytes = C.sizeof(_lib.HerDyn)
+        self._dyn_host = torch.zeros(nbytes, dtype=torch.uint8, pin_memory=True)
+        self._dyn_dev = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self._q_ring = torch.zeros(self.LOSS_RING, dtype=torch.float32, device=dev)
+        self._pi_ring = torch.zeros(self.LOSS_RING, dtype=torch.float32, device=dev)
+        self._q_pi = torch.zeros((B, 1), dtype=torch.float32, device=dev)
+        self._adam_tables = [torch.from_numpy(_adam_table(lr, adam.beta1, adam.beta2, self.ADAM_TABLE)).to(dev)
+                             for adam, lr in ((self.Q_adam, self.Q_lr), (self.pi_adam, self.pi_lr))]
+        dims = dict(o=L.dimo, g=L.dimg, u=L.dimu, td=L.dimtd, o_2=L.dimo, r=1)
+        want = [k for k in ('o', 'g', 'u', 'td', 'o_2', 'r') if dims[k] > 0]
+        if self.relative_goals:
+            want.append('g_2')
+            dims['g_2'] = L.dimg
+        self._gbatch = {k: torch.empty((B, dims[k]), dtype=torch.float32, device=dev) for k in want}
+        self._gwant = tuple(want)
+        self._ghyper = _lib.DdpgHyper(self._hyper.gamma, self._hyper.clip_return, self._hyper.action_l2,
+                                      self._hyper.clip_pos_returns, self._step.data_ptr(), self.LOSS_RING, 0)
+        self._workspace(B)
+        self._graph_sig = None
+        self._refresh_dyn()
+        torch.cuda.current_stream().synchronize()
+        # warm-up run outside capture (lazy module loading, cudaFuncSetAttribute, NCCL channels)
+        state = (self.theta_main.clone(), self.Q_adam.m.clone(), self.Q_adam.v.clone(), self.pi_adam.m.clone(),
+                 self.pi_adam.v.clone(), self._step.clone())
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._train_step_launches()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.theta_main.copy_(state[0])
+        for dst, src in zip((self.Q_adam.m, self.Q_adam.v, self.pi_adam.m, self.pi_adam.v, self._step), state[1:]):
+            dst.copy_(src)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._train_step_launches()
+        self._graph = g
+
+    def _train_step_launches(self):
+        """The launches of one update, all parameters frozen / device-resident (capturable)."""
+        lib = _lib.load()
+        sampler = self.sample_transitions
+        segs = [(buf.device_view(), 0, ttr) for buf, ttr in self._all_segments()]
+        sampler.sample_device(segs, self.batch_size, clip_obs=self.clip_obs, relative_goals=self.relative_goals,
+                              want=self._gwant, out=self._gbatch, dyn=self._dyn_dev.data_ptr(),
+                              call_offset=self.GRAPH_STREAM_OFFSET)
+        b = self._gbatch
+        n = self.batch_size
+        g2 = b['g_2'] if self.relative_goals else b['g']       # g_2 == g without relative goals (ddpg.py:353)
+        cb = _lib.Batch(b['o'].data_ptr(), b['g'].data_ptr(), b['u'].data_ptr(),
+                        b['td'].data_ptr() if self.modular else None, b['o_2'].data_ptr(), g2.data_ptr(),
+                        b['r'].data_ptr(), n)
+        _lib.check(lib.cur_ddpg_grads(
+            _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
+            C.byref(self._stats), C.byref(cb), C.byref(self._ghyper), self._workspace(n).data_ptr(),
+            self.grads.data_ptr(), self._q_ring.data_ptr(), self._pi_ring.data_ptr(), self._q_pi.data_ptr()),
+            'cur_ddpg_grads')
+        group, world = _world(self.comm)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)       # SUM, not mean (ddpg.py:452-453)
+        for adam, which, table in ((self.Q_adam, 'Q', self._adam_tables[0]), (self.pi_adam, 'pi', self._adam_tables[1])):
+            _lib.check(lib.cur_adam_step_graph(
+                _lib.stream_ptr(), adam.theta.data_ptr(), self._view(self.grads, which).data_ptr(), adam.m.data_ptr(),
+                adam.v.data_ptr(), adam.theta.numel(), table.data_ptr(), self.ADAM_TABLE, self._step.data_ptr(),
+                adam.beta1, adam.beta2, adam.epsilon, 1.0), 'cur_adam_step_graph')
+
+    def _train_graph(self):
+        if self._graph is None:
+            self._build_graph()
+        if self.Q_adam.t % 100 == 0:
+            self.Q_adam.check_synced()
+            self.pi_adam.check_synced()
+        self._refresh_dyn()
+        slot = self._n_updates % self.LOSS_RING
+        self._graph.replay()
+        self._n_updates += 1
+        self.Q_adam.t += 1
+        self.pi_adam.t += 1
+        return LazyHost(self._q_ring[slot]), LazyHost(self._q_pi)
+
     def train(self, stage=True):
+        """One DDPG update (ddpg.py:368-373).  Returns (critic_loss, actor_loss) as lazily synchronising
+        host values; like the reference, "actor_loss" is main.Q_pi, the whole [B,1] array (ddpg.py:237-243)."""
+        if stage and self.use_cuda_graph and self.her_rng == 'philox':
+            return self._train_graph()
         if stage:
             self.stage_batch()
         critic_loss, actor_loss, Q_grad, pi_grad = self._grads()
         self._update(Q_grad, pi_grad)
-        # like the reference, "actor_loss" is main.Q_pi, the whole [B,1] array (ddpg.py:237-243)
+        self._step += 1                      # keep the device step counter in line with Adam's t
+        self._n_updates += 1
         return LazyHost(critic_loss.clone().reshape(())), LazyHost(actor_loss)
 
     def _init_target_net(self):

@@ -127,7 +127,7 @@ class HerSampler:
     def sample_device(self, segments, B, *, cp_proba=None, draws=None, perm=None, clip_obs=0.0,
                       relative_goals=False, want=('o', 'ag', 'g', 'u', 'td', 'change', 'info', 'o_2',
                                                   'ag_2', 'r'),
-                      want_idx=False, out=None, stream=None):
+                      want_idx=False, out=None, stream=None, dyn=None, call_offset=None):
         """segments: list of (DeviceEpisodes, count, task_to_replay or None).
         Returns {key: float32 cuda tensor [B, dim]} (+ 'idx' int32 [B,4] if want_idx)."""
         if self.mode is None:
@@ -158,7 +158,8 @@ class HerSampler:
             a.seg[i].count = int(count)
             a.seg[i].task_to_replay = -1 if ttr is None else int(ttr)
             total += int(count)
-        assert total == B                                                    # ddpg.py:323
+        assert dyn is not None or total == B                                 # ddpg.py:323
+        a.dyn = dyn
         a.batch = B
         a.future_p = float(self.future_p)
         keep = []
@@ -170,8 +171,9 @@ class HerSampler:
             a.inj_choice = d['choice'].data_ptr() if d.get('choice') is not None else None
         else:
             a.seed = int(self.seed) & 0xFFFFFFFFFFFFFFFF
-            a.call_offset = self.calls
-        self.calls += 1
+            a.call_offset = self.calls if call_offset is None else call_offset
+        if call_offset is None:
+            self.calls += 1
         if perm is not None:
             if not torch.is_tensor(perm):
                 perm = torch.from_numpy(np.ascontiguousarray(perm, dtype=np.int32)).to(dev, non_blocking=True)

@@ -130,6 +130,16 @@ typedef struct cur_task_table {
   double cdf[CUR_MAX_TASKS];         /* CP_TASK: normalised cumsum(cp_proba) (np.random.choice) */
 } cur_task_table;
 
+/* Device-resident control block for CUDA-graph replays: the values that change between launches are
+ * read from memory instead of from the (frozen) kernel arguments.  `step` is the shared train-step
+ * counter: the Philox counter of a launch is call_offset + *step; cur_ddpg_grads bumps it. */
+typedef struct cur_her_dyn {
+  const int64_t* step;                   /* device pointer                                    */
+  int32_t n_episodes[CUR_MAX_SEGMENTS];  /* overrides seg[i].n_episodes                       */
+  int32_t count[CUR_MAX_SEGMENTS];       /* overrides seg[i].count; must sum to batch         */
+  double cdf[CUR_MAX_TASKS];             /* overrides tasks.cdf (CP_TASK mode)                */
+} cur_her_dyn;
+
 typedef struct cur_her_args {
   cur_layout L;
   cur_task_table tasks;
@@ -151,6 +161,7 @@ typedef struct cur_her_args {
   int32_t relative_goals; /* g <- g - ag (g_2 <- g - ag_2) before clipping                    */
   float *o, *ag, *g, *u, *td, *change, *info, *o_2, *ag_2, *g_2, *r;
   int32_t* idx_out;       /* optional [batch,4]: ep, t, future_t (-1 if not HER), module (-1) */
+  const cur_her_dyn* dyn; /* optional DEVICE control block (Philox mode only), see cur_her_dyn  */
 } cur_her_args;
 
 int cur_her_sample(void* stream, const cur_her_args* args);
@@ -183,11 +194,14 @@ int cur_norm_invert(void* stream, const float* v, int64_t n, int dim, const floa
  * from the exact python value, as NumPy does. */
 int cur_adam_step(void* stream, float* theta, const float* grad, float* m, float* v, int64_t n,
                   float neg_a, double beta1, double beta2, double eps, float grad_div);
-/* Same, but the step scale is read from a device table indexed by a device step counter that the
- * kernel increments (CUDA-graph friendly).  a_table[min(t, table_len-1)], t counted from 0. */
+/* Same, but CUDA-graph friendly: the step scale is read from a device table indexed by the shared
+ * device train-step counter, which cur_ddpg_grads has ALREADY bumped for this step, so Adam's 1-based
+ * t equals *step_counter and the scale is neg_a_table[min(t, table_len) - 1].  Beyond the table the
+ * last entry is used (the bias correction is exactly 1 in float64 after ~4e4 steps). */
 int cur_adam_step_graph(void* stream, float* theta, const float* grad, float* m, float* v,
-                        int64_t n, const float* neg_a_table, int table_len, int32_t* step_counter,
-                        double beta1, double beta2, double eps, float grad_div);
+                        int64_t n, const float* neg_a_table, int table_len,
+                        const int64_t* step_counter, double beta1, double beta2, double eps,
+                        float grad_div);
 /* target = polyak*target + (1-polyak)*main (ddpg.py:461-462); polyak == 0 is the init copy. */
 int cur_polyak(void* stream, float* target, const float* main_, int64_t n, double polyak);
 /* Order-independent 64-bit checksum of a float32 vector (for check_synced, mpi_adam.py:42-50). */
@@ -240,6 +254,12 @@ typedef struct cur_batch {
 typedef struct cur_ddpg_hyper {
   float gamma, clip_return, action_l2;
   int32_t clip_pos_returns;
+  /* CUDA-graph replays (both optional): when step_counter != NULL the loss kernel writes q_loss /
+   * pi_loss to slot (*step_counter % loss_ring) of the arrays passed to cur_ddpg_grads and then
+   * increments *step_counter (after the HER kernel of this step read it, before Adam reads it). */
+  int64_t* step_counter;
+  int32_t loss_ring;
+  int32_t _pad;
 } cur_ddpg_hyper;
 
 /* DDPG._grads (ddpg.py:235-243): writes grads = [Q_grad | pi_grad] (flat), Q_loss (1 float),

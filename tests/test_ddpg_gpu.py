@@ -229,3 +229,40 @@ def test_save_load_weights_roundtrip(tmp_path):
     for which in ('Q', 'pi'):
         for tgt in (False, True):
             assert np.array_equal(a.get_flat(which, tgt), b.get_flat(which, tgt))
+
+
+@pytest.mark.parametrize('task_replay', ['replay_task_cp_buffer', 'replay_cp_task_transition'])
+def test_cuda_graph_path_equals_eager_path(task_replay):
+    """train() through the captured CUDA graph (device control block, device step counter, Adam table)
+    must be bit-identical to the launch-by-launch path fed with the same Philox counters."""
+    import torch
+    from curious_b200.ddpg import DDPG
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, task_replay=task_replay)
+    episodes = episode_stream(dims, kw['T'], 6)
+    agents = []
+    for use_graph in (True, False):
+        ag = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', use_cuda_graph=use_graph)
+        np.random.seed(4)
+        _fill(ag, episodes, np.array([0.05, 0.2, 0.1, 0.0]))
+        agents.append(ag)
+    g, e = agents
+    # the normaliser stats of the two agents were fed by identical Philox samples
+    assert torch.equal(g.o_stats.mean, e.o_stats.mean)
+    e.sample_transitions.calls = DDPG.GRAPH_STREAM_OFFSET
+    for step in range(7):
+        if step == 4:      # change the LP weights and the buffer contents mid-way: the control block must follow
+            for ag in agents:
+                np.random.seed(5)
+                _fill(ag, episode_stream(dims, kw['T'], 2, seed=77), np.array([0.3, 0.0, 0.1, 0.2]))
+            e.sample_transitions.calls = DDPG.GRAPH_STREAM_OFFSET + step
+        lg, qg = g.train()
+        le, qe = e.train()
+        assert float(lg) == float(le), step
+        assert np.array_equal(np.asarray(qg), np.asarray(qe)), step
+    for which in ('Q', 'pi'):
+        assert np.array_equal(g.get_flat(which), e.get_flat(which)), which
+    assert torch.equal(g.Q_adam.m, e.Q_adam.m) and torch.equal(g.pi_adam.v, e.pi_adam.v)
+    assert int(g._step.item()) == int(e._step.item()) == 7
+    g.update_target_net()
+    e.update_target_net()
+    assert np.array_equal(g.get_flat('Q', True), e.get_flat('Q', True))
