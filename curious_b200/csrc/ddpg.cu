@@ -300,13 +300,21 @@ static GemmProb bwd_dx(const float* dY, int lddy, const float* W, int n_in, int 
   p.epi = act ? EPI_RELU_MASK : EPI_NONE; p.aux = act; p.ldaux = ldact;
   return p;
 }
-// [dW;db] = [X|1]^T * dY  -> (n_in + 1) x n_out block of the flat gradient
-static GemmProb bwd_dw(const float* X, int ldx, int n_in, const float* dY, int lddy, int n_out, float* dWb,
-                       int with_bias, int64_t n) {
+// dW = X^T * dY  -> n_in x n_out block of the flat gradient
+static GemmProb bwd_dw(const float* X, int ldx, int n_in, const float* dY, int lddy, int n_out, float* dW,
+                       int64_t n) {
   GemmProb p = zero_prob();
-  p.A = X; p.lda = ldx; p.a_trans = 1; p.a_ones = with_bias; p.K = (int)n;
+  p.A = X; p.lda = ldx; p.a_trans = 1; p.K = (int)n;
   p.B = dY; p.ldb = lddy;
-  p.C = dWb; p.ldc = n_out; p.M = n_in + (with_bias ? 1 : 0); p.N = n_out;
+  p.C = dW; p.ldc = n_out; p.M = n_in; p.N = n_out;
+  return p;
+}
+// db = 1^T * dY  -> the n_out floats right behind dW in the flat gradient ([W;b] is contiguous)
+static GemmProb bwd_db(const float* dY, int lddy, int n_out, float* db, int64_t n) {
+  GemmProb p = zero_prob();
+  p.ones_a = 1; p.a_trans = 1; p.K = (int)n;
+  p.B = dY; p.ldb = lddy;
+  p.C = db; p.ldc = n_out; p.M = 1; p.N = n_out;
   return p;
 }
 
@@ -491,18 +499,21 @@ extern "C" int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* 
   // ---- bwd-1: critic chain (weights grads of main/Q) | actor-through-Q chain (data grads only)
   int cur = 0;
   B.add(bwd_dx(w.dQ, 1, mQ + LQ.off_Wout, H, 1, w.hq[L - 1], H, w.dc[0], H, n));
-  B.add(bwd_dw(w.hq[L - 1], H, H, w.dQ, 1, 1, gQ + LQ.off_Wout, 1, n));
+  B.add(bwd_dw(w.hq[L - 1], H, H, w.dQ, 1, 1, gQ + LQ.off_Wout, n));
+  B.add(bwd_db(w.dQ, 1, 1, gQ + LQ.off_bout, n));
   B.add(bwd_dx(w.dQpi, 1, mQ + LQ.off_Wout, H, 1, w.hqp[L - 1], H, w.da[0], H, n));
   CUR_TRY(B.flush());
   for (int l = L - 1; l >= 1; --l) {
     B.add(bwd_dx(w.dc[cur], H, mQ + LQ.off_W[l], H, H, w.hq[l - 1], H, w.dc[cur ^ 1], H, n));
-    B.add(bwd_dw(w.hq[l - 1], H, H, w.dc[cur], H, H, gQ + LQ.off_W[l], 1, n));
+    B.add(bwd_dw(w.hq[l - 1], H, H, w.dc[cur], H, H, gQ + LQ.off_W[l], n));
+    B.add(bwd_db(w.dc[cur], H, H, gQ + LQ.off_b[l], n));
     B.add(bwd_dx(w.da[cur], H, mQ + LQ.off_W[l], H, H, w.hqp[l - 1], H, w.da[cur ^ 1], H, n));
     CUR_TRY(B.flush());
     cur ^= 1;
   }
-  B.add(bwd_dw(w.XQu, w.ld_sq, LQ.in_s, w.dc[cur], H, H, gQ + LQ.off_W0, 1, n));
-  if (LQ.in_g > 0) B.add(bwd_dw(w.Xg, w.ld_g, LQ.in_g, w.dc[cur], H, H, gQ + LQ.off_W0g, 0, n));
+  B.add(bwd_dw(w.XQu, w.ld_sq, LQ.in_s, w.dc[cur], H, H, gQ + LQ.off_W0, n));
+  B.add(bwd_db(w.dc[cur], H, H, gQ + LQ.off_b0, n));
+  if (LQ.in_g > 0) B.add(bwd_dw(w.Xg, w.ld_g, LQ.in_g, w.dc[cur], H, H, gQ + LQ.off_W0g, n));
   {
     // d pi_loss / d(pre-tanh) = (dL/d(pi/max_u) + action_l2 * 2/(B*dimu) * th) * (1 - th^2)
     GemmProb p = bwd_dx(w.da[cur], H, mQ + LQ.off_W0 + (int64_t)LP.in_s * H, d->dimu, H, nullptr, 0, w.dy,
@@ -516,16 +527,19 @@ extern "C" int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* 
   const int lddy = (int)r4(d->dimu);
   cur = 0;
   B.add(bwd_dx(w.dy, lddy, mP + LP.off_Wout, H, d->dimu, w.hp[L - 1], H, w.dp[0], H, n));
-  B.add(bwd_dw(w.hp[L - 1], H, H, w.dy, lddy, d->dimu, gP + LP.off_Wout, 1, n));
+  B.add(bwd_dw(w.hp[L - 1], H, H, w.dy, lddy, d->dimu, gP + LP.off_Wout, n));
+  B.add(bwd_db(w.dy, lddy, d->dimu, gP + LP.off_bout, n));
   CUR_TRY(B.flush());
   for (int l = L - 1; l >= 1; --l) {
     B.add(bwd_dx(w.dp[cur], H, mP + LP.off_W[l], H, H, w.hp[l - 1], H, w.dp[cur ^ 1], H, n));
-    B.add(bwd_dw(w.hp[l - 1], H, H, w.dp[cur], H, H, gP + LP.off_W[l], 1, n));
+    B.add(bwd_dw(w.hp[l - 1], H, H, w.dp[cur], H, H, gP + LP.off_W[l], n));
+    B.add(bwd_db(w.dp[cur], H, H, gP + LP.off_b[l], n));
     CUR_TRY(B.flush());
     cur ^= 1;
   }
-  B.add(bwd_dw(w.Xpi, w.ld_spi, LP.in_s, w.dp[cur], H, H, gP + LP.off_W0, 1, n));
-  if (LP.in_g > 0) B.add(bwd_dw(w.Xg, w.ld_g, LP.in_g, w.dp[cur], H, H, gP + LP.off_W0g, 0, n));
+  B.add(bwd_dw(w.Xpi, w.ld_spi, LP.in_s, w.dp[cur], H, H, gP + LP.off_W0, n));
+  B.add(bwd_db(w.dp[cur], H, H, gP + LP.off_b0, n));
+  if (LP.in_g > 0) B.add(bwd_dw(w.Xg, w.ld_g, LP.in_g, w.dp[cur], H, H, gP + LP.off_W0g, n));
   CUR_TRY(B.flush());
   return CUR_OK;
 }

@@ -25,7 +25,8 @@ import torch
 from . import _lib, apportion
 from .her import HostDraws
 from .mpi_adam import MpiAdam, adam_step_scale
-from .normalizer import Normalizer, _world
+from .normalizer import Normalizer
+from .parallel import allreduce_sum_, world as _world
 from .replay_buffer import StagedEpisodes, episodes_to_device
 from .util import LazyHost, dims_to_shapes, import_function, store_args, transitions_in_episode_batch
 
@@ -118,8 +119,12 @@ class DDPG(object):
         self.grads = torch.zeros(net.arena, dtype=torch.float32, device=dev)
         self._init_weights()
         # optimisers (ddpg.py:451-453): separate Adam state and step counters for Q and pi
-        self.Q_adam = MpiAdam([self._view(self.theta_main, 'Q')], scale_grad_by_procs=False, comm=self.comm)
-        self.pi_adam = MpiAdam([self._view(self.theta_main, 'pi')], scale_grad_by_procs=False, comm=self.comm)
+        self._adam_m = torch.zeros(net.arena, dtype=torch.float32, device=dev)
+        self._adam_v = torch.zeros(net.arena, dtype=torch.float32, device=dev)
+        self.Q_adam = MpiAdam([self._view(self.theta_main, 'Q')], scale_grad_by_procs=False, comm=self.comm,
+                              m=self._view(self._adam_m, 'Q'), v=self._view(self._adam_v, 'Q'))
+        self.pi_adam = MpiAdam([self._view(self.theta_main, 'pi')], scale_grad_by_procs=False, comm=self.comm,
+                               m=self._view(self._adam_m, 'pi'), v=self._view(self._adam_v, 'pi'))
         self._hyper = _lib.DdpgHyper(float(self.gamma), float(min(self.clip_return, 3.0e38)), float(self.action_l2),
                                      1 if self.clip_pos_returns else 0)
         self._ws = {}
@@ -392,9 +397,7 @@ class DDPG(object):
         if self.Q_adam.t % 100 == 0:
             self.Q_adam.check_synced()
             self.pi_adam.check_synced()
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)       # SUM, not mean (ddpg.py:452-453)
+        allreduce_sum_(self.grads, self.comm)                     # SUM, not mean (ddpg.py:452-453)
         self.Q_adam.t += 1
         self.pi_adam.t += 1
         lib = _lib.load()
@@ -479,8 +482,7 @@ class DDPG(object):
         self._refresh_dyn()
         torch.cuda.current_stream().synchronize()
         # warm-up run outside capture (lazy module loading, cudaFuncSetAttribute, NCCL channels)
-        state = (self.theta_main.clone(), self.Q_adam.m.clone(), self.Q_adam.v.clone(), self.pi_adam.m.clone(),
-                 self.pi_adam.v.clone(), self._step.clone())
+        state = (self.theta_main.clone(), self._adam_m.clone(), self._adam_v.clone(), self._step.clone())
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -488,7 +490,7 @@ class DDPG(object):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         self.theta_main.copy_(state[0])
-        for dst, src in zip((self.Q_adam.m, self.Q_adam.v, self.pi_adam.m, self.pi_adam.v, self._step), state[1:]):
+        for dst, src in zip((self._adam_m, self._adam_v, self._step), state[1:]):
             dst.copy_(src)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -514,10 +516,16 @@ class DDPG(object):
             C.byref(self._stats), C.byref(cb), C.byref(self._ghyper), self._workspace(n).data_ptr(),
             self.grads.data_ptr(), self._q_ring.data_ptr(), self._pi_ring.data_ptr(), self._q_pi.data_ptr()),
             'cur_ddpg_grads')
-        group, world = _world(self.comm)
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)       # SUM, not mean (ddpg.py:452-453)
+        allreduce_sum_(self.grads, self.comm)                     # SUM, not mean (ddpg.py:452-453)
+        qa, pa = self.Q_adam, self.pi_adam
+        if (self.Q_lr, qa.beta1, qa.beta2, qa.epsilon) == (self.pi_lr, pa.beta1, pa.beta2, pa.epsilon):
+            # same step rule for both nets: ONE launch over the whole [Q | pad | pi] arena (padding has zero
+            # gradient and stays zero)
+            _lib.check(lib.cur_adam_step_graph(
+                _lib.stream_ptr(), self.theta_main.data_ptr(), self.grads.data_ptr(), self._adam_m.data_ptr(),
+                self._adam_v.data_ptr(), self.theta_main.numel(), self._adam_tables[0].data_ptr(), self.ADAM_TABLE,
+                self._step.data_ptr(), qa.beta1, qa.beta2, qa.epsilon, 1.0), 'cur_adam_step_graph')
+            return
         for adam, which, table in ((self.Q_adam, 'Q', self._adam_tables[0]), (self.pi_adam, 'pi', self._adam_tables[1])):
             _lib.check(lib.cur_adam_step_graph(
                 _lib.stream_ptr(), adam.theta.data_ptr(), self._view(self.grads, which).data_ptr(), adam.m.data_ptr(),

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .normalizer import _world
+from .parallel import allreduce_sum_, assert_synced, broadcast_from_root_, world as _world
 
 
 def adam_step_scale(stepsize, beta1, beta2, t):
@@ -36,7 +36,8 @@ def flat_view(var_list):
 
 
 class MpiAdam(object):
-    def __init__(self, var_list, *, beta1=0.9, beta2=0.999, epsilon=1e-08, scale_grad_by_procs=True, comm=None):
+    def __init__(self, var_list, *, beta1=0.9, beta2=0.999, epsilon=1e-08, scale_grad_by_procs=True, comm=None,
+                 m=None, v=None):
         self.var_list = var_list
         self.beta1 = beta1
         self.beta2 = beta2
@@ -46,8 +47,11 @@ class MpiAdam(object):
         assert self.theta.is_cuda, 'MpiAdam works on device vectors (no CPU fallback)'
         assert self.theta.data_ptr() % 16 == 0, 'flat parameter vector must be 16-byte aligned'
         size = self.theta.numel()
-        self.m = torch.zeros(size, dtype=torch.float32, device=self.theta.device)
-        self.v = torch.zeros(size, dtype=torch.float32, device=self.theta.device)
+        # optional caller-provided state views (DDPG keeps Q and pi moments in one arena so that a single
+        # fused launch can step both nets)
+        self.m = m if m is not None else torch.zeros(size, dtype=torch.float32, device=self.theta.device)
+        self.v = v if v is not None else torch.zeros(size, dtype=torch.float32, device=self.theta.device)
+        assert self.m.numel() == size and self.v.numel() == size
         self.t = 0
         self.comm = comm
 
@@ -72,10 +76,9 @@ class MpiAdam(object):
         g = self._grad_tensor(localg)                       # localg.astype('float32')
         group, world = _world(self.comm)
         if world > 1:
-            import torch.distributed as dist
             if g.data_ptr() == (localg.data_ptr() if torch.is_tensor(localg) else 0):
                 g = g.clone()                               # the reference leaves localg untouched
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)    # mpi_adam.py:26
+            allreduce_sum_(g, self.comm)                    # mpi_adam.py:26
         self.t += 1
         a = adam_step_scale(stepsize, self.beta1, self.beta2, self.t)
         grad_div = float(world) if self.scale_grad_by_procs else 1.0  # mpi_adam.py:27-28
@@ -85,10 +88,7 @@ class MpiAdam(object):
                    'cur_adam_step')
 
     def sync(self):
-        group, world = _world(self.comm)
-        if world > 1:
-            import torch.distributed as dist
-            dist.broadcast(self.theta, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        broadcast_from_root_(self.theta, self.comm)
 
     def checksum(self):
         out = torch.zeros(1, dtype=torch.int64, device=self.theta.device)
@@ -102,8 +102,4 @@ class MpiAdam(object):
         group, world = _world(self.comm)
         if world <= 1:
             return
-        import torch.distributed as dist
-        mine = self.checksum()
-        root = mine.clone()
-        dist.broadcast(root, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-        assert bool((root == mine).item()), 'parameters diverged from rank 0'
+        assert_synced(self.checksum(), self.comm)

@@ -13,14 +13,7 @@ import torch
 from . import _lib
 
 
-def _world(comm):
-    import torch.distributed as dist
-    if comm is False:
-        return None, 1
-    if dist.is_available() and dist.is_initialized():
-        group = comm if comm is not None else dist.group.WORLD
-        return group, dist.get_world_size(group)
-    return None, 1
+from .parallel import allreduce_sum_, world as _world
 
 
 class Normalizer:
@@ -99,11 +92,7 @@ class Normalizer:
         """Cross-rank SUM of the packed partials (the division by the world size, normalizer.py:87,
         happens in recompute).  Arguments are accepted for signature parity; the packed device buffer
         is what is reduced."""
-        group, world = _world(self.comm)
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self._partial, op=dist.ReduceOp.SUM, group=group)
-        return world
+        return allreduce_sum_(self._partial, self.comm)
 
     def recompute_stats(self):
         with self.lock:
