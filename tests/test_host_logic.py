@@ -183,3 +183,27 @@ def test_adam_oracle_on_reference_test_problem():
         assert ora.theta.dtype == np.float32 and ora.m.dtype == np.float32
         assert np.allclose(ora.theta, th, rtol=1e-5, atol=1e-6)
     assert losses[-1] < losses[0]
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under curious_b200/ (nor its CUDA sources) may import,
+    call or link it, and the product must not read /root/reference at run time."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'curious_b200')
+    pat = re.compile(r'^\s*(from|import)\s+oracle\b|/root/reference', re.M)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), os.path.join(dirpath, f)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: with the shared library absent the binding raises instead of degrading."""
+    from curious_b200 import _lib
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    monkeypatch.setattr(_lib, '_lib', None)
+    import pytest
+    with pytest.raises((OSError, RuntimeError)):
+        _lib.load()

@@ -1,0 +1,89 @@
+"""2-rank NCCL test of the data-parallel DDPG update (needs >= 2 GPUs; skipped otherwise).
+
+Reference semantics (mpi_adam.py:24-28 with scale_grad_by_procs=False, ddpg.py:452-453): every rank
+computes gradients on ITS OWN batch, the flat gradients are SUMMED over ranks, every rank applies the same
+Adam step, and the parameters stay bit-identical (check_synced, mpi_adam.py:42-50).  Replay data never
+crosses ranks.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, use_graph, out_dir):
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        from curious_b200 import parallel
+        from tests.ddpg_util import ddpg_kwargs, episode_stream, make_gpu_agent
+        kw, dims, ag_ids, g_ids = ddpg_kwargs(4)
+        # rank 1 starts from different weights: _sync_optimizers must broadcast rank 0's (ddpg.py:466)
+        agent = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', seed=rank, use_cuda_graph=use_graph,
+                               device=dev)
+        assert parallel.world(agent.comm)[1] == world
+        theta0 = agent.theta_main.clone()
+        gathered = [torch.empty_like(theta0) for _ in range(world)]
+        dist.all_gather(gathered, theta0)
+        assert torch.equal(gathered[0], gathered[1]), 'init broadcast from rank 0 failed'
+        np.random.seed(parallel.rank_seed(0, rank))                       # train.py:242
+        n = 0
+        for ep in episode_stream(dims, kw['T'], 6, seed=123 + rank):     # each rank owns its replay data
+            n += 2
+            agent.store_episode(ep, np.array([0.05, 0.2, 0.1, 0.0]), n)
+        # normaliser statistics are averaged over ranks -> identical everywhere (normalizer.py:84-94)
+        st = torch.cat([agent.o_stats.mean, agent.o_stats.std, agent.g_stats.mean, agent.g_stats.std])
+        parallel.assert_synced(st)
+
+        if not use_graph:
+            # one eager update, dissected: local grads -> all-gather -> expected Adam(sum) on a clone
+            agent.stage_batch()
+            agent._grads()
+            local = agent.grads.clone()
+            parts = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(parts, local)
+            assert not torch.equal(parts[0], parts[1]), 'ranks must train on different batches'
+            expect = (parts[0] + parts[1])
+            agent._update(agent._view(agent.grads, 'Q'), agent._view(agent.grads, 'pi'))
+            assert torch.equal(agent.grads, expect), 'all-reduce must be a plain SUM'
+        for _ in range(120):                                              # crosses the every-100 check_synced
+            agent.train()
+        agent.update_target_net()
+        torch.cuda.synchronize()
+        fp = agent.theta_main.clone()
+        parallel.assert_synced(fp)
+        assert torch.isfinite(fp).all()
+        assert not torch.equal(fp, theta0)
+        np.save(os.path.join(out_dir, 'ok%d.npy' % rank), np.array([1.0]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_two_rank_update_sums_gradients_and_stays_synced(use_graph, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    mp.spawn(_worker, args=(2, _free_port(), use_graph, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), 'ok0.npy'))
+    assert os.path.exists(os.path.join(str(tmp_path), 'ok1.npy'))

@@ -1,0 +1,156 @@
+"""world_size-2 `gloo` tests (CPU) of the data-parallel plumbing in curious_b200/parallel.py.
+
+The reference runs one MPI rank per worker (train.py:221-243); its only collectives on the hot path are
+  MpiAdam.update  Allreduce(SUM) of the flat gradient, no division        mpi_adam.py:24-28, ddpg.py:452-453
+  MpiAdam.sync / check_synced  Bcast from rank 0 (+ assert)               mpi_adam.py:37-50
+  Normalizer._mpi_average  Allreduce(SUM) / size                          normalizer.py:84-88
+The same helper functions run on NCCL tensors on the box; here they run on CPU tensors and are checked
+against the oracle emulating the world in-process.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn_name, out_dir):
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        res = globals()[fn_name](rank, world)
+        np.save(os.path.join(out_dir, 'r%d.npy' % rank), np.asarray(res, dtype=np.float64))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn_name, tmp_path, world=2):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, fn_name, str(tmp_path)), nprocs=world, join=True)
+    return [np.load(os.path.join(str(tmp_path), 'r%d.npy' % r)) for r in range(world)]
+
+
+# ---------------------------------------------------------------------------------------------------
+def _local_grad(rank, n=1003):
+    return np.random.RandomState(100 + rank).randn(n).astype(np.float32)
+
+
+def _body_grad_sum_adam(rank, world):
+    """all-reduce SUM of the local flat gradients, then the oracle Adam step on every rank."""
+    from curious_b200 import parallel
+    from oracle.ddpg_oracle import MpiAdamOracle
+    g = torch.from_numpy(_local_grad(rank))
+    n = parallel.allreduce_sum_(g)
+    assert n == world
+    theta = np.linspace(-1, 1, g.numel()).astype(np.float32)
+    adam = MpiAdamOracle(theta, scale_grad_by_procs=False)
+    for _ in range(3):
+        adam.update(g.numpy(), 1e-3)
+    fp = torch.from_numpy(adam.theta.copy())
+    parallel.assert_synced(fp)                     # every rank holds bit-identical parameters
+    return adam.theta
+
+
+def test_grad_allreduce_is_sum_not_mean(tmp_path):
+    res = _run('_body_grad_sum_adam', tmp_path)
+    from oracle.ddpg_oracle import MpiAdamOracle
+    # oracle world emulated in-process: allreduce_sum callable (mpi_adam.py:24-26)
+    total = _local_grad(0) + _local_grad(1)
+    theta = np.linspace(-1, 1, total.size).astype(np.float32)
+    adam = MpiAdamOracle(theta, scale_grad_by_procs=False, allreduce_sum=lambda x: total, world_size=2)
+    for _ in range(3):
+        adam.update(_local_grad(0), 1e-3)
+    for r in res:
+        assert np.array_equal(r.astype(np.float32), adam.theta)
+
+
+def _body_bcast(rank, world):
+    from curious_b200 import parallel
+    t = torch.full((17,), float(rank + 1))
+    parallel.broadcast_from_root_(t)
+    return t.numpy()
+
+
+def test_sync_broadcasts_rank0(tmp_path):
+    res = _run('_body_bcast', tmp_path)
+    for r in res:
+        assert np.array_equal(r, np.ones(17))
+
+
+def _body_desync(rank, world):
+    from curious_b200 import parallel
+    fp = torch.tensor([1.0 + rank])
+    try:
+        parallel.assert_synced(fp)
+    except AssertionError:
+        return [1.0]
+    return [0.0]
+
+
+def test_check_synced_detects_divergence(tmp_path):
+    res = _run('_body_desync', tmp_path)
+    assert res[0][0] == 0.0 and res[1][0] == 1.0      # rank 0 is the reference copy; rank 1 diverged
+
+
+def _norm_input(rank, dim=7):
+    return np.random.RandomState(7 + rank).randn(50 + 10 * rank, dim).astype(np.float32)
+
+
+def _body_norm(rank, world):
+    """Packed partial [sum | sumsq | count] -> SUM over ranks -> / world (normalizer.py:84-94)."""
+    from curious_b200 import parallel
+    v = _norm_input(rank)
+    packed = torch.from_numpy(np.concatenate([v.sum(0), np.square(v).sum(0), [np.float32(v.shape[0])]])
+                              .astype(np.float32))
+    n = parallel.allreduce_sum_(packed)
+    return (packed / np.float32(n)).numpy()
+
+
+def test_normalizer_partials_are_averaged_over_ranks(tmp_path):
+    res = _run('_body_norm', tmp_path)
+    from oracle.ddpg_oracle import NormalizerOracle
+    vs = [_norm_input(0), _norm_input(1)]
+
+    class World:
+        """the oracle's mean_over_ranks hook fed with both ranks' partials, in call order sum, sumsq, count"""
+        def __init__(self):
+            self.k = 0
+
+        def __call__(self, x):
+            which = self.k % 3
+            self.k += 1
+            parts = [(v.sum(0), np.square(v).sum(0), np.array([v.shape[0]], np.float32))[which] for v in vs]
+            return ((parts[0] + parts[1]) / np.float32(2)).astype(np.float32)
+
+    ora = NormalizerOracle(7, mean_over_ranks=World())
+    ora.update(vs[0])
+    ora.recompute_stats()
+    dim = 7
+    for r in res:
+        r = r.astype(np.float32)
+        assert np.array_equal((np.zeros(dim, np.float32) + r[:dim]), ora.sum)
+        assert np.array_equal(r[dim:2 * dim], ora.sumsq)
+        assert np.float32(1) + r[2 * dim] == ora.count[0]
+
+
+def test_rank_seed_matches_reference():
+    from curious_b200 import parallel
+    assert parallel.rank_seed(5, 0) == 5 and parallel.rank_seed(5, 3) == 3000005      # train.py:242
+    assert parallel.world(False) == (None, 1)
