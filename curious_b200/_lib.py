@@ -84,6 +84,11 @@ class DdpgHyper(C.Structure):
                 ('_pad', C.c_int32)]
 
 
+class AdamFused(C.Structure):
+    _fields_ = [('m', C.c_void_p), ('v', C.c_void_p), ('neg_a_table', C.c_void_p), ('table_len', C.c_int32),
+                ('_pad', C.c_int32), ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/curious_b200.h declares
 SIGNATURES = {
     'cur_abi_version': (C.c_int, []),
@@ -117,6 +122,11 @@ SIGNATURES = {
     'cur_ddpg_grads': (C.c_int, [C.c_void_p, C.POINTER(NetDesc), C.c_void_p, C.c_void_p,
                                  C.POINTER(NormStats), C.POINTER(Batch), C.POINTER(DdpgHyper), C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'cur_ddpg_rows_supported': (C.c_int, [C.POINTER(NetDesc), C.c_int64]),
+    'cur_ddpg_rows_workspace_floats': (C.c_int64, [C.POINTER(NetDesc), C.c_int64]),
+    'cur_ddpg_rows_step': (C.c_int, [C.c_void_p, C.POINTER(NetDesc), C.c_void_p, C.c_void_p,
+                                     C.POINTER(NormStats), C.POINTER(Batch), C.POINTER(DdpgHyper), C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AdamFused)]),
 }
 
 _lib = None

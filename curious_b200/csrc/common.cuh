@@ -72,4 +72,13 @@ __host__ __device__ inline double u01_from_u32(uint32_t x) {
   return ((double)x + 0.5) * (1.0 / 4294967296.0);
 }
 
+// Adam on one element: unfused IEEE float32 operations in NumPy's order (mpi_adam.py:32-35)
+__device__ __forceinline__ void adam_elem(float& th, float g, float& m, float& v, float neg_a, float b1,
+                                          float omb1, float b2, float omb2, float eps) {
+  m = __fadd_rn(__fmul_rn(b1, m), __fmul_rn(omb1, g));                 // mpi_adam.py:32
+  v = __fadd_rn(__fmul_rn(b2, v), __fmul_rn(omb2, __fmul_rn(g, g)));   // mpi_adam.py:33
+  float step = __fdiv_rn(__fmul_rn(neg_a, m), __fadd_rn(__fsqrt_rn(v), eps));   // mpi_adam.py:34
+  th = __fadd_rn(th, step);                                            // mpi_adam.py:35
+}
+
 }  // namespace cur

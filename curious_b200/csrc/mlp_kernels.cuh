@@ -43,7 +43,16 @@ struct GemmProb {
   int tiles_n, tile_begin;     // filled by the launcher
 };
 
-constexpr int GEMM_MAX_PROBS = 8;
+// Optional Adam epilogue (fused dW + optimiser launch of the "rows" schedule): C is a block of the flat
+// gradient arena; the parameter / moment at the same arena offset is stepped right after the gradient
+// element is final.  All scalars are resolved by the calling kernel (see ddpg_rows.cu).
+struct AdamCtx {
+  const float* grads;          // arena base of C
+  float *theta, *m, *v;        // arenas with the same layout
+  float neg_a, b1, omb1, b2, omb2, eps;
+};
+
+constexpr int GEMM_MAX_PROBS = 24;
 constexpr int GT = 32;          // tile edge
 constexpr int GK = 64;          // K chunk per stage (4 k-groups x 16)
 constexpr int GEMM_THREADS = 256;
@@ -82,15 +91,23 @@ __device__ __forceinline__ float gemm_epilogue(const GemmProb& P, float v, int g
 }
 
 // Split-K reduction over the 4 k-groups + epilogue.  `red` holds 4 partial 32x32 tiles.
-__device__ __forceinline__ void reduce_and_store(const GemmProb& P, const float* red, int m0, int n0, int tid) {
+__device__ __forceinline__ void reduce_and_store(const GemmProb& P, const float* red, int m0, int n0, int tid,
+                                                 const AdamCtx* ax = nullptr) {
   for (int i = tid; i < GT * GT; i += GEMM_THREADS) {
     const int m = i >> 5, n = i & 31;
     const int gm = m0 + m, gn = n0 + n;
     if (gm >= P.M || gn >= P.N) continue;
     float v = (red[i] + red[GT * GT + i]) + (red[2 * GT * GT + i] + red[3 * GT * GT + i]);
     v = gemm_epilogue(P, v, gm, gn);
-    P.C[(int64_t)gm * P.ldc + gn] = v;
+    float* c = P.C + (int64_t)gm * P.ldc + gn;
+    *c = v;
     if (P.C2) P.C2[(int64_t)gm * P.ldc2 + gn] = v * P.scale2;
+    if (ax) {
+      const int64_t off = c - ax->grads;
+      float th = ax->theta[off], mm = ax->m[off], vv = ax->v[off];
+      adam_elem(th, v, mm, vv, ax->neg_a, ax->b1, ax->omb1, ax->b2, ax->omb2, ax->eps);
+      ax->theta[off] = th; ax->m[off] = mm; ax->v[off] = vv;
+    }
   }
 }
 
@@ -103,7 +120,8 @@ __device__ __forceinline__ void reduce_and_store(const GemmProb& P, const float*
 // The optional second K segment (A2,B2) exists only for the <false,false> instantiation.
 // ------------------------------------------------------------------------------------------------
 template <bool A_KM, bool B_NK>
-__device__ __forceinline__ void gemm_tile_fast(const GemmProb& P, float* As, float* Bs, int m0, int n0) {
+__device__ __forceinline__ void gemm_tile_fast(const GemmProb& P, float* As, float* Bs, int m0, int n0,
+                                               const AdamCtx* ax = nullptr) {
   const int tid = threadIdx.x;
   const int kg = tid >> 6;
   const int lt = tid & 63;
@@ -237,7 +255,7 @@ __device__ __forceinline__ void gemm_tile_fast(const GemmProb& P, float* As, flo
       mine[r * GT + cc] = acc[i][j];
     }
   __syncthreads();
-  reduce_and_store(P, red, m0, n0, tid);
+  reduce_and_store(P, red, m0, n0, tid, ax);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,7 +331,8 @@ __device__ __forceinline__ void chunk_sstore(const GemmProb& P, int seg, int tid
   }
 }
 
-__device__ __noinline__ void gemm_tile_generic(const GemmProb& P, float* As, float* Bs, int m0, int n0) {
+static __device__ __noinline__ void gemm_tile_generic(const GemmProb& P, float* As, float* Bs, int m0, int n0,
+                                               const AdamCtx* ax = nullptr) {
   const int tid = threadIdx.x;
   const int kg = tid >> 6;
   const int lt = tid & 63;
@@ -361,16 +380,14 @@ __device__ __noinline__ void gemm_tile_generic(const GemmProb& P, float* As, flo
 #pragma unroll
     for (int j = 0; j < 4; ++j) mine[(ty * 4 + i) * GT + tx * 4 + j] = acc[i][j];
   __syncthreads();
-  reduce_and_store(P, red, m0, n0, tid);
+  reduce_and_store(P, red, m0, n0, tid, ax);
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 2) grouped_gemm_kernel(const __grid_constant__ GemmBatch G) {
-  __shared__ __align__(16) float As[2 * TILE_FLOATS];
-  __shared__ __align__(16) float Bs[2 * TILE_FLOATS];
-  __shared__ GemmProb Ps;
-
-  // which problem / tile; the descriptor is copied to shared memory once (dynamic indexing of the
-  // kernel-parameter array would otherwise turn every field access into a constant-bank load)
+// problem / tile lookup shared by the kernels built on the tile routines; the descriptor is copied to
+// shared memory once (dynamic indexing of the kernel-parameter array would otherwise turn every field
+// access into a constant-bank load)
+__device__ __forceinline__ void gemm_run_tile(const GemmBatch& G, GemmProb& Ps, float* As, float* Bs,
+                                              const AdamCtx* ax) {
   int pi = 0;
 #pragma unroll 1
   while (pi + 1 < G.n && (int)blockIdx.x >= G.p[pi + 1].tile_begin) ++pi;
@@ -385,11 +402,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) grouped_gemm_kernel(const __g
   const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
   const int m0 = tm * GT, n0 = tn * GT;
   switch (P.variant) {
-    case VAR_MK_KN: gemm_tile_fast<false, false>(P, As, Bs, m0, n0); break;
-    case VAR_MK_NK: gemm_tile_fast<false, true>(P, As, Bs, m0, n0); break;
-    case VAR_KM_KN: gemm_tile_fast<true, false>(P, As, Bs, m0, n0); break;
-    default: gemm_tile_generic(P, As, Bs, m0, n0); break;
+    case VAR_MK_KN: gemm_tile_fast<false, false>(P, As, Bs, m0, n0, ax); break;
+    case VAR_MK_NK: gemm_tile_fast<false, true>(P, As, Bs, m0, n0, ax); break;
+    case VAR_KM_KN: gemm_tile_fast<true, false>(P, As, Bs, m0, n0, ax); break;
+    default: gemm_tile_generic(P, As, Bs, m0, n0, ax); break;
   }
+}
+
+static __global__ void __launch_bounds__(GEMM_THREADS, 2) grouped_gemm_kernel(const __grid_constant__ GemmBatch G) {
+  __shared__ __align__(16) float As[2 * TILE_FLOATS];
+  __shared__ __align__(16) float Bs[2 * TILE_FLOATS];
+  __shared__ GemmProb Ps;
+  gemm_run_tile(G, Ps, As, Bs, nullptr);
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -414,7 +438,7 @@ inline int pick_variant(const GemmProb& P) {
   return VAR_GENERIC;
 }
 
-inline int launch_gemm_batch(GemmBatch& G, cudaStream_t s) {
+inline int plan_gemm_batch(GemmBatch& G) {
   int t = 0;
   for (int i = 0; i < G.n; ++i) {
     GemmProb& P = G.p[i];
@@ -424,6 +448,11 @@ inline int launch_gemm_batch(GemmBatch& G, cudaStream_t s) {
     t += ((P.M + GT - 1) / GT) * P.tiles_n;
   }
   G.total_tiles = t;
+  return t;
+}
+
+inline int launch_gemm_batch(GemmBatch& G, cudaStream_t s) {
+  const int t = plan_gemm_batch(G);
   if (t == 0) return CUR_OK;
   grouped_gemm_kernel<<<t, GEMM_THREADS, 0, s>>>(G);
   CUR_CHECK_LAUNCH();

@@ -121,14 +121,6 @@ __global__ void norm_invert_kernel(const float* __restrict__ v, int64_t total, i
 }
 
 // ---------------------------------------------------------------- Adam / polyak
-__device__ __forceinline__ void adam_elem(float& th, float g, float& m, float& v, float neg_a, float b1,
-                                          float omb1, float b2, float omb2, float eps) {
-  m = __fadd_rn(__fmul_rn(b1, m), __fmul_rn(omb1, g));                 // mpi_adam.py:32
-  v = __fadd_rn(__fmul_rn(b2, v), __fmul_rn(omb2, __fmul_rn(g, g)));   // mpi_adam.py:33
-  float step = __fdiv_rn(__fmul_rn(neg_a, m), __fadd_rn(__fsqrt_rn(v), eps));   // mpi_adam.py:34
-  th = __fadd_rn(th, step);                                            // mpi_adam.py:35
-}
-
 template <bool kTable>
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,

@@ -60,6 +60,9 @@ class DDPG(object):
         self.her_rng = kwargs.get('her_rng', 'philox')
         self.seed = kwargs.get('seed', 0)
         self.use_cuda_graph = kwargs.get('use_cuda_graph', True)
+        # 'rows' (cluster kernel + fused dW/Adam, 2 launches), 'levels' (one grouped GEMM per dependency
+        # level) or 'auto' (rows whenever the shape is supported)
+        self.update_schedule = kwargs.get('update_schedule', 'auto')
         self.create_actor_critic = import_function(self.network_class)
 
         self.dimo = self.input_dims['o']
@@ -170,6 +173,21 @@ class DDPG(object):
             floats = _lib.load().cur_ddpg_workspace_floats(C.byref(self.net.desc), n)
             self._ws[n] = torch.empty(floats, dtype=torch.float32, device=self.device)
         return self._ws[n]
+
+    def _use_rows(self, n):
+        if self.update_schedule in ('levels', 'auto'):      # 'auto' == 'levels' until the rows kernel wins
+            return False
+        ok = bool(_lib.load().cur_ddpg_rows_supported(C.byref(self.net.desc), n))
+        if self.update_schedule == 'rows' and not ok:
+            raise ValueError('update_schedule="rows" does not support this network / batch shape')
+        return ok
+
+    def _workspace_rows(self, n):
+        key = ('rows', n)
+        if key not in self._ws:
+            floats = _lib.load().cur_ddpg_rows_workspace_floats(C.byref(self.net.desc), n)
+            self._ws[key] = torch.zeros(floats, dtype=torch.float32, device=self.device)   # holds a ticket: zeroed
+        return self._ws[key]
 
     # ------------------------------------------------------------------------------------------
     def _random_action(self, n):
@@ -382,11 +400,18 @@ class DDPG(object):
                         b['td'].data_ptr() if self.modular else None, b['o_2'].data_ptr(), b['g_2'].data_ptr(),
                         b['r'].data_ptr(), n)
         q_pi = torch.empty((n, 1), dtype=torch.float32, device=self.device)
-        _lib.check(_lib.load().cur_ddpg_grads(
-            _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
-            C.byref(self._stats), C.byref(cb), C.byref(self._hyper), self._workspace(n).data_ptr(),
-            self.grads.data_ptr(), self._q_loss.data_ptr(), self._pi_loss.data_ptr(), q_pi.data_ptr()),
-            'cur_ddpg_grads')
+        if self._use_rows(n):
+            _lib.check(_lib.load().cur_ddpg_rows_step(
+                _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
+                C.byref(self._stats), C.byref(cb), C.byref(self._hyper), self._workspace_rows(n).data_ptr(),
+                self.grads.data_ptr(), self._q_loss.data_ptr(), self._pi_loss.data_ptr(), q_pi.data_ptr(), None),
+                'cur_ddpg_rows_step')
+        else:
+            _lib.check(_lib.load().cur_ddpg_grads(
+                _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
+                C.byref(self._stats), C.byref(cb), C.byref(self._hyper), self._workspace(n).data_ptr(),
+                self.grads.data_ptr(), self._q_loss.data_ptr(), self._pi_loss.data_ptr(), q_pi.data_ptr()),
+                'cur_ddpg_grads')
         return self._q_loss, q_pi, self._view(self.grads, 'Q'), self._view(self.grads, 'pi')
 
     def _update(self, Q_grad, pi_grad):
@@ -477,28 +502,42 @@ class DDPG(object):
         self._gwant = tuple(want)
         self._ghyper = _lib.DdpgHyper(self._hyper.gamma, self._hyper.clip_return, self._hyper.action_l2,
                                       self._hyper.clip_pos_returns, self._step.data_ptr(), self.LOSS_RING, 0)
-        self._workspace(B)
+        self._workspace_rows(B) if self._use_rows(B) else self._workspace(B)
         self._graph_sig = None
         self._refresh_dyn()
         torch.cuda.current_stream().synchronize()
-        # warm-up run outside capture (lazy module loading, cudaFuncSetAttribute, NCCL channels)
+        # warm-up run outside capture (lazy module loading, cudaFuncSetAttribute)
         state = (self.theta_main.clone(), self._adam_m.clone(), self._adam_v.clone(), self._step.clone())
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            self._train_step_launches()
+            fused = self._launch_sample_and_grads()
+            if not fused:
+                self._launch_adam()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         self.theta_main.copy_(state[0])
         for dst, src in zip((self._adam_m, self._adam_v, self._step), state[1:]):
             dst.copy_(src)
+        # One rank: the whole update is one graph.  Several ranks: the graph ends after the gradients; the
+        # NCCL all-reduce and the Adam launch follow on the same stream (collectives are kept out of the
+        # capture: a captured torch NCCL all-reduce dead-locked on the 2-GPU box).
+        self._graph_has_adam = _world(self.comm)[1] == 1
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._train_step_launches()
+            fused = self._launch_sample_and_grads()
+            if self._graph_has_adam and not fused:
+                self._launch_adam()
         self._graph = g
+        self._graph_fused = fused
 
-    def _train_step_launches(self):
-        """The launches of one update, all parameters frozen / device-resident (capturable)."""
+    def _same_rule(self):
+        qa, pa = self.Q_adam, self.pi_adam
+        return (self.Q_lr, qa.beta1, qa.beta2, qa.epsilon) == (self.pi_lr, pa.beta1, pa.beta2, pa.epsilon)
+
+    def _launch_sample_and_grads(self):
+        """HER sample + gradients of one update, all parameters frozen / device-resident (capturable).
+        Returns True when Adam was fused into the weight-gradient launch."""
         lib = _lib.load()
         sampler = self.sample_transitions
         segs = [(buf.device_view(), 0, ttr) for buf, ttr in self._all_segments()]
@@ -511,14 +550,32 @@ class DDPG(object):
         cb = _lib.Batch(b['o'].data_ptr(), b['g'].data_ptr(), b['u'].data_ptr(),
                         b['td'].data_ptr() if self.modular else None, b['o_2'].data_ptr(), g2.data_ptr(),
                         b['r'].data_ptr(), n)
+        qa = self.Q_adam
+        if self._use_rows(n):
+            # with one rank there is no all-reduce between _grads and _update: Adam runs in the epilogue of
+            # the weight-gradient launch (2 launches per update after the HER kernel)
+            fuse = self._same_rule() and _world(self.comm)[1] == 1
+            adam = _lib.AdamFused(self._adam_m.data_ptr(), self._adam_v.data_ptr(), self._adam_tables[0].data_ptr(),
+                                  self.ADAM_TABLE, 0, qa.beta1, qa.beta2, qa.epsilon) if fuse else None
+            _lib.check(lib.cur_ddpg_rows_step(
+                _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
+                C.byref(self._stats), C.byref(cb), C.byref(self._ghyper), self._workspace_rows(n).data_ptr(),
+                self.grads.data_ptr(), self._q_ring.data_ptr(), self._pi_ring.data_ptr(), self._q_pi.data_ptr(),
+                C.byref(adam) if fuse else None), 'cur_ddpg_rows_step')
+            return fuse
         _lib.check(lib.cur_ddpg_grads(
             _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
             C.byref(self._stats), C.byref(cb), C.byref(self._ghyper), self._workspace(n).data_ptr(),
             self.grads.data_ptr(), self._q_ring.data_ptr(), self._pi_ring.data_ptr(), self._q_pi.data_ptr()),
             'cur_ddpg_grads')
-        allreduce_sum_(self.grads, self.comm)                     # SUM, not mean (ddpg.py:452-453)
-        qa, pa = self.Q_adam, self.pi_adam
-        if (self.Q_lr, qa.beta1, qa.beta2, qa.epsilon) == (self.pi_lr, pa.beta1, pa.beta2, pa.epsilon):
+        return False
+
+    def _launch_adam(self):
+        """Adam on the (already all-reduced) gradient arena; the step scale is read from the device table with
+        the device step counter, so the launch is identical every update."""
+        lib = _lib.load()
+        qa = self.Q_adam
+        if self._same_rule():
             # same step rule for both nets: ONE launch over the whole [Q | pad | pi] arena (padding has zero
             # gradient and stays zero)
             _lib.check(lib.cur_adam_step_graph(
@@ -541,6 +598,9 @@ class DDPG(object):
         self._refresh_dyn()
         slot = self._n_updates % self.LOSS_RING
         self._graph.replay()
+        if not self._graph_has_adam:
+            allreduce_sum_(self.grads, self.comm)                 # SUM, not mean (ddpg.py:452-453)
+            self._launch_adam()
         self._n_updates += 1
         self.Q_adam.t += 1
         self.pi_adam.t += 1

@@ -269,6 +269,38 @@ int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* theta_main,
                    const cur_ddpg_hyper* h, float* workspace, float* grads, float* q_loss,
                    float* pi_loss, float* q_pi);
 
+/* ------------------------------------------------------------------------------------------
+ * "Rows" schedule of the same update (csrc/ddpg_rows.cu): DDPG._grads (ddpg.py:235-243) and,
+ * optionally, both MpiAdam.update calls of DDPG._update (ddpg.py:246-248, mpi_adam.py:30-35) in
+ * TWO launches: a thread-block-cluster kernel that runs the whole forward / backward data path for
+ * 16-row groups of the batch, then one grouped weight-gradient GEMM over the full batch that
+ * applies Adam in its epilogue.  Supported shapes: hidden == 256, layers <= 4, dimu <= 8,
+ * first-layer fan-in <= 256, batch a multiple of 16 (cur_ddpg_rows_supported); anything else
+ * uses cur_ddpg_grads.  Same outputs as cur_ddpg_grads.
+ *
+ * `workspace` must be ZERO-INITIALISED once by the caller (it holds a completion ticket).
+ * With h->step_counter != NULL the losses go to slot (*step_counter % loss_ring) and the counter is
+ * incremented at the end of the second launch.  With `adam` != NULL (requires step_counter) the
+ * parameters theta_main and the moments are stepped in place with
+ * neg_a_table[min(*step_counter + 1, table_len) - 1]; use it only when no gradient all-reduce is
+ * needed between _grads and _update (world size 1) and both nets share the step size.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cur_adam_fused {
+  float *m, *v;               /* Adam moments, same arena layout as theta */
+  const float* neg_a_table;   /* float32(-a_t), t = 1..table_len (see cur_adam_step_graph) */
+  int32_t table_len;
+  int32_t _pad;
+  double beta1, beta2, eps;
+} cur_adam_fused;
+
+int cur_ddpg_rows_supported(const cur_net_desc* d, int64_t batch);
+int64_t cur_ddpg_rows_workspace_floats(const cur_net_desc* d, int64_t batch);
+int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* theta_main,
+                       const float* theta_target, const cur_norm_stats* stats,
+                       const cur_batch* batch, const cur_ddpg_hyper* h, float* workspace,
+                       float* grads, float* q_loss, float* pi_loss, float* q_pi,
+                       const cur_adam_fused* adam /* or NULL: gradients only */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,9 +27,10 @@ def _fill(agent, episodes, cp):
         agent.store_episode({k: v.copy() for k, v in ep.items()}, cp, n)
 
 
+@pytest.mark.parametrize('schedule', ['levels', 'rows'])
 @pytest.mark.parametrize('normalize_obs', [False, True])
 @pytest.mark.parametrize('n_modules', [4, 8])
-def test_store_sample_train_against_oracle(normalize_obs, n_modules):
+def test_store_sample_train_against_oracle(normalize_obs, n_modules, schedule):
     """Same seeds on both sides: buffers, normaliser stats, sampled batch (bit exact), losses, gradients and
     updated weights (tolerance) must agree over several updates."""
     import torch
@@ -37,7 +38,7 @@ def test_store_sample_train_against_oracle(normalize_obs, n_modules):
     cp = np.linspace(0.0, 0.3, n_modules)
     episodes = episode_stream(dims, kw['T'], 12)
     ora = make_oracle_agent(kw, dims, ag_ids, g_ids)
-    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy')
+    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy', update_schedule=schedule)
     np.random.seed(2024)
     _fill(ora, episodes, cp)
     np.random.seed(2024)
@@ -231,8 +232,45 @@ def test_save_load_weights_roundtrip(tmp_path):
             assert np.array_equal(a.get_flat(which, tgt), b.get_flat(which, tgt))
 
 
+@pytest.mark.parametrize('structure,layers,batch_size', [('curious', 3, 256), ('flat', 2, 64), ('task_experts', 1, 32),
+                                                         ('curious', 4, 16)])
+def test_rows_schedule_trajectory(structure, layers, batch_size):
+    """The cluster ("rows") schedule end to end through train(): modular and flat nets, 1-4 hidden layers,
+    batches of 1..16 clusters; weights after 5 updates within tolerance of the oracle trajectory, and the
+    levels schedule fed the same batches lands on the same weights within the same tolerance."""
+    task_replay = {'curious': 'replay_task_cp_buffer', 'flat': '', 'task_experts': 'replay_current_task_buffer'}[structure]
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, structure=structure, task_replay=task_replay, hidden=256, layers=layers,
+                                          batch_size=batch_size)
+    if structure == 'task_experts':
+        kw['t_id'] = 2
+    cp = np.array([0.05, 0.2, 0.1, 0.0])
+    episodes = episode_stream(dims, kw['T'], 6, flat=structure == 'flat')
+    ora = make_oracle_agent(kw, dims, ag_ids, g_ids)
+    gpus = [make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy', update_schedule=s) for s in ('rows', 'levels')]
+    for agent in [ora] + gpus:
+        np.random.seed(7)
+        _fill(agent, episodes, cp)
+    np.random.seed(8)
+    for _ in range(5):
+        ql_o, qpi_o = ora.train()
+    for gpu in gpus:
+        np.random.seed(8)
+        for _ in range(5):
+            ql_g, qpi_g = gpu.train()
+        assert abs(float(ql_g) - ql_o) <= 1e-4 * abs(ql_o) + 1e-6
+        assert rel_err(np.asarray(qpi_g), qpi_o) <= 5e-4     # 5 Adam steps amplify summation-order differences
+        for which, adam in (('Q', ora.Q_adam), ('pi', ora.pi_adam)):
+            # Adam normalises every step to ~lr whatever the gradient's size, so a gradient element that is
+            # pure rounding noise may step the other way in a re-implementation with a different summation
+            # order: bound the bulk tightly and the stragglers by the 5 steps of lr = 1e-3 themselves
+            err = np.abs(gpu.get_flat(which) - adam.theta)
+            assert np.quantile(err, 0.999) <= 2e-4, which
+            assert err.max() <= 5 * 1e-3 * 1.01, which
+
+
+@pytest.mark.parametrize('schedule', ['levels', 'rows'])
 @pytest.mark.parametrize('task_replay', ['replay_task_cp_buffer', 'replay_cp_task_transition'])
-def test_cuda_graph_path_equals_eager_path(task_replay):
+def test_cuda_graph_path_equals_eager_path(task_replay, schedule):
     """train() through the captured CUDA graph (device control block, device step counter, Adam table)
     must be bit-identical to the launch-by-launch path fed with the same Philox counters."""
     import torch
@@ -241,7 +279,8 @@ def test_cuda_graph_path_equals_eager_path(task_replay):
     episodes = episode_stream(dims, kw['T'], 6)
     agents = []
     for use_graph in (True, False):
-        ag = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', use_cuda_graph=use_graph)
+        ag = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', use_cuda_graph=use_graph,
+                            update_schedule=schedule)
         np.random.seed(4)
         _fill(ag, episodes, np.array([0.05, 0.2, 0.1, 0.0]))
         agents.append(ag)
