@@ -1,4 +1,4 @@
-// DDPG / UVFA update, "rows" schedule (sm_100a): the whole actor-critic graph of one update in TWO launches.
+// DDPG / UVFA update, "rows" schedule (sm_100a): the whole actor-critic graph of one update in THREE launches.
 //
 // Replaces (reference flowersteam/curious), like ddpg.cu but with a latency-oriented schedule:
 //   baselines/her/actor_critic.py:5-98, util.py:56-107   networks
@@ -7,237 +7,221 @@
 //
 // Why: at the reference batch (256 rows, 3x256 MLPs) one update is 0.73 GFLOP - ~10 us of FFMA - but the
 // dependency-level schedule of ddpg.cu needs 17 dependent launches (140 us).  Rows of the batch are
-// independent until the weight gradient, so:
+// independent until the weight gradient, so the data path is run "decode style":
 //
-//   launch 1  ddpg_rows_kernel   one thread-block CLUSTER of 8 CTAs per 16 batch rows.  CTA c owns hidden
-//             columns [32c, 32c+32) of every layer of every net.  The cluster runs the whole chain for its
-//             rows - input assembly (normalise / concat), 5 forward nets, loss seeds, the critic,
-//             actor-through-critic and actor data-gradient chains.
-//               * weights never touch shared memory: every thread loads the 16 k-rows x 2 columns it
-//                 multiplies straight from L2 into registers (each element is fetched once per CTA), and
-//                 the loads for the NEXT net/layer are issued as soon as the current FFMA loop ends, so
-//                 their latency hides behind the reduction, the epilogue and the exchange;
-//               * activations live in a transposed shared tile [k][16 rows]: a k-slice (half warp) reads
-//                 its 16 rows with 4 broadcast LDS.128 per k for 32 FFMA;
-//               * K is split 16 ways (2 k-slices per warp), combined by one shuffle + a shared-memory
-//                 reduction in fixed order (deterministic);
-//               * layer outputs are exchanged through DISTRIBUTED SHARED MEMORY: the thread that owns 4 rows
-//                 of one output column stores the float4 straight into the activation tile of all 8 CTAs of
-//                 the cluster (st.shared::cluster), bracketed by split cluster barriers (arrive after the
-//                 last tile read / wait before the remote stores; arrive.release after them / wait.acquire
-//                 before the next layer).  No L2 round trip and no global fence between layers; the
-//                 row-major global copies that launch 2 needs are plain posted stores off the critical path.
-//             <= 128 registers and ~112 KB of shared memory per CTA, so two CTAs fit on an SM and all 16
-//             clusters of a 256-row batch are co-resident (the first version - 1 CTA/SM - could only place
-//             15 clusters and ran in two waves, see profiles/).
+//   launch 0  transpose_kernel   W_l^T of the hidden layers of main.Q / main.pi (operands of the backward
+//             streams), 0.5 MB, rebuilt every update so no host-side state has to track weight changes.
+//   launch 1  ddpg_stream_kernel one CTA per 4 batch rows, no inter-CTA communication at all.  Each CTA walks
+//             the WHOLE chain for its rows - input assembly, main.pi, target.pi, main.Q on (u | pi) stacked,
+//             target.Q, loss seeds, critic + actor-through-critic backward stacked, actor backward - while
+//             a producer warp streams every weight matrix it needs (3.4 MB per update) from L2 through a
+//             4 x 32 KB shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier full/empty
+//             pairs).  8 consumer warps do GEMV-like FFMA: a thread owns 4 output columns and a quarter of
+//             the chunk's k rows, reads W as LDS.128 and the (transposed) activations as one broadcast
+//             LDS.128 per k; activations never leave shared memory between layers.  The first version of
+//             this schedule split columns over an 8-CTA cluster and exchanged activations every layer
+//             (DSMEM or L2): the per-layer cluster synchronisation cost more than the layer (profiles/).
 //   launch 2  rows_dw_kernel     every dW = X^T dY and db = 1^T dY of both nets as one grouped GEMM with
 //             the full batch as K (deterministic, no atomics), written into the flat GetFlat-ordered
 //             gradient arena; optionally Adam is applied to the element in the same epilogue (world
 //             size 1: no all-reduce between gradient and step).  The last CTA to finish folds the
-//             per-cluster loss partials and bumps the device step counter.
+//             per-CTA loss partials and bumps the device step counter.
 //
 // All arithmetic is FP32 FFMA (IEEE); see DESIGN.md section 4 for why tensor cores do not apply here.
-#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "net_layout.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace cur {
 
-constexpr int R_ROWS = 16;               // batch rows per cluster
-constexpr int R_CS = 8;                  // CTAs per cluster
-constexpr int R_CW = 32;                 // hidden columns per CTA
-constexpr int R_H = R_CS * R_CW;         // 256 hidden units
-constexpr int R_THREADS = 256;
-constexpr int R_NSLICE = 16;             // k-slices (half warps)
-constexpr int R_TILE = R_H * R_ROWS;     // floats of one transposed activation tile [k][16]
-constexpr int R_MAXA = 3;                // activation tiles (nets per step)
-constexpr int R_LDP = R_ROWS + 4;        // column stride of a split-K partial [32 cols][16 rows (+4)]
-constexpr int R_PART = R_CW * R_LDP;     // floats of one warp's partial
-constexpr int R_RED = (R_THREADS / 32) * R_PART;          // floats of the split-K partials of one net
-constexpr int R_MAXL = 4;                // hidden layers supported by this schedule
-constexpr int R_MAXW = 7 * R_MAXL;       // net-layer weight descriptors
-constexpr int R_MAXS = 4 * R_MAXL;       // steps
-constexpr int R_DU = 8;                  // max action dim
-constexpr int R_MISC = 1024;
-constexpr size_t R_SMEM_FLOATS = (size_t)R_MAXA * R_TILE + R_MAXA * R_RED + R_MISC;
+constexpr int S_ROWS = 4;                // batch rows per CTA
+constexpr int S_H = 256;                 // hidden units
+constexpr int S_CONSUMERS = 256;         // 8 consumer warps
+constexpr int S_THREADS = S_CONSUMERS + 32;   // + 1 producer warp
+constexpr int S_CK = 32;                 // k rows per weight chunk
+constexpr int S_NSLOT = 4;               // ring slots
+constexpr int S_SLOT = S_CK * S_H;       // floats per slot (32 KB)
+constexpr int S_MAXL = 4;                // hidden layers supported by this schedule
+constexpr int S_MAXCHUNK = 192;          // weight chunks per update (L = 4: 4 * 27 + 2 * 24 = 156)
+constexpr int S_DU = 8;                  // max action dim
+constexpr int S_XT = S_H * 8;            // floats of one transposed activation buffer [256 k][<= 8 rows]
+constexpr int S_RED = 4 * 8 * S_H;       // split-K partials [4 k-slices][<= 8 rows][256]
+constexpr int S_MISC = 1024;
+constexpr size_t S_SMEM_BYTES = (size_t)(S_NSLOT * S_SLOT + 2 * S_XT + S_RED + S_MISC) * 4 + 128;
 
-struct WDesc {
-  const float* w;     // fwd: rows = k ([K][H]);  bwd: rows = output columns ([H][H])
-  const float* w2;    // first layer: rows >= split come from here (the goal block W0g)
-  int split;          // rows < split from w, the rest from w2
-  int kvalid;         // rows >= kvalid are zero
-  int kper;           // k-rows per slice (K padded / 16)
-  int kind;           // 0: forward hidden layer (fast path), 1: backward, 2: forward first layer (generic)
+struct SChunk {
+  const float* src;   // nrows x 256 floats, contiguous
+  int nrows;          // <= 32
+  int k0;             // first k row of the layer this chunk covers
 };
 
-enum { POST_NONE = 0, POST_FOUT = 1, POST_GOUT = 2, POST_BIN = 3, POST_GOUT_BIN = 4 };
-
-struct RStep {
-  const float* aux[R_MAXA];   // forward: bias [H];  backward: row-major activation whose sign masks the gradient
-  float* out_rm[R_MAXA];      // row-major [n][H] copy of the output (NULL: only the cluster needs it)
-  int nA, bwd, shared_w, kper, post;
-  int _pad;
-};
-
-struct RowsParams {
+struct StreamParams {
   cur_net_desc d;
-  int in_sp, in_sq, in_g, KP, L, nw, nsteps;
+  int in_sp, in_sq, in_g, KP, L, nchunks;
   int64_t n;
   const float *o, *g, *u, *td, *o_2, *g_2, *r;
   const float *o_mean, *o_std, *g_mean, *g_std;
   float gamma, clip_return, action_l2;
   int clip_pos;
+  const float *bP[S_MAXL], *bPT[S_MAXL], *bQ[S_MAXL], *bQT[S_MAXL];
   const float *WoutP, *boutP, *WoutPT, *boutPT, *WoutQ, *boutQ, *WoutQT, *boutQT;
   const float* W0Q_act;      // main Q first-layer rows of the action inputs: [dimu][H]
+  int ch0[2];                // chunks of a first layer: [0] pi nets, [1] Q nets
   float *Xp, *Xq;            // [n][KP] first-layer inputs of main.pi / main.Q(u)   (weight-gradient operands)
-  const float *hq_last, *hqp_last, *hp_last;    // row-major last hidden activations (ReLU masks of the seeds)
-  float *dc_last, *dp_last;  // row-major gradients at the last hidden layer
+  float *hp[S_MAXL], *hq[S_MAXL], *hqp[S_MAXL], *dc[S_MAXL], *dp[S_MAXL];   // row-major [n][256]
   float *dQ, *dy;            // [n], [n][lddy]
   int lddy;
-  float* loss_part;          // [n / 16][4]
+  float* loss_part;          // [n / 4][4]
   float* q_pi;               // [n]
-  long long* tl;            // optional debug timeline (clock64 stamps of CTA 0), CUR_ROWS_TIMELINE=1
-  WDesc wd[R_MAXW];
-  RStep steps[R_MAXS];
+  long long* tl;             // optional debug timeline (clock64 stamps of CTA 0), CUR_ROWS_TIMELINE=1
+  int dbg_skip_math;         // debug: consumers only wait/release (measures the pure streaming rate)
+  SChunk chunks[S_MAXCHUNK];
 };
 
-#define R_TL(i)                                                                   \
+#define S_TL(i)                                                                   \
   do {                                                                            \
     if (P.tl != nullptr && threadIdx.x == 0 && blockIdx.x == 0) P.tl[i] = clock64(); \
   } while (0)
 
-struct Lane {
-  int cp, s;      // column pair (0..15) and k-slice (0..15) of this thread (GEMM role)
-  int col, rq;    // column (0..31) and row quad (0..3) this thread finishes (epilogue role), group = tid >> 7
+// ---------------------------------------------------------------- mbarrier / bulk-copy primitives
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(S_CONSUMERS) : "memory"); }
+
+struct Ring {
+  const float* slots;
+  uint32_t full, empty;     // shared addresses of the barrier arrays (8 bytes per slot)
+  int cons;                 // chunks consumed so far
 };
 
-// Load this thread's weights of one net-layer into registers: wr[kk] = W[k = s*kper + kk][cols 2cp, 2cp+1]
-// (forward) or the transposed equivalent (backward: rows 32*rank + 2cp + {0,1}, k contiguous).
-__device__ __forceinline__ void load_w(const RowsParams& P, int idx, int rank, const Lane& ln, float2 (&wr)[16]) {
-  if (idx >= P.nw) return;
-  const float* w = P.wd[idx].w;
-  const int kind = P.wd[idx].kind;
-  if (kind == 0) {
-    const float2* p = reinterpret_cast<const float2*>(w + (int64_t)(ln.s * 16) * R_H + rank * R_CW + 2 * ln.cp);
+// ---------------------------------------------------------------- the GEMV core
+// Blackwell issues a scalar FFMA only every other cycle per scheduler; full FP32 rate needs the packed FFMA2
+// (fma.rn.f32x2, __ffma2_rn): two IEEE fmas per lane per instruction.  Accumulators are therefore kept as row
+// pairs: acc[p][c] = (row 2p, row 2p+1) of column 4cg + c, the activation pair comes straight out of the
+// transposed tile's float4 and only the weight is duplicated.  Each half is a plain fma.rn, so results are
+// bit-identical to the scalar form.
+template <int NR>
+__device__ __forceinline__ void fma_row(float2 (&acc)[NR / 2][4], const float* __restrict__ xs, float4 w) {
+  const float2 w0 = make_float2(w.x, w.x), w1 = make_float2(w.y, w.y), w2 = make_float2(w.z, w.z),
+               w3 = make_float2(w.w, w.w);
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) wr[kk] = __ldg(p + kk * (R_H / 2));
-  } else if (kind == 1) {
-    const float4* r0 = reinterpret_cast<const float4*>(w + (int64_t)(rank * R_CW + 2 * ln.cp) * R_H + ln.s * 16);
-    const float4* r1 = r0 + R_H / 4;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 a = __ldg(r0 + q);
-      const float4 b = __ldg(r1 + q);
-      wr[4 * q + 0] = make_float2(a.x, b.x);
-      wr[4 * q + 1] = make_float2(a.y, b.y);
-      wr[4 * q + 2] = make_float2(a.z, b.z);
-      wr[4 * q + 3] = make_float2(a.w, b.w);
-    }
-  } else {
-    const float* w2 = P.wd[idx].w2;
-    const int split = P.wd[idx].split, kvalid = P.wd[idx].kvalid, kper = P.wd[idx].kper;
-    const int col = rank * R_CW + 2 * ln.cp;
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float2 v = make_float2(0.f, 0.f);
-      const int gk = ln.s * kper + kk;
-      if (kk < kper && gk < kvalid) {
-        const float* src = (gk < split) ? w + (int64_t)gk * R_H : w2 + (int64_t)(gk - split) * R_H;
-        v = __ldg(reinterpret_cast<const float2*>(src + col));
-      }
-      wr[kk] = v;
-    }
+  for (int q = 0; q < NR / 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(xs + 4 * q);
+    const float2 xa = make_float2(v.x, v.y), xb = make_float2(v.z, v.w);
+    acc[2 * q][0] = __ffma2_rn(xa, w0, acc[2 * q][0]);
+    acc[2 * q][1] = __ffma2_rn(xa, w1, acc[2 * q][1]);
+    acc[2 * q][2] = __ffma2_rn(xa, w2, acc[2 * q][2]);
+    acc[2 * q][3] = __ffma2_rn(xa, w3, acc[2 * q][3]);
+    acc[2 * q + 1][0] = __ffma2_rn(xb, w0, acc[2 * q + 1][0]);
+    acc[2 * q + 1][1] = __ffma2_rn(xb, w1, acc[2 * q + 1][1]);
+    acc[2 * q + 1][2] = __ffma2_rn(xb, w2, acc[2 * q + 1][2]);
+    acc[2 * q + 1][3] = __ffma2_rn(xb, w3, acc[2 * q + 1][3]);
   }
 }
 
-// acc[r][c] = sum over this thread's k-slice of tile[k][r] * w[k][c];  then the two k-slices of the warp are
-// combined and lanes 0..15 park the warp's partial, transposed [32 cols][16 rows], in `red`.
-__device__ __forceinline__ void slice_gemm(const float* __restrict__ tile, const float2 (&wr)[16], int kper,
-                                           const Lane& ln, float* __restrict__ red) {
-  float acc[R_ROWS][2];
+// acc += sum over this thread's k rows of the next `nchunks` weight chunks of  xT[k][r] * W[k][4cg + c]
+template <int NR>
+__device__ __forceinline__ void gemv_chunks(const StreamParams& P, Ring& rg, int nchunks, const float* __restrict__ xT,
+                                            float2 (&acc)[NR / 2][4]) {
+  const int cg = threadIdx.x & 63, ks = threadIdx.x >> 6;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const int slot = rg.cons % S_NSLOT;
+    const int nrows = P.chunks[rg.cons].nrows, k0 = P.chunks[rg.cons].k0;
+    mbar_wait(rg.full + 8 * slot, (rg.cons / S_NSLOT) & 1);
+    const float* ws = rg.slots + slot * S_SLOT + 4 * cg;
+    const float* xs = xT + (k0 + ks * 8) * NR;
+    if (P.dbg_skip_math) {
+    } else if (nrows == S_CK) {
+      // full chunk (all but the ragged first-layer blocks): no guards, so the LDS.128 of the thread's 8 k rows
+      // are issued up front and the FFMA2s run back to back
+      float4 w[8];
 #pragma unroll
-  for (int r = 0; r < R_ROWS; ++r) acc[r][0] = acc[r][1] = 0.f;
-  const float* base = tile + ln.s * kper * R_ROWS;
+      for (int kk = 0; kk < 8; ++kk) w[kk] = *reinterpret_cast<const float4*>(ws + (ks * 8 + kk) * S_H);
 #pragma unroll
-  for (int kk = 0; kk < 16; ++kk) {
-    if (kk < kper) {
-      float a[R_ROWS];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(base + kk * R_ROWS + 4 * q);
-        a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
-      }
-#pragma unroll
-      for (int r = 0; r < R_ROWS; ++r) {
-        acc[r][0] = fmaf(a[r], wr[kk].x, acc[r][0]);
-        acc[r][1] = fmaf(a[r], wr[kk].y, acc[r][1]);
-      }
+      for (int kk = 0; kk < 8; ++kk) fma_row<NR>(acc, xs + kk * NR, w[kk]);
+    } else {
+#pragma unroll 1
+      for (int kk = 0; kk < 8; ++kk)
+        if (ks * 8 + kk < nrows)
+          fma_row<NR>(acc, xs + kk * NR, *reinterpret_cast<const float4*>(ws + (ks * 8 + kk) * S_H));
     }
-  }
-#pragma unroll
-  for (int r = 0; r < R_ROWS; ++r) {
-    acc[r][0] += __shfl_xor_sync(0xffffffffu, acc[r][0], 16);
-    acc[r][1] += __shfl_xor_sync(0xffffffffu, acc[r][1], 16);
-  }
-  if ((threadIdx.x & 31) < 16) {
-    float* mine = red + (threadIdx.x >> 5) * R_PART + (2 * ln.cp) * R_LDP;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      *reinterpret_cast<float4*>(mine + 4 * q) =
-          make_float4(acc[4 * q][0], acc[4 * q + 1][0], acc[4 * q + 2][0], acc[4 * q + 3][0]);
-      *reinterpret_cast<float4*>(mine + R_LDP + 4 * q) =
-          make_float4(acc[4 * q][1], acc[4 * q + 1][1], acc[4 * q + 2][1], acc[4 * q + 3][1]);
-    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(rg.empty + 8 * slot);
+    ++rg.cons;
   }
 }
 
-// rows 4rq..4rq+3 of column `col` of one net: the 8 warp partials summed in fixed order
-__device__ __forceinline__ float4 reduce_partials(const float* __restrict__ red, const Lane& ln) {
-  const float* p = red + ln.col * R_LDP + 4 * ln.rq;
-  float4 v[8];
+// One dense layer for NR rows: chunks -> split-K partials -> fixed-order sum.  Returns, for the thread's column
+// `col = tid`, the NR pre-activation sums in v[] (without bias).
+template <int NR>
+__device__ __forceinline__ void layer_gemv(const StreamParams& P, Ring& rg, int nchunks, const float* xT, float* red,
+                                           float (&v)[NR]) {
+  float2 acc[NR / 2][4];
 #pragma unroll
-  for (int w = 0; w < 8; ++w) v[w] = *reinterpret_cast<const float4*>(p + w * R_PART);
-  float4 o;
-  o.x = ((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x));
-  o.y = ((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y));
-  o.z = ((v[0].z + v[1].z) + (v[2].z + v[3].z)) + ((v[4].z + v[5].z) + (v[6].z + v[7].z));
-  o.w = ((v[0].w + v[1].w) + (v[2].w + v[3].w)) + ((v[4].w + v[5].w) + (v[6].w + v[7].w));
-  return o;
-}
-
-// store rows 4rq..4rq+3 of global column gcol into activation tile `tile_off` of every CTA of the cluster
-__device__ __forceinline__ void publish(cg::cluster_group& cluster, float* smem_base, int tile_off, int gcol, int rq,
-                                        float4 v) {
-  float* local = smem_base + tile_off + gcol * R_ROWS + 4 * rq;
+  for (int p = 0; p < NR / 2; ++p)
 #pragma unroll
-  for (int p = 0; p < R_CS; ++p) *reinterpret_cast<float4*>(cluster.map_shared_rank(local, p)) = v;
+    for (int c = 0; c < 4; ++c) acc[p][c] = make_float2(0.f, 0.f);
+  gemv_chunks<NR>(P, rg, nchunks, xT, acc);
+  const int cg = threadIdx.x & 63, ks = threadIdx.x >> 6;
+#pragma unroll
+  for (int p = 0; p < NR / 2; ++p) {
+    *reinterpret_cast<float4*>(red + (ks * NR + 2 * p) * S_H + 4 * cg) =
+        make_float4(acc[p][0].x, acc[p][1].x, acc[p][2].x, acc[p][3].x);
+    *reinterpret_cast<float4*>(red + (ks * NR + 2 * p + 1) * S_H + 4 * cg) =
+        make_float4(acc[p][0].y, acc[p][1].y, acc[p][2].y, acc[p][3].y);
+  }
+  consumer_sync();
+  const int col = threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const float* p = red + r * S_H + col;
+    v[r] = (p[0] + p[NR * S_H]) + (p[2 * NR * S_H] + p[3 * NR * S_H]);
+  }
 }
 
-__device__ __forceinline__ void store_rm(float* out_rm, int64_t row0, int gcol, int rq, float4 v) {
-  float* o = out_rm + (row0 + 4 * rq) * R_H + gcol;
-  o[0] = v.x; o[R_H] = v.y; o[2 * R_H] = v.z; o[3 * R_H] = v.w;
+// write the layer output: transposed into shared memory for the next layer, row-major to global for launch 2
+template <int NR>
+__device__ __forceinline__ void put_xT(float* yT, const float (&v)[NR]) {
+  const int col = threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < NR / 4; ++q)
+    *reinterpret_cast<float4*>(yT + col * NR + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
-__device__ __forceinline__ float4 load_mask(const float* rm, int64_t row0, int gcol, int rq) {
-  const float* m = rm + (row0 + 4 * rq) * R_H + gcol;
-  return make_float4(__ldcg(m), __ldcg(m + R_H), __ldcg(m + 2 * R_H), __ldcg(m + 3 * R_H));
-}
-
-__device__ __forceinline__ float4 mask4(float4 v, float4 m) {
-  return make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f);
-}
-
-__device__ __forceinline__ float norm1r(float x, const float* mean, const float* std, int k, float clip) {
+__device__ __forceinline__ float norm1s(float x, const float* mean, const float* std, int k, float clip) {
   float v = __fdiv_rn(__fsub_rn(x, mean[k]), std[k]);          // normalizer.py:72-77
   return fminf(fmaxf(v, -clip), clip);
 }
 
-// Element (row r, column k) of a first-layer input [o | task_descr | action | g] (modular) or [o | g | action]
+// Element (row, column k) of a first-layer input [o | task_descr | action | g] (modular) or [o | g | action]
 // (flat), zero beyond the fan-in (actor_critic.py:76-91).  act_kind: 0 none (pi net), 1 u / max_u, 2 `ths`.
-__device__ __forceinline__ float x_elem(const RowsParams& P, int64_t row, int r, int k, bool target, int act_kind,
+__device__ __forceinline__ float x_elem(const StreamParams& P, int64_t row, int r, int k, bool target, int act_kind,
                                         const float* ths) {
   const cur_net_desc& d = P.d;
   const bool nrm = d.normalize_obs != 0;
@@ -248,7 +232,7 @@ __device__ __forceinline__ float x_elem(const RowsParams& P, int64_t row, int r,
   int gj = -1, aj = -1;
   if (k < d.dimo) {
     v = o[row * d.dimo + k];
-    if (nrm) v = norm1r(v, P.o_mean, P.o_std, k, d.norm_clip);
+    if (nrm) v = norm1s(v, P.o_mean, P.o_std, k, d.norm_clip);
   } else if (d.modular) {
     if (k < d.dimo + d.dimtd) v = P.td[row * d.dimtd + (k - d.dimo)];     // never normalised
     else if (k < in_s) aj = k - d.dimo - d.dimtd;
@@ -259,270 +243,323 @@ __device__ __forceinline__ float x_elem(const RowsParams& P, int64_t row, int r,
   }
   if (gj >= 0) {
     v = g[row * d.dimg + gj];
-    if (nrm) v = norm1r(v, P.g_mean, P.g_std, gj, d.norm_clip);
+    if (nrm) v = norm1s(v, P.g_mean, P.g_std, gj, d.norm_clip);
   }
-  if (aj >= 0) v = (act_kind == 1) ? __fdiv_rn(P.u[row * d.dimu + aj], d.max_u) : ths[r * R_DU + aj];
+  if (aj >= 0) v = (act_kind == 1) ? __fdiv_rn(P.u[row * d.dimu + aj], d.max_u) : ths[r * S_DU + aj];
   return v;
 }
 
-// transposed first-layer tile [KP][16]; optionally also the row-major [n][KP] copy for the weight gradient
-__device__ __noinline__ void build_x(const RowsParams& P, float* tile, int64_t row0, bool target, int act_kind,
-                                     const float* ths, float* gout) {
-  for (int idx = threadIdx.x; idx < R_ROWS * P.KP; idx += R_THREADS) {
-    const int k = idx >> 4, r = idx & 15;
-    tile[idx] = x_elem(P, row0 + r, r, k, target, act_kind, ths);
+// transposed first-layer input xT[k][NR] for rows [roff, roff + 4) of the buffer; optional row-major global copy
+__device__ __noinline__ void build_x(const StreamParams& P, float* xT, int NR, int roff, int64_t row0, bool target,
+                                     int act_kind, const float* ths, float* gout) {
+  for (int idx = threadIdx.x; idx < S_ROWS * P.KP; idx += S_CONSUMERS) {
+    const int k = idx >> 2, r = idx & 3;
+    xT[k * NR + roff + r] = x_elem(P, row0 + r, r, k, target, act_kind, ths);
   }
   if (gout) {
-    for (int idx = threadIdx.x; idx < R_ROWS * P.KP; idx += R_THREADS) {
+    for (int idx = threadIdx.x; idx < S_ROWS * P.KP; idx += S_CONSUMERS) {
       const int r = idx / P.KP, k = idx - r * P.KP;
       gout[(row0 + r) * P.KP + k] = x_elem(P, row0 + r, r, k, target, act_kind, ths);
     }
   }
 }
 
-// partial[part][r][j] = sum over k in [16 part, 16 part + 16) of tile[k][r] * W[k * ldk + j * ldj], j < NOUT.
-// 16 rows x 16 k-parts = 256 threads; the 16 lanes of a half warp read the same weight (broadcast).
-template <int NOUT>
-__device__ __forceinline__ void rowdot_partial(const float* __restrict__ tile, const float* __restrict__ W, int ldk,
-                                               int ldj, float* __restrict__ scratch) {
-  const int r = threadIdx.x & 15, part = threadIdx.x >> 4;
-  float acc[NOUT];
-#pragma unroll
-  for (int j = 0; j < NOUT; ++j) acc[j] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < 16; ++kk) {
-    const int k = part * 16 + kk;
-    const float x = tile[k * R_ROWS + r];
-#pragma unroll
-    for (int j = 0; j < NOUT; ++j) acc[j] = fmaf(x, __ldg(W + (int64_t)k * ldk + (int64_t)j * ldj), acc[j]);
-  }
-#pragma unroll
-  for (int j = 0; j < NOUT; ++j) scratch[(part * R_ROWS + r) * R_DU + j] = acc[j];
-}
-
-__device__ __noinline__ void rowdot(const float* tile, const float* W, int ldk, int ldj, int nout, float* scratch) {
-  if (nout == 1) rowdot_partial<1>(tile, W, ldk, ldj, scratch);
-  else if (nout == 4) rowdot_partial<4>(tile, W, ldk, ldj, scratch);
-  else
-    for (int j = 0; j < nout; ++j) rowdot_partial<1>(tile, W + (int64_t)j * ldj, ldk, ldj, scratch + j);
-}
-
-// out[r][j] = sum over the 16 k-parts (fixed order) + bias[j];  call with all threads after a __syncthreads
-__device__ __forceinline__ void rowdot_finish(const float* scratch, int nout, const float* bias, float* out) {
-  if (threadIdx.x < R_ROWS * R_DU) {
-    const int r = threadIdx.x >> 3, j = threadIdx.x & (R_DU - 1);
-    if (j < nout) {
-      float v = 0.f;
-#pragma unroll
-      for (int p = 0; p < 16; ++p) v += scratch[(p * R_ROWS + r) * R_DU + j];
-      out[threadIdx.x] = v + (bias ? bias[j] : 0.f);
+// y[r][j] = sum_k xT[k][r] * W[k * ldk + j * ldj] + bias[j]  for r < NR, j < nout (NR * nout <= 32), K = 256.
+// 8 k-parts per output (interleaved k), combined with a fixed shuffle tree; every thread must call it.
+__device__ __noinline__ void small_out(const float* xT, int NR, int roff, int nr, const float* __restrict__ W, int ldk,
+                                       int ldj, int nout, const float* bias, float* out /* [r][S_DU] */) {
+  const int kp = threadIdx.x & 7, oj = threadIdx.x >> 3;
+  const int r = oj / nout, j = oj - r * nout;
+  const bool on = r < nr;
+  float acc = 0.f;
+  if (on) {
+#pragma unroll 8
+    for (int kk = 0; kk < S_H / 8; ++kk) {
+      const int k = kp + 8 * kk;
+      acc = fmaf(xT[k * NR + roff + r], __ldg(W + (int64_t)k * ldk + (int64_t)j * ldj), acc);
     }
   }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (on && kp == 0) out[r * S_DU + j] = acc + (bias ? bias[j] : 0.f);
 }
 
-__global__ void __cluster_dims__(R_CS, 1, 1) __launch_bounds__(R_THREADS, 2)
-ddpg_rows_kernel(const __grid_constant__ RowsParams P) {
-  extern __shared__ __align__(16) float smem[];
-  float* tiles = smem;
-  float* red = tiles + R_MAXA * R_TILE;
-  float* misc = red + R_MAXA * R_RED;
-  float* s_th = misc;                 // [16][8] tanh output of main.pi (= pi / max_u)
-  float* s_tht = misc + 128;          // target.pi
-  float* s_q = misc + 256;            // [16][8] col 0: main.Q(o,g,u)
-  float* s_qpi = misc + 384;          // main.Q(o,g,pi)
-  float* s_qt = misc + 512;           // target.Q
-  float* s_dq = misc + 640;           // [16] dQ, [16..32) dQpi, [32..48) squared TD error
-  float* s_dy = misc + 768;           // [16][8]
+__device__ __forceinline__ float relu_mask(float v, float m) { return m > 0.f ? v : 0.f; }
 
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const int64_t row0 = (int64_t)(blockIdx.x / R_CS) * R_ROWS;
+__global__ void __launch_bounds__(S_THREADS, 1) ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ringf = reinterpret_cast<float*>(smem_raw);
+  float* xa = ringf + S_NSLOT * S_SLOT;
+  float* xb = xa + S_XT;
+  float* red = xb + S_XT;
+  float* misc = red + S_RED;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + S_MISC);      // full[4], empty[4]
+  float* s_th = misc;                 // [4][8] tanh output of main.pi (= pi / max_u)
+  float* s_tht = misc + 32;           // target.pi
+  float* s_q = misc + 64;             // [8][8]: rows 0-3 main.Q(o,g,u), rows 4-7 main.Q(o,g,pi)
+  float* s_qt = misc + 128;           // [4][8] target.Q
+  float* s_dq = misc + 160;           // [8]: dQ (rows 0-3), dQ_pi (rows 4-7);  [8..12): squared TD error
+  float* s_dy = misc + 192;           // [4][8]
+
   const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * S_ROWS;
   const cur_net_desc& d = P.d;
   const int L = P.L;
-  const float inv_n = 1.0f / (float)P.n;
-  Lane ln;
-  ln.cp = tid & 15;
-  ln.s = 2 * (tid >> 5) + ((tid >> 4) & 1);
-  ln.col = (tid & 127) >> 2;
-  ln.rq = tid & 3;
-  const int group = tid >> 7;                   // which nets of a step this thread finishes: a with (a & 1) == group
-  const int gcol = rank * R_CW + ln.col;
+  const uint32_t full = smem_addr(bars), empty = smem_addr(bars + S_NSLOT);
 
-  float2 wr[16];
-  int wi = 0;
-  R_TL(0);
-  load_w(P, wi, rank, ln, wr);
-
-  // first-layer inputs of main.pi | target.pi | main.Q(o,g,u)
-  build_x(P, tiles + 0 * R_TILE, row0, false, 0, nullptr, rank == 0 ? P.Xp : nullptr);
-  build_x(P, tiles + 1 * R_TILE, row0, true, 0, nullptr, nullptr);
-  build_x(P, tiles + 2 * R_TILE, row0, false, 1, nullptr, rank == 0 ? P.Xq : nullptr);
-  R_TL(1);
-  cluster.sync();        // every CTA of the cluster is running before the first remote store (and tiles are built)
-  R_TL(2);
-
-#pragma unroll 1
-  for (int st = 0; st < P.nsteps; ++st) {
-    const int nA = P.steps[st].nA, bwd = P.steps[st].bwd, shared_w = P.steps[st].shared_w;
-    const int kper = P.steps[st].kper, post = P.steps[st].post;
-    // ---- prefetch what the epilogue of this step needs (bias / ReLU mask), for the nets this thread finishes
-    const int a0 = group, a1 = group + 2;       // group 0: nets 0 and 2;  group 1: net 1
-    float4 aux0 = make_float4(0.f, 0.f, 0.f, 0.f), aux1 = aux0;
-    if (a0 < nA) {
-      const float* ax = P.steps[st].aux[a0];
-      if (!bwd) aux0.x = __ldg(ax + gcol); else aux0 = load_mask(ax, row0, gcol, ln.rq);
+  if (tid == 0) {
+    for (int i = 0; i < S_NSLOT; ++i) {
+      mbar_init(full + 8 * i, 1);
+      mbar_init(empty + 8 * i, S_CONSUMERS / 32);
     }
-    if (a1 < nA) {
-      const float* ax = P.steps[st].aux[a1];
-      if (!bwd) aux1.x = __ldg(ax + gcol); else aux1 = load_mask(ax, row0, gcol, ln.rq);
-    }
-    // ---- the layer GEMMs of this step
-#pragma unroll 1
-    for (int a = 0; a < nA; ++a) {
-      slice_gemm(tiles + a * R_TILE, wr, kper, ln, red + a * R_RED);
-      if (!shared_w || a == nA - 1) load_w(P, ++wi, rank, ln, wr);
-    }
-    R_TL(8 + 8 * st + 0);
-    __syncthreads();
-    R_TL(8 + 8 * st + 1);
-    cluster.barrier_arrive();                   // E1: this thread will not read the tiles of this step again
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-    if (a0 < nA) {
-      v0 = reduce_partials(red + a0 * R_RED, ln);
-      if (!bwd) {
-        v0.x = fmaxf(v0.x + aux0.x, 0.f); v0.y = fmaxf(v0.y + aux0.x, 0.f);
-        v0.z = fmaxf(v0.z + aux0.x, 0.f); v0.w = fmaxf(v0.w + aux0.x, 0.f);
-      } else v0 = mask4(v0, aux0);
-      if (P.steps[st].out_rm[a0]) store_rm(P.steps[st].out_rm[a0], row0, gcol, ln.rq, v0);
-    }
-    if (a1 < nA) {
-      v1 = reduce_partials(red + a1 * R_RED, ln);
-      if (!bwd) {
-        v1.x = fmaxf(v1.x + aux1.x, 0.f); v1.y = fmaxf(v1.y + aux1.x, 0.f);
-        v1.z = fmaxf(v1.z + aux1.x, 0.f); v1.w = fmaxf(v1.w + aux1.x, 0.f);
-      } else v1 = mask4(v1, aux1);
-      if (P.steps[st].out_rm[a1]) store_rm(P.steps[st].out_rm[a1], row0, gcol, ln.rq, v1);
-    }
-    R_TL(8 + 8 * st + 2);
-    cluster.barrier_wait();                     // E1: every CTA of the cluster is done reading its tiles
-    R_TL(8 + 8 * st + 3);
-    if (a0 < nA) publish(cluster, smem, a0 * R_TILE, gcol, ln.rq, v0);
-    if (a1 < nA) publish(cluster, smem, a1 * R_TILE, gcol, ln.rq, v1);
-    R_TL(8 + 8 * st + 4);
-    cluster.barrier_arrive();                   // E2 (release): remote stores issued
-    cluster.barrier_wait();                     // E2 (acquire): all slices of the next layer's input have landed
-    R_TL(8 + 8 * st + 5);
-
-    if (post == POST_FOUT) {
-      // output layers of main.pi | target.pi | main.Q(u), redundantly in every CTA, then the first-layer inputs
-      // of main.Q(o,g,pi) | target.Q(o2,g2,pi_t)
-      rowdot(tiles + 0 * R_TILE, P.WoutP, d.dimu, 1, d.dimu, red);
-      rowdot(tiles + 1 * R_TILE, P.WoutPT, d.dimu, 1, d.dimu, red + 2048);
-      rowdot(tiles + 2 * R_TILE, P.WoutQ, 1, 1, 1, red + 4096);
-      __syncthreads();
-      rowdot_finish(red, d.dimu, P.boutP, s_th);
-      rowdot_finish(red + 2048, d.dimu, P.boutPT, s_tht);
-      rowdot_finish(red + 4096, 1, P.boutQ, s_q);
-      __syncthreads();
-      if (tid < R_ROWS * R_DU && (tid & (R_DU - 1)) < d.dimu) {
-        s_th[tid] = tanhf(s_th[tid]);          // actor_critic.py:89: pi = max_u * tanh(.)
-        s_tht[tid] = tanhf(s_tht[tid]);
-      }
-      __syncthreads();
-      build_x(P, tiles + 0 * R_TILE, row0, false, 2, s_th, nullptr);
-      build_x(P, tiles + 1 * R_TILE, row0, true, 2, s_tht, nullptr);   // same u-slot and td for the target (ddpg.py:427-431)
-      __syncthreads();
-    }
-    if (post == POST_GOUT || post == POST_GOUT_BIN) {
-      rowdot(tiles + 0 * R_TILE, P.WoutQ, 1, 1, 1, red);
-      rowdot(tiles + 1 * R_TILE, P.WoutQT, 1, 1, 1, red + 2048);
-      __syncthreads();
-      rowdot_finish(red, 1, P.boutQ, s_qpi);
-      rowdot_finish(red + 2048, 1, P.boutQT, s_qt);
-      __syncthreads();
-      // losses (ddpg.py:436-441) and backward seeds
-      if (tid < R_ROWS) {
-        const int64_t row = row0 + tid;
-        const float hi = P.clip_pos ? 0.f : INFINITY;
-        const float tgt = fminf(fmaxf(P.r[row] + P.gamma * s_qt[tid * R_DU], -P.clip_return), hi);
-        const float diff = tgt - s_q[tid * R_DU];
-        s_dq[tid] = -2.0f * inv_n * diff;          // d mean((tgt - Q)^2) / dQ
-        s_dq[R_ROWS + tid] = -inv_n;               // d (-mean(Q_pi)) / dQ_pi
-        s_dq[2 * R_ROWS + tid] = diff * diff;
-        if (rank == 0) {
-          P.dQ[row] = s_dq[tid];
-          P.q_pi[row] = s_qpi[tid * R_DU];
-        }
-      }
-      __syncthreads();
-      if (rank == 0 && tid == 0) {
-        float ssq = 0.f, sq = 0.f, sth = 0.f;
-        for (int r = 0; r < R_ROWS; ++r) {
-          ssq += s_dq[2 * R_ROWS + r];
-          sq += s_qpi[r * R_DU];
-          for (int j = 0; j < d.dimu; ++j) sth += s_th[r * R_DU + j] * s_th[r * R_DU + j];
-        }
-        float* lp = P.loss_part + (blockIdx.x / R_CS) * 4;
-        lp[0] = ssq; lp[1] = sq; lp[2] = sth; lp[3] = 0.f;
-      }
-      // critic / actor-through-critic gradients at the last hidden layer: dY * Wout^T (Wout is [H][1]),
-      // group 0 -> critic chain into tile 0, group 1 -> actor-through-critic chain into tile 1
-      cluster.barrier_arrive();                 // E1 (the rowdots above were the last readers of the tiles)
-      {
-        const float wq = __ldg(P.WoutQ + gcol);
-        const float4 m = load_mask(group == 0 ? P.hq_last : P.hqp_last, row0, gcol, ln.rq);
-        const float* sd = s_dq + group * R_ROWS + 4 * ln.rq;
-        float4 v = mask4(make_float4(sd[0] * wq, sd[1] * wq, sd[2] * wq, sd[3] * wq), m);
-        if (group == 0) store_rm(P.dc_last, row0, gcol, ln.rq, v);
-        cluster.barrier_wait();
-        publish(cluster, smem, group * R_TILE, gcol, ln.rq, v);
-      }
-      cluster.barrier_arrive();
-      cluster.barrier_wait();
-    }
-    if (post == POST_BIN || post == POST_GOUT_BIN) {
-      // gradient wrt the action inputs of main.Q (tile 1 holds the full actor-through-critic gradient at layer 0),
-      // then through tanh and the action penalty (ddpg.py:440-441):
-      // d pi_loss / d(pre-tanh) = (dL/d(pi/max_u) + action_l2 * 2/(B*dimu) * th) * (1 - th^2)
-      rowdot(tiles + 1 * R_TILE, P.W0Q_act, 1, R_H, d.dimu, red);
-      __syncthreads();
-      rowdot_finish(red, d.dimu, nullptr, s_dy);
-      __syncthreads();
-      if (tid < R_ROWS * R_DU) {
-        const int r = tid >> 3, j = tid & (R_DU - 1);
-        float v = 0.f;
-        if (j < d.dimu) {
-          const float coef = P.action_l2 * 2.0f / (float)(P.n * d.dimu);
-          const float th = s_th[tid];
-          v = (s_dy[tid] + coef * th) * (1.f - th * th);
-        }
-        s_dy[tid] = v;
-        if (rank == 0 && j < P.lddy) P.dy[(row0 + r) * P.lddy + j] = v;
-      }
-      __syncthreads();
-      // actor gradient at the last hidden layer: dy * Wout_pi^T, into tile 0
-      cluster.barrier_arrive();
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (group == 0) {
-        const float4 m = load_mask(P.hp_last, row0, gcol, ln.rq);
-        float o4[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int j = 0; j < d.dimu; ++j) {
-          const float wj = __ldg(P.WoutP + (int64_t)gcol * d.dimu + j);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) o4[i] = fmaf(s_dy[(4 * ln.rq + i) * R_DU + j], wj, o4[i]);
-        }
-        v = mask4(make_float4(o4[0], o4[1], o4[2], o4[3]), m);
-        store_rm(P.dp_last, row0, gcol, ln.rq, v);
-      }
-      cluster.barrier_wait();
-      if (group == 0) publish(cluster, smem, 0, gcol, ln.rq, v);
-      cluster.barrier_arrive();
-      cluster.barrier_wait();
-    }
-    R_TL(8 + 8 * st + 6);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  R_TL(3);
+  __syncthreads();
+
+  if (tid >= S_CONSUMERS) {
+    // ------------------------------------------------------------ producer warp: stream every weight chunk
+    if (tid == S_CONSUMERS) {
+      const uint32_t ring_s = smem_addr(ringf);
+      for (int i = 0; i < P.nchunks; ++i) {
+        const int slot = i % S_NSLOT, round = i / S_NSLOT;
+        if (round > 0) mbar_wait(empty + 8 * slot, (round - 1) & 1);
+        const uint32_t bytes = (uint32_t)P.chunks[i].nrows * S_H * 4;
+        mbar_expect_tx(full + 8 * slot, bytes);
+        bulk_g2s(ring_s + slot * S_SLOT * 4, P.chunks[i].src, bytes, full + 8 * slot);
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- consumers
+  Ring rg;
+  rg.slots = ringf; rg.full = full; rg.empty = empty; rg.cons = 0;
+  const int col = tid;
+  const float inv_n = 1.0f / (float)P.n;
+  S_TL(0);
+
+  // ===== stream 1: main.pi =====  (activations ping-pong between xa and xb)
+  build_x(P, xa, 4, 0, row0, false, 0, nullptr, P.Xp);
+  consumer_sync();
+  S_TL(1);
+  {
+    float* xin = xa; float* xout = xb;
+    for (int l = 0; l < L; ++l) {
+      float v[4];
+      layer_gemv<4>(P, rg, l == 0 ? P.ch0[0] : S_H / S_CK, xin, red, v);
+      const float b = P.bP[l][col];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r] = fmaxf(v[r] + b, 0.f);
+        P.hp[l][(row0 + r) * S_H + col] = v[r];
+      }
+      put_xT<4>(xout, v);
+      consumer_sync();
+      float* t = xin; xin = xout; xout = t;
+    }
+    small_out(xin, 4, 0, 4, P.WoutP, d.dimu, 1, d.dimu, P.boutP, s_th);
+    consumer_sync();
+  }
+  S_TL(2);
+  // ===== stream 2: target.pi =====
+  build_x(P, xa, 4, 0, row0, true, 0, nullptr, nullptr);      // (xa is free: L >= 1 layers later the input is dead)
+  consumer_sync();
+  {
+    float* xin = xa; float* xout = xb;
+    for (int l = 0; l < L; ++l) {
+      float v[4];
+      layer_gemv<4>(P, rg, l == 0 ? P.ch0[0] : S_H / S_CK, xin, red, v);
+      const float b = P.bPT[l][col];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[r] = fmaxf(v[r] + b, 0.f);
+      put_xT<4>(xout, v);
+      consumer_sync();
+      float* t = xin; xin = xout; xout = t;
+    }
+    small_out(xin, 4, 0, 4, P.WoutPT, d.dimu, 1, d.dimu, P.boutPT, s_tht);
+  }
+  consumer_sync();
+  if (tid < S_ROWS * S_DU && (tid & (S_DU - 1)) < d.dimu) {
+    s_th[tid] = tanhf(s_th[tid]);            // actor_critic.py:89: pi = max_u * tanh(.)
+    s_tht[tid] = tanhf(s_tht[tid]);
+  }
+  consumer_sync();
+  S_TL(3);
+  // ===== stream 3: main.Q on rows 0-3 = (o,g,u) and rows 4-7 = (o,g,pi), sharing one pass over the weights =====
+  build_x(P, xa, 8, 0, row0, false, 1, nullptr, P.Xq);
+  build_x(P, xa, 8, 4, row0, false, 2, s_th, nullptr);
+  consumer_sync();
+  {
+    float* xin = xa; float* xout = xb;
+    for (int l = 0; l < L; ++l) {
+      float v[8];
+      layer_gemv<8>(P, rg, l == 0 ? P.ch0[1] : S_H / S_CK, xin, red, v);
+      const float b = P.bQ[l][col];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = fmaxf(v[r] + b, 0.f);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        P.hq[l][(row0 + r) * S_H + col] = v[r];
+        P.hqp[l][(row0 + r) * S_H + col] = v[4 + r];
+      }
+      put_xT<8>(xout, v);
+      consumer_sync();
+      float* t = xin; xin = xout; xout = t;
+    }
+    small_out(xin, 8, 0, 8, P.WoutQ, 1, 1, 1, P.boutQ, s_q);
+    consumer_sync();
+  }
+  S_TL(4);
+  // ===== stream 4: target.Q(o2, g2, pi_target) with the same u-slot and td (ddpg.py:427-431) =====
+  build_x(P, xa, 4, 0, row0, true, 2, s_tht, nullptr);
+  consumer_sync();
+  {
+    float* xin = xa; float* xout = xb;
+    for (int l = 0; l < L; ++l) {
+      float v[4];
+      layer_gemv<4>(P, rg, l == 0 ? P.ch0[1] : S_H / S_CK, xin, red, v);
+      const float b = P.bQT[l][col];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[r] = fmaxf(v[r] + b, 0.f);
+      put_xT<4>(xout, v);
+      consumer_sync();
+      float* t = xin; xin = xout; xout = t;
+    }
+    small_out(xin, 4, 0, 4, P.WoutQT, 1, 1, 1, P.boutQT, s_qt);
+  }
+  consumer_sync();
+  S_TL(5);
+  // ===== losses (ddpg.py:436-441) and backward seeds =====
+  if (tid < S_ROWS) {
+    const int64_t row = row0 + tid;
+    const float hi = P.clip_pos ? 0.f : INFINITY;
+    const float tgt = fminf(fmaxf(P.r[row] + P.gamma * s_qt[tid * S_DU], -P.clip_return), hi);
+    const float diff = tgt - s_q[tid * S_DU];
+    s_dq[tid] = -2.0f * inv_n * diff;          // d mean((tgt - Q)^2) / dQ
+    s_dq[4 + tid] = -inv_n;                    // d (-mean(Q_pi)) / dQ_pi
+    s_dq[8 + tid] = diff * diff;
+    P.dQ[row] = s_dq[tid];
+    P.q_pi[row] = s_q[(4 + tid) * S_DU];
+  }
+  consumer_sync();
+  if (tid == 0) {
+    float ssq = 0.f, sq = 0.f, sth = 0.f;
+    for (int r = 0; r < S_ROWS; ++r) {
+      ssq += s_dq[8 + r];
+      sq += s_q[(4 + r) * S_DU];
+      for (int j = 0; j < d.dimu; ++j) sth += s_th[r * S_DU + j] * s_th[r * S_DU + j];
+    }
+    float* lp = P.loss_part + (int64_t)blockIdx.x * 4;
+    lp[0] = ssq; lp[1] = sq; lp[2] = sth; lp[3] = 0.f;
+  }
+  // ===== stream 5: backward through main.Q, critic chain (rows 0-3) and actor-through-critic chain (rows 4-7) =====
+  {
+    float* xin = xa; float* xout = xb;
+    {
+      // gradient at the last hidden layer: dY * Wout^T (Wout is [H][1]), masked by the layer's ReLU
+      const float wq = __ldg(P.WoutQ + col);
+      float v[8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r] = relu_mask(s_dq[r] * wq, __ldcg(P.hq[L - 1] + (row0 + r) * S_H + col));
+        v[4 + r] = relu_mask(s_dq[4 + r] * wq, __ldcg(P.hqp[L - 1] + (row0 + r) * S_H + col));
+        P.dc[L - 1][(row0 + r) * S_H + col] = v[r];
+      }
+      put_xT<8>(xin, v);
+      consumer_sync();
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      float m[8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {           // ReLU masks of layer l-1, fetched while the chunks stream
+        m[r] = __ldcg(P.hq[l - 1] + (row0 + r) * S_H + col);
+        m[4 + r] = __ldcg(P.hqp[l - 1] + (row0 + r) * S_H + col);
+      }
+      float v[8];
+      layer_gemv<8>(P, rg, S_H / S_CK, xin, red, v);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = relu_mask(v[r], m[r]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) P.dc[l - 1][(row0 + r) * S_H + col] = v[r];
+      put_xT<8>(xout, v);
+      consumer_sync();
+      float* t = xin; xin = xout; xout = t;
+    }
+    // gradient wrt the action inputs of main.Q (rows 4-7 = actor chain at layer 0), then through tanh and the
+    // action penalty (ddpg.py:440-441): d pi_loss/d(pre-tanh) = (dL/d(pi/max_u) + action_l2*2/(B*dimu)*th) * (1 - th^2)
+    small_out(xin, 8, 4, 4, P.W0Q_act, 1, S_H, d.dimu, nullptr, s_dy);
+    consumer_sync();
+    if (tid < S_ROWS * S_DU) {
+      const int r = tid >> 3, j = tid & (S_DU - 1);
+      float v = 0.f;
+      if (j < d.dimu) {
+        const float coef = P.action_l2 * 2.0f / (float)(P.n * d.dimu);
+        const float th = s_th[tid];
+        v = (s_dy[tid] + coef * th) * (1.f - th * th);
+      }
+      s_dy[tid] = v;
+      if (j < P.lddy) P.dy[(row0 + r) * P.lddy + j] = v;
+    }
+    consumer_sync();
+  }
+  S_TL(6);
+  // ===== stream 6: backward through main.pi =====
+  {
+    float* xin = xa; float* xout = xb;
+    {
+      float v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[r] = 0.f;
+      for (int j = 0; j < d.dimu; ++j) {
+        const float wj = __ldg(P.WoutP + (int64_t)col * d.dimu + j);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = fmaf(s_dy[r * S_DU + j], wj, v[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r] = relu_mask(v[r], __ldcg(P.hp[L - 1] + (row0 + r) * S_H + col));
+        P.dp[L - 1][(row0 + r) * S_H + col] = v[r];
+      }
+      put_xT<4>(xin, v);
+      consumer_sync();
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      float m[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) m[r] = __ldcg(P.hp[l - 1] + (row0 + r) * S_H + col);
+      float v[4];
+      layer_gemv<4>(P, rg, S_H / S_CK, xin, red, v);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r] = relu_mask(v[r], m[r]);
+        P.dp[l - 1][(row0 + r) * S_H + col] = v[r];
+      }
+      put_xT<4>(xout, v);
+      consumer_sync();
+      float* t = xin; xin = xout; xout = t;
+    }
+  }
+  S_TL(7);
+}
+
+// W^T of the hidden layers (operands of the backward streams): dst[m][j][i] = src_m[i][j], 256 x 256 each
+struct TransposeParams {
+  const float* src[2 * S_MAXL];
+  float* dst[2 * S_MAXL];
+};
+
+__global__ void __launch_bounds__(256) transpose_kernel(const __grid_constant__ TransposeParams T) {
+  __shared__ float tile[32][33];
+  const float* src = T.src[blockIdx.z];
+  float* dst = T.dst[blockIdx.z];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tile[ty + 8 * q][tx] = src[(int64_t)(i0 + ty + 8 * q) * S_H + j0 + tx];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dst[(int64_t)(j0 + ty + 8 * q) * S_H + i0 + tx] = tile[tx][ty + 8 * q];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -590,7 +627,8 @@ struct RowsWorkspace {
   unsigned int* ticket;
   float* loss_part;
   float *Xp, *Xq;
-  float *hp[R_MAXL], *hq[R_MAXL], *hqp[R_MAXL], *dc[R_MAXL], *dp[R_MAXL];   // row-major [n][256]
+  float *hp[S_MAXL], *hq[S_MAXL], *hqp[S_MAXL], *dc[S_MAXL], *dp[S_MAXL];   // row-major [n][256]
+  float *TQ[S_MAXL], *TP[S_MAXL];                                            // W_l^T, l = 1..L-1
   float *dQ, *dy;
   int KP, lddy;
   int64_t total;
@@ -600,7 +638,7 @@ static RowsWorkspace carve_rows(const cur_net_desc& d, int64_t n, float* base) {
   RowsWorkspace w;
   const NetLayout q = net_layout(d, 0);
   const int K0q = q.in_s + q.in_g;
-  w.KP = ((K0q + 63) / 64) * 64;
+  w.KP = (int)r4(K0q);
   w.lddy = (int)r4(d.dimu);
   int64_t o = 0;
   auto take = [&](int64_t floats) {
@@ -609,12 +647,14 @@ static RowsWorkspace carve_rows(const cur_net_desc& d, int64_t n, float* base) {
     return ptr;
   };
   w.ticket = reinterpret_cast<unsigned int*>(take(4));
-  w.loss_part = take((n / R_ROWS) * 4);
+  w.loss_part = take((n / S_ROWS) * 4);
   w.Xp = take(n * w.KP);
   w.Xq = take(n * w.KP);
   for (int l = 0; l < d.layers; ++l) {
-    w.hp[l] = take(n * R_H); w.hq[l] = take(n * R_H); w.hqp[l] = take(n * R_H);
-    w.dc[l] = take(n * R_H); w.dp[l] = take(n * R_H);
+    w.hp[l] = take(n * S_H); w.hq[l] = take(n * S_H); w.hqp[l] = take(n * S_H);
+    w.dc[l] = take(n * S_H); w.dp[l] = take(n * S_H);
+    w.TQ[l] = (l >= 1) ? take((int64_t)S_H * S_H) : nullptr;
+    w.TP[l] = (l >= 1) ? take((int64_t)S_H * S_H) : nullptr;
   }
   w.dQ = take(n);
   w.dy = take(n * w.lddy);
@@ -624,10 +664,10 @@ static RowsWorkspace carve_rows(const cur_net_desc& d, int64_t n, float* base) {
 
 static bool rows_supported(const cur_net_desc* d, int64_t n) {
   if (check_desc(d) != CUR_OK) return false;
-  if (d->hidden != R_H || d->layers < 1 || d->layers > R_MAXL) return false;
-  if (d->dimu > R_DU || n <= 0 || (n % R_ROWS) != 0 || n >= (1 << 24)) return false;
+  if (d->hidden != S_H || d->layers < 1 || d->layers > S_MAXL) return false;
+  if (d->dimu > S_DU || n <= 0 || (n % S_ROWS) != 0 || n >= (1 << 24)) return false;
   const NetLayout q = net_layout(*d, 0);
-  if (q.in_s + q.in_g > R_H) return false;
+  if (q.in_s + q.in_g > S_H) return false;
   return true;
 }
 
@@ -667,13 +707,26 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   const int L = d->layers, H = d->hidden;
 
   static bool configured = false;
-  const size_t smem = R_SMEM_FLOATS * sizeof(float);
   if (!configured) {
-    CUR_CUDA_TRY(cudaFuncSetAttribute(ddpg_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUR_CUDA_TRY(cudaFuncSetAttribute(ddpg_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)S_SMEM_BYTES));
     configured = true;
   }
 
-  RowsParams P;
+  // ---- launch 0: W_l^T of the hidden layers of main.Q and main.pi
+  if (L > 1) {
+    TransposeParams TP;
+    memset(&TP, 0, sizeof(TP));
+    int m = 0;
+    for (int l = 1; l < L; ++l) {
+      TP.src[m] = mQ + LQ.off_W[l]; TP.dst[m++] = w.TQ[l];
+      TP.src[m] = mP + LP.off_W[l]; TP.dst[m++] = w.TP[l];
+    }
+    transpose_kernel<<<dim3(H / 32, H / 32, m), 256, 0, s>>>(TP);
+    CUR_CHECK_LAUNCH();
+  }
+
+  StreamParams P;
   memset(&P, 0, sizeof(P));
   P.d = *d;
   P.in_sp = LP.in_s; P.in_sq = LQ.in_s; P.in_g = LQ.in_g; P.KP = w.KP; P.L = L;
@@ -682,84 +735,59 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   P.r = batch->r;
   if (stats) { P.o_mean = stats->o_mean; P.o_std = stats->o_std; P.g_mean = stats->g_mean; P.g_std = stats->g_std; }
   P.gamma = h->gamma; P.clip_return = h->clip_return; P.action_l2 = h->action_l2; P.clip_pos = h->clip_pos_returns;
+  for (int l = 0; l < L; ++l) {
+    const int64_t bq = (l == 0) ? LQ.off_b0 : LQ.off_b[l], bp = (l == 0) ? LP.off_b0 : LP.off_b[l];
+    P.bP[l] = mP + bp; P.bPT[l] = tP + bp; P.bQ[l] = mQ + bq; P.bQT[l] = tQ + bq;
+    P.hp[l] = w.hp[l]; P.hq[l] = w.hq[l]; P.hqp[l] = w.hqp[l]; P.dc[l] = w.dc[l]; P.dp[l] = w.dp[l];
+  }
   P.WoutP = mP + LP.off_Wout; P.boutP = mP + LP.off_bout; P.WoutPT = tP + LP.off_Wout; P.boutPT = tP + LP.off_bout;
   P.WoutQ = mQ + LQ.off_Wout; P.boutQ = mQ + LQ.off_bout; P.WoutQT = tQ + LQ.off_Wout; P.boutQT = tQ + LQ.off_bout;
   P.W0Q_act = mQ + LQ.off_W0 + (int64_t)LP.in_s * H;
   P.Xp = w.Xp; P.Xq = w.Xq; P.dQ = w.dQ; P.dy = w.dy; P.lddy = w.lddy;
-  P.hq_last = w.hq[L - 1]; P.hqp_last = w.hqp[L - 1]; P.hp_last = w.hp[L - 1];
-  P.dc_last = w.dc[L - 1]; P.dp_last = w.dp[L - 1];
   P.loss_part = w.loss_part; P.q_pi = q_pi;
 
-  // ---- steps and net-layer weight descriptors, in consumption order
-  int nw = 0, ns = 0;
-  auto first_layer = [&](const float* th, const NetLayout& NL) {
-    WDesc& D = P.wd[nw++];
-    D.w = th + NL.off_W0; D.w2 = th + NL.off_W0g; D.split = NL.in_s; D.kvalid = NL.in_s + NL.in_g;
-    D.kper = w.KP / R_NSLICE; D.kind = 2;
+  // ---- weight chunks in consumption order
+  int nc = 0;
+  auto rows_of = [&](const float* src, int nrows, int k0) {      // a row block as chunks of <= 32 rows
+    for (int r = 0; r < nrows; r += S_CK) {
+      SChunk& C = P.chunks[nc++];
+      C.src = src + (int64_t)r * H; C.nrows = (nrows - r < S_CK) ? nrows - r : S_CK; C.k0 = k0 + r;
+    }
   };
-  auto hidden_layer = [&](const float* th, const NetLayout& NL, int l, int bwd) {
-    WDesc& D = P.wd[nw++];
-    D.w = th + NL.off_W[l]; D.w2 = nullptr; D.split = H; D.kvalid = H; D.kper = H / R_NSLICE; D.kind = bwd ? 1 : 0;
+  auto forward_net = [&](const float* th, const NetLayout& NL) {
+    const int before = nc;
+    rows_of(th + NL.off_W0, NL.in_s, 0);
+    if (NL.in_g > 0) rows_of(th + NL.off_W0g, NL.in_g, NL.in_s);
+    const int first = nc - before;
+    for (int l = 1; l < L; ++l) rows_of(th + NL.off_W[l], H, 0);
+    return first;
   };
-  auto bias = [&](const float* th, const NetLayout& NL, int l) { return th + (l == 0 ? NL.off_b0 : NL.off_b[l]); };
-  for (int l = 0; l < L; ++l) {                       // forward 1: main.pi | target.pi | main.Q(u)
-    RStep& S = P.steps[ns++];
-    S.nA = 3; S.bwd = 0; S.shared_w = 0; S.kper = (l == 0 ? w.KP : H) / R_NSLICE;
-    S.post = (l == L - 1) ? POST_FOUT : POST_NONE;
-    S.aux[0] = bias(mP, LP, l); S.aux[1] = bias(tP, LP, l); S.aux[2] = bias(mQ, LQ, l);
-    S.out_rm[0] = w.hp[l]; S.out_rm[1] = nullptr; S.out_rm[2] = w.hq[l];
-    if (l == 0) { first_layer(mP, LP); first_layer(tP, LP); first_layer(mQ, LQ); }
-    else { hidden_layer(mP, LP, l, 0); hidden_layer(tP, LP, l, 0); hidden_layer(mQ, LQ, l, 0); }
-  }
-  for (int l = 0; l < L; ++l) {                       // forward 2: main.Q(pi) | target.Q
-    RStep& S = P.steps[ns++];
-    S.nA = 2; S.bwd = 0; S.shared_w = 0; S.kper = (l == 0 ? w.KP : H) / R_NSLICE;
-    S.post = (l == L - 1) ? (L == 1 ? POST_GOUT_BIN : POST_GOUT) : POST_NONE;
-    S.aux[0] = bias(mQ, LQ, l); S.aux[1] = bias(tQ, LQ, l);
-    S.out_rm[0] = w.hqp[l]; S.out_rm[1] = nullptr;
-    if (l == 0) { first_layer(mQ, LQ); first_layer(tQ, LQ); }
-    else { hidden_layer(mQ, LQ, l, 0); hidden_layer(tQ, LQ, l, 0); }
-  }
-  for (int l = L - 1; l >= 1; --l) {                  // backward 1: critic | actor-through-critic share main.Q's W_l
-    RStep& S = P.steps[ns++];
-    S.nA = 2; S.bwd = 1; S.shared_w = 1; S.kper = H / R_NSLICE;
-    S.post = (l == 1) ? POST_BIN : POST_NONE;
-    S.aux[0] = w.hq[l - 1]; S.aux[1] = w.hqp[l - 1];
-    S.out_rm[0] = w.dc[l - 1]; S.out_rm[1] = nullptr;
-    hidden_layer(mQ, LQ, l, 1);
-  }
-  for (int l = L - 1; l >= 1; --l) {                  // backward 2: actor
-    RStep& S = P.steps[ns++];
-    S.nA = 1; S.bwd = 1; S.shared_w = 1; S.kper = H / R_NSLICE; S.post = POST_NONE;
-    S.aux[0] = w.hp[l - 1];
-    S.out_rm[0] = w.dp[l - 1];
-    hidden_layer(mP, LP, l, 1);
-  }
-  P.nw = nw; P.nsteps = ns;
+  P.ch0[0] = forward_net(mP, LP);
+  forward_net(tP, LP);
+  P.ch0[1] = forward_net(mQ, LQ);
+  forward_net(tQ, LQ);
+  for (int l = L - 1; l >= 1; --l) rows_of(w.TQ[l], H, 0);
+  for (int l = L - 1; l >= 1; --l) rows_of(w.TP[l], H, 0);
+  CUR_REQUIRE(nc <= S_MAXCHUNK, "too many weight chunks for the rows schedule");
+  P.nchunks = nc;
 
   static long long* tl_dev = nullptr;
   static int tl_calls = 0;
   const bool tl_on = getenv("CUR_ROWS_TIMELINE") != nullptr;
-  if (tl_on && tl_dev == nullptr) CUR_CUDA_TRY(cudaMalloc(&tl_dev, 256 * sizeof(long long)));
+  if (tl_on && tl_dev == nullptr) CUR_CUDA_TRY(cudaMalloc(&tl_dev, 64 * sizeof(long long)));
   P.tl = tl_on ? tl_dev : nullptr;
+  P.dbg_skip_math = getenv("CUR_ROWS_SKIP_MATH") != nullptr;
 
-  const unsigned int n_clusters = (unsigned int)(n / R_ROWS);
-  ddpg_rows_kernel<<<n_clusters * R_CS, R_THREADS, smem, s>>>(P);
+  const unsigned int n_ctas = (unsigned int)(n / S_ROWS);
+  ddpg_stream_kernel<<<n_ctas, S_THREADS, S_SMEM_BYTES, s>>>(P);
   CUR_CHECK_LAUNCH();
-  if (tl_on && ++tl_calls == 40) {          // debug only: print one warmed-up timeline of CTA 0
-    long long h_tl[256];
+  if (tl_on && ++tl_calls == 40) {          // debug only: one warmed-up timeline of CTA 0
+    long long t[64];
     CUR_CUDA_TRY(cudaStreamSynchronize(s));
-    CUR_CUDA_TRY(cudaMemcpy(h_tl, tl_dev, sizeof(h_tl), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[rows timeline] prologue load_w+build_x %lld, first sync %lld, total %lld cycles\n",
-            h_tl[1] - h_tl[0], h_tl[2] - h_tl[1], h_tl[3] - h_tl[0]);
-    long long prev = h_tl[2];
-    for (int st = 0; st < ns; ++st) {
-      const long long* t = h_tl + 8 + 8 * st;
-      fprintf(stderr, "[rows timeline] step %2d nA=%d bwd=%d post=%d: gemm %6lld sync %5lld reduce %5lld E1wait %5lld publish %5lld E2 %5lld post %6lld\n",
-              st, P.steps[st].nA, P.steps[st].bwd, P.steps[st].post, t[0] - prev, t[1] - t[0], t[2] - t[1], t[3] - t[2],
-              t[4] - t[3], t[5] - t[4], t[6] - t[5]);
-      prev = t[6];
-    }
+    CUR_CUDA_TRY(cudaMemcpy(t, tl_dev, sizeof(t), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[rows timeline] build %lld | main.pi %lld | target.pi %lld | main.Q x2 %lld | target.Q %lld | "
+                    "loss+bwd Q %lld | bwd pi %lld | total %lld cycles\n",
+            t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6], t[7] - t[0]);
   }
 
   // ---- launch 2: weight gradients
@@ -792,7 +820,7 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     T.neg_a_table = adam->neg_a_table; T.table_len = adam->table_len;
   }
   T.step_counter = h->step_counter; T.ring = h->loss_ring;
-  T.ticket = w.ticket; T.loss_part = w.loss_part; T.n_clusters = (int)n_clusters; T.n = n; T.dimu = d->dimu;
+  T.ticket = w.ticket; T.loss_part = w.loss_part; T.n_clusters = (int)n_ctas; T.n = n; T.dimu = d->dimu;
   T.action_l2 = h->action_l2; T.q_loss = q_loss; T.pi_loss = pi_loss;
   rows_dw_kernel<<<tiles, GEMM_THREADS, 0, s>>>(G, T);
   CUR_CHECK_LAUNCH();

@@ -175,7 +175,7 @@ class DDPG(object):
         return self._ws[n]
 
     def _use_rows(self, n):
-        if self.update_schedule in ('levels', 'auto'):      # 'auto' == 'levels' until the rows kernel wins
+        if self.update_schedule == 'levels':
             return False
         ok = bool(_lib.load().cur_ddpg_rows_supported(C.byref(self.net.desc), n))
         if self.update_schedule == 'rows' and not ok:
