@@ -42,12 +42,13 @@ constexpr int S_CK = 32;                 // k rows per weight chunk
 constexpr int S_NSLOT = 4;               // ring slots
 constexpr int S_SLOT = S_CK * S_H;       // floats per slot (32 KB)
 constexpr int S_MAXL = 4;                // hidden layers supported by this schedule
-constexpr int S_MAXCHUNK = 192;          // weight chunks per update (L = 4: 4 * 27 + 2 * 24 = 156)
+constexpr int S_MAXCHUNK = 128;          // weight chunks of the main CTA (L = 4: 2 * 33 + 2 * 24 = 114)
+constexpr int S_MAXCHUNK_T = 72;         // weight chunks of the target CTA (L = 4: 2 * 33 = 66)
 constexpr int S_DU = 8;                  // max action dim
 constexpr int S_XT = S_H * 8;            // floats of one transposed activation buffer [256 k][<= 8 rows]
 constexpr int S_RED = 4 * 8 * S_H;       // split-K partials [4 k-slices][<= 8 rows][256]
 constexpr int S_MISC = 1024;
-constexpr size_t S_SMEM_BYTES = (size_t)(S_NSLOT * S_SLOT + 2 * S_XT + S_RED + S_MISC) * 4 + 128;
+constexpr size_t S_SMEM_BYTES = (size_t)(S_NSLOT * S_SLOT + 2 * S_XT + S_RED + S_MISC) * 4 + 128;   // + 9 mbarriers
 
 struct SChunk {
   const float* src;   // nrows x 256 floats, contiguous
@@ -57,7 +58,7 @@ struct SChunk {
 
 struct StreamParams {
   cur_net_desc d;
-  int in_sp, in_sq, in_g, KP, L, nchunks;
+  int in_sp, in_sq, in_g, KP, L, nchunks, nchunks_t;
   int64_t n;
   const float *o, *g, *u, *td, *o_2, *g_2, *r;
   const float *o_mean, *o_std, *g_mean, *g_std;
@@ -75,7 +76,8 @@ struct StreamParams {
   float* q_pi;               // [n]
   long long* tl;             // optional debug timeline (clock64 stamps of CTA 0), CUR_ROWS_TIMELINE=1
   int dbg_skip_math;         // debug: consumers only wait/release (measures the pure streaming rate)
-  SChunk chunks[S_MAXCHUNK];
+  SChunk chunks[S_MAXCHUNK];       // main CTA: main.pi fwd, main.Q fwd, main.Q^T bwd, main.pi^T bwd
+  SChunk chunks_t[S_MAXCHUNK_T];   // target CTA: target.pi fwd, target.Q fwd
 };
 
 #define S_TL(i)                                                                   \
@@ -111,9 +113,41 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_remote_f32(uint32_t remote_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITC_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAITC_DONE;\n"
+      "bra WAITC_LOOP;\n"
+      "WAITC_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(S_CONSUMERS) : "memory"); }
 
 struct Ring {
+  const SChunk* chunks;     // this CTA's chunk list (kernel-parameter space)
   const float* slots;
   uint32_t full, empty;     // shared addresses of the barrier arrays (8 bytes per slot)
   int cons;                 // chunks consumed so far
@@ -152,7 +186,7 @@ __device__ __forceinline__ void gemv_chunks(const StreamParams& P, Ring& rg, int
 #pragma unroll 1
   for (int c = 0; c < nchunks; ++c) {
     const int slot = rg.cons % S_NSLOT;
-    const int nrows = P.chunks[rg.cons].nrows, k0 = P.chunks[rg.cons].k0;
+    const int nrows = rg.chunks[rg.cons].nrows, k0 = rg.chunks[rg.cons].k0;
     mbar_wait(rg.full + 8 * slot, (rg.cons / S_NSLOT) & 1);
     const float* ws = rg.slots + slot * S_SLOT + 4 * cg;
     const float* xs = xT + (k0 + ks * 8) * NR;
@@ -287,46 +321,84 @@ __device__ __noinline__ void small_out(const float* xT, int NR, int roff, int nr
 
 __device__ __forceinline__ float relu_mask(float v, float m) { return m > 0.f ? v : 0.f; }
 
-__global__ void __launch_bounds__(S_THREADS, 1) ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
+// One forward net for NR rows: L hidden layers (bias + ReLU) from the first-layer input already in `xa`; optional
+// row-major copies of every hidden activation (rows 0-3 -> h_a, rows 4-7 -> h_b).  Returns the buffer that holds
+// the last hidden activations (transposed).
+template <int NR>
+__device__ __forceinline__ float* forward_net(const StreamParams& P, Ring& rg, int ch0, float* xa, float* xb, float* red,
+                                              const float* const* bias, float* const* h_a, float* const* h_b,
+                                              int64_t row0) {
+  const int col = threadIdx.x;
+  float* xin = xa;
+  float* xout = xb;
+  for (int l = 0; l < P.L; ++l) {
+    float v[NR];
+    layer_gemv<NR>(P, rg, l == 0 ? ch0 : S_H / S_CK, xin, red, v);
+    const float b = bias[l][col];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) v[r] = fmaxf(v[r] + b, 0.f);
+    if (h_a != nullptr) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) h_a[l][(row0 + r) * S_H + col] = v[r];
+    }
+    if (NR == 8 && h_b != nullptr) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) h_b[l][(row0 + r) * S_H + col] = v[NR - 4 + r];
+    }
+    put_xT<NR>(xout, v);
+    consumer_sync();
+    float* t = xin; xin = xout; xout = t;
+  }
+  return xin;
+}
+
+// Cluster of 2 CTAs per 4 batch rows: rank 0 walks the main nets (and everything that follows the losses), rank 1
+// the target nets - the two chains are independent until the TD target, so each SM only ingests the weights of
+// its own chain (per-SM L2 -> shared bandwidth is what bounds this kernel).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S_THREADS, 1)
+ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ringf = reinterpret_cast<float*>(smem_raw);
   float* xa = ringf + S_NSLOT * S_SLOT;
   float* xb = xa + S_XT;
   float* red = xb + S_XT;
   float* misc = red + S_RED;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + S_MISC);      // full[4], empty[4]
-  float* s_th = misc;                 // [4][8] tanh output of main.pi (= pi / max_u)
-  float* s_tht = misc + 32;           // target.pi
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + S_MISC);      // full[4], empty[4], qt
+  float* s_th = misc;                 // [4][8] tanh output of this CTA's pi net (= pi / max_u)
   float* s_q = misc + 64;             // [8][8]: rows 0-3 main.Q(o,g,u), rows 4-7 main.Q(o,g,pi)
-  float* s_qt = misc + 128;           // [4][8] target.Q
+  float* s_qt = misc + 128;           // [4][8] target.Q (written by the target CTA through DSMEM)
   float* s_dq = misc + 160;           // [8]: dQ (rows 0-3), dQ_pi (rows 4-7);  [8..12): squared TD error
   float* s_dy = misc + 192;           // [4][8]
 
   const int tid = threadIdx.x;
-  const int64_t row0 = (int64_t)blockIdx.x * S_ROWS;
+  const uint32_t role = cluster_ctarank();                   // 0: main chain, 1: target chain
+  const int64_t row0 = (int64_t)(blockIdx.x >> 1) * S_ROWS;
   const cur_net_desc& d = P.d;
   const int L = P.L;
-  const uint32_t full = smem_addr(bars), empty = smem_addr(bars + S_NSLOT);
+  const uint32_t full = smem_addr(bars), empty = smem_addr(bars + S_NSLOT), qt_bar = smem_addr(bars + 2 * S_NSLOT);
 
   if (tid == 0) {
     for (int i = 0; i < S_NSLOT; ++i) {
       mbar_init(full + 8 * i, 1);
       mbar_init(empty + 8 * i, S_CONSUMERS / 32);
     }
+    mbar_init(qt_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  cluster_sync_all();       // barriers initialised in both CTAs before anybody signals across the pair
 
+  const SChunk* my_chunks = role == 0 ? P.chunks : P.chunks_t;
   if (tid >= S_CONSUMERS) {
     // ------------------------------------------------------------ producer warp: stream every weight chunk
     if (tid == S_CONSUMERS) {
       const uint32_t ring_s = smem_addr(ringf);
-      for (int i = 0; i < P.nchunks; ++i) {
+      const int total = role == 0 ? P.nchunks : P.nchunks_t;
+      for (int i = 0; i < total; ++i) {
         const int slot = i % S_NSLOT, round = i / S_NSLOT;
         if (round > 0) mbar_wait(empty + 8 * slot, (round - 1) & 1);
-        const uint32_t bytes = (uint32_t)P.chunks[i].nrows * S_H * 4;
+        const uint32_t bytes = (uint32_t)my_chunks[i].nrows * S_H * 4;
         mbar_expect_tx(full + 8 * slot, bytes);
-        bulk_g2s(ring_s + slot * S_SLOT * 4, P.chunks[i].src, bytes, full + 8 * slot);
+        bulk_g2s(ring_s + slot * S_SLOT * 4, my_chunks[i].src, bytes, full + 8 * slot);
       }
     }
     return;
@@ -334,101 +406,57 @@ __global__ void __launch_bounds__(S_THREADS, 1) ddpg_stream_kernel(const __grid_
 
   // -------------------------------------------------------------- consumers
   Ring rg;
-  rg.slots = ringf; rg.full = full; rg.empty = empty; rg.cons = 0;
+  rg.chunks = my_chunks; rg.slots = ringf; rg.full = full; rg.empty = empty; rg.cons = 0;
   const int col = tid;
   const float inv_n = 1.0f / (float)P.n;
-  S_TL(0);
 
-  // ===== stream 1: main.pi =====  (activations ping-pong between xa and xb)
+  if (role == 1) {
+    // ===== target chain: target.pi, then target.Q(o2, g2, pi_target) with the same u-slot and td (ddpg.py:427-431)
+    build_x(P, xa, 4, 0, row0, true, 0, nullptr, nullptr);
+    consumer_sync();
+    float* xl = forward_net<4>(P, rg, P.ch0[0], xa, xb, red, P.bPT, nullptr, nullptr, row0);
+    small_out(xl, 4, 0, 4, P.WoutPT, d.dimu, 1, d.dimu, P.boutPT, s_th);
+    consumer_sync();
+    if (tid < S_ROWS * S_DU && (tid & (S_DU - 1)) < d.dimu) s_th[tid] = tanhf(s_th[tid]);
+    consumer_sync();
+    build_x(P, xa, 4, 0, row0, true, 2, s_th, nullptr);
+    consumer_sync();
+    xl = forward_net<4>(P, rg, P.ch0[1], xa, xb, red, P.bQT, nullptr, nullptr, row0);
+    small_out(xl, 4, 0, 4, P.WoutQT, 1, 1, 1, P.boutQT, s_qt);
+    consumer_sync();
+    if (tid == 0) {
+      const uint32_t dst = map_to_cta(smem_addr(s_qt), 0);
+      for (int r = 0; r < S_ROWS; ++r) st_remote_f32(dst + 4 * (r * S_DU), s_qt[r * S_DU]);
+      mbar_arrive_remote(map_to_cta(qt_bar, 0));        // release: the stores above are visible to the waiter
+    }
+    return;
+  }
+
+  S_TL(0);
+  // ===== main.pi =====
   build_x(P, xa, 4, 0, row0, false, 0, nullptr, P.Xp);
   consumer_sync();
   S_TL(1);
   {
-    float* xin = xa; float* xout = xb;
-    for (int l = 0; l < L; ++l) {
-      float v[4];
-      layer_gemv<4>(P, rg, l == 0 ? P.ch0[0] : S_H / S_CK, xin, red, v);
-      const float b = P.bP[l][col];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        v[r] = fmaxf(v[r] + b, 0.f);
-        P.hp[l][(row0 + r) * S_H + col] = v[r];
-      }
-      put_xT<4>(xout, v);
-      consumer_sync();
-      float* t = xin; xin = xout; xout = t;
-    }
-    small_out(xin, 4, 0, 4, P.WoutP, d.dimu, 1, d.dimu, P.boutP, s_th);
+    float* xl = forward_net<4>(P, rg, P.ch0[0], xa, xb, red, P.bP, P.hp, nullptr, row0);
+    small_out(xl, 4, 0, 4, P.WoutP, d.dimu, 1, d.dimu, P.boutP, s_th);
+    consumer_sync();
+    if (tid < S_ROWS * S_DU && (tid & (S_DU - 1)) < d.dimu) s_th[tid] = tanhf(s_th[tid]);   // actor_critic.py:89
     consumer_sync();
   }
   S_TL(2);
-  // ===== stream 2: target.pi =====
-  build_x(P, xa, 4, 0, row0, true, 0, nullptr, nullptr);      // (xa is free: L >= 1 layers later the input is dead)
-  consumer_sync();
-  {
-    float* xin = xa; float* xout = xb;
-    for (int l = 0; l < L; ++l) {
-      float v[4];
-      layer_gemv<4>(P, rg, l == 0 ? P.ch0[0] : S_H / S_CK, xin, red, v);
-      const float b = P.bPT[l][col];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) v[r] = fmaxf(v[r] + b, 0.f);
-      put_xT<4>(xout, v);
-      consumer_sync();
-      float* t = xin; xin = xout; xout = t;
-    }
-    small_out(xin, 4, 0, 4, P.WoutPT, d.dimu, 1, d.dimu, P.boutPT, s_tht);
-  }
-  consumer_sync();
-  if (tid < S_ROWS * S_DU && (tid & (S_DU - 1)) < d.dimu) {
-    s_th[tid] = tanhf(s_th[tid]);            // actor_critic.py:89: pi = max_u * tanh(.)
-    s_tht[tid] = tanhf(s_tht[tid]);
-  }
-  consumer_sync();
   S_TL(3);
-  // ===== stream 3: main.Q on rows 0-3 = (o,g,u) and rows 4-7 = (o,g,pi), sharing one pass over the weights =====
+  // ===== main.Q on rows 0-3 = (o,g,u) and rows 4-7 = (o,g,pi), sharing one pass over the weights =====
   build_x(P, xa, 8, 0, row0, false, 1, nullptr, P.Xq);
   build_x(P, xa, 8, 4, row0, false, 2, s_th, nullptr);
   consumer_sync();
   {
-    float* xin = xa; float* xout = xb;
-    for (int l = 0; l < L; ++l) {
-      float v[8];
-      layer_gemv<8>(P, rg, l == 0 ? P.ch0[1] : S_H / S_CK, xin, red, v);
-      const float b = P.bQ[l][col];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = fmaxf(v[r] + b, 0.f);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        P.hq[l][(row0 + r) * S_H + col] = v[r];
-        P.hqp[l][(row0 + r) * S_H + col] = v[4 + r];
-      }
-      put_xT<8>(xout, v);
-      consumer_sync();
-      float* t = xin; xin = xout; xout = t;
-    }
-    small_out(xin, 8, 0, 8, P.WoutQ, 1, 1, 1, P.boutQ, s_q);
+    float* xl = forward_net<8>(P, rg, P.ch0[1], xa, xb, red, P.bQ, P.hq, P.hqp, row0);
+    small_out(xl, 8, 0, 8, P.WoutQ, 1, 1, 1, P.boutQ, s_q);
     consumer_sync();
   }
   S_TL(4);
-  // ===== stream 4: target.Q(o2, g2, pi_target) with the same u-slot and td (ddpg.py:427-431) =====
-  build_x(P, xa, 4, 0, row0, true, 2, s_tht, nullptr);
-  consumer_sync();
-  {
-    float* xin = xa; float* xout = xb;
-    for (int l = 0; l < L; ++l) {
-      float v[4];
-      layer_gemv<4>(P, rg, l == 0 ? P.ch0[1] : S_H / S_CK, xin, red, v);
-      const float b = P.bQT[l][col];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) v[r] = fmaxf(v[r] + b, 0.f);
-      put_xT<4>(xout, v);
-      consumer_sync();
-      float* t = xin; xin = xout; xout = t;
-    }
-    small_out(xin, 4, 0, 4, P.WoutQT, 1, 1, 1, P.boutQT, s_qt);
-  }
-  consumer_sync();
+  mbar_wait_cluster(qt_bar, 0);          // target.Q of these rows has arrived from the partner CTA
   S_TL(5);
   // ===== losses (ddpg.py:436-441) and backward seeds =====
   if (tid < S_ROWS) {
@@ -450,7 +478,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) ddpg_stream_kernel(const __grid_
       sq += s_q[(4 + r) * S_DU];
       for (int j = 0; j < d.dimu; ++j) sth += s_th[r * S_DU + j] * s_th[r * S_DU + j];
     }
-    float* lp = P.loss_part + (int64_t)blockIdx.x * 4;
+    float* lp = P.loss_part + (int64_t)(blockIdx.x >> 1) * 4;
     lp[0] = ssq; lp[1] = sq; lp[2] = sth; lp[3] = 0.f;
   }
   // ===== stream 5: backward through main.Q, critic chain (rows 0-3) and actor-through-critic chain (rows 4-7) =====
@@ -748,9 +776,10 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
 
   // ---- weight chunks in consumption order
   int nc = 0;
+  SChunk* list = P.chunks;
   auto rows_of = [&](const float* src, int nrows, int k0) {      // a row block as chunks of <= 32 rows
     for (int r = 0; r < nrows; r += S_CK) {
-      SChunk& C = P.chunks[nc++];
+      SChunk& C = list[nc++];
       C.src = src + (int64_t)r * H; C.nrows = (nrows - r < S_CK) ? nrows - r : S_CK; C.k0 = k0 + r;
     }
   };
@@ -763,13 +792,17 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     return first;
   };
   P.ch0[0] = forward_net(mP, LP);
-  forward_net(tP, LP);
   P.ch0[1] = forward_net(mQ, LQ);
-  forward_net(tQ, LQ);
   for (int l = L - 1; l >= 1; --l) rows_of(w.TQ[l], H, 0);
   for (int l = L - 1; l >= 1; --l) rows_of(w.TP[l], H, 0);
   CUR_REQUIRE(nc <= S_MAXCHUNK, "too many weight chunks for the rows schedule");
   P.nchunks = nc;
+  nc = 0;
+  list = P.chunks_t;
+  forward_net(tP, LP);
+  forward_net(tQ, LQ);
+  CUR_REQUIRE(nc <= S_MAXCHUNK_T, "too many weight chunks for the rows schedule");
+  P.nchunks_t = nc;
 
   static long long* tl_dev = nullptr;
   static int tl_calls = 0;
@@ -779,15 +812,15 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   P.dbg_skip_math = getenv("CUR_ROWS_SKIP_MATH") != nullptr;
 
   const unsigned int n_ctas = (unsigned int)(n / S_ROWS);
-  ddpg_stream_kernel<<<n_ctas, S_THREADS, S_SMEM_BYTES, s>>>(P);
+  ddpg_stream_kernel<<<2 * n_ctas, S_THREADS, S_SMEM_BYTES, s>>>(P);      // (main, target) CTA pairs
   CUR_CHECK_LAUNCH();
   if (tl_on && ++tl_calls == 40) {          // debug only: one warmed-up timeline of CTA 0
     long long t[64];
     CUR_CUDA_TRY(cudaStreamSynchronize(s));
     CUR_CUDA_TRY(cudaMemcpy(t, tl_dev, sizeof(t), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[rows timeline] build %lld | main.pi %lld | target.pi %lld | main.Q x2 %lld | target.Q %lld | "
+    fprintf(stderr, "[rows timeline] build %lld | main.pi %lld | main.Q x2 %lld | wait target.Q %lld | "
                     "loss+bwd Q %lld | bwd pi %lld | total %lld cycles\n",
-            t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6], t[7] - t[0]);
+            t[1] - t[0], t[2] - t[1], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6], t[7] - t[0]);
   }
 
   // ---- launch 2: weight gradients
