@@ -606,15 +606,154 @@ struct DwTail {
   int dimu;
   float action_l2;
   float *q_loss, *pi_loss;
+  long long* tl;                   // debug timeline (CUR_ROWS_TIMELINE)
+  int tl_skinny_block;
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+// Tile kinds of the weight-gradient launch (K = batch <= 256 is the reduction dimension):
+//   DW_FULLK   C[32x32 tile] = A^T B, A = X [K][M] and B = dY [K][N] both staged for the WHOLE K with one burst of
+//              cp.async (one L2 round trip instead of a multi-stage pipeline of dependent ones), 4-way split-K
+//              inside the CTA, packed FFMA2; 3 CTAs per SM so that all ~330 tiles are co-resident (one wave)
+//   DW_SKINNY  N <= 4 (output layers): 32 rows of C per tile, 8 k-parts per row
+//   DW_COLSUM  C[n] = sum_k B[k][n] (bias gradients), 64 columns x 4 k-parts per tile
+// (A 64 x 64 / 8 x 8-micro-tile variant, which is not bound by shared-memory wavefronts, measured slower here:
+//  88 fat CTAs leave 60 SMs idle and cannot overlap staging with compute - see profiles/README.md.)
+enum { DW_FULLK = 0, DW_SKINNY = 1, DW_COLSUM = 2 };
+constexpr int DW_KMAX = 256;
+constexpr int DW_LD = GT + 4;                                   // row stride of a staged [k][32] tile
+constexpr size_t DW_SMEM_BYTES = (size_t)2 * DW_KMAX * DW_LD * 4;
+
+__device__ __forceinline__ void dw_store(float* c, float v, const AdamCtx* ax) {
+  *c = v;
+  if (ax) {
+    const int64_t off = c - ax->grads;
+    float th = ax->theta[off], mm = ax->m[off], vv = ax->v[off];
+    adam_elem(th, v, mm, vv, ax->neg_a, ax->b1, ax->omb1, ax->b2, ax->omb2, ax->eps);
+    ax->theta[off] = th; ax->m[off] = mm; ax->v[off] = vv;
+  }
+}
+
+__device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, float* Bs, int m0, int n0, const AdamCtx* ax) {
+  const int tid = threadIdx.x;
+  // ---- stage A[k][m0..m0+32) and B[k][n0..n0+32) for every k (zero fill past the edges)
+#pragma unroll
+  for (int j = 0; j < (DW_KMAX * 8) / GEMM_THREADS; ++j) {
+    const int f = tid + j * GEMM_THREADS;
+    const int k = f >> 3, c4 = (f & 7) << 2;
+    const bool oka = (k < P.K) && (m0 + c4 < P.M);
+    cp16_zfill(As + k * DW_LD + c4, P.A + (oka ? (int64_t)k * P.lda + (m0 + c4) : 0), oka);
+    const bool okb = (k < P.K) && (n0 + c4 < P.N);
+    cp16_zfill(Bs + k * DW_LD + c4, P.B + (okb ? (int64_t)k * P.ldb + (n0 + c4) : 0), okb);
+  }
+  cp_commit();
+  cp_wait0();
+  __syncthreads();
+  const int kg = tid >> 6, lt = tid & 63, ty = lt >> 3, tx = lt & 7;
+  float2 acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+  const float* ap = As + (kg * (DW_KMAX / 4)) * DW_LD + 4 * ty;
+  const float* bp = Bs + (kg * (DW_KMAX / 4)) * DW_LD + 4 * tx;
+#pragma unroll 8
+  for (int k = 0; k < DW_KMAX / 4; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(ap + k * DW_LD);
+    const float4 b = *reinterpret_cast<const float4*>(bp + k * DW_LD);
+    const float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
+    acc[0][0] = __ffma2_rn(make_float2(a.x, a.x), b01, acc[0][0]);
+    acc[0][1] = __ffma2_rn(make_float2(a.x, a.x), b23, acc[0][1]);
+    acc[1][0] = __ffma2_rn(make_float2(a.y, a.y), b01, acc[1][0]);
+    acc[1][1] = __ffma2_rn(make_float2(a.y, a.y), b23, acc[1][1]);
+    acc[2][0] = __ffma2_rn(make_float2(a.z, a.z), b01, acc[2][0]);
+    acc[2][1] = __ffma2_rn(make_float2(a.z, a.z), b23, acc[2][1]);
+    acc[3][0] = __ffma2_rn(make_float2(a.w, a.w), b01, acc[3][0]);
+    acc[3][1] = __ffma2_rn(make_float2(a.w, a.w), b23, acc[3][1]);
+  }
+  __syncthreads();                       // everybody is done with the staged tiles: reuse them for the partials
+  float* red = As;                       // 4 x [32][32]
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(red + kg * (GT * GT) + (4 * ty + i) * GT + 4 * tx) =
+        make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < (GT * GT) / GEMM_THREADS; ++j) {
+    const int i = tid + j * GEMM_THREADS;
+    const int gm = m0 + (i >> 5), gn = n0 + (i & 31);
+    if (gm < P.M && gn < P.N) {
+      const float v = (red[i] + red[GT * GT + i]) + (red[2 * GT * GT + i] + red[3 * GT * GT + i]);
+      dw_store(P.C + (int64_t)gm * P.ldc + gn, v, ax);
+    }
+  }
+}
+
+// C[m][j] = sum_k A[k][m] * B[k*ldb + j], j < N <= 4, for the 32 rows m0.. of C; 8 interleaved k-parts per row,
+// loads of 8 k steps in flight per thread
+__device__ __forceinline__ void dw_tile_skinny(const GemmProb& P, float* red, int m0, const AdamCtx* ax) {
+  const int tid = threadIdx.x, m = tid & 31, kp = tid >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool on = m0 + m < P.M;
+  const float* ap = P.A + (on ? m0 + m : 0);
+  const int N = P.N;
+  for (int kb = kp; kb < P.K; kb += 64) {        // batches of 8 k steps: all loads first, then the FMAs
+    float a8[8], b8[8][4];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = kb + 8 * u;
+      const bool kin = k < P.K;
+      a8[u] = (on && kin) ? __ldg(ap + (int64_t)k * P.lda) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b8[u][j] = (kin && j < N) ? __ldg(P.B + (int64_t)k * P.ldb + j) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(a8[u], b8[u][j], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[(kp * 32 + m) * 4 + j] = acc[j];
+  __syncthreads();
+  if (tid < 32 * 4) {
+    const int mm = tid >> 2, j = tid & 3;
+    if (m0 + mm < P.M && j < P.N) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v += red[(q * 32 + mm) * 4 + j];
+      dw_store(P.C + (int64_t)(m0 + mm) * P.ldc + j, v, ax);
+    }
+  }
+}
+
+// C[n] = sum_k B[k][n] for the 64 columns n0.. : 4 k-parts per column, 16 loads in flight per thread
+__device__ __forceinline__ void dw_tile_colsum(const GemmProb& P, float* red, int n0, const AdamCtx* ax) {
+  const int tid = threadIdx.x, c = tid & 63, kp = tid >> 6;
+  const int n = n0 + c;
+  float s = 0.f;
+  if (n < P.N) {
+    const float* bp = P.B + n;
+#pragma unroll 16
+    for (int k = kp; k < P.K; k += 4) s += __ldg(bp + (int64_t)k * P.ldb);
+  }
+  red[kp * 64 + c] = s;
+  __syncthreads();
+  if (tid < 64 && n0 + tid < P.N)
+    dw_store(P.C + n0 + tid, (red[tid] + red[64 + tid]) + (red[128 + tid] + red[192 + tid]), ax);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 3)
 rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTail T) {
-  __shared__ __align__(16) float As[2 * TILE_FLOATS];
-  __shared__ __align__(16) float Bs[2 * TILE_FLOATS];
+  extern __shared__ __align__(16) float dw_smem[];
+  float* As = dw_smem;
+  float* Bs = dw_smem + DW_KMAX * DW_LD;
   __shared__ GemmProb Ps;
   __shared__ AdamCtx ax;
   __shared__ unsigned int s_last;
+  long long* tl = nullptr;
+  if (T.tl != nullptr && threadIdx.x == 0) {
+    if (blockIdx.x == 0) tl = T.tl + 32;
+    else if ((int)blockIdx.x == T.tl_skinny_block) tl = T.tl + 40;
+    else if (blockIdx.x == gridDim.x - 1) tl = T.tl + 48;
+  }
+  if (tl) tl[0] = clock64();
   const long long st = T.step_counter ? *T.step_counter : 0;     // value BEFORE this update's bump
   if (threadIdx.x == 0) {
     ax = T.ax;
@@ -623,10 +762,32 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
       ax.neg_a = T.neg_a_table[(t <= T.table_len ? t : (long long)T.table_len) - 1];
     }
   }
-  // (gemm_run_tile synchronises before the first use of `ax`)
-  gemm_run_tile(G, Ps, As, Bs, T.ax.theta != nullptr ? &ax : nullptr);
+  int pi = 0;
+#pragma unroll 1
+  while (pi + 1 < G.n && (int)blockIdx.x >= G.p[pi + 1].tile_begin) ++pi;
+  {
+    const int* src = reinterpret_cast<const int*>(&G.p[pi]);
+    int* dst = reinterpret_cast<int*>(&Ps);
+    for (int i = threadIdx.x; i < (int)(sizeof(GemmProb) / 4); i += GEMM_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  {
+    const GemmProb& P = Ps;
+    const AdamCtx* axp = T.ax.theta != nullptr ? &ax : nullptr;
+    const int tile = blockIdx.x - P.tile_begin;
+    if (tl) tl[1] = clock64();
+    if (P.variant == DW_FULLK) {
+      const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
+      dw_tile_fullk(P, As, Bs, tm * GT, tn * GT, axp);
+    } else if (P.variant == DW_SKINNY) {
+      dw_tile_skinny(P, As, tile * GT, axp);
+    } else {
+      dw_tile_colsum(P, As, tile * 64, axp);
+    }
+  }
   // ---- the last CTA to finish folds the loss partials and bumps the step counter
   __syncthreads();
+  if (tl) tl[2] = clock64();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int t = atomicAdd(T.ticket, 1u);
@@ -648,6 +809,31 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     *T.ticket = 0u;
     __threadfence();
   }
+  if (tl) tl[3] = clock64();
+}
+
+// tile plan of the weight-gradient launch; returns the grid size, or -1 if a problem does not fit a tile kind
+static int plan_dw_batch(GemmBatch& G) {
+  int t = 0;
+  for (int i = 0; i < G.n; ++i) {
+    GemmProb& P = G.p[i];
+    P.tile_begin = t;
+    if (P.ones_a) {
+      P.variant = DW_COLSUM; P.tiles_n = (P.N + 63) / 64;
+      t += P.tiles_n;
+    } else if (P.N <= 4) {
+      P.variant = DW_SKINNY; P.tiles_n = 1;
+      t += (P.M + GT - 1) / GT;
+    } else {
+      if (!(P.a_trans && !P.b_trans && al16(P.A) && al16(P.B) && P.lda % 4 == 0 && P.ldb % 4 == 0 && P.M % 4 == 0 &&
+            P.N % 4 == 0 && P.K <= DW_KMAX))
+        return -1;
+      P.variant = DW_FULLK; P.tiles_n = (P.N + GT - 1) / GT;
+      t += ((P.M + GT - 1) / GT) * P.tiles_n;
+    }
+  }
+  G.total_tiles = t;
+  return t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -693,9 +879,12 @@ static RowsWorkspace carve_rows(const cur_net_desc& d, int64_t n, float* base) {
 static bool rows_supported(const cur_net_desc* d, int64_t n) {
   if (check_desc(d) != CUR_OK) return false;
   if (d->hidden != S_H || d->layers < 1 || d->layers > S_MAXL) return false;
-  if (d->dimu > S_DU || n <= 0 || (n % S_ROWS) != 0 || n >= (1 << 24)) return false;
-  const NetLayout q = net_layout(*d, 0);
+  if (d->dimu > S_DU || n <= 0 || (n % S_ROWS) != 0 || n > DW_KMAX) return false;      // K of the dW tiles is the batch
+  const NetLayout q = net_layout(*d, 0), p = net_layout(*d, 1);
   if (q.in_s + q.in_g > S_H) return false;
+  // operands of the first-layer weight gradients must be 16-byte aligned column blocks of X
+  if ((q.in_s % 4) != 0 || (p.in_s % 4) != 0 || (q.in_g % 4) != 0) return false;
+  if (d->dimu > 4 && (d->dimu % 4) != 0) return false;
   return true;
 }
 
@@ -807,7 +996,10 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   static long long* tl_dev = nullptr;
   static int tl_calls = 0;
   const bool tl_on = getenv("CUR_ROWS_TIMELINE") != nullptr;
-  if (tl_on && tl_dev == nullptr) CUR_CUDA_TRY(cudaMalloc(&tl_dev, 64 * sizeof(long long)));
+  if (tl_on && tl_dev == nullptr) {
+    CUR_CUDA_TRY(cudaMalloc(&tl_dev, 64 * sizeof(long long)));
+    CUR_CUDA_TRY(cudaMemset(tl_dev, 0, 64 * sizeof(long long)));
+  }
   P.tl = tl_on ? tl_dev : nullptr;
   P.dbg_skip_math = getenv("CUR_ROWS_SKIP_MATH") != nullptr;
 
@@ -829,19 +1021,19 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   auto add = [&](const GemmProb& p) { G.p[G.n++] = p; };
   auto net_grads = [&](const NetLayout& NL, float* gN, const float* X0, float* const* hN, float* const* dN,
                        const float* dOut, int lddo) {
+    // the narrow, latency-bound problems go first so that they start in the first CTAs
     add(bwd_dw(hN[L - 1], H, H, dOut, lddo, NL.out, gN + NL.off_Wout, n));
     add(bwd_db(dOut, lddo, NL.out, gN + NL.off_bout, n));
-    for (int l = L - 1; l >= 1; --l) {
-      add(bwd_dw(hN[l - 1], H, H, dN[l], H, H, gN + NL.off_W[l], n));
-      add(bwd_db(dN[l], H, H, gN + NL.off_b[l], n));
-    }
-    add(bwd_dw(X0, w.KP, NL.in_s, dN[0], H, H, gN + NL.off_W0, n));
+    for (int l = L - 1; l >= 1; --l) add(bwd_db(dN[l], H, H, gN + NL.off_b[l], n));
     add(bwd_db(dN[0], H, H, gN + NL.off_b0, n));
+    for (int l = L - 1; l >= 1; --l) add(bwd_dw(hN[l - 1], H, H, dN[l], H, H, gN + NL.off_W[l], n));
+    add(bwd_dw(X0, w.KP, NL.in_s, dN[0], H, H, gN + NL.off_W0, n));
     if (NL.in_g > 0) add(bwd_dw(X0 + NL.in_s, w.KP, NL.in_g, dN[0], H, H, gN + NL.off_W0g, n));
   };
   net_grads(LQ, gQ, w.Xq, w.hq, w.dc, w.dQ, 1);
   net_grads(LP, gP, w.Xp, w.hp, w.dp, w.dy, w.lddy);
-  const int tiles = plan_gemm_batch(G);
+  const int tiles = plan_dw_batch(G);
+  CUR_REQUIRE(tiles > 0, "weight-gradient problems do not fit the rows schedule (batch > 256 or unaligned dims)");
 
   DwTail T;
   memset(&T, 0, sizeof(T));
@@ -855,7 +1047,27 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   T.step_counter = h->step_counter; T.ring = h->loss_ring;
   T.ticket = w.ticket; T.loss_part = w.loss_part; T.n_clusters = (int)n_ctas; T.n = n; T.dimu = d->dimu;
   T.action_l2 = h->action_l2; T.q_loss = q_loss; T.pi_loss = pi_loss;
-  rows_dw_kernel<<<tiles, GEMM_THREADS, 0, s>>>(G, T);
+  static bool dw_configured = false;
+  if (!dw_configured) {
+    CUR_CUDA_TRY(cudaFuncSetAttribute(rows_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_SMEM_BYTES));
+    dw_configured = true;
+  }
+  T.tl = tl_on ? tl_dev : nullptr;
+  T.tl_skinny_block = 0;
+  for (int i = 0; i < G.n; ++i)
+    if (G.p[i].variant == DW_FULLK) { T.tl_skinny_block = G.p[i].tile_begin; break; }
+  rows_dw_kernel<<<tiles, GEMM_THREADS, DW_SMEM_BYTES, s>>>(G, T);
+  if (tl_on && tl_calls == 40) {
+    long long t[64];
+    CUR_CUDA_TRY(cudaStreamSynchronize(s));
+    CUR_CUDA_TRY(cudaMemcpy(t, tl_dev, sizeof(t), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < 3; ++b) {
+      const long long* q = t + 32 + 8 * b;
+      fprintf(stderr, "[dw timeline] %s: prologue %lld | tile %lld | tail %lld | total %lld cycles (start +%lld after block 0)\n",
+              b == 0 ? "block 0 (output-layer tile)" : b == 1 ? "first full-K tile" : "last block", q[1] - q[0], q[2] - q[1],
+              q[3] - q[2], q[3] - q[0], q[0] - t[32]);
+    }
+  }
   CUR_CHECK_LAUNCH();
   return CUR_OK;
 }
