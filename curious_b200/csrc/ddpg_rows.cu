@@ -615,7 +615,7 @@ struct DwTail {
 //              cp.async (one L2 round trip instead of a multi-stage pipeline of dependent ones), 4-way split-K
 //              inside the CTA, packed FFMA2; 3 CTAs per SM so that all ~330 tiles are co-resident (one wave)
 //   DW_SKINNY  N <= 4 (output layers): 32 rows of C per tile, 8 k-parts per row
-//   DW_COLSUM  C[n] = sum_k B[k][n] (bias gradients), 64 columns x 4 k-parts per tile
+//   DW_COLSUM  C[n] = sum_k B[k][n] (bias gradients), 256 columns per tile
 // (A 64 x 64 / 8 x 8-micro-tile variant, which is not bound by shared-memory wavefronts, measured slower here:
 //  88 fat CTAs leave 60 SMs idle and cannot overlap staging with compute - see profiles/README.md.)
 enum { DW_FULLK = 0, DW_SKINNY = 1, DW_COLSUM = 2 };
@@ -723,20 +723,20 @@ __device__ __forceinline__ void dw_tile_skinny(const GemmProb& P, float* red, in
   }
 }
 
-// C[n] = sum_k B[k][n] for the 64 columns n0.. : 4 k-parts per column, 16 loads in flight per thread
+// C[n] = sum_k B[k][n] for 256 columns n0.. : one thread per column, 4 independent partial sums
 __device__ __forceinline__ void dw_tile_colsum(const GemmProb& P, float* red, int n0, const AdamCtx* ax) {
-  const int tid = threadIdx.x, c = tid & 63, kp = tid >> 6;
-  const int n = n0 + c;
-  float s = 0.f;
-  if (n < P.N) {
-    const float* bp = P.B + n;
-#pragma unroll 16
-    for (int k = kp; k < P.K; k += 4) s += __ldg(bp + (int64_t)k * P.ldb);
+  const int n = n0 + threadIdx.x;
+  if (n >= P.N) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= P.K; k += 4) {
+    s0 += P.B[(int64_t)k * P.ldb + n];
+    s1 += P.B[(int64_t)(k + 1) * P.ldb + n];
+    s2 += P.B[(int64_t)(k + 2) * P.ldb + n];
+    s3 += P.B[(int64_t)(k + 3) * P.ldb + n];
   }
-  red[kp * 64 + c] = s;
-  __syncthreads();
-  if (tid < 64 && n0 + tid < P.N)
-    dw_store(P.C + n0 + tid, (red[tid] + red[64 + tid]) + (red[128 + tid] + red[192 + tid]), ax);
+  for (; k < P.K; ++k) s0 += P.B[(int64_t)k * P.ldb + n];
+  dw_store(P.C + n, (s0 + s1) + (s2 + s3), ax);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 3)
@@ -782,7 +782,7 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     } else if (P.variant == DW_SKINNY) {
       dw_tile_skinny(P, As, tile * GT, axp);
     } else {
-      dw_tile_colsum(P, As, tile * 64, axp);
+      dw_tile_colsum(P, As, tile * GEMM_THREADS, axp);
     }
   }
   // ---- the last CTA to finish folds the loss partials and bumps the step counter
@@ -819,7 +819,7 @@ static int plan_dw_batch(GemmBatch& G) {
     GemmProb& P = G.p[i];
     P.tile_begin = t;
     if (P.ones_a) {
-      P.variant = DW_COLSUM; P.tiles_n = (P.N + 63) / 64;
+      P.variant = DW_COLSUM; P.tiles_n = (P.N + GEMM_THREADS - 1) / GEMM_THREADS;
       t += P.tiles_n;
     } else if (P.N <= 4) {
       P.variant = DW_SKINNY; P.tiles_n = 1;
@@ -1021,13 +1021,14 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   auto add = [&](const GemmProb& p) { G.p[G.n++] = p; };
   auto net_grads = [&](const NetLayout& NL, float* gN, const float* X0, float* const* hN, float* const* dN,
                        const float* dOut, int lddo) {
-    // the narrow, latency-bound problems go first so that they start in the first CTAs
     add(bwd_dw(hN[L - 1], H, H, dOut, lddo, NL.out, gN + NL.off_Wout, n));
     add(bwd_db(dOut, lddo, NL.out, gN + NL.off_bout, n));
-    for (int l = L - 1; l >= 1; --l) add(bwd_db(dN[l], H, H, gN + NL.off_b[l], n));
-    add(bwd_db(dN[0], H, H, gN + NL.off_b0, n));
-    for (int l = L - 1; l >= 1; --l) add(bwd_dw(hN[l - 1], H, H, dN[l], H, H, gN + NL.off_W[l], n));
+    for (int l = L - 1; l >= 1; --l) {
+      add(bwd_dw(hN[l - 1], H, H, dN[l], H, H, gN + NL.off_W[l], n));
+      add(bwd_db(dN[l], H, H, gN + NL.off_b[l], n));
+    }
     add(bwd_dw(X0, w.KP, NL.in_s, dN[0], H, H, gN + NL.off_W0, n));
+    add(bwd_db(dN[0], H, H, gN + NL.off_b0, n));
     if (NL.in_g > 0) add(bwd_dw(X0 + NL.in_s, w.KP, NL.in_g, dN[0], H, H, gN + NL.off_W0g, n));
   };
   net_grads(LQ, gQ, w.Xq, w.hq, w.dc, w.dQ, 1);

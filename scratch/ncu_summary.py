@@ -1,28 +1,42 @@
-import csv, sys, subprocess, re, collections
+"""Dump a compact text summary of an .ncu-rep (key raw metrics + top stall sites) for profiles/."""
+import csv, io, subprocess, sys
 rep = sys.argv[1]
-raw = subprocess.run(['ncu','-i',rep,'--page','raw','--csv'],capture_output=True,text=True).stdout
-rows=list(csv.reader(raw.splitlines())); hdr=rows[0]
-want=['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','sm__throughput.avg.pct_of_peak_sustained_elapsed','sm__warps_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','launch__occupancy_limit_shared_mem','launch__occupancy_limit_registers','lts__t_sector_hit_rate.pct','smsp__issue_active.avg.pct_of_peak_sustained_active','dram__bytes.sum.per_second','smsp__inst_executed.sum','launch__grid_size','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','smsp__warps_eligible.avg.per_cycle_active']
-for w in want:
-    if w in hdr:
-        i=hdr.index(w); print('%-70s %s %s'%(w, rows[1][i], [r[i] for r in rows[2:]]))
-src = subprocess.run(['ncu','-i',rep,'--page','source','--csv'],capture_output=True,text=True).stdout
-rows=list(csv.reader(src.splitlines()))
-h=rows[1]; isrc=h.index('Source'); iex=h.index('Instructions Executed'); ist=h.index('Warp Stall Sampling (All Samples)')
-body=[]
+raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+h, u = rows[0], rows[1]
+want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_bytes.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'launch__registers_per_thread',
+        'launch__grid_size', 'launch__block_size', 'launch__cluster_size', 'launch__cluster_max_active', 'launch__waves_per_multiprocessor',
+        'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers', 'sm__cycles_active.avg',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__inst_executed_pipe_fma.sum', 'smsp__inst_executed_pipe_fmaheavy.sum',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active']
 for r in rows[2:]:
-    if len(r)<=iex:
-        if r and r[0]=='Kernel Name': break
-        continue
-    try: body.append((float(r[iex]), float(r[ist] or 0), r[isrc]))
-    except: pass
-tot=sum(b[0] for b in body); stot=sum(b[1] for b in body)
-print('n sass',len(body),'total warp inst',tot,'stall samples',stot)
-op=collections.Counter()
-for v,s,t in body:
-    m=re.sub(r'^@!?U?P\d+\s+','',t.strip()).split()[0].split('.')[0]; op[m]+=v
-print(' '.join('%s:%.1f%%'%(k,100*v/tot) for k,v in op.most_common(16)))
-thr=float(sys.argv[2]) if len(sys.argv)>2 else 0.012
-for i,(v,s,t) in enumerate(body):
-    if v/tot>thr or s/stot>0.02:
-        print('%4d %5.2f%% st%5.2f%%  %s'%(i,100*v/tot,100*s/stot,t[:90]))
+    print('kernel:', r[h.index('Kernel Name')][:80])
+    for i, n in enumerate(h):
+        if n in want:
+            print('  %-70s %-14s %s' % (n, u[i], r[i]))
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(src)))
+h = rows[1]; idx = {n: i for i, n in enumerate(h)}
+data = rows[2:]
+stalls = [n for n in h if n.startswith('stall_') and 'Not Issued' not in n]
+tot = sum(int(r[idx['# Samples']] or 0) for r in data)
+print('SASS instructions: %d, warp stall samples: %d' % (len(data), tot))
+agg = {s: 0 for s in stalls}
+for r in data:
+    for s in stalls:
+        agg[s] += int(r[idx[s]] or 0)
+print('stall reasons: ' + ', '.join('%s %.1f%%' % (s[6:], 100.0 * v / max(tot, 1)) for s, v in sorted(agg.items(), key=lambda x: -x[1])[:8]))
+ops = {}
+for r in data:
+    t = r[idx['Source']].split()
+    if not t: continue
+    op = (t[1] if t[0].startswith('@') else t[0]).split('.')[0]
+    ops[op] = ops.get(op, 0) + int(r[idx['Instructions Executed']] or 0)
+ex = sum(ops.values())
+print('executed instruction mix: ' + ' '.join('%s:%.1f%%' % (k, 100.0 * v / max(ex, 1)) for k, v in sorted(ops.items(), key=lambda x: -x[1])[:14]))
+print('top stall sites:')
+for r in sorted(data, key=lambda r: -int(r[idx['# Samples']] or 0))[:12]:
+    st = sorted(((int(r[idx[s]] or 0), s[6:]) for s in stalls), reverse=True)[:2]
+    print('  %5s samples  x%-8s %-70s %s' % (r[idx['# Samples']], r[idx['Instructions Executed']], r[idx['Source']][:70], st))
