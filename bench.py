@@ -82,6 +82,17 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def her_traffic_per_launch(rows_per_step):
+    """DRAM bytes of one fused HER launch from the committed `ncu --set full` capture (profiles/), scaled to the
+    rows of this launch; None if the capture is missing."""
+    p = os.path.join(ROOT, 'profiles', 'r01_her_traffic.json')
+    try:
+        t = json.load(open(p))
+        return (t['dram_bytes_read'] + t['dram_bytes_write']) * rows_per_step / t['rows_per_launch']
+    except Exception:
+        return None
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -395,7 +406,8 @@ def run_ours(args):
                        'l2': 'inputs (1.44 GB of replay rows per rank) and outputs (0.42 GB) exceed the 126 MB L2',
                        'rows_per_step': ROWS_PER_STEP, 'batch': BATCH},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_transition': bpt,
+                         'traffic': her_traffic_per_launch(ROWS_PER_STEP), 'peak_source': peak_src,
+                         'algorithmic_bytes': bpt * ROWS_PER_STEP, 'algorithmic_bytes_per_transition': bpt,
                          'kernel': 'her_sample_kernel'},
             'e2e': {'value': world * n_cyc * N_BATCHES_E2E * BATCH / cyc_s, 'unit': 'transitions/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(res.nbytes),
@@ -406,6 +418,7 @@ def run_ours(args):
             'clocks': clock_info,
             'updates_per_s': world * n_upd / (upd_ms * 1e-3),
             'update_us': 1e3 * upd_ms / n_upd,
+            'update_schedule': 'rows' if agent._use_rows(BATCH) else 'levels',
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_sampler_baseline()

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcurious_b200.so')
 SOURCES = ['her.cu', 'norm_adam.cu', 'ddpg.cu', 'ddpg_rows.cu']
 HEADERS = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'mlp_kernels.cuh'),
-           os.path.join(CSRC, 'net_layout.cuh'),
+           os.path.join(CSRC, 'net_layout.cuh'), os.path.join(CSRC, 'her_device.cuh'),
            os.path.join(os.path.dirname(HERE), 'include', 'curious_b200.h')]
 
 NVCC_FLAGS = [

@@ -30,6 +30,7 @@
 // All arithmetic is FP32 FFMA (IEEE); see DESIGN.md section 4 for why tensor cores do not apply here.
 #include <stdlib.h>
 
+#include "her_device.cuh"
 #include "net_layout.cuh"
 
 namespace cur {
@@ -47,7 +48,8 @@ constexpr int S_MAXCHUNK_T = 72;         // weight chunks of the target CTA (L =
 constexpr int S_DU = 8;                  // max action dim
 constexpr int S_XT = S_H * 8;            // floats of one transposed activation buffer [256 k][<= 8 rows]
 constexpr int S_RED = 4 * 8 * S_H;       // split-K partials [4 k-slices][<= 8 rows][256]
-constexpr int S_MISC = 1024;
+constexpr int S_MISC = 2048;              // small per-CTA state + the staged HER images of the 4 rows
+constexpr int S_STAGE_OFF = 256;          // float offset of the HER stage inside misc
 constexpr size_t S_SMEM_BYTES = (size_t)(S_NSLOT * S_SLOT + 2 * S_XT + S_RED + S_MISC) * 4 + 128;   // + 9 mbarriers
 
 struct SChunk {
@@ -76,6 +78,9 @@ struct StreamParams {
   float* q_pi;               // [n]
   long long* tl;             // optional debug timeline (clock64 stamps of CTA 0), CUR_ROWS_TIMELINE=1
   int dbg_skip_math;         // debug: consumers only wait/release (measures the pure streaming rate)
+  int fused_her;             // sample the CTA's 4 rows here (her, plan) instead of reading a staged batch
+  HerPlan plan;
+  cur_her_args her;
   SChunk chunks[S_MAXCHUNK];       // main CTA: main.pi fwd, main.Q fwd, main.Q^T bwd, main.pi^T bwd
   SChunk chunks_t[S_MAXCHUNK_T];   // target CTA: target.pi fwd, target.Q fwd
 };
@@ -255,47 +260,99 @@ __device__ __forceinline__ float norm1s(float x, const float* mean, const float*
 
 // Element (row, column k) of a first-layer input [o | task_descr | action | g] (modular) or [o | g | action]
 // (flat), zero beyond the fan-in (actor_critic.py:76-91).  act_kind: 0 none (pi net), 1 u / max_u, 2 `ths`.
+// The batch values come from the staged batch arrays, or - fused HER sampling - from the relabelled row image
+// `st` in shared memory, preprocessed exactly like the HER kernel's outputs (ddpg.py:118-127: relative goals,
+// clip to +-clip_obs).
 __device__ __forceinline__ float x_elem(const StreamParams& P, int64_t row, int r, int k, bool target, int act_kind,
-                                        const float* ths) {
+                                        const float* ths, const float* st) {
   const cur_net_desc& d = P.d;
   const bool nrm = d.normalize_obs != 0;
-  const float* o = target ? P.o_2 : P.o;
-  const float* g = target ? P.g_2 : P.g;
   const int in_s = P.in_sp + (act_kind ? d.dimu : 0);
+  const cur_layout& HL = P.her.L;
+  const HerPlan& pl = P.plan;
+  const float clip = P.her.clip_obs;
   float v = 0.f;
   int gj = -1, aj = -1;
   if (k < d.dimo) {
-    v = o[row * d.dimo + k];
+    if (st) {
+      v = st[(target ? pl.i0 + HL.off_o : HL.off_o - pl.img_off) + k];
+      if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+    } else {
+      v = (target ? P.o_2 : P.o)[row * d.dimo + k];
+    }
     if (nrm) v = norm1s(v, P.o_mean, P.o_std, k, d.norm_clip);
   } else if (d.modular) {
-    if (k < d.dimo + d.dimtd) v = P.td[row * d.dimtd + (k - d.dimo)];     // never normalised
-    else if (k < in_s) aj = k - d.dimo - d.dimtd;
+    if (k < d.dimo + d.dimtd) {
+      const int j = k - d.dimo;
+      v = st ? st[pl.i0 + HL.off_td + j] : P.td[row * d.dimtd + j];       // never normalised
+    } else if (k < in_s) aj = k - d.dimo - d.dimtd;
     else if (k < in_s + d.dimg) gj = k - in_s;
   } else {
     if (k < d.dimo + d.dimg) gj = k - d.dimo;
     else if (k < in_s) aj = k - d.dimo - d.dimg;
   }
   if (gj >= 0) {
-    v = g[row * d.dimg + gj];
+    if (st) {
+      v = st[pl.i0 + HL.off_g + gj];
+      if (P.her.relative_goals) v -= st[(target ? pl.i0 + HL.off_ag : HL.off_ag - pl.img_off) + gj];
+      if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+    } else {
+      v = (target ? P.g_2 : P.g)[row * d.dimg + gj];
+    }
     if (nrm) v = norm1s(v, P.g_mean, P.g_std, gj, d.norm_clip);
   }
-  if (aj >= 0) v = (act_kind == 1) ? __fdiv_rn(P.u[row * d.dimu + aj], d.max_u) : ths[r * S_DU + aj];
+  if (aj >= 0) {
+    if (act_kind == 1) v = __fdiv_rn(st ? st[pl.i0 + HL.off_u + aj] : P.u[row * d.dimu + aj], d.max_u);
+    else v = ths[r * S_DU + aj];
+  }
   return v;
 }
 
 // transposed first-layer input xT[k][NR] for rows [roff, roff + 4) of the buffer; optional row-major global copy
 __device__ __noinline__ void build_x(const StreamParams& P, float* xT, int NR, int roff, int64_t row0, bool target,
-                                     int act_kind, const float* ths, float* gout) {
+                                     int act_kind, const float* ths, float* gout, const float* stage) {
+  const int ss = P.plan.stage_stride;
   for (int idx = threadIdx.x; idx < S_ROWS * P.KP; idx += S_CONSUMERS) {
     const int k = idx >> 2, r = idx & 3;
-    xT[k * NR + roff + r] = x_elem(P, row0 + r, r, k, target, act_kind, ths);
+    xT[k * NR + roff + r] = x_elem(P, row0 + r, r, k, target, act_kind, ths, stage ? stage + r * ss : nullptr);
   }
   if (gout) {
     for (int idx = threadIdx.x; idx < S_ROWS * P.KP; idx += S_CONSUMERS) {
       const int r = idx / P.KP, k = idx - r * P.KP;
-      gout[(row0 + r) * P.KP + k] = x_elem(P, row0 + r, r, k, target, act_kind, ths);
+      gout[(row0 + r) * P.KP + k] = x_elem(P, row0 + r, r, k, target, act_kind, ths, stage ? stage + r * ss : nullptr);
     }
   }
+}
+
+// Fused HER sampling of the CTA's 4 rows: draws -> cp.async gather of the row images -> relabel + reward, with
+// the same per-row device functions as her_sample_kernel (bit-identical batches).  Both CTAs of a pair sample the
+// same rows (a 4 x ~0.5 KB gather).
+__device__ __forceinline__ void sample_rows(const StreamParams& P, int64_t row0, float* stage, const float** m_src,
+                                            float* s_r) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const HerPlan& pl = P.plan;
+  HerRow row;
+  row.ft = -1; row.choice = -1; row.ep = 0; row.t = 0; row.ttr = -1; row.her = false;
+  if (tid < S_ROWS) her_draw_row(P.her, pl, row0 + tid, row, m_src + 3 * tid);
+  consumer_sync();
+  if (warp < S_ROWS) {
+    const int per_row = pl.img4 + pl.fut4;           // (cold rows are never needed here)
+    float* dst = stage + warp * pl.stage_stride;
+    for (int c = lane; c < per_row; c += 32) {
+      const bool fut = c >= pl.img4;
+      const int q = fut ? c - pl.img4 : c;
+      const float* src = m_src[3 * warp + (fut ? 1 : 0)];
+      if (src != nullptr) cp16_zfill(dst + (fut ? pl.fut_off : 0) + 4 * q, src + 4 * q, true);
+    }
+  }
+  cp_commit();
+  cp_wait0();
+  consumer_sync();
+  if (tid < S_ROWS) {
+    int relab;
+    s_r[tid] = her_relabel_row(P.her, pl, stage + tid * pl.stage_stride, row, &relab);
+  }
+  consumer_sync();
 }
 
 // y[r][j] = sum_k xT[k][r] * W[k * ldk + j * ldj] + bias[j]  for r < NR, j < nout (NR * nout <= 32), K = 256.
@@ -369,6 +426,9 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   float* s_qt = misc + 128;           // [4][8] target.Q (written by the target CTA through DSMEM)
   float* s_dq = misc + 160;           // [8]: dQ (rows 0-3), dQ_pi (rows 4-7);  [8..12): squared TD error
   float* s_dy = misc + 192;           // [4][8]
+  float* s_r = misc + 224;            // [4] rewards of the rows (fused HER sampling)
+  const float** m_src = reinterpret_cast<const float**>(misc + 228);     // [4][3] source addresses
+  float* her_stage = misc + S_STAGE_OFF;                                  // [4][stage_stride]
 
   const int tid = threadIdx.x;
   const uint32_t role = cluster_ctarank();                   // 0: main chain, 1: target chain
@@ -409,17 +469,22 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   rg.chunks = my_chunks; rg.slots = ringf; rg.full = full; rg.empty = empty; rg.cons = 0;
   const int col = tid;
   const float inv_n = 1.0f / (float)P.n;
+  const float* stage = nullptr;
+  if (P.fused_her) {
+    sample_rows(P, row0, her_stage, m_src, s_r);
+    stage = her_stage;
+  }
 
   if (role == 1) {
     // ===== target chain: target.pi, then target.Q(o2, g2, pi_target) with the same u-slot and td (ddpg.py:427-431)
-    build_x(P, xa, 4, 0, row0, true, 0, nullptr, nullptr);
+    build_x(P, xa, 4, 0, row0, true, 0, nullptr, nullptr, stage);
     consumer_sync();
     float* xl = forward_net<4>(P, rg, P.ch0[0], xa, xb, red, P.bPT, nullptr, nullptr, row0);
     small_out(xl, 4, 0, 4, P.WoutPT, d.dimu, 1, d.dimu, P.boutPT, s_th);
     consumer_sync();
     if (tid < S_ROWS * S_DU && (tid & (S_DU - 1)) < d.dimu) s_th[tid] = tanhf(s_th[tid]);
     consumer_sync();
-    build_x(P, xa, 4, 0, row0, true, 2, s_th, nullptr);
+    build_x(P, xa, 4, 0, row0, true, 2, s_th, nullptr, stage);
     consumer_sync();
     xl = forward_net<4>(P, rg, P.ch0[1], xa, xb, red, P.bQT, nullptr, nullptr, row0);
     small_out(xl, 4, 0, 4, P.WoutQT, 1, 1, 1, P.boutQT, s_qt);
@@ -434,7 +499,7 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
 
   S_TL(0);
   // ===== main.pi =====
-  build_x(P, xa, 4, 0, row0, false, 0, nullptr, P.Xp);
+  build_x(P, xa, 4, 0, row0, false, 0, nullptr, P.Xp, stage);
   consumer_sync();
   S_TL(1);
   {
@@ -447,8 +512,8 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   S_TL(2);
   S_TL(3);
   // ===== main.Q on rows 0-3 = (o,g,u) and rows 4-7 = (o,g,pi), sharing one pass over the weights =====
-  build_x(P, xa, 8, 0, row0, false, 1, nullptr, P.Xq);
-  build_x(P, xa, 8, 4, row0, false, 2, s_th, nullptr);
+  build_x(P, xa, 8, 0, row0, false, 1, nullptr, P.Xq, stage);
+  build_x(P, xa, 8, 4, row0, false, 2, s_th, nullptr, stage);
   consumer_sync();
   {
     float* xl = forward_net<8>(P, rg, P.ch0[1], xa, xb, red, P.bQ, P.hq, P.hqp, row0);
@@ -462,7 +527,8 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   if (tid < S_ROWS) {
     const int64_t row = row0 + tid;
     const float hi = P.clip_pos ? 0.f : INFINITY;
-    const float tgt = fminf(fmaxf(P.r[row] + P.gamma * s_qt[tid * S_DU], -P.clip_return), hi);
+    const float rew = stage ? s_r[tid] : P.r[row];
+    const float tgt = fminf(fmaxf(rew + P.gamma * s_qt[tid * S_DU], -P.clip_return), hi);
     const float diff = tgt - s_q[tid * S_DU];
     s_dq[tid] = -2.0f * inv_n * diff;          // d mean((tgt - Q)^2) / dQ
     s_dq[4 + tid] = -inv_n;                    // d (-mean(Q_pi)) / dQ_pi
@@ -902,11 +968,13 @@ extern "C" int64_t cur_ddpg_rows_workspace_floats(const cur_net_desc* d, int64_t
 extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* theta_main, const float* theta_target,
                                   const cur_norm_stats* stats, const cur_batch* batch, const cur_ddpg_hyper* h,
                                   float* workspace, float* grads, float* q_loss, float* pi_loss, float* q_pi,
-                                  const cur_adam_fused* adam) {
+                                  const cur_adam_fused* adam, const cur_her_args* her) {
   CUR_TRY(check_desc(d));
   CUR_REQUIRE(theta_main && theta_target && batch && h && workspace && grads && q_pi, "NULL argument");
-  CUR_REQUIRE(batch->o && batch->g && batch->u && batch->o_2 && batch->g_2 && batch->r, "NULL batch array");
-  CUR_REQUIRE(!d->modular || batch->td, "task_descr required for a modular net");
+  if (her == nullptr) {
+    CUR_REQUIRE(batch->o && batch->g && batch->u && batch->o_2 && batch->g_2 && batch->r, "NULL batch array");
+    CUR_REQUIRE(!d->modular || batch->td, "task_descr required for a modular net");
+  }
   CUR_REQUIRE(rows_supported(d, batch->n), "shape not supported by the rows schedule (see cur_ddpg_rows_supported)");
   if (d->normalize_obs)
     CUR_REQUIRE(stats && stats->o_mean && stats->o_std && stats->g_mean && stats->g_std, "normalizer stats required");
@@ -962,6 +1030,19 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   P.W0Q_act = mQ + LQ.off_W0 + (int64_t)LP.in_s * H;
   P.Xp = w.Xp; P.Xq = w.Xq; P.dQ = w.dQ; P.dy = w.dy; P.lddy = w.lddy;
   P.loss_part = w.loss_part; P.q_pi = q_pi;
+  if (her != nullptr) {
+    // fused sampling: the rows of the batch are drawn, gathered and relabelled in the kernel's prologue
+    CUR_REQUIRE(her->batch == n, "HER args must describe exactly this batch");
+    CUR_REQUIRE(her->L.dimo == d->dimo && her->L.dimg == d->dimg && her->L.dimu == d->dimu &&
+                her->L.dimtd == (d->modular ? d->dimtd : her->L.dimtd), "HER layout does not match the networks");
+    CUR_REQUIRE(!her->relative_goals || her->L.dimag == her->L.dimg, "relative goals need dimg == dimag");
+    P.her = *her;
+    P.her.change = nullptr; P.her.info = nullptr;         // cold rows are not needed
+    P.her.ag = nullptr;                                    // (ag_t is staged iff relative_goals)
+    make_plan(P.her, &P.plan);
+    CUR_REQUIRE(S_ROWS * P.plan.stage_stride <= S_MISC - S_STAGE_OFF, "transition too wide for the fused HER stage");
+    P.fused_her = 1;
+  }
 
   // ---- weight chunks in consumption order
   int nc = 0;

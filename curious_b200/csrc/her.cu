@@ -16,7 +16,7 @@
 //     no register staging, ~16 KB in flight per CTA, up to 14 CTAs per SM;
 //   * relabel (g, task_descr), the float64 reward and the clip are evaluated straight out of shared
 //     memory and every output array is written as contiguous, fully coalesced 16-byte stores.
-#include "common.cuh"
+#include "her_device.cuh"
 
 namespace cur {
 
@@ -38,18 +38,6 @@ int sm_count() {
 constexpr int TILE = 32;         // transitions per CTA
 constexpr int HER_THREADS = 128;
 constexpr int HER_WARPS = HER_THREADS / 32;
-
-struct HerPlan {
-  // shared-memory image of one transition = global floats [row t + img_off, row t+1 end), then the
-  // future achieved goal, then (optionally) the cold row
-  int img_off;      // first float of row t that is copied (off_o, or off_ag when ag_t is needed)
-  int i0;           // image index where row t+1 starts (= row_stride - img_off)
-  int img4;         // 16-byte chunks of the image
-  int fut_off, fut4;
-  int cold_off, cold4;   // cold4 == 0 when change/info are not requested
-  int stage_stride; // floats per transition in shared memory
-  int dimg_pad;
-};
 
 struct HerKernelParams {
   cur_her_args a;
@@ -150,67 +138,9 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
   const int ss = pl.stage_stride;
 
   // ---------------------------------------------------------------- phase A: draws (warp 0)
-  int my_ft = -1, my_choice = -1, my_ep = 0, my_t = 0, my_ttr = -1;
-  bool my_her = false;
-  if (warp == 0) {
-    if (lane < nrows) {
-      const int64_t j = j0 + lane;
-      const int64_t c = a.perm ? (int64_t)a.perm[j] : j;
-      // segment lookup: concat rows are the segments' counts laid end to end (ddpg.py:326-345)
-      // (with a device control block - CUDA-graph replays - counts / sizes / counter come from memory)
-      const cur_her_dyn* dyn = a.dyn;
-      int s = 0;
-      int64_t acc = 0;
-      while (s + 1 < a.n_segments) {
-        const int cnt = dyn ? dyn->count[s] : a.seg[s].count;
-        if (c < acc + cnt) break;
-        acc += cnt;
-        ++s;
-      }
-      const float* base = a.seg[s].base;
-      const int E = dyn ? dyn->n_episodes[s] : a.seg[s].n_episodes;
-      my_ttr = a.seg[s].task_to_replay;
-      const uint64_t call_offset = a.call_offset + (dyn ? (uint64_t)*dyn->step : 0ull);
-      double u_her, u_off;
-      if (a.inj_ep != nullptr) {
-        my_ep = a.inj_ep[c];
-        my_t = a.inj_t[c];
-        u_her = a.inj_u_her[c];
-        u_off = a.inj_u_off[c];
-        if (a.inj_choice) my_choice = a.inj_choice[c];
-      } else {
-        Philox x = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)call_offset,
-                                 (uint32_t)(call_offset >> 32), (uint32_t)a.seed,
-                                 (uint32_t)(a.seed >> 32));
-        my_ep = (int)mulhi32(x.x[0], (uint32_t)E);
-        my_t = (int)mulhi32(x.x[1], (uint32_t)L.T);
-        u_her = u01_from_u32(x.x[2]);
-        u_off = u01_from_u32(x.x[3]);
-        if (a.mode == CUR_MODE_RANDOM_TASK || a.mode == CUR_MODE_CP_TASK) {
-          Philox y = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)call_offset,
-                                   (uint32_t)(call_offset >> 32) ^ 0x80000000u, (uint32_t)a.seed,
-                                   (uint32_t)(a.seed >> 32));
-          if (a.mode == CUR_MODE_RANDOM_TASK) {
-            my_choice = (int)mulhi32(y.x[0], (uint32_t)a.tasks.n_tasks);
-          } else {
-            // np.random.choice(p=): cdf.searchsorted(u, side='right')
-            double u = u01_from_u32(y.x[0]);
-            int k = 0;
-            while (k < a.tasks.n_tasks - 1 && (dyn ? dyn->cdf[k] : a.tasks.cdf[k]) <= u) ++k;
-            my_choice = k;
-          }
-        }
-      }
-      my_her = u_her < a.future_p;                                           // her.py:115
-      if (my_her) my_ft = my_t + 1 + (int)(u_off * (double)(L.T - my_t));    // her.py:116-118
-      const int64_t row = ((int64_t)my_ep * (L.T + 1) + my_t) * (int64_t)L.row_stride;
-      m_src[3 * lane + 0] = base + row + pl.img_off;
-      m_src[3 * lane + 1] = my_her ? base + ((int64_t)my_ep * (L.T + 1) + my_ft) * (int64_t)L.row_stride + L.off_ag
-                                   : nullptr;
-      m_src[3 * lane + 2] = (pl.cold4 > 0) ? a.seg[s].cold + ((int64_t)my_ep * L.T + my_t) * (int64_t)L.cold_stride
-                                           : nullptr;
-    }
-  }
+  HerRow row;
+  row.ft = -1; row.choice = -1; row.ep = 0; row.t = 0; row.ttr = -1; row.her = false;
+  if (warp == 0 && lane < nrows) her_draw_row(a, pl, j0 + lane, row, m_src + 3 * lane);
   __syncthreads();
 
   // ---------------------------------------------------------------- copies: global -> shared
@@ -246,64 +176,14 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
   const bool wipe = (a.mode == CUR_MODE_BUFFER || a.mode == CUR_MODE_RANDOM_TASK || a.mode == CUR_MODE_CP_TASK);
 
   if (warp == 0 && lane < nrows) {
-    float* st = stage + lane * ss;
-    int own = -1;
-    for (int k = 0; k < L.dimtd; ++k)
-      if (st[iTD + k] == 1.0f) { own = k; break; }                 // argwhere(td == 1) (her.py:134)
-    int relab = -1, newtd = -1;
-    if (my_her) {
-      switch (a.mode) {
-        case CUR_MODE_BUFFER: relab = (my_ttr >= 0) ? my_ttr : own; newtd = relab; break;
-        case CUR_MODE_RANDOM_TASK:
-        case CUR_MODE_CP_TASK: relab = my_choice; newtd = relab; break;
-        case CUR_MODE_CURRENT_TASK: relab = own; newtd = -1; break;
-        default: break;                          // FLAT handled below
-      }
-      // relabel IN PLACE in the staged image (this lane owns the row)
-      const float* fut = st + pl.fut_off;
-      if (a.mode == CUR_MODE_FLAT) {
-        for (int m = 0; m < a.tasks.n_tasks; ++m)                   // her.py:43-47
-          for (int k = 0; k < a.tasks.len[m]; ++k) st[iG + a.tasks.g_idx[m][k]] = fut[a.tasks.ag_idx[m][k]];
-      } else if (relab >= 0) {
-        if (wipe) {
-          for (int k = 0; k < L.dimg; ++k) st[iG + k] = 0.0f;       // her.py:151
-          for (int k = 0; k < L.dimtd; ++k) st[iTD + k] = (k == newtd) ? 1.0f : 0.0f;   // her.py:152,155
-        }
-        for (int k = 0; k < a.tasks.len[relab]; ++k)                // her.py:154 / 163
-          st[iG + a.tasks.g_idx[relab][k]] = fut[a.tasks.ag_idx[relab][k]];
-      } else if (wipe) {
-        // HER row whose module could not be determined (task_descr not one-hot): the reference would
-        // raise; clear like her.py:151-152 so the output is at least well defined
-        for (int k = 0; k < L.dimg; ++k) st[iG + k] = 0.0f;
-        for (int k = 0; k < L.dimtd; ++k) st[iTD + k] = 0.0f;
-      }
-    }
+    int relab_out = -1;
+    const float rew1 = her_relabel_row(a, pl, stage + lane * ss, row, &relab_out);
     if (a.idx_out) {
       int32_t* io = a.idx_out + (j0 + lane) * 4;
-      io[0] = my_ep; io[1] = my_t; io[2] = my_ft;
-      io[3] = my_her ? ((a.mode == CUR_MODE_FLAT) ? 0 : relab) : -1;
+      io[0] = row.ep; io[1] = row.t; io[2] = row.ft;
+      io[3] = row.her ? ((a.mode == CUR_MODE_FLAT) ? 0 : relab_out) : -1;
     }
-    if (a.r != nullptr) {
-      // reward on (ag_2, relabelled g, final task_descr) in float64, NumPy's operation order
-      const float* ag2 = st + iAG2;
-      const float* gf = st + iG;
-      double d2 = 0.0;
-      if (a.mode == CUR_MODE_FLAT) {
-        for (int m = 0; m < a.tasks.n_tasks; ++m)
-          for (int k = 0; k < a.tasks.len[m]; ++k) {
-            double diff = (double)ag2[a.tasks.ag_idx[m][k]] - (double)gf[a.tasks.g_idx[m][k]];
-            d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
-          }
-      } else {
-        const int m = (newtd >= 0) ? newtd : own;
-        if (m >= 0)
-          for (int k = 0; k < a.tasks.len[m]; ++k) {
-            double diff = (double)ag2[a.tasks.ag_idx[m][k]] - (double)gf[a.tasks.g_idx[m][k]];
-            d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
-          }
-      }
-      a.r[j0 + lane] = (sqrt(d2) > a.tasks.threshold) ? -1.0f : 0.0f;
-    }
+    if (a.r != nullptr) a.r[j0 + lane] = rew1;
   }
   __syncthreads();
 
@@ -418,22 +298,6 @@ __global__ void __launch_bounds__(128) store_episodes_kernel(const __grid_consta
       cd[k] = v;
     }
   }
-}
-
-static int make_plan(const cur_her_args& a, HerPlan* p) {
-  const cur_layout& L = a.L;
-  const bool need_ag_t = (a.ag != nullptr) || a.relative_goals;
-  const bool need_cold = (a.change != nullptr && L.dimchange > 0) || (a.info != nullptr && L.diminfo > 0);
-  p->img_off = need_ag_t ? L.off_ag : L.off_o;
-  p->i0 = L.row_stride - p->img_off;
-  p->img4 = (p->i0 + L.row_stride) / 4;
-  p->fut_off = p->i0 + L.row_stride;
-  p->fut4 = round_up4(L.dimag) / 4;
-  p->cold_off = p->fut_off + 4 * p->fut4;
-  p->cold4 = need_cold ? L.cold_stride / 4 : 0;
-  p->stage_stride = p->cold_off + 4 * p->cold4;
-  p->dimg_pad = round_up4(L.dimg);
-  return CUR_OK;
 }
 
 }  // namespace cur

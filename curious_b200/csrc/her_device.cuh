@@ -1,0 +1,167 @@
+// Per-row pieces of the fused HER relabel kernel, shared by her.cu (the batched kernel) and ddpg_rows.cu (which
+// samples its own 4 rows in the prologue of the update kernel).  Same draws, same relabelling, same reward:
+// the two callers are bit-identical by construction.
+//
+// Reference: baselines/her/her.py:108-118 (draws), :129-164 (relabel), :174-176 + config.py:158-159 (reward),
+// ddpg.py:326-345 (segment table).
+#pragma once
+#include "common.cuh"
+
+namespace cur {
+
+struct HerPlan {
+  // shared-memory image of one transition = global floats [row t + img_off, row t+1 end), then the
+  // future achieved goal, then (optionally) the cold row
+  int img_off;      // first float of row t that is copied (off_o, or off_ag when ag_t is needed)
+  int i0;           // image index where row t+1 starts (= row_stride - img_off)
+  int img4;         // 16-byte chunks of the image
+  int fut_off, fut4;
+  int cold_off, cold4;   // cold4 == 0 when change/info are not requested
+  int stage_stride; // floats per transition in shared memory
+  int dimg_pad;
+};
+
+
+struct HerRow {
+  int ep, t, ft, choice, ttr;
+  bool her;
+};
+
+// Draws of concat row j (injected stream or Philox), segment lookup, and the three source addresses of the row:
+// src[0] main span, src[1] future achieved goal (NULL: not a HER row), src[2] cold row (NULL: not requested).
+__device__ __forceinline__ void her_draw_row(const cur_her_args& a, const HerPlan& pl, int64_t j, HerRow& row,
+                                             const float** src) {
+  const cur_layout& L = a.L;
+  const int64_t c = a.perm ? (int64_t)a.perm[j] : j;
+  // segment lookup: concat rows are the segments' counts laid end to end (ddpg.py:326-345)
+  // (with a device control block - CUDA-graph replays - counts / sizes / counter come from memory)
+  const cur_her_dyn* dyn = a.dyn;
+  int s = 0;
+  int64_t acc = 0;
+  while (s + 1 < a.n_segments) {
+    const int cnt = dyn ? dyn->count[s] : a.seg[s].count;
+    if (c < acc + cnt) break;
+    acc += cnt;
+    ++s;
+  }
+  const float* base = a.seg[s].base;
+  const int E = dyn ? dyn->n_episodes[s] : a.seg[s].n_episodes;
+  row.ttr = a.seg[s].task_to_replay;
+  row.choice = -1;
+  const uint64_t call_offset = a.call_offset + (dyn ? (uint64_t)*dyn->step : 0ull);
+  double u_her, u_off;
+  if (a.inj_ep != nullptr) {
+    row.ep = a.inj_ep[c];
+    row.t = a.inj_t[c];
+    u_her = a.inj_u_her[c];
+    u_off = a.inj_u_off[c];
+    if (a.inj_choice) row.choice = a.inj_choice[c];
+  } else {
+    Philox x = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)call_offset, (uint32_t)(call_offset >> 32),
+                             (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    row.ep = (int)mulhi32(x.x[0], (uint32_t)E);
+    row.t = (int)mulhi32(x.x[1], (uint32_t)L.T);
+    u_her = u01_from_u32(x.x[2]);
+    u_off = u01_from_u32(x.x[3]);
+    if (a.mode == CUR_MODE_RANDOM_TASK || a.mode == CUR_MODE_CP_TASK) {
+      Philox y = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)call_offset,
+                               (uint32_t)(call_offset >> 32) ^ 0x80000000u, (uint32_t)a.seed,
+                               (uint32_t)(a.seed >> 32));
+      if (a.mode == CUR_MODE_RANDOM_TASK) {
+        row.choice = (int)mulhi32(y.x[0], (uint32_t)a.tasks.n_tasks);
+      } else {
+        // np.random.choice(p=): cdf.searchsorted(u, side='right')
+        double u = u01_from_u32(y.x[0]);
+        int k = 0;
+        while (k < a.tasks.n_tasks - 1 && (dyn ? dyn->cdf[k] : a.tasks.cdf[k]) <= u) ++k;
+        row.choice = k;
+      }
+    }
+  }
+  row.her = u_her < a.future_p;                                                   // her.py:115
+  row.ft = row.her ? row.t + 1 + (int)(u_off * (double)(L.T - row.t)) : -1;       // her.py:116-118
+  const int64_t off = ((int64_t)row.ep * (L.T + 1) + row.t) * (int64_t)L.row_stride;
+  src[0] = base + off + pl.img_off;
+  src[1] = row.her ? base + ((int64_t)row.ep * (L.T + 1) + row.ft) * (int64_t)L.row_stride + L.off_ag : nullptr;
+  src[2] = (pl.cold4 > 0) ? a.seg[s].cold + ((int64_t)row.ep * L.T + row.t) * (int64_t)L.cold_stride : nullptr;
+}
+
+// Relabel the staged image of one row in place (g, task_descr) and return its reward.
+// image indices: row t sections at (off - img_off); row t+1 sections at (i0 + off); g/u/td of step t live in
+// row t+1 (shifted layout).  *relab_out receives the module whose goal slice was relabelled (-1: none).
+__device__ __forceinline__ float her_relabel_row(const cur_her_args& a, const HerPlan& pl, float* st, const HerRow& row,
+                                                 int* relab_out) {
+  const cur_layout& L = a.L;
+  const int iG = pl.i0 + L.off_g, iTD = pl.i0 + L.off_td, iAG2 = pl.i0 + L.off_ag;
+  const bool wipe = (a.mode == CUR_MODE_BUFFER || a.mode == CUR_MODE_RANDOM_TASK || a.mode == CUR_MODE_CP_TASK);
+  int own = -1;
+  for (int k = 0; k < L.dimtd; ++k)
+    if (st[iTD + k] == 1.0f) { own = k; break; }                 // argwhere(td == 1) (her.py:134)
+  int relab = -1, newtd = -1;
+  if (row.her) {
+    switch (a.mode) {
+      case CUR_MODE_BUFFER: relab = (row.ttr >= 0) ? row.ttr : own; newtd = relab; break;
+      case CUR_MODE_RANDOM_TASK:
+      case CUR_MODE_CP_TASK: relab = row.choice; newtd = relab; break;
+      case CUR_MODE_CURRENT_TASK: relab = own; newtd = -1; break;
+      default: break;                          // FLAT handled below
+    }
+    // relabel IN PLACE in the staged image (this lane owns the row)
+    const float* fut = st + pl.fut_off;
+    if (a.mode == CUR_MODE_FLAT) {
+      for (int m = 0; m < a.tasks.n_tasks; ++m)                   // her.py:43-47
+        for (int k = 0; k < a.tasks.len[m]; ++k) st[iG + a.tasks.g_idx[m][k]] = fut[a.tasks.ag_idx[m][k]];
+    } else if (relab >= 0) {
+      if (wipe) {
+        for (int k = 0; k < L.dimg; ++k) st[iG + k] = 0.0f;       // her.py:151
+        for (int k = 0; k < L.dimtd; ++k) st[iTD + k] = (k == newtd) ? 1.0f : 0.0f;   // her.py:152,155
+      }
+      for (int k = 0; k < a.tasks.len[relab]; ++k)                // her.py:154 / 163
+        st[iG + a.tasks.g_idx[relab][k]] = fut[a.tasks.ag_idx[relab][k]];
+    } else if (wipe) {
+      // HER row whose module could not be determined (task_descr not one-hot): the reference would
+      // raise; clear like her.py:151-152 so the output is at least well defined
+      for (int k = 0; k < L.dimg; ++k) st[iG + k] = 0.0f;
+      for (int k = 0; k < L.dimtd; ++k) st[iTD + k] = 0.0f;
+    }
+  }
+  *relab_out = relab;
+  // reward on (ag_2, relabelled g, final task_descr) in float64, NumPy's operation order
+  const float* ag2 = st + iAG2;
+  const float* gf = st + iG;
+  double d2 = 0.0;
+  if (a.mode == CUR_MODE_FLAT) {
+    for (int m = 0; m < a.tasks.n_tasks; ++m)
+      for (int k = 0; k < a.tasks.len[m]; ++k) {
+        double diff = (double)ag2[a.tasks.ag_idx[m][k]] - (double)gf[a.tasks.g_idx[m][k]];
+        d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+      }
+  } else {
+    const int m = (newtd >= 0) ? newtd : own;
+    if (m >= 0)
+      for (int k = 0; k < a.tasks.len[m]; ++k) {
+        double diff = (double)ag2[a.tasks.ag_idx[m][k]] - (double)gf[a.tasks.g_idx[m][k]];
+        d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+      }
+  }
+  return (sqrt(d2) > a.tasks.threshold) ? -1.0f : 0.0f;
+}
+
+inline int make_plan(const cur_her_args& a, HerPlan* p) {
+  const cur_layout& L = a.L;
+  const bool need_ag_t = (a.ag != nullptr) || a.relative_goals;
+  const bool need_cold = (a.change != nullptr && L.dimchange > 0) || (a.info != nullptr && L.diminfo > 0);
+  p->img_off = need_ag_t ? L.off_ag : L.off_o;
+  p->i0 = L.row_stride - p->img_off;
+  p->img4 = (p->i0 + L.row_stride) / 4;
+  p->fut_off = p->i0 + L.row_stride;
+  p->fut4 = round_up4(L.dimag) / 4;
+  p->cold_off = p->fut_off + 4 * p->fut4;
+  p->cold4 = need_cold ? L.cold_stride / 4 : 0;
+  p->stage_stride = p->cold_off + 4 * p->cold4;
+  p->dimg_pad = round_up4(L.dimg);
+  return CUR_OK;
+}
+
+
+}  // namespace cur

@@ -63,6 +63,7 @@ class DDPG(object):
         # 'rows' (cluster kernel + fused dW/Adam, 2 launches), 'levels' (one grouped GEMM per dependency
         # level) or 'auto' (rows whenever the shape is supported)
         self.update_schedule = kwargs.get('update_schedule', 'auto')
+        self.fuse_her = kwargs.get('fuse_her', True)      # rows schedule: sample inside the update kernel
         self.create_actor_critic = import_function(self.network_class)
 
         self.dimo = self.input_dims['o']
@@ -404,7 +405,7 @@ class DDPG(object):
             _lib.check(_lib.load().cur_ddpg_rows_step(
                 _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
                 C.byref(self._stats), C.byref(cb), C.byref(self._hyper), self._workspace_rows(n).data_ptr(),
-                self.grads.data_ptr(), self._q_loss.data_ptr(), self._pi_loss.data_ptr(), q_pi.data_ptr(), None),
+                self.grads.data_ptr(), self._q_loss.data_ptr(), self._pi_loss.data_ptr(), q_pi.data_ptr(), None, None),
                 'cur_ddpg_rows_step')
         else:
             _lib.check(_lib.load().cur_ddpg_grads(
@@ -541,9 +542,16 @@ class DDPG(object):
         lib = _lib.load()
         sampler = self.sample_transitions
         segs = [(buf.device_view(), 0, ttr) for buf, ttr in self._all_segments()]
-        sampler.sample_device(segs, self.batch_size, clip_obs=self.clip_obs, relative_goals=self.relative_goals,
-                              want=self._gwant, out=self._gbatch, dyn=self._dyn_dev.data_ptr(),
-                              call_offset=self.GRAPH_STREAM_OFFSET)
+        her_args = None
+        if self._use_rows(self.batch_size) and self.fuse_her:
+            # rows schedule: every CTA of the update kernel samples its own rows (no separate HER launch)
+            her_args, self._her_keep = sampler.sample_device(
+                segs, self.batch_size, clip_obs=self.clip_obs, relative_goals=self.relative_goals, want=(),
+                dyn=self._dyn_dev.data_ptr(), call_offset=self.GRAPH_STREAM_OFFSET, args_only=True)
+        else:
+            sampler.sample_device(segs, self.batch_size, clip_obs=self.clip_obs, relative_goals=self.relative_goals,
+                                  want=self._gwant, out=self._gbatch, dyn=self._dyn_dev.data_ptr(),
+                                  call_offset=self.GRAPH_STREAM_OFFSET)
         b = self._gbatch
         n = self.batch_size
         g2 = b['g_2'] if self.relative_goals else b['g']       # g_2 == g without relative goals (ddpg.py:353)
@@ -561,7 +569,8 @@ class DDPG(object):
                 _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
                 C.byref(self._stats), C.byref(cb), C.byref(self._ghyper), self._workspace_rows(n).data_ptr(),
                 self.grads.data_ptr(), self._q_ring.data_ptr(), self._pi_ring.data_ptr(), self._q_pi.data_ptr(),
-                C.byref(adam) if fuse else None), 'cur_ddpg_rows_step')
+                C.byref(adam) if fuse else None, C.byref(her_args) if her_args is not None else None),
+                'cur_ddpg_rows_step')
             return fuse
         _lib.check(lib.cur_ddpg_grads(
             _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),

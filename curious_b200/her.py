@@ -127,7 +127,7 @@ class HerSampler:
     def sample_device(self, segments, B, *, cp_proba=None, draws=None, perm=None, clip_obs=0.0,
                       relative_goals=False, want=('o', 'ag', 'g', 'u', 'td', 'change', 'info', 'o_2',
                                                   'ag_2', 'r'),
-                      want_idx=False, out=None, stream=None, dyn=None, call_offset=None):
+                      want_idx=False, out=None, stream=None, dyn=None, call_offset=None, args_only=False):
         """segments: list of (DeviceEpisodes, count, task_to_replay or None).
         Returns {key: float32 cuda tensor [B, dim]} (+ 'idx' int32 [B,4] if want_idx)."""
         if self.mode is None:
@@ -193,6 +193,10 @@ class HerSampler:
         if want_idx:
             res['idx'] = torch.empty((B, 4), dtype=torch.int32, device=dev)
             a.idx_out = res['idx'].data_ptr()
+        if args_only:
+            # the caller launches a kernel that samples for itself (cur_ddpg_rows_step with `her`)
+            res['_keep'] = keep
+            return a, res
         _lib.check(lib.cur_her_sample(_lib.stream_ptr(stream), C.byref(a)), 'cur_her_sample')
         res['_keep'] = keep
         return res

@@ -284,6 +284,10 @@ int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* theta_main,
  * parameters theta_main and the moments are stepped in place with
  * neg_a_table[min(*step_counter + 1, table_len) - 1]; use it only when no gradient all-reduce is
  * needed between _grads and _update (world size 1) and both nets share the step size.
+ * With `her` != NULL the batch is not read from `batch` (only batch->n is used): every CTA draws,
+ * gathers and relabels its own rows in the kernel prologue with the code of cur_her_sample (same
+ * Philox counters / injected draws / control block, bit-identical transitions); output pointers
+ * inside `her` are ignored.
  * ------------------------------------------------------------------------------------------ */
 typedef struct cur_adam_fused {
   float *m, *v;               /* Adam moments, same arena layout as theta */
@@ -299,7 +303,8 @@ int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* theta_main,
                        const float* theta_target, const cur_norm_stats* stats,
                        const cur_batch* batch, const cur_ddpg_hyper* h, float* workspace,
                        float* grads, float* q_loss, float* pi_loss, float* q_pi,
-                       const cur_adam_fused* adam /* or NULL: gradients only */);
+                       const cur_adam_fused* adam /* or NULL: gradients only */,
+                       const cur_her_args* her /* or NULL: read `batch` */);
 
 #ifdef __cplusplus
 }
