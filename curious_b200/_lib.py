@@ -81,12 +81,20 @@ class Batch(C.Structure):
 class DdpgHyper(C.Structure):
     _fields_ = [('gamma', C.c_float), ('clip_return', C.c_float), ('action_l2', C.c_float),
                 ('clip_pos_returns', C.c_int32), ('step_counter', C.c_void_p), ('loss_ring', C.c_int32),
-                ('_pad', C.c_int32)]
+                ('_pad', C.c_int32), ('grads_parity_stride', C.c_int64)]
 
 
 class AdamFused(C.Structure):
     _fields_ = [('m', C.c_void_p), ('v', C.c_void_p), ('neg_a_table', C.c_void_p), ('table_len', C.c_int32),
                 ('_pad', C.c_int32), ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double)]
+
+
+CUR_MAX_RANKS = 8
+
+
+class P2PCtx(C.Structure):
+    _fields_ = [('rank', C.c_int32), ('world', C.c_int32), ('region', C.c_void_p * CUR_MAX_RANKS),
+                ('arena', C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol include/curious_b200.h declares
@@ -128,6 +136,14 @@ SIGNATURES = {
                                      C.POINTER(NormStats), C.POINTER(Batch), C.POINTER(DdpgHyper), C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AdamFused),
                                      C.POINTER(HerArgs)]),
+    'cur_p2p_region_bytes': (C.c_int64, [C.c_int64]),
+    'cur_p2p_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    'cur_p2p_open': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    'cur_p2p_close': (C.c_int, [C.c_void_p]),
+    'cur_p2p_free': (C.c_int, [C.c_void_p]),
+    'cur_p2p_allreduce_adam': (C.c_int, [C.c_void_p, C.POINTER(P2PCtx), C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                         C.c_void_p]),
 }
 
 _lib = None

@@ -674,6 +674,7 @@ struct DwTail {
   float *q_loss, *pi_loss;
   long long* tl;                   // debug timeline (CUR_ROWS_TIMELINE)
   int tl_skinny_block;
+  int64_t parity_stride;           // > 0: gradients go to C + ((step + 1) & 1) * parity_stride (peer-memory exchange)
 };
 
 // Tile kinds of the weight-gradient launch (K = batch <= 256 is the reduction dimension):
@@ -837,6 +838,8 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     for (int i = threadIdx.x; i < (int)(sizeof(GemmProb) / 4); i += GEMM_THREADS) dst[i] = src[i];
   }
   __syncthreads();
+  if (T.parity_stride > 0 && threadIdx.x == 0) Ps.C += ((st + 1) & 1) * T.parity_stride;
+  if (T.parity_stride > 0) __syncthreads();
   {
     const GemmProb& P = Ps;
     const AdamCtx* axp = T.ax.theta != nullptr ? &ax : nullptr;
@@ -1129,6 +1132,9 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   T.step_counter = h->step_counter; T.ring = h->loss_ring;
   T.ticket = w.ticket; T.loss_part = w.loss_part; T.n_clusters = (int)n_ctas; T.n = n; T.dimu = d->dimu;
   T.action_l2 = h->action_l2; T.q_loss = q_loss; T.pi_loss = pi_loss;
+  T.parity_stride = h->grads_parity_stride;
+  CUR_REQUIRE(T.parity_stride == 0 || (h->step_counter != nullptr && adam == nullptr),
+              "gradient double buffering needs the step counter and excludes the fused Adam epilogue");
   static bool dw_configured = false;
   if (!dw_configured) {
     CUR_CUDA_TRY(cudaFuncSetAttribute(rows_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_SMEM_BYTES));

@@ -64,6 +64,10 @@ class DDPG(object):
         # level) or 'auto' (rows whenever the shape is supported)
         self.update_schedule = kwargs.get('update_schedule', 'auto')
         self.fuse_her = kwargs.get('fuse_her', True)      # rows schedule: sample inside the update kernel
+        # several ranks: 'p2p' = gradient exchange over NVLink peer memory fused with Adam inside the update's
+        # CUDA graph (csrc/p2p.cu), 'nccl' = NCCL all-reduce + Adam launch after the graph, 'auto' = p2p when
+        # the rows schedule runs on an NCCL (one GPU per rank) group
+        self.grad_exchange = kwargs.get('grad_exchange', 'auto')
         self.create_actor_critic = import_function(self.network_class)
 
         self.dimo = self.input_dims['o']
@@ -504,6 +508,11 @@ class DDPG(object):
         self._ghyper = _lib.DdpgHyper(self._hyper.gamma, self._hyper.clip_return, self._hyper.action_l2,
                                       self._hyper.clip_pos_returns, self._step.data_ptr(), self.LOSS_RING, 0)
         self._workspace_rows(B) if self._use_rows(B) else self._workspace(B)
+        self._peer = None
+        if self._want_peer_exchange():
+            from .parallel import PeerGradExchange
+            self._peer = PeerGradExchange(self.net.arena, self.comm)
+            self._ghyper.grads_parity_stride = self.net.arena
         self._graph_sig = None
         self._refresh_dyn()
         torch.cuda.current_stream().synchronize()
@@ -514,7 +523,7 @@ class DDPG(object):
         with torch.cuda.stream(side):
             fused = self._launch_sample_and_grads()
             if not fused:
-                self._launch_adam()
+                self._launch_adam(warmup=True)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         self.theta_main.copy_(state[0])
@@ -523,7 +532,8 @@ class DDPG(object):
         # One rank: the whole update is one graph.  Several ranks: the graph ends after the gradients; the
         # NCCL all-reduce and the Adam launch follow on the same stream (collectives are kept out of the
         # capture: a captured torch NCCL all-reduce dead-locked on the 2-GPU box).
-        self._graph_has_adam = _world(self.comm)[1] == 1
+        # With the peer-memory exchange the all-reduce IS the Adam kernel and the whole update is one graph again.
+        self._graph_has_adam = _world(self.comm)[1] == 1 or self._peer is not None
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             fused = self._launch_sample_and_grads()
@@ -531,6 +541,21 @@ class DDPG(object):
                 self._launch_adam()
         self._graph = g
         self._graph_fused = fused
+        if self._peer is not None:
+            import torch.distributed as dist
+            dist.barrier(group=_world(self.comm)[0])
+
+    def _want_peer_exchange(self):
+        group, n = _world(self.comm)
+        if n <= 1 or self.grad_exchange == 'nccl':
+            return False
+        import torch.distributed as dist
+        ok = (self._use_rows(self.batch_size) and self._same_rule() and n <= _lib.CUR_MAX_RANKS and
+              dist.get_backend(group) == 'nccl')
+        if self.grad_exchange == 'p2p' and not ok:
+            raise ValueError('grad_exchange="p2p" needs the rows schedule, one Adam rule for both nets and an NCCL '
+                             'group of <= %d ranks' % _lib.CUR_MAX_RANKS)
+        return ok
 
     def _same_rule(self):
         qa, pa = self.Q_adam, self.pi_adam
@@ -568,7 +593,8 @@ class DDPG(object):
             _lib.check(lib.cur_ddpg_rows_step(
                 _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
                 C.byref(self._stats), C.byref(cb), C.byref(self._ghyper), self._workspace_rows(n).data_ptr(),
-                self.grads.data_ptr(), self._q_ring.data_ptr(), self._pi_ring.data_ptr(), self._q_pi.data_ptr(),
+                self._peer.grads_ptr(0) if self._peer is not None else self.grads.data_ptr(),
+                self._q_ring.data_ptr(), self._pi_ring.data_ptr(), self._q_pi.data_ptr(),
                 C.byref(adam) if fuse else None, C.byref(her_args) if her_args is not None else None),
                 'cur_ddpg_rows_step')
             return fuse
@@ -579,11 +605,27 @@ class DDPG(object):
             'cur_ddpg_grads')
         return False
 
-    def _launch_adam(self):
+    def _launch_adam(self, warmup=False):
         """Adam on the (already all-reduced) gradient arena; the step scale is read from the device table with
         the device step counter, so the launch is identical every update."""
         lib = _lib.load()
         qa = self.Q_adam
+        if self._peer is not None:
+            # sum the world's gradients out of peer memory and step, one kernel (csrc/p2p.cu).  The warm-up run
+            # outside capture uses a world-of-one context so that no peer is signalled with a discarded update.
+            if warmup:
+                solo = _lib.P2PCtx()
+                solo.rank, solo.world, solo.arena = 0, 1, self._peer.arena
+                solo.region[0] = self._peer.own
+                _lib.check(lib.cur_p2p_allreduce_adam(
+                    _lib.stream_ptr(), C.byref(solo), self.theta_main.data_ptr(), self._adam_m.data_ptr(),
+                    self._adam_v.data_ptr(), self._adam_tables[0].data_ptr(), self.ADAM_TABLE, self._step.data_ptr(),
+                    qa.beta1, qa.beta2, qa.epsilon, None), 'cur_p2p_allreduce_adam')
+            else:
+                self._peer.allreduce_adam(_lib.stream_ptr(), self.theta_main, self._adam_m, self._adam_v,
+                                          self._adam_tables[0], self.ADAM_TABLE, self._step, qa.beta1, qa.beta2,
+                                          qa.epsilon)
+            return
         if self._same_rule():
             # same step rule for both nets: ONE launch over the whole [Q | pad | pi] arena (padding has zero
             # gradient and stays zero)
@@ -602,6 +644,8 @@ class DDPG(object):
         if self._graph is None:
             self._build_graph()
         if self.Q_adam.t % 100 == 0:
+            if self._peer is not None:
+                self._peer.check()
             self.Q_adam.check_synced()
             self.pi_adam.check_synced()
         self._refresh_dyn()
@@ -681,7 +725,8 @@ class DDPG(object):
         excluded_subnames = ['_tf', '_op', '_vars', '_adam', 'buffer', 'sess', '_stats', 'main', 'target', 'lock',
                              'env', 'sample_transitions', 'stage_shapes', 'create_actor_critic', 'theta_', 'grads',
                              '_ws', '_batch', '_staged', 'net', 'device', 'comm', '_hyper', '_q_loss', '_pi_loss',
-                             'kwargs']
+                             'kwargs', '_graph', '_peer', '_dyn', '_gbatch', '_ghyper', '_gwant', '_q_ring', '_pi_ring',
+                             '_q_pi', '_her_keep', '_step', '_last_perm']
         state = {k: v for k, v in self.__dict__.items() if all([subname not in k for subname in excluded_subnames])}
         state['weights'] = [self.get_flat('Q'), self.get_flat('pi'), self.get_flat('Q', True), self.get_flat('pi', True),
                             self.o_stats.state_list(), self.g_stats.state_list()]

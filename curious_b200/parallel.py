@@ -68,3 +68,71 @@ def assert_synced(fingerprint, comm=None):
 def rank_seed(seed, r):
     """train.py:242: every worker draws from its own NumPy stream."""
     return seed + 1000000 * r
+
+
+class PeerGradExchange(object):
+    """Gradient exchange over NVLink peer memory, fused with Adam (csrc/p2p.cu; replaces the Allreduce + Adam of
+    mpi_adam.py:24-35 on the CUDA-graph path).  Every rank allocates a region [flags | grads 0 | grads 1],
+    ships its CUDA-IPC handle through torch.distributed and maps the peers' regions.  Needs one process per GPU
+    on one NVLink domain (cudaIpcOpenMemHandle fails otherwise -> the caller falls back to NCCL explicitly)."""
+
+    FLAG_BYTES = 128
+
+    def __init__(self, arena_floats, comm=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib
+        lib = _lib.load()
+        group, n = world(comm)
+        assert 1 < n <= _lib.CUR_MAX_RANKS, 'peer exchange needs 2..%d ranks' % _lib.CUR_MAX_RANKS
+        self.lib = lib
+        self.world = n
+        self.rank = dist.get_rank(group)
+        self.arena = int(arena_floats)
+        nbytes = lib.cur_p2p_region_bytes(self.arena)
+        assert nbytes > 0, 'gradient arena must be a positive multiple of 4 floats'
+        self.nbytes = nbytes
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(lib.cur_p2p_alloc(nbytes, C.byref(own), handle), 'cur_p2p_alloc')
+        self.own = own.value
+        self.opened = []
+        handles = [None] * n
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ctx = _lib.P2PCtx()
+        self.ctx.rank, self.ctx.world, self.ctx.arena = self.rank, n, self.arena
+        for r in range(n):
+            if r == self.rank:
+                self.ctx.region[r] = self.own
+                continue
+            p = C.c_void_p()
+            _lib.check(lib.cur_p2p_open(handles[r], C.byref(p)), 'cur_p2p_open')
+            self.opened.append(p.value)
+            self.ctx.region[r] = p.value
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+        dist.barrier(group=group)                       # every region is mapped before anyone signals
+
+    def grads_ptr(self, parity=0):
+        """Device address of gradient buffer `parity` in this rank's own region."""
+        return self.own + self.FLAG_BYTES + 4 * self.arena * parity
+
+    def allreduce_adam(self, stream, theta, m, v, neg_a_table, table_len, step_counter, beta1, beta2, eps):
+        import ctypes as C
+        from . import _lib
+        _lib.check(self.lib.cur_p2p_allreduce_adam(
+            stream, C.byref(self.ctx), theta.data_ptr(), m.data_ptr(), v.data_ptr(), neg_a_table.data_ptr(),
+            int(table_len), step_counter.data_ptr(), beta1, beta2, eps, self.error_flag.data_ptr()),
+            'cur_p2p_allreduce_adam')
+
+    def check(self):
+        """Raises if a peer did not show up within the kernel's spin budget (a rank died or diverged)."""
+        if int(self.error_flag.item()) != 0:
+            raise RuntimeError('peer gradient exchange timed out waiting for another rank')
+
+    def close(self):
+        for p in self.opened:
+            self.lib.cur_p2p_close(p)
+        self.opened = []
+        if self.own:
+            self.lib.cur_p2p_free(self.own)
+            self.own = None

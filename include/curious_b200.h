@@ -32,6 +32,7 @@ extern "C" {
 #define CUR_MAX_SEGMENTS 17 /* per-module buffers + buffer 0 (ddpg.py:255)          */
 #define CUR_MAX_COPIES 64   /* (episode, destination) pairs per cur_store_episodes  */
 #define CUR_MAX_LAYERS 8
+#define CUR_MAX_RANKS 8      /* GPUs of one NVLink domain                            */
 
 int cur_abi_version(void);
 const char* cur_last_error(void);          /* message of the last CUR_ERR_CUDA on this thread */
@@ -260,6 +261,10 @@ typedef struct cur_ddpg_hyper {
   int64_t* step_counter;
   int32_t loss_ring;
   int32_t _pad;
+  /* rows schedule only: when > 0 (requires step_counter) the gradient of update s is written to
+   * grads + (s & 1) * grads_parity_stride floats, s = counter value after this update's bump
+   * (double buffering for cur_p2p_allreduce_adam).  0: always `grads`. */
+  int64_t grads_parity_stride;
 } cur_ddpg_hyper;
 
 /* DDPG._grads (ddpg.py:235-243): writes grads = [Q_grad | pi_grad] (flat), Q_loss (1 float),
@@ -305,6 +310,36 @@ int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* theta_main,
                        float* grads, float* q_loss, float* pi_loss, float* q_pi,
                        const cur_adam_fused* adam /* or NULL: gradients only */,
                        const cur_her_args* her /* or NULL: read `batch` */);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink peer memory, fused with Adam (csrc/p2p.cu).
+ * Replaces MpiAdam.update's Allreduce(SUM) + Adam (mpi_adam.py:24-35, scale_grad_by_procs=False)
+ * on the CUDA-graph path: no host involvement, no NCCL, bit-identical parameters on every rank.
+ *
+ * Every rank allocates a region with cur_p2p_alloc (cudaMalloc + cudaIpcGetMemHandle, zeroed),
+ * sends the 64-byte handle to its peers (any transport; curious_b200/parallel.py uses
+ * torch.distributed all_gather_object) and maps theirs with cur_p2p_open.  Region layout:
+ *   [ 128 bytes of flags | gradient arena buffer 0 | gradient arena buffer 1 ]   (arena floats each)
+ * The gradient of update s (s = value of the device step counter AFTER the weight-gradient launch
+ * bumped it) must be in buffer (s & 1) of the rank's own region; cur_ddpg_rows_step does that when
+ * h->grads_parity_stride = arena and `grads` points at buffer 0.  cur_p2p_allreduce_adam then
+ * signals the peers, waits for them, sums the world's gradients in rank order out of peer memory
+ * and steps theta / m / v (same arithmetic as cur_adam_step_graph).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cur_p2p_ctx {
+  int32_t rank, world;
+  void* region[CUR_MAX_RANKS]; /* region[r] as mapped in this process; region[rank] is the local one */
+  int64_t arena;               /* floats per gradient buffer, multiple of 4 */
+} cur_p2p_ctx;
+
+int64_t cur_p2p_region_bytes(int64_t arena_floats);
+int cur_p2p_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int cur_p2p_open(const unsigned char* handle64, void** ptr);
+int cur_p2p_close(void* ptr);
+int cur_p2p_free(void* ptr);
+int cur_p2p_allreduce_adam(void* stream, const cur_p2p_ctx* ctx, float* theta, float* m, float* v,
+                           const float* neg_a_table, int table_len, const int64_t* step_counter,
+                           double beta1, double beta2, double eps, int32_t* error_flag /* or NULL */);
 
 #ifdef __cplusplus
 }

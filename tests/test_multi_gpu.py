@@ -26,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, use_graph, out_dir):
+def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto'):
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -41,7 +41,7 @@ def _worker(rank, world, port, use_graph, out_dir):
         kw, dims, ag_ids, g_ids = ddpg_kwargs(4)
         # rank 1 starts from different weights: _sync_optimizers must broadcast rank 0's (ddpg.py:466)
         agent = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', seed=rank, use_cuda_graph=use_graph,
-                               device=dev)
+                               device=dev, grad_exchange=grad_exchange)
         assert parallel.world(agent.comm)[1] == world
         theta0 = agent.theta_main.clone()
         gathered = [torch.empty_like(theta0) for _ in range(world)]
@@ -69,12 +69,17 @@ def _worker(rank, world, port, use_graph, out_dir):
             assert torch.equal(agent.grads, expect), 'all-reduce must be a plain SUM'
         for _ in range(120):                                              # crosses the every-100 check_synced
             agent.train()
+        if use_graph:
+            assert (agent._peer is not None) == (grad_exchange != 'nccl'), 'wrong gradient exchange path'
+            if agent._peer is not None:
+                agent._peer.check()
         agent.update_target_net()
         torch.cuda.synchronize()
         fp = agent.theta_main.clone()
         parallel.assert_synced(fp)
         assert torch.isfinite(fp).all()
         assert not torch.equal(fp, theta0)
+        np.save(os.path.join(out_dir, 'theta%d.npy' % rank), fp.cpu().numpy())
         np.save(os.path.join(out_dir, 'ok%d.npy' % rank), np.array([1.0]))
     finally:
         dist.destroy_process_group()
@@ -87,3 +92,18 @@ def test_two_rank_update_sums_gradients_and_stays_synced(use_graph, tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), use_graph, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(os.path.join(str(tmp_path), 'ok0.npy'))
     assert os.path.exists(os.path.join(str(tmp_path), 'ok1.npy'))
+
+
+def test_peer_memory_exchange_equals_nccl_allreduce(tmp_path):
+    """The fused peer-memory all-reduce + Adam kernel (csrc/p2p.cu) sums the ranks' gradients in rank order;
+    with two ranks that is the same float32 sum as NCCL's, so 120 updates end on bit-identical parameters."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    thetas = {}
+    for mode in ('p2p', 'nccl'):
+        d = tmp_path / mode
+        d.mkdir()
+        mp.spawn(_worker, args=(2, _free_port(), True, str(d), mode), nprocs=2, join=True)
+        thetas[mode] = [np.load(os.path.join(str(d), 'theta%d.npy' % r)) for r in range(2)]
+        assert np.array_equal(thetas[mode][0], thetas[mode][1])
+    assert np.array_equal(thetas['p2p'][0], thetas['nccl'][0])
