@@ -136,6 +136,11 @@ SIGNATURES = {
                                      C.POINTER(NormStats), C.POINTER(Batch), C.POINTER(DdpgHyper), C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AdamFused),
                                      C.POINTER(HerArgs)]),
+    'cur_tc_gemm_supported': (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    'cur_tc_gemm_workspace_floats': (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
+    'cur_tc_gemm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                              C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                              C.c_void_p]),
     'cur_p2p_region_bytes': (C.c_int64, [C.c_int64]),
     'cur_p2p_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
     'cur_p2p_open': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),

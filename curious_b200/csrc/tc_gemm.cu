@@ -1,0 +1,514 @@
+// Large-batch layer GEMMs of the DDPG actor/critic MLPs on the 5th-generation tensor cores (sm_100a).
+//
+// Replaces, for batches where the tensor pipe pays off (BASELINE config 5, per-GPU batch sweep 256-16384), the dense
+// layers of reference baselines/her/util.py:56-107 (forward), and the tf.gradients of ddpg.py:443-449 through them
+// (dX = dY W^T, dW = X^T dY) - the same problems the FFMA grouped kernel (mlp_kernels.cuh) executes at batch 256.
+//
+// Precision: the parity target is an fp32 restatement of the TF graph (rel 1e-5), which a single TF32 pass
+// (10-bit mantissa) misses by two orders of magnitude.  Every operand is therefore split in shared memory into
+//   x = hi + lo,  hi = rna_tf32(x),  lo = rna_tf32(x - hi)            (error-compensated "3xTF32")
+// and each k-step issues three tcgen05.mma.kind::tf32:  hi*hi + hi*lo + lo*hi  into the same fp32 TMEM accumulator.
+//
+// One CTA = one 128 x 256 output tile (one K split of it), 10 warps, warp specialised:
+//   warp 0      TMA producer: raw fp32 operand tiles, cp.async.bulk.tensor.2d with 128-byte swizzle, 2-stage ring,
+//               mbarrier complete_tx
+//   warps 2-5   splitters: rewrite the landed tile in place as `hi` and write `lo` next to it (element-wise, so the
+//               swizzled image is preserved), fence.proxy.async, arrive on the stage's "split" barrier
+//   warp 1      MMA issuer: one lane issues 4 k-steps x 3 tcgen05.mma (M=128, N=256, K=8) per stage from shared-memory
+//               descriptors, tcgen05.commit frees the stage / publishes the accumulator; also owns the TMEM allocation
+//   warps 6-9   epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction), bias / ReLU / ReLU-mask, 16-byte
+//               stores of the thread's own row
+// Operands are read in their NATIVE row-major orientation; whether an operand is K-major or MN-major for the MMA is
+// expressed in the shared-memory / instruction descriptors only:
+//   K-major  (fwd A = X[n][K]; dX B = W[k_in][n_out]): one box {32 k, 128|256 rows}; k-step = +32 B in the swizzle row
+//   MN-major (fwd B = W[K][N]; dW A = X[n][M], B = dY[n][N]): boxes {32 mn, 32 k rows}, one per 32-wide MN block
+//             (LBO = 4 KB between blocks); k-step = +1 KB (8 k rows)
+// The weight gradients have K = batch: K is split over CTAs into partial tiles that a second small kernel sums in
+// fixed order (deterministic, no atomics) - that also keeps every TMEM accumulation chain short.
+#include <cuda.h>
+#include <string.h>
+
+#include "net_layout.cuh"
+#include "tc_gemm.cuh"
+
+namespace cur {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 256;
+constexpr int TC_BK = 32;                       // floats per stage and k-block = one 128-byte swizzle row
+constexpr int TC_STAGES = 2;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 96 KB
+constexpr int TC_THREADS = 320;
+constexpr int TC_SPLIT_WARP0 = 2, TC_EPI_WARP0 = 6;
+constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int TC_TMEM_COLS = 256;
+
+struct TcProb {
+  int M, N, K;
+  int a_mn, b_mn;                 // 1: operand is MN-major in memory
+  int splits, k_per_split;        // K split over CTAs (weight gradients)
+  float* C; int64_t ldc; int64_t split_stride;   // split s writes C + s * split_stride
+  const float* bias; const float* aux; int64_t ldaux; int epi;
+  int tile_begin, tiles_m;
+};
+
+struct __align__(64) TcBatch {
+  CUtensorMap mapA[TC_MAX_PROBS];
+  CUtensorMap mapB[TC_MAX_PROBS];
+  TcProb p[TC_MAX_PROBS];
+  int n, total_tiles;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t tc_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_bar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void tc_bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (long long spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1ll << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tc_rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start >> 4 at [0,14), LBO >> 4 at
+// [16,30), SBO >> 4 at [32,46), version 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64))
+// MN-major 32-bit operands only exist in the SWIZZLE_128B_BASE32B flavour (layout type 1: 32-byte chunks swizzled
+// within the 128-byte row, 4-row atoms - cute::UMMA::Layout_MN_SW128_32B_Atom; TMA: SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+
+// x -> (hi, lo) in place over `n4` float4 of one operand tile; `lo_off` = byte distance hi buffer -> lo buffer
+__device__ __forceinline__ void tc_split_tile(float* hi, int lo_off_floats, int n4, int t, int nthreads) {
+  float4* h4 = reinterpret_cast<float4*>(hi);
+  float4* l4 = reinterpret_cast<float4*>(hi + lo_off_floats);
+#pragma unroll 4
+  for (int i = t; i < n4; i += nthreads) {
+    const float4 x = h4[i];
+    float4 h, l;
+    h.x = tc_rna_tf32(x.x); h.y = tc_rna_tf32(x.y); h.z = tc_rna_tf32(x.z); h.w = tc_rna_tf32(x.w);
+    l.x = tc_rna_tf32(x.x - h.x); l.y = tc_rna_tf32(x.y - h.y); l.z = tc_rna_tf32(x.z - h.z); l.w = tc_rna_tf32(x.w - h.w);
+    h4[i] = h;
+    l4[i] = l;
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcBatch G) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- which tile
+  int pi = 0;
+#pragma unroll 1
+  while (pi + 1 < G.n && (int)blockIdx.x >= G.p[pi + 1].tile_begin) ++pi;
+  const TcProb& P = G.p[pi];
+  const int tile = blockIdx.x - P.tile_begin;
+  const int tm = tile % P.tiles_m, split = tile / P.tiles_m;
+  const int m0 = tm * TC_BM;
+  const int k_begin = split * P.k_per_split;
+  const int nkb = P.k_per_split / TC_BK;
+
+  const uint32_t base = (tc_smem(tc_smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
+  const uint32_t full = bars, splitb = bars + 8 * TC_STAGES, empty = bars + 16 * TC_STAGES, accb = bars + 24 * TC_STAGES;
+  uint8_t* gen_base = tc_smem_raw + (base - tc_smem(tc_smem_raw));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      tc_bar_init(full + 8 * s, 1);
+      tc_bar_init(splitb + 8 * s, 4);
+      tc_bar_init(empty + 8 * s, 1);
+    }
+    tc_bar_init(accb, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&s_tmem)), "n"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer
+    if (lane == 0) {
+      const CUtensorMap* mA = &G.mapA[pi];
+      const CUtensorMap* mB = &G.mapB[pi];
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+        if (round > 0) tc_bar_wait(empty + 8 * s, (round - 1) & 1);
+        const uint32_t st = base + s * TC_STAGE_BYTES;
+        const uint32_t a_hi = st, b_hi = st + 2 * TC_A_BYTES;
+        const int k0 = k_begin + kb * TC_BK;
+        tc_bar_expect_tx(full + 8 * s, TC_A_BYTES + TC_B_BYTES);
+        if (!P.a_mn) {
+          tc_tma_2d(a_hi, mA, k0, m0, full + 8 * s);                           // [128 m][32 k]
+        } else {
+          for (int j = 0; j < TC_BM / 32; ++j) tc_tma_2d(a_hi + j * 4096, mA, m0 + 32 * j, k0, full + 8 * s);   // [32 k][32 m]
+        }
+        if (!P.b_mn) {
+          tc_tma_2d(b_hi, mB, k0, 0, full + 8 * s);                            // [256 n][32 k]
+        } else {
+          for (int j = 0; j < TC_BN / 32; ++j) tc_tma_2d(b_hi + j * 4096, mB, 32 * j, k0, full + 8 * s);        // [32 k][32 n]
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10),
+    // a_major at 15, b_major at 16, N >> 3 at [17,23), M >> 4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)P.a_mn << 15) | ((uint32_t)P.b_mn << 16) |
+                           ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t a_step = P.a_mn ? 1024u : 32u, b_step = P.b_mn ? 1024u : 32u;   // bytes per k-step of 8
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+      tc_bar_wait(splitb + 8 * s, round & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = base + s * TC_STAGE_BYTES;
+        const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+        // K-major: 8-row groups 1 KB apart (SBO), LBO unused.  MN-major: 32-wide MN blocks 4 KB apart (LBO), 4-row
+        // k atoms 512 B apart (SBO)
+        const uint32_t a_lbo = P.a_mn ? 4096u : 16u, b_lbo = P.b_mn ? 4096u : 16u;
+        const uint32_t a_sbo = P.a_mn ? 512u : 1024u, b_sbo = P.b_mn ? 512u : 1024u;
+        const uint32_t a_lt = P.a_mn ? 1u : 2u, b_lt = P.b_mn ? 1u : 2u;
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          const uint64_t dah = tc_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt), dal = tc_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
+          const uint64_t dbh = tc_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt), dbl = tc_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
+          tc_mma_tf32(tmem, dal, dbh, idesc, (kb | ks) != 0);      // small terms first
+          tc_mma_tf32(tmem, dah, dbl, idesc, 1u);
+          tc_mma_tf32(tmem, dah, dbh, idesc, 1u);
+        }
+        tc_commit(empty + 8 * s);                 // stage reusable once these MMAs have read it
+        if (kb == nkb - 1) tc_commit(accb);       // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else if (warp < TC_EPI_WARP0) {
+    // ===== splitters (4 warps)
+    const int t = threadIdx.x - TC_SPLIT_WARP0 * 32;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+      tc_bar_wait(full + 8 * s, round & 1);
+      float* st = reinterpret_cast<float*>(gen_base + s * TC_STAGE_BYTES);
+      tc_split_tile(st, TC_A_BYTES / 4, TC_A_BYTES / 16, t, 128);
+      tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, TC_B_BYTES / 16, t, 128);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc_bar_arrive(splitb + 8 * s);
+    }
+  } else {
+    // ===== epilogue (4 warps; warp w may only touch TMEM lanes 32 (w % 4) .. + 31)
+    const int q = warp & 3;
+    const int row = m0 + 32 * q + lane;
+    tc_bar_wait(accb, 0);
+    tc_fence_after();
+    float* crow = P.C + (int64_t)split * P.split_stride + (int64_t)row * P.ldc;
+    const float* arow = P.aux ? P.aux + (int64_t)row * P.ldaux : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      uint32_t r[32];
+      tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), r);
+      if (row < P.M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = c * 32 + 4 * j;
+          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
+          if (P.bias) {
+            const float4 b = *reinterpret_cast<const float4*>(P.bias + col);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          if (P.epi == EPI_RELU) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          } else if (P.epi == EPI_RELU_MASK) {
+            const float4 a = *reinterpret_cast<const float4*>(arow + col);
+            v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
+          }
+          *reinterpret_cast<float4*>(crow + col) = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// out[i] = sum_s part[s][i], fixed order (split-K weight gradients)
+__global__ void __launch_bounds__(256) tc_reduce_kernel(const __grid_constant__ TcReduceBatch R) {
+  int pi = 0;
+#pragma unroll 1
+  while (pi + 1 < R.n && (int)blockIdx.x >= R.p[pi + 1].block_begin) ++pi;
+  const TcReduce& P = R.p[pi];
+  const int64_t i4 = (int64_t)(blockIdx.x - P.block_begin) * 256 + threadIdx.x;
+  if (i4 * 4 >= P.count) return;
+  float4 acc = *reinterpret_cast<const float4*>(P.part + i4 * 4);
+  for (int s = 1; s < P.splits; ++s) {
+    const float4 x = *reinterpret_cast<const float4*>(P.part + (int64_t)s * P.stride + i4 * 4);
+    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+  }
+  *reinterpret_cast<float4*>(P.out + i4 * 4) = acc;
+}
+
+// partial column sums of dY over row chunks (bias gradients at large batch): part[chunk][n]
+__global__ void __launch_bounds__(256) tc_colsum_kernel(const float* __restrict__ B, int64_t ldb, int64_t rows, int N,
+                                                        int rows_per_chunk, float* __restrict__ part) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int chunk = blockIdx.y;
+  if (n >= N) return;
+  const int64_t r0 = (int64_t)chunk * rows_per_chunk;
+  const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int64_t r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += B[r * ldb + n]; s1 += B[(r + 1) * ldb + n]; s2 += B[(r + 2) * ldb + n]; s3 += B[(r + 3) * ldb + n];
+  }
+  for (; r < r1; ++r) s0 += B[r * ldb + n];
+  part[(int64_t)chunk * N + n] = (s0 + s1) + (s2 + s3);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major [rows][cols] fp32 with leading dimension ld; box = {32 floats, box_rows}; 128-byte swizzle of 16-byte
+// chunks (K-major operands) or of 32-byte chunks (MN-major operands)
+static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  CUR_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled failed (%d): rows %lld cols %lld ld %lld", (int)rc,
+             (long long)rows, (long long)cols, (long long)ld);
+    return CUR_ERR_CUDA;
+  }
+  return CUR_OK;
+}
+
+bool tc_supported(const GemmProb& p) {
+  if (p.ones_a || p.K2 != 0 || p.C2 != nullptr) return false;
+  if (p.N != TC_BN || (p.M % TC_BM) != 0 || (p.K % TC_BK) != 0 || p.M <= 0 || p.K <= 0) return false;
+  if (!(p.epi == EPI_NONE || p.epi == EPI_RELU || p.epi == EPI_RELU_MASK)) return false;
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al(p.A) || !al(p.B) || !al(p.C) || (p.bias && !al(p.bias)) || (p.aux && !al(p.aux))) return false;
+  if ((p.lda % 4) || (p.ldb % 4) || (p.ldc % 4) || (p.aux && (p.ldaux % 4))) return false;
+  return true;
+}
+
+int tc_pick_splits(const GemmProb& p) {
+  // forward / dX problems have M = batch: plenty of tiles.  Weight gradients (M = 256) split K = batch into chunks of
+  // 512 rows: 2 x batch / 512 CTAs per matrix and short accumulation chains
+  if (p.M >= 1024) return 1;
+  int s = p.K / 512;
+  if (s < 1) s = 1;
+  while (s > 1 && (p.K % (s * TC_BK)) != 0) --s;
+  return s;
+}
+
+int64_t tc_partial_floats(const GemmProb& p) {
+  const int s = tc_pick_splits(p);
+  return s > 1 ? (int64_t)s * p.M * p.N : 0;
+}
+
+// Adds `p` to the batch.  `partial` (tc_partial_floats(p) floats, 16-byte aligned) is needed when K is split.
+int TcLauncher::add(const GemmProb& p, float* partial) {
+  CUR_REQUIRE(tc_supported(p), "problem does not fit the tensor-core GEMM");
+  CUR_REQUIRE(G.n < TC_MAX_PROBS, "too many problems in one tensor-core batch");
+  TcBatch& B = *reinterpret_cast<TcBatch*>(storage);
+  const int i = G.n;
+  TcProb& q = B.p[i];
+  memset(&q, 0, sizeof(q));
+  q.M = p.M; q.N = p.N; q.K = p.K;
+  q.a_mn = p.a_trans ? 1 : 0;          // A stored [K][M]
+  q.b_mn = p.b_trans ? 0 : 1;          // B stored [K][N] is N-major; stored [N][K] is K-major
+  q.splits = tc_pick_splits(p);
+  q.k_per_split = p.K / q.splits;
+  CUR_REQUIRE(q.k_per_split % TC_BK == 0, "K split must be a multiple of 32");
+  q.bias = p.bias; q.aux = p.aux; q.ldaux = p.ldaux; q.epi = p.epi;
+  if (q.splits > 1) {
+    CUR_REQUIRE(partial != nullptr, "split-K needs a partial buffer");
+    CUR_REQUIRE(p.bias == nullptr && p.epi == EPI_NONE, "split-K problems have no epilogue");
+    q.C = partial; q.ldc = p.N; q.split_stride = (int64_t)p.M * p.N;
+    CUR_REQUIRE(R.n < 2 * TC_MAX_PROBS, "too many reductions");
+    CUR_REQUIRE(p.ldc == p.N, "split-K output must be contiguous");
+    TcReduce& r = R.p[R.n++];
+    r.part = partial; r.out = p.C; r.count = (int64_t)p.M * p.N; r.stride = q.split_stride; r.splits = q.splits;
+  } else {
+    q.C = p.C; q.ldc = p.ldc; q.split_stride = 0;
+  }
+  q.tiles_m = p.M / TC_BM;
+  q.tile_begin = G.total_tiles;
+  G.total_tiles += q.tiles_m * q.splits;
+  if (!q.a_mn) CUR_TRY(make_map(&B.mapA[i], p.A, p.M, p.K, p.lda, TC_BM, false));
+  else CUR_TRY(make_map(&B.mapA[i], p.A, p.K, p.M, p.lda, TC_BK, true));
+  if (!q.b_mn) CUR_TRY(make_map(&B.mapB[i], p.B, p.N, p.K, p.ldb, TC_BN, false));
+  else CUR_TRY(make_map(&B.mapB[i], p.B, p.K, p.N, p.ldb, TC_BK, true));
+  G.n = i + 1;
+  return CUR_OK;
+}
+
+int TcLauncher::add_colsum(const float* B, int64_t ldb, int64_t rows, int N, float* out, float* partial) {
+  CUR_REQUIRE(n_colsum < TC_MAX_PROBS && R.n < 2 * TC_MAX_PROBS, "too many column sums");
+  CUR_REQUIRE((N % 4) == 0 && partial != nullptr, "bad column-sum problem");
+  ColSum& c = colsum[n_colsum++];
+  c.B = B; c.ldb = ldb; c.rows = rows; c.N = N; c.part = partial;
+  c.chunks = (int)((rows + TC_COLSUM_ROWS - 1) / TC_COLSUM_ROWS);
+  TcReduce& r = R.p[R.n++];
+  r.part = partial; r.out = out; r.count = N; r.stride = N; r.splits = c.chunks;
+  return CUR_OK;
+}
+
+int TcLauncher::flush(cudaStream_t s) {
+  TcBatch& B = *reinterpret_cast<TcBatch*>(storage);
+  static bool configured = false;
+  if (!configured) {
+    CUR_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    configured = true;
+  }
+  if (G.n > 0) {
+    B.n = G.n; B.total_tiles = G.total_tiles;
+    tc_gemm_kernel<<<G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s>>>(B);
+    CUR_CHECK_LAUNCH();
+  }
+  for (int i = 0; i < n_colsum; ++i) {
+    const ColSum& c = colsum[i];
+    dim3 grid((c.N + 255) / 256, c.chunks);
+    tc_colsum_kernel<<<grid, 256, 0, s>>>(c.B, c.ldb, c.rows, c.N, TC_COLSUM_ROWS, c.part);
+    CUR_CHECK_LAUNCH();
+  }
+  if (R.n > 0) {
+    CUR_REQUIRE(R.n <= 2 * TC_MAX_PROBS, "too many reductions");
+    int blocks = 0;
+    for (int i = 0; i < R.n; ++i) {
+      R.p[i].block_begin = blocks;
+      blocks += (int)((R.p[i].count / 4 + 255) / 256);
+    }
+    tc_reduce_kernel<<<blocks, 256, 0, s>>>(R);
+    CUR_CHECK_LAUNCH();
+  }
+  G.n = 0; G.total_tiles = 0; R.n = 0; n_colsum = 0;
+  return CUR_OK;
+}
+
+TcLauncher::TcLauncher() : n_colsum(0) {
+  static_assert(sizeof(TcBatch) <= sizeof(storage), "TcLauncher storage too small");
+  G.n = 0; G.total_tiles = 0; R.n = 0;
+}
+
+}  // namespace cur
+
+using namespace cur;
+
+extern "C" int cur_tc_gemm_supported(int64_t M, int64_t N, int64_t K) {
+  return (N == TC_BN && M > 0 && (M % TC_BM) == 0 && K > 0 && (K % TC_BK) == 0) ? 1 : 0;
+}
+
+extern "C" int64_t cur_tc_gemm_workspace_floats(int64_t M, int64_t N, int64_t K) {
+  GemmProb p = zero_prob();
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  return tc_partial_floats(p);
+}
+
+extern "C" int cur_tc_gemm(void* stream, const float* A, int64_t lda, int a_trans, const float* B, int64_t ldb, int b_trans,
+                           float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* aux,
+                           int64_t ldaux, int epilogue, float* workspace) {
+  CUR_REQUIRE(A && B && C, "NULL argument");
+  CUR_REQUIRE(cur_tc_gemm_supported(M, N, K), "shape: N must be 256, M a multiple of 128, K a multiple of 32");
+  GemmProb p = zero_prob();
+  p.A = A; p.lda = (int)lda; p.a_trans = a_trans; p.B = B; p.ldb = (int)ldb; p.b_trans = b_trans;
+  p.C = C; p.ldc = (int)ldc; p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.bias = bias; p.aux = aux; p.ldaux = (int)ldaux;
+  p.epi = epilogue == 1 ? EPI_RELU : epilogue == 2 ? EPI_RELU_MASK : EPI_NONE;
+  CUR_REQUIRE(tc_supported(p), "alignment: pointers 16-byte aligned, leading dimensions multiples of 4");
+  TcLauncher L;
+  CUR_TRY(L.add(p, workspace));
+  return L.flush((cudaStream_t)stream);
+}

@@ -341,6 +341,24 @@ int cur_p2p_allreduce_adam(void* stream, const cur_p2p_ctx* ctx, float* theta, f
                            const float* neg_a_table, int table_len, const int64_t* step_counter,
                            double beta1, double beta2, double eps, int32_t* error_flag /* or NULL */);
 
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core layer GEMM for large batches (csrc/tc_gemm.cu): tcgen05 (kind::tf32) with TMEM
+ * accumulators, TMA operand staging and error-compensated 3xTF32 operands (fp32-level accuracy).
+ * The dense layers of util.py:56-107 and their gradients (ddpg.py:443-449) at batch >= 1024 -
+ * cur_ddpg_grads routes its hidden-layer problems here; this entry point exposes one problem:
+ *   C[M,N] = epi( opA(A)[M,K] * opB(B)[K,N] + bias[N] )
+ *   a_trans: A is stored [K][M] (lda >= M);  b_trans: B is stored [N][K] (ldb >= K)
+ *   epilogue: 0 none, 1 ReLU, 2 gate by aux[M][N] > 0 (ReLU backward)
+ * Shape: N == 256, M % 128 == 0, K % 32 == 0; 16-byte aligned pointers, leading dimensions % 4.
+ * M < 1024 splits K over CTAs (weight gradients, K = batch): `workspace` must then hold
+ * cur_tc_gemm_workspace_floats(M, N, K) floats and bias / epilogue must be unset.
+ * ------------------------------------------------------------------------------------------ */
+int cur_tc_gemm_supported(int64_t M, int64_t N, int64_t K);
+int64_t cur_tc_gemm_workspace_floats(int64_t M, int64_t N, int64_t K);
+int cur_tc_gemm(void* stream, const float* A, int64_t lda, int a_trans, const float* B, int64_t ldb,
+                int b_trans, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
+                const float* aux, int64_t ldaux, int epilogue, float* workspace);
+
 #ifdef __cplusplus
 }
 #endif
