@@ -17,7 +17,10 @@
 // kernel [in,out] followed by bias [out] is exactly one contiguous (in+1) x out matrix there.
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "net_layout.cuh"
+#include "tc_gemm.cuh"
 
 namespace cur {
 
@@ -28,8 +31,28 @@ struct Workspace {
   float *hp[CUR_MAX_LAYERS], *hq[CUR_MAX_LAYERS], *hqp[CUR_MAX_LAYERS], *ht[CUR_MAX_LAYERS], *htq[CUR_MAX_LAYERS];
   float *Q, *Qt, *dQ, *dQpi, *dy;
   float *dc[2], *da[2], *dp[2];
+  // tensor-core path (large batch only): split-K partial tiles / partial row reductions, TC_SLOTS problems per level
+  float *tc_part, *tc_rowpart;
+  int64_t tc_part_stride, tc_rowpart_stride;
   int64_t total;
 };
+
+// Batches this large run their hidden-layer GEMMs on the tensor cores (tc_gemm.cu); below it every GEMM of a
+// level is latency-bound and the FFMA grouped kernel wins.  CUR_DDPG_TC=0 forces the FFMA path (A/B measurements).
+constexpr int64_t TC_MIN_BATCH = 1024;
+constexpr int TC_SLOTS = 3;          // split-K weight gradients / row reductions per dependency level
+static int g_tc_mode = -1;          // -1: environment (default on), 0: off, 1: on  (cur_ddpg_set_tensor_cores)
+static bool tc_enabled() {
+  if (g_tc_mode >= 0) return g_tc_mode == 1;
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CUR_DDPG_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+static bool tc_shape_ok(const cur_net_desc& d, int64_t n) { return n >= TC_MIN_BATCH && (n % 128) == 0 && d.hidden == 256; }
+static bool use_tc(const cur_net_desc& d, int64_t n) { return tc_enabled() && tc_shape_ok(d, n); }
 
 static Workspace carve(const cur_net_desc& d, int64_t n, float* base) {
   Workspace w;
@@ -67,6 +90,16 @@ static Workspace carve(const cur_net_desc& d, int64_t n, float* base) {
     w.dc[i] = take(n * w.H);
     w.da[i] = take(n * w.H);
     w.dp[i] = take(n * w.H);
+  }
+  w.tc_part = w.tc_rowpart = nullptr;
+  w.tc_part_stride = w.tc_rowpart_stride = 0;
+  if (tc_shape_ok(d, n)) {      // carved whenever the shape is eligible: the workspace size does not depend on the toggle
+    GemmProb dwp = zero_prob();
+    dwp.M = w.H; dwp.N = w.H; dwp.K = (int)n; dwp.a_trans = 1;
+    w.tc_part_stride = r4(tc_partial_floats(dwp));
+    w.tc_rowpart_stride = r4(tc_rowred_partial_floats(n, w.H, 4));
+    w.tc_part = take(TC_SLOTS * w.tc_part_stride);
+    w.tc_rowpart = take(TC_SLOTS * w.tc_rowpart_stride);
   }
   w.total = o;
   return w;
@@ -220,15 +253,56 @@ __global__ void __launch_bounds__(1024) loss_kernel(const __grid_constant__ Loss
   }
 }
 
+// One dependency level: problems that fit the tensor-core kernel go there when the batch is large, everything else
+// (first / output layers, small batches) to the FFMA grouped kernel.  Both launches of a level are independent.
 struct Batcher {
   GemmBatch G;
+  TcLauncher T;
   cudaStream_t s;
-  explicit Batcher(cudaStream_t st) : s(st) { G.n = 0; G.total_tiles = 0; }
-  void add(const GemmProb& p) { G.p[G.n++] = p; }
+  bool tc;
+  float *tc_part, *tc_rowpart;
+  int64_t part_stride, rowpart_stride;
+  int rc, parts_used, rowparts_used;
+  explicit Batcher(cudaStream_t st) : s(st), tc(false), tc_part(nullptr), tc_rowpart(nullptr), part_stride(0),
+                                      rowpart_stride(0), rc(CUR_OK), parts_used(0), rowparts_used(0) {
+    G.n = 0; G.total_tiles = 0;
+  }
+  Batcher(cudaStream_t st, bool use_tensor_cores, const Workspace& w)
+      : s(st), tc(use_tensor_cores && w.tc_part != nullptr), tc_part(w.tc_part), tc_rowpart(w.tc_rowpart),
+        part_stride(w.tc_part_stride), rowpart_stride(w.tc_rowpart_stride), rc(CUR_OK), parts_used(0), rowparts_used(0) {
+    G.n = 0; G.total_tiles = 0;
+  }
+  void add(const GemmProb& p) {
+    if (tc && !p.ones_a && tc_supported(p)) {
+      const bool split = tc_pick_splits(p) > 1;
+      if (!split || (parts_used < TC_SLOTS && tc_partial_floats(p) <= part_stride)) {
+        const int r = T.add(p, split ? tc_part + parts_used * part_stride : nullptr);
+        if (r != CUR_OK) rc = r;
+        if (split) ++parts_used;
+        return;
+      }
+    }
+    // K = batch reductions with a skinny output: bias gradients (column sums) and the output-layer weight gradients
+    const bool colsum = p.ones_a && p.N <= 256;
+    const bool skinny = !p.ones_a && p.a_trans && !p.b_trans && p.N <= 4 && p.K2 == 0 && p.ldc == p.N && p.epi == EPI_NONE &&
+                        p.bias == nullptr && p.C2 == nullptr;
+    if (tc && (colsum || skinny) && rowparts_used < TC_SLOTS) {
+      float* part = tc_rowpart + rowparts_used * rowpart_stride;
+      const int r = colsum ? T.add_rowred(p.B, p.ldb, p.N, nullptr, 0, 1, p.K, p.C, part)
+                           : T.add_rowred(p.A, p.lda, p.M, p.B, p.ldb, p.N, p.K, p.C, part);
+      if (r != CUR_OK) rc = r;
+      ++rowparts_used;
+      return;
+    }
+    G.p[G.n++] = p;
+  }
   int flush() {
-    int rc = launch_gemm_batch(G, s);
+    if (rc != CUR_OK) return rc;
+    int r = launch_gemm_batch(G, s);
     G.n = 0;
-    return rc;
+    if (r != CUR_OK) return r;
+    parts_used = rowparts_used = 0;
+    return T.empty() ? CUR_OK : T.flush(s);
   }
 };
 
@@ -252,6 +326,17 @@ extern "C" int64_t cur_theta_pi_offset(const cur_net_desc* d, int64_t* total) {
   const int64_t off = r4(net_layout(*d, 0).total);
   if (total) *total = off + r4(net_layout(*d, 1).total);
   return off;
+}
+
+extern "C" int cur_ddpg_set_tensor_cores(int mode) {
+  CUR_REQUIRE(mode >= -1 && mode <= 1, "mode must be -1 (default), 0 (off) or 1 (on)");
+  g_tc_mode = mode;
+  return CUR_OK;
+}
+
+extern "C" int cur_ddpg_uses_tensor_cores(const cur_net_desc* d, int64_t batch) {
+  if (check_desc(d) != CUR_OK || batch <= 0) return 0;
+  return use_tc(*d, batch) ? 1 : 0;
 }
 
 extern "C" int64_t cur_ddpg_workspace_floats(const cur_net_desc* d, int64_t batch) {
@@ -343,7 +428,7 @@ extern "C" int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* 
   prep_kernel<<<grid_prep(n * LQ.in_s), 256, 0, s>>>(P);
   CUR_CHECK_LAUNCH();
 
-  Batcher B(s);
+  Batcher B(s, use_tc(*d, n), w);
   // ---- fwd-1: main.pi | target.pi | main.Q(o,g,u)
   B.add(fwd0(LP, mP, w.Xpi, w.ld_spi, w.Xg, w.ld_g, w.hp[0], n));
   B.add(fwd0(LP, tP, w.Xpi_t, w.ld_spi, w.Xg_t, w.ld_g, w.ht[0], n));

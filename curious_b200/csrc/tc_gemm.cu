@@ -6,25 +6,29 @@
 //
 // Precision: the parity target is an fp32 restatement of the TF graph (rel 1e-5), which a single TF32 pass
 // (10-bit mantissa) misses by two orders of magnitude.  Every operand is therefore split in shared memory into
-//   x = hi + lo,  hi = rna_tf32(x),  lo = rna_tf32(x - hi)            (error-compensated "3xTF32")
-// and each k-step issues three tcgen05.mma.kind::tf32:  hi*hi + hi*lo + lo*hi  into the same fp32 TMEM accumulator.
+//   x = hi + lo,  hi = x rounded to TF32,  lo = x - hi (exact in fp32, then cut to TF32)      ("3xTF32")
+// and each k-step issues three tcgen05.mma.kind::tf32: hi*hi into TMEM accumulator 0, lo*hi + hi*lo into TMEM
+// accumulator 1.  Two accumulators because the tensor core's fp32 accumulation does not round to nearest: keeping the
+// small cross terms out of the large sum cuts the number of lossy additions into it by 3x; the epilogue adds the two.
 //
-// One CTA = one 128 x 256 output tile (one K split of it), 10 warps, warp specialised:
+// One CTA = one 128 x 256 output tile (one K split of it), 14 warps, warp specialised:
 //   warp 0      TMA producer: raw fp32 operand tiles, cp.async.bulk.tensor.2d with 128-byte swizzle, 2-stage ring,
-//               mbarrier complete_tx
-//   warps 2-5   splitters: rewrite the landed tile in place as `hi` and write `lo` next to it (element-wise, so the
-//               swizzled image is preserved), fence.proxy.async, arrive on the stage's "split" barrier
+//               mbarrier complete_tx; out-of-bounds rows / columns are zero-filled by the TMA unit, which is how
+//               K = 44..60 first layers and M = 12..48 first-layer weight gradients ride the same 128 x 256 x 32 tiles
+//   warps 2-9   splitters: rewrite the landed tile in place as `hi` and write `lo` next to it (element-wise integer /
+//               FADD work, so the swizzled image is preserved), fence.proxy.async, arrive on the "split" barrier
 //   warp 1      MMA issuer: one lane issues 4 k-steps x 3 tcgen05.mma (M=128, N=256, K=8) per stage from shared-memory
-//               descriptors, tcgen05.commit frees the stage / publishes the accumulator; also owns the TMEM allocation
-//   warps 6-9   epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction), bias / ReLU / ReLU-mask, 16-byte
-//               stores of the thread's own row
+//               descriptors, tcgen05.commit frees the stage / publishes the accumulators; owns the TMEM allocation
+//   warps 10-13 epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction), transposed through a padded
+//               shared-memory slab so that bias / ReLU / ReLU-mask and the stores are 128-byte coalesced
 // Operands are read in their NATIVE row-major orientation; whether an operand is K-major or MN-major for the MMA is
 // expressed in the shared-memory / instruction descriptors only:
-//   K-major  (fwd A = X[n][K]; dX B = W[k_in][n_out]): one box {32 k, 128|256 rows}; k-step = +32 B in the swizzle row
+//   K-major  (fwd A = X[n][K]; dX B = W[k_in][n_out]): one box {32 k, 128|256 rows}, SWIZZLE_128B; k-step = +32 B
 //   MN-major (fwd B = W[K][N]; dW A = X[n][M], B = dY[n][N]): boxes {32 mn, 32 k rows}, one per 32-wide MN block
-//             (LBO = 4 KB between blocks); k-step = +1 KB (8 k rows)
-// The weight gradients have K = batch: K is split over CTAs into partial tiles that a second small kernel sums in
-// fixed order (deterministic, no atomics) - that also keeps every TMEM accumulation chain short.
+//             (LBO = 4 KB), SWIZZLE_128B_BASE32B (the only MN-major layout 32-bit operands have); k-step = +1 KB
+// A problem may have a second K segment (first layer: [o|td|u] W0 + g W0g, util.py:92-99) - the producer switches
+// tensor maps, the accumulators keep going.  The weight gradients have K = batch: K is split over CTAs into partial
+// tiles that a second small kernel sums in fixed order (deterministic, no atomics).
 #include <cuda.h>
 #include <string.h>
 
@@ -40,15 +44,20 @@ constexpr int TC_STAGES = 2;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 96 KB
-constexpr int TC_THREADS = 320;
-constexpr int TC_SPLIT_WARP0 = 2, TC_EPI_WARP0 = 6;
-constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_SPLIT_WARP0 = 2, TC_EPI_WARP0 = TC_SPLIT_WARP0 + TC_SPLIT_WARPS;
+constexpr int TC_THREADS = (TC_EPI_WARP0 + 4) * 32;           // 448
+constexpr int TC_EPI_LD = 36;                                  // padded row of the epilogue slab (floats)
+constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_LD * 4;          // one 32 x 32 slab per epilogue warp
+constexpr size_t TC_SMEM_BYTES =
+    (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + TC_EPI_BYTES;
+constexpr int TC_TMEM_COLS = 512;                              // accumulator 0: columns 0..255, accumulator 1: 256..511
 
 struct TcProb {
   int M, N, K;
   int a_mn, b_mn;                 // 1: operand is MN-major in memory
   int splits, k_per_split;        // K split over CTAs (weight gradients)
+  int nkb1, nkb2;                 // k-blocks of 32 per CTA: first segment (of this split), second segment
   float* C; int64_t ldc; int64_t split_stride;   // split s writes C + s * split_stride
   const float* bias; const float* aux; int64_t ldaux; int epi;
   int tile_begin, tiles_m;
@@ -57,6 +66,8 @@ struct TcProb {
 struct __align__(64) TcBatch {
   CUtensorMap mapA[TC_MAX_PROBS];
   CUtensorMap mapB[TC_MAX_PROBS];
+  CUtensorMap mapA2[TC_MAX_PROBS];   // second K segment (nkb2 > 0)
+  CUtensorMap mapB2[TC_MAX_PROBS];
   TcProb p[TC_MAX_PROBS];
   int n, total_tiles;
 };
@@ -137,7 +148,13 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 
-// x -> (hi, lo) in place over `n4` float4 of one operand tile; `lo_off` = byte distance hi buffer -> lo buffer
+// x -> (hi, lo) in place over `n4` float4 of one operand tile.  hi = x rounded to 11 significant bits (integer
+// round-half-up on the bit pattern), lo = x - hi is exact in fp32 and is cut to TF32 as well, so the tensor core sees
+// exactly representable operands whatever it does with the low 13 bits.
+__device__ __forceinline__ void tc_split1(float x, float& h, float& l) {
+  h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  l = __uint_as_float(__float_as_uint(x - h) & 0xFFFFE000u);
+}
 __device__ __forceinline__ void tc_split_tile(float* hi, int lo_off_floats, int n4, int t, int nthreads) {
   float4* h4 = reinterpret_cast<float4*>(hi);
   float4* l4 = reinterpret_cast<float4*>(hi + lo_off_floats);
@@ -145,8 +162,7 @@ __device__ __forceinline__ void tc_split_tile(float* hi, int lo_off_floats, int 
   for (int i = t; i < n4; i += nthreads) {
     const float4 x = h4[i];
     float4 h, l;
-    h.x = tc_rna_tf32(x.x); h.y = tc_rna_tf32(x.y); h.z = tc_rna_tf32(x.z); h.w = tc_rna_tf32(x.w);
-    l.x = tc_rna_tf32(x.x - h.x); l.y = tc_rna_tf32(x.y - h.y); l.z = tc_rna_tf32(x.z - h.z); l.w = tc_rna_tf32(x.w - h.w);
+    tc_split1(x.x, h.x, l.x); tc_split1(x.y, h.y, l.y); tc_split1(x.z, h.z, l.z); tc_split1(x.w, h.w, l.w);
     h4[i] = h;
     l4[i] = l;
   }
@@ -166,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const int tm = tile % P.tiles_m, split = tile / P.tiles_m;
   const int m0 = tm * TC_BM;
   const int k_begin = split * P.k_per_split;
-  const int nkb = P.k_per_split / TC_BK;
+  const int nkb = P.nkb1 + P.nkb2;
 
   const uint32_t base = (tc_smem(tc_smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
@@ -176,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       tc_bar_init(full + 8 * s, 1);
-      tc_bar_init(splitb + 8 * s, 4);
+      tc_bar_init(splitb + 8 * s, TC_SPLIT_WARPS);
       tc_bar_init(empty + 8 * s, 1);
     }
     tc_bar_init(accb, 1);
@@ -195,15 +211,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (warp == 0) {
     // ===== TMA producer
     if (lane == 0) {
-      const CUtensorMap* mA = &G.mapA[pi];
-      const CUtensorMap* mB = &G.mapB[pi];
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TC_STAGES, round = kb / TC_STAGES;
         if (round > 0) tc_bar_wait(empty + 8 * s, (round - 1) & 1);
         const uint32_t st = base + s * TC_STAGE_BYTES;
         const uint32_t a_hi = st, b_hi = st + 2 * TC_A_BYTES;
-        const int k0 = k_begin + kb * TC_BK;
-        tc_bar_expect_tx(full + 8 * s, TC_A_BYTES + TC_B_BYTES);
+        const bool seg2 = kb >= P.nkb1;
+        const CUtensorMap* mA = seg2 ? &G.mapA2[pi] : &G.mapA[pi];
+        const CUtensorMap* mB = seg2 ? &G.mapB2[pi] : &G.mapB[pi];
+        const int k0 = seg2 ? (kb - P.nkb1) * TC_BK : k_begin + kb * TC_BK;
+        tc_bar_expect_tx(full + 8 * s, TC_A_BYTES + TC_B_BYTES);      // zero-filled out-of-bounds bytes count too
         if (!P.a_mn) {
           tc_tma_2d(a_hi, mA, k0, m0, full + 8 * s);                           // [128 m][32 k]
         } else {
@@ -223,6 +240,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)P.a_mn << 15) | ((uint32_t)P.b_mn << 16) |
                            ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     const uint32_t a_step = P.a_mn ? 1024u : 32u, b_step = P.b_mn ? 1024u : 32u;   // bytes per k-step of 8
+    // K-major: 8-row groups 1 KB apart (SBO), LBO unused.  MN-major: 32-wide MN blocks 4 KB apart (LBO), 4-row
+    // k atoms 512 B apart (SBO)
+    const uint32_t a_lbo = P.a_mn ? 4096u : 16u, b_lbo = P.b_mn ? 4096u : 16u;
+    const uint32_t a_sbo = P.a_mn ? 512u : 1024u, b_sbo = P.b_mn ? 512u : 1024u;
+    const uint32_t a_lt = P.a_mn ? 1u : 2u, b_lt = P.b_mn ? 1u : 2u;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % TC_STAGES, round = kb / TC_STAGES;
       tc_bar_wait(splitb + 8 * s, round & 1);
@@ -230,33 +252,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       if (lane == 0) {
         const uint32_t st = base + s * TC_STAGE_BYTES;
         const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
-        // K-major: 8-row groups 1 KB apart (SBO), LBO unused.  MN-major: 32-wide MN blocks 4 KB apart (LBO), 4-row
-        // k atoms 512 B apart (SBO)
-        const uint32_t a_lbo = P.a_mn ? 4096u : 16u, b_lbo = P.b_mn ? 4096u : 16u;
-        const uint32_t a_sbo = P.a_mn ? 512u : 1024u, b_sbo = P.b_mn ? 512u : 1024u;
-        const uint32_t a_lt = P.a_mn ? 1u : 2u, b_lt = P.b_mn ? 1u : 2u;
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
           const uint64_t dah = tc_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt), dal = tc_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
           const uint64_t dbh = tc_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt), dbl = tc_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
-          tc_mma_tf32(tmem, dal, dbh, idesc, (kb | ks) != 0);      // small terms first
-          tc_mma_tf32(tmem, dah, dbl, idesc, 1u);
-          tc_mma_tf32(tmem, dah, dbh, idesc, 1u);
+          tc_mma_tf32(tmem + TC_BN, dal, dbh, idesc, (kb | ks) != 0);      // cross terms -> accumulator 1
+          tc_mma_tf32(tmem + TC_BN, dah, dbl, idesc, 1u);
+          tc_mma_tf32(tmem, dah, dbh, idesc, (kb | ks) != 0);              // main term   -> accumulator 0
         }
         tc_commit(empty + 8 * s);                 // stage reusable once these MMAs have read it
-        if (kb == nkb - 1) tc_commit(accb);       // accumulator complete
+        if (kb == nkb - 1) tc_commit(accb);       // accumulators complete
       }
       __syncwarp();
     }
   } else if (warp < TC_EPI_WARP0) {
-    // ===== splitters (4 warps)
+    // ===== splitters
     const int t = threadIdx.x - TC_SPLIT_WARP0 * 32;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % TC_STAGES, round = kb / TC_STAGES;
       tc_bar_wait(full + 8 * s, round & 1);
       float* st = reinterpret_cast<float*>(gen_base + s * TC_STAGE_BYTES);
-      tc_split_tile(st, TC_A_BYTES / 4, TC_A_BYTES / 16, t, 128);
-      tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, TC_B_BYTES / 16, t, 128);
+      tc_split_tile(st, TC_A_BYTES / 4, TC_A_BYTES / 16, t, TC_SPLIT_WARPS * 32);
+      tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, TC_B_BYTES / 16, t, TC_SPLIT_WARPS * 32);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) tc_bar_arrive(splitb + 8 * s);
@@ -264,34 +281,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   } else {
     // ===== epilogue (4 warps; warp w may only touch TMEM lanes 32 (w % 4) .. + 31)
     const int q = warp & 3;
-    const int row = m0 + 32 * q + lane;
+    float* slab = reinterpret_cast<float*>(gen_base + TC_STAGES * TC_STAGE_BYTES + 256) + q * 32 * TC_EPI_LD;
+    const int row0 = m0 + 32 * q;
     tc_bar_wait(accb, 0);
     tc_fence_after();
-    float* crow = P.C + (int64_t)split * P.split_stride + (int64_t)row * P.ldc;
-    const float* arow = P.aux ? P.aux + (int64_t)row * P.ldaux : nullptr;
+    float* cbase = P.C + (int64_t)split * P.split_stride;
+    const int rr = lane >> 3, ch = lane & 7;          // phase 2: this lane owns rows rr + 4 i, columns 4 ch .. 4 ch + 3
 #pragma unroll 1
     for (int c = 0; c < TC_BN / 32; ++c) {
-      uint32_t r[32];
-      tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), r);
-      if (row < P.M) {
+      uint32_t r0[32], r1[32];
+      tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), r0);
+      tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(TC_BN + c * 32), r1);
+      // phase 1: lane = row of the slab, 32 columns -> 8 conflict-free 16-byte stores (row pitch 36 floats)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = c * 32 + 4 * j;
-          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                 __uint_as_float(r[4 * j + 3]));
-          if (P.bias) {
-            const float4 b = *reinterpret_cast<const float4*>(P.bias + col);
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          }
+      for (int j = 0; j < 8; ++j) {
+        float4 v;
+        v.x = __uint_as_float(r0[4 * j]) + __uint_as_float(r1[4 * j]);
+        v.y = __uint_as_float(r0[4 * j + 1]) + __uint_as_float(r1[4 * j + 1]);
+        v.z = __uint_as_float(r0[4 * j + 2]) + __uint_as_float(r1[4 * j + 2]);
+        v.w = __uint_as_float(r0[4 * j + 3]) + __uint_as_float(r1[4 * j + 3]);
+        *reinterpret_cast<float4*>(slab + lane * TC_EPI_LD + 4 * j) = v;
+      }
+      __syncwarp();
+      // phase 2: 8 lanes cover one 128-byte row segment -> coalesced bias / mask loads and stores
+      const int col = c * 32 + 4 * ch;
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (P.bias) b = *reinterpret_cast<const float4*>(P.bias + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rr + 4 * i;
+        const int row = row0 + r;
+        float4 v = *reinterpret_cast<const float4*>(slab + r * TC_EPI_LD + 4 * ch);
+        if (row < P.M) {
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
           if (P.epi == EPI_RELU) {
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
           } else if (P.epi == EPI_RELU_MASK) {
-            const float4 a = *reinterpret_cast<const float4*>(arow + col);
+            const float4 a = *reinterpret_cast<const float4*>(P.aux + (int64_t)row * P.ldaux + col);
             v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
           }
-          *reinterpret_cast<float4*>(crow + col) = v;
+          *reinterpret_cast<float4*>(cbase + (int64_t)row * P.ldc + col) = v;
         }
       }
+      __syncwarp();
     }
     tc_fence_before();
   }
@@ -310,29 +342,80 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(const __grid_constant__ 
   const TcReduce& P = R.p[pi];
   const int64_t i4 = (int64_t)(blockIdx.x - P.block_begin) * 256 + threadIdx.x;
   if (i4 * 4 >= P.count) return;
-  float4 acc = *reinterpret_cast<const float4*>(P.part + i4 * 4);
-  for (int s = 1; s < P.splits; ++s) {
-    const float4 x = *reinterpret_cast<const float4*>(P.part + (int64_t)s * P.stride + i4 * 4);
-    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+  if (P.vec) {
+    float4 acc = *reinterpret_cast<const float4*>(P.part + i4 * 4);
+    for (int s = 1; s < P.splits; ++s) {
+      const float4 x = *reinterpret_cast<const float4*>(P.part + (int64_t)s * P.stride + i4 * 4);
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    *reinterpret_cast<float4*>(P.out + i4 * 4) = acc;
+  } else {
+    for (int64_t i = i4 * 4; i < i4 * 4 + 4 && i < P.count; ++i) {
+      float acc = P.part[i];
+      for (int s = 1; s < P.splits; ++s) acc += P.part[(int64_t)s * P.stride + i];
+      P.out[i] = acc;
+    }
   }
-  *reinterpret_cast<float4*>(P.out + i4 * 4) = acc;
 }
 
-// partial column sums of dY over row chunks (bias gradients at large batch): part[chunk][n]
-__global__ void __launch_bounds__(256) tc_colsum_kernel(const float* __restrict__ B, int64_t ldb, int64_t rows, int N,
-                                                        int rows_per_chunk, float* __restrict__ part) {
-  const int n = blockIdx.x * 256 + threadIdx.x;
+// Row reductions at large batch, partial over chunks of TC_COLSUM_ROWS rows (summed by tc_reduce_kernel):
+//   Y == NULL:  part[chunk][m]    = sum_r X[r][m]                      bias gradients  db = 1^T dY
+//   Y != NULL:  part[chunk][m][j] = sum_r X[r][m] * Y[r][j], j < NJ    output-layer weight gradients (N = 1 or dimu)
+// Block = 16 column quads x 16 row lanes: every thread owns 4 columns and every 16th row of the chunk; the 16 row
+// lanes are folded through shared memory in fixed order.
+struct RowRed {
+  const float* X; int64_t ldx; const float* Y; int64_t ldy;
+  int64_t rows; int M, NJ; float* part;
+};
+__global__ void __launch_bounds__(256) tc_rowred_kernel(const __grid_constant__ RowRed P) {
+  __shared__ float red[16][16][4 * 4 + 1];
+  const int cq = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int m = blockIdx.x * 64 + 4 * cq;
   const int chunk = blockIdx.y;
-  if (n >= N) return;
-  const int64_t r0 = (int64_t)chunk * rows_per_chunk;
-  const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int64_t r = r0;
-  for (; r + 3 < r1; r += 4) {
-    s0 += B[r * ldb + n]; s1 += B[(r + 1) * ldb + n]; s2 += B[(r + 2) * ldb + n]; s3 += B[(r + 3) * ldb + n];
+  const int64_t r0 = (int64_t)chunk * TC_COLSUM_ROWS;
+  const int64_t r1 = r0 + TC_COLSUM_ROWS < P.rows ? r0 + TC_COLSUM_ROWS : P.rows;
+  const int NJ = P.Y ? P.NJ : 1;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool vec = (m + 3 < P.M) && ((P.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.X) & 15) == 0);
+  for (int64_t r = r0 + rl; r < r1; r += 16) {
+    float x[4];
+    if (vec) {
+      const float4 v = *reinterpret_cast<const float4*>(P.X + r * P.ldx + m);
+      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = (m + i < P.M) ? P.X[r * P.ldx + m + i] : 0.f;
+    }
+    if (P.Y) {
+      float y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = j < NJ ? P.Y[r * P.ldy + j] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x[i], y[j], acc[i][j]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i][0] += x[i];
+    }
   }
-  for (; r < r1; ++r) s0 += B[r * ldb + n];
-  part[(int64_t)chunk * N + n] = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[rl][cq][4 * i + j] = acc[i][j];
+  __syncthreads();
+  // 256 threads -> 16 column quads x 16 (i, j) slots
+  const int slot = threadIdx.x >> 4;       // 4 i + j
+  const int i = slot >> 2, j = slot & 3;
+  float sum = 0.f;
+#pragma unroll
+  for (int l = 0; l < 16; ++l) sum += red[l][cq][slot];
+  const int mm = blockIdx.x * 64 + 4 * cq + i;
+  if (mm < P.M && j < NJ) P.part[((int64_t)chunk * P.M + mm) * NJ + j] = sum;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -374,19 +457,22 @@ static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols
 }
 
 bool tc_supported(const GemmProb& p) {
-  if (p.ones_a || p.K2 != 0 || p.C2 != nullptr) return false;
-  if (p.N != TC_BN || (p.M % TC_BM) != 0 || (p.K % TC_BK) != 0 || p.M <= 0 || p.K <= 0) return false;
+  if (p.ones_a || p.C2 != nullptr) return false;
+  if (p.N != TC_BN || p.M <= 0 || p.K <= 0) return false;
+  if (p.K2 != 0 && (p.a_trans || p.b_trans || p.A2 == nullptr || p.B2 == nullptr)) return false;
   if (!(p.epi == EPI_NONE || p.epi == EPI_RELU || p.epi == EPI_RELU_MASK)) return false;
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al(p.A) || !al(p.B) || !al(p.C) || (p.bias && !al(p.bias)) || (p.aux && !al(p.aux))) return false;
   if ((p.lda % 4) || (p.ldb % 4) || (p.ldc % 4) || (p.aux && (p.ldaux % 4))) return false;
+  if (p.K2 != 0 && (!al(p.A2) || !al(p.B2) || (p.lda2 % 4) || (p.ldb2 % 4))) return false;
+  if (tc_pick_splits(p) > 1 && (p.bias != nullptr || p.epi != EPI_NONE || p.ldc != p.N || p.K2 != 0)) return false;
   return true;
 }
 
 int tc_pick_splits(const GemmProb& p) {
-  // forward / dX problems have M = batch: plenty of tiles.  Weight gradients (M = 256) split K = batch into chunks of
-  // 512 rows: 2 x batch / 512 CTAs per matrix and short accumulation chains
-  if (p.M >= 1024) return 1;
+  // forward / dX problems have M = batch: plenty of tiles.  Weight gradients (M <= 256, K = batch) split K into
+  // chunks of 512 rows: batch / 512 CTAs per 128 rows of dW and short accumulation chains
+  if (p.M >= 1024 || !p.a_trans) return 1;
   int s = p.K / 512;
   if (s < 1) s = 1;
   while (s > 1 && (p.K % (s * TC_BK)) != 0) --s;
@@ -410,40 +496,51 @@ int TcLauncher::add(const GemmProb& p, float* partial) {
   q.a_mn = p.a_trans ? 1 : 0;          // A stored [K][M]
   q.b_mn = p.b_trans ? 0 : 1;          // B stored [K][N] is N-major; stored [N][K] is K-major
   q.splits = tc_pick_splits(p);
-  q.k_per_split = p.K / q.splits;
-  CUR_REQUIRE(q.k_per_split % TC_BK == 0, "K split must be a multiple of 32");
+  q.k_per_split = (q.splits > 1) ? p.K / q.splits : p.K;
+  q.nkb1 = (q.k_per_split + TC_BK - 1) / TC_BK;       // a K tail is zero-filled by the TMA unit
+  q.nkb2 = (p.K2 + TC_BK - 1) / TC_BK;
   q.bias = p.bias; q.aux = p.aux; q.ldaux = p.ldaux; q.epi = p.epi;
   if (q.splits > 1) {
     CUR_REQUIRE(partial != nullptr, "split-K needs a partial buffer");
-    CUR_REQUIRE(p.bias == nullptr && p.epi == EPI_NONE, "split-K problems have no epilogue");
     q.C = partial; q.ldc = p.N; q.split_stride = (int64_t)p.M * p.N;
     CUR_REQUIRE(R.n < 2 * TC_MAX_PROBS, "too many reductions");
-    CUR_REQUIRE(p.ldc == p.N, "split-K output must be contiguous");
     TcReduce& r = R.p[R.n++];
     r.part = partial; r.out = p.C; r.count = (int64_t)p.M * p.N; r.stride = q.split_stride; r.splits = q.splits;
+    r.vec = 1;
   } else {
     q.C = p.C; q.ldc = p.ldc; q.split_stride = 0;
   }
-  q.tiles_m = p.M / TC_BM;
+  q.tiles_m = (p.M + TC_BM - 1) / TC_BM;              // rows beyond M: zero-filled operands, stores suppressed
   q.tile_begin = G.total_tiles;
   G.total_tiles += q.tiles_m * q.splits;
   if (!q.a_mn) CUR_TRY(make_map(&B.mapA[i], p.A, p.M, p.K, p.lda, TC_BM, false));
   else CUR_TRY(make_map(&B.mapA[i], p.A, p.K, p.M, p.lda, TC_BK, true));
   if (!q.b_mn) CUR_TRY(make_map(&B.mapB[i], p.B, p.N, p.K, p.ldb, TC_BN, false));
   else CUR_TRY(make_map(&B.mapB[i], p.B, p.K, p.N, p.ldb, TC_BK, true));
+  if (q.nkb2 > 0) {                                   // plain NN second segment: A2 [M][K2], B2 [K2][N]
+    CUR_TRY(make_map(&B.mapA2[i], p.A2, p.M, p.K2, p.lda2, TC_BM, false));
+    CUR_TRY(make_map(&B.mapB2[i], p.B2, p.K2, p.N, p.ldb2, TC_BK, true));
+  }
   G.n = i + 1;
   return CUR_OK;
 }
 
-int TcLauncher::add_colsum(const float* B, int64_t ldb, int64_t rows, int N, float* out, float* partial) {
-  CUR_REQUIRE(n_colsum < TC_MAX_PROBS && R.n < 2 * TC_MAX_PROBS, "too many column sums");
-  CUR_REQUIRE((N % 4) == 0 && partial != nullptr, "bad column-sum problem");
-  ColSum& c = colsum[n_colsum++];
-  c.B = B; c.ldb = ldb; c.rows = rows; c.N = N; c.part = partial;
+int TcLauncher::add_rowred(const float* X, int64_t ldx, int M, const float* Y, int64_t ldy, int NJ, int64_t rows, float* out,
+                           float* partial) {
+  CUR_REQUIRE(n_rowred < TC_MAX_PROBS && R.n < 2 * TC_MAX_PROBS, "too many row reductions");
+  CUR_REQUIRE(X && M > 0 && rows > 0 && partial != nullptr && (Y == nullptr || (NJ >= 1 && NJ <= 4)), "bad row reduction");
+  RowRedDesc& c = rowred[n_rowred++];
+  c.X = X; c.ldx = ldx; c.Y = Y; c.ldy = ldy; c.rows = rows; c.M = M; c.NJ = Y ? NJ : 1; c.part = partial;
   c.chunks = (int)((rows + TC_COLSUM_ROWS - 1) / TC_COLSUM_ROWS);
+  const int64_t count = (int64_t)M * c.NJ;
   TcReduce& r = R.p[R.n++];
-  r.part = partial; r.out = out; r.count = N; r.stride = N; r.splits = c.chunks;
+  r.part = partial; r.out = out; r.count = count; r.stride = count; r.splits = c.chunks;
+  r.vec = ((count % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0) ? 1 : 0;
   return CUR_OK;
+}
+
+int64_t tc_rowred_partial_floats(int64_t rows, int M, int NJ) {
+  return ((rows + TC_COLSUM_ROWS - 1) / TC_COLSUM_ROWS) * (int64_t)M * (NJ < 1 ? 1 : NJ);
 }
 
 int TcLauncher::flush(cudaStream_t s) {
@@ -458,10 +555,12 @@ int TcLauncher::flush(cudaStream_t s) {
     tc_gemm_kernel<<<G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s>>>(B);
     CUR_CHECK_LAUNCH();
   }
-  for (int i = 0; i < n_colsum; ++i) {
-    const ColSum& c = colsum[i];
-    dim3 grid((c.N + 255) / 256, c.chunks);
-    tc_colsum_kernel<<<grid, 256, 0, s>>>(c.B, c.ldb, c.rows, c.N, TC_COLSUM_ROWS, c.part);
+  for (int i = 0; i < n_rowred; ++i) {
+    const RowRedDesc& c = rowred[i];
+    RowRed P;
+    P.X = c.X; P.ldx = c.ldx; P.Y = c.Y; P.ldy = c.ldy; P.rows = c.rows; P.M = c.M; P.NJ = c.NJ; P.part = c.part;
+    dim3 grid((c.M + 63) / 64, c.chunks);
+    tc_rowred_kernel<<<grid, 256, 0, s>>>(P);
     CUR_CHECK_LAUNCH();
   }
   if (R.n > 0) {
@@ -469,16 +568,16 @@ int TcLauncher::flush(cudaStream_t s) {
     int blocks = 0;
     for (int i = 0; i < R.n; ++i) {
       R.p[i].block_begin = blocks;
-      blocks += (int)((R.p[i].count / 4 + 255) / 256);
+      blocks += (int)(((R.p[i].count + 3) / 4 + 255) / 256);
     }
     tc_reduce_kernel<<<blocks, 256, 0, s>>>(R);
     CUR_CHECK_LAUNCH();
   }
-  G.n = 0; G.total_tiles = 0; R.n = 0; n_colsum = 0;
+  G.n = 0; G.total_tiles = 0; R.n = 0; n_rowred = 0;
   return CUR_OK;
 }
 
-TcLauncher::TcLauncher() : n_colsum(0) {
+TcLauncher::TcLauncher() : n_rowred(0) {
   static_assert(sizeof(TcBatch) <= sizeof(storage), "TcLauncher storage too small");
   G.n = 0; G.total_tiles = 0; R.n = 0;
 }
@@ -488,12 +587,12 @@ TcLauncher::TcLauncher() : n_colsum(0) {
 using namespace cur;
 
 extern "C" int cur_tc_gemm_supported(int64_t M, int64_t N, int64_t K) {
-  return (N == TC_BN && M > 0 && (M % TC_BM) == 0 && K > 0 && (K % TC_BK) == 0) ? 1 : 0;
+  return (N == TC_BN && M > 0 && K > 0 && M < (1 << 30) && K < (1 << 30)) ? 1 : 0;
 }
 
-extern "C" int64_t cur_tc_gemm_workspace_floats(int64_t M, int64_t N, int64_t K) {
+extern "C" int64_t cur_tc_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int a_trans) {
   GemmProb p = zero_prob();
-  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.a_trans = a_trans;
   return tc_partial_floats(p);
 }
 
@@ -501,7 +600,7 @@ extern "C" int cur_tc_gemm(void* stream, const float* A, int64_t lda, int a_tran
                            float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* aux,
                            int64_t ldaux, int epilogue, float* workspace) {
   CUR_REQUIRE(A && B && C, "NULL argument");
-  CUR_REQUIRE(cur_tc_gemm_supported(M, N, K), "shape: N must be 256, M a multiple of 128, K a multiple of 32");
+  CUR_REQUIRE(cur_tc_gemm_supported(M, N, K), "shape: N must be 256");
   GemmProb p = zero_prob();
   p.A = A; p.lda = (int)lda; p.a_trans = a_trans; p.B = B; p.ldb = (int)ldb; p.b_trans = b_trans;
   p.C = C; p.ldc = (int)ldc; p.M = (int)M; p.N = (int)N; p.K = (int)K;

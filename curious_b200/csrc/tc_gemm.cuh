@@ -5,12 +5,12 @@
 namespace cur {
 
 constexpr int TC_MAX_PROBS = 16;
-constexpr int TC_COLSUM_ROWS = 512;      // rows per partial column sum
+constexpr int TC_COLSUM_ROWS = 256;      // rows per partial row reduction
 
 struct TcReduce {
   const float* part; float* out;
   int64_t count, stride;                 // floats per slice (multiple of 4), distance between slices
-  int splits, block_begin;
+  int splits, block_begin, vec;
 };
 struct TcReduceBatch {
   TcReduce p[2 * TC_MAX_PROBS];
@@ -20,19 +20,23 @@ struct TcReduceBatch {
 bool tc_supported(const GemmProb& p);     // shape / alignment fit the tcgen05 kernel
 int tc_pick_splits(const GemmProb& p);
 int64_t tc_partial_floats(const GemmProb& p);   // floats of split-K workspace the problem needs (0: none)
+int64_t tc_rowred_partial_floats(int64_t rows, int M, int NJ);
 
 struct TcLauncher {
   struct { int n, total_tiles; } G;
   TcReduceBatch R;
-  struct ColSum { const float* B; int64_t ldb, rows; int N, chunks; float* part; } colsum[TC_MAX_PROBS];
-  int n_colsum;
-  alignas(64) unsigned char storage[TC_MAX_PROBS * (2 * 128 + 128) + 64];   // TcBatch (tensor maps + problems)
+  struct RowRedDesc { const float* X; int64_t ldx; const float* Y; int64_t ldy; int64_t rows; int M, NJ, chunks; float* part; }
+      rowred[TC_MAX_PROBS];
+  int n_rowred;
+  alignas(64) unsigned char storage[TC_MAX_PROBS * (4 * 128 + 128) + 64];   // TcBatch (tensor maps + problems)
   TcLauncher();
   int add(const GemmProb& p, float* partial);
-  // out[n] = sum over rows of B[rows][N] (bias gradient); partial: ceil(rows / TC_COLSUM_ROWS) * N floats
-  int add_colsum(const float* B, int64_t ldb, int64_t rows, int N, float* out, float* partial);
+  // out[m][j] = sum_r X[r][m] * Y[r][j] (j < NJ <= 4), or the column sums of X when Y == NULL;
+  // partial: tc_rowred_partial_floats(rows, M, NJ) floats
+  int add_rowred(const float* X, int64_t ldx, int M, const float* Y, int64_t ldy, int NJ, int64_t rows, float* out,
+                 float* partial);
   int flush(cudaStream_t s);
-  bool empty() const { return G.n == 0 && R.n == 0 && n_colsum == 0; }
+  bool empty() const { return G.n == 0 && R.n == 0 && n_rowred == 0; }
 };
 
 }  // namespace cur

@@ -349,12 +349,17 @@ int cur_p2p_allreduce_adam(void* stream, const cur_p2p_ctx* ctx, float* theta, f
  *   C[M,N] = epi( opA(A)[M,K] * opB(B)[K,N] + bias[N] )
  *   a_trans: A is stored [K][M] (lda >= M);  b_trans: B is stored [N][K] (ldb >= K)
  *   epilogue: 0 none, 1 ReLU, 2 gate by aux[M][N] > 0 (ReLU backward)
- * Shape: N == 256, M % 128 == 0, K % 32 == 0; 16-byte aligned pointers, leading dimensions % 4.
- * M < 1024 splits K over CTAs (weight gradients, K = batch): `workspace` must then hold
- * cur_tc_gemm_workspace_floats(M, N, K) floats and bias / epilogue must be unset.
+ * Shape: N == 256, any M and K (tiles of 128 x 256 x 32; tails are zero-filled by the TMA unit);
+ * 16-byte aligned pointers, leading dimensions % 4.  a_trans with M < 1024 splits K over CTAs (weight
+ * gradients, K = batch): `workspace` must then hold cur_tc_gemm_workspace_floats(M, N, K, a_trans)
+ * floats, C must be contiguous (ldc == N) and bias / epilogue must be unset.
  * ------------------------------------------------------------------------------------------ */
 int cur_tc_gemm_supported(int64_t M, int64_t N, int64_t K);
-int64_t cur_tc_gemm_workspace_floats(int64_t M, int64_t N, int64_t K);
+/* cur_ddpg_grads runs its hidden-layer GEMMs on the tensor cores when batch >= 1024, batch % 128 == 0 and
+ * hidden == 256.  mode: -1 default (on unless the environment says CUR_DDPG_TC=0), 0 FFMA only, 1 on. */
+int cur_ddpg_set_tensor_cores(int mode);
+int cur_ddpg_uses_tensor_cores(const cur_net_desc* d, int64_t batch);
+int64_t cur_tc_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int a_trans);
 int cur_tc_gemm(void* stream, const float* A, int64_t lda, int a_trans, const float* B, int64_t ldb,
                 int b_trans, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
                 const float* aux, int64_t ldaux, int epilogue, float* workspace);

@@ -305,3 +305,61 @@ def test_cuda_graph_path_equals_eager_path(task_replay, schedule):
     g.update_target_net()
     e.update_target_net()
     assert np.array_equal(g.get_flat('Q', True), e.get_flat('Q', True))
+
+
+@pytest.mark.parametrize('batch_size', [1024, 4096])
+def test_large_batch_tensor_core_update_against_oracle(batch_size):
+    """BASELINE config 5 batch sweep: at batch >= 1024 the hidden-layer GEMMs of cur_ddpg_grads run on tcgen05
+    (3xTF32, csrc/tc_gemm.cu).  Same tolerances as the batch-256 path versus the oracle, and the tensor-core
+    gradients must agree with the FFMA path of the same library on the same batch."""
+    import ctypes as C
+    from curious_b200 import _lib
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, batch_size=batch_size)
+    cp = np.linspace(0.0, 0.3, 4)
+    episodes = episode_stream(dims, kw['T'], 12)
+    ora = make_oracle_agent(kw, dims, ag_ids, g_ids)
+    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy', update_schedule='levels')
+    np.random.seed(7)
+    _fill(ora, episodes, cp)
+    np.random.seed(7)
+    _fill(gpu, episodes, cp)
+    lib = _lib.load()
+    try:
+        for step in range(2):
+            np.random.seed(300 + step)
+            ob = ora.sample_batch()
+            np.random.seed(300 + step)
+            gb = gpu.sample_batch()
+            for key, x, y in zip(ora.stage_keys, gb, ob):
+                assert np.array_equal(x, np.asarray(y, np.float64)), key
+            ref = ora.grads(ob)
+            got = {}
+            for mode in (1, 0):
+                _lib.check(lib.cur_ddpg_set_tensor_cores(mode), 'cur_ddpg_set_tensor_cores')
+                assert lib.cur_ddpg_uses_tensor_cores(C.byref(gpu.net.desc), batch_size) == mode
+                gpu.stage_batch(gb)
+                ql, qpi, gq, gp = gpu._grads()
+                got[mode] = (float(ql), float(gpu._pi_loss), qpi.cpu().numpy().copy(), gq.cpu().numpy().copy(),
+                             gp.cpu().numpy().copy())
+            for mode in (1, 0):
+                ql, pl, qpi, gq, gp = got[mode]
+                assert abs(ql - ref['Q_loss']) <= LOSS_RTOL * abs(ref['Q_loss']) + 1e-7, mode
+                assert abs(pl - ref['pi_loss']) <= LOSS_RTOL * abs(ref['pi_loss']) + 1e-7, mode
+                assert rel_err(qpi, ref['Q_pi']) <= 1e-5, mode
+                tol = GRAD_RTOL if ref['relu_margin'] > 2e-6 else 2e-3        # see the module docstring
+                assert rel_err(gq, ref['Q_grad']) <= tol, (mode, ref['relu_margin'])
+                assert rel_err(gp, ref['pi_grad']) <= tol, (mode, ref['relu_margin'])
+            assert rel_err(got[1][3], got[0][3]) <= tol
+            assert rel_err(got[1][4], got[0][4]) <= tol
+            # step both sides with the ORACLE's gradient (Adam's m / sqrt(v) turns last-bit gradient noise into
+            # +-lr parameter differences on the first steps, see the module docstring): bit exact
+            import torch
+            gpu.grads.zero_()
+            gpu._view(gpu.grads, 'Q').copy_(torch.from_numpy(ref['Q_grad']).cuda())
+            gpu._view(gpu.grads, 'pi').copy_(torch.from_numpy(ref['pi_grad']).cuda())
+            gpu._update(gpu._view(gpu.grads, 'Q'), gpu._view(gpu.grads, 'pi'))
+            ora.train(ob)
+            assert np.array_equal(gpu.get_flat('Q'), ora.Q_adam.theta)
+            assert np.array_equal(gpu.get_flat('pi'), ora.pi_adam.theta)
+    finally:
+        lib.cur_ddpg_set_tensor_cores(-1)

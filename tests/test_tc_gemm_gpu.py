@@ -25,7 +25,7 @@ def _run(A, B, a_trans, b_trans, bias=None, aux=None, epi=0):
     dbias = torch.from_numpy(bias).to(dev) if bias is not None else None
     daux = torch.from_numpy(aux).to(dev) if aux is not None else None
     assert lib.cur_tc_gemm_supported(M, N, K) == 1
-    wsf = lib.cur_tc_gemm_workspace_floats(M, N, K)
+    wsf = lib.cur_tc_gemm_workspace_floats(M, N, K, int(a_trans))
     ws = torch.empty(max(int(wsf), 4), dtype=torch.float32, device=dev)
     _lib.check(lib.cur_tc_gemm(_lib.stream_ptr(), dA.data_ptr(), A.shape[1], int(a_trans), dB.data_ptr(), B.shape[1],
                                int(b_trans), dC.data_ptr(), N, M, N, K, dbias.data_ptr() if dbias is not None else None,
@@ -100,3 +100,22 @@ def test_k_tail_and_column_order():
     got = _run(A, B, 0, 0)
     ref, mag = _ref(A, B, 0, 0)
     _check(got, ref, mag)
+
+
+def test_first_layer_shapes_ride_on_tma_zero_fill():
+    """K = 44 (first layer of main.pi: dimo + N) and M = 48 / 12 (first-layer weight gradients): the tails of the
+    128 x 256 x 32 tiles are out-of-bounds boxes that the TMA unit zero-fills."""
+    rng = np.random.RandomState(5)
+    X = rng.randn(1024, 44).astype(np.float32)
+    W = (rng.uniform(-1, 1, (44, 256)) * 0.14).astype(np.float32)
+    b = rng.randn(256).astype(np.float32) * 0.1
+    got = _run(X, W, 0, 0, bias=b, epi=1)
+    ref, mag = _ref(X, W, 0, 0, bias=b, epi=1)
+    _check(got, ref, mag, epi=1)
+    for m in (48, 12):
+        Xs = rng.randn(2048, m).astype(np.float32)
+        dY = rng.randn(2048, 256).astype(np.float32) * 1e-3
+        got = _run(Xs, dY, 1, 0)                       # dW0 = Xs^T dY, M = 48 / 12 rows of a 128-row tile
+        ref, mag = _ref(Xs, dY, 1, 0)
+        assert got.shape == (m, 256)
+        _check(got, ref, mag)
