@@ -138,6 +138,7 @@ SIGNATURES = {
                                      C.POINTER(HerArgs)]),
     'cur_ddpg_set_tensor_cores': (C.c_int, [C.c_int]),
     'cur_ddpg_uses_tensor_cores': (C.c_int, [C.POINTER(NetDesc), C.c_int64]),
+    'cur_tc_gemm_timeline': (C.c_int, [C.c_void_p]),
     'cur_tc_gemm_supported': (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     'cur_tc_gemm_workspace_floats': (C.c_int64, [C.c_int64, C.c_int64, C.c_int64, C.c_int]),
     'cur_tc_gemm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,

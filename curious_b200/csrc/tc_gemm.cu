@@ -15,11 +15,11 @@
 //   warp 0      TMA producer: raw fp32 operand tiles, cp.async.bulk.tensor.2d with 128-byte swizzle, 2-stage ring,
 //               mbarrier complete_tx; out-of-bounds rows / columns are zero-filled by the TMA unit, which is how
 //               K = 44..60 first layers and M = 12..48 first-layer weight gradients ride the same 128 x 256 x 32 tiles
-//   warps 2-9   splitters: rewrite the landed tile in place as `hi` and write `lo` next to it (element-wise integer /
+//   warps 2-5   splitters: rewrite the landed tile in place as `hi` and write `lo` next to it (element-wise integer /
 //               FADD work, so the swizzled image is preserved), fence.proxy.async, arrive on the "split" barrier
 //   warp 1      MMA issuer: one lane issues 4 k-steps x 3 tcgen05.mma (M=128, N=256, K=8) per stage from shared-memory
 //               descriptors, tcgen05.commit frees the stage / publishes the accumulators; owns the TMEM allocation
-//   warps 10-13 epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction), transposed through a padded
+//   warps 6-13  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction), transposed through a padded
 //               shared-memory slab so that bias / ReLU / ReLU-mask and the stores are 128-byte coalesced
 // Operands are read in their NATIVE row-major orientation; whether an operand is K-major or MN-major for the MMA is
 // expressed in the shared-memory / instruction descriptors only:
@@ -44,13 +44,14 @@ constexpr int TC_STAGES = 2;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 96 KB
-constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_SPLIT_WARPS = 4;                              // the split is shared-memory-bandwidth-bound: 4 warps saturate it
 constexpr int TC_SPLIT_WARP0 = 2, TC_EPI_WARP0 = TC_SPLIT_WARP0 + TC_SPLIT_WARPS;
-constexpr int TC_THREADS = (TC_EPI_WARP0 + 4) * 32;           // 448
+constexpr int TC_EPI_WARPS = 8;                                // two per TMEM lane quarter, 4 column chunks each
+constexpr int TC_THREADS = (TC_EPI_WARP0 + TC_EPI_WARPS) * 32;   // 576
 constexpr int TC_EPI_LD = 36;                                  // padded row of the epilogue slab (floats)
-constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_LD * 4;          // one 32 x 32 slab per epilogue warp
-constexpr size_t TC_SMEM_BYTES =
-    (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + TC_EPI_BYTES;
+constexpr int TC_EPI_BYTES = TC_EPI_WARPS * 32 * TC_EPI_LD * 4;   // one 32 x 32 slab per epilogue warp
+static_assert(TC_EPI_BYTES <= TC_STAGE_BYTES, "the epilogue slabs reuse stage 0 once the accumulators are complete");
+constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int TC_TMEM_COLS = 512;                              // accumulator 0: columns 0..255, accumulator 1: 256..511
 
 struct TcProb {
@@ -70,6 +71,7 @@ struct __align__(64) TcBatch {
   CUtensorMap mapB2[TC_MAX_PROBS];
   TcProb p[TC_MAX_PROBS];
   int n, total_tiles;
+  long long* tl;                     // debug timeline of CTA 0 (cur_tc_gemm_timeline), normally NULL
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -131,8 +133,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tc_rna_tf32(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -168,10 +170,74 @@ __device__ __forceinline__ void tc_split_tile(float* hi, int lo_off_floats, int 
   }
 }
 
+// Epilogue of one warp: 4 column chunks of 32 for its 32 accumulator rows.  Per chunk: both accumulators TMEM ->
+// registers (lane = row), summed, transposed through the warp's padded shared-memory slab so that 8 lanes cover one
+// 128-byte row segment, then bias / ReLU / ReLU-mask and 16-byte coalesced stores.  Bias and the mask of the first
+// chunk are fetched before the accumulators are waited for; the next chunk's mask streams in behind the stores.
+template <int EPI, bool FULL>
+__device__ __forceinline__ void tc_epilogue(const TcProb& P, uint32_t taddr, float* slab, float* cbase, int row0, int c_begin,
+                                            int lane, uint32_t accb, long long* tl) {
+  const int rr = lane >> 3, ch = lane & 7;            // phase 2: this lane owns rows rr + 4 i, columns 4 ch .. 4 ch + 3
+  const int M = P.M;
+  const int64_t ldc = P.ldc, ldaux = P.ldaux;
+  const float* aux = P.aux + (int64_t)(row0 + rr) * ldaux + 4 * ch;
+  float* crow = cbase + (int64_t)(row0 + rr) * ldc + 4 * ch;
+  float4 bias4[4];
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc)
+    bias4[cc] = P.bias ? *reinterpret_cast<const float4*>(P.bias + (c_begin + cc) * 32 + 4 * ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 mk[8];
+  if (EPI == EPI_RELU_MASK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (FULL || row0 + rr + 4 * i < M) mk[i] = *reinterpret_cast<const float4*>(aux + (int64_t)(4 * i) * ldaux + c_begin * 32);
+  }
+  tc_bar_wait(accb, 0);
+  tc_fence_after();
+  if (tl) tl[88] = clock64();
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    const int c = c_begin + cc;
+    uint32_t r0[32], r1[32];
+    tc_ld32(taddr + (uint32_t)(c * 32), r0);
+    tc_ld32(taddr + (uint32_t)(TC_BN + c * 32), r1);
+    tc_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 v;
+      v.x = __uint_as_float(r0[4 * j]) + __uint_as_float(r1[4 * j]);
+      v.y = __uint_as_float(r0[4 * j + 1]) + __uint_as_float(r1[4 * j + 1]);
+      v.z = __uint_as_float(r0[4 * j + 2]) + __uint_as_float(r1[4 * j + 2]);
+      v.w = __uint_as_float(r0[4 * j + 3]) + __uint_as_float(r1[4 * j + 3]);
+      *reinterpret_cast<float4*>(slab + lane * TC_EPI_LD + 4 * j) = v;      // conflict-free: row pitch 36 floats
+    }
+    __syncwarp();
+    const float4 b = cc == 0 ? bias4[0] : cc == 1 ? bias4[1] : cc == 2 ? bias4[2] : bias4[3];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 v = *reinterpret_cast<const float4*>(slab + (rr + 4 * i) * TC_EPI_LD + 4 * ch);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      if (EPI == EPI_RELU) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      } else if (EPI == EPI_RELU_MASK) {
+        const float4 a = mk[i];
+        v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
+        // the next chunk's mask streams in behind this chunk's stores
+        if (cc + 1 < 4 && (FULL || row0 + rr + 4 * i < M))
+          mk[i] = *reinterpret_cast<const float4*>(aux + (int64_t)(4 * i) * ldaux + (c + 1) * 32);
+      }
+      if (FULL || row0 + rr + 4 * i < M) *reinterpret_cast<float4*>(crow + (int64_t)(4 * i) * ldc + c * 32) = v;
+    }
+    __syncwarp();
+    if (tl) tl[89 + cc] = clock64();
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcBatch G) {
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (G.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) G.tl[0] = clock64();
 
   // ---- which tile
   int pi = 0;
@@ -207,6 +273,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  long long* tl = (G.tl != nullptr && blockIdx.x == 0 && lane == 0) ? G.tl : nullptr;
+  if (tl && warp == 0) tl[1] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer
@@ -220,6 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         const CUtensorMap* mA = seg2 ? &G.mapA2[pi] : &G.mapA[pi];
         const CUtensorMap* mB = seg2 ? &G.mapB2[pi] : &G.mapB[pi];
         const int k0 = seg2 ? (kb - P.nkb1) * TC_BK : k_begin + kb * TC_BK;
+        if (tl && kb < 16) tl[8 + kb] = clock64();
         tc_bar_expect_tx(full + 8 * s, TC_A_BYTES + TC_B_BYTES);      // zero-filled out-of-bounds bytes count too
         if (!P.a_mn) {
           tc_tma_2d(a_hi, mA, k0, m0, full + 8 * s);                           // [128 m][32 k]
@@ -249,6 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int s = kb % TC_STAGES, round = kb / TC_STAGES;
       tc_bar_wait(splitb + 8 * s, round & 1);
       tc_fence_after();
+      if (tl && kb < 16) tl[56 + 2 * kb] = clock64();
       if (lane == 0) {
         const uint32_t st = base + s * TC_STAGE_BYTES;
         const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
@@ -262,6 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         }
         tc_commit(empty + 8 * s);                 // stage reusable once these MMAs have read it
         if (kb == nkb - 1) tc_commit(accb);       // accumulators complete
+        if (tl && kb < 16) tl[57 + 2 * kb] = clock64();
       }
       __syncwarp();
     }
@@ -271,63 +342,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % TC_STAGES, round = kb / TC_STAGES;
       tc_bar_wait(full + 8 * s, round & 1);
+      if (tl && warp == TC_SPLIT_WARP0 && kb < 16) tl[24 + 2 * kb] = clock64();
       float* st = reinterpret_cast<float*>(gen_base + s * TC_STAGE_BYTES);
       tc_split_tile(st, TC_A_BYTES / 4, TC_A_BYTES / 16, t, TC_SPLIT_WARPS * 32);
       tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, TC_B_BYTES / 16, t, TC_SPLIT_WARPS * 32);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
+      if (tl && warp == TC_SPLIT_WARP0 && kb < 16) tl[25 + 2 * kb] = clock64();
       if (lane == 0) tc_bar_arrive(splitb + 8 * s);
     }
   } else {
-    // ===== epilogue (4 warps; warp w may only touch TMEM lanes 32 (w % 4) .. + 31)
-    const int q = warp & 3;
-    float* slab = reinterpret_cast<float*>(gen_base + TC_STAGES * TC_STAGE_BYTES + 256) + q * 32 * TC_EPI_LD;
+    // ===== epilogue (8 warps; warp w may only touch TMEM lanes 32 (w % 4) .. + 31; the two warps of a lane quarter
+    // take 4 of the 8 column chunks each)
+    const int q = warp & 3, ew = warp - TC_EPI_WARP0;
     const int row0 = m0 + 32 * q;
-    tc_bar_wait(accb, 0);
-    tc_fence_after();
+    float* slab = reinterpret_cast<float*>(gen_base) + ew * 32 * TC_EPI_LD;   // stage 0 is free once `accb` fires
     float* cbase = P.C + (int64_t)split * P.split_stride;
-    const int rr = lane >> 3, ch = lane & 7;          // phase 2: this lane owns rows rr + 4 i, columns 4 ch .. 4 ch + 3
-#pragma unroll 1
-    for (int c = 0; c < TC_BN / 32; ++c) {
-      uint32_t r0[32], r1[32];
-      tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32), r0);
-      tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(TC_BN + c * 32), r1);
-      // phase 1: lane = row of the slab, 32 columns -> 8 conflict-free 16-byte stores (row pitch 36 floats)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 v;
-        v.x = __uint_as_float(r0[4 * j]) + __uint_as_float(r1[4 * j]);
-        v.y = __uint_as_float(r0[4 * j + 1]) + __uint_as_float(r1[4 * j + 1]);
-        v.z = __uint_as_float(r0[4 * j + 2]) + __uint_as_float(r1[4 * j + 2]);
-        v.w = __uint_as_float(r0[4 * j + 3]) + __uint_as_float(r1[4 * j + 3]);
-        *reinterpret_cast<float4*>(slab + lane * TC_EPI_LD + 4 * j) = v;
-      }
-      __syncwarp();
-      // phase 2: 8 lanes cover one 128-byte row segment -> coalesced bias / mask loads and stores
-      const int col = c * 32 + 4 * ch;
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (P.bias) b = *reinterpret_cast<const float4*>(P.bias + col);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rr + 4 * i;
-        const int row = row0 + r;
-        float4 v = *reinterpret_cast<const float4*>(slab + r * TC_EPI_LD + 4 * ch);
-        if (row < P.M) {
-          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          if (P.epi == EPI_RELU) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-          } else if (P.epi == EPI_RELU_MASK) {
-            const float4 a = *reinterpret_cast<const float4*>(P.aux + (int64_t)row * P.ldaux + col);
-            v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
-          }
-          *reinterpret_cast<float4*>(cbase + (int64_t)row * P.ldc + col) = v;
-        }
-      }
-      __syncwarp();
+    const bool full_rows = row0 + 32 <= P.M;
+    const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
+    const int c_begin = (ew >> 2) * 4;
+    long long* etl = (tl && warp == TC_EPI_WARP0) ? tl : nullptr;
+    // the epilogue kind and the row-tail handling are resolved once, outside the chunk loop
+    if (P.epi == EPI_RELU_MASK) {
+      if (full_rows) tc_epilogue<EPI_RELU_MASK, true>(P, taddr, slab, cbase, row0, c_begin, lane, accb, etl);
+      else tc_epilogue<EPI_RELU_MASK, false>(P, taddr, slab, cbase, row0, c_begin, lane, accb, etl);
+    } else if (P.epi == EPI_RELU) {
+      if (full_rows) tc_epilogue<EPI_RELU, true>(P, taddr, slab, cbase, row0, c_begin, lane, accb, etl);
+      else tc_epilogue<EPI_RELU, false>(P, taddr, slab, cbase, row0, c_begin, lane, accb, etl);
+    } else {
+      if (full_rows) tc_epilogue<EPI_NONE, true>(P, taddr, slab, cbase, row0, c_begin, lane, accb, etl);
+      else tc_epilogue<EPI_NONE, false>(P, taddr, slab, cbase, row0, c_begin, lane, accb, etl);
     }
     tc_fence_before();
   }
   __syncthreads();
+  if (tl && warp == 0) tl[2] = clock64();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
@@ -456,6 +505,9 @@ static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols
   return CUR_OK;
 }
 
+static long long* g_tc_timeline = nullptr;
+void tc_set_timeline(long long* dev) { g_tc_timeline = dev; }
+
 bool tc_supported(const GemmProb& p) {
   if (p.ones_a || p.C2 != nullptr) return false;
   if (p.N != TC_BN || p.M <= 0 || p.K <= 0) return false;
@@ -551,7 +603,7 @@ int TcLauncher::flush(cudaStream_t s) {
     configured = true;
   }
   if (G.n > 0) {
-    B.n = G.n; B.total_tiles = G.total_tiles;
+    B.n = G.n; B.total_tiles = G.total_tiles; B.tl = g_tc_timeline;
     tc_gemm_kernel<<<G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s>>>(B);
     CUR_CHECK_LAUNCH();
   }
@@ -585,6 +637,11 @@ TcLauncher::TcLauncher() : n_rowred(0) {
 }  // namespace cur
 
 using namespace cur;
+
+extern "C" int cur_tc_gemm_timeline(long long* device_buffer_128) {
+  tc_set_timeline(device_buffer_128);
+  return CUR_OK;
+}
 
 extern "C" int cur_tc_gemm_supported(int64_t M, int64_t N, int64_t K) {
   return (N == TC_BN && M > 0 && K > 0 && M < (1 << 30) && K < (1 << 30)) ? 1 : 0;
