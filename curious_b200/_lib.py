@@ -84,6 +84,12 @@ class DdpgHyper(C.Structure):
                 ('_pad', C.c_int32), ('grads_parity_stride', C.c_int64)]
 
 
+class DdpgExpert(C.Structure):
+    _fields_ = [('theta_main', C.c_void_p), ('theta_target', C.c_void_p), ('stats', NormStats), ('has_stats', C.c_int32),
+                ('_pad', C.c_int32), ('batch', Batch), ('hyper', DdpgHyper), ('workspace', C.c_void_p),
+                ('grads', C.c_void_p), ('q_loss', C.c_void_p), ('pi_loss', C.c_void_p), ('q_pi', C.c_void_p)]
+
+
 class AdamFused(C.Structure):
     _fields_ = [('m', C.c_void_p), ('v', C.c_void_p), ('neg_a_table', C.c_void_p), ('table_len', C.c_int32),
                 ('_pad', C.c_int32), ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double)]
@@ -136,6 +142,7 @@ SIGNATURES = {
                                      C.POINTER(NormStats), C.POINTER(Batch), C.POINTER(DdpgHyper), C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AdamFused),
                                      C.POINTER(HerArgs)]),
+    'cur_ddpg_grads_group': (C.c_int, [C.c_void_p, C.POINTER(NetDesc), C.c_int, C.POINTER(DdpgExpert)]),
     'cur_ddpg_set_tensor_cores': (C.c_int, [C.c_int]),
     'cur_ddpg_uses_tensor_cores': (C.c_int, [C.POINTER(NetDesc), C.c_int64]),
     'cur_tc_gemm_timeline': (C.c_int, [C.c_void_p]),

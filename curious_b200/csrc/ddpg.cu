@@ -397,120 +397,233 @@ extern "C" int cur_ddpg_actions(void* stream, const cur_net_desc* d, const float
   return CUR_OK;
 }
 
-extern "C" int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* theta_main,
-                              const float* theta_target, const cur_norm_stats* stats, const cur_batch* batch,
-                              const cur_ddpg_hyper* h, float* workspace, float* grads, float* q_loss,
-                              float* pi_loss, float* q_pi) {
-  CUR_TRY(check_desc(d));
+// One expert (= one DDPG agent) of a grouped update: its parameters, staged batch, outputs and workspace.
+struct Expert {
+  Workspace w;
+  const float *mQ, *mP, *tQ, *tP;
+  float *gQ, *gP;
+  const cur_batch* batch;
+  const cur_norm_stats* stats;
+  const cur_ddpg_hyper* h;
+  float *q_loss, *pi_loss, *q_pi;
+  float* th;                           // tanh output = action columns of main.Q's input
+  int parts_used, rowparts_used;       // split-K / row-reduction workspace slots taken in the current level
+};
+
+// Level batcher over several experts: every add() names the expert whose workspace slots the problem may use.
+struct GroupBatcher {
+  Batcher B;
+  Expert* e;
+  int n_e;
+  GroupBatcher(cudaStream_t s, bool tc, Expert* experts, int n) : B(s), e(experts), n_e(n) {
+    B.tc = tc && experts[0].w.tc_part != nullptr;
+  }
+  int add(int i, const GemmProb& p) {
+    // flush early when a launch is full (many experts): problems of one level are independent, so splitting a level
+    // over several launches is always legal
+    if (B.G.n >= GEMM_MAX_PROBS - 1 || B.T.G.n >= TC_MAX_PROBS - 1 || B.T.R.n >= 2 * TC_MAX_PROBS - 2 ||
+        B.T.n_rowred >= TC_MAX_PROBS - 1)
+      CUR_TRY(flush());
+    Expert& x = e[i];
+    B.tc_part = x.w.tc_part; B.tc_rowpart = x.w.tc_rowpart;
+    B.part_stride = x.w.tc_part_stride; B.rowpart_stride = x.w.tc_rowpart_stride;
+    B.parts_used = x.parts_used; B.rowparts_used = x.rowparts_used;
+    B.add(p);
+    x.parts_used = B.parts_used; x.rowparts_used = B.rowparts_used;
+    return B.rc;
+  }
+  int flush() {
+    CUR_TRY(B.flush());
+    for (int i = 0; i < n_e; ++i) e[i].parts_used = e[i].rowparts_used = 0;
+    return CUR_OK;
+  }
+};
+
+// DDPG._grads for n_e experts of identical shape: every dependency level is ONE launch (per kernel kind) over all
+// experts - the grouped-GEMM form of structure='task_experts' (train.py:287-289 builds one DDPG per module).
+static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_e, int64_t n) {
+  const NetLayout LQ = net_layout(*d, 0), LP = net_layout(*d, 1);
+  const int L = d->layers, H = d->hidden;
+  // ---- inputs
+  for (int i = 0; i < n_e; ++i) {
+    Expert& x = E[i];
+    PrepParams P;
+    memset(&P, 0, sizeof(P));
+    const cur_batch* b = x.batch;
+    P.d = *d; P.o = b->o; P.g = b->g; P.u = b->u; P.td = b->td; P.o_2 = b->o_2; P.g_2 = b->g_2;
+    P.n = n;
+    if (x.stats) { P.o_mean = x.stats->o_mean; P.o_std = x.stats->o_std; P.g_mean = x.stats->g_mean; P.g_std = x.stats->g_std; }
+    P.ld_spi = x.w.ld_spi; P.ld_sq = x.w.ld_sq; P.ld_g = x.w.ld_g;
+    P.Xpi = x.w.Xpi; P.Xg = x.w.Xg; P.XQu = x.w.XQu; P.XQpi = x.w.XQpi; P.Xpi_t = x.w.Xpi_t; P.Xg_t = x.w.Xg_t; P.XQ_t = x.w.XQ_t;
+    prep_kernel<<<grid_prep(n * LQ.in_s), 256, 0, s>>>(P);
+    CUR_CHECK_LAUNCH();
+    x.th = x.w.XQpi + LP.in_s;
+    x.parts_used = x.rowparts_used = 0;
+  }
+  GroupBatcher B(s, use_tc(*d, n), E, n_e);
+#define FOR_EXPERTS for (int i = 0; i < n_e; ++i)
+#define ADD(prob) CUR_TRY(B.add(i, (prob)))
+  // ---- fwd-1: main.pi | target.pi | main.Q(o,g,u)
+  FOR_EXPERTS {
+    Expert& x = E[i]; const Workspace& w = x.w;
+    ADD(fwd0(LP, x.mP, w.Xpi, w.ld_spi, w.Xg, w.ld_g, w.hp[0], n));
+    ADD(fwd0(LP, x.tP, w.Xpi_t, w.ld_spi, w.Xg_t, w.ld_g, w.ht[0], n));
+    ADD(fwd0(LQ, x.mQ, w.XQu, w.ld_sq, w.Xg, w.ld_g, w.hq[0], n));
+  }
+  CUR_TRY(B.flush());
+  for (int l = 1; l < L; ++l) {
+    FOR_EXPERTS {
+      Expert& x = E[i]; const Workspace& w = x.w;
+      ADD(fwdl(LP, x.mP, l, w.hp[l - 1], w.hp[l], n));
+      ADD(fwdl(LP, x.tP, l, w.ht[l - 1], w.ht[l], n));
+      ADD(fwdl(LQ, x.mQ, l, w.hq[l - 1], w.hq[l], n));
+    }
+    CUR_TRY(B.flush());
+  }
+  FOR_EXPERTS {
+    Expert& x = E[i]; const Workspace& w = x.w;
+    ADD(fwdout(LP, x.mP, w.hp[L - 1], x.th, w.ld_sq, EPI_TANH, n));
+    ADD(fwdout(LP, x.tP, w.ht[L - 1], w.XQ_t + LP.in_s, w.ld_sq, EPI_TANH, n));
+    ADD(fwdout(LQ, x.mQ, w.hq[L - 1], w.Q, 1, EPI_NONE, n));
+  }
+  CUR_TRY(B.flush());
+  // ---- fwd-2: main.Q(o,g,pi) | target.Q(o2,g2,pi_t)   (same u and td for the target, ddpg.py:427-431)
+  FOR_EXPERTS {
+    Expert& x = E[i]; const Workspace& w = x.w;
+    ADD(fwd0(LQ, x.mQ, w.XQpi, w.ld_sq, w.Xg, w.ld_g, w.hqp[0], n));
+    ADD(fwd0(LQ, x.tQ, w.XQ_t, w.ld_sq, w.Xg_t, w.ld_g, w.htq[0], n));
+  }
+  CUR_TRY(B.flush());
+  for (int l = 1; l < L; ++l) {
+    FOR_EXPERTS {
+      Expert& x = E[i]; const Workspace& w = x.w;
+      ADD(fwdl(LQ, x.mQ, l, w.hqp[l - 1], w.hqp[l], n));
+      ADD(fwdl(LQ, x.tQ, l, w.htq[l - 1], w.htq[l], n));
+    }
+    CUR_TRY(B.flush());
+  }
+  FOR_EXPERTS {
+    Expert& x = E[i]; const Workspace& w = x.w;
+    ADD(fwdout(LQ, x.mQ, w.hqp[L - 1], x.q_pi, 1, EPI_NONE, n));
+    ADD(fwdout(LQ, x.tQ, w.htq[L - 1], w.Qt, 1, EPI_NONE, n));
+  }
+  CUR_TRY(B.flush());
+
+  // ---- losses and backward seeds
+  FOR_EXPERTS {
+    Expert& x = E[i]; const Workspace& w = x.w;
+    LossParams LPm;
+    LPm.r = x.batch->r; LPm.Q = w.Q; LPm.Qpi = x.q_pi; LPm.Qt = w.Qt; LPm.th = x.th; LPm.ldth = w.ld_sq; LPm.dimu = d->dimu;
+    LPm.n = n; LPm.gamma = x.h->gamma; LPm.clip_return = x.h->clip_return; LPm.action_l2 = x.h->action_l2;
+    LPm.clip_pos = x.h->clip_pos_returns; LPm.dQ = w.dQ; LPm.dQpi = w.dQpi; LPm.q_loss = x.q_loss; LPm.pi_loss = x.pi_loss;
+    LPm.step_counter = x.h->step_counter; LPm.ring = x.h->loss_ring;
+    loss_kernel<<<1, 1024, 0, s>>>(LPm);
+    CUR_CHECK_LAUNCH();
+  }
+
+  // ---- bwd-1: critic chain (weights grads of main/Q) | actor-through-Q chain (data grads only)
+  int cur = 0;
+  FOR_EXPERTS {
+    Expert& x = E[i]; const Workspace& w = x.w;
+    ADD(bwd_dx(w.dQ, 1, x.mQ + LQ.off_Wout, H, 1, w.hq[L - 1], H, w.dc[0], H, n));
+    ADD(bwd_dw(w.hq[L - 1], H, H, w.dQ, 1, 1, x.gQ + LQ.off_Wout, n));
+    ADD(bwd_db(w.dQ, 1, 1, x.gQ + LQ.off_bout, n));
+    ADD(bwd_dx(w.dQpi, 1, x.mQ + LQ.off_Wout, H, 1, w.hqp[L - 1], H, w.da[0], H, n));
+  }
+  CUR_TRY(B.flush());
+  for (int l = L - 1; l >= 1; --l) {
+    FOR_EXPERTS {
+      Expert& x = E[i]; const Workspace& w = x.w;
+      ADD(bwd_dx(w.dc[cur], H, x.mQ + LQ.off_W[l], H, H, w.hq[l - 1], H, w.dc[cur ^ 1], H, n));
+      ADD(bwd_dw(w.hq[l - 1], H, H, w.dc[cur], H, H, x.gQ + LQ.off_W[l], n));
+      ADD(bwd_db(w.dc[cur], H, H, x.gQ + LQ.off_b[l], n));
+      ADD(bwd_dx(w.da[cur], H, x.mQ + LQ.off_W[l], H, H, w.hqp[l - 1], H, w.da[cur ^ 1], H, n));
+    }
+    CUR_TRY(B.flush());
+    cur ^= 1;
+  }
+  FOR_EXPERTS {
+    Expert& x = E[i]; const Workspace& w = x.w;
+    ADD(bwd_dw(w.XQu, w.ld_sq, LQ.in_s, w.dc[cur], H, H, x.gQ + LQ.off_W0, n));
+    ADD(bwd_db(w.dc[cur], H, H, x.gQ + LQ.off_b0, n));
+    if (LQ.in_g > 0) ADD(bwd_dw(w.Xg, w.ld_g, LQ.in_g, w.dc[cur], H, H, x.gQ + LQ.off_W0g, n));
+    // d pi_loss / d(pre-tanh) = (dL/d(pi/max_u) + action_l2 * 2/(B*dimu) * th) * (1 - th^2)
+    GemmProb p = bwd_dx(w.da[cur], H, x.mQ + LQ.off_W0 + (int64_t)LP.in_s * H, d->dimu, H, nullptr, 0, w.dy,
+                        (int)r4(d->dimu), n);
+    p.epi = EPI_ACTOR_DY; p.aux = x.th; p.ldaux = w.ld_sq;
+    p.coef = x.h->action_l2 * 2.0f / (float)(n * d->dimu);
+    ADD(p);
+  }
+  CUR_TRY(B.flush());
+  // ---- bwd-2: actor chain (weight grads of main/pi)
+  const int lddy = (int)r4(d->dimu);
+  cur = 0;
+  FOR_EXPERTS {
+    Expert& x = E[i]; const Workspace& w = x.w;
+    ADD(bwd_dx(w.dy, lddy, x.mP + LP.off_Wout, H, d->dimu, w.hp[L - 1], H, w.dp[0], H, n));
+    ADD(bwd_dw(w.hp[L - 1], H, H, w.dy, lddy, d->dimu, x.gP + LP.off_Wout, n));
+    ADD(bwd_db(w.dy, lddy, d->dimu, x.gP + LP.off_bout, n));
+  }
+  CUR_TRY(B.flush());
+  for (int l = L - 1; l >= 1; --l) {
+    FOR_EXPERTS {
+      Expert& x = E[i]; const Workspace& w = x.w;
+      ADD(bwd_dx(w.dp[cur], H, x.mP + LP.off_W[l], H, H, w.hp[l - 1], H, w.dp[cur ^ 1], H, n));
+      ADD(bwd_dw(w.hp[l - 1], H, H, w.dp[cur], H, H, x.gP + LP.off_W[l], n));
+      ADD(bwd_db(w.dp[cur], H, H, x.gP + LP.off_b[l], n));
+    }
+    CUR_TRY(B.flush());
+    cur ^= 1;
+  }
+  FOR_EXPERTS {
+    Expert& x = E[i]; const Workspace& w = x.w;
+    ADD(bwd_dw(w.Xpi, w.ld_spi, LP.in_s, w.dp[cur], H, H, x.gP + LP.off_W0, n));
+    ADD(bwd_db(w.dp[cur], H, H, x.gP + LP.off_b0, n));
+    if (LP.in_g > 0) ADD(bwd_dw(w.Xg, w.ld_g, LP.in_g, w.dp[cur], H, H, x.gP + LP.off_W0g, n));
+  }
+  CUR_TRY(B.flush());
+#undef FOR_EXPERTS
+#undef ADD
+  return CUR_OK;
+}
+
+static int fill_expert(Expert& x, const cur_net_desc* d, const float* theta_main, const float* theta_target,
+                       const cur_norm_stats* stats, const cur_batch* batch, const cur_ddpg_hyper* h, float* workspace,
+                       float* grads, float* q_loss, float* pi_loss, float* q_pi) {
   CUR_REQUIRE(theta_main && theta_target && batch && h && workspace && grads && q_pi, "NULL argument");
   CUR_REQUIRE(batch->o && batch->g && batch->u && batch->o_2 && batch->g_2 && batch->r, "NULL batch array");
   CUR_REQUIRE(!d->modular || batch->td, "task_descr required for a modular net");
   CUR_REQUIRE(batch->n > 0 && batch->n < (1 << 30), "bad batch");
   if (d->normalize_obs)
     CUR_REQUIRE(stats && stats->o_mean && stats->o_std && stats->g_mean && stats->g_std, "normalizer stats required");
-  cudaStream_t s = (cudaStream_t)stream;
-  const int64_t n = batch->n;
-  const NetLayout LQ = net_layout(*d, 0), LP = net_layout(*d, 1);
-  const int64_t offP = r4(LQ.total);
-  const float *mQ = theta_main, *mP = theta_main + offP, *tQ = theta_target, *tP = theta_target + offP;
-  float *gQ = grads, *gP = grads + offP;
-  Workspace w = carve(*d, n, workspace);
-  const int L = d->layers, H = d->hidden;
-
-  // ---- inputs
-  PrepParams P;
-  memset(&P, 0, sizeof(P));
-  P.d = *d; P.o = batch->o; P.g = batch->g; P.u = batch->u; P.td = batch->td; P.o_2 = batch->o_2; P.g_2 = batch->g_2;
-  P.n = n;
-  if (stats) { P.o_mean = stats->o_mean; P.o_std = stats->o_std; P.g_mean = stats->g_mean; P.g_std = stats->g_std; }
-  P.ld_spi = w.ld_spi; P.ld_sq = w.ld_sq; P.ld_g = w.ld_g;
-  P.Xpi = w.Xpi; P.Xg = w.Xg; P.XQu = w.XQu; P.XQpi = w.XQpi; P.Xpi_t = w.Xpi_t; P.Xg_t = w.Xg_t; P.XQ_t = w.XQ_t;
-  prep_kernel<<<grid_prep(n * LQ.in_s), 256, 0, s>>>(P);
-  CUR_CHECK_LAUNCH();
-
-  Batcher B(s, use_tc(*d, n), w);
-  // ---- fwd-1: main.pi | target.pi | main.Q(o,g,u)
-  B.add(fwd0(LP, mP, w.Xpi, w.ld_spi, w.Xg, w.ld_g, w.hp[0], n));
-  B.add(fwd0(LP, tP, w.Xpi_t, w.ld_spi, w.Xg_t, w.ld_g, w.ht[0], n));
-  B.add(fwd0(LQ, mQ, w.XQu, w.ld_sq, w.Xg, w.ld_g, w.hq[0], n));
-  CUR_TRY(B.flush());
-  for (int l = 1; l < L; ++l) {
-    B.add(fwdl(LP, mP, l, w.hp[l - 1], w.hp[l], n));
-    B.add(fwdl(LP, tP, l, w.ht[l - 1], w.ht[l], n));
-    B.add(fwdl(LQ, mQ, l, w.hq[l - 1], w.hq[l], n));
-    CUR_TRY(B.flush());
-  }
-  float* th = w.XQpi + LP.in_s;   // tanh output lives in the action columns of main.Q's input
-  B.add(fwdout(LP, mP, w.hp[L - 1], th, w.ld_sq, EPI_TANH, n));
-  B.add(fwdout(LP, tP, w.ht[L - 1], w.XQ_t + LP.in_s, w.ld_sq, EPI_TANH, n));
-  B.add(fwdout(LQ, mQ, w.hq[L - 1], w.Q, 1, EPI_NONE, n));
-  CUR_TRY(B.flush());
-  // ---- fwd-2: main.Q(o,g,pi) | target.Q(o2,g2,pi_t)   (same u and td for the target, ddpg.py:427-431)
-  B.add(fwd0(LQ, mQ, w.XQpi, w.ld_sq, w.Xg, w.ld_g, w.hqp[0], n));
-  B.add(fwd0(LQ, tQ, w.XQ_t, w.ld_sq, w.Xg_t, w.ld_g, w.htq[0], n));
-  CUR_TRY(B.flush());
-  for (int l = 1; l < L; ++l) {
-    B.add(fwdl(LQ, mQ, l, w.hqp[l - 1], w.hqp[l], n));
-    B.add(fwdl(LQ, tQ, l, w.htq[l - 1], w.htq[l], n));
-    CUR_TRY(B.flush());
-  }
-  B.add(fwdout(LQ, mQ, w.hqp[L - 1], q_pi, 1, EPI_NONE, n));
-  B.add(fwdout(LQ, tQ, w.htq[L - 1], w.Qt, 1, EPI_NONE, n));
-  CUR_TRY(B.flush());
-
-  // ---- losses and backward seeds
-  LossParams LPm;
-  LPm.r = batch->r; LPm.Q = w.Q; LPm.Qpi = q_pi; LPm.Qt = w.Qt; LPm.th = th; LPm.ldth = w.ld_sq; LPm.dimu = d->dimu;
-  LPm.n = n; LPm.gamma = h->gamma; LPm.clip_return = h->clip_return; LPm.action_l2 = h->action_l2;
-  LPm.clip_pos = h->clip_pos_returns; LPm.dQ = w.dQ; LPm.dQpi = w.dQpi; LPm.q_loss = q_loss; LPm.pi_loss = pi_loss;
-  LPm.step_counter = h->step_counter; LPm.ring = h->loss_ring;
-  loss_kernel<<<1, 1024, 0, s>>>(LPm);
-  CUR_CHECK_LAUNCH();
-
-  // ---- bwd-1: critic chain (weights grads of main/Q) | actor-through-Q chain (data grads only)
-  int cur = 0;
-  B.add(bwd_dx(w.dQ, 1, mQ + LQ.off_Wout, H, 1, w.hq[L - 1], H, w.dc[0], H, n));
-  B.add(bwd_dw(w.hq[L - 1], H, H, w.dQ, 1, 1, gQ + LQ.off_Wout, n));
-  B.add(bwd_db(w.dQ, 1, 1, gQ + LQ.off_bout, n));
-  B.add(bwd_dx(w.dQpi, 1, mQ + LQ.off_Wout, H, 1, w.hqp[L - 1], H, w.da[0], H, n));
-  CUR_TRY(B.flush());
-  for (int l = L - 1; l >= 1; --l) {
-    B.add(bwd_dx(w.dc[cur], H, mQ + LQ.off_W[l], H, H, w.hq[l - 1], H, w.dc[cur ^ 1], H, n));
-    B.add(bwd_dw(w.hq[l - 1], H, H, w.dc[cur], H, H, gQ + LQ.off_W[l], n));
-    B.add(bwd_db(w.dc[cur], H, H, gQ + LQ.off_b[l], n));
-    B.add(bwd_dx(w.da[cur], H, mQ + LQ.off_W[l], H, H, w.hqp[l - 1], H, w.da[cur ^ 1], H, n));
-    CUR_TRY(B.flush());
-    cur ^= 1;
-  }
-  B.add(bwd_dw(w.XQu, w.ld_sq, LQ.in_s, w.dc[cur], H, H, gQ + LQ.off_W0, n));
-  B.add(bwd_db(w.dc[cur], H, H, gQ + LQ.off_b0, n));
-  if (LQ.in_g > 0) B.add(bwd_dw(w.Xg, w.ld_g, LQ.in_g, w.dc[cur], H, H, gQ + LQ.off_W0g, n));
-  {
-    // d pi_loss / d(pre-tanh) = (dL/d(pi/max_u) + action_l2 * 2/(B*dimu) * th) * (1 - th^2)
-    GemmProb p = bwd_dx(w.da[cur], H, mQ + LQ.off_W0 + (int64_t)LP.in_s * H, d->dimu, H, nullptr, 0, w.dy,
-                        (int)r4(d->dimu), n);
-    p.epi = EPI_ACTOR_DY; p.aux = th; p.ldaux = w.ld_sq;
-    p.coef = h->action_l2 * 2.0f / (float)(n * d->dimu);
-    B.add(p);
-  }
-  CUR_TRY(B.flush());
-  // ---- bwd-2: actor chain (weight grads of main/pi)
-  const int lddy = (int)r4(d->dimu);
-  cur = 0;
-  B.add(bwd_dx(w.dy, lddy, mP + LP.off_Wout, H, d->dimu, w.hp[L - 1], H, w.dp[0], H, n));
-  B.add(bwd_dw(w.hp[L - 1], H, H, w.dy, lddy, d->dimu, gP + LP.off_Wout, n));
-  B.add(bwd_db(w.dy, lddy, d->dimu, gP + LP.off_bout, n));
-  CUR_TRY(B.flush());
-  for (int l = L - 1; l >= 1; --l) {
-    B.add(bwd_dx(w.dp[cur], H, mP + LP.off_W[l], H, H, w.hp[l - 1], H, w.dp[cur ^ 1], H, n));
-    B.add(bwd_dw(w.hp[l - 1], H, H, w.dp[cur], H, H, gP + LP.off_W[l], n));
-    B.add(bwd_db(w.dp[cur], H, H, gP + LP.off_b[l], n));
-    CUR_TRY(B.flush());
-    cur ^= 1;
-  }
-  B.add(bwd_dw(w.Xpi, w.ld_spi, LP.in_s, w.dp[cur], H, H, gP + LP.off_W0, n));
-  B.add(bwd_db(w.dp[cur], H, H, gP + LP.off_b0, n));
-  if (LP.in_g > 0) B.add(bwd_dw(w.Xg, w.ld_g, LP.in_g, w.dp[cur], H, H, gP + LP.off_W0g, n));
-  CUR_TRY(B.flush());
+  const int64_t offP = r4(net_layout(*d, 0).total);
+  x.w = carve(*d, batch->n, workspace);
+  x.mQ = theta_main; x.mP = theta_main + offP; x.tQ = theta_target; x.tP = theta_target + offP;
+  x.gQ = grads; x.gP = grads + offP;
+  x.batch = batch; x.stats = stats; x.h = h; x.q_loss = q_loss; x.pi_loss = pi_loss; x.q_pi = q_pi;
+  x.th = nullptr; x.parts_used = x.rowparts_used = 0;
   return CUR_OK;
+}
+
+extern "C" int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* theta_main,
+                              const float* theta_target, const cur_norm_stats* stats, const cur_batch* batch,
+                              const cur_ddpg_hyper* h, float* workspace, float* grads, float* q_loss,
+                              float* pi_loss, float* q_pi) {
+  CUR_TRY(check_desc(d));
+  Expert x;
+  CUR_TRY(fill_expert(x, d, theta_main, theta_target, stats, batch, h, workspace, grads, q_loss, pi_loss, q_pi));
+  return grads_levels((cudaStream_t)stream, d, &x, 1, batch->n);
+}
+
+extern "C" int cur_ddpg_grads_group(void* stream, const cur_net_desc* d, int n_experts, const cur_ddpg_expert* experts) {
+  CUR_TRY(check_desc(d));
+  CUR_REQUIRE(experts != nullptr && n_experts >= 1 && n_experts <= CUR_MAX_TASKS, "bad expert list");
+  Expert E[CUR_MAX_TASKS];
+  for (int i = 0; i < n_experts; ++i) {
+    const cur_ddpg_expert& a = experts[i];
+    CUR_REQUIRE(a.batch.n == experts[0].batch.n, "all experts must train on the same batch size");
+    CUR_TRY(fill_expert(E[i], d, a.theta_main, a.theta_target, a.has_stats ? &a.stats : nullptr, &a.batch, &a.hyper,
+                        a.workspace, a.grads, a.q_loss, a.pi_loss, a.q_pi));
+  }
+  return grads_levels((cudaStream_t)stream, d, E, n_experts, experts[0].batch.n);
 }

@@ -484,7 +484,8 @@ class DDPG(object):
         self._dyn_dev.copy_(self._dyn_host, non_blocking=True)
         self._graph_sig = sig
 
-    def _build_graph(self):
+    def _prepare_graph_state(self):
+        """Device-resident state of the graph path (control block, loss rings, Adam tables, fixed batch buffers)."""
         dev = self.device
         B = self.batch_size
         L = self._all_segments()[0][0].layout
@@ -515,6 +516,11 @@ class DDPG(object):
             self._ghyper.grads_parity_stride = self.net.arena
         self._graph_sig = None
         self._refresh_dyn()
+        self._graph_state_ready = True
+
+    def _build_graph(self):
+        dev = self.device
+        self._prepare_graph_state()
         torch.cuda.current_stream().synchronize()
         # warm-up run outside capture (lazy module loading, cudaFuncSetAttribute)
         state = (self.theta_main.clone(), self._adam_m.clone(), self._adam_v.clone(), self._step.clone())

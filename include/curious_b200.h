@@ -274,6 +274,28 @@ int cur_ddpg_grads(void* stream, const cur_net_desc* d, const float* theta_main,
                    const cur_ddpg_hyper* h, float* workspace, float* grads, float* q_loss,
                    float* pi_loss, float* q_pi);
 
+/* structure='task_experts' (train.py:287-289: one DDPG per module, all of the same shape): DDPG._grads of
+ * n_experts agents as ONE sequence of grouped launches - every dependency level of the graph covers the
+ * problems of all experts (FFMA grouped GEMM at batch 256, tcgen05 batch at batch >= 1024).  Semantically
+ * `for p in policies: p._grads()`; each expert keeps its own parameters, batch, losses and workspace
+ * (cur_ddpg_workspace_floats(d, batch) floats each). */
+typedef struct cur_ddpg_expert {
+  const float* theta_main;
+  const float* theta_target;
+  cur_norm_stats stats;
+  int32_t has_stats;
+  int32_t _pad;
+  cur_batch batch;
+  cur_ddpg_hyper hyper;
+  float* workspace;
+  float* grads;
+  float* q_loss;
+  float* pi_loss;
+  float* q_pi;
+} cur_ddpg_expert;
+int cur_ddpg_grads_group(void* stream, const cur_net_desc* d, int n_experts, const cur_ddpg_expert* experts);
+
+
 /* ------------------------------------------------------------------------------------------
  * "Rows" schedule of the same update (csrc/ddpg_rows.cu): DDPG._grads (ddpg.py:235-243) and,
  * optionally, both MpiAdam.update calls of DDPG._update (ddpg.py:246-248, mpi_adam.py:30-35) in

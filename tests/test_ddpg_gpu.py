@@ -363,3 +363,45 @@ def test_large_batch_tensor_core_update_against_oracle(batch_size):
             assert np.array_equal(gpu.get_flat('pi'), ora.pi_adam.theta)
     finally:
         lib.cur_ddpg_set_tensor_cores(-1)
+
+
+@pytest.mark.parametrize('batch_size,use_graph', [(256, True), (256, False), (1024, True)])
+def test_task_experts_grouped_update_equals_sequential(batch_size, use_graph):
+    """structure='task_experts': TaskExperts.train() steps all experts with grouped launches (one launch per
+    dependency level over every expert's problems, cur_ddpg_grads_group).  It must be `for p in policies:
+    p.train()` - bit-identical parameters and losses to stepping the same experts one after the other on the
+    levels schedule (same Philox streams, same per-problem arithmetic)."""
+    import torch
+    from curious_b200.experts import TaskExperts
+    n_exp = 3
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, structure='task_experts', task_replay='replay_current_task_buffer',
+                                          batch_size=batch_size)
+    cp = np.array([0.05, 0.2, 0.1, 0.0])
+    episodes = episode_stream(dims, kw['T'], 8)
+
+    def build(use_cuda_graph):
+        agents = []
+        for t in range(n_exp):
+            k = dict(kw)
+            k['t_id'] = t
+            a = make_gpu_agent(k, dims, ag_ids, g_ids, her_rng='philox', seed=10 + t, update_schedule='levels',
+                               use_cuda_graph=use_cuda_graph)
+            np.random.seed(7)
+            _fill(a, episodes, cp)
+            agents.append(a)
+        return agents
+
+    seq = build(use_graph)
+    grp = TaskExperts(build(use_graph), use_cuda_graph=use_graph)
+    losses_seq, losses_grp = [], []
+    for _ in range(4):
+        losses_seq.append([float(p.train()[0]) for p in seq])
+        losses_grp.append([float(x[0]) for x in grp.train()])
+    torch.cuda.synchronize()
+    assert np.array_equal(np.array(losses_seq), np.array(losses_grp))
+    for a, b in zip(seq, grp.policies):
+        assert torch.equal(a.theta_main, b.theta_main)
+        assert torch.equal(a._adam_v, b._adam_v)
+        assert a.Q_adam.t == b.Q_adam.t == 4
+    # different experts do learn different things
+    assert not torch.equal(grp[0].theta_main, grp[1].theta_main)

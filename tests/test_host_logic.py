@@ -27,16 +27,16 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_structs_match_header(tmp_path):
     from curious_b200 import _lib
     src = tmp_path / 'sz.cpp'
-    src.write_text('#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
+    src.write_text('#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
                    'sizeof(cur_layout),sizeof(cur_task_table),sizeof(cur_segment),sizeof(cur_her_args),'
                    'sizeof(cur_net_desc),sizeof(cur_batch),sizeof(cur_ddpg_hyper),sizeof(cur_norm_stats),'
-                   'sizeof(cur_episode_src),sizeof(cur_her_dyn),sizeof(cur_adam_fused),sizeof(cur_p2p_ctx));}\n' % os.path.join(ROOT, 'include', 'curious_b200.h'))
+                   'sizeof(cur_episode_src),sizeof(cur_her_dyn),sizeof(cur_adam_fused),sizeof(cur_p2p_ctx),sizeof(cur_ddpg_expert));}\n' % os.path.join(ROOT, 'include', 'curious_b200.h'))
     exe = tmp_path / 'sz'
     subprocess.check_call(['g++', str(src), '-o', str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(t) for t in (_lib.Layout, _lib.TaskTable, _lib.Segment, _lib.HerArgs, _lib.NetDesc, _lib.Batch,
                                   _lib.DdpgHyper, _lib.NormStats, _lib.EpisodeSrc, _lib.HerDyn, _lib.AdamFused,
-                                  _lib.P2PCtx)]
+                                  _lib.P2PCtx, _lib.DdpgExpert)]
     assert got == want
 
 
