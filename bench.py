@@ -163,15 +163,86 @@ def build_gpu_workload(device, seed):
     for i in range(1, N_MODULES + 1):
         fill_buffer_on_device(buffers[i], dims, seed * 100 + i)
     gamma = 1. - 1. / T
-    agent = DDPG(input_dims=dims, hidden=256, layers=3, network_class='baselines.her.actor_critic:MultiTaskActorCritic',
-                 polyak=0.95, batch_size=BATCH, Q_lr=0.001, pi_lr=0.001, norm_eps=0.01, norm_clip=5, max_u=1.,
+
+    def make_agent(batch_size=BATCH, structure='curious', task_replay='replay_task_cp_buffer', **extra):
+        a = DDPG(input_dims=dims, hidden=256, layers=3, network_class='baselines.her.actor_critic:MultiTaskActorCritic',
+                 polyak=0.95, batch_size=batch_size, Q_lr=0.001, pi_lr=0.001, norm_eps=0.01, norm_clip=5, max_u=1.,
                  action_l2=1.0, clip_obs=200., scope='ddpg', T=T, rollout_batch_size=2,
                  subtract_goals=lambda a, b: a - b, relative_goals=False, clip_pos_returns=True,
                  clip_return=1. / (1. - gamma), normalize_obs=False, sample_transitions=sampler, gamma=gamma,
-                 buffers=buffers, tasks_ag_id=ag_ids, tasks_g_id=g_ids, task_replay='replay_task_cp_buffer',
-                 eps_task=EPS_TASK, structure='curious', her_rng='philox', seed=0, device=device)
-    agent.cp = np.array(CP)
+                 buffers=buffers, tasks_ag_id=ag_ids, tasks_g_id=g_ids, task_replay=task_replay,
+                 eps_task=EPS_TASK, structure=structure, her_rng='philox', seed=0, device=device, **extra)
+        a.cp = np.array(CP)
+        return a
+
+    agent = make_agent()
+    agent.make_agent = make_agent
     return agent, sampler, buffers, dims, ag_ids, g_ids
+
+
+def update_flops(dims, n_modules, batch, hidden=256):
+    """algorithmic FLOPs of one DDPG update (forward of main/target pi and the three Q passes, critic,
+    actor-through-critic and actor backward chains)."""
+    H, B = hidden, batch
+    s_pi, s_q = dims['o'] + n_modules, dims['o'] + n_modules + dims['u']
+    f_pi = 2 * B * ((s_pi + dims['g']) * H + 2 * H * H + H * dims['u'])
+    f_q = 2 * B * ((s_q + dims['g']) * H + 2 * H * H + H)
+    fwd = 2 * f_pi + 3 * f_q
+    bwd = (2 * f_q - 2 * B * (s_q + dims['g']) * H) + (f_q - 2 * B * (s_q + dims['g'] - dims['u']) * H) + \
+          (2 * f_pi - 2 * B * (s_pi + dims['g']) * H)
+    return fwd + bwd
+
+
+def time_updates(fn, n, torch):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def large_batch_sweep(agent, dims, torch):
+    """BASELINE config 5: per-GPU batch sweep of the DDPG update through DDPG.train() (HER sample + grads + Adam in
+    one CUDA graph) and structure='task_experts' as grouped launches.  At batch >= 1024 the hidden-layer GEMMs run on
+    tcgen05 (3xTF32): `tensor_frac` = 3 x algorithmic FLOP/s / (measured dense bf16 peak / 2), i.e. against the TF32
+    rate of the tensor pipe, all 3 error-compensation passes counted."""
+    from curious_b200 import _lib
+    from curious_b200.experts import TaskExperts
+    import ctypes as C
+    try:
+        bf16 = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops'])
+    except Exception:
+        bf16 = 2250.0 * 0.745
+    sweep = []
+    for b in (256, 1024, 4096, 16384):
+        a = agent if b == BATCH else agent.make_agent(batch_size=b)
+        ms = time_updates(a.train, 200 if b <= 1024 else 40, torch)
+        fl = update_flops(dims, N_MODULES, b)
+        tc = bool(_lib.load().cur_ddpg_uses_tensor_cores(C.byref(a.net.desc), b)) and not a._use_rows(b)
+        sweep.append({'batch': b, 'update_us': 1e3 * ms, 'updates_per_s': 1e3 / ms, 'transitions_per_s': 1e3 * b / ms,
+                      'tflops': fl / (ms * 1e-3) / 1e12, 'schedule': 'rows' if a._use_rows(b) else 'levels',
+                      'tensor_cores': tc, 'tensor_frac': (3 * fl / (ms * 1e-3) / 1e12) / (bf16 / 2) if tc else None})
+        if b != BATCH:
+            del a
+            torch.cuda.empty_cache()
+    experts = []
+    for b in (256, 4096):
+        ps = [agent.make_agent(batch_size=b, structure='task_experts', task_replay='replay_current_task_buffer', t_id=t,
+                               update_schedule='auto') for t in range(N_MODULES)]
+        for p in ps:
+            p.cp = np.array(CP)
+        grp = TaskExperts(ps)
+        ms = time_updates(grp.train, 100 if b <= 1024 else 20, torch)
+        experts.append({'experts': N_MODULES, 'batch': b, 'round_us': 1e3 * ms, 'expert_updates_per_s': 1e3 * N_MODULES / ms,
+                        'mode': 'sequential rows' if all(p._use_rows(b) for p in ps) else 'grouped levels'})
+        del grp, ps
+        torch.cuda.empty_cache()
+    return {'batch_sweep': sweep, 'task_experts': experts, 'tf32_peak_tflops_assumed': bf16 / 2}
 
 
 def her_step_segments(buffers, rows):
@@ -420,6 +491,8 @@ def run_ours(args):
             'update_us': 1e3 * upd_ms / n_upd,
             'update_schedule': 'rows' if agent._use_rows(BATCH) else 'levels',
         }
+        if world == 1 and not args.no_sweep:
+            line['ddpg_update'] = large_batch_sweep(agent, dims, torch)
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_sampler_baseline()
         print(json.dumps(line))
@@ -434,6 +507,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sweep', action='store_true', help='skip the batch sweep / task_experts section')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
