@@ -37,9 +37,11 @@ struct Workspace {
   int64_t total;
 };
 
-// Batches this large run their hidden-layer GEMMs on the tensor cores (tc_gemm.cu); below it every GEMM of a
-// level is latency-bound and the FFMA grouped kernel wins.  CUR_DDPG_TC=0 forces the FFMA path (A/B measurements).
-constexpr int64_t TC_MIN_BATCH = 1024;
+// Batches this large run their layer GEMMs on the tensor cores (tc_gemm.cu); below it every GEMM of a level is
+// latency-bound and the FFMA grouped kernel wins (measured us/update, FFMA vs tcgen05: 1024: 337 / 392,
+// 2048: 556 / 420, 4096: 1161 / 479, 16384: 4130 / 1038).  CUR_DDPG_TC=0 or cur_ddpg_set_tensor_cores(0) forces the
+// FFMA path, cur_ddpg_set_tensor_cores(1) forces the tensor cores for every eligible shape (A/B measurements, tests).
+constexpr int64_t TC_MIN_BATCH = 2048;
 constexpr int TC_SLOTS = 3;          // split-K weight gradients / row reductions per dependency level
 static int g_tc_mode = -1;          // -1: environment (default on), 0: off, 1: on  (cur_ddpg_set_tensor_cores)
 static bool tc_enabled() {
@@ -51,8 +53,11 @@ static bool tc_enabled() {
   }
   return v == 1;
 }
-static bool tc_shape_ok(const cur_net_desc& d, int64_t n) { return n >= TC_MIN_BATCH && (n % 128) == 0 && d.hidden == 256; }
-static bool use_tc(const cur_net_desc& d, int64_t n) { return tc_enabled() && tc_shape_ok(d, n); }
+static bool tc_shape_ok(const cur_net_desc& d, int64_t n) { return n >= 256 && (n % 128) == 0 && d.hidden == 256; }
+static bool use_tc(const cur_net_desc& d, int64_t n) {
+  if (!tc_shape_ok(d, n) || !tc_enabled()) return false;
+  return g_tc_mode == 1 || n >= TC_MIN_BATCH;
+}
 
 static Workspace carve(const cur_net_desc& d, int64_t n, float* base) {
   Workspace w;

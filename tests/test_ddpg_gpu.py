@@ -365,7 +365,7 @@ def test_large_batch_tensor_core_update_against_oracle(batch_size):
         lib.cur_ddpg_set_tensor_cores(-1)
 
 
-@pytest.mark.parametrize('batch_size,use_graph', [(256, True), (256, False), (1024, True)])
+@pytest.mark.parametrize('batch_size,use_graph', [(256, True), (256, False), (2048, True)])
 def test_task_experts_grouped_update_equals_sequential(batch_size, use_graph):
     """structure='task_experts': TaskExperts.train() steps all experts with grouped launches (one launch per
     dependency level over every expert's problems, cur_ddpg_grads_group).  It must be `for p in policies:

@@ -154,3 +154,36 @@ def test_rank_seed_matches_reference():
     from curious_b200 import parallel
     assert parallel.rank_seed(5, 0) == 5 and parallel.rank_seed(5, 3) == 3000005      # train.py:242
     assert parallel.world(False) == (None, 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+def _rollout_results(rank, i):
+    rng = np.random.RandomState(1000 * rank + i)
+    tasks = rng.randint(0, 3, size=2).tolist()
+    return tasks, [float(rng.uniform() < 0.2 + 0.02 * i * (t == 1)) for t in tasks]
+
+
+def _body_competence(rank, world):
+    """LP pipeline (rollout.py:332-404): rank 0 gathers every rank's (task, success) pairs, updates the queues and
+    broadcasts CP and p."""
+    from curious_b200.queues import CompetenceTracker
+    tr = CompetenceTracker(3, queue_length=6)
+    for i in range(25):
+        cp, p = tr.update(*_rollout_results(rank, i))
+    return np.concatenate([np.asarray(cp, np.float64), np.asarray(p, np.float64)])
+
+
+def test_competence_progress_is_gathered_on_rank0_and_broadcast(tmp_path):
+    from curious_b200.queues import CompetenceTracker
+    res = _run('_body_competence', tmp_path)
+    assert np.array_equal(res[0], res[1])                       # every rank ends with rank 0's CP and p
+    # emulate the world in-process: rank order of the gather is rank 0's pairs first (MPI gather order)
+    tr = CompetenceTracker(3, queue_length=6, comm=False)
+    for i in range(25):
+        tasks, succ = [], []
+        for r in range(2):
+            t, s = _rollout_results(r, i)
+            tasks += t
+            succ += s
+        cp, p = tr.update(tasks, succ)
+    assert np.array_equal(res[0], np.concatenate([cp, p]))
