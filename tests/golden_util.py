@@ -12,7 +12,7 @@ def sampler_cases():
     names = []
     for p in sorted(glob.glob(os.path.join(GOLDEN, '*.npz'))):
         n = os.path.basename(p)[:-4]
-        if not n.startswith('storage_'):
+        if not n.startswith('storage_') and n != 'competence_queue':
             names.append(n)
     return names
 
