@@ -171,7 +171,8 @@ def build_gpu_workload(device, seed):
                  subtract_goals=lambda a, b: a - b, relative_goals=False, clip_pos_returns=True,
                  clip_return=1. / (1. - gamma), normalize_obs=False, sample_transitions=sampler, gamma=gamma,
                  buffers=buffers, tasks_ag_id=ag_ids, tasks_g_id=g_ids, task_replay=task_replay,
-                 eps_task=EPS_TASK, structure=structure, her_rng='philox', seed=0, device=device, **extra)
+                 eps_task=EPS_TASK, structure=structure, her_rng='philox', seed=0, device=device,
+                 grad_exchange=os.environ.get('CUR_GRAD_EXCHANGE', 'auto'), **extra)
         a.cp = np.array(CP)
         return a
 

@@ -159,6 +159,9 @@ SIGNATURES = {
     'cur_p2p_allreduce_adam': (C.c_int, [C.c_void_p, C.POINTER(P2PCtx), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
                                          C.c_void_p]),
+    'cur_p2p_sharded_adam': (C.c_int, [C.c_void_p, C.POINTER(P2PCtx), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                       C.c_void_p]),
 }
 
 _lib = None

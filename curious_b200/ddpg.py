@@ -65,8 +65,9 @@ class DDPG(object):
         self.update_schedule = kwargs.get('update_schedule', 'auto')
         self.fuse_her = kwargs.get('fuse_her', True)      # rows schedule: sample inside the update kernel
         # several ranks: 'p2p' = gradient exchange over NVLink peer memory fused with Adam inside the update's
-        # CUDA graph (csrc/p2p.cu), 'nccl' = NCCL all-reduce + Adam launch after the graph, 'auto' = p2p when
-        # the rows schedule runs on an NCCL (one GPU per rank) group
+        # CUDA graph (csrc/p2p.cu: every rank sums all peers' gradients in rank order), 'p2p_sharded' = reduce-scatter
+        # by loads, Adam on the own slice, all-gather by stores, 'nccl' = NCCL all-reduce + Adam launch after the
+        # graph, 'auto' = p2p when the rows schedule runs on an NCCL (one GPU per rank) group
         self.grad_exchange = kwargs.get('grad_exchange', 'auto')
         self.create_actor_critic = import_function(self.network_class)
 
@@ -512,7 +513,9 @@ class DDPG(object):
         self._peer = None
         if self._want_peer_exchange():
             from .parallel import PeerGradExchange
-            self._peer = PeerGradExchange(self.net.arena, self.comm)
+            # the sharded exchange moves 8x fewer bytes at 8 GPUs but measured no faster (2 GPUs: 83 us full / 91 us
+            # sharded, 8 GPUs: 97.3 / 98.2): the exchange is latency / straggler bound, so the one-round kernel is default
+            self._peer = PeerGradExchange(self.net.arena, self.comm, sharded=self.grad_exchange == 'p2p_sharded')
             self._ghyper.grads_parity_stride = self.net.arena
         self._graph_sig = None
         self._refresh_dyn()
@@ -558,7 +561,7 @@ class DDPG(object):
         import torch.distributed as dist
         ok = (self._use_rows(self.batch_size) and self._same_rule() and n <= _lib.CUR_MAX_RANKS and
               dist.get_backend(group) == 'nccl')
-        if self.grad_exchange == 'p2p' and not ok:
+        if self.grad_exchange in ('p2p', 'p2p_sharded') and not ok:
             raise ValueError('grad_exchange="p2p" needs the rows schedule, one Adam rule for both nets and an NCCL '
                              'group of <= %d ranks' % _lib.CUR_MAX_RANKS)
         return ok

@@ -76,10 +76,11 @@ class PeerGradExchange(object):
     ships its CUDA-IPC handle through torch.distributed and maps the peers' regions.  Needs one process per GPU
     on one NVLink domain (cudaIpcOpenMemHandle fails otherwise -> the caller falls back to NCCL explicitly)."""
 
-    FLAG_BYTES = 128
+    FLAG_BYTES = 256
 
-    def __init__(self, arena_floats, comm=None):
+    def __init__(self, arena_floats, comm=None, sharded=True):
         import ctypes as C
+        self.sharded = sharded
         import torch.distributed as dist
         from . import _lib
         lib = _lib.load()
@@ -119,7 +120,8 @@ class PeerGradExchange(object):
     def allreduce_adam(self, stream, theta, m, v, neg_a_table, table_len, step_counter, beta1, beta2, eps):
         import ctypes as C
         from . import _lib
-        _lib.check(self.lib.cur_p2p_allreduce_adam(
+        fn = self.lib.cur_p2p_sharded_adam if self.sharded else self.lib.cur_p2p_allreduce_adam
+        _lib.check(fn(
             stream, C.byref(self.ctx), theta.data_ptr(), m.data_ptr(), v.data_ptr(), neg_a_table.data_ptr(),
             int(table_len), step_counter.data_ptr(), beta1, beta2, eps, self.error_flag.data_ptr()),
             'cur_p2p_allreduce_adam')

@@ -341,7 +341,7 @@ int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* theta_main,
  * Every rank allocates a region with cur_p2p_alloc (cudaMalloc + cudaIpcGetMemHandle, zeroed),
  * sends the 64-byte handle to its peers (any transport; curious_b200/parallel.py uses
  * torch.distributed all_gather_object) and maps theirs with cur_p2p_open.  Region layout:
- *   [ 128 bytes of flags | gradient arena buffer 0 | gradient arena buffer 1 ]   (arena floats each)
+ *   [ 256 bytes of flags | gradient arena buffer 0 | gradient arena buffer 1 | parameter staging ]   (arena floats each)
  * The gradient of update s (s = value of the device step counter AFTER the weight-gradient launch
  * bumped it) must be in buffer (s & 1) of the rank's own region; cur_ddpg_rows_step does that when
  * h->grads_parity_stride = arena and `grads` points at buffer 0.  cur_p2p_allreduce_adam then
@@ -362,6 +362,13 @@ int cur_p2p_free(void* ptr);
 int cur_p2p_allreduce_adam(void* stream, const cur_p2p_ctx* ctx, float* theta, float* m, float* v,
                            const float* neg_a_table, int table_len, const int64_t* step_counter,
                            double beta1, double beta2, double eps, int32_t* error_flag /* or NULL */);
+/* Sharded form of the same step (reduce-scatter by peer loads, Adam on the rank's own slice of the arena,
+ * all-gather by peer stores into the staging arenas, second flag round, local copy): (W-1)/W of one arena
+ * in each direction per rank instead of W-1 arenas of loads.  Same result on every rank, bit-identical to
+ * cur_p2p_allreduce_adam; m / v are only maintained for the rank's own slice. */
+int cur_p2p_sharded_adam(void* stream, const cur_p2p_ctx* ctx, float* theta, float* m, float* v,
+                         const float* neg_a_table, int table_len, const int64_t* step_counter,
+                         double beta1, double beta2, double eps, int32_t* error_flag /* or NULL */);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core layer GEMM for large batches (csrc/tc_gemm.cu): tcgen05 (kind::tf32) with TMEM

@@ -95,15 +95,17 @@ def test_two_rank_update_sums_gradients_and_stays_synced(use_graph, tmp_path):
 
 
 def test_peer_memory_exchange_equals_nccl_allreduce(tmp_path):
-    """The fused peer-memory all-reduce + Adam kernel (csrc/p2p.cu) sums the ranks' gradients in rank order;
-    with two ranks that is the same float32 sum as NCCL's, so 120 updates end on bit-identical parameters."""
+    """The fused peer-memory exchange + Adam kernels (csrc/p2p.cu; sharded and full variants) sum the ranks'
+    gradients in rank order; with two ranks that is the same float32 sum as NCCL's, so 120 updates end on
+    bit-identical parameters in all three modes."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     thetas = {}
-    for mode in ('p2p', 'nccl'):
+    for mode in ('p2p', 'p2p_sharded', 'nccl'):
         d = tmp_path / mode
         d.mkdir()
         mp.spawn(_worker, args=(2, _free_port(), True, str(d), mode), nprocs=2, join=True)
         thetas[mode] = [np.load(os.path.join(str(d), 'theta%d.npy' % r)) for r in range(2)]
         assert np.array_equal(thetas[mode][0], thetas[mode][1])
     assert np.array_equal(thetas['p2p'][0], thetas['nccl'][0])
+    assert np.array_equal(thetas['p2p_sharded'][0], thetas['nccl'][0])
