@@ -436,6 +436,21 @@ def run_ours(args):
     e1.record()
     barrier()
     upd_ms = e0.elapsed_time(e1)
+    # ---- 19-worker-equivalent (BASELINE config 4 / SURVEY 8e): the reference's 19 MPI workers spread over the ranks,
+    # ceil(19 / world) batch-256 workers per GPU, gradients summed per rank and across ranks, one Adam step
+    k19 = -(-19 // world)
+    agent19 = agent.make_agent(workers_per_rank=k19)
+    for _ in range(3):
+        agent19.train()
+    barrier()
+    n19 = 30
+    e0.record()
+    for _ in range(n19):
+        agent19.train()
+    e1.record()
+    barrier()
+    upd19_ms = e0.elapsed_time(e1)
+    del agent19
     # ---- e2e: training cycles through the plugin API with host episode buffers
     from curious_b200 import synth
     rng = np.random.RandomState(99 + rank)
@@ -459,9 +474,9 @@ def run_ours(args):
     cyc_s = time.perf_counter() - t0
     clock_info = clocks.stop()
     if world > 1:
-        tt = torch.tensor([ms, upd_ms, cyc_s], device=device, dtype=torch.float64)
+        tt = torch.tensor([ms, upd_ms, cyc_s, upd19_ms], device=device, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, upd_ms, cyc_s = [float(x) for x in tt.cpu()]
+        ms, upd_ms, cyc_s, upd19_ms = [float(x) for x in tt.cpu()]
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         bpt = algorithmic_bytes_per_transition(dims, N_MODULES)
@@ -491,6 +506,9 @@ def run_ours(args):
             'updates_per_s': world * n_upd / (upd_ms * 1e-3),
             'update_us': 1e3 * upd_ms / n_upd,
             'update_schedule': 'rows' if agent._use_rows(BATCH) else 'levels',
+            'workers19_equivalent': {'workers_per_rank': k19, 'workers': k19 * world, 'global_batch': k19 * world * BATCH,
+                                     'update_us': 1e3 * upd19_ms / n19, 'updates_per_s': n19 / (upd19_ms * 1e-3),
+                                     'transitions_per_s': k19 * world * BATCH * n19 / (upd19_ms * 1e-3)},
         }
         if world == 1 and not args.no_sweep:
             line['ddpg_update'] = large_batch_sweep(agent, dims, torch)

@@ -81,7 +81,7 @@ class Batch(C.Structure):
 class DdpgHyper(C.Structure):
     _fields_ = [('gamma', C.c_float), ('clip_return', C.c_float), ('action_l2', C.c_float),
                 ('clip_pos_returns', C.c_int32), ('step_counter', C.c_void_p), ('loss_ring', C.c_int32),
-                ('_pad', C.c_int32), ('grads_parity_stride', C.c_int64)]
+                ('micro_batches', C.c_int32), ('grads_parity_stride', C.c_int64)]
 
 
 class DdpgExpert(C.Structure):
@@ -100,7 +100,7 @@ CUR_MAX_RANKS = 8
 
 class P2PCtx(C.Structure):
     _fields_ = [('rank', C.c_int32), ('world', C.c_int32), ('region', C.c_void_p * CUR_MAX_RANKS),
-                ('arena', C.c_int64)]
+                ('arena', C.c_int64), ('step_div', C.c_int32), ('_pad', C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/curious_b200.h declares
@@ -124,7 +124,7 @@ SIGNATURES = {
                                 C.c_float, C.c_double, C.c_double, C.c_double, C.c_float]),
     'cur_adam_step_graph': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
-                                      C.c_float]),
+                                      C.c_float, C.c_int32]),
     'cur_polyak': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double]),
     'cur_checksum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'cur_net_param_count': (C.c_int64, [C.POINTER(NetDesc), C.c_int]),

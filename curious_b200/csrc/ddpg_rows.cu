@@ -674,7 +674,8 @@ struct DwTail {
   float *q_loss, *pi_loss;
   long long* tl;                   // debug timeline (CUR_ROWS_TIMELINE)
   int tl_skinny_block;
-  int64_t parity_stride;           // > 0: gradients go to C + ((step + 1) & 1) * parity_stride (peer-memory exchange)
+  int64_t parity_stride;           // > 0: gradients go to C + ((update + 1) & 1) * parity_stride (peer-memory exchange)
+  int micro;                       // micro-batches (workers) per update: launch j = step % micro accumulates for j > 0
 };
 
 // Tile kinds of the weight-gradient launch (K = batch <= 256 is the reduction dimension):
@@ -690,7 +691,8 @@ constexpr int DW_KMAX = 256;
 constexpr int DW_LD = GT + 4;                                   // row stride of a staged [k][32] tile
 constexpr size_t DW_SMEM_BYTES = (size_t)2 * DW_KMAX * DW_LD * 4;
 
-__device__ __forceinline__ void dw_store(float* c, float v, const AdamCtx* ax) {
+__device__ __forceinline__ void dw_store(float* c, float v, const AdamCtx* ax, bool accumulate = false) {
+  if (accumulate) v += *c;         // micro-batch j > 0 of a several-workers-per-rank update adds to the running sum
   *c = v;
   if (ax) {
     const int64_t off = c - ax->grads;
@@ -748,7 +750,7 @@ __device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, floa
     const int gm = m0 + (i >> 5), gn = n0 + (i & 31);
     if (gm < P.M && gn < P.N) {
       const float v = (red[i] + red[GT * GT + i]) + (red[2 * GT * GT + i] + red[3 * GT * GT + i]);
-      dw_store(P.C + (int64_t)gm * P.ldc + gn, v, ax);
+      dw_store(P.C + (int64_t)gm * P.ldc + gn, v, ax, P.accumulate != 0);
     }
   }
 }
@@ -785,7 +787,7 @@ __device__ __forceinline__ void dw_tile_skinny(const GemmProb& P, float* red, in
       float v = 0.f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) v += red[(q * 32 + mm) * 4 + j];
-      dw_store(P.C + (int64_t)(m0 + mm) * P.ldc + j, v, ax);
+      dw_store(P.C + (int64_t)(m0 + mm) * P.ldc + j, v, ax, P.accumulate != 0);
     }
   }
 }
@@ -803,7 +805,7 @@ __device__ __forceinline__ void dw_tile_colsum(const GemmProb& P, float* red, in
     s3 += P.B[(int64_t)(k + 3) * P.ldb + n];
   }
   for (; k < P.K; ++k) s0 += P.B[(int64_t)k * P.ldb + n];
-  dw_store(P.C + n, (s0 + s1) + (s2 + s3), ax);
+  dw_store(P.C + n, (s0 + s1) + (s2 + s3), ax, P.accumulate != 0);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 3)
@@ -838,8 +840,14 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     for (int i = threadIdx.x; i < (int)(sizeof(GemmProb) / 4); i += GEMM_THREADS) dst[i] = src[i];
   }
   __syncthreads();
-  if (T.parity_stride > 0 && threadIdx.x == 0) Ps.C += ((st + 1) & 1) * T.parity_stride;
-  if (T.parity_stride > 0) __syncthreads();
+  if (threadIdx.x == 0) {
+    // several workers per rank (19-worker-equivalent batches): the device counter counts micro-batches,
+    // update u = st / micro, launch j = st % micro of it adds its gradient to the sum of launches 0..j-1
+    const long long u = st / T.micro, j = st - u * T.micro;
+    if (T.parity_stride > 0) Ps.C += ((u + 1) & 1) * T.parity_stride;
+    Ps.accumulate = j > 0 ? 1 : 0;
+  }
+  __syncthreads();
   {
     const GemmProb& P = Ps;
     const AdamCtx* axp = T.ax.theta != nullptr ? &ax : nullptr;
@@ -1133,6 +1141,9 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   T.ticket = w.ticket; T.loss_part = w.loss_part; T.n_clusters = (int)n_ctas; T.n = n; T.dimu = d->dimu;
   T.action_l2 = h->action_l2; T.q_loss = q_loss; T.pi_loss = pi_loss;
   T.parity_stride = h->grads_parity_stride;
+  T.micro = h->micro_batches > 1 ? h->micro_batches : 1;
+  CUR_REQUIRE(T.micro == 1 || (h->step_counter != nullptr && adam == nullptr),
+              "several micro-batches per update need the step counter and exclude the fused Adam epilogue");
   CUR_REQUIRE(T.parity_stride == 0 || (h->step_counter != nullptr && adam == nullptr),
               "gradient double buffering needs the step counter and excludes the fused Adam epilogue");
   static bool dw_configured = false;

@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
             float* __restrict__ v, int64_t n, float neg_a, const float* __restrict__ table, int table_len,
             const int64_t* __restrict__ step_counter, float b1, float omb1, float b2, float omb2, float eps,
-            float grad_div) {
+            float grad_div, int step_div) {
   if (kTable) {
-    long long t = *step_counter;                 // 1-based: already bumped for this step
+    long long t = *step_counter / step_div;      // 1-based: already bumped for this step
     if (t < 1) t = 1;
     neg_a = table[(t <= table_len ? t : (long long)table_len) - 1];
   }
@@ -247,7 +247,7 @@ extern "C" int cur_adam_step(void* stream, float* theta, const float* grad, floa
   // python-float (1 - beta) rounded to float32, as NumPy does for a python scalar times a float32 array
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   adam_kernel<false><<<grid_for(n / 4 + 1, 256, 2), 256, 0, (cudaStream_t)stream>>>(
-      theta, grad, m, v, n, neg_a, nullptr, 0, nullptr, (float)beta1, omb1, (float)beta2, omb2, (float)eps, grad_div);
+      theta, grad, m, v, n, neg_a, nullptr, 0, nullptr, (float)beta1, omb1, (float)beta2, omb2, (float)eps, grad_div, 1);
   CUR_CHECK_LAUNCH();
   return CUR_OK;
 }
@@ -255,7 +255,7 @@ extern "C" int cur_adam_step(void* stream, float* theta, const float* grad, floa
 extern "C" int cur_adam_step_graph(void* stream, float* theta, const float* grad, float* m, float* v,
                                    int64_t n, const float* neg_a_table, int table_len,
                                    const int64_t* step_counter, double beta1, double beta2, double eps,
-                                   float grad_div) {
+                                   float grad_div, int32_t step_div) {
   CUR_REQUIRE(theta && grad && m && v && neg_a_table && step_counter, "NULL argument");
   CUR_REQUIRE(n >= 0 && table_len > 0, "bad sizes");
   if (n == 0) return CUR_OK;
@@ -264,7 +264,7 @@ extern "C" int cur_adam_step_graph(void* stream, float* theta, const float* grad
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   adam_kernel<true><<<grid_for(n / 4 + 1, 256, 2), 256, 0, (cudaStream_t)stream>>>(
       theta, grad, m, v, n, 0.f, neg_a_table, table_len, step_counter, (float)beta1, omb1, (float)beta2, omb2,
-      (float)eps, grad_div);
+      (float)eps, grad_div, step_div > 1 ? step_div : 1);
   CUR_CHECK_LAUNCH();
   return CUR_OK;
 }

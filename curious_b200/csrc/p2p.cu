@@ -42,7 +42,8 @@ struct P2PParams {
   float *theta, *m, *v;
   const float* neg_a_table;
   int table_len;
-  const int64_t* step_counter;                  // already bumped for this update (Adam's 1-based t)
+  const int64_t* step_counter;                  // already bumped for this update (Adam's 1-based t = counter / step_div)
+  int step_div;
   float b1, omb1, b2, omb2, eps;
   int* error_flag;                              // set to 1 if the peers did not show up in time
 };
@@ -63,7 +64,7 @@ __device__ __forceinline__ float4 ld_peer_f4(const float4* p) {
 
 __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(const __grid_constant__ P2PParams P) {
   __shared__ int s_ok;
-  const long long t = *P.step_counter;                         // update number, 1-based
+  const long long t = *P.step_counter / P.step_div;            // update number, 1-based
   const unsigned long long want = (unsigned long long)t;
   if (blockIdx.x == 0 && threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
     // my gradient of update t was written by the previous kernel on this stream: publish
@@ -130,7 +131,7 @@ __device__ __forceinline__ bool wait_flags(const unsigned long long* flags, int 
 }
 
 __global__ void __launch_bounds__(256) p2p_sharded_adam_kernel(const __grid_constant__ P2PParams P) {
-  const long long t = *P.step_counter;                         // update number, 1-based
+  const long long t = *P.step_counter / P.step_div;            // update number, 1-based
   const unsigned long long want = (unsigned long long)t;
   unsigned char* own = const_cast<unsigned char*>(P.region[P.rank]);
   unsigned long long* own_flags = reinterpret_cast<unsigned long long*>(own);
@@ -241,7 +242,7 @@ static int p2p_launch(void* stream, const cur_p2p_ctx* ctx, float* theta, float*
     P.region[r] = reinterpret_cast<const unsigned char*>(ctx->region[r]);
   }
   P.theta = theta; P.m = m; P.v = v; P.neg_a_table = neg_a_table; P.table_len = table_len;
-  P.step_counter = step_counter;
+  P.step_counter = step_counter; P.step_div = ctx->step_div > 1 ? ctx->step_div : 1;
   P.b1 = (float)beta1; P.omb1 = (float)(1.0 - beta1); P.b2 = (float)beta2; P.omb2 = (float)(1.0 - beta2);
   P.eps = (float)eps; P.error_flag = error_flag;
   const int64_t n4 = ctx->arena >> 2;

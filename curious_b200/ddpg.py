@@ -69,6 +69,11 @@ class DDPG(object):
         # by loads, Adam on the own slice, all-gather by stores, 'nccl' = NCCL all-reduce + Adam launch after the
         # graph, 'auto' = p2p when the rows schedule runs on an NCCL (one GPU per rank) group
         self.grad_exchange = kwargs.get('grad_exchange', 'auto')
+        # reference workers hosted by this rank (the 19 MPI workers become ceil(19 / G) workers per GPU):
+        # every update is the SUM of `workers_per_rank` batch-256 gradients, each with its own loss mean, exactly what
+        # the reference's SUM all-reduce over that many single-batch workers produces (ddpg.py:452-453)
+        self.workers_per_rank = int(kwargs.get('workers_per_rank', 1))
+        assert self.workers_per_rank >= 1
         self.create_actor_critic = import_function(self.network_class)
 
         self.dimo = self.input_dims['o']
@@ -508,7 +513,10 @@ class DDPG(object):
         self._gbatch = {k: torch.empty((B, dims[k]), dtype=torch.float32, device=dev) for k in want}
         self._gwant = tuple(want)
         self._ghyper = _lib.DdpgHyper(self._hyper.gamma, self._hyper.clip_return, self._hyper.action_l2,
-                                      self._hyper.clip_pos_returns, self._step.data_ptr(), self.LOSS_RING, 0)
+                                      self._hyper.clip_pos_returns, self._step.data_ptr(), self.LOSS_RING,
+                                      self.workers_per_rank if self.workers_per_rank > 1 else 0)
+        if self.workers_per_rank > 1 and not self._use_rows(B):
+            raise ValueError('workers_per_rank > 1 on the CUDA-graph path needs the rows schedule')
         self._workspace_rows(B) if self._use_rows(B) else self._workspace(B)
         self._peer = None
         if self._want_peer_exchange():
@@ -516,6 +524,7 @@ class DDPG(object):
             # the sharded exchange moves 8x fewer bytes at 8 GPUs but measured no faster (2 GPUs: 83 us full / 91 us
             # sharded, 8 GPUs: 97.3 / 98.2): the exchange is latency / straggler bound, so the one-round kernel is default
             self._peer = PeerGradExchange(self.net.arena, self.comm, sharded=self.grad_exchange == 'p2p_sharded')
+            self._peer.ctx.step_div = self.workers_per_rank
             self._ghyper.grads_parity_stride = self.net.arena
         self._graph_sig = None
         self._refresh_dyn()
@@ -596,16 +605,21 @@ class DDPG(object):
         if self._use_rows(n):
             # with one rank there is no all-reduce between _grads and _update: Adam runs in the epilogue of
             # the weight-gradient launch (2 launches per update after the HER kernel)
-            fuse = self._same_rule() and _world(self.comm)[1] == 1
+            fuse = self._same_rule() and _world(self.comm)[1] == 1 and self.workers_per_rank == 1
             adam = _lib.AdamFused(self._adam_m.data_ptr(), self._adam_v.data_ptr(), self._adam_tables[0].data_ptr(),
                                   self.ADAM_TABLE, 0, qa.beta1, qa.beta2, qa.epsilon) if fuse else None
-            _lib.check(lib.cur_ddpg_rows_step(
-                _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
-                C.byref(self._stats), C.byref(cb), C.byref(self._ghyper), self._workspace_rows(n).data_ptr(),
-                self._peer.grads_ptr(0) if self._peer is not None else self.grads.data_ptr(),
-                self._q_ring.data_ptr(), self._pi_ring.data_ptr(), self._q_pi.data_ptr(),
-                C.byref(adam) if fuse else None, C.byref(her_args) if her_args is not None else None),
-                'cur_ddpg_rows_step')
+            for j in range(self.workers_per_rank):
+                if j > 0 and her_args is None:            # unfused sampling: a fresh batch for every worker
+                    sampler.sample_device(segs, self.batch_size, clip_obs=self.clip_obs,
+                                          relative_goals=self.relative_goals, want=self._gwant, out=self._gbatch,
+                                          dyn=self._dyn_dev.data_ptr(), call_offset=self.GRAPH_STREAM_OFFSET)
+                _lib.check(lib.cur_ddpg_rows_step(
+                    _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
+                    C.byref(self._stats), C.byref(cb), C.byref(self._ghyper), self._workspace_rows(n).data_ptr(),
+                    self._peer.grads_ptr(0) if self._peer is not None else self.grads.data_ptr(),
+                    self._q_ring.data_ptr(), self._pi_ring.data_ptr(), self._q_pi.data_ptr(),
+                    C.byref(adam) if fuse else None, C.byref(her_args) if her_args is not None else None),
+                    'cur_ddpg_rows_step')
             return fuse
         _lib.check(lib.cur_ddpg_grads(
             _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
@@ -625,6 +639,7 @@ class DDPG(object):
             if warmup:
                 solo = _lib.P2PCtx()
                 solo.rank, solo.world, solo.arena = 0, 1, self._peer.arena
+                solo.step_div = self.workers_per_rank
                 solo.region[0] = self._peer.own
                 _lib.check(lib.cur_p2p_allreduce_adam(
                     _lib.stream_ptr(), C.byref(solo), self.theta_main.data_ptr(), self._adam_m.data_ptr(),
@@ -641,13 +656,13 @@ class DDPG(object):
             _lib.check(lib.cur_adam_step_graph(
                 _lib.stream_ptr(), self.theta_main.data_ptr(), self.grads.data_ptr(), self._adam_m.data_ptr(),
                 self._adam_v.data_ptr(), self.theta_main.numel(), self._adam_tables[0].data_ptr(), self.ADAM_TABLE,
-                self._step.data_ptr(), qa.beta1, qa.beta2, qa.epsilon, 1.0), 'cur_adam_step_graph')
+                self._step.data_ptr(), qa.beta1, qa.beta2, qa.epsilon, 1.0, self.workers_per_rank), 'cur_adam_step_graph')
             return
         for adam, which, table in ((self.Q_adam, 'Q', self._adam_tables[0]), (self.pi_adam, 'pi', self._adam_tables[1])):
             _lib.check(lib.cur_adam_step_graph(
                 _lib.stream_ptr(), adam.theta.data_ptr(), self._view(self.grads, which).data_ptr(), adam.m.data_ptr(),
                 adam.v.data_ptr(), adam.theta.numel(), table.data_ptr(), self.ADAM_TABLE, self._step.data_ptr(),
-                adam.beta1, adam.beta2, adam.epsilon, 1.0), 'cur_adam_step_graph')
+                adam.beta1, adam.beta2, adam.epsilon, 1.0, self.workers_per_rank), 'cur_adam_step_graph')
 
     def _train_graph(self):
         if self._graph is None:
@@ -658,7 +673,8 @@ class DDPG(object):
             self.Q_adam.check_synced()
             self.pi_adam.check_synced()
         self._refresh_dyn()
-        slot = self._n_updates % self.LOSS_RING
+        k = self.workers_per_rank          # the loss of the rank's last worker (device ring slot = launch index % ring)
+        slot = (self._n_updates * k + k - 1) % self.LOSS_RING
         self._graph.replay()
         if not self._graph_has_adam:
             allreduce_sum_(self.grads, self.comm)                 # SUM, not mean (ddpg.py:452-453)
@@ -676,8 +692,17 @@ class DDPG(object):
         if stage:
             self.stage_batch()
         critic_loss, actor_loss, Q_grad, pi_grad = self._grads()
+        if self.workers_per_rank > 1:
+            # several reference workers on this rank: sum of their single-batch gradients (ddpg.py:452-453)
+            assert stage, 'workers_per_rank > 1 samples its own batches'
+            total = self.grads.clone()
+            for _ in range(self.workers_per_rank - 1):
+                self.stage_batch()
+                critic_loss, actor_loss, Q_grad, pi_grad = self._grads()
+                total += self.grads
+            self.grads.copy_(total)
         self._update(Q_grad, pi_grad)
-        self._step += 1                      # keep the device step counter in line with Adam's t
+        self._step += self.workers_per_rank   # the device counter counts sampled batches (Philox stream position)
         self._n_updates += 1
         return LazyHost(critic_loss.clone().reshape(())), LazyHost(actor_loss)
 

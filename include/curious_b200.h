@@ -202,7 +202,7 @@ int cur_adam_step(void* stream, float* theta, const float* grad, float* m, float
 int cur_adam_step_graph(void* stream, float* theta, const float* grad, float* m, float* v,
                         int64_t n, const float* neg_a_table, int table_len,
                         const int64_t* step_counter, double beta1, double beta2, double eps,
-                        float grad_div);
+                        float grad_div, int32_t step_div /* t = *step_counter / step_div; 1 normally */);
 /* target = polyak*target + (1-polyak)*main (ddpg.py:461-462); polyak == 0 is the init copy. */
 int cur_polyak(void* stream, float* target, const float* main_, int64_t n, double polyak);
 /* Order-independent 64-bit checksum of a float32 vector (for check_synced, mpi_adam.py:42-50). */
@@ -260,9 +260,14 @@ typedef struct cur_ddpg_hyper {
    * increments *step_counter (after the HER kernel of this step read it, before Adam reads it). */
   int64_t* step_counter;
   int32_t loss_ring;
-  int32_t _pad;
+  /* rows schedule only, > 1 (requires step_counter): the update is the SUM of `micro_batches` consecutive launches'
+   * gradients - several reference workers (each a batch of 256 with its own loss mean, ddpg.py:439-441) on one rank,
+   * SURVEY 8e "19-worker-equivalent".  The device counter then counts launches: launch j = counter % micro_batches
+   * overwrites the gradient for j == 0 and adds to it otherwise; consumers derive the update number as
+   * counter / micro_batches (step_div of cur_adam_step_graph / cur_p2p_ctx). */
+  int32_t micro_batches;
   /* rows schedule only: when > 0 (requires step_counter) the gradient of update s is written to
-   * grads + (s & 1) * grads_parity_stride floats, s = counter value after this update's bump
+   * grads + (s & 1) * grads_parity_stride floats, s = update number (counter / micro_batches) after this update's bump
    * (double buffering for cur_p2p_allreduce_adam).  0: always `grads`. */
   int64_t grads_parity_stride;
 } cur_ddpg_hyper;
@@ -352,6 +357,8 @@ typedef struct cur_p2p_ctx {
   int32_t rank, world;
   void* region[CUR_MAX_RANKS]; /* region[r] as mapped in this process; region[rank] is the local one */
   int64_t arena;               /* floats per gradient buffer, multiple of 4 */
+  int32_t step_div;            /* update number = *step_counter / step_div (cur_ddpg_hyper.micro_batches); 0 or 1: none */
+  int32_t _pad;
 } cur_p2p_ctx;
 
 int64_t cur_p2p_region_bytes(int64_t arena_floats);

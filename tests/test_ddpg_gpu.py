@@ -405,3 +405,61 @@ def test_task_experts_grouped_update_equals_sequential(batch_size, use_graph):
         assert a.Q_adam.t == b.Q_adam.t == 4
     # different experts do learn different things
     assert not torch.equal(grp[0].theta_main, grp[1].theta_main)
+
+
+def test_workers_per_rank_sums_single_batch_gradients():
+    """the reference's 19 MPI workers become ceil(19 / G) workers per GPU.  `workers_per_rank=k` makes one
+    update the SUM of k batch-256 gradients, each with its own loss mean - what MpiAdam's SUM all-reduce over k
+    single-batch workers produces (mpi_adam.py:24-28 with scale_grad_by_procs=False, ddpg.py:452-453).
+      (1) eager path with the reference's np.random draws == oracle emulating k workers (Adam fed the summed gradient)
+      (2) CUDA-graph path (k launches accumulating in the weight-gradient epilogue, Adam's t = counter / k)
+          == eager path, bit for bit, on the same Philox stream."""
+    import torch
+    from curious_b200.ddpg import DDPG
+    from oracle.ddpg_oracle import unflatten
+    k = 3
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4)
+    cp = np.array([0.05, 0.2, 0.1, 0.0])
+    episodes = episode_stream(dims, kw['T'], 8)
+    # ---- (1) against the oracle
+    ora = make_oracle_agent(kw, dims, ag_ids, g_ids)
+    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy', workers_per_rank=k)
+    for a in (ora, gpu):
+        np.random.seed(11)
+        _fill(a, episodes, cp)
+    for step in range(3):
+        np.random.seed(500 + step)
+        outs = [ora.grads(ora.sample_batch()) for _ in range(k)]
+        gq = np.sum([o['Q_grad'] for o in outs], axis=0, dtype=np.float32)
+        gp = np.sum([o['pi_grad'] for o in outs], axis=0, dtype=np.float32)
+        np.random.seed(500 + step)
+        gpu.train()
+        tol = GRAD_RTOL if min(o['relu_margin'] for o in outs) > 2e-6 else 2e-3
+        assert rel_err(gpu._view(gpu.grads, 'Q').cpu().numpy(), gq) <= tol
+        assert rel_err(gpu._view(gpu.grads, 'pi').cpu().numpy(), gp) <= tol
+        # keep both sides on the oracle's trajectory (see the module docstring about Adam and tiny gradients)
+        ora.main_Q = unflatten(ora.Q_adam.update(gq, ora.Q_lr), ora.ac.Q_shapes)
+        ora.main_pi = unflatten(ora.pi_adam.update(gp, ora.pi_lr), ora.ac.pi_shapes)
+        gpu.set_flat('Q', ora.Q_adam.theta)
+        gpu.set_flat('pi', ora.pi_adam.theta)
+        gpu.Q_adam.m.copy_(torch.from_numpy(ora.Q_adam.m).cuda()); gpu.Q_adam.v.copy_(torch.from_numpy(ora.Q_adam.v).cuda())
+        gpu.pi_adam.m.copy_(torch.from_numpy(ora.pi_adam.m).cuda()); gpu.pi_adam.v.copy_(torch.from_numpy(ora.pi_adam.v).cuda())
+    assert gpu.Q_adam.t == ora.Q_adam.t == 3 and int(gpu._step.item()) == 3 * k
+    # ---- (2) graph == eager
+    agents = []
+    for use_graph in (True, False):
+        ag = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', use_cuda_graph=use_graph, workers_per_rank=k)
+        np.random.seed(4)
+        _fill(ag, episodes, cp)
+        agents.append(ag)
+    g, e = agents
+    e.sample_transitions.calls = DDPG.GRAPH_STREAM_OFFSET
+    for step in range(5):
+        lg, qg = g.train()
+        le, qe = e.train()
+        assert float(lg) == float(le), step
+        assert np.array_equal(np.asarray(qg), np.asarray(qe)), step
+    for which in ('Q', 'pi'):
+        assert np.array_equal(g.get_flat(which), e.get_flat(which)), which
+    assert torch.equal(g.Q_adam.m, e.Q_adam.m) and torch.equal(g.pi_adam.v, e.pi_adam.v)
+    assert int(g._step.item()) == int(e._step.item()) == 5 * k and g.Q_adam.t == 5

@@ -26,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto'):
+def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto', workers_per_rank=1):
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -41,7 +41,7 @@ def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto'):
         kw, dims, ag_ids, g_ids = ddpg_kwargs(4)
         # rank 1 starts from different weights: _sync_optimizers must broadcast rank 0's (ddpg.py:466)
         agent = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', seed=rank, use_cuda_graph=use_graph,
-                               device=dev, grad_exchange=grad_exchange)
+                               device=dev, grad_exchange=grad_exchange, workers_per_rank=workers_per_rank)
         assert parallel.world(agent.comm)[1] == world
         theta0 = agent.theta_main.clone()
         gathered = [torch.empty_like(theta0) for _ in range(world)]
@@ -56,7 +56,7 @@ def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto'):
         st = torch.cat([agent.o_stats.mean, agent.o_stats.std, agent.g_stats.mean, agent.g_stats.std])
         parallel.assert_synced(st)
 
-        if not use_graph:
+        if not use_graph and workers_per_rank == 1:
             # one eager update, dissected: local grads -> all-gather -> expected Adam(sum) on a clone
             agent.stage_batch()
             agent._grads()
@@ -109,3 +109,21 @@ def test_peer_memory_exchange_equals_nccl_allreduce(tmp_path):
         assert np.array_equal(thetas[mode][0], thetas[mode][1])
     assert np.array_equal(thetas['p2p'][0], thetas['nccl'][0])
     assert np.array_equal(thetas['p2p_sharded'][0], thetas['nccl'][0])
+
+
+def test_two_ranks_with_two_workers_each(tmp_path):
+    """4-worker-equivalent on 2 GPUs: every rank sums the gradients of its 2 batch-256 workers in the
+    weight-gradient epilogue, the peer-memory kernel sums the ranks and steps Adam with t = launches / 2; the NCCL
+    path (all-reduce + Adam launch after the graph) must land on the same parameters bit for bit.  (The
+    launch-by-launch path draws from a different Philox offset here; its equality with the graph path is covered on
+    one GPU by test_workers_per_rank_sums_single_batch_gradients.)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    thetas = {}
+    for mode, graph in (('p2p', True), ('nccl', True)):
+        d = tmp_path / ('%s_%d' % (mode, graph))
+        d.mkdir()
+        mp.spawn(_worker, args=(2, _free_port(), graph, str(d), mode, 2), nprocs=2, join=True)
+        thetas[(mode, graph)] = [np.load(os.path.join(str(d), 'theta%d.npy' % r)) for r in range(2)]
+        assert np.array_equal(thetas[(mode, graph)][0], thetas[(mode, graph)][1])
+    assert np.array_equal(thetas[('p2p', True)][0], thetas[('nccl', True)][0])
