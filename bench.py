@@ -246,6 +246,43 @@ def large_batch_sweep(agent, dims, torch):
     return {'batch_sweep': sweep, 'task_experts': experts, 'tf32_peak_tflops_assumed': bf16 / 2}
 
 
+def her_arm8_line(device, torch):
+    """BASELINE config 4 shape: MultiTaskFetchArm8-v5 (4 distractor modules; buffers 6..8 alias 5, ddpg.py:107-110),
+    dimo=64, dimg=dimag=24, N=8 -> 1340 algorithmic bytes per transition.  Same fused kernel, same launch."""
+    from curious_b200 import apportion, her, synth
+    from curious_b200.replay_buffer import ReplayBuffer
+    from curious_b200.reward import ModuleDistanceReward
+    n_mod = 8
+    dims = synth.arm_dims(n_mod)
+    ag_ids, g_ids = synth.arm_task_ids(n_mod)
+    sampler = her.make_sample_multi_task_her_transitions('her', 4, 'replay_task_cp_buffer',
+                                                         ModuleDistanceReward(ag_ids, g_ids), tasks_ag_id=ag_ids,
+                                                         tasks_g_id=g_ids)
+    sampler.rng = 'philox'
+    sampler.seed = 5
+    shapes = synth.buffer_shapes(dims, T)
+    buffers = [ReplayBuffer(shapes, BUFFER_TRANSITIONS if 0 < i <= 5 else T, T, sampler, device=device) for i in range(6)]
+    for i in range(1, 6):
+        fill_buffer_on_device(buffers[i], dims, 700 + i)
+    buffers += [buffers[5]] * 3                                       # distractor modules share one buffer
+    cp = np.array([0.05, 0.2, 0.1, 0.0, 0.0, 0.0, 0.0, 0.0])
+    sizes = [b.current_size for b in buffers]
+    prop = apportion.proportions_curious(sizes, T, ROWS_PER_STEP, 'replay_task_cp_buffer', cp, EPS_TASK)
+    segs = [(buffers[i].device_view(), int(prop[i]), i - 1) for i in range(1, len(buffers)) if prop[i] > 0]
+    out = {}
+    want = ('o', 'g', 'u', 'td', 'o_2', 'r')
+    ms = time_updates(lambda: sampler.sample_device(segs, ROWS_PER_STEP, clip_obs=200.0, want=want, out=out), 20, torch)
+    bpt = algorithmic_bytes_per_transition(dims, n_mod)
+    peak, _ = measured_peak_hbm()
+    achieved = bpt * ROWS_PER_STEP / (ms * 1e-3) / 1e9
+    del buffers, out
+    torch.cuda.empty_cache()
+    return {'transitions_per_s': ROWS_PER_STEP / (ms * 1e-3), 'ms_per_launch': ms, 'algorithmic_bytes_per_transition': bpt,
+            'achieved_gbs': achieved, 'frac_of_hbm_peak': achieved / peak,
+            'workload': 'arm8-shaped: 5 distinct module buffers x 1e6 transitions (dimo=64, dimg=24, dimu=4, N=8), '
+                        '%d rows per launch' % ROWS_PER_STEP}
+
+
 def her_step_segments(buffers, rows):
     from curious_b200 import apportion
     sizes = [b.current_size for b in buffers]
@@ -512,6 +549,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_sweep:
             line['ddpg_update'] = large_batch_sweep(agent, dims, torch)
+            line['her_arm8'] = her_arm8_line(device, torch)
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_sampler_baseline()
         print(json.dumps(line))

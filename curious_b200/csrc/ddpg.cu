@@ -34,6 +34,8 @@ struct Workspace {
   // tensor-core path (large batch only): split-K partial tiles / partial row reductions, TC_SLOTS problems per level
   float *tc_part, *tc_rowpart;
   int64_t tc_part_stride, tc_rowpart_stride;
+  float* loss_part;                // multi-CTA loss (large batch): LOSS_MAX_CTAS x 4 partial sums
+  unsigned int* loss_ticket;       // self-resetting completion ticket (the workspace is zero-initialised by the caller)
   int64_t total;
 };
 
@@ -42,6 +44,8 @@ struct Workspace {
 // 2048: 556 / 420, 4096: 1161 / 479, 16384: 4130 / 1038).  CUR_DDPG_TC=0 or cur_ddpg_set_tensor_cores(0) forces the
 // FFMA path, cur_ddpg_set_tensor_cores(1) forces the tensor cores for every eligible shape (A/B measurements, tests).
 constexpr int64_t TC_MIN_BATCH = 2048;
+constexpr int LOSS_MAX_CTAS = 128;
+constexpr int64_t LOSS_MC_MIN_BATCH = 2048;   // from here the loss / backward-seed kernel runs on several CTAs
 constexpr int TC_SLOTS = 3;          // split-K weight gradients / row reductions per dependency level
 static int g_tc_mode = -1;          // -1: environment (default on), 0: off, 1: on  (cur_ddpg_set_tensor_cores)
 static bool tc_enabled() {
@@ -96,6 +100,8 @@ static Workspace carve(const cur_net_desc& d, int64_t n, float* base) {
     w.da[i] = take(n * w.H);
     w.dp[i] = take(n * w.H);
   }
+  w.loss_ticket = reinterpret_cast<unsigned int*>(take(4));
+  w.loss_part = take(LOSS_MAX_CTAS * 4);
   w.tc_part = w.tc_rowpart = nullptr;
   w.tc_part_stride = w.tc_rowpart_stride = 0;
   if (tc_shape_ok(d, n)) {      // carved whenever the shape is eligible: the workspace size does not depend on the toggle
@@ -258,8 +264,70 @@ __global__ void __launch_bounds__(1024) loss_kernel(const __grid_constant__ Loss
   }
 }
 
+// Same computation on several CTAs (batch >= LOSS_MC_MIN_BATCH; one CTA takes 53 us at batch 16384): every CTA reduces a
+// contiguous slice of rows, the last one to finish (ticket) folds the per-CTA partials in CTA order - deterministic.
+struct LossMcParams {
+  LossParams L;
+  float* part;
+  unsigned int* ticket;
+};
+__global__ void __launch_bounds__(512) loss_mc_kernel(const __grid_constant__ LossMcParams M) {
+  const LossParams& P = M.L;
+  __shared__ float red[3][16];
+  __shared__ unsigned int s_last;
+  const int64_t per = (P.n + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = per * blockIdx.x, r1 = (r0 + per < P.n) ? r0 + per : P.n;
+  float ssq = 0.f, sq = 0.f, sth = 0.f;
+  const float inv_n = 1.0f / (float)P.n;
+  const float hi = P.clip_pos ? 0.f : INFINITY;
+  for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+    float tgt = fminf(fmaxf(P.r[i] + P.gamma * P.Qt[i], -P.clip_return), hi);   // ddpg.py:436-438
+    float diff = tgt - P.Q[i];
+    ssq += diff * diff;
+    sq += P.Qpi[i];
+    P.dQ[i] = -2.0f * inv_n * diff;
+    P.dQpi[i] = -inv_n;
+    for (int j = 0; j < P.dimu; ++j) {
+      const float t = P.th[i * P.ldth + j];
+      sth += t * t;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    sth += __shfl_xor_sync(0xffffffffu, sth, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = ssq; red[1][w] = sq; red[2][w] = sth; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; b += red[1][i]; c += red[2][i]; }
+    M.part[4 * blockIdx.x + 0] = a; M.part[4 * blockIdx.x + 1] = b; M.part[4 * blockIdx.x + 2] = c;
+    __threadfence();
+    s_last = (atomicAdd(M.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int i = 0; i < (int)gridDim.x; ++i) {
+      a += ((volatile float*)M.part)[4 * i + 0]; b += ((volatile float*)M.part)[4 * i + 1]; c += ((volatile float*)M.part)[4 * i + 2];
+    }
+    long long slot = 0;
+    if (P.step_counter) {
+      const long long st = *P.step_counter;
+      slot = P.ring > 0 ? st % P.ring : 0;
+      *P.step_counter = st + 1;
+    }
+    if (P.q_loss) P.q_loss[slot] = a * inv_n;                                           // ddpg.py:439
+    if (P.pi_loss) P.pi_loss[slot] = -b * inv_n + P.action_l2 * c / (float)(P.n * P.dimu);   // :440-441
+    *M.ticket = 0u;
+  }
+}
+
 // One dependency level: problems that fit the tensor-core kernel go there when the batch is large, everything else
-// (first / output layers, small batches) to the FFMA grouped kernel.  Both launches of a level are independent.
+// (output layers at small batch, batches below the crossover) to the FFMA grouped kernel.
 struct Batcher {
   GemmBatch G;
   TcLauncher T;
@@ -278,6 +346,11 @@ struct Batcher {
     G.n = 0; G.total_tiles = 0;
   }
   void add(const GemmProb& p) {
+    if (tc && tc_skinny_supported(p)) {               // before the tensor-core test: K <= 4 outer products fit both
+      const int r = T.add_skinny(p);
+      if (r != CUR_OK) rc = r;
+      return;
+    }
     if (tc && !p.ones_a && tc_supported(p)) {
       const bool split = tc_pick_splits(p) > 1;
       if (!split || (parts_used < TC_SLOTS && tc_partial_floats(p) <= part_stride)) {
@@ -427,7 +500,7 @@ struct GroupBatcher {
     // flush early when a launch is full (many experts): problems of one level are independent, so splitting a level
     // over several launches is always legal
     if (B.G.n >= GEMM_MAX_PROBS - 1 || B.T.G.n >= TC_MAX_PROBS - 1 || B.T.R.n >= 2 * TC_MAX_PROBS - 2 ||
-        B.T.n_rowred >= TC_MAX_PROBS - 1)
+        B.T.n_rowred >= TC_MAX_PROBS - 1 || B.T.n_skinny >= TC_MAX_PROBS - 1)
       CUR_TRY(flush());
     Expert& x = e[i];
     B.tc_part = x.w.tc_part; B.tc_rowpart = x.w.tc_rowpart;
@@ -522,7 +595,15 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
     LPm.n = n; LPm.gamma = x.h->gamma; LPm.clip_return = x.h->clip_return; LPm.action_l2 = x.h->action_l2;
     LPm.clip_pos = x.h->clip_pos_returns; LPm.dQ = w.dQ; LPm.dQpi = w.dQpi; LPm.q_loss = x.q_loss; LPm.pi_loss = x.pi_loss;
     LPm.step_counter = x.h->step_counter; LPm.ring = x.h->loss_ring;
-    loss_kernel<<<1, 1024, 0, s>>>(LPm);
+    if (n >= LOSS_MC_MIN_BATCH) {
+      LossMcParams MC;
+      MC.L = LPm; MC.part = w.loss_part; MC.ticket = w.loss_ticket;
+      int ctas = (int)((n + 511) / 512);
+      if (ctas > LOSS_MAX_CTAS) ctas = LOSS_MAX_CTAS;
+      loss_mc_kernel<<<ctas, 512, 0, s>>>(MC);
+    } else {
+      loss_kernel<<<1, 1024, 0, s>>>(LPm);
+    }
     CUR_CHECK_LAUNCH();
   }
 

@@ -392,8 +392,17 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(const __grid_constant__ 
   const int64_t i4 = (int64_t)(blockIdx.x - P.block_begin) * 256 + threadIdx.x;
   if (i4 * 4 >= P.count) return;
   if (P.vec) {
+    // fixed order s = 0, 1, 2, ...; the loads of 8 slices are issued together (the loop is latency-bound otherwise)
     float4 acc = *reinterpret_cast<const float4*>(P.part + i4 * 4);
-    for (int s = 1; s < P.splits; ++s) {
+    int s = 1;
+    for (; s + 7 < P.splits; s += 8) {
+      float4 x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = *reinterpret_cast<const float4*>(P.part + (int64_t)(s + u) * P.stride + i4 * 4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w; }
+    }
+    for (; s < P.splits; ++s) {
       const float4 x = *reinterpret_cast<const float4*>(P.part + (int64_t)s * P.stride + i4 * 4);
       acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
     }
@@ -415,12 +424,23 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(const __grid_constant__ 
 struct RowRed {
   const float* X; int64_t ldx; const float* Y; int64_t ldy;
   int64_t rows; int M, NJ; float* part;
+  int col_blocks, block_begin;
 };
-__global__ void __launch_bounds__(256) tc_rowred_kernel(const __grid_constant__ RowRed P) {
+struct RowRedBatch {
+  RowRed p[TC_MAX_PROBS];
+  int n;
+};
+__global__ void __launch_bounds__(256) tc_rowred_kernel(const __grid_constant__ RowRedBatch R) {
   __shared__ float red[16][16][4 * 4 + 1];
+  int pi = 0;
+#pragma unroll 1
+  while (pi + 1 < R.n && (int)blockIdx.x >= R.p[pi + 1].block_begin) ++pi;
+  const RowRed& P = R.p[pi];
+  const int lb = blockIdx.x - P.block_begin;
+  const int cb = lb % P.col_blocks;
   const int cq = threadIdx.x & 15, rl = threadIdx.x >> 4;
-  const int m = blockIdx.x * 64 + 4 * cq;
-  const int chunk = blockIdx.y;
+  const int m = cb * 64 + 4 * cq;
+  const int chunk = lb / P.col_blocks;
   const int64_t r0 = (int64_t)chunk * TC_COLSUM_ROWS;
   const int64_t r1 = r0 + TC_COLSUM_ROWS < P.rows ? r0 + TC_COLSUM_ROWS : P.rows;
   const int NJ = P.Y ? P.NJ : 1;
@@ -463,8 +483,132 @@ __global__ void __launch_bounds__(256) tc_rowred_kernel(const __grid_constant__ 
   float sum = 0.f;
 #pragma unroll
   for (int l = 0; l < 16; ++l) sum += red[l][cq][slot];
-  const int mm = blockIdx.x * 64 + 4 * cq + i;
+  const int mm = cb * 64 + 4 * cq + i;
   if (mm < P.M && j < NJ) P.part[((int64_t)chunk * P.M + mm) * NJ + j] = sum;
+}
+
+// Skinny problems of the large-batch schedule (M = batch rows, one of N / K is <= 4): bandwidth-bound streams that the
+// 32x32-tile FFMA kernel runs at a few percent of HBM speed (scalar generic path).  One grouped launch per level.
+//   SK_ROWDOT  out[r][j] = epi( sum_k X[r][k] W(k, j) + b[j] ), N <= 4, K <= 1024: output layers (util.py:65-71,
+//              N = 1 critic / dimu actor, tanh) and the action gradient d pi_loss / d(pre-tanh) (ddpg.py:440-447)
+//   SK_OUTER   dX[r][c] = mask(aux[r][c]) * sum_{j<K} dY[r][j] W[c][j], K <= 4: backward through the output layers
+enum { SK_ROWDOT = 0, SK_OUTER = 1 };
+struct Skinny {
+  int kind;
+  const float* X; int64_t ldx;       // ROWDOT: X [M][K];          OUTER: dY [M][K]
+  const float* W; int64_t ldw; int w_nk;   // ROWDOT: W [K][N] (w_nk = 0) or [N][K] (w_nk = 1);  OUTER: W [N][K]
+  const float* bias;
+  const float* aux; int64_t ldaux;
+  float* C; int64_t ldc;
+  int M, N, K, epi;
+  float coef;
+  int block_begin, blocks;
+};
+struct SkinnyBatch {
+  Skinny p[TC_MAX_PROBS];
+  int n;
+};
+constexpr int SK_ROWS_PER_BLOCK = 64;   // ROWDOT: 8 warps x 8 rows; OUTER: 64 rows x N columns per block
+
+__global__ void __launch_bounds__(256) tc_skinny_kernel(const __grid_constant__ SkinnyBatch S) {
+  __shared__ __align__(16) float wsm[4 * 1024];
+  int pi = 0;
+#pragma unroll 1
+  while (pi + 1 < S.n && (int)blockIdx.x >= S.p[pi + 1].block_begin) ++pi;
+  const Skinny& P = S.p[pi];
+  const int lb = blockIdx.x - P.block_begin;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (P.kind == SK_ROWDOT) {
+    // weights as [j][k] in shared memory
+    for (int i = threadIdx.x; i < P.N * P.K; i += 256) {
+      const int j = i / P.K, k = i - j * P.K;
+      wsm[j * P.K + k] = P.w_nk ? P.W[(int64_t)j * P.ldw + k] : P.W[(int64_t)k * P.ldw + j];
+    }
+    __syncthreads();
+    const int64_t r0 = (int64_t)lb * SK_ROWS_PER_BLOCK + warp * 8;
+    const int k4 = P.K >> 2;
+#pragma unroll 1
+    for (int rr = 0; rr < 8; rr += 4) {
+      float acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[a][j] = 0.f;
+      for (int q = lane; q < k4; q += 32) {
+        float4 x[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int64_t r = r0 + rr + a;
+          x[a] = r < P.M ? *reinterpret_cast<const float4*>(P.X + r * P.ldx + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < P.N) {
+            const float4 w = *reinterpret_cast<const float4*>(wsm + j * P.K + 4 * q);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              acc[a][j] = fmaf(x[a].w, w.w, fmaf(x[a].z, w.z, fmaf(x[a].y, w.y, fmaf(x[a].x, w.x, acc[a][j]))));
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc[a][j] += __shfl_xor_sync(0xffffffffu, acc[a][j], o);
+      // lane 4 a + j writes output (row a, column j)
+      const int a = lane >> 2, j = lane & 3;
+      if (lane < 16 && j < P.N) {
+        const int64_t r = r0 + rr + a;
+        if (r < P.M) {
+          float v = 0.f;
+#pragma unroll
+          for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              if (aa == a && jj == j) v = acc[aa][jj];
+          if (P.bias) v += P.bias[j];
+          if (P.epi == EPI_TANH) v = tanhf(v);
+          else if (P.epi == EPI_ACTOR_DY) {
+            const float th = P.aux[r * P.ldaux + j];
+            v = (v + P.coef * th) * (1.f - th * th);
+          }
+          P.C[r * P.ldc + j] = v;
+        }
+      }
+    }
+  } else {
+    // OUTER: weights [c][j] (j < K <= 4) in shared memory, padded to 4 per column
+    for (int i = threadIdx.x; i < P.N * 4; i += 256) {
+      const int c = i >> 2, j = i & 3;
+      wsm[i] = j < P.K ? P.W[(int64_t)c * P.ldw + j] : 0.f;
+    }
+    __syncthreads();
+    const int n4 = P.N >> 2;
+    const int64_t r0 = (int64_t)lb * SK_ROWS_PER_BLOCK;
+    for (int i = threadIdx.x; i < SK_ROWS_PER_BLOCK * n4; i += 256) {
+      const int64_t r = r0 + i / n4;
+      const int c4 = i % n4;
+      if (r >= P.M) break;
+      float y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = j < P.K ? P.X[r * P.ldx + j] : 0.f;
+      float o[4];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float4 w = *reinterpret_cast<const float4*>(wsm + (4 * c4 + cc) * 4);
+        // same association as a K-loop: ((y0 w0 + y1 w1) + y2 w2) + y3 w3
+        o[cc] = fmaf(y[3], w.w, fmaf(y[2], w.z, fmaf(y[1], w.y, y[0] * w.x)));
+      }
+      float4 v = make_float4(o[0], o[1], o[2], o[3]);
+      if (P.epi == EPI_RELU_MASK) {
+        const float4 a = *reinterpret_cast<const float4*>(P.aux + r * P.ldaux + 4 * c4);
+        v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(P.C + r * P.ldc + 4 * c4) = v;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -591,6 +735,26 @@ int TcLauncher::add_rowred(const float* X, int64_t ldx, int M, const float* Y, i
   return CUR_OK;
 }
 
+bool tc_skinny_supported(const GemmProb& p) {
+  if (p.ones_a || p.a_trans || p.K2 != 0 || p.C2 != nullptr || p.M <= 0) return false;
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (p.N <= 4 && p.N >= 1 && p.K >= 4 && p.K <= 1024 && (p.K % 4) == 0 && (p.lda % 4) == 0 && al(p.A) &&
+      (p.epi == EPI_NONE || p.epi == EPI_TANH || p.epi == EPI_ACTOR_DY))
+    return true;                                                        // SK_ROWDOT
+  if (p.b_trans && p.K >= 1 && p.K <= 4 && p.N >= 4 && p.N <= 1024 && (p.N % 4) == 0 && (p.ldc % 4) == 0 && al(p.C) &&
+      p.bias == nullptr && (p.epi == EPI_NONE || (p.epi == EPI_RELU_MASK && al(p.aux) && (p.ldaux % 4) == 0)))
+    return true;                                                        // SK_OUTER
+  return false;
+}
+
+int TcLauncher::add_skinny(const GemmProb& p) {
+  CUR_REQUIRE(tc_skinny_supported(p), "problem does not fit the skinny kernels");
+  CUR_REQUIRE(n_skinny < TC_MAX_PROBS, "too many skinny problems");
+  SkinnyDesc& q = skinny[n_skinny++];
+  q.p = p;
+  return CUR_OK;
+}
+
 int64_t tc_rowred_partial_floats(int64_t rows, int M, int NJ) {
   return ((rows + TC_COLSUM_ROWS - 1) / TC_COLSUM_ROWS) * (int64_t)M * (NJ < 1 ? 1 : NJ);
 }
@@ -607,12 +771,39 @@ int TcLauncher::flush(cudaStream_t s) {
     tc_gemm_kernel<<<G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s>>>(B);
     CUR_CHECK_LAUNCH();
   }
-  for (int i = 0; i < n_rowred; ++i) {
-    const RowRedDesc& c = rowred[i];
-    RowRed P;
-    P.X = c.X; P.ldx = c.ldx; P.Y = c.Y; P.ldy = c.ldy; P.rows = c.rows; P.M = c.M; P.NJ = c.NJ; P.part = c.part;
-    dim3 grid((c.M + 63) / 64, c.chunks);
-    tc_rowred_kernel<<<grid, 256, 0, s>>>(P);
+  if (n_skinny > 0) {
+    SkinnyBatch S;
+    int blocks = 0;
+    for (int i = 0; i < n_skinny; ++i) {
+      const GemmProb& p = skinny[i].p;
+      Skinny& q = S.p[i];
+      memset(&q, 0, sizeof(q));
+      q.M = p.M; q.N = p.N; q.K = p.K; q.epi = p.epi; q.coef = p.coef;
+      q.X = p.A; q.ldx = p.lda; q.W = p.B; q.ldw = p.ldb; q.bias = p.bias; q.aux = p.aux; q.ldaux = p.ldaux;
+      q.C = p.C; q.ldc = p.ldc;
+      if (p.N <= 4) { q.kind = SK_ROWDOT; q.w_nk = p.b_trans ? 1 : 0; }
+      else { q.kind = SK_OUTER; q.w_nk = 1; }
+      q.block_begin = blocks;
+      q.blocks = (p.M + SK_ROWS_PER_BLOCK - 1) / SK_ROWS_PER_BLOCK;
+      blocks += q.blocks;
+    }
+    S.n = n_skinny;
+    tc_skinny_kernel<<<blocks, 256, 0, s>>>(S);
+    CUR_CHECK_LAUNCH();
+  }
+  if (n_rowred > 0) {
+    RowRedBatch RB;
+    int blocks = 0;
+    for (int i = 0; i < n_rowred; ++i) {
+      const RowRedDesc& c = rowred[i];
+      RowRed& P = RB.p[i];
+      P.X = c.X; P.ldx = c.ldx; P.Y = c.Y; P.ldy = c.ldy; P.rows = c.rows; P.M = c.M; P.NJ = c.NJ; P.part = c.part;
+      P.col_blocks = (c.M + 63) / 64;
+      P.block_begin = blocks;
+      blocks += P.col_blocks * c.chunks;
+    }
+    RB.n = n_rowred;
+    tc_rowred_kernel<<<blocks, 256, 0, s>>>(RB);
     CUR_CHECK_LAUNCH();
   }
   if (R.n > 0) {
@@ -625,11 +816,11 @@ int TcLauncher::flush(cudaStream_t s) {
     tc_reduce_kernel<<<blocks, 256, 0, s>>>(R);
     CUR_CHECK_LAUNCH();
   }
-  G.n = 0; G.total_tiles = 0; R.n = 0; n_rowred = 0;
+  G.n = 0; G.total_tiles = 0; R.n = 0; n_rowred = 0; n_skinny = 0;
   return CUR_OK;
 }
 
-TcLauncher::TcLauncher() : n_rowred(0) {
+TcLauncher::TcLauncher() : n_rowred(0), n_skinny(0) {
   static_assert(sizeof(TcBatch) <= sizeof(storage), "TcLauncher storage too small");
   G.n = 0; G.total_tiles = 0; R.n = 0;
 }

@@ -21,6 +21,7 @@ bool tc_supported(const GemmProb& p);     // shape / alignment fit the tcgen05 k
 int tc_pick_splits(const GemmProb& p);
 int64_t tc_partial_floats(const GemmProb& p);   // floats of split-K workspace the problem needs (0: none)
 int64_t tc_rowred_partial_floats(int64_t rows, int M, int NJ);
+bool tc_skinny_supported(const GemmProb& p);
 
 struct TcLauncher {
   struct { int n, total_tiles; } G;
@@ -28,6 +29,8 @@ struct TcLauncher {
   struct RowRedDesc { const float* X; int64_t ldx; const float* Y; int64_t ldy; int64_t rows; int M, NJ, chunks; float* part; }
       rowred[TC_MAX_PROBS];
   int n_rowred;
+  struct SkinnyDesc { GemmProb p; } skinny[TC_MAX_PROBS];
+  int n_skinny;
   alignas(64) unsigned char storage[TC_MAX_PROBS * (4 * 128 + 128) + 64];   // TcBatch (tensor maps + problems)
   TcLauncher();
   int add(const GemmProb& p, float* partial);
@@ -35,8 +38,10 @@ struct TcLauncher {
   // partial: tc_rowred_partial_floats(rows, M, NJ) floats
   int add_rowred(const float* X, int64_t ldx, int M, const float* Y, int64_t ldy, int NJ, int64_t rows, float* out,
                  float* partial);
+  // bandwidth-bound problems with N <= 4 (output layers) or K <= 4 (backward through them), see tc_skinny_kernel
+  int add_skinny(const GemmProb& p);
   int flush(cudaStream_t s);
-  bool empty() const { return G.n == 0 && R.n == 0 && n_rowred == 0; }
+  bool empty() const { return G.n == 0 && R.n == 0 && n_rowred == 0 && n_skinny == 0; }
 };
 
 }  // namespace cur

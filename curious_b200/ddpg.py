@@ -182,7 +182,7 @@ class DDPG(object):
     def _workspace(self, n):
         if n not in self._ws:
             floats = _lib.load().cur_ddpg_workspace_floats(C.byref(self.net.desc), n)
-            self._ws[n] = torch.empty(floats, dtype=torch.float32, device=self.device)
+            self._ws[n] = torch.zeros(floats, dtype=torch.float32, device=self.device)     # holds a ticket: zeroed
         return self._ws[n]
 
     def _use_rows(self, n):

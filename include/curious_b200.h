@@ -231,7 +231,8 @@ int64_t cur_net_param_count(const cur_net_desc* d, int which /*0: Q, 1: pi*/);
  * so that both nets start 16-byte aligned and one elementwise launch / one all-reduce covers both.
  * Returns the float offset of the pi block; *total (optional) receives the arena length. */
 int64_t cur_theta_pi_offset(const cur_net_desc* d, int64_t* total);
-/* floats of scratch needed by cur_ddpg_grads / cur_ddpg_actions for `batch` rows */
+/* floats of scratch needed by cur_ddpg_grads / cur_ddpg_actions for `batch` rows; the caller zero-initialises it
+ * once (it holds a self-resetting completion ticket of the multi-CTA loss kernel) */
 int64_t cur_ddpg_workspace_floats(const cur_net_desc* d, int64_t batch);
 
 typedef struct cur_norm_stats {
