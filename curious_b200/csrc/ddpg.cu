@@ -52,8 +52,9 @@ static bool tc_enabled() {
   if (g_tc_mode >= 0) return g_tc_mode == 1;
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("CUR_DDPG_TC");
+    const char* e = getenv("CUR_DDPG_TC");     // "0": FFMA only, "2": force the tensor cores for every eligible shape
     v = (e && e[0] == '0') ? 0 : 1;
+    if (e && e[0] == '2') g_tc_mode = 1;
   }
   return v == 1;
 }

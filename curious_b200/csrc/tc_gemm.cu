@@ -667,9 +667,10 @@ bool tc_supported(const GemmProb& p) {
 
 int tc_pick_splits(const GemmProb& p) {
   // forward / dX problems have M = batch: plenty of tiles.  Weight gradients (M <= 256, K = batch) split K into
-  // chunks of 512 rows: batch / 512 CTAs per 128 rows of dW and short accumulation chains
+  // chunks of 256 rows: 8 k-blocks per CTA like every other tile of the level (balanced waves), batch / 256 CTAs per
+  // 128 rows of dW, accumulation chains as short as the forward ones
   if (p.M >= 1024 || !p.a_trans) return 1;
-  int s = p.K / 512;
+  int s = p.K / 256;
   if (s < 1) s = 1;
   while (s > 1 && (p.K % (s * TC_BK)) != 0) --s;
   return s;
@@ -759,16 +760,47 @@ int64_t tc_rowred_partial_floats(int64_t rows, int M, int NJ) {
   return ((rows + TC_COLSUM_ROWS - 1) / TC_COLSUM_ROWS) * (int64_t)M * (NJ < 1 ? 1 : NJ);
 }
 
-int TcLauncher::flush(cudaStream_t s) {
+// The bandwidth-bound helpers of a level (skinny problems, row reductions) are independent of its tensor-core launch:
+// they run on a side stream forked from / joined to the caller's stream with events (capturable: inside a CUDA graph
+// the two become parallel branches), filling the SMs' idle issue slots and the L2 while the tcgen05 tiles run.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+};
+static int side_stream(SideStream** out) {
+  static thread_local SideStream ss;
+  int dev = 0;
+  CUR_CUDA_TRY(cudaGetDevice(&dev));
+  if (ss.stream == nullptr || ss.device != dev) {
+    CUR_CUDA_TRY(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
+    CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    ss.device = dev;
+  }
+  *out = &ss;
+  return CUR_OK;
+}
+
+int TcLauncher::flush(cudaStream_t s_main) {
   TcBatch& B = *reinterpret_cast<TcBatch*>(storage);
   static bool configured = false;
   if (!configured) {
     CUR_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     configured = true;
   }
+  cudaStream_t s = s_main;
+  SideStream* ss = nullptr;
+  const bool forked = G.n > 0 && (n_skinny > 0 || n_rowred > 0);
+  if (forked) {
+    CUR_TRY(side_stream(&ss));
+    CUR_CUDA_TRY(cudaEventRecord(ss->fork, s_main));
+    CUR_CUDA_TRY(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+    s = ss->stream;                       // helpers below go to the side stream
+  }
   if (G.n > 0) {
     B.n = G.n; B.total_tiles = G.total_tiles; B.tl = g_tc_timeline;
-    tc_gemm_kernel<<<G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s>>>(B);
+    tc_gemm_kernel<<<G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s_main>>>(B);
     CUR_CHECK_LAUNCH();
   }
   if (n_skinny > 0) {
@@ -805,6 +837,11 @@ int TcLauncher::flush(cudaStream_t s) {
     RB.n = n_rowred;
     tc_rowred_kernel<<<blocks, 256, 0, s>>>(RB);
     CUR_CHECK_LAUNCH();
+  }
+  if (forked) {
+    CUR_CUDA_TRY(cudaEventRecord(ss->join, ss->stream));
+    CUR_CUDA_TRY(cudaStreamWaitEvent(s_main, ss->join, 0));
+    s = s_main;
   }
   if (R.n > 0) {
     CUR_REQUIRE(R.n <= 2 * TC_MAX_PROBS, "too many reductions");
