@@ -40,12 +40,12 @@ struct Workspace {
 };
 
 // Batches this large run their layer GEMMs on the tensor cores (tc_gemm.cu); below it every GEMM of a level is
-// latency-bound and the FFMA grouped kernel wins (measured us/update, FFMA vs tcgen05: 1024: 337 / 392,
-// 2048: 556 / 420, 4096: 1161 / 479, 16384: 4130 / 1038).  CUR_DDPG_TC=0 or cur_ddpg_set_tensor_cores(0) forces the
+// latency-bound and the FFMA grouped kernel wins (measured us/update, FFMA vs tcgen05: 512: 203 / 268, 1024: 332 / 277,
+// 1536: 454 / 281, 2048: 556 / 287, 4096: 1161 / 319, 16384: 4130 / 688).  CUR_DDPG_TC=0 or cur_ddpg_set_tensor_cores(0) forces the
 // FFMA path, cur_ddpg_set_tensor_cores(1) forces the tensor cores for every eligible shape (A/B measurements, tests).
-constexpr int64_t TC_MIN_BATCH = 2048;
+constexpr int64_t TC_MIN_BATCH = 1024;
 constexpr int LOSS_MAX_CTAS = 128;
-constexpr int64_t LOSS_MC_MIN_BATCH = 2048;   // from here the loss / backward-seed kernel runs on several CTAs
+constexpr int64_t LOSS_MC_MIN_BATCH = 1024;   // from here the loss / backward-seed kernel runs on several CTAs
 constexpr int TC_SLOTS = 3;          // split-K weight gradients / row reductions per dependency level
 static int g_tc_mode = -1;          // -1: environment (default on), 0: off, 1: on  (cur_ddpg_set_tensor_cores)
 static bool tc_enabled() {

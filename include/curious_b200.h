@@ -395,7 +395,7 @@ int cur_tc_gemm_supported(int64_t M, int64_t N, int64_t K);
 /* debug: CTA 0 of every following tensor-core launch writes clock64() stamps of its warp roles into
  * device_buffer_128 (128 x int64); NULL switches it off */
 int cur_tc_gemm_timeline(long long* device_buffer_128);
-/* cur_ddpg_grads runs its layer GEMMs on the tensor cores when batch >= 2048, batch % 128 == 0 and
+/* cur_ddpg_grads runs its layer GEMMs on the tensor cores when batch >= 1024, batch % 128 == 0 and
  * hidden == 256.  mode: -1 default (on unless the environment says CUR_DDPG_TC=0), 0 FFMA only,
  * 1 tensor cores for every eligible shape (batch >= 256, batch % 128 == 0, hidden == 256). */
 int cur_ddpg_set_tensor_cores(int mode);
