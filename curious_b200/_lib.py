@@ -92,7 +92,7 @@ class DdpgExpert(C.Structure):
 
 class AdamFused(C.Structure):
     _fields_ = [('m', C.c_void_p), ('v', C.c_void_p), ('neg_a_table', C.c_void_p), ('table_len', C.c_int32),
-                ('_pad', C.c_int32), ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double)]
+                ('transposes_valid', C.c_int32), ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double)]
 
 
 CUR_MAX_RANKS = 8
@@ -142,6 +142,7 @@ SIGNATURES = {
                                      C.POINTER(NormStats), C.POINTER(Batch), C.POINTER(DdpgHyper), C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AdamFused),
                                      C.POINTER(HerArgs)]),
+    'cur_ddpg_rows_refresh': (C.c_int, [C.c_void_p, C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.c_int64]),
     'cur_ddpg_grads_group': (C.c_int, [C.c_void_p, C.POINTER(NetDesc), C.c_int, C.POINTER(DdpgExpert)]),
     'cur_ddpg_set_tensor_cores': (C.c_int, [C.c_int]),
     'cur_ddpg_uses_tensor_cores': (C.c_int, [C.POINTER(NetDesc), C.c_int64]),

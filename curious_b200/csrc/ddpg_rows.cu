@@ -691,15 +691,19 @@ constexpr int DW_KMAX = 256;
 constexpr int DW_LD = GT + 4;                                   // row stride of a staged [k][32] tile
 constexpr size_t DW_SMEM_BYTES = (size_t)2 * DW_KMAX * DW_LD * 4;
 
-__device__ __forceinline__ void dw_store(float* c, float v, const AdamCtx* ax, bool accumulate = false) {
+// Returns the parameter after the fused Adam step (undefined without `ax`).
+__device__ __forceinline__ float dw_store(float* c, float v, const AdamCtx* ax, bool accumulate = false) {
   if (accumulate) v += *c;         // micro-batch j > 0 of a several-workers-per-rank update adds to the running sum
   *c = v;
+  float th = 0.f;
   if (ax) {
     const int64_t off = c - ax->grads;
-    float th = ax->theta[off], mm = ax->m[off], vv = ax->v[off];
+    th = ax->theta[off];
+    float mm = ax->m[off], vv = ax->v[off];
     adam_elem(th, v, mm, vv, ax->neg_a, ax->b1, ax->omb1, ax->b2, ax->omb2, ax->eps);
     ax->theta[off] = th; ax->m[off] = mm; ax->v[off] = vv;
   }
+  return th;
 }
 
 __device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, float* Bs, int m0, int n0, const AdamCtx* ax) {
@@ -744,13 +748,28 @@ __device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, floa
     *reinterpret_cast<float4*>(red + kg * (GT * GT) + (4 * ty + i) * GT + 4 * tx) =
         make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
   __syncthreads();
+  // hidden layers with the fused optimiser: keep W^T (the backward operand of the next update's stream kernel) current
+  // right here instead of re-transposing every update; the stepped tile is turned in shared memory (Bs is free by
+  // now) so that the transposed stores are as coalesced as the direct ones
+  const bool keep_t = ax != nullptr && P.C2 != nullptr;
+  float* tt = Bs;                        // [32 n][33]
 #pragma unroll
   for (int j = 0; j < (GT * GT) / GEMM_THREADS; ++j) {
     const int i = tid + j * GEMM_THREADS;
     const int gm = m0 + (i >> 5), gn = n0 + (i & 31);
     if (gm < P.M && gn < P.N) {
       const float v = (red[i] + red[GT * GT + i]) + (red[2 * GT * GT + i] + red[3 * GT * GT + i]);
-      dw_store(P.C + (int64_t)gm * P.ldc + gn, v, ax, P.accumulate != 0);
+      const float th = dw_store(P.C + (int64_t)gm * P.ldc + gn, v, ax, P.accumulate != 0);
+      if (keep_t) tt[(i & 31) * (GT + 1) + (i >> 5)] = th;
+    }
+  }
+  if (keep_t) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < (GT * GT) / GEMM_THREADS; ++j) {
+      const int i = tid + j * GEMM_THREADS;
+      const int gn = n0 + (i >> 5), gm = m0 + (i & 31);
+      if (gm < P.M && gn < P.N) P.C2[(int64_t)gn * P.ldc2 + gm] = tt[(i >> 5) * (GT + 1) + (i & 31)];
     }
   }
 }
@@ -1009,8 +1028,11 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     configured = true;
   }
 
-  // ---- launch 0: W_l^T of the hidden layers of main.Q and main.pi
-  if (L > 1) {
+  // ---- launch 0: W_l^T of the hidden layers of main.Q and main.pi.  With the fused optimiser the weight-gradient
+  // epilogue of the previous call already left the transposes of the stepped weights in the workspace; the caller says
+  // so with adam->transposes_valid (and refreshes them with cur_ddpg_rows_refresh after any other change of theta).
+  const bool keep_wT = adam != nullptr && adam->transposes_valid != 0;
+  if (L > 1 && !keep_wT) {
     TransposeParams TP;
     memset(&TP, 0, sizeof(TP));
     int m = 0;
@@ -1116,7 +1138,9 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     add(bwd_dw(hN[L - 1], H, H, dOut, lddo, NL.out, gN + NL.off_Wout, n));
     add(bwd_db(dOut, lddo, NL.out, gN + NL.off_bout, n));
     for (int l = L - 1; l >= 1; --l) {
-      add(bwd_dw(hN[l - 1], H, H, dN[l], H, H, gN + NL.off_W[l], n));
+      GemmProb p = bwd_dw(hN[l - 1], H, H, dN[l], H, H, gN + NL.off_W[l], n);
+      if (adam) { p.C2 = (&NL == &LQ) ? w.TQ[l] : w.TP[l]; p.ldc2 = H; }     // transposed copy of the stepped weights
+      add(p);
       add(bwd_db(dN[l], H, H, gN + NL.off_b[l], n));
     }
     add(bwd_dw(X0, w.KP, NL.in_s, dN[0], H, H, gN + NL.off_W0, n));
@@ -1167,6 +1191,28 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
               q[3] - q[2], q[3] - q[0], q[0] - t[32]);
     }
   }
+  CUR_CHECK_LAUNCH();
+  return CUR_OK;
+}
+
+extern "C" int cur_ddpg_rows_refresh(void* stream, const cur_net_desc* d, const float* theta_main, float* workspace,
+                                     int64_t batch) {
+  CUR_TRY(check_desc(d));
+  CUR_REQUIRE(theta_main && workspace, "NULL argument");
+  CUR_REQUIRE(rows_supported(d, batch), "shape not supported by the rows schedule");
+  const NetLayout LQ = net_layout(*d, 0), LP = net_layout(*d, 1);
+  const float *mQ = theta_main, *mP = theta_main + r4(LQ.total);
+  const RowsWorkspace w = carve_rows(*d, batch, workspace);
+  const int L = d->layers, H = d->hidden;
+  if (L <= 1) return CUR_OK;
+  TransposeParams TP;
+  memset(&TP, 0, sizeof(TP));
+  int m = 0;
+  for (int l = 1; l < L; ++l) {
+    TP.src[m] = mQ + LQ.off_W[l]; TP.dst[m++] = w.TQ[l];
+    TP.src[m] = mP + LP.off_W[l]; TP.dst[m++] = w.TP[l];
+  }
+  transpose_kernel<<<dim3(H / 32, H / 32, m), 256, 0, (cudaStream_t)stream>>>(TP);
   CUR_CHECK_LAUNCH();
   return CUR_OK;
 }

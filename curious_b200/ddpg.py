@@ -152,6 +152,8 @@ class DDPG(object):
         self._n_updates = 0
         self._graph = None
         self._graph_sig = None
+        self._graph_fused = False
+        self._wT_dirty = True
 
     def _view(self, arena, which):
         net = self.net
@@ -178,6 +180,7 @@ class DDPG(object):
     def set_flat(self, which, values, target=False):
         v = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float32))
         self._view(self.theta_target if target else self.theta_main, which).copy_(v.to(self.device))
+        self._wT_dirty = True
 
     def _workspace(self, n):
         if n not in self._ws:
@@ -307,7 +310,7 @@ class DDPG(object):
             episode_batch['o_2'] = episode_batch['o'][:, 1:, :]
             episode_batch['ag_2'] = episode_batch['ag'][:, 1:, :]
             num = transitions_in_episode_batch(episode_batch)
-            epi = episodes_to_device({k: episode_batch[k] for k in keys}, self.device)
+            epi = episodes_to_device({k: episode_batch[k] for k in keys}, self.device, staged=staged)
             sampler = self.sample_transitions
             draws = None
             if self.her_rng == 'numpy':
@@ -327,6 +330,7 @@ class DDPG(object):
     def _sync_optimizers(self):
         self.Q_adam.sync()
         self.pi_adam.sync()
+        self._wT_dirty = True
 
     # ------------------------------------------------------------------------------------------
     def _proportions(self):
@@ -430,6 +434,7 @@ class DDPG(object):
         MPI all-reduces of the reference become ONE NCCL all-reduce, and when both nets share the step
         size one fused Adam launch covers the arena."""
         group, world = _world(self.comm)
+        self._wT_dirty = True
         if self.Q_adam.t % 100 == 0:
             self.Q_adam.check_synced()
             self.pi_adam.check_synced()
@@ -554,11 +559,13 @@ class DDPG(object):
         self._graph_has_adam = _world(self.comm)[1] == 1 or self._peer is not None
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            fused = self._launch_sample_and_grads()
+            # fused Adam: its epilogue keeps W^T current, so the captured update has no transpose launch
+            fused = self._launch_sample_and_grads(keep_wT=fused)
             if self._graph_has_adam and not fused:
                 self._launch_adam()
         self._graph = g
         self._graph_fused = fused
+        self._wT_dirty = True            # the warm-up stepped (and we restored) theta: rebuild W^T before the first replay
         if self._peer is not None:
             import torch.distributed as dist
             dist.barrier(group=_world(self.comm)[0])
@@ -579,9 +586,10 @@ class DDPG(object):
         qa, pa = self.Q_adam, self.pi_adam
         return (self.Q_lr, qa.beta1, qa.beta2, qa.epsilon) == (self.pi_lr, pa.beta1, pa.beta2, pa.epsilon)
 
-    def _launch_sample_and_grads(self):
+    def _launch_sample_and_grads(self, keep_wT=False):
         """HER sample + gradients of one update, all parameters frozen / device-resident (capturable).
-        Returns True when Adam was fused into the weight-gradient launch."""
+        Returns True when Adam was fused into the weight-gradient launch.  keep_wT: the transposed hidden-layer
+        weights in the rows workspace are current (maintained by the fused Adam epilogue, see _refresh_wT)."""
         lib = _lib.load()
         sampler = self.sample_transitions
         segs = [(buf.device_view(), 0, ttr) for buf, ttr in self._all_segments()]
@@ -607,7 +615,7 @@ class DDPG(object):
             # the weight-gradient launch (2 launches per update after the HER kernel)
             fuse = self._same_rule() and _world(self.comm)[1] == 1 and self.workers_per_rank == 1
             adam = _lib.AdamFused(self._adam_m.data_ptr(), self._adam_v.data_ptr(), self._adam_tables[0].data_ptr(),
-                                  self.ADAM_TABLE, 0, qa.beta1, qa.beta2, qa.epsilon) if fuse else None
+                                  self.ADAM_TABLE, 1 if keep_wT else 0, qa.beta1, qa.beta2, qa.epsilon) if fuse else None
             for j in range(self.workers_per_rank):
                 if j > 0 and her_args is None:            # unfused sampling: a fresh batch for every worker
                     sampler.sample_device(segs, self.batch_size, clip_obs=self.clip_obs,
@@ -664,6 +672,14 @@ class DDPG(object):
                 adam.v.data_ptr(), adam.theta.numel(), table.data_ptr(), self.ADAM_TABLE, self._step.data_ptr(),
                 adam.beta1, adam.beta2, adam.epsilon, 1.0, self.workers_per_rank), 'cur_adam_step_graph')
 
+    def _refresh_wT(self):
+        """Rebuild the transposed hidden-layer weights in the rows workspace after theta_main changed outside the
+        fused update (initial weights, set_flat / load_weights, broadcast from rank 0, launch-by-launch updates)."""
+        B = self.batch_size
+        _lib.check(_lib.load().cur_ddpg_rows_refresh(_lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(),
+                                                     self._workspace_rows(B).data_ptr(), B), 'cur_ddpg_rows_refresh')
+        self._wT_dirty = False
+
     def _train_graph(self):
         if self._graph is None:
             self._build_graph()
@@ -673,6 +689,8 @@ class DDPG(object):
             self.Q_adam.check_synced()
             self.pi_adam.check_synced()
         self._refresh_dyn()
+        if self._graph_fused and self._wT_dirty:
+            self._refresh_wT()
         k = self.workers_per_rank          # the loss of the rank's last worker (device ring slot = launch index % ring)
         slot = (self._n_updates * k + k - 1) % self.LOSS_RING
         self._graph.replay()

@@ -135,16 +135,19 @@ def default_device():
     return torch.device('cuda', torch.cuda.current_device())
 
 
-def episodes_to_device(episode_batch, device=None):
+def episodes_to_device(episode_batch, device=None, staged=None):
     """Pack a host episode batch {key: [n, T(+1), dim]} into a temporary device buffer and return the
-    DeviceEpisodes view the sampler consumes (used for the normaliser path, ddpg.py:209-215)."""
+    DeviceEpisodes view the sampler consumes (used for the normaliser path, ddpg.py:209-215).  `staged`: the
+    StagedEpisodes of the SAME batch already uploaded by the caller (store_episode) - reused instead of a second
+    host->device copy."""
     device = device or default_device()
     batch = {k: v for k, v in episode_batch.items() if k not in ('o_2', 'ag_2')}
     shapes = {k: np.asarray(v).shape[1:] for k, v in batch.items()}
     L, info_keys, has_td, has_change = layout_from_shapes(shapes)
     n = len(batch['u'])
     hot, cold = alloc_storage(L, n, device)
-    staged = StagedEpisodes(batch, L, info_keys, has_td, has_change, device)
+    if staged is None or staged.n != n or bytes(staged.layout) != bytes(L):
+        staged = StagedEpisodes(batch, L, info_keys, has_td, has_change, device)
     staged.store([(e, hot, cold, e) for e in range(n)])
     epi = DeviceEpisodes(hot, cold, n, L, info_keys, has_td, has_change)
     epi._staged = staged

@@ -326,11 +326,18 @@ typedef struct cur_adam_fused {
   float *m, *v;               /* Adam moments, same arena layout as theta */
   const float* neg_a_table;   /* float32(-a_t), t = 1..table_len (see cur_adam_step_graph) */
   int32_t table_len;
-  int32_t _pad;
+  /* 1: the transposed hidden-layer weights in `workspace` are current (the previous call on this workspace was a
+   * fused-Adam call, whose epilogue writes them next to the stepped weights, or cur_ddpg_rows_refresh ran after the
+   * last outside change of theta_main) - the transpose launch is skipped.  0: re-transpose first. */
+  int32_t transposes_valid;
   double beta1, beta2, eps;
 } cur_adam_fused;
 
 int cur_ddpg_rows_supported(const cur_net_desc* d, int64_t batch);
+/* (Re)build the transposed hidden-layer weights of main.Q / main.pi in a rows-schedule workspace (see
+ * cur_adam_fused.transposes_valid). */
+int cur_ddpg_rows_refresh(void* stream, const cur_net_desc* d, const float* theta_main, float* workspace,
+                          int64_t batch);
 int64_t cur_ddpg_rows_workspace_floats(const cur_net_desc* d, int64_t batch);
 int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* theta_main,
                        const float* theta_target, const cur_norm_stats* stats,

@@ -302,6 +302,17 @@ def test_cuda_graph_path_equals_eager_path(task_replay, schedule):
         assert np.array_equal(g.get_flat(which), e.get_flat(which)), which
     assert torch.equal(g.Q_adam.m, e.Q_adam.m) and torch.equal(g.pi_adam.v, e.pi_adam.v)
     assert int(g._step.item()) == int(e._step.item()) == 7
+    # weights changed from outside (load_weights / set_flat): the rows graph keeps W^T of the hidden layers in its
+    # workspace (maintained by the fused Adam epilogue) and must rebuild it before the next replay
+    for ag in agents:
+        ag.set_flat('Q', (ag.get_flat('Q') * np.float32(0.5)))
+        ag.set_flat('pi', (ag.get_flat('pi') * np.float32(1.25)))
+    for step in range(2):
+        lg, qg = g.train()
+        le, qe = e.train()
+        assert float(lg) == float(le), step
+    for which in ('Q', 'pi'):
+        assert np.array_equal(g.get_flat(which), e.get_flat(which)), which
     g.update_target_net()
     e.update_target_net()
     assert np.array_equal(g.get_flat('Q', True), e.get_flat('Q', True))
