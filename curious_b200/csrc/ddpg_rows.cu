@@ -1,4 +1,5 @@
-// DDPG / UVFA update, "rows" schedule (sm_100a): the whole actor-critic graph of one update in THREE launches.
+// DDPG / UVFA update, "rows" schedule (sm_100a): the whole actor-critic graph of one update in TWO launches
+// (three when the optimiser is not fused).
 //
 // Replaces (reference flowersteam/curious), like ddpg.cu but with a latency-oriented schedule:
 //   baselines/her/actor_critic.py:5-98, util.py:56-107   networks
@@ -10,17 +11,19 @@
 // independent until the weight gradient, so the data path is run "decode style":
 //
 //   launch 0  transpose_kernel   W_l^T of the hidden layers of main.Q / main.pi (operands of the backward
-//             streams), 0.5 MB, rebuilt every update so no host-side state has to track weight changes.
-//   launch 1  ddpg_stream_kernel one CTA per 4 batch rows, no inter-CTA communication at all.  Each CTA walks
-//             the WHOLE chain for its rows - input assembly, main.pi, target.pi, main.Q on (u | pi) stacked,
-//             target.Q, loss seeds, critic + actor-through-critic backward stacked, actor backward - while
-//             a producer warp streams every weight matrix it needs (3.4 MB per update) from L2 through a
-//             4 x 32 KB shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier full/empty
-//             pairs).  8 consumer warps do GEMV-like FFMA: a thread owns 4 output columns and a quarter of
-//             the chunk's k rows, reads W as LDS.128 and the (transposed) activations as one broadcast
-//             LDS.128 per k; activations never leave shared memory between layers.  The first version of
-//             this schedule split columns over an 8-CTA cluster and exchanged activations every layer
-//             (DSMEM or L2): the per-layer cluster synchronisation cost more than the layer (profiles/).
+//             streams), 0.5 MB.  Only when the optimiser is NOT fused into launch 2: the fused Adam epilogue
+//             writes the transposed copy of every stepped hidden-layer tile itself (cur_adam_fused.transposes_valid).
+//   launch 1  ddpg_stream_kernel two independent CTAs per 4 batch rows, no inter-CTA communication at all:
+//               actor CTA   main.pi -> main.Q(o,g,pi) -> actor loss -> backward through main.Q and main.pi
+//               critic CTA  target.pi -> target.Q -> main.Q(o,g,u) -> TD loss -> critic backward through main.Q
+//             Each CTA walks its whole chain for its rows while a producer warp streams every weight matrix it
+//             needs (2.2 / 2.3 MB per update) from L2 through a 4 x 32 KB shared-memory ring with TMA bulk copies
+//             (cp.async.bulk + mbarrier full/empty pairs).  8 consumer warps do GEMV-like FFMA: a thread owns 4
+//             output columns and a quarter of the chunk's k rows, reads W as LDS.128 and the (transposed)
+//             activations as one broadcast LDS.128 per k; activations never leave shared memory between
+//             layers.  History (profiles/README.md): column split over an 8-CTA cluster with a per-layer
+//             exchange (lost to the synchronisation), one CTA for everything, main / target CTA pair with
+//             main.Q streamed once for 8 stacked rows (FFMA-bound passes, idle target CTA), this split.
 //   launch 2  rows_dw_kernel     every dW = X^T dY and db = 1^T dY of both nets as one grouped GEMM with
 //             the full batch as K (deterministic, no atomics), written into the flat GetFlat-ordered
 //             gradient arena; optionally Adam is applied to the element in the same epilogue (world
@@ -44,7 +47,7 @@ constexpr int S_NSLOT = 4;               // ring slots
 constexpr int S_SLOT = S_CK * S_H;       // floats per slot (32 KB)
 constexpr int S_MAXL = 4;                // hidden layers supported by this schedule
 constexpr int S_MAXCHUNK = 128;          // weight chunks of the main CTA (L = 4: 2 * 33 + 2 * 24 = 114)
-constexpr int S_MAXCHUNK_T = 72;         // weight chunks of the target CTA (L = 4: 2 * 33 = 66)
+constexpr int S_MAXCHUNK_T = 128;        // weight chunks of the critic CTA (L = 4: 3 * 33 + 24 = 123)
 constexpr int S_DU = 8;                  // max action dim
 constexpr int S_XT = S_H * 8;            // floats of one transposed activation buffer [256 k][<= 8 rows]
 constexpr int S_RED = 4 * 8 * S_H;       // split-K partials [4 k-slices][<= 8 rows][256]
@@ -81,8 +84,8 @@ struct StreamParams {
   int fused_her;             // sample the CTA's 4 rows here (her, plan) instead of reading a staged batch
   HerPlan plan;
   cur_her_args her;
-  SChunk chunks[S_MAXCHUNK];       // main CTA: main.pi fwd, main.Q fwd, main.Q^T bwd, main.pi^T bwd
-  SChunk chunks_t[S_MAXCHUNK_T];   // target CTA: target.pi fwd, target.Q fwd
+  SChunk chunks[S_MAXCHUNK];       // actor CTA: main.pi fwd, main.Q fwd, main.Q^T bwd, main.pi^T bwd
+  SChunk chunks_t[S_MAXCHUNK_T];   // critic CTA: target.pi fwd, target.Q fwd, main.Q fwd, main.Q^T bwd
 };
 
 #define S_TL(i)                                                                   \
@@ -409,10 +412,13 @@ __device__ __forceinline__ float* forward_net(const StreamParams& P, Ring& rg, i
   return xin;
 }
 
-// Cluster of 2 CTAs per 4 batch rows: rank 0 walks the main nets (and everything that follows the losses), rank 1
-// the target nets - the two chains are independent until the TD target, so each SM only ingests the weights of
-// its own chain (per-SM L2 -> shared bandwidth is what bounds this kernel).
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S_THREADS, 1)
+// Two CTAs per 4 batch rows, fully independent of each other:
+//   even CTA (actor):  main.pi -> main.Q(o,g,pi) -> actor loss -> backward through main.Q (action gradient) and main.pi
+//   odd CTA (critic):  target.pi -> target.Q -> main.Q(o,g,u) -> TD loss -> backward through main.Q (critic chain)
+// Each SM ingests 2.2-2.3 MB of weights for FOUR rows at a time (per-SM L2 -> shared bandwidth is what bounds this
+// kernel; the earlier main / target split streamed main.Q once for 8 stacked rows, which made those passes FFMA-bound
+// and left the target CTA idle for 40 % of the kernel).
+__global__ void __launch_bounds__(S_THREADS, 1)
 ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ringf = reinterpret_cast<float*>(smem_raw);
@@ -431,21 +437,20 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   float* her_stage = misc + S_STAGE_OFF;                                  // [4][stage_stride]
 
   const int tid = threadIdx.x;
-  const uint32_t role = cluster_ctarank();                   // 0: main chain, 1: target chain
+  const uint32_t role = blockIdx.x & 1;                      // 0: actor chain, 1: critic chain (independent CTAs)
   const int64_t row0 = (int64_t)(blockIdx.x >> 1) * S_ROWS;
   const cur_net_desc& d = P.d;
   const int L = P.L;
-  const uint32_t full = smem_addr(bars), empty = smem_addr(bars + S_NSLOT), qt_bar = smem_addr(bars + 2 * S_NSLOT);
+  const uint32_t full = smem_addr(bars), empty = smem_addr(bars + S_NSLOT);
 
   if (tid == 0) {
     for (int i = 0; i < S_NSLOT; ++i) {
       mbar_init(full + 8 * i, 1);
       mbar_init(empty + 8 * i, S_CONSUMERS / 32);
     }
-    mbar_init(qt_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  cluster_sync_all();       // barriers initialised in both CTAs before anybody signals across the pair
+  __syncthreads();          // barriers initialised before the producer / consumers use them
 
   const SChunk* my_chunks = role == 0 ? P.chunks : P.chunks_t;
   if (tid >= S_CONSUMERS) {
@@ -475,8 +480,10 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
     stage = her_stage;
   }
 
+  const float hi_clip = P.clip_pos ? 0.f : INFINITY;
   if (role == 1) {
-    // ===== target chain: target.pi, then target.Q(o2, g2, pi_target) with the same u-slot and td (ddpg.py:427-431)
+    // ===== critic CTA: target.pi -> target.Q(o2, g2, pi_target) with the same u-slot and td (ddpg.py:427-431),
+    // main.Q(o, g, u), the TD loss and the critic's backward chain.  Nothing is exchanged with the actor CTA.
     build_x(P, xa, 4, 0, row0, true, 0, nullptr, nullptr, stage);
     consumer_sync();
     float* xl = forward_net<4>(P, rg, P.ch0[0], xa, xb, red, P.bPT, nullptr, nullptr, row0);
@@ -489,16 +496,61 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
     xl = forward_net<4>(P, rg, P.ch0[1], xa, xb, red, P.bQT, nullptr, nullptr, row0);
     small_out(xl, 4, 0, 4, P.WoutQT, 1, 1, 1, P.boutQT, s_qt);
     consumer_sync();
+    // main.Q(o, g, u)
+    build_x(P, xa, 4, 0, row0, false, 1, nullptr, P.Xq, stage);
+    consumer_sync();
+    xl = forward_net<4>(P, rg, P.ch0[1], xa, xb, red, P.bQ, P.hq, nullptr, row0);
+    small_out(xl, 4, 0, 4, P.WoutQ, 1, 1, 1, P.boutQ, s_q);
+    consumer_sync();
+    // critic loss (ddpg.py:436-439) and its backward seed
+    if (tid < S_ROWS) {
+      const int64_t row = row0 + tid;
+      const float rew = stage ? s_r[tid] : P.r[row];
+      const float tgt = fminf(fmaxf(rew + P.gamma * s_qt[tid * S_DU], -P.clip_return), hi_clip);
+      const float diff = tgt - s_q[tid * S_DU];
+      s_dq[tid] = -2.0f * inv_n * diff;          // d mean((tgt - Q)^2) / dQ
+      s_dq[8 + tid] = diff * diff;
+      P.dQ[row] = s_dq[tid];
+    }
+    consumer_sync();
     if (tid == 0) {
-      const uint32_t dst = map_to_cta(smem_addr(s_qt), 0);
-      for (int r = 0; r < S_ROWS; ++r) st_remote_f32(dst + 4 * (r * S_DU), s_qt[r * S_DU]);
-      mbar_arrive_remote(map_to_cta(qt_bar, 0));        // release: the stores above are visible to the waiter
+      float ssq = 0.f;
+      for (int r = 0; r < S_ROWS; ++r) ssq += s_dq[8 + r];
+      P.loss_part[(int64_t)(blockIdx.x >> 1) * 4] = ssq;
+    }
+    // backward through main.Q (critic chain): gradient at the last hidden layer is dQ * Wout^T (Wout is [H][1])
+    float* xin = xa; float* xout = xb;
+    {
+      const float wq = __ldg(P.WoutQ + col);
+      float v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r] = relu_mask(s_dq[r] * wq, __ldcg(P.hq[L - 1] + (row0 + r) * S_H + col));
+        P.dc[L - 1][(row0 + r) * S_H + col] = v[r];
+      }
+      put_xT<4>(xin, v);
+      consumer_sync();
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      float m[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) m[r] = __ldcg(P.hq[l - 1] + (row0 + r) * S_H + col);   // ReLU masks of layer l-1
+      float v[4];
+      layer_gemv<4>(P, rg, S_H / S_CK, xin, red, v);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r] = relu_mask(v[r], m[r]);
+        P.dc[l - 1][(row0 + r) * S_H + col] = v[r];
+      }
+      put_xT<4>(xout, v);
+      consumer_sync();
+      float* t = xin; xin = xout; xout = t;
     }
     return;
   }
 
+  // ===== actor CTA: main.pi -> main.Q(o, g, pi) -> actor loss -> backward through main.Q and main.pi =====
   S_TL(0);
-  // ===== main.pi =====
   build_x(P, xa, 4, 0, row0, false, 0, nullptr, P.Xp, stage);
   consumer_sync();
   S_TL(1);
@@ -511,78 +563,56 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   }
   S_TL(2);
   S_TL(3);
-  // ===== main.Q on rows 0-3 = (o,g,u) and rows 4-7 = (o,g,pi), sharing one pass over the weights =====
-  build_x(P, xa, 8, 0, row0, false, 1, nullptr, P.Xq, stage);
-  build_x(P, xa, 8, 4, row0, false, 2, s_th, nullptr, stage);
+  build_x(P, xa, 4, 0, row0, false, 2, s_th, nullptr, stage);
   consumer_sync();
   {
-    float* xl = forward_net<8>(P, rg, P.ch0[1], xa, xb, red, P.bQ, P.hq, P.hqp, row0);
-    small_out(xl, 8, 0, 8, P.WoutQ, 1, 1, 1, P.boutQ, s_q);
+    float* xl = forward_net<4>(P, rg, P.ch0[1], xa, xb, red, P.bQ, P.hqp, nullptr, row0);
+    small_out(xl, 4, 0, 4, P.WoutQ, 1, 1, 1, P.boutQ, s_q);
     consumer_sync();
   }
   S_TL(4);
-  mbar_wait_cluster(qt_bar, 0);          // target.Q of these rows has arrived from the partner CTA
   S_TL(5);
-  // ===== losses (ddpg.py:436-441) and backward seeds =====
+  // ===== actor loss terms (ddpg.py:440-441) and backward seed =====
   if (tid < S_ROWS) {
-    const int64_t row = row0 + tid;
-    const float hi = P.clip_pos ? 0.f : INFINITY;
-    const float rew = stage ? s_r[tid] : P.r[row];
-    const float tgt = fminf(fmaxf(rew + P.gamma * s_qt[tid * S_DU], -P.clip_return), hi);
-    const float diff = tgt - s_q[tid * S_DU];
-    s_dq[tid] = -2.0f * inv_n * diff;          // d mean((tgt - Q)^2) / dQ
-    s_dq[4 + tid] = -inv_n;                    // d (-mean(Q_pi)) / dQ_pi
-    s_dq[8 + tid] = diff * diff;
-    P.dQ[row] = s_dq[tid];
-    P.q_pi[row] = s_q[(4 + tid) * S_DU];
+    s_dq[tid] = -inv_n;                        // d (-mean(Q_pi)) / dQ_pi
+    P.q_pi[row0 + tid] = s_q[tid * S_DU];
   }
-  consumer_sync();
   if (tid == 0) {
-    float ssq = 0.f, sq = 0.f, sth = 0.f;
+    float sq = 0.f, sth = 0.f;
     for (int r = 0; r < S_ROWS; ++r) {
-      ssq += s_dq[8 + r];
-      sq += s_q[(4 + r) * S_DU];
+      sq += s_q[r * S_DU];
       for (int j = 0; j < d.dimu; ++j) sth += s_th[r * S_DU + j] * s_th[r * S_DU + j];
     }
     float* lp = P.loss_part + (int64_t)(blockIdx.x >> 1) * 4;
-    lp[0] = ssq; lp[1] = sq; lp[2] = sth; lp[3] = 0.f;
+    lp[1] = sq; lp[2] = sth; lp[3] = 0.f;
   }
-  // ===== stream 5: backward through main.Q, critic chain (rows 0-3) and actor-through-critic chain (rows 4-7) =====
+  consumer_sync();
+  // ===== backward through main.Q, actor-through-critic chain =====
   {
     float* xin = xa; float* xout = xb;
     {
-      // gradient at the last hidden layer: dY * Wout^T (Wout is [H][1]), masked by the layer's ReLU
       const float wq = __ldg(P.WoutQ + col);
-      float v[8];
+      float v[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        v[r] = relu_mask(s_dq[r] * wq, __ldcg(P.hq[L - 1] + (row0 + r) * S_H + col));
-        v[4 + r] = relu_mask(s_dq[4 + r] * wq, __ldcg(P.hqp[L - 1] + (row0 + r) * S_H + col));
-        P.dc[L - 1][(row0 + r) * S_H + col] = v[r];
-      }
-      put_xT<8>(xin, v);
+      for (int r = 0; r < 4; ++r) v[r] = relu_mask(s_dq[r] * wq, __ldcg(P.hqp[L - 1] + (row0 + r) * S_H + col));
+      put_xT<4>(xin, v);
       consumer_sync();
     }
     for (int l = L - 1; l >= 1; --l) {
-      float m[8];
+      float m[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {           // ReLU masks of layer l-1, fetched while the chunks stream
-        m[r] = __ldcg(P.hq[l - 1] + (row0 + r) * S_H + col);
-        m[4 + r] = __ldcg(P.hqp[l - 1] + (row0 + r) * S_H + col);
-      }
-      float v[8];
-      layer_gemv<8>(P, rg, S_H / S_CK, xin, red, v);
+      for (int r = 0; r < 4; ++r) m[r] = __ldcg(P.hqp[l - 1] + (row0 + r) * S_H + col);
+      float v[4];
+      layer_gemv<4>(P, rg, S_H / S_CK, xin, red, v);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = relu_mask(v[r], m[r]);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) P.dc[l - 1][(row0 + r) * S_H + col] = v[r];
-      put_xT<8>(xout, v);
+      for (int r = 0; r < 4; ++r) v[r] = relu_mask(v[r], m[r]);
+      put_xT<4>(xout, v);
       consumer_sync();
       float* t = xin; xin = xout; xout = t;
     }
-    // gradient wrt the action inputs of main.Q (rows 4-7 = actor chain at layer 0), then through tanh and the
-    // action penalty (ddpg.py:440-441): d pi_loss/d(pre-tanh) = (dL/d(pi/max_u) + action_l2*2/(B*dimu)*th) * (1 - th^2)
-    small_out(xin, 8, 4, 4, P.W0Q_act, 1, S_H, d.dimu, nullptr, s_dy);
+    // gradient wrt the action inputs of main.Q, then through tanh and the action penalty (ddpg.py:440-441):
+    // d pi_loss/d(pre-tanh) = (dL/d(pi/max_u) + action_l2*2/(B*dimu)*th) * (1 - th^2)
+    small_out(xin, 4, 0, 4, P.W0Q_act, 1, S_H, d.dimu, nullptr, s_dy);
     consumer_sync();
     if (tid < S_ROWS * S_DU) {
       const int r = tid >> 3, j = tid & (S_DU - 1);
@@ -598,7 +628,7 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
     consumer_sync();
   }
   S_TL(6);
-  // ===== stream 6: backward through main.pi =====
+  // ===== backward through main.pi =====
   {
     float* xin = xa; float* xout = xb;
     {
@@ -1104,6 +1134,8 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   list = P.chunks_t;
   forward_net(tP, LP);
   forward_net(tQ, LQ);
+  forward_net(mQ, LQ);                                            // critic CTA: main.Q(o,g,u) ...
+  for (int l = L - 1; l >= 1; --l) rows_of(w.TQ[l], H, 0);        // ... and its backward chain
   CUR_REQUIRE(nc <= S_MAXCHUNK_T, "too many weight chunks for the rows schedule");
   P.nchunks_t = nc;
 
