@@ -139,6 +139,7 @@ class DDPG(object):
                               m=self._view(self._adam_m, 'Q'), v=self._view(self._adam_v, 'Q'))
         self.pi_adam = MpiAdam([self._view(self.theta_main, 'pi')], scale_grad_by_procs=False, comm=self.comm,
                                m=self._view(self._adam_m, 'pi'), v=self._view(self._adam_v, 'pi'))
+        self.Q_adam.on_change = self.pi_adam.on_change = self._mark_weights_changed
         self._hyper = _lib.DdpgHyper(float(self.gamma), float(min(self.clip_return, 3.0e38)), float(self.action_l2),
                                      1 if self.clip_pos_returns else 0)
         self._ws = {}
@@ -153,6 +154,10 @@ class DDPG(object):
         self._graph = None
         self._graph_sig = None
         self._graph_fused = False
+        self._wT_dirty = True
+
+    def _mark_weights_changed(self):
+        """theta_main was written outside the fused update: W^T kept by the rows graph must be rebuilt (_refresh_wT)."""
         self._wT_dirty = True
 
     def _view(self, arena, which):

@@ -54,6 +54,7 @@ class MpiAdam(object):
         assert self.m.numel() == size and self.v.numel() == size
         self.t = 0
         self.comm = comm
+        self.on_change = None      # optional callback: the owner (DDPG) invalidates state derived from theta
 
     # reference helpers (tf_util.GetFlat / SetFromFlat)
     def getflat(self):
@@ -61,6 +62,8 @@ class MpiAdam(object):
 
     def setfromflat(self, theta):
         self.theta.copy_(torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float32)).to(self.theta.device))
+        if self.on_change:
+            self.on_change()
 
     def _grad_tensor(self, localg):
         if torch.is_tensor(localg):
@@ -86,9 +89,13 @@ class MpiAdam(object):
                                              self.m.data_ptr(), self.v.data_ptr(), self.theta.numel(),
                                              float(np.float32(-a)), self.beta1, self.beta2, self.epsilon, grad_div),
                    'cur_adam_step')
+        if self.on_change:
+            self.on_change()
 
     def sync(self):
         broadcast_from_root_(self.theta, self.comm)
+        if self.on_change:
+            self.on_change()
 
     def checksum(self):
         out = torch.zeros(1, dtype=torch.int64, device=self.theta.device)
