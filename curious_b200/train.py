@@ -1,0 +1,173 @@
+"""Driver loop: reference baselines/her/experiment/train.py:48-170 and the pieces of config.py it needs
+(config.py:20-90 defaults, :110-170 configure_her, :184-214 configure_buffer, :219-253 configure_ddpg, :257-275
+configure_dims) for environments with the gym_flowers attribute contract.
+
+    exp = make_experiment(nb_tasks=4, structure='curious', task_selection='active_competence_progress',
+                          task_replay='replay_task_cp_buffer')
+    history = train(**exp, n_epochs=10)
+
+Process launch (`mpirun -np N` -> `python -m torch.distributed.run --nproc-per-node N`), logging to files and
+policy checkpoints are the caller's business; this module is the loop itself.
+"""
+import numpy as np
+
+from . import her
+from .ddpg import DDPG
+from .envs import ModularPointEnv
+from .replay_buffer import ReplayBuffer
+from .rollout import RolloutWorker
+
+MULTI_TASK_PARAMS = {            # config.py:56-90
+    'max_u': 1., 'layers': 3, 'hidden': 256, 'network_class': 'baselines.her.actor_critic:MultiTaskActorCritic',
+    'Q_lr': 0.001, 'pi_lr': 0.001, 'buffer_size': int(1E6), 'polyak': 0.95, 'action_l2': 1.0, 'clip_obs': 200.,
+    'scope': 'ddpg', 'relative_goals': False, 'n_cycles': 25, 'rollout_batch_size': 2, 'n_batches': 100,
+    'batch_size': 256, 'n_test_rollouts': 5, 'test_with_polyak': False, 'random_eps': 0.3, 'noise_eps': 0.2,
+    'her_replay_k': 4, 'norm_eps': 0.01, 'norm_clip': 5,
+    'her_sampling_func': 'baselines.her.her:make_sample_multi_task_her_transitions', 'queue_length': 300, 'eps_task': 0.4,
+}
+FLAT_PARAMS = dict(MULTI_TASK_PARAMS, network_class='baselines.her.actor_critic:ActorCritic',
+                   her_sampling_func='baselines.her.her:make_sample_her_transitions', queue_length=200)
+
+
+def configure_dims(env, structure):
+    """config.py:257-275: dims from one reset + step of the environment."""
+    env.reset()
+    obs, _, _, info = env.step(env.action_space.sample())
+    dims = {'o': obs['observation'].shape[0], 'u': env.action_space.shape[0], 'g': obs['desired_goal'].shape[0],
+            'ag': obs['achieved_goal'].shape[0]}
+    if structure != 'flat':
+        dims['task_descr'] = env.unwrapped.nb_tasks
+    for key, value in info.items():
+        value = np.array(value)
+        if value.ndim == 0:
+            value = value.reshape(1)
+        dims['info_{}'.format(key)] = value.shape[0]
+    return dims
+
+
+def configure_buffer(dims, T, sampler, buffer_size, structure, task_replay, nb_tasks, device=None):
+    """config.py:184-214: one buffer, or one per module + buffer 0 for the *_buffer replay modes."""
+    shapes = {key: (T if key != 'o' and key != 'ag' else T + 1, val) for key, val in dims.items()}
+    if structure != 'flat':
+        shapes['change'] = (T, dims['ag'])
+    if structure != 'flat' and ('buffer' in task_replay or task_replay == 'hand_designed'):
+        return [ReplayBuffer(shapes, buffer_size, T, sampler, device=device) for _ in range(nb_tasks + 1)]
+    return ReplayBuffer(shapes, buffer_size, T, sampler, device=device)
+
+
+def make_experiment(nb_tasks=4, n_controllable=None, structure='curious', task_selection='active_competence_progress',
+                    goal_replay='her', task_replay='replay_task_cp_buffer', seed=0, device=None, normalize_obs=False,
+                    make_env=None, **overrides):
+    """config.prepare_params + configure_* + the RolloutWorker pair of train.py:268-337.  Returns the keyword
+    arguments of train()."""
+    params = dict(FLAT_PARAMS if structure == 'flat' else MULTI_TASK_PARAMS)
+    params.update(overrides)
+    if make_env is None:
+        def make_env():
+            return ModularPointEnv(nb_tasks, n_controllable)
+    env = make_env()
+    T = env._max_episode_steps
+    gamma = 1. - 1. / T                                             # config.py:127
+    dims = configure_dims(env, structure)
+    ag_ids, g_ids = env.unwrapped.tasks_ag_id, env.unwrapped.tasks_g_id
+    reward = env.unwrapped.reward_spec                              # config.py:158-159 as data (see reward.py)
+    if structure == 'flat':
+        sampler = her.make_sample_her_transitions(goal_replay, params['her_replay_k'], reward, '', tasks_ag_id=ag_ids,
+                                                  tasks_g_id=g_ids)
+        task_replay = ''
+    else:
+        sampler = her.make_sample_multi_task_her_transitions(goal_replay, params['her_replay_k'], task_replay, reward,
+                                                             tasks_ag_id=ag_ids, tasks_g_id=g_ids)
+    ddpg_kw = dict(input_dims=dims, hidden=params['hidden'], layers=params['layers'], network_class=params['network_class'],
+                   polyak=params['polyak'], batch_size=params['batch_size'], Q_lr=params['Q_lr'], pi_lr=params['pi_lr'],
+                   norm_eps=params['norm_eps'], norm_clip=params['norm_clip'], max_u=params['max_u'],
+                   action_l2=params['action_l2'], clip_obs=params['clip_obs'], scope=params['scope'], T=T,
+                   rollout_batch_size=params['rollout_batch_size'], subtract_goals=lambda a, b: a - b,
+                   relative_goals=params['relative_goals'], clip_pos_returns=True, clip_return=1. / (1. - gamma),
+                   normalize_obs=normalize_obs, sample_transitions=sampler, gamma=gamma, tasks_ag_id=ag_ids, tasks_g_id=g_ids,
+                   task_replay=task_replay, eps_task=params.get('eps_task'), structure=structure, her_rng='philox',
+                   seed=seed, device=device)
+    buffers = configure_buffer({k: v for k, v in dims.items() if structure != 'flat' or k != 'task_descr'}, T, sampler,
+                               params['buffer_size'], structure, task_replay, nb_tasks, device=device)
+    rollout_kw = dict(dims=dims, logger=None, T=T, rollout_batch_size=params['rollout_batch_size'], structure=structure,
+                      task_selection=task_selection, queue_length=params['queue_length'])
+    explore = dict(rollout_kw, exploit=False, use_target_net=False, compute_Q=False, noise_eps=params['noise_eps'],
+                   random_eps=params['random_eps'])
+    test = dict(rollout_kw, exploit=True, use_target_net=params['test_with_polyak'], compute_Q=True, eval=True)
+    if structure == 'task_experts':                                 # train.py:287-289,325-331
+        policy = [DDPG(buffers=buffers, t_id=i, **ddpg_kw) for i in range(nb_tasks)]
+        rollout_worker = [RolloutWorker(make_env, policy[i], unique_task=i, **explore) for i in range(nb_tasks)]
+    else:
+        policy = DDPG(buffers=buffers, **ddpg_kw)
+        rollout_worker = RolloutWorker(make_env, policy, **explore)
+    evaluator = RolloutWorker(make_env, policy, **test)
+    for i, w in enumerate((rollout_worker if isinstance(rollout_worker, list) else [rollout_worker]) + [evaluator]):
+        w.seed(seed + 10 * i)
+    return dict(policy=policy, rollout_worker=rollout_worker, evaluator=evaluator, n_cycles=params['n_cycles'],
+                n_batches=params['n_batches'], n_test_rollouts=params['n_test_rollouts'], structure=structure,
+                task_selection=task_selection, eps_task=params.get('eps_task', 0.4))
+
+
+def _evaluate(evaluator, n_test_rollouts):
+    evaluator.clear_history()
+    evaluator.clear_competence_queue() if evaluator.modular else None
+    for _ in range(n_test_rollouts):
+        evaluator.generate_rollouts()
+    out = dict(test_success_rate=float(evaluator.current_success_rate()), test_mean_Q=float(evaluator.current_mean_Q()))
+    if evaluator.modular:
+        out['C'] = np.asarray(evaluator.get_C(), np.float64).copy()
+    return out
+
+
+def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles, n_batches, structure='curious',
+          task_selection='active_competence_progress', eps_task=0.4, log=None):
+    """train.py:48-170 without the file I/O: per epoch n_cycles x (rollouts -> store_episode -> n_batches x train ->
+    update_target_net), then n_test_rollouts evaluation rollouts.  Returns one dict per epoch."""
+    history = []
+    if structure == 'task_experts':
+        nb_tasks = len(policy)
+        p = 1 / nb_tasks * np.ones([nb_tasks])
+        for epoch in range(n_epochs):
+            if task_selection == 'random':
+                i_policy = epoch % nb_tasks                                  # train.py:79-81
+            else:
+                cps = [np.array([rollout_worker[i].get_CP()]).squeeze()[i] for i in range(nb_tasks)]   # train.py:84-101
+                CP = np.array(cps).copy()
+                if CP.sum() == 0:
+                    p = (1 / nb_tasks) * np.ones([nb_tasks])
+                else:
+                    p = eps_task * (1 / nb_tasks) * np.ones([nb_tasks]) + (1 - eps_task) * CP / CP.sum()
+                if p.sum() > 1:
+                    p[np.argmax(p)] -= p.sum() - 1
+                elif p.sum() < 1:
+                    p[-1] = 1 - p[:-1].sum()
+                i_policy = int(np.random.choice(range(nb_tasks), p=p))
+            rollout_worker[i_policy].clear_history()
+            for _ in range(n_cycles):
+                episode, cp, n_ep = rollout_worker[i_policy].generate_rollouts()
+                policy[i_policy].store_episode(episode, cp, n_ep)
+                for _ in range(n_batches):
+                    policy[i_policy].train()
+                policy[i_policy].update_target_net()
+            rec = dict(epoch=epoch, i_policy=i_policy, p=p.copy(), **_evaluate(evaluator, n_test_rollouts))
+            history.append(rec)
+            if log:
+                log(rec)
+        return history
+    for epoch in range(n_epochs):                                            # train.py:125-166
+        rollout_worker.clear_history()
+        for _ in range(n_cycles):
+            episode, cp, n_ep = rollout_worker.generate_rollouts()
+            policy.store_episode(episode, cp, n_ep)
+            for _ in range(n_batches):
+                policy.train()
+            policy.update_target_net()
+        rec = dict(epoch=epoch, train_success_rate=float(rollout_worker.current_success_rate()),
+                   **_evaluate(evaluator, n_test_rollouts))
+        if rollout_worker.modular:
+            rec['CP'] = np.asarray(rollout_worker.get_CP(), np.float64).copy()
+            rec['p'] = np.asarray(rollout_worker.p, np.float64).copy()
+        history.append(rec)
+        if log:
+            log(rec)
+    return history
