@@ -81,7 +81,7 @@ class Batch(C.Structure):
 class DdpgHyper(C.Structure):
     _fields_ = [('gamma', C.c_float), ('clip_return', C.c_float), ('action_l2', C.c_float),
                 ('clip_pos_returns', C.c_int32), ('step_counter', C.c_void_p), ('loss_ring', C.c_int32),
-                ('micro_batches', C.c_int32), ('grads_parity_stride', C.c_int64)]
+                ('micro_batches', C.c_int32), ('grads_parity_stride', C.c_int64), ('loss_rows', C.c_int64)]
 
 
 class DdpgExpert(C.Structure):

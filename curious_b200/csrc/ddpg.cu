@@ -212,6 +212,8 @@ struct LossParams {
   float gamma, clip_return, action_l2;
   int clip_pos;
   float *dQ, *dQpi, *q_loss, *pi_loss;
+  int64_t grad_rows;       // rows one loss mean runs over for the GRADIENT seeds (n, or the per-worker batch when the
+                           // launch carries several reference workers, cur_ddpg_hyper.loss_rows)
   int64_t* step_counter;   // optional: losses go to slot (*step % ring), then *step += 1
   int ring;
 };
@@ -220,14 +222,15 @@ __global__ void __launch_bounds__(1024) loss_kernel(const __grid_constant__ Loss
   __shared__ float red[3][32];
   float ssq = 0.f, sq = 0.f, sth = 0.f;
   const float inv_n = 1.0f / (float)P.n;
+  const float inv_g = 1.0f / (float)P.grad_rows;
   const float hi = P.clip_pos ? 0.f : INFINITY;
   for (int64_t i = threadIdx.x; i < P.n; i += blockDim.x) {
     float tgt = fminf(fmaxf(P.r[i] + P.gamma * P.Qt[i], -P.clip_return), hi);   // ddpg.py:436-438
     float diff = tgt - P.Q[i];
     ssq += diff * diff;
     sq += P.Qpi[i];
-    P.dQ[i] = -2.0f * inv_n * diff;      // d mean((tgt - Q)^2) / dQ
-    P.dQpi[i] = -inv_n;                  // d (-mean(Q_pi)) / dQ_pi
+    P.dQ[i] = -2.0f * inv_g * diff;      // d mean((tgt - Q)^2) / dQ
+    P.dQpi[i] = -inv_g;                  // d (-mean(Q_pi)) / dQ_pi
   }
   for (int64_t i = threadIdx.x; i < P.n * P.dimu; i += blockDim.x) {
     int64_t r = i / P.dimu;
@@ -280,14 +283,15 @@ __global__ void __launch_bounds__(512) loss_mc_kernel(const __grid_constant__ Lo
   const int64_t r0 = per * blockIdx.x, r1 = (r0 + per < P.n) ? r0 + per : P.n;
   float ssq = 0.f, sq = 0.f, sth = 0.f;
   const float inv_n = 1.0f / (float)P.n;
+  const float inv_g = 1.0f / (float)P.grad_rows;
   const float hi = P.clip_pos ? 0.f : INFINITY;
   for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
     float tgt = fminf(fmaxf(P.r[i] + P.gamma * P.Qt[i], -P.clip_return), hi);   // ddpg.py:436-438
     float diff = tgt - P.Q[i];
     ssq += diff * diff;
     sq += P.Qpi[i];
-    P.dQ[i] = -2.0f * inv_n * diff;
-    P.dQpi[i] = -inv_n;
+    P.dQ[i] = -2.0f * inv_g * diff;
+    P.dQpi[i] = -inv_g;
     for (int j = 0; j < P.dimu; ++j) {
       const float t = P.th[i * P.ldth + j];
       sth += t * t;
@@ -596,6 +600,7 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
     LPm.n = n; LPm.gamma = x.h->gamma; LPm.clip_return = x.h->clip_return; LPm.action_l2 = x.h->action_l2;
     LPm.clip_pos = x.h->clip_pos_returns; LPm.dQ = w.dQ; LPm.dQpi = w.dQpi; LPm.q_loss = x.q_loss; LPm.pi_loss = x.pi_loss;
     LPm.step_counter = x.h->step_counter; LPm.ring = x.h->loss_ring;
+    LPm.grad_rows = x.h->loss_rows > 0 ? x.h->loss_rows : n;
     if (n >= LOSS_MC_MIN_BATCH) {
       LossMcParams MC;
       MC.L = LPm; MC.part = w.loss_part; MC.ticket = w.loss_ticket;
@@ -638,7 +643,7 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
     GemmProb p = bwd_dx(w.da[cur], H, x.mQ + LQ.off_W0 + (int64_t)LP.in_s * H, d->dimu, H, nullptr, 0, w.dy,
                         (int)r4(d->dimu), n);
     p.epi = EPI_ACTOR_DY; p.aux = x.th; p.ldaux = w.ld_sq;
-    p.coef = x.h->action_l2 * 2.0f / (float)(n * d->dimu);
+    p.coef = x.h->action_l2 * 2.0f / (float)((x.h->loss_rows > 0 ? x.h->loss_rows : n) * d->dimu);
     ADD(p);
   }
   CUR_TRY(B.flush());

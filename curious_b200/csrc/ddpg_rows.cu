@@ -1036,6 +1036,7 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     CUR_REQUIRE(!d->modular || batch->td, "task_descr required for a modular net");
   }
   CUR_REQUIRE(rows_supported(d, batch->n), "shape not supported by the rows schedule (see cur_ddpg_rows_supported)");
+  CUR_REQUIRE(h->loss_rows == 0 || h->loss_rows == batch->n, "loss_rows is a cur_ddpg_grads option (use micro_batches here)");
   if (d->normalize_obs)
     CUR_REQUIRE(stats && stats->o_mean && stats->o_std && stats->g_mean && stats->g_std, "normalizer stats required");
   if (adam) {

@@ -493,9 +493,10 @@ class DDPG(object):
                 _lib.set_cdf(d, apportion.cp_probabilities(self.cp, self.eps_task))
             elif self.sample_transitions.mode == _lib.MODE_CP_TASK:
                 _lib.set_cdf(d, np.ones(self.nb_tasks) / self.nb_tasks)
+        mult = self._graph_rows // self.batch_size          # wide batch: every worker's apportioning, k times
         for i, (buf, _) in enumerate(segs):
             d.n_episodes[i] = int(buf.current_size)
-            d.count[i] = int(prop[i])
+            d.count[i] = int(prop[i]) * mult
         C.memmove(self._dyn_host.data_ptr(), C.addressof(d), C.sizeof(d))
         self._dyn_dev.copy_(self._dyn_host, non_blocking=True)
         self._graph_sig = sig
@@ -503,7 +504,14 @@ class DDPG(object):
     def _prepare_graph_state(self):
         """Device-resident state of the graph path (control block, loss rings, Adam tables, fixed batch buffers)."""
         dev = self.device
-        B = self.batch_size
+        # several workers per rank as ONE wide batch on the tensor-core levels schedule when that batch is large enough
+        # (k x batch_size >= 1024 rows): same gradient as k single-batch launches (loss seeds scaled by 1 / batch_size,
+        # cur_ddpg_hyper.loss_rows), 3x faster at 19 workers; otherwise k accumulating launches of the rows schedule
+        k = self.workers_per_rank
+        self._wide = bool(k > 1 and _lib.load().cur_ddpg_uses_tensor_cores(C.byref(self.net.desc), k * self.batch_size))
+        self._graph_rows = self.batch_size * (k if self._wide else 1)
+        self._micro = 1 if self._wide else k
+        B = self._graph_rows
         L = self._all_segments()[0][0].layout
         self._dyn_struct = _lib.HerDyn()
         self._dyn_struct.step = self._step.data_ptr()
@@ -524,9 +532,12 @@ class DDPG(object):
         self._gwant = tuple(want)
         self._ghyper = _lib.DdpgHyper(self._hyper.gamma, self._hyper.clip_return, self._hyper.action_l2,
                                       self._hyper.clip_pos_returns, self._step.data_ptr(), self.LOSS_RING,
-                                      self.workers_per_rank if self.workers_per_rank > 1 else 0)
-        if self.workers_per_rank > 1 and not self._use_rows(B):
-            raise ValueError('workers_per_rank > 1 on the CUDA-graph path needs the rows schedule')
+                                      self._micro if self._micro > 1 else 0)
+        if self._wide:
+            self._ghyper.loss_rows = self.batch_size
+        if self._micro > 1 and not self._use_rows(B):
+            raise ValueError('workers_per_rank > 1 on the CUDA-graph path needs the rows schedule or a batch the '
+                             'tensor-core levels schedule takes (workers x batch_size >= 1024, a multiple of 128)')
         self._workspace_rows(B) if self._use_rows(B) else self._workspace(B)
         self._peer = None
         if self._want_peer_exchange():
@@ -534,7 +545,7 @@ class DDPG(object):
             # the sharded exchange moves 8x fewer bytes at 8 GPUs but measured no faster (2 GPUs: 83 us full / 91 us
             # sharded, 8 GPUs: 97.3 / 98.2): the exchange is latency / straggler bound, so the one-round kernel is default
             self._peer = PeerGradExchange(self.net.arena, self.comm, sharded=self.grad_exchange == 'p2p_sharded')
-            self._peer.ctx.step_div = self.workers_per_rank
+            self._peer.ctx.step_div = self._micro
             self._ghyper.grads_parity_stride = self.net.arena
         self._graph_sig = None
         self._refresh_dyn()
@@ -580,7 +591,7 @@ class DDPG(object):
         if n <= 1 or self.grad_exchange == 'nccl':
             return False
         import torch.distributed as dist
-        ok = (self._use_rows(self.batch_size) and self._same_rule() and n <= _lib.CUR_MAX_RANKS and
+        ok = (self._use_rows(self._graph_rows) and self._same_rule() and n <= _lib.CUR_MAX_RANKS and
               dist.get_backend(group) == 'nccl')
         if self.grad_exchange in ('p2p', 'p2p_sharded') and not ok:
             raise ValueError('grad_exchange="p2p" needs the rows schedule, one Adam rule for both nets and an NCCL '
@@ -599,17 +610,17 @@ class DDPG(object):
         sampler = self.sample_transitions
         segs = [(buf.device_view(), 0, ttr) for buf, ttr in self._all_segments()]
         her_args = None
-        if self._use_rows(self.batch_size) and self.fuse_her:
+        if self._use_rows(self._graph_rows) and self.fuse_her:
             # rows schedule: every CTA of the update kernel samples its own rows (no separate HER launch)
             her_args, self._her_keep = sampler.sample_device(
-                segs, self.batch_size, clip_obs=self.clip_obs, relative_goals=self.relative_goals, want=(),
+                segs, self._graph_rows, clip_obs=self.clip_obs, relative_goals=self.relative_goals, want=(),
                 dyn=self._dyn_dev.data_ptr(), call_offset=self.GRAPH_STREAM_OFFSET, args_only=True)
         else:
-            sampler.sample_device(segs, self.batch_size, clip_obs=self.clip_obs, relative_goals=self.relative_goals,
+            sampler.sample_device(segs, self._graph_rows, clip_obs=self.clip_obs, relative_goals=self.relative_goals,
                                   want=self._gwant, out=self._gbatch, dyn=self._dyn_dev.data_ptr(),
                                   call_offset=self.GRAPH_STREAM_OFFSET)
         b = self._gbatch
-        n = self.batch_size
+        n = self._graph_rows
         g2 = b['g_2'] if self.relative_goals else b['g']       # g_2 == g without relative goals (ddpg.py:353)
         cb = _lib.Batch(b['o'].data_ptr(), b['g'].data_ptr(), b['u'].data_ptr(),
                         b['td'].data_ptr() if self.modular else None, b['o_2'].data_ptr(), g2.data_ptr(),
@@ -618,12 +629,12 @@ class DDPG(object):
         if self._use_rows(n):
             # with one rank there is no all-reduce between _grads and _update: Adam runs in the epilogue of
             # the weight-gradient launch (2 launches per update after the HER kernel)
-            fuse = self._same_rule() and _world(self.comm)[1] == 1 and self.workers_per_rank == 1
+            fuse = self._same_rule() and _world(self.comm)[1] == 1 and self._micro == 1
             adam = _lib.AdamFused(self._adam_m.data_ptr(), self._adam_v.data_ptr(), self._adam_tables[0].data_ptr(),
                                   self.ADAM_TABLE, 1 if keep_wT else 0, qa.beta1, qa.beta2, qa.epsilon) if fuse else None
-            for j in range(self.workers_per_rank):
+            for j in range(self._micro):
                 if j > 0 and her_args is None:            # unfused sampling: a fresh batch for every worker
-                    sampler.sample_device(segs, self.batch_size, clip_obs=self.clip_obs,
+                    sampler.sample_device(segs, self._graph_rows, clip_obs=self.clip_obs,
                                           relative_goals=self.relative_goals, want=self._gwant, out=self._gbatch,
                                           dyn=self._dyn_dev.data_ptr(), call_offset=self.GRAPH_STREAM_OFFSET)
                 _lib.check(lib.cur_ddpg_rows_step(
@@ -652,7 +663,7 @@ class DDPG(object):
             if warmup:
                 solo = _lib.P2PCtx()
                 solo.rank, solo.world, solo.arena = 0, 1, self._peer.arena
-                solo.step_div = self.workers_per_rank
+                solo.step_div = self._micro
                 solo.region[0] = self._peer.own
                 _lib.check(lib.cur_p2p_allreduce_adam(
                     _lib.stream_ptr(), C.byref(solo), self.theta_main.data_ptr(), self._adam_m.data_ptr(),
@@ -669,13 +680,13 @@ class DDPG(object):
             _lib.check(lib.cur_adam_step_graph(
                 _lib.stream_ptr(), self.theta_main.data_ptr(), self.grads.data_ptr(), self._adam_m.data_ptr(),
                 self._adam_v.data_ptr(), self.theta_main.numel(), self._adam_tables[0].data_ptr(), self.ADAM_TABLE,
-                self._step.data_ptr(), qa.beta1, qa.beta2, qa.epsilon, 1.0, self.workers_per_rank), 'cur_adam_step_graph')
+                self._step.data_ptr(), qa.beta1, qa.beta2, qa.epsilon, 1.0, self._micro), 'cur_adam_step_graph')
             return
         for adam, which, table in ((self.Q_adam, 'Q', self._adam_tables[0]), (self.pi_adam, 'pi', self._adam_tables[1])):
             _lib.check(lib.cur_adam_step_graph(
                 _lib.stream_ptr(), adam.theta.data_ptr(), self._view(self.grads, which).data_ptr(), adam.m.data_ptr(),
                 adam.v.data_ptr(), adam.theta.numel(), table.data_ptr(), self.ADAM_TABLE, self._step.data_ptr(),
-                adam.beta1, adam.beta2, adam.epsilon, 1.0, self.workers_per_rank), 'cur_adam_step_graph')
+                adam.beta1, adam.beta2, adam.epsilon, 1.0, self._micro), 'cur_adam_step_graph')
 
     def _refresh_wT(self):
         """Rebuild the transposed hidden-layer weights in the rows workspace after theta_main changed outside the
@@ -694,9 +705,9 @@ class DDPG(object):
             self.Q_adam.check_synced()
             self.pi_adam.check_synced()
         self._refresh_dyn()
-        if self._graph_fused and self._wT_dirty:
+        if self._graph_fused and self._wT_dirty:          # (only the rows schedule with the fused optimiser)
             self._refresh_wT()
-        k = self.workers_per_rank          # the loss of the rank's last worker (device ring slot = launch index % ring)
+        k = self._micro                    # the loss of the rank's last worker (device ring slot = launch index % ring)
         slot = (self._n_updates * k + k - 1) % self.LOSS_RING
         self._graph.replay()
         if not self._graph_has_adam:

@@ -474,3 +474,54 @@ def test_workers_per_rank_sums_single_batch_gradients():
         assert np.array_equal(g.get_flat(which), e.get_flat(which)), which
     assert torch.equal(g.Q_adam.m, e.Q_adam.m) and torch.equal(g.pi_adam.v, e.pi_adam.v)
     assert int(g._step.item()) == int(e._step.item()) == 5 * k and g.Q_adam.t == 5
+
+
+def test_wide_batch_of_workers_equals_sum_of_single_batch_gradients():
+    """workers_per_rank as ONE wide batch (k x 256 >= 1024 rows on the tensor-core levels schedule): with the
+    backward seeds scaled by 1 / 256 (cur_ddpg_hyper.loss_rows) the gradient of the wide batch is the SUM of the k
+    single-batch gradients - the reference's SUM all-reduce over k workers (ddpg.py:452-453)."""
+    import torch
+    from curious_b200 import _lib
+    k = 4
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4)
+    cp = np.array([0.05, 0.2, 0.1, 0.0])
+    a = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy', update_schedule='levels')
+    np.random.seed(21)
+    _fill(a, episode_stream(dims, kw['T'], 8), cp)
+    np.random.seed(22)
+    batches = [a.sample_batch() for _ in range(k)]
+    lib = _lib.load()
+    try:
+        lib.cur_ddpg_set_tensor_cores(0)
+        total, losses = None, []
+        for b in batches:
+            a.stage_batch(b)
+            ql, _, _, _ = a._grads()
+            losses.append(float(ql))
+            total = a.grads.clone() if total is None else total + a.grads
+        wide = [np.concatenate([b[i] for b in batches], axis=0) for i in range(len(batches[0]))]
+        for mode, tol in ((0, 2e-6), (1, GRAD_RTOL)):          # FFMA: summation order only; tcgen05: 3xTF32
+            lib.cur_ddpg_set_tensor_cores(mode)
+            a._hyper.loss_rows = kw['batch_size']
+            a.stage_batch(wide)
+            ql, qpi, _, _ = a._grads()
+            a._hyper.loss_rows = 0
+            assert qpi.shape == (k * kw['batch_size'], 1)
+            assert abs(float(ql) - np.mean(losses)) <= 1e-5 * abs(np.mean(losses))      # mean over all workers' rows
+            for which in ('Q', 'pi'):
+                assert rel_err(a._view(a.grads, which).cpu().numpy(), a._view(total, which).cpu().numpy()) <= tol, (mode, which)
+    finally:
+        lib.cur_ddpg_set_tensor_cores(-1)
+        a._hyper.loss_rows = 0
+    # the CUDA-graph path picks the wide form on its own and counts one device step / one Adam step per update
+    g = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', workers_per_rank=k)
+    np.random.seed(21)
+    _fill(g, episode_stream(dims, kw['T'], 8), cp)
+    out = [float(g.train()[0]) for _ in range(5)]
+    assert g._wide and g._graph_rows == k * kw['batch_size'] and np.isfinite(out).all()
+    assert int(g._step.item()) == 5 and g.Q_adam.t == 5
+    small = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', workers_per_rank=3)      # 768 rows: accumulating launches
+    np.random.seed(21)
+    _fill(small, episode_stream(dims, kw['T'], 8), cp)
+    small.train()
+    assert not small._wide and small._micro == 3
