@@ -110,8 +110,8 @@ static Workspace carve(const cur_net_desc& d, int64_t n, float* base) {
     dwp.M = w.H; dwp.N = w.H; dwp.K = (int)n; dwp.a_trans = 1;
     w.tc_part_stride = r4(tc_partial_floats(dwp));
     w.tc_rowpart_stride = r4(tc_rowred_partial_floats(n, w.H, 4));
-    w.tc_part = take(TC_SLOTS * w.tc_part_stride);
-    w.tc_rowpart = take(TC_SLOTS * w.tc_rowpart_stride);
+    w.tc_part = take(2 * TC_SLOTS * w.tc_part_stride);          // two sets: the reductions of a level are deferred
+    w.tc_rowpart = take(2 * TC_SLOTS * w.tc_rowpart_stride);    // (TcLauncher::flush), the next level uses the other set
   }
   w.total = o;
   return w;
@@ -359,7 +359,7 @@ struct Batcher {
     if (tc && !p.ones_a && tc_supported(p)) {
       const bool split = tc_pick_splits(p) > 1;
       if (!split || (parts_used < TC_SLOTS && tc_partial_floats(p) <= part_stride)) {
-        const int r = T.add(p, split ? tc_part + parts_used * part_stride : nullptr);
+        const int r = T.add(p, split ? tc_part + ((T.level & 1) * TC_SLOTS + parts_used) * part_stride : nullptr);
         if (r != CUR_OK) rc = r;
         if (split) ++parts_used;
         return;
@@ -370,7 +370,7 @@ struct Batcher {
     const bool skinny = !p.ones_a && p.a_trans && !p.b_trans && p.N <= 4 && p.K2 == 0 && p.ldc == p.N && p.epi == EPI_NONE &&
                         p.bias == nullptr && p.C2 == nullptr;
     if (tc && (colsum || skinny) && rowparts_used < TC_SLOTS) {
-      float* part = tc_rowpart + rowparts_used * rowpart_stride;
+      float* part = tc_rowpart + ((T.level & 1) * TC_SLOTS + rowparts_used) * rowpart_stride;
       const int r = colsum ? T.add_rowred(p.B, p.ldb, p.N, nullptr, 0, 1, p.K, p.C, part)
                            : T.add_rowred(p.A, p.lda, p.M, p.B, p.ldb, p.N, p.K, p.C, part);
       if (r != CUR_OK) rc = r;
@@ -674,6 +674,7 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
     if (LP.in_g > 0) ADD(bwd_dw(w.Xg, w.ld_g, LP.in_g, w.dp[cur], H, H, x.gP + LP.off_W0g, n));
   }
   CUR_TRY(B.flush());
+  CUR_TRY(B.B.T.finish(s));               // deferred reductions of the last levels -> gradients complete on `s`
 #undef FOR_EXPERTS
 #undef ADD
   return CUR_OK;

@@ -765,7 +765,8 @@ int64_t tc_rowred_partial_floats(int64_t rows, int M, int NJ) {
 // the two become parallel branches), filling the SMs' idle issue slots and the L2 while the tcgen05 tiles run.
 struct SideStream {
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, gemm = nullptr;
+  cudaEvent_t red[2] = {nullptr, nullptr};      // "the reductions of the last level that used partial set 0 / 1 are done"
   int device = -1;
 };
 static int side_stream(SideStream** out) {
@@ -776,6 +777,9 @@ static int side_stream(SideStream** out) {
     CUR_CUDA_TRY(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
     CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
     CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.gemm, cudaEventDisableTiming));
+    CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.red[0], cudaEventDisableTiming));
+    CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.red[1], cudaEventDisableTiming));
     ss.device = dev;
   }
   *out = &ss;
@@ -791,17 +795,27 @@ int TcLauncher::flush(cudaStream_t s_main) {
   }
   cudaStream_t s = s_main;
   SideStream* ss = nullptr;
-  const bool forked = G.n > 0 && (n_skinny > 0 || n_rowred > 0);
+  const bool forked = G.n > 0 && (n_skinny > 0 || n_rowred > 0 || R.n > 0);
+  const int set = level & 1;
   if (forked) {
     CUR_TRY(side_stream(&ss));
     CUR_CUDA_TRY(cudaEventRecord(ss->fork, s_main));
     CUR_CUDA_TRY(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
     s = ss->stream;                       // helpers below go to the side stream
   }
+  // the split-K / row-reduction partials of this level live in workspace set `set`: the deferred reductions of the
+  // level that used the set before (two levels ago) must have read them
+  if (red_pending[set]) {
+    if (!ss) CUR_TRY(side_stream(&ss));
+    CUR_CUDA_TRY(cudaStreamWaitEvent(s_main, ss->red[set], 0));
+    if (forked) CUR_CUDA_TRY(cudaStreamWaitEvent(ss->stream, ss->red[set], 0));
+    red_pending[set] = false;
+  }
   if (G.n > 0) {
     B.n = G.n; B.total_tiles = G.total_tiles; B.tl = g_tc_timeline;
     tc_gemm_kernel<<<G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s_main>>>(B);
     CUR_CHECK_LAUNCH();
+    if (forked) CUR_CUDA_TRY(cudaEventRecord(ss->gemm, s_main));
   }
   if (n_skinny > 0) {
     SkinnyBatch S;
@@ -839,9 +853,12 @@ int TcLauncher::flush(cudaStream_t s_main) {
     CUR_CHECK_LAUNCH();
   }
   if (forked) {
+    // the caller's stream only waits for the skinny kernels / row reductions (their outputs may feed the next level);
+    // the fixed-order sums of the partials produce weight / bias gradients that nothing reads before the optimiser,
+    // so they stay on the side stream behind the tensor-core launch and are joined in finish()
     CUR_CUDA_TRY(cudaEventRecord(ss->join, ss->stream));
     CUR_CUDA_TRY(cudaStreamWaitEvent(s_main, ss->join, 0));
-    s = s_main;
+    CUR_CUDA_TRY(cudaStreamWaitEvent(ss->stream, ss->gemm, 0));
   }
   if (R.n > 0) {
     CUR_REQUIRE(R.n <= 2 * TC_MAX_PROBS, "too many reductions");
@@ -852,12 +869,30 @@ int TcLauncher::flush(cudaStream_t s_main) {
     }
     tc_reduce_kernel<<<blocks, 256, 0, s>>>(R);
     CUR_CHECK_LAUNCH();
+    if (forked) {
+      CUR_CUDA_TRY(cudaEventRecord(ss->red[set], ss->stream));
+      red_pending[set] = true;
+    }
   }
+  ++level;
   G.n = 0; G.total_tiles = 0; R.n = 0; n_rowred = 0; n_skinny = 0;
   return CUR_OK;
 }
 
-TcLauncher::TcLauncher() : n_rowred(0), n_skinny(0) {
+// Join the deferred reductions into the caller's stream (end of cur_ddpg_grads, before the optimiser reads the gradients).
+int TcLauncher::finish(cudaStream_t s_main) {
+  SideStream* ss = nullptr;
+  for (int set = 0; set < 2; ++set) {
+    if (!red_pending[set]) continue;
+    if (!ss) CUR_TRY(side_stream(&ss));
+    CUR_CUDA_TRY(cudaStreamWaitEvent(s_main, ss->red[set], 0));
+    red_pending[set] = false;
+  }
+  return CUR_OK;
+}
+
+TcLauncher::TcLauncher() : n_rowred(0), n_skinny(0), level(0) {
+  red_pending[0] = red_pending[1] = false;
   static_assert(sizeof(TcBatch) <= sizeof(storage), "TcLauncher storage too small");
   G.n = 0; G.total_tiles = 0; R.n = 0;
 }
@@ -894,5 +929,6 @@ extern "C" int cur_tc_gemm(void* stream, const float* A, int64_t lda, int a_tran
   CUR_REQUIRE(tc_supported(p), "alignment: pointers 16-byte aligned, leading dimensions multiples of 4");
   TcLauncher L;
   CUR_TRY(L.add(p, workspace));
-  return L.flush((cudaStream_t)stream);
+  CUR_TRY(L.flush((cudaStream_t)stream));
+  return L.finish((cudaStream_t)stream);          // the split-K sum runs on the side stream: join it
 }

@@ -31,6 +31,8 @@ struct TcLauncher {
   int n_rowred;
   struct SkinnyDesc { GemmProb p; } skinny[TC_MAX_PROBS];
   int n_skinny;
+  int level;                 // flushes so far; partial workspaces alternate between two sets (level & 1)
+  bool red_pending[2];       // deferred reductions reading partial set 0 / 1 are still in flight on the side stream
   alignas(64) unsigned char storage[TC_MAX_PROBS * (4 * 128 + 128) + 64];   // TcBatch (tensor maps + problems)
   TcLauncher();
   int add(const GemmProb& p, float* partial);
@@ -41,6 +43,7 @@ struct TcLauncher {
   // bandwidth-bound problems with N <= 4 (output layers) or K <= 4 (backward through them), see tc_skinny_kernel
   int add_skinny(const GemmProb& p);
   int flush(cudaStream_t s);
+  int finish(cudaStream_t s);        // join the deferred reductions (call once after the last flush)
   bool empty() const { return G.n == 0 && R.n == 0 && n_rowred == 0 && n_skinny == 0; }
 };
 
