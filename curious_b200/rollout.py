@@ -1,13 +1,17 @@
-"""RolloutWorker - the caller of DDPG.get_actions / the producer of DDPG.store_episode's input.
+"""RolloutWorker - the caller of DDPG.get_actions and the producer of DDPG.store_episode's input.
 
-Mirror of reference baselines/her/rollout.py:13-491 (same constructor arguments, same methods, same episode
-dict) for environments with the gym_flowers attribute contract (curious_b200.envs.ModularPointEnv here, since
-gym_flowers / MuJoCo are absent).  What changed:
-  * one batched `policy.get_actions` device forward per timestep for all `rollout_batch_size` environments
-    (rollout.py:209-226 already batches per worker; with many envs per GPU rank this is north_star's "batched
-    get_actions on device, MuJoCo stepping on host cores"),
-  * the rank-0 LP block (rollout.py:316-404) lives in curious_b200.queues.CompetenceTracker; the MPI gathers /
-    scatters / broadcasts become torch.distributed object collectives,
+Same constructor arguments, public methods and episode dictionary as reference baselines/her/rollout.py:13-491, for
+environments with the gym_flowers attribute contract (curious_b200.envs.ModularPointEnv here: gym_flowers / MuJoCo
+are absent).  Built around fixed batch-major arrays instead of per-step Python lists:
+
+  * all `rollout_batch_size` environments of the rank are stepped on host cores, with ONE batched
+    `policy.get_actions` device forward per timestep (north_star: "MuJoCo stepping stays on host cores, with
+    batched get_actions on device"),
+  * the episode is written straight into [B, T(+1), dim] arrays (what store_episode wants; the reference builds
+    time-major lists and transposes them, util.py:174-184),
+  * task / goal draws for every rank are made on rank 0 in one go and scattered (rollout.py:118-140), the LP block
+    (rollout.py:316-404) lives in curious_b200.queues.CompetenceTracker; MPI collectives become torch.distributed
+    object collectives,
   * SAGG-RIAC goal selection (`goal_selection='active'`) is not supported (readme.md:19 marks it unsupported).
 """
 import pickle
@@ -17,7 +21,7 @@ import numpy as np
 
 from .parallel import rank as _rank, world as _world
 from .queues import CompetenceTracker
-from .util import convert_episode_to_batch_major, store_args
+from .util import store_args
 
 
 class RolloutWorker(object):
@@ -26,200 +30,177 @@ class RolloutWorker(object):
                  compute_Q=False, noise_eps=0, random_eps=0, history_len=100, render=False, structure='curious',
                  task_selection='random', goal_selection='random', queue_length=500, eval=False, unique_task=None,
                  temperature=None, **kwargs):
-        """See reference rollout.py:19-41 for the arguments."""
-        assert goal_selection != 'active', "goal_selection='active' (SAGG-RIAC) is unsupported, as in the reference readme"
+        """Arguments as in reference rollout.py:19-41."""
+        if goal_selection == 'active':
+            raise ValueError("goal_selection='active' (SAGG-RIAC) is unsupported, as in the reference readme")
+        assert T > 0
         self.comm = kwargs.get('comm')
+        self.rank, self.nb_cpu = _rank(self.comm), _world(self.comm)[1]
         self.envs = [make_env() for _ in range(rollout_batch_size)]
-        assert self.T > 0
-        self.info_keys = [key.replace('info_', '') for key in dims.keys() if key.startswith('info_')]
-        self.success_history = deque(maxlen=history_len)
-        self.reward_history = deque(maxlen=history_len)
-        self.Q_history = deque(maxlen=history_len)
+        core = self.envs[0].unwrapped
+        self.nb_tasks = core.nb_tasks
+        self.modular = structure in ('curious', 'task_experts')
+        self.info_keys = [k[len('info_'):] for k in dims if k.startswith('info_')]
         self.n_episodes = 0
-        self.g = np.empty((self.rollout_batch_size, self.dims['g']), np.float32)
-        self.initial_o = np.empty((self.rollout_batch_size, self.dims['o']), np.float32)
-        self.initial_ag = np.empty((self.rollout_batch_size, self.dims['ag']), np.float32)
-        self.rank = _rank(self.comm)
-        self.nb_cpu = _world(self.comm)[1]
-        self.nb_goals_per_rollout = self.nb_cpu * self.rollout_batch_size
-        self.nb_tasks = self.envs[0].unwrapped.nb_tasks
-        self.C = np.zeros([self.nb_tasks])
-        self.CP = np.zeros([self.nb_tasks])
-        self.modular = self.structure in ('curious', 'task_experts')
+        self.nb_goals_per_rollout = self.nb_cpu * rollout_batch_size
+        B = rollout_batch_size
+        self.g = np.zeros((B, dims['g']), np.float32)
+        self.initial_o = np.zeros((B, dims['o']), np.float32)
+        self.initial_ag = np.zeros((B, dims['ag']), np.float32)
+        self.task_descr = np.zeros((B, self.nb_tasks), np.float32)
+        self.C, self.CP = np.zeros(self.nb_tasks), np.zeros(self.nb_tasks)
+        self.success_history, self.reward_history, self.Q_history = (deque(maxlen=history_len) for _ in range(3))
+        self.task_history, self.goal_history = deque(), deque()
         if self.modular:
-            self.tasks_ag_id = self.envs[0].unwrapped.tasks_ag_id
-            self.tasks_g_id = self.envs[0].unwrapped.tasks_g_id
-            self.task_descr = np.empty((self.rollout_batch_size, self.nb_tasks), np.float32)
+            self.tasks_ag_id, self.tasks_g_id = core.tasks_ag_id, core.tasks_g_id
             self.tracker = CompetenceTracker(self.nb_tasks, queue_length=queue_length, task_selection=task_selection,
                                              structure=structure, unique_task=unique_task, eval=eval, comm=self.comm)
-            self.p = self.tracker.p.copy()
             self.competence_computers = self.tracker.competence_computers
-            self.task_history = deque()
-            self.goal_history = deque()
-        elif self.structure == 'flat':
+            self.p = self.tracker.p.copy()
+        else:
             for env in self.envs:
                 env.unwrapped.set_flat_env()
         self.stochastic_reset = False
         self.count = -1
         self.reset_all_rollouts()
-        self.clear_history()
 
-    # ------------------------------------------------------------------------------------------------------
-    def _scatter(self, per_rank_values):
-        """rank 0's list (one entry per rank) -> this rank's entry (MPI.COMM_WORLD.scatter, rollout.py:139-140)."""
+    # ---------------------------------------------------------------------------------------- tasks and goals
+    def _from_rank0(self, make):
+        """`make()` runs on rank 0 and returns one entry per rank; every rank gets its own (scatter)."""
         if self.nb_cpu == 1:
-            return per_rank_values[0]
+            return make()[0]
         import torch.distributed as dist
-        box = [per_rank_values if self.rank == 0 else None]
         group = _world(self.comm)[0]
+        box = [make() if self.rank == 0 else None]
         dist.broadcast_object_list(box, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
         return box[0][self.rank]
 
+    def _draw_assignment(self, i):
+        """Rank 0 picks (task, goal) for rollout slot i of every rank: task ~ p, goal uniform in [-1, 1]^len(g_id)."""
+        out = []
+        for cpu in range(self.nb_cpu):
+            if self.modular:
+                task = int(np.random.choice(self.nb_tasks, p=self.p))
+                goal = np.random.uniform(-1, 1, len(self.tasks_g_id[task]))
+            else:
+                task, goal = 0, np.random.uniform(-1, 1, self.dims['g'])
+            slot = cpu * self.rollout_batch_size + i
+            self.tasks[slot] = task
+            self.goals[slot] = self.envs[i].unwrapped._compute_goal(goal, task, eval=self.eval)[0]
+            out.append((task, goal))
+        return out
+
     def reset_rollout(self, i):
-        """rollout.py:104-165: reset env i, sample the next task (by p) and goal on rank 0, hand them to the env."""
-        env = self.envs[i].unwrapped
-        if self.eval or not self.stochastic_reset or np.random.rand() < 0.3 or self.exploit:
-            self.envs[i].reset()
+        """Reset environment i and give it its next task and goal (rollout.py:104-165)."""
+        env = self.envs[i]
+        if self.eval or self.exploit or not self.stochastic_reset or np.random.rand() < 0.3:
+            env.reset()
+        task, goal = self._from_rank0(lambda: self._draw_assignment(i))
+        self.count += 1
         if self.modular:
-            tasks, goals = [], []
-            if self.rank == 0:
-                tasks = np.random.choice(range(self.nb_tasks), p=self.p, size=self.nb_cpu).tolist()
-                goals = [np.random.uniform(-1, 1, len(self.tasks_g_id[tasks[c]])) for c in range(self.nb_cpu)]
-                for cpu in range(self.nb_cpu):
-                    good_ind = cpu * self.rollout_batch_size + i
-                    self.tasks[good_ind] = tasks[cpu]
-                    self.goals[good_ind] = env._compute_goal(goals[cpu], tasks[cpu], eval=self.eval)[0][
-                        self.tasks_g_id[tasks[cpu]]]
-            task = self._scatter(tasks)
-            goal = self._scatter(goals)
-            self.count += 1
-            obs = env.reset_task_goal(goal=goal, task=task, directly=False, eval=self.eval)
-        else:
-            goals = []
-            if self.rank == 0:
-                goals = [np.random.uniform(-1, 1, self.dims['g']) for _ in range(self.nb_cpu)]
-            obs = env.reset_task_goal(goal=self._scatter(goals))
-        self.initial_o[i] = obs['observation']
-        self.initial_ag[i] = obs['achieved_goal']
-        self.g[i] = obs['desired_goal']
-        if self.modular:
+            obs = env.unwrapped.reset_task_goal(goal=goal, task=task, directly=False, eval=self.eval)
             self.task_descr[i] = obs['mask']
+        else:
+            obs = env.unwrapped.reset_task_goal(goal=goal)
+        self.initial_o[i], self.initial_ag[i], self.g[i] = obs['observation'], obs['achieved_goal'], obs['desired_goal']
 
     def reset_all_rollouts(self):
-        self.goals = [[] for _ in range(self.nb_goals_per_rollout)]
-        if self.modular:
-            self.tasks = [[] for _ in range(self.nb_goals_per_rollout)]
+        self.goals = [None] * self.nb_goals_per_rollout
+        self.tasks = [None] * self.nb_goals_per_rollout
         for i in range(self.rollout_batch_size):
             self.reset_rollout(i)
 
-    # ------------------------------------------------------------------------------------------------------
+    # ---------------------------------------------------------------------------------------------- acting
+    def _act(self, o, ag):
+        """One device forward for all environments of the rank -> (u [B, dimu], Q [B, 1] or None)."""
+        quiet = self.exploit
+        kw = dict(compute_Q=self.compute_Q, noise_eps=0. if quiet else self.noise_eps,
+                  random_eps=0. if quiet else self.random_eps, use_target_net=self.use_target_net)
+        if self.structure == 'task_experts' and self.eval:
+            # evaluation of experts: the expert of the demanded task acts (rollout.py:211-223)
+            u = np.zeros((len(o), self.dims['u']))
+            q = np.zeros((len(o), 1))
+            for i in range(len(o)):
+                expert = self.policy[int(np.argmax(self.task_descr[i]))]
+                out = expert.get_actions(o[i:i + 1], ag[i:i + 1], self.g[i:i + 1], task_descr=self.task_descr[i:i + 1], **kw)
+                if self.compute_Q:
+                    u[i], q[i, 0] = out[0], np.asarray(out[1]).reshape(-1)[0]
+                else:
+                    u[i] = out
+            return u, (q if self.compute_Q else None)
+        out = self.policy.get_actions(o, ag, self.g, task_descr=self.task_descr if self.modular else None, **kw)
+        u, q = (out if self.compute_Q else (out, None))
+        return np.asarray(u).reshape(len(o), -1), q
+
     def generate_rollouts(self):
-        """rollout.py:178-406.  Returns (episode batch-major, CP, n_episodes)."""
-        if self.modular and not self.eval:
-            self.exploit = True if np.random.random() < 0.1 else False        # competence is measured without noise
-            if self.exploit and self.structure == 'curious':
-                self.p = 1 / self.nb_tasks * np.ones([self.nb_tasks])
-        elif self.eval:
+        """`rollout_batch_size` episodes of T steps with the current policy (rollout.py:178-406).
+        Returns (episode {key: [B, T(+1), dim]}, CP, n_episodes)."""
+        if self.eval:
             self.exploit = True
-            if self.modular:
-                self.p = 1 / self.nb_tasks * np.ones([self.nb_tasks])
+        elif self.modular:
+            self.exploit = bool(np.random.random() < 0.1)       # competence is measured on noise-free rollouts
+        if self.modular and self.exploit and (self.eval or self.structure == 'curious'):
+            self.p = np.ones(self.nb_tasks) / self.nb_tasks
         self.reset_all_rollouts()
-        B = self.rollout_batch_size
-        o = np.empty((B, self.dims['o']), np.float32)
-        ag = np.empty((B, self.dims['ag']), np.float32)
-        o[:] = self.initial_o
-        ag[:] = self.initial_ag
-        obs, achieved_goals, acts, goals, successes = [], [], [], [], []
-        info_values = [np.empty((self.T, B, self.dims['info_' + key]), np.float32) for key in self.info_keys]
-        Qs, task_descrs, changes = [], [], []
-        r_competence = np.zeros(B)
-        for t in range(self.T):
-            if self.structure == 'task_experts' and self.eval:
-                act_output = np.zeros([B, self.dims['u']])
-                q_output = np.zeros([B, 1])
-                for i in range(B):                    # the expert of the demanded task acts (rollout.py:211-223)
-                    tsk = int(np.argmax(self.task_descr[i]))
-                    out = self.policy[tsk].get_actions(o[i:i + 1], ag[i:i + 1], self.g[i:i + 1],
-                                                       task_descr=self.task_descr[i:i + 1], compute_Q=self.compute_Q,
-                                                       noise_eps=0., random_eps=0., use_target_net=self.use_target_net)
-                    if self.compute_Q:
-                        act_output[i, :], q_output[i, 0] = out[0], np.asarray(out[1]).reshape(-1)[0]
-                    else:
-                        act_output[i, :] = out
-                policy_output = [act_output, q_output] if self.compute_Q else act_output
-            else:
-                policy_output = self.policy.get_actions(
-                    o, ag, self.g, task_descr=self.task_descr if self.modular else None, compute_Q=self.compute_Q,
-                    noise_eps=self.noise_eps if not self.exploit else 0.,
-                    random_eps=self.random_eps if not self.exploit else 0., use_target_net=self.use_target_net)
-            if self.compute_Q:
-                u, Q = policy_output
-                Qs.append(Q)
-            else:
-                u = policy_output
-            if u.ndim == 1:
-                u = u.reshape(1, -1)
-            o_new = np.empty((B, self.dims['o']))
-            ag_new = np.empty((B, self.dims['ag']))
-            success = np.zeros(B)
-            for i in range(B):
-                curr_o_new, r_competence[i], _, info = self.envs[i].step(u[i])   # reward is recomputed for HER
-                if 'is_success' in info:
-                    success[i] = info['is_success']
-                o_new[i] = curr_o_new['observation']
-                ag_new[i] = curr_o_new['achieved_goal']
-                self.g[i] = curr_o_new['desired_goal']
-                for idx, key in enumerate(self.info_keys):
-                    info_values[idx][t, i] = info[key]
-            if np.isnan(o_new).any():
+        B, T, d = self.rollout_batch_size, self.T, self.dims
+        ep = {'o': np.zeros((B, T + 1, d['o'])), 'ag': np.zeros((B, T + 1, d['ag'])), 'u': np.zeros((B, T, d['u'])),
+              'g': np.zeros((B, T, d['g']))}
+        if self.modular:
+            ep['task_descr'] = np.zeros((B, T, self.nb_tasks))
+            ep['change'] = np.zeros((B, T, d['ag']), bool)
+        for key in self.info_keys:
+            ep['info_' + key] = np.zeros((B, T, d['info_' + key]), np.float32)
+        ep['o'][:, 0], ep['ag'][:, 0] = self.initial_o, self.initial_ag
+        success = np.zeros(B)
+        env_reward = np.zeros(B)
+        q_sum = 0.0
+        for t in range(T):
+            u, q = self._act(ep['o'][:, t].astype(np.float32), ep['ag'][:, t].astype(np.float32))
+            if q is not None:
+                q_sum += float(np.mean(q))
+            ep['u'][:, t], ep['g'][:, t] = u, self.g
+            if self.modular:
+                ep['task_descr'][:, t] = self.task_descr
+            for i, env in enumerate(self.envs):
+                obs, env_reward[i], _, info = env.step(u[i])        # the reward is recomputed by the HER sampler
+                success[i] = info.get('is_success', 0.0)
+                ep['o'][i, t + 1], ep['ag'][i, t + 1] = obs['observation'], obs['achieved_goal']
+                self.g[i] = obs['desired_goal']
+                for key in self.info_keys:
+                    ep['info_' + key][i, t] = info[key]
+            if np.isnan(ep['o'][:, t + 1]).any():
                 self.reset_all_rollouts()
                 return self.generate_rollouts()
-            obs.append(o.copy())
-            achieved_goals.append(ag.copy())
-            successes.append(success.copy())
-            acts.append(u.copy())
-            goals.append(self.g.copy())
-            o[...] = o_new
-            ag[...] = ag_new
-            if self.modular:
-                task_descrs.append(self.task_descr.copy())
-                changes.append(np.abs(achieved_goals[0] - ag) > 1e-3)
-        obs.append(o.copy())
-        achieved_goals.append(ag.copy())
-        episode = dict(o=obs, u=acts, g=goals, ag=achieved_goals)
-        if self.modular:
-            episode['task_descr'] = task_descrs
-            episode['change'] = changes
-        self.initial_o[:] = o
-        for key, value in zip(self.info_keys, info_values):
-            episode['info_{}'.format(key)] = value
-        successful = np.array(successes)[-1, :]
-        assert successful.shape == (B,)
-        self.success_history.append(np.mean(successful))
-        self.reward_history.append(r_competence.copy())
+            if self.modular:                                        # did the outcome move since the start? (routing)
+                ep['change'][:, t] = np.abs(ep['ag'][:, 0] - ep['ag'][:, t + 1]) > 1e-3
+        self.initial_o[:] = ep['o'][:, T]
+        self.success_history.append(float(success.mean()))
+        self.reward_history.append(env_reward.copy())
         if self.compute_Q:
-            self.Q_history.append(np.mean(Qs))
+            self.Q_history.append(q_sum / T)
         self.n_episodes += B * self.nb_cpu
         if self.modular:
-            if self.exploit:
-                tasks_c = [int(self.envs[i].unwrapped.task) for i in range(B)]
-                succ_c = successful.tolist()
-            else:
-                tasks_c, succ_c = [], []
-            if self.rank == 0:
-                self.task_history.extend([t for t in self.tasks if t != []])
-                self.goal_history.extend([g for g in self.goals if len(g)])
-            self.CP, p = self.tracker.update(tasks_c, succ_c)
-            self.C = self.tracker.C
-            if not self.eval:
-                self.p = np.asarray(p, np.float64).copy()
-        return convert_episode_to_batch_major(episode), self.CP, self.n_episodes
+            self._update_competence(success)
+        return ep, self.CP, self.n_episodes
 
-    # ------------------------------------------------------------------------------------------------------
+    def _update_competence(self, success):
+        """rollout.py:316-404: only noise-free rollouts count; rank 0 owns the queues, everybody gets CP and p back."""
+        if self.exploit:
+            tasks, succ = [int(env.unwrapped.task) for env in self.envs], success.tolist()
+        else:
+            tasks, succ = [], []
+        if self.rank == 0:
+            self.task_history.extend(t for t in self.tasks if t is not None)
+            self.goal_history.extend(g for g in self.goals if g is not None)
+        self.CP, p = self.tracker.update(tasks, succ)
+        self.C = self.tracker.C
+        if not self.eval:
+            self.p = np.array(p, np.float64)
+
+    # ------------------------------------------------------------------------------------------ bookkeeping
     def clear_history(self):
-        self.success_history.clear()
-        self.reward_history.clear()
-        self.Q_history.clear()
+        for h in (self.success_history, self.reward_history, self.Q_history):
+            h.clear()
 
     def clear_competence_queue(self):
         self.tracker.clear_competence_queue()
@@ -230,36 +211,6 @@ class RolloutWorker(object):
     def current_mean_Q(self):
         return np.mean(self.Q_history)
 
-    def save_policy(self, path):
-        with open(path, 'wb') as f:
-            pickle.dump(self.policy, f)
-        try:
-            self.policy.save_weights(path)
-        except Exception:
-            pass
-
-    def logs(self, prefix='worker'):
-        logs = [('success_rate', np.mean(self.success_history)), ('avg_reward', np.mean(self.reward_history))]
-        if self.compute_Q:
-            logs += [('mean_Q', np.mean(self.Q_history))]
-        logs += [('episode', self.n_episodes)]
-        if prefix != '' and not prefix.endswith('/'):
-            return [(prefix + '/' + key, val) for key, val in logs]
-        return logs
-
-    def additional_logs(self, prefix='worker'):
-        logs = []
-        if self.modular:
-            Cs = self.get_C()
-            for i in range(self.nb_tasks):
-                logs += [('C_task' + str(i), '%.3g' % Cs[i])]
-                if not self.eval:
-                    logs += [('CP_task' + str(i), '%.3g' % self.get_CP()[i])]
-                    logs += [('p_task' + str(i), '%.3g' % self.p[i])]
-        if prefix != '' and not prefix.endswith('/'):
-            return [(prefix + '/' + key, val) for key, val in logs]
-        return logs
-
     def get_CP(self):
         return self.tracker.get_CP()
 
@@ -269,3 +220,29 @@ class RolloutWorker(object):
     def seed(self, seed):
         for idx, env in enumerate(self.envs):
             env.seed(seed + 1000 * idx)
+
+    def save_policy(self, path):
+        with open(path, 'wb') as f:
+            pickle.dump(self.policy, f)
+        if hasattr(self.policy, 'save_weights'):
+            self.policy.save_weights(path)
+
+    def _prefixed(self, items, prefix):
+        return [((prefix.rstrip('/') + '/' + k) if prefix else k, v) for k, v in items]
+
+    def logs(self, prefix='worker'):
+        items = [('success_rate', np.mean(self.success_history)), ('avg_reward', np.mean(self.reward_history))]
+        if self.compute_Q:
+            items.append(('mean_Q', np.mean(self.Q_history)))
+        items.append(('episode', self.n_episodes))
+        return self._prefixed(items, prefix)
+
+    def additional_logs(self, prefix='worker'):
+        items = []
+        if self.modular:
+            C, CP = self.get_C(), self.get_CP()
+            for i in range(self.nb_tasks):
+                items.append(('C_task%d' % i, '%.3g' % C[i]))
+                if not self.eval:
+                    items += [('CP_task%d' % i, '%.3g' % CP[i]), ('p_task%d' % i, '%.3g' % self.p[i])]
+        return self._prefixed(items, prefix)
