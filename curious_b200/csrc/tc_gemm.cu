@@ -30,6 +30,7 @@
 // tensor maps, the accumulators keep going.  The weight gradients have K = batch: K is split over CTAs into partial
 // tiles that a second small kernel sums in fixed order (deterministic, no atomics).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "net_layout.cuh"
@@ -39,8 +40,14 @@ namespace cur {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 256;
-constexpr int TC_BK = 32;                       // floats per stage and k-block = one 128-byte swizzle row
+// floats per stage and k-block / ring depth.  32 x 2 (128-byte K-major rows, SWIZZLE_128B) and 16 x 4 (64-byte rows,
+// SWIZZLE_64B) both work; measured the same speed within 5 % (accumulator ready after 22.1 k vs 23.4 k cycles at
+// K = 256): the main loop is bound by shared-memory bandwidth (TMA writes + split + three operand passes), not by the
+// depth of the ring.
+constexpr int TC_BK = 32;
 constexpr int TC_STAGES = 2;
+constexpr int TC_MNBLK = TC_BK * 128;           // bytes of one 32-wide MN block of an MN-major operand tile
+static_assert(TC_BK == 16 || TC_BK == 32, "K-major rows are one 64- or 128-byte swizzle row");
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 96 KB
@@ -72,6 +79,7 @@ struct __align__(64) TcBatch {
   TcProb p[TC_MAX_PROBS];
   int n, total_tiles;
   long long* tl;                     // debug timeline of CTA 0 (cur_tc_gemm_timeline), normally NULL
+  int raw_hi;                        // experiment: see tc_lo_of_raw
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -157,9 +165,23 @@ __device__ __forceinline__ void tc_split1(float x, float& h, float& l) {
   h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   l = __uint_as_float(__float_as_uint(x - h) & 0xFFFFE000u);
 }
-__device__ __forceinline__ void tc_split_tile(float* hi, int lo_off_floats, int n4, int t, int nthreads) {
+__device__ __forceinline__ float tc_lo_of_raw(float x) {
+  // experiment (CUR_TC_RAW_HI=1): leave the raw fp32 in place as `hi` (valid only if the tensor core TRUNCATES fp32 to
+  // TF32 when it reads kind::tf32 operands) and write lo = x - trunc(x)
+  const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float(__float_as_uint(x - h) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void tc_split_tile(float* hi, int lo_off_floats, int n4, int t, int nthreads, bool raw_hi) {
   float4* h4 = reinterpret_cast<float4*>(hi);
   float4* l4 = reinterpret_cast<float4*>(hi + lo_off_floats);
+  if (raw_hi) {
+#pragma unroll 4
+    for (int i = t; i < n4; i += nthreads) {
+      const float4 x = h4[i];
+      l4[i] = make_float4(tc_lo_of_raw(x.x), tc_lo_of_raw(x.y), tc_lo_of_raw(x.z), tc_lo_of_raw(x.w));
+    }
+    return;
+  }
 #pragma unroll 4
   for (int i = t; i < n4; i += nthreads) {
     const float4 x = h4[i];
@@ -293,12 +315,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (!P.a_mn) {
           tc_tma_2d(a_hi, mA, k0, m0, full + 8 * s);                           // [128 m][32 k]
         } else {
-          for (int j = 0; j < TC_BM / 32; ++j) tc_tma_2d(a_hi + j * 4096, mA, m0 + 32 * j, k0, full + 8 * s);   // [32 k][32 m]
+          for (int j = 0; j < TC_BM / 32; ++j) tc_tma_2d(a_hi + j * TC_MNBLK, mA, m0 + 32 * j, k0, full + 8 * s);   // [BK k][32 m]
         }
         if (!P.b_mn) {
           tc_tma_2d(b_hi, mB, k0, 0, full + 8 * s);                            // [256 n][32 k]
         } else {
-          for (int j = 0; j < TC_BN / 32; ++j) tc_tma_2d(b_hi + j * 4096, mB, 32 * j, k0, full + 8 * s);        // [32 k][32 n]
+          for (int j = 0; j < TC_BN / 32; ++j) tc_tma_2d(b_hi + j * TC_MNBLK, mB, 32 * j, k0, full + 8 * s);        // [BK k][32 n]
         }
       }
     }
@@ -309,11 +331,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)P.a_mn << 15) | ((uint32_t)P.b_mn << 16) |
                            ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     const uint32_t a_step = P.a_mn ? 1024u : 32u, b_step = P.b_mn ? 1024u : 32u;   // bytes per k-step of 8
-    // K-major: 8-row groups 1 KB apart (SBO), LBO unused.  MN-major: 32-wide MN blocks 4 KB apart (LBO), 4-row
-    // k atoms 512 B apart (SBO)
-    const uint32_t a_lbo = P.a_mn ? 4096u : 16u, b_lbo = P.b_mn ? 4096u : 16u;
-    const uint32_t a_sbo = P.a_mn ? 512u : 1024u, b_sbo = P.b_mn ? 512u : 1024u;
-    const uint32_t a_lt = P.a_mn ? 1u : 2u, b_lt = P.b_mn ? 1u : 2u;
+    // K-major: rows of TC_BK floats (64 B: SWIZZLE_64B, layout type 4; 128 B: SWIZZLE_128B, type 2), 8-row groups
+    // 8 rows apart (SBO), LBO unused.  MN-major: SWIZZLE_128B_BASE32B (type 1), 32-wide MN blocks TC_MNBLK apart (LBO),
+    // 4-row k atoms 512 B apart (SBO)
+    constexpr uint32_t kmaj_sbo = 8u * TC_BK * 4u, kmaj_lt = (TC_BK == 32) ? 2u : 4u;
+    const uint32_t a_lbo = P.a_mn ? (uint32_t)TC_MNBLK : 16u, b_lbo = P.b_mn ? (uint32_t)TC_MNBLK : 16u;
+    const uint32_t a_sbo = P.a_mn ? 512u : kmaj_sbo, b_sbo = P.b_mn ? 512u : kmaj_sbo;
+    const uint32_t a_lt = P.a_mn ? 1u : kmaj_lt, b_lt = P.b_mn ? 1u : kmaj_lt;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % TC_STAGES, round = kb / TC_STAGES;
       tc_bar_wait(splitb + 8 * s, round & 1);
@@ -344,8 +368,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       tc_bar_wait(full + 8 * s, round & 1);
       if (tl && warp == TC_SPLIT_WARP0 && kb < 16) tl[24 + 2 * kb] = clock64();
       float* st = reinterpret_cast<float*>(gen_base + s * TC_STAGE_BYTES);
-      tc_split_tile(st, TC_A_BYTES / 4, TC_A_BYTES / 16, t, TC_SPLIT_WARPS * 32);
-      tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, TC_B_BYTES / 16, t, TC_SPLIT_WARPS * 32);
+      tc_split_tile(st, TC_A_BYTES / 4, TC_A_BYTES / 16, t, TC_SPLIT_WARPS * 32, G.raw_hi != 0);
+      tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, TC_B_BYTES / 16, t, TC_SPLIT_WARPS * 32, G.raw_hi != 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (tl && warp == TC_SPLIT_WARP0 && kb < 16) tl[25 + 2 * kb] = clock64();
@@ -628,17 +652,19 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// row-major [rows][cols] fp32 with leading dimension ld; box = {32 floats, box_rows}; 128-byte swizzle of 16-byte
-// chunks (K-major operands) or of 32-byte chunks (MN-major operands)
+// row-major [rows][cols] fp32 with leading dimension ld; K-major operands: box = {TC_BK floats, box_rows}, 16-byte chunks
+// swizzled within the 64- / 128-byte row; MN-major operands: box = {32 floats, TC_BK rows}, 32-byte chunks swizzled
+// within the 128-byte row
 static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   CUR_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {mn_major ? 32u : (cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (TC_BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
@@ -813,6 +839,8 @@ int TcLauncher::flush(cudaStream_t s_main) {
   }
   if (G.n > 0) {
     B.n = G.n; B.total_tiles = G.total_tiles; B.tl = g_tc_timeline;
+    static const int raw_hi = (getenv("CUR_TC_RAW_HI") != nullptr && getenv("CUR_TC_RAW_HI")[0] == '1') ? 1 : 0;
+    B.raw_hi = raw_hi;
     tc_gemm_kernel<<<G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s_main>>>(B);
     CUR_CHECK_LAUNCH();
     if (forked) CUR_CUDA_TRY(cudaEventRecord(ss->gemm, s_main));

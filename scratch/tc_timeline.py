@@ -31,7 +31,7 @@ def run(M, K, a_trans, b_trans, epi, dbg=0):
     lib.cur_tc_gemm_timeline(None)
     t = tl.cpu().numpy()
     t0 = t[0]
-    nkb = min(16, (K if not a_trans or M >= 1024 else 512) // 32)
+    nkb = min(16, (K if not a_trans or M >= 1024 else 256) // 32)
     print('  setup %d  total %d cycles' % (t[1] - t0, t[2] - t0))
     print('  producer issue :', [int(t[8 + k] - t0) for k in range(nkb)])
     print('  split wait/done:', [(int(t[24 + 2 * k] - t0), int(t[25 + 2 * k] - t0)) for k in range(nkb)])
