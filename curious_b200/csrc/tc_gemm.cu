@@ -51,7 +51,9 @@ static_assert(TC_BK == 16 || TC_BK == 32, "K-major rows are one 64- or 128-byte 
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 96 KB
-constexpr int TC_SPLIT_WARPS = 4;                              // the split is shared-memory-bandwidth-bound: 4 warps saturate it
+constexpr int TC_SPLIT_GROUPS = 1;                             // split groups take alternate k-blocks; 2 groups x (16 x 4)
+constexpr int TC_SPLIT_GROUP_WARPS = 4;                        // measured no faster than 1 group x (32 x 2), see profiles/
+constexpr int TC_SPLIT_WARPS = TC_SPLIT_GROUPS * TC_SPLIT_GROUP_WARPS;
 constexpr int TC_SPLIT_WARP0 = 2, TC_EPI_WARP0 = TC_SPLIT_WARP0 + TC_SPLIT_WARPS;
 constexpr int TC_EPI_WARPS = 8;                                // two per TMEM lane quarter, 4 column chunks each
 constexpr int TC_THREADS = (TC_EPI_WARP0 + TC_EPI_WARPS) * 32;   // 576
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       tc_bar_init(full + 8 * s, 1);
-      tc_bar_init(splitb + 8 * s, TC_SPLIT_WARPS);
+      tc_bar_init(splitb + 8 * s, TC_SPLIT_GROUP_WARPS);
       tc_bar_init(empty + 8 * s, 1);
     }
     tc_bar_init(accb, 1);
@@ -362,14 +364,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
   } else if (warp < TC_EPI_WARP0) {
     // ===== splitters
-    const int t = threadIdx.x - TC_SPLIT_WARP0 * 32;
-    for (int kb = 0; kb < nkb; ++kb) {
+    const int group = (warp - TC_SPLIT_WARP0) / TC_SPLIT_GROUP_WARPS;
+    const int t = threadIdx.x - (TC_SPLIT_WARP0 + group * TC_SPLIT_GROUP_WARPS) * 32;
+    for (int kb = group; kb < nkb; kb += TC_SPLIT_GROUPS) {
       const int s = kb % TC_STAGES, round = kb / TC_STAGES;
       tc_bar_wait(full + 8 * s, round & 1);
       if (tl && warp == TC_SPLIT_WARP0 && kb < 16) tl[24 + 2 * kb] = clock64();
       float* st = reinterpret_cast<float*>(gen_base + s * TC_STAGE_BYTES);
-      tc_split_tile(st, TC_A_BYTES / 4, TC_A_BYTES / 16, t, TC_SPLIT_WARPS * 32, G.raw_hi != 0);
-      tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, TC_B_BYTES / 16, t, TC_SPLIT_WARPS * 32, G.raw_hi != 0);
+      tc_split_tile(st, TC_A_BYTES / 4, TC_A_BYTES / 16, t, TC_SPLIT_GROUP_WARPS * 32, G.raw_hi != 0);
+      tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, TC_B_BYTES / 16, t, TC_SPLIT_GROUP_WARPS * 32, G.raw_hi != 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (tl && warp == TC_SPLIT_WARP0 && kb < 16) tl[25 + 2 * kb] = clock64();
