@@ -220,7 +220,7 @@ def large_batch_sweep(agent, dims, torch):
     except Exception:
         bf16 = 2250.0 * 0.745
     sweep = []
-    for b in (256, 1024, 4096, 16384):
+    for b in (256, 512, 1024, 2048, 4096, 16384):
         a = agent if b == BATCH else agent.make_agent(batch_size=b)
         ms = time_updates(a.train, 200 if b <= 1024 else 40, torch)
         fl = update_flops(dims, N_MODULES, b)

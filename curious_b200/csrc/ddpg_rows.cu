@@ -65,6 +65,7 @@ struct StreamParams {
   cur_net_desc d;
   int in_sp, in_sq, in_g, KP, L, nchunks, nchunks_t;
   int64_t n;
+  int64_t grad_rows;         // rows one loss mean runs over for the backward seeds (n, or cur_ddpg_hyper.loss_rows)
   const float *o, *g, *u, *td, *o_2, *g_2, *r;
   const float *o_mean, *o_std, *g_mean, *g_std;
   float gamma, clip_return, action_l2;
@@ -473,7 +474,7 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   Ring rg;
   rg.chunks = my_chunks; rg.slots = ringf; rg.full = full; rg.empty = empty; rg.cons = 0;
   const int col = tid;
-  const float inv_n = 1.0f / (float)P.n;
+  const float inv_n = 1.0f / (float)P.grad_rows;      // scale of the backward seeds
   const float* stage = nullptr;
   if (P.fused_her) {
     sample_rows(P, row0, her_stage, m_src, s_r);
@@ -618,7 +619,7 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
       const int r = tid >> 3, j = tid & (S_DU - 1);
       float v = 0.f;
       if (j < d.dimu) {
-        const float coef = P.action_l2 * 2.0f / (float)(P.n * d.dimu);
+        const float coef = P.action_l2 * 2.0f / (float)(P.grad_rows * d.dimu);
         const float th = s_th[tid];
         v = (s_dy[tid] + coef * th) * (1.f - th * th);
       }
@@ -706,6 +707,8 @@ struct DwTail {
   int tl_skinny_block;
   int64_t parity_stride;           // > 0: gradients go to C + ((update + 1) & 1) * parity_stride (peer-memory exchange)
   int micro;                       // micro-batches (workers) per update: launch j = step % micro accumulates for j > 0
+  int chunk, last_chunk;           // batches > 256 rows: one launch per 256-row K chunk; chunks > 0 accumulate, only the
+                                   // last one runs the optimiser epilogue, folds the losses and bumps the step counter
 };
 
 // Tile kinds of the weight-gradient launch (K = batch <= 256 is the reduction dimension):
@@ -894,7 +897,7 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     // update u = st / micro, launch j = st % micro of it adds its gradient to the sum of launches 0..j-1
     const long long u = st / T.micro, j = st - u * T.micro;
     if (T.parity_stride > 0) Ps.C += ((u + 1) & 1) * T.parity_stride;
-    Ps.accumulate = j > 0 ? 1 : 0;
+    Ps.accumulate = (j > 0 || T.chunk > 0) ? 1 : 0;
   }
   __syncthreads();
   {
@@ -914,6 +917,7 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
   // ---- the last CTA to finish folds the loss partials and bumps the step counter
   __syncthreads();
   if (tl) tl[2] = clock64();
+  if (!T.last_chunk) return;
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int t = atomicAdd(T.ticket, 1u);
@@ -1002,10 +1006,14 @@ static RowsWorkspace carve_rows(const cur_net_desc& d, int64_t n, float* base) {
   return w;
 }
 
+// Batches above 256 rows run the stream kernel in several waves and the weight-gradient launch once per 256-row K chunk.
+// Measured against the tensor-core levels schedule (us/update): 512: see profiles/README.md.
+constexpr int64_t ROWS_MAX_BATCH = 1024;
+
 static bool rows_supported(const cur_net_desc* d, int64_t n) {
   if (check_desc(d) != CUR_OK) return false;
   if (d->hidden != S_H || d->layers < 1 || d->layers > S_MAXL) return false;
-  if (d->dimu > S_DU || n <= 0 || (n % S_ROWS) != 0 || n > DW_KMAX) return false;      // K of the dW tiles is the batch
+  if (d->dimu > S_DU || n <= 0 || (n % S_ROWS) != 0 || n > ROWS_MAX_BATCH) return false;
   const NetLayout q = net_layout(*d, 0), p = net_layout(*d, 1);
   if (q.in_s + q.in_g > S_H) return false;
   // operands of the first-layer weight gradients must be 16-byte aligned column blocks of X
@@ -1036,7 +1044,6 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     CUR_REQUIRE(!d->modular || batch->td, "task_descr required for a modular net");
   }
   CUR_REQUIRE(rows_supported(d, batch->n), "shape not supported by the rows schedule (see cur_ddpg_rows_supported)");
-  CUR_REQUIRE(h->loss_rows == 0 || h->loss_rows == batch->n, "loss_rows is a cur_ddpg_grads option (use micro_batches here)");
   if (d->normalize_obs)
     CUR_REQUIRE(stats && stats->o_mean && stats->o_std && stats->g_mean && stats->g_std, "normalizer stats required");
   if (adam) {
@@ -1080,6 +1087,7 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   P.d = *d;
   P.in_sp = LP.in_s; P.in_sq = LQ.in_s; P.in_g = LQ.in_g; P.KP = w.KP; P.L = L;
   P.n = n;
+  P.grad_rows = h->loss_rows > 0 ? h->loss_rows : n;
   P.o = batch->o; P.g = batch->g; P.u = batch->u; P.td = batch->td; P.o_2 = batch->o_2; P.g_2 = batch->g_2;
   P.r = batch->r;
   if (stats) { P.o_mean = stats->o_mean; P.o_std = stats->o_std; P.g_mean = stats->g_mean; P.g_std = stats->g_std; }
@@ -1162,29 +1170,7 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
             t[1] - t[0], t[2] - t[1], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6], t[7] - t[0]);
   }
 
-  // ---- launch 2: weight gradients
-  GemmBatch G;
-  G.n = 0; G.total_tiles = 0;
-  auto add = [&](const GemmProb& p) { G.p[G.n++] = p; };
-  auto net_grads = [&](const NetLayout& NL, float* gN, const float* X0, float* const* hN, float* const* dN,
-                       const float* dOut, int lddo) {
-    add(bwd_dw(hN[L - 1], H, H, dOut, lddo, NL.out, gN + NL.off_Wout, n));
-    add(bwd_db(dOut, lddo, NL.out, gN + NL.off_bout, n));
-    for (int l = L - 1; l >= 1; --l) {
-      GemmProb p = bwd_dw(hN[l - 1], H, H, dN[l], H, H, gN + NL.off_W[l], n);
-      if (adam) { p.C2 = (&NL == &LQ) ? w.TQ[l] : w.TP[l]; p.ldc2 = H; }     // transposed copy of the stepped weights
-      add(p);
-      add(bwd_db(dN[l], H, H, gN + NL.off_b[l], n));
-    }
-    add(bwd_dw(X0, w.KP, NL.in_s, dN[0], H, H, gN + NL.off_W0, n));
-    add(bwd_db(dN[0], H, H, gN + NL.off_b0, n));
-    if (NL.in_g > 0) add(bwd_dw(X0 + NL.in_s, w.KP, NL.in_g, dN[0], H, H, gN + NL.off_W0g, n));
-  };
-  net_grads(LQ, gQ, w.Xq, w.hq, w.dc, w.dQ, 1);
-  net_grads(LP, gP, w.Xp, w.hp, w.dp, w.dy, w.lddy);
-  const int tiles = plan_dw_batch(G);
-  CUR_REQUIRE(tiles > 0, "weight-gradient problems do not fit the rows schedule (batch > 256 or unaligned dims)");
-
+  // ---- launch 2: weight gradients, one launch per 256-row chunk of the batch (K of the tiles)
   DwTail T;
   memset(&T, 0, sizeof(T));
   if (adam) {
@@ -1209,10 +1195,43 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     dw_configured = true;
   }
   T.tl = tl_on ? tl_dev : nullptr;
-  T.tl_skinny_block = 0;
-  for (int i = 0; i < G.n; ++i)
-    if (G.p[i].variant == DW_FULLK) { T.tl_skinny_block = G.p[i].tile_begin; break; }
-  rows_dw_kernel<<<tiles, GEMM_THREADS, DW_SMEM_BYTES, s>>>(G, T);
+  const AdamCtx ax_full = T.ax;
+  const int n_chunks = (int)((n + DW_KMAX - 1) / DW_KMAX);
+  for (int c = 0; c < n_chunks; ++c) {
+    const int64_t r0 = (int64_t)c * DW_KMAX;
+    const int64_t rows = (n - r0 < DW_KMAX) ? n - r0 : DW_KMAX;
+    const bool last = c == n_chunks - 1;
+    GemmBatch G;
+    G.n = 0; G.total_tiles = 0;
+    auto add = [&](const GemmProb& p) { G.p[G.n++] = p; };
+    auto net_grads = [&](const NetLayout& NL, float* gN, const float* X0, float* const* hN, float* const* dN,
+                         const float* dOut, int lddo) {
+      const float* dO = dOut + r0 * lddo;
+      add(bwd_dw(hN[L - 1] + r0 * H, H, H, dO, lddo, NL.out, gN + NL.off_Wout, rows));
+      add(bwd_db(dO, lddo, NL.out, gN + NL.off_bout, rows));
+      for (int l = L - 1; l >= 1; --l) {
+        GemmProb p = bwd_dw(hN[l - 1] + r0 * H, H, H, dN[l] + r0 * H, H, H, gN + NL.off_W[l], rows);
+        if (adam && last) { p.C2 = (&NL == &LQ) ? w.TQ[l] : w.TP[l]; p.ldc2 = H; }   // transposed copy of the stepped weights
+        add(p);
+        add(bwd_db(dN[l] + r0 * H, H, H, gN + NL.off_b[l], rows));
+      }
+      add(bwd_dw(X0 + r0 * w.KP, w.KP, NL.in_s, dN[0] + r0 * H, H, H, gN + NL.off_W0, rows));
+      add(bwd_db(dN[0] + r0 * H, H, H, gN + NL.off_b0, rows));
+      if (NL.in_g > 0) add(bwd_dw(X0 + r0 * w.KP + NL.in_s, w.KP, NL.in_g, dN[0] + r0 * H, H, H, gN + NL.off_W0g, rows));
+    };
+    net_grads(LQ, gQ, w.Xq, w.hq, w.dc, w.dQ, 1);
+    net_grads(LP, gP, w.Xp, w.hp, w.dp, w.dy, w.lddy);
+    const int tiles = plan_dw_batch(G);
+    CUR_REQUIRE(tiles > 0, "weight-gradient problems do not fit the rows schedule (unaligned dims)");
+    T.chunk = c; T.last_chunk = last ? 1 : 0;
+    T.ax = ax_full;
+    if (!last) T.ax.theta = nullptr;             // the optimiser runs once, on the complete sum
+    T.tl_skinny_block = 0;
+    for (int i = 0; i < G.n; ++i)
+      if (G.p[i].variant == DW_FULLK) { T.tl_skinny_block = G.p[i].tile_begin; break; }
+    rows_dw_kernel<<<tiles, GEMM_THREADS, DW_SMEM_BYTES, s>>>(G, T);
+    CUR_CHECK_LAUNCH();
+  }
   if (tl_on && tl_calls == 40) {
     long long t[64];
     CUR_CUDA_TRY(cudaStreamSynchronize(s));

@@ -74,6 +74,11 @@ class DDPG(object):
         # the reference's SUM all-reduce over that many single-batch workers produces (ddpg.py:452-453)
         self.workers_per_rank = int(kwargs.get('workers_per_rank', 1))
         assert self.workers_per_rank >= 1
+        # 'wide' = the workers' batches as one batch with 1 / batch_size loss seeds, 'micro' = one accumulating launch
+        # pair per worker (same Philox stream positions as the launch-by-launch path), 'auto' = wide when a schedule
+        # takes workers x batch_size rows
+        self.workers_mode = kwargs.get('workers_mode', 'auto')
+        assert self.workers_mode in ('auto', 'wide', 'micro')
         self.create_actor_critic = import_function(self.network_class)
 
         self.dimo = self.input_dims['o']
@@ -504,11 +509,15 @@ class DDPG(object):
     def _prepare_graph_state(self):
         """Device-resident state of the graph path (control block, loss rings, Adam tables, fixed batch buffers)."""
         dev = self.device
-        # several workers per rank as ONE wide batch on the tensor-core levels schedule when that batch is large enough
-        # (k x batch_size >= 1024 rows): same gradient as k single-batch launches (loss seeds scaled by 1 / batch_size,
-        # cur_ddpg_hyper.loss_rows), 3x faster at 19 workers; otherwise k accumulating launches of the rows schedule
+        # several workers per rank as ONE wide batch: same gradient as k single-batch launches (loss seeds scaled by
+        # 1 / batch_size, cur_ddpg_hyper.loss_rows) on the rows schedule up to 1024 rows or the tensor-core levels
+        # schedule above (3x faster at 19 workers); otherwise k accumulating launches of the rows schedule
         k = self.workers_per_rank
-        self._wide = bool(k > 1 and _lib.load().cur_ddpg_uses_tensor_cores(C.byref(self.net.desc), k * self.batch_size))
+        lib = _lib.load()
+        wide_rows = k * self.batch_size
+        self._wide = bool(k > 1 and self.workers_mode != 'micro' and (
+            (self.update_schedule != 'levels' and lib.cur_ddpg_rows_supported(C.byref(self.net.desc), wide_rows)) or
+            lib.cur_ddpg_uses_tensor_cores(C.byref(self.net.desc), wide_rows)))
         self._graph_rows = self.batch_size * (k if self._wide else 1)
         self._micro = 1 if self._wide else k
         B = self._graph_rows

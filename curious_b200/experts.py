@@ -113,7 +113,7 @@ class TaskExperts(object):
         """One update of every expert.  Returns [(critic_loss, actor_loss), ...] like DDPG.train (ddpg.py:368-373)."""
         ps = self.policies
         if self.mode == 'sequential' or (self.mode == 'auto' and all(
-                p.update_schedule != 'levels' and p._use_rows(p.batch_size) for p in ps)):
+                p.update_schedule != 'levels' and p.batch_size <= 256 and p._use_rows(p.batch_size) for p in ps)):
             return [p.train(stage) for p in ps]
         graph = stage and self.use_cuda_graph and all(p.her_rng == 'philox' for p in ps)
         if graph:

@@ -271,7 +271,7 @@ typedef struct cur_ddpg_hyper {
    * grads + (s & 1) * grads_parity_stride floats, s = update number (counter / micro_batches) after this update's bump
    * (double buffering for cur_p2p_allreduce_adam).  0: always `grads`. */
   int64_t grads_parity_stride;
-  /* cur_ddpg_grads only, > 0: the batch holds batch / loss_rows reference workers - the backward seeds
+  /* > 0: the batch holds batch / loss_rows reference workers - the backward seeds
    * are scaled by 1 / loss_rows instead of 1 / batch, so that the gradient is the SUM of the workers' single-batch
    * gradients (each loss a mean over loss_rows rows, ddpg.py:439-441 + the SUM all-reduce of ddpg.py:452-453).  The
    * reported losses stay means over the whole batch (= the average worker's loss).  0: loss_rows = batch. */

@@ -232,7 +232,7 @@ def test_save_load_weights_roundtrip(tmp_path):
             assert np.array_equal(a.get_flat(which, tgt), b.get_flat(which, tgt))
 
 
-@pytest.mark.parametrize('structure,layers,batch_size', [('curious', 3, 256), ('flat', 2, 64), ('task_experts', 1, 32),
+@pytest.mark.parametrize('structure,layers,batch_size', [('curious', 3, 256), ('curious', 3, 640), ('flat', 2, 64), ('task_experts', 1, 32),
                                                          ('curious', 4, 16)])
 def test_rows_schedule_trajectory(structure, layers, batch_size):
     """The cluster ("rows") schedule end to end through train(): modular and flat nets, 1-4 hidden layers,
@@ -459,7 +459,8 @@ def test_workers_per_rank_sums_single_batch_gradients():
     # ---- (2) graph == eager
     agents = []
     for use_graph in (True, False):
-        ag = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', use_cuda_graph=use_graph, workers_per_rank=k)
+        ag = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', use_cuda_graph=use_graph, workers_per_rank=k,
+                            workers_mode='micro')
         np.random.seed(4)
         _fill(ag, episodes, cp)
         agents.append(ag)
@@ -520,8 +521,7 @@ def test_wide_batch_of_workers_equals_sum_of_single_batch_gradients():
     out = [float(g.train()[0]) for _ in range(5)]
     assert g._wide and g._graph_rows == k * kw['batch_size'] and np.isfinite(out).all()
     assert int(g._step.item()) == 5 and g.Q_adam.t == 5
-    small = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', workers_per_rank=3)      # 768 rows: accumulating launches
+    big = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', workers_per_rank=8)        # 2048 rows: tensor-core levels
     np.random.seed(21)
-    _fill(small, episode_stream(dims, kw['T'], 8), cp)
-    small.train()
-    assert not small._wide and small._micro == 3
+    _fill(big, episode_stream(dims, kw['T'], 8), cp)
+    assert np.isfinite(float(big.train()[0])) and big._wide and not big._use_rows(big._graph_rows)

@@ -41,7 +41,8 @@ def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto', workers
         kw, dims, ag_ids, g_ids = ddpg_kwargs(4)
         # rank 1 starts from different weights: _sync_optimizers must broadcast rank 0's (ddpg.py:466)
         agent = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', seed=rank, use_cuda_graph=use_graph,
-                               device=dev, grad_exchange=grad_exchange, workers_per_rank=workers_per_rank)
+                               device=dev, grad_exchange=grad_exchange, workers_per_rank=workers_per_rank,
+                               workers_mode='micro')
         assert parallel.world(agent.comm)[1] == world
         theta0 = agent.theta_main.clone()
         gathered = [torch.empty_like(theta0) for _ in range(world)]
