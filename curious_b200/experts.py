@@ -21,8 +21,9 @@ from .util import LazyHost
 class TaskExperts(object):
     def __init__(self, policies, use_cuda_graph=True, mode='auto'):
         """mode: 'grouped' = grouped launches; 'sequential' = p.train() one after the other; 'auto' = sequential
-        when every expert runs the rows schedule (batch <= 256: one expert's row clusters already fill the
-        148 SMs, measured 67 us per expert update against 80 us grouped), grouped otherwise."""
+        when every expert runs the rows schedule at batch <= 512 (one expert's row CTAs already fill the 148 SMs;
+        measured per round of 4 experts: batch 256 237 us vs 322 us grouped, 512 435 vs 524, 1024 841 vs 372),
+        grouped otherwise."""
         assert len(policies) >= 1 and mode in ('auto', 'grouped', 'sequential')
         self.mode = mode
         p0 = policies[0]
@@ -113,7 +114,7 @@ class TaskExperts(object):
         """One update of every expert.  Returns [(critic_loss, actor_loss), ...] like DDPG.train (ddpg.py:368-373)."""
         ps = self.policies
         if self.mode == 'sequential' or (self.mode == 'auto' and all(
-                p.update_schedule != 'levels' and p.batch_size <= 256 and p._use_rows(p.batch_size) for p in ps)):
+                p.update_schedule != 'levels' and p.batch_size <= 512 and p._use_rows(p.batch_size) for p in ps)):
             return [p.train(stage) for p in ps]
         graph = stage and self.use_cuda_graph and all(p.her_rng == 'philox' for p in ps)
         if graph:

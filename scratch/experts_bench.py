@@ -23,7 +23,7 @@ def timeit(fn):
     for _ in range(N): fn()
     e1.record(); torch.cuda.synchronize()
     return 1e3 * e0.elapsed_time(e1) / N
-for sched in (['rows', 'levels'] if B <= 256 else ['levels']):
+for sched in (['rows', 'levels'] if B <= 1024 else ['levels']):
     seq = build(sched)
     print('B=%d experts=%d sequential (%s): %.1f us per round of %d expert updates' % (B, NE, sched, timeit(lambda: [p.train() for p in seq]), NE))
 grp = TaskExperts(build('levels'))
