@@ -26,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto', workers_per_rank=1):
+def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto', workers_per_rank=1, workers_mode='micro'):
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -42,7 +42,7 @@ def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto', workers
         # rank 1 starts from different weights: _sync_optimizers must broadcast rank 0's (ddpg.py:466)
         agent = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', seed=rank, use_cuda_graph=use_graph,
                                device=dev, grad_exchange=grad_exchange, workers_per_rank=workers_per_rank,
-                               workers_mode='micro')
+                               workers_mode=workers_mode)
         assert parallel.world(agent.comm)[1] == world
         theta0 = agent.theta_main.clone()
         gathered = [torch.empty_like(theta0) for _ in range(world)]
@@ -128,3 +128,18 @@ def test_two_ranks_with_two_workers_each(tmp_path):
         thetas[(mode, graph)] = [np.load(os.path.join(str(d), 'theta%d.npy' % r)) for r in range(2)]
         assert np.array_equal(thetas[(mode, graph)][0], thetas[(mode, graph)][1])
     assert np.array_equal(thetas[('p2p', True)][0], thetas[('nccl', True)][0])
+
+
+def test_two_ranks_wide_worker_batches(tmp_path):
+    """3 workers per rank as ONE 768-row batch on the rows schedule (several waves of the stream kernel, three
+    accumulating weight-gradient launches, loss seeds scaled by 1 / 256): peer-memory exchange == NCCL, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    thetas = {}
+    for mode in ('p2p', 'nccl'):
+        d = tmp_path / mode
+        d.mkdir()
+        mp.spawn(_worker, args=(2, _free_port(), True, str(d), mode, 3, 'auto'), nprocs=2, join=True)
+        thetas[mode] = [np.load(os.path.join(str(d), 'theta%d.npy' % r)) for r in range(2)]
+        assert np.array_equal(thetas[mode][0], thetas[mode][1])
+    assert np.array_equal(thetas['p2p'][0], thetas['nccl'][0])
