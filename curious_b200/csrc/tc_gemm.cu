@@ -129,6 +129,51 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far are done
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((unsigned short)3)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t tc_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in the pair's leader CTA (rank 0)
+__device__ __forceinline__ void tc_bar_arrive_leader(uint32_t bar) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(0u));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void tc_bar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (long long spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1ll << 26)) __trap();
+  }
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -257,7 +302,11 @@ __device__ __forceinline__ void tc_epilogue(const TcProb& P, uint32_t taddr, flo
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcBatch G) {
+// PAIR: two CTAs of a cluster (one TPC) compute a 256 x 256 tile with tcgen05.mma.cta_group::2: each CTA stages its own 128
+// rows of A and only HALF of the B tile (128 of the 256 N columns) - a third less operand traffic through each SM's L2 port
+// and shared memory.  Rank 0 issues the MMAs for both; every CTA splits / drains its own half.
+template <bool PAIR>
+__device__ __forceinline__ void tc_gemm_body(const TcBatch& G) {
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -266,11 +315,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   // ---- which tile
   int pi = 0;
 #pragma unroll 1
-  while (pi + 1 < G.n && (int)blockIdx.x >= G.p[pi + 1].tile_begin) ++pi;
+  while (pi + 1 < G.n && (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) >= G.p[pi + 1].tile_begin) ++pi;
   const TcProb& P = G.p[pi];
-  const int tile = blockIdx.x - P.tile_begin;
+  const uint32_t rank = PAIR ? tc_cta_rank() : 0u;
+  const int tile = (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) - P.tile_begin;
   const int tm = tile % P.tiles_m, split = tile / P.tiles_m;
-  const int m0 = tm * TC_BM;
+  const int m0 = PAIR ? tm * 2 * TC_BM + (int)rank * TC_BM : tm * TC_BM;
+  constexpr int B_BYTES_OWN = PAIR ? TC_B_BYTES / 2 : TC_B_BYTES;      // bytes of B this CTA stages per k-block
+  constexpr int BN_OWN = PAIR ? TC_BN / 2 : TC_BN;
   const int k_begin = split * P.k_per_split;
   const int nkb = P.nkb1 + P.nkb2;
 
@@ -282,19 +334,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       tc_bar_init(full + 8 * s, 1);
-      tc_bar_init(splitb + 8 * s, TC_SPLIT_GROUP_WARPS);
+      tc_bar_init(splitb + 8 * s, PAIR ? 2 * TC_SPLIT_GROUP_WARPS : TC_SPLIT_GROUP_WARPS);
       tc_bar_init(empty + 8 * s, 1);
     }
     tc_bar_init(accb, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (PAIR) tc_cluster_sync();        // both CTAs' barriers exist before anything in the pair signals or allocates
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&s_tmem)), "n"(TC_TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&s_tmem)), "n"(TC_TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&s_tmem)), "n"(TC_TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) tc_cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
   long long* tl = (G.tl != nullptr && blockIdx.x == 0 && lane == 0) ? G.tl : nullptr;
@@ -313,25 +372,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         const CUtensorMap* mB = seg2 ? &G.mapB2[pi] : &G.mapB[pi];
         const int k0 = seg2 ? (kb - P.nkb1) * TC_BK : k_begin + kb * TC_BK;
         if (tl && kb < 16) tl[8 + kb] = clock64();
-        tc_bar_expect_tx(full + 8 * s, TC_A_BYTES + TC_B_BYTES);      // zero-filled out-of-bounds bytes count too
+        tc_bar_expect_tx(full + 8 * s, TC_A_BYTES + B_BYTES_OWN);     // zero-filled out-of-bounds bytes count too
         if (!P.a_mn) {
           tc_tma_2d(a_hi, mA, k0, m0, full + 8 * s);                           // [128 m][32 k]
         } else {
           for (int j = 0; j < TC_BM / 32; ++j) tc_tma_2d(a_hi + j * TC_MNBLK, mA, m0 + 32 * j, k0, full + 8 * s);   // [BK k][32 m]
         }
         if (!P.b_mn) {
-          tc_tma_2d(b_hi, mB, k0, 0, full + 8 * s);                            // [256 n][32 k]
+          tc_tma_2d(b_hi, mB, k0, (int)rank * BN_OWN, full + 8 * s);           // [256 | 128 n][BK k]
         } else {
-          for (int j = 0; j < TC_BN / 32; ++j) tc_tma_2d(b_hi + j * TC_MNBLK, mB, 32 * j, k0, full + 8 * s);        // [BK k][32 n]
+          for (int j = 0; j < BN_OWN / 32; ++j)
+            tc_tma_2d(b_hi + j * TC_MNBLK, mB, (int)rank * BN_OWN + 32 * j, k0, full + 8 * s);                    // [BK k][32 n]
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (the pair's leader issues for both CTAs)
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10),
     // a_major at 15, b_major at 16, N >> 3 at [17,23), M >> 4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)P.a_mn << 15) | ((uint32_t)P.b_mn << 16) |
-                           ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                           ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
     const uint32_t a_step = P.a_mn ? 1024u : 32u, b_step = P.b_mn ? 1024u : 32u;   // bytes per k-step of 8
     // K-major: rows of TC_BK floats (64 B: SWIZZLE_64B, layout type 4; 128 B: SWIZZLE_128B, type 2), 8-row groups
     // 8 rows apart (SBO), LBO unused.  MN-major: SWIZZLE_128B_BASE32B (type 1), 32-wide MN blocks TC_MNBLK apart (LBO),
@@ -342,7 +402,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const uint32_t a_lt = P.a_mn ? 1u : kmaj_lt, b_lt = P.b_mn ? 1u : kmaj_lt;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % TC_STAGES, round = kb / TC_STAGES;
-      tc_bar_wait(splitb + 8 * s, round & 1);
+      if (PAIR) tc_bar_wait_cluster(splitb + 8 * s, round & 1); else tc_bar_wait(splitb + 8 * s, round & 1);
       tc_fence_after();
       if (tl && kb < 16) tl[56 + 2 * kb] = clock64();
       if (lane == 0) {
@@ -352,17 +412,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
           const uint64_t dah = tc_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt), dal = tc_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
           const uint64_t dbh = tc_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt), dbl = tc_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
-          tc_mma_tf32(tmem + TC_BN, dal, dbh, idesc, (kb | ks) != 0);      // cross terms -> accumulator 1
-          tc_mma_tf32(tmem + TC_BN, dah, dbl, idesc, 1u);
-          tc_mma_tf32(tmem, dah, dbh, idesc, (kb | ks) != 0);              // main term   -> accumulator 0
+          if (PAIR) {
+            tc_mma_tf32_pair(tmem + TC_BN, dal, dbh, idesc, (kb | ks) != 0);
+            tc_mma_tf32_pair(tmem + TC_BN, dah, dbl, idesc, 1u);
+            tc_mma_tf32_pair(tmem, dah, dbh, idesc, (kb | ks) != 0);
+          } else {
+            tc_mma_tf32(tmem + TC_BN, dal, dbh, idesc, (kb | ks) != 0);      // cross terms -> accumulator 1
+            tc_mma_tf32(tmem + TC_BN, dah, dbl, idesc, 1u);
+            tc_mma_tf32(tmem, dah, dbh, idesc, (kb | ks) != 0);              // main term   -> accumulator 0
+          }
         }
-        tc_commit(empty + 8 * s);                 // stage reusable once these MMAs have read it
-        if (kb == nkb - 1) tc_commit(accb);       // accumulators complete
+        if (PAIR) {
+          tc_commit_pair(empty + 8 * s);
+          if (kb == nkb - 1) tc_commit_pair(accb);
+        } else {
+          tc_commit(empty + 8 * s);                 // stage reusable once these MMAs have read it
+          if (kb == nkb - 1) tc_commit(accb);       // accumulators complete
+        }
         if (tl && kb < 16) tl[57 + 2 * kb] = clock64();
       }
       __syncwarp();
     }
-  } else if (warp < TC_EPI_WARP0) {
+  } else if (warp >= TC_SPLIT_WARP0 && warp < TC_EPI_WARP0) {
     // ===== splitters
     const int group = (warp - TC_SPLIT_WARP0) / TC_SPLIT_GROUP_WARPS;
     const int t = threadIdx.x - (TC_SPLIT_WARP0 + group * TC_SPLIT_GROUP_WARPS) * 32;
@@ -372,13 +443,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       if (tl && warp == TC_SPLIT_WARP0 && kb < 16) tl[24 + 2 * kb] = clock64();
       float* st = reinterpret_cast<float*>(gen_base + s * TC_STAGE_BYTES);
       tc_split_tile(st, TC_A_BYTES / 4, TC_A_BYTES / 16, t, TC_SPLIT_GROUP_WARPS * 32, G.raw_hi != 0);
-      tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, TC_B_BYTES / 16, t, TC_SPLIT_GROUP_WARPS * 32, G.raw_hi != 0);
+      tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, B_BYTES_OWN / 16, t, TC_SPLIT_GROUP_WARPS * 32, G.raw_hi != 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (tl && warp == TC_SPLIT_WARP0 && kb < 16) tl[25 + 2 * kb] = clock64();
-      if (lane == 0) tc_bar_arrive(splitb + 8 * s);
+      if (lane == 0) {
+        if (PAIR) tc_bar_arrive_leader(splitb + 8 * s); else tc_bar_arrive(splitb + 8 * s);
+      }
     }
-  } else {
+  } else if (warp >= TC_EPI_WARP0) {
     // ===== epilogue (8 warps; warp w may only touch TMEM lanes 32 (w % 4) .. + 31; the two warps of a lane quarter
     // take 4 of the 8 column chunks each)
     const int q = warp & 3, ew = warp - TC_EPI_WARP0;
@@ -402,13 +475,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
     tc_fence_before();
   }
-  __syncthreads();
+  if (PAIR) tc_cluster_sync(); else __syncthreads();
   if (tl && warp == 0) tl[2] = clock64();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
   }
 }
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcBatch G) { tc_gemm_body<false>(G); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_gemm_pair_kernel(const __grid_constant__ TcBatch G) { tc_gemm_body<true>(G); }
 
 // out[i] = sum_s part[s][i], fixed order (split-K weight gradients)
 __global__ void __launch_bounds__(256) tc_reduce_kernel(const __grid_constant__ TcReduceBatch R) {
@@ -737,11 +815,15 @@ int TcLauncher::add(const GemmProb& p, float* partial) {
     q.C = p.C; q.ldc = p.ldc; q.split_stride = 0;
   }
   q.tiles_m = (p.M + TC_BM - 1) / TC_BM;              // rows beyond M: zero-filled operands, stores suppressed
+  if (pair) {                                         // CTA pairs: 256-row tiles, each CTA stages half of B
+    CUR_REQUIRE(p.M % (2 * TC_BM) == 0, "the CTA-pair kernel needs M to be a multiple of 256");
+    q.tiles_m = p.M / (2 * TC_BM);
+  }
   q.tile_begin = G.total_tiles;
   G.total_tiles += q.tiles_m * q.splits;
   if (!q.a_mn) CUR_TRY(make_map(&B.mapA[i], p.A, p.M, p.K, p.lda, TC_BM, false));
   else CUR_TRY(make_map(&B.mapA[i], p.A, p.K, p.M, p.lda, TC_BK, true));
-  if (!q.b_mn) CUR_TRY(make_map(&B.mapB[i], p.B, p.N, p.K, p.ldb, TC_BN, false));
+  if (!q.b_mn) CUR_TRY(make_map(&B.mapB[i], p.B, p.N, p.K, p.ldb, pair ? TC_BN / 2 : TC_BN, false));
   else CUR_TRY(make_map(&B.mapB[i], p.B, p.K, p.N, p.ldb, TC_BK, true));
   if (q.nkb2 > 0) {                                   // plain NN second segment: A2 [M][K2], B2 [K2][N]
     CUR_TRY(make_map(&B.mapA2[i], p.A2, p.M, p.K2, p.lda2, TC_BM, false));
@@ -820,6 +902,7 @@ int TcLauncher::flush(cudaStream_t s_main) {
   static bool configured = false;
   if (!configured) {
     CUR_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    CUR_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     configured = true;
   }
   cudaStream_t s = s_main;
@@ -844,7 +927,8 @@ int TcLauncher::flush(cudaStream_t s_main) {
     B.n = G.n; B.total_tiles = G.total_tiles; B.tl = g_tc_timeline;
     static const int raw_hi = (getenv("CUR_TC_RAW_HI") != nullptr && getenv("CUR_TC_RAW_HI")[0] == '1') ? 1 : 0;
     B.raw_hi = raw_hi;
-    tc_gemm_kernel<<<G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s_main>>>(B);
+    if (pair) tc_gemm_pair_kernel<<<2 * G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s_main>>>(B);
+    else tc_gemm_kernel<<<G.total_tiles, TC_THREADS, TC_SMEM_BYTES, s_main>>>(B);
     CUR_CHECK_LAUNCH();
     if (forked) CUR_CUDA_TRY(cudaEventRecord(ss->gemm, s_main));
   }
@@ -923,6 +1007,8 @@ int TcLauncher::finish(cudaStream_t s_main) {
 }
 
 TcLauncher::TcLauncher() : n_rowred(0), n_skinny(0), level(0) {
+  static const bool pair_env = getenv("CUR_TC_PAIR") != nullptr && getenv("CUR_TC_PAIR")[0] == '1';
+  pair = pair_env;
   red_pending[0] = red_pending[1] = false;
   static_assert(sizeof(TcBatch) <= sizeof(storage), "TcLauncher storage too small");
   G.n = 0; G.total_tiles = 0; R.n = 0;

@@ -31,6 +31,7 @@ struct TcLauncher {
   int n_rowred;
   struct SkinnyDesc { GemmProb p; } skinny[TC_MAX_PROBS];
   int n_skinny;
+  bool pair;                 // launch the CTA-pair (cta_group::2) kernel: every problem of the batch needs M % 256 == 0
   int level;                 // flushes so far; partial workspaces alternate between two sets (level & 1)
   bool red_pending[2];       // deferred reductions reading partial set 0 / 1 are still in flight on the side stream
   alignas(64) unsigned char storage[TC_MAX_PROBS * (4 * 128 + 128) + 64];   // TcBatch (tensor maps + problems)

@@ -119,3 +119,27 @@ def test_first_layer_shapes_ride_on_tma_zero_fill():
         ref, mag = _ref(Xs, dY, 1, 0)
         assert got.shape == (m, 256)
         _check(got, ref, mag)
+
+
+def test_cta_pair_variant_in_a_subprocess():
+    """CUR_TC_PAIR=1 launches the cta_group::2 variant (a cluster of two CTAs computes a 256 x 256 tile, each CTA stages
+    only half of the B tile, rank 0 issues tcgen05.mma.cta_group::2 for both).  Kept as an opt-in experiment (measured
+    slower than the single-CTA kernel, profiles/README.md); it must stay correct for all four operand orientations."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from tests.test_tc_gemm_gpu import _run, _ref, _check\n"
+        "rng = np.random.RandomState(1)\n"
+        "for a_t in (0, 1):\n"
+        "    for b_t in (0, 1):\n"
+        "        a = rng.randn(512, 96).astype(np.float32); b = rng.randn(96, 256).astype(np.float32)\n"
+        "        A = np.ascontiguousarray(a.T) if a_t else a; B = np.ascontiguousarray(b.T) if b_t else b\n"
+        "        got = _run(A, B, a_t, b_t); ref, mag = _ref(A, B, a_t, b_t); _check(got, ref, mag)\n"
+        "print('pair ok')\n" % root)
+    env = dict(os.environ, CUR_TC_PAIR='1')
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and 'pair ok' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
