@@ -323,16 +323,20 @@ __device__ __forceinline__ void tc_gemm_body(const TcBatch& G) {
   const int m0 = PAIR ? tm * 2 * TC_BM + (int)rank * TC_BM : tm * TC_BM;
   constexpr int B_BYTES_OWN = PAIR ? TC_B_BYTES / 2 : TC_B_BYTES;      // bytes of B this CTA stages per k-block
   constexpr int BN_OWN = PAIR ? TC_BN / 2 : TC_BN;
+  // stage = A_hi | A_lo | B_hi | B_lo; a CTA of a pair holds half of B, which makes room for a third stage in the same 192 KB
+  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES_OWN;
+  constexpr int STAGES = PAIR ? (TC_STAGES * TC_STAGE_BYTES) / STAGE_BYTES : TC_STAGES;
+  static_assert(TC_EPI_BYTES <= STAGE_BYTES, "the epilogue slabs reuse stage 0");
   const int k_begin = split * P.k_per_split;
   const int nkb = P.nkb1 + P.nkb2;
 
   const uint32_t base = (tc_smem(tc_smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
-  const uint32_t full = bars, splitb = bars + 8 * TC_STAGES, empty = bars + 16 * TC_STAGES, accb = bars + 24 * TC_STAGES;
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  const uint32_t full = bars, splitb = bars + 8 * STAGES, empty = bars + 16 * STAGES, accb = bars + 24 * STAGES;
   uint8_t* gen_base = tc_smem_raw + (base - tc_smem(tc_smem_raw));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       tc_bar_init(full + 8 * s, 1);
       tc_bar_init(splitb + 8 * s, PAIR ? 2 * TC_SPLIT_GROUP_WARPS : TC_SPLIT_GROUP_WARPS);
       tc_bar_init(empty + 8 * s, 1);
@@ -363,9 +367,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcBatch& G) {
     // ===== TMA producer
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+        const int s = kb % STAGES, round = kb / STAGES;
         if (round > 0) tc_bar_wait(empty + 8 * s, (round - 1) & 1);
-        const uint32_t st = base + s * TC_STAGE_BYTES;
+        const uint32_t st = base + s * STAGE_BYTES;
         const uint32_t a_hi = st, b_hi = st + 2 * TC_A_BYTES;
         const bool seg2 = kb >= P.nkb1;
         const CUtensorMap* mA = seg2 ? &G.mapA2[pi] : &G.mapA[pi];
@@ -401,13 +405,13 @@ __device__ __forceinline__ void tc_gemm_body(const TcBatch& G) {
     const uint32_t a_sbo = P.a_mn ? 512u : kmaj_sbo, b_sbo = P.b_mn ? 512u : kmaj_sbo;
     const uint32_t a_lt = P.a_mn ? 1u : kmaj_lt, b_lt = P.b_mn ? 1u : kmaj_lt;
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+      const int s = kb % STAGES, round = kb / STAGES;
       if (PAIR) tc_bar_wait_cluster(splitb + 8 * s, round & 1); else tc_bar_wait(splitb + 8 * s, round & 1);
       tc_fence_after();
       if (tl && kb < 16) tl[56 + 2 * kb] = clock64();
       if (lane == 0) {
-        const uint32_t st = base + s * TC_STAGE_BYTES;
-        const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+        const uint32_t st = base + s * STAGE_BYTES;
+        const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2 * TC_A_BYTES, b_lo = b_hi + B_BYTES_OWN;
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
           const uint64_t dah = tc_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt), dal = tc_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
@@ -438,12 +442,12 @@ __device__ __forceinline__ void tc_gemm_body(const TcBatch& G) {
     const int group = (warp - TC_SPLIT_WARP0) / TC_SPLIT_GROUP_WARPS;
     const int t = threadIdx.x - (TC_SPLIT_WARP0 + group * TC_SPLIT_GROUP_WARPS) * 32;
     for (int kb = group; kb < nkb; kb += TC_SPLIT_GROUPS) {
-      const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+      const int s = kb % STAGES, round = kb / STAGES;
       tc_bar_wait(full + 8 * s, round & 1);
       if (tl && warp == TC_SPLIT_WARP0 && kb < 16) tl[24 + 2 * kb] = clock64();
-      float* st = reinterpret_cast<float*>(gen_base + s * TC_STAGE_BYTES);
+      float* st = reinterpret_cast<float*>(gen_base + s * STAGE_BYTES);
       tc_split_tile(st, TC_A_BYTES / 4, TC_A_BYTES / 16, t, TC_SPLIT_GROUP_WARPS * 32, G.raw_hi != 0);
-      tc_split_tile(st + 2 * TC_A_BYTES / 4, TC_B_BYTES / 4, B_BYTES_OWN / 16, t, TC_SPLIT_GROUP_WARPS * 32, G.raw_hi != 0);
+      tc_split_tile(st + 2 * TC_A_BYTES / 4, B_BYTES_OWN / 4, B_BYTES_OWN / 16, t, TC_SPLIT_GROUP_WARPS * 32, G.raw_hi != 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (tl && warp == TC_SPLIT_WARP0 && kb < 16) tl[25 + 2 * kb] = clock64();
