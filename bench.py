@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append([x.strip() for x in out.split(',')])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
