@@ -81,7 +81,8 @@ class Batch(C.Structure):
 class DdpgHyper(C.Structure):
     _fields_ = [('gamma', C.c_float), ('clip_return', C.c_float), ('action_l2', C.c_float),
                 ('clip_pos_returns', C.c_int32), ('step_counter', C.c_void_p), ('loss_ring', C.c_int32),
-                ('micro_batches', C.c_int32), ('grads_parity_stride', C.c_int64), ('loss_rows', C.c_int64)]
+                ('micro_batches', C.c_int32), ('grads_parity_stride', C.c_int64), ('loss_rows', C.c_int64),
+                ('transposes_valid', C.c_int32), ('_pad2', C.c_int32)]
 
 
 class DdpgExpert(C.Structure):
@@ -96,6 +97,14 @@ class AdamFused(C.Structure):
 
 
 CUR_MAX_RANKS = 8
+
+
+CUR_P2P_MAX_TRANSPOSES = 8
+
+
+class P2PTransposes(C.Structure):
+    _fields_ = [('n', C.c_int32), ('H', C.c_int32), ('begin', C.c_int64 * CUR_P2P_MAX_TRANSPOSES),
+                ('dst', C.c_void_p * CUR_P2P_MAX_TRANSPOSES)]
 
 
 class P2PCtx(C.Structure):
@@ -160,6 +169,10 @@ SIGNATURES = {
     'cur_p2p_allreduce_adam': (C.c_int, [C.c_void_p, C.POINTER(P2PCtx), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
                                          C.c_void_p]),
+    'cur_p2p_allreduce_adam_t': (C.c_int, [C.c_void_p, C.POINTER(P2PCtx), C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                           C.c_void_p, C.POINTER(P2PTransposes)]),
+    'cur_ddpg_rows_transposes': (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int64, C.POINTER(P2PTransposes)]),
     'cur_p2p_sharded_adam': (C.c_int, [C.c_void_p, C.POINTER(P2PCtx), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
                                        C.c_void_p]),

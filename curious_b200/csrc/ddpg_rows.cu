@@ -1069,7 +1069,7 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   // ---- launch 0: W_l^T of the hidden layers of main.Q and main.pi.  With the fused optimiser the weight-gradient
   // epilogue of the previous call already left the transposes of the stepped weights in the workspace; the caller says
   // so with adam->transposes_valid (and refreshes them with cur_ddpg_rows_refresh after any other change of theta).
-  const bool keep_wT = adam != nullptr && adam->transposes_valid != 0;
+  const bool keep_wT = adam != nullptr ? adam->transposes_valid != 0 : h->transposes_valid != 0;
   if (L > 1 && !keep_wT) {
     TransposeParams TP;
     memset(&TP, 0, sizeof(TP));
@@ -1266,5 +1266,22 @@ extern "C" int cur_ddpg_rows_refresh(void* stream, const cur_net_desc* d, const 
   }
   transpose_kernel<<<dim3(H / 32, H / 32, m), 256, 0, (cudaStream_t)stream>>>(TP);
   CUR_CHECK_LAUNCH();
+  return CUR_OK;
+}
+
+extern "C" int cur_ddpg_rows_transposes(const cur_net_desc* d, float* workspace, int64_t batch, cur_p2p_transposes* out) {
+  CUR_TRY(check_desc(d));
+  CUR_REQUIRE(workspace && out, "NULL argument");
+  CUR_REQUIRE(rows_supported(d, batch), "shape not supported by the rows schedule");
+  const NetLayout LQ = net_layout(*d, 0), LP = net_layout(*d, 1);
+  const int64_t offP = r4(LQ.total);
+  const RowsWorkspace w = carve_rows(*d, batch, workspace);
+  memset(out, 0, sizeof(*out));
+  out->H = d->hidden;
+  for (int l = 1; l < d->layers; ++l) {
+    CUR_REQUIRE(out->n + 2 <= CUR_P2P_MAX_TRANSPOSES, "too many hidden layers for the transposes table");
+    out->begin[out->n] = LQ.off_W[l]; out->dst[out->n++] = w.TQ[l];
+    out->begin[out->n] = offP + LP.off_W[l]; out->dst[out->n++] = w.TP[l];
+  }
   return CUR_OK;
 }

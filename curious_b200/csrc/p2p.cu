@@ -46,6 +46,11 @@ struct P2PParams {
   int step_div;
   float b1, omb1, b2, omb2, eps;
   int* error_flag;                              // set to 1 if the peers did not show up in time
+  // optional: H x H blocks of the arena whose stepped values are also written TRANSPOSED to dst (the backward
+  // operands W^T of the rows schedule, see cur_p2p_transposes)
+  int n_t, H;
+  int64_t t_begin4[CUR_P2P_MAX_TRANSPOSES];     // first float4 of the block inside the arena
+  float* t_dst[CUR_P2P_MAX_TRANSPOSES];
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -91,9 +96,10 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(const __grid_co
   float4* th4 = reinterpret_cast<float4*>(P.theta);
   float4* m4 = reinterpret_cast<float4*>(P.m);
   float4* v4 = reinterpret_cast<float4*>(P.v);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+  // one element group: sum over ranks in fixed order (bit-identical on every rank), Adam, returns the new parameters
+  auto step4 = [&](int64_t i) {
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < P.world; ++r) {                        // fixed order: bit-identical on every rank
+    for (int r = 0; r < P.world; ++r) {
       const float4 x = ld_peer_f4(reinterpret_cast<const float4*>(P.region[r] + buf_off) + i);
       if (r == 0) g = x;
       else { g.x = __fadd_rn(g.x, x.x); g.y = __fadd_rn(g.y, x.y); g.z = __fadd_rn(g.z, x.z); g.w = __fadd_rn(g.w, x.w); }
@@ -104,6 +110,31 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(const __grid_co
     adam_elem(T.z, g.z, M.z, V.z, neg_a, P.b1, P.omb1, P.b2, P.omb2, P.eps);
     adam_elem(T.w, g.w, M.w, V.w, neg_a, P.b1, P.omb1, P.b2, P.omb2, P.eps);
     th4[i] = T; m4[i] = M; v4[i] = V;
+    return T;
+  };
+  const int64_t blk4 = (int64_t)P.H * P.H / 4;                 // float4s of one H x H block
+  // ---- everything outside the transposed blocks: linear
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    bool in_block = false;
+    for (int b = 0; b < P.n_t; ++b) in_block |= (i >= P.t_begin4[b] && i < P.t_begin4[b] + blk4);
+    if (!in_block) step4(i);
+  }
+  // ---- the H x H blocks by 32 x 32 tiles: stepped values go to theta and, turned in shared memory, to W^T
+  if (P.n_t > 0) {
+    __shared__ float tile[32][33];
+    const int tiles_per_row = P.H / 32, tiles = tiles_per_row * tiles_per_row;
+    const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+    for (int w = blockIdx.x; w < P.n_t * tiles; w += gridDim.x) {
+      const int b = w / tiles, t = w - b * tiles;
+      const int tr = t / tiles_per_row, tc = t - tr * tiles_per_row;
+      const float4 T = step4(P.t_begin4[b] + (int64_t)(tr * 32 + ty) * (P.H / 4) + tc * 8 + tx);
+      tile[4 * tx + 0][ty] = T.x; tile[4 * tx + 1][ty] = T.y; tile[4 * tx + 2][ty] = T.z; tile[4 * tx + 3][ty] = T.w;
+      __syncthreads();
+      // row ty of the turned tile = column tc * 32 + ty of W; its 32 values are rows tr * 32 .. + 31 of W
+      *reinterpret_cast<float4*>(P.t_dst[b] + (int64_t)(tc * 32 + ty) * P.H + tr * 32 + 4 * tx) =
+          make_float4(tile[ty][4 * tx], tile[ty][4 * tx + 1], tile[ty][4 * tx + 2], tile[ty][4 * tx + 3]);
+      __syncthreads();
+    }
   }
 }
 
@@ -230,7 +261,7 @@ extern "C" int cur_p2p_free(void* ptr) {
 
 static int p2p_launch(void* stream, const cur_p2p_ctx* ctx, float* theta, float* m, float* v, const float* neg_a_table,
                       int table_len, const int64_t* step_counter, double beta1, double beta2, double eps,
-                      int32_t* error_flag, bool sharded) {
+                      int32_t* error_flag, bool sharded, const cur_p2p_transposes* tr = nullptr) {
   CUR_REQUIRE(ctx && theta && m && v && neg_a_table && step_counter && table_len > 0, "NULL argument");
   CUR_REQUIRE(ctx->world >= 1 && ctx->world <= CUR_MAX_RANKS && ctx->rank >= 0 && ctx->rank < ctx->world, "bad rank/world");
   CUR_REQUIRE(ctx->arena > 0 && (ctx->arena & 3) == 0, "arena must be a positive multiple of 4 floats");
@@ -245,6 +276,17 @@ static int p2p_launch(void* stream, const cur_p2p_ctx* ctx, float* theta, float*
   P.step_counter = step_counter; P.step_div = ctx->step_div > 1 ? ctx->step_div : 1;
   P.b1 = (float)beta1; P.omb1 = (float)(1.0 - beta1); P.b2 = (float)beta2; P.omb2 = (float)(1.0 - beta2);
   P.eps = (float)eps; P.error_flag = error_flag;
+  P.H = 32;
+  if (tr != nullptr && tr->n > 0) {
+    CUR_REQUIRE(!sharded, "the sharded exchange does not maintain transposes");
+    CUR_REQUIRE(tr->n <= CUR_P2P_MAX_TRANSPOSES && tr->H >= 32 && (tr->H % 32) == 0, "bad transposes table");
+    P.n_t = tr->n; P.H = tr->H;
+    for (int b = 0; b < tr->n; ++b) {
+      CUR_REQUIRE(tr->begin[b] >= 0 && (tr->begin[b] & 3) == 0 && tr->begin[b] + (int64_t)tr->H * tr->H <= ctx->arena &&
+                  tr->dst[b] != nullptr, "bad transposes entry");
+      P.t_begin4[b] = tr->begin[b] >> 2; P.t_dst[b] = tr->dst[b];
+    }
+  }
   const int64_t n4 = ctx->arena >> 2;
   int blocks = (int)((n4 + 255) / 256);
   const int cap = sm_count();
@@ -268,6 +310,14 @@ extern "C" int cur_p2p_allreduce_adam(void* stream, const cur_p2p_ctx* ctx, floa
                                       const float* neg_a_table, int table_len, const int64_t* step_counter,
                                       double beta1, double beta2, double eps, int32_t* error_flag) {
   return p2p_launch(stream, ctx, theta, m, v, neg_a_table, table_len, step_counter, beta1, beta2, eps, error_flag, false);
+}
+
+extern "C" int cur_p2p_allreduce_adam_t(void* stream, const cur_p2p_ctx* ctx, float* theta, float* m, float* v,
+                                        const float* neg_a_table, int table_len, const int64_t* step_counter,
+                                        double beta1, double beta2, double eps, int32_t* error_flag,
+                                        const cur_p2p_transposes* transposes) {
+  return p2p_launch(stream, ctx, theta, m, v, neg_a_table, table_len, step_counter, beta1, beta2, eps, error_flag, false,
+                    transposes);
 }
 
 extern "C" int cur_p2p_sharded_adam(void* stream, const cur_p2p_ctx* ctx, float* theta, float* m, float* v,

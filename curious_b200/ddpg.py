@@ -555,6 +555,12 @@ class DDPG(object):
             # sharded, 8 GPUs: 97.3 / 98.2): the exchange is latency / straggler bound, so the one-round kernel is default
             self._peer = PeerGradExchange(self.net.arena, self.comm, sharded=self.grad_exchange == 'p2p_sharded')
             self._peer.ctx.step_div = self._micro
+            # the one-round exchange kernel also writes W^T of the stepped hidden layers: no transpose launch per update
+            self._peer_wT = None
+            if not self._peer.sharded:
+                self._peer_wT = _lib.P2PTransposes()
+                _lib.check(lib.cur_ddpg_rows_transposes(C.byref(self.net.desc), self._workspace_rows(B).data_ptr(), B,
+                                                        C.byref(self._peer_wT)), 'cur_ddpg_rows_transposes')
             self._ghyper.grads_parity_stride = self.net.arena
         self._graph_sig = None
         self._refresh_dyn()
@@ -582,6 +588,9 @@ class DDPG(object):
         # capture: a captured torch NCCL all-reduce dead-locked on the 2-GPU box).
         # With the peer-memory exchange the all-reduce IS the Adam kernel and the whole update is one graph again.
         self._graph_has_adam = _world(self.comm)[1] == 1 or self._peer is not None
+        keeps_wT = self._peer is not None and getattr(self, '_peer_wT', None) is not None
+        if keeps_wT:
+            self._ghyper.transposes_valid = 1
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             # fused Adam: its epilogue keeps W^T current, so the captured update has no transpose launch
@@ -589,7 +598,7 @@ class DDPG(object):
             if self._graph_has_adam and not fused:
                 self._launch_adam()
         self._graph = g
-        self._graph_fused = fused
+        self._graph_fused = fused or keeps_wT
         self._wT_dirty = True            # the warm-up stepped (and we restored) theta: rebuild W^T before the first replay
         if self._peer is not None:
             import torch.distributed as dist
@@ -681,7 +690,7 @@ class DDPG(object):
             else:
                 self._peer.allreduce_adam(_lib.stream_ptr(), self.theta_main, self._adam_m, self._adam_v,
                                           self._adam_tables[0], self.ADAM_TABLE, self._step, qa.beta1, qa.beta2,
-                                          qa.epsilon)
+                                          qa.epsilon, transposes=self._peer_wT)
             return
         if self._same_rule():
             # same step rule for both nets: ONE launch over the whole [Q | pad | pi] arena (padding has zero
@@ -700,7 +709,7 @@ class DDPG(object):
     def _refresh_wT(self):
         """Rebuild the transposed hidden-layer weights in the rows workspace after theta_main changed outside the
         fused update (initial weights, set_flat / load_weights, broadcast from rank 0, launch-by-launch updates)."""
-        B = self.batch_size
+        B = self._graph_rows                 # the workspace of the captured update (workers x batch_size rows when wide)
         _lib.check(_lib.load().cur_ddpg_rows_refresh(_lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(),
                                                      self._workspace_rows(B).data_ptr(), B), 'cur_ddpg_rows_refresh')
         self._wT_dirty = False

@@ -117,9 +117,16 @@ class PeerGradExchange(object):
         """Device address of gradient buffer `parity` in this rank's own region."""
         return self.own + self.FLAG_BYTES + 4 * self.arena * parity
 
-    def allreduce_adam(self, stream, theta, m, v, neg_a_table, table_len, step_counter, beta1, beta2, eps):
+    def allreduce_adam(self, stream, theta, m, v, neg_a_table, table_len, step_counter, beta1, beta2, eps,
+                       transposes=None):
         import ctypes as C
         from . import _lib
+        if transposes is not None and not self.sharded:
+            _lib.check(self.lib.cur_p2p_allreduce_adam_t(
+                stream, C.byref(self.ctx), theta.data_ptr(), m.data_ptr(), v.data_ptr(), neg_a_table.data_ptr(),
+                int(table_len), step_counter.data_ptr(), beta1, beta2, eps, self.error_flag.data_ptr(),
+                C.byref(transposes)), 'cur_p2p_allreduce_adam_t')
+            return
         fn = self.lib.cur_p2p_sharded_adam if self.sharded else self.lib.cur_p2p_allreduce_adam
         _lib.check(fn(
             stream, C.byref(self.ctx), theta.data_ptr(), m.data_ptr(), v.data_ptr(), neg_a_table.data_ptr(),

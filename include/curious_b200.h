@@ -276,6 +276,10 @@ typedef struct cur_ddpg_hyper {
    * gradients (each loss a mean over loss_rows rows, ddpg.py:439-441 + the SUM all-reduce of ddpg.py:452-453).  The
    * reported losses stay means over the whole batch (= the average worker's loss).  0: loss_rows = batch. */
   int64_t loss_rows;
+  /* rows schedule, without the fused optimiser: 1 = the transposed hidden-layer weights in the workspace are current
+   * (maintained by cur_p2p_allreduce_adam_t or cur_ddpg_rows_refresh), the transpose launch is skipped. */
+  int32_t transposes_valid;
+  int32_t _pad;
 } cur_ddpg_hyper;
 
 /* DDPG._grads (ddpg.py:235-243): writes grads = [Q_grad | pi_grad] (flat), Q_loss (1 float),
@@ -382,6 +386,21 @@ int cur_p2p_free(void* ptr);
 int cur_p2p_allreduce_adam(void* stream, const cur_p2p_ctx* ctx, float* theta, float* m, float* v,
                            const float* neg_a_table, int table_len, const int64_t* step_counter,
                            double beta1, double beta2, double eps, int32_t* error_flag /* or NULL */);
+/* Same, and for up to CUR_P2P_MAX_TRANSPOSES H x H blocks of the arena (hidden-layer kernels) the stepped values are
+ * also written transposed to dst[b] - the backward operands W^T that the rows schedule would otherwise rebuild with a
+ * transpose launch at the start of every update (cur_ddpg_hyper.transposes_valid). */
+#define CUR_P2P_MAX_TRANSPOSES 8
+typedef struct cur_p2p_transposes {
+  int32_t n, H;
+  int64_t begin[CUR_P2P_MAX_TRANSPOSES];   /* float offset of the block inside the arena, multiple of 4 */
+  float* dst[CUR_P2P_MAX_TRANSPOSES];      /* H x H floats each */
+} cur_p2p_transposes;
+int cur_p2p_allreduce_adam_t(void* stream, const cur_p2p_ctx* ctx, float* theta, float* m, float* v,
+                             const float* neg_a_table, int table_len, const int64_t* step_counter,
+                             double beta1, double beta2, double eps, int32_t* error_flag /* or NULL */,
+                             const cur_p2p_transposes* transposes /* or NULL */);
+/* The table for this rank's rows-schedule workspace (hidden-layer blocks of main.Q / main.pi -> their W^T buffers). */
+int cur_ddpg_rows_transposes(const cur_net_desc* d, float* workspace, int64_t batch, cur_p2p_transposes* out);
 /* Sharded form of the same step (reduce-scatter by peer loads, Adam on the rank's own slice of the arena,
  * all-gather by peer stores into the staging arenas, second flag round, local copy): (W-1)/W of one arena
  * in each direction per rank instead of W-1 arenas of loads.  Same result on every rank, bit-identical to

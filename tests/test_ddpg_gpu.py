@@ -521,6 +521,16 @@ def test_wide_batch_of_workers_equals_sum_of_single_batch_gradients():
     out = [float(g.train()[0]) for _ in range(5)]
     assert g._wide and g._graph_rows == k * kw['batch_size'] and np.isfinite(out).all()
     assert int(g._step.item()) == 5 and g.Q_adam.t == 5
+    # the same wide batches on the levels schedule (same Philox stream, other kernels): the trajectories stay together
+    lv = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', workers_per_rank=k, update_schedule='levels')
+    np.random.seed(21)
+    _fill(lv, episode_stream(dims, kw['T'], 8), cp)
+    out_lv = [float(lv.train()[0]) for _ in range(5)]
+    assert lv._wide and not lv._use_rows(lv._graph_rows) and g._use_rows(g._graph_rows)
+    assert np.allclose(out, out_lv, rtol=2e-3), (out, out_lv)
+    for which in ('Q', 'pi'):
+        err = np.abs(g.get_flat(which) - lv.get_flat(which))
+        assert np.quantile(err, 0.999) <= 2e-4 and err.max() <= 5 * 1e-3 * 1.01, which
     big = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', workers_per_rank=8)        # 2048 rows: tensor-core levels
     np.random.seed(21)
     _fill(big, episode_stream(dims, kw['T'], 8), cp)
