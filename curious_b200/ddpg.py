@@ -557,7 +557,10 @@ class DDPG(object):
             self._peer.ctx.step_div = self._micro
             # the one-round exchange kernel also writes W^T of the stepped hidden layers: no transpose launch per update
             self._peer_wT = None
-            if not self._peer.sharded:
+            import os
+            # opt-in (CUR_P2P_WT=1): measured 4 us SLOWER per update on 2 GPUs than the separate 2.5 us transpose
+            # launch (the tile phase runs behind the linear phase on the kernel's 148 CTAs)
+            if not self._peer.sharded and os.environ.get('CUR_P2P_WT', '0') == '1':
                 self._peer_wT = _lib.P2PTransposes()
                 _lib.check(lib.cur_ddpg_rows_transposes(C.byref(self.net.desc), self._workspace_rows(B).data_ptr(), B,
                                                         C.byref(self._peer_wT)), 'cur_ddpg_rows_transposes')
@@ -650,7 +653,10 @@ class DDPG(object):
             fuse = self._same_rule() and _world(self.comm)[1] == 1 and self._micro == 1
             adam = _lib.AdamFused(self._adam_m.data_ptr(), self._adam_v.data_ptr(), self._adam_tables[0].data_ptr(),
                                   self.ADAM_TABLE, 1 if keep_wT else 0, qa.beta1, qa.beta2, qa.epsilon) if fuse else None
+            base_valid = self._ghyper.transposes_valid
             for j in range(self._micro):
+                # the weights do not change between the workers of one update: only the first launch re-transposes
+                self._ghyper.transposes_valid = 1 if (j > 0 or base_valid) else 0
                 if j > 0 and her_args is None:            # unfused sampling: a fresh batch for every worker
                     sampler.sample_device(segs, self._graph_rows, clip_obs=self.clip_obs,
                                           relative_goals=self.relative_goals, want=self._gwant, out=self._gbatch,
@@ -662,6 +668,7 @@ class DDPG(object):
                     self._q_ring.data_ptr(), self._pi_ring.data_ptr(), self._q_pi.data_ptr(),
                     C.byref(adam) if fuse else None, C.byref(her_args) if her_args is not None else None),
                     'cur_ddpg_rows_step')
+            self._ghyper.transposes_valid = base_valid
             return fuse
         _lib.check(lib.cur_ddpg_grads(
             _lib.stream_ptr(), C.byref(self.net.desc), self.theta_main.data_ptr(), self.theta_target.data_ptr(),
