@@ -98,13 +98,17 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(const __grid_co
   float4* v4 = reinterpret_cast<float4*>(P.v);
   // one element group: sum over ranks in fixed order (bit-identical on every rank), Adam, returns the new parameters
   auto step4 = [&](int64_t i) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < P.world; ++r) {
-      const float4 x = ld_peer_f4(reinterpret_cast<const float4*>(P.region[r] + buf_off) + i);
-      if (r == 0) g = x;
-      else { g.x = __fadd_rn(g.x, x.x); g.y = __fadd_rn(g.y, x.y); g.z = __fadd_rn(g.z, x.z); g.w = __fadd_rn(g.w, x.w); }
-    }
+    // all ranks' loads are issued before the first add: a runtime-length loop would serialise W - 1 NVLink round
+    // trips per element group (~1.5 us each)
+    float4 x[CUR_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < CUR_MAX_RANKS; ++r)
+      if (r < P.world) x[r] = ld_peer_f4(reinterpret_cast<const float4*>(P.region[r] + buf_off) + i);
     float4 T = th4[i], M = m4[i], V = v4[i];
+    float4 g = x[0];
+#pragma unroll
+    for (int r = 1; r < CUR_MAX_RANKS; ++r)
+      if (r < P.world) { g.x = __fadd_rn(g.x, x[r].x); g.y = __fadd_rn(g.y, x[r].y); g.z = __fadd_rn(g.z, x[r].z); g.w = __fadd_rn(g.w, x[r].w); }
     adam_elem(T.x, g.x, M.x, V.x, neg_a, P.b1, P.omb1, P.b2, P.omb2, P.eps);
     adam_elem(T.y, g.y, M.y, V.y, neg_a, P.b1, P.omb1, P.b2, P.omb2, P.eps);
     adam_elem(T.z, g.z, M.z, V.z, neg_a, P.b1, P.omb1, P.b2, P.omb2, P.eps);
@@ -184,13 +188,15 @@ __global__ void __launch_bounds__(256) p2p_sharded_adam_kernel(const __grid_cons
   float4* m4 = reinterpret_cast<float4*>(P.m);
   float4* v4 = reinterpret_cast<float4*>(P.v);
   for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < P.world; ++r) {
-      const float4 x = ld_peer_f4(reinterpret_cast<const float4*>(P.region[r] + gbuf) + i);
-      if (r == 0) g = x;
-      else { g.x = __fadd_rn(g.x, x.x); g.y = __fadd_rn(g.y, x.y); g.z = __fadd_rn(g.z, x.z); g.w = __fadd_rn(g.w, x.w); }
-    }
+    float4 x[CUR_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < CUR_MAX_RANKS; ++r)
+      if (r < P.world) x[r] = ld_peer_f4(reinterpret_cast<const float4*>(P.region[r] + gbuf) + i);
     float4 T = th4[i], M = m4[i], V = v4[i];
+    float4 g = x[0];
+#pragma unroll
+    for (int r = 1; r < CUR_MAX_RANKS; ++r)
+      if (r < P.world) { g.x = __fadd_rn(g.x, x[r].x); g.y = __fadd_rn(g.y, x[r].y); g.z = __fadd_rn(g.z, x[r].z); g.w = __fadd_rn(g.w, x[r].w); }
     adam_elem(T.x, g.x, M.x, V.x, neg_a, P.b1, P.omb1, P.b2, P.omb2, P.eps);
     adam_elem(T.y, g.y, M.y, V.y, neg_a, P.b1, P.omb1, P.b2, P.omb2, P.eps);
     adam_elem(T.z, g.z, M.z, V.z, neg_a, P.b1, P.omb1, P.b2, P.omb2, P.eps);
@@ -289,7 +295,7 @@ static int p2p_launch(void* stream, const cur_p2p_ctx* ctx, float* theta, float*
   }
   const int64_t n4 = ctx->arena >> 2;
   int blocks = (int)((n4 + 255) / 256);
-  const int cap = sm_count();
+  const int cap = 2 * sm_count();          // co-resident (256 threads, no shared memory): all blocks spin on the flags
   if (blocks > cap) blocks = cap;
   if (sharded && ctx->world > 1) {
     // all blocks spin on flags: they must be co-resident (blocks <= SM count holds) and few enough that the slice loop
