@@ -813,14 +813,84 @@ class DDPG(object):
         self.o_stats.load_state_list(weights[4])
         self.g_stats.load_state_list(weights[5])
 
+    # ------------------------------------------------------------------------------------------ resume
+    def _unique_buffers(self):
+        """The distinct ReplayBuffer objects behind self.buffer (Arm8: buffers 6.. alias 5, ddpg.py:107-110)."""
+        seen, out = set(), []
+        for i, b in enumerate(self.buffer if isinstance(self.buffer, (list, tuple)) else [self.buffer]):
+            if id(b) not in seen:
+                seen.add(id(b))
+                out.append((i, b))
+        return out
+
+    def save_checkpoint(self, path, buffers=True, numpy_rng=True):
+        """Everything a run needs to continue bit for bit: parameters, Adam moments and step counters, normaliser
+        accumulators, the Philox stream positions and (optionally) the replay buffers and the host np.random state.
+        The reference can only save weights + normaliser statistics (ddpg.py:481-497): its Adam
+        state, replay data and RNG position are lost on restart.  One torch.save file, tensors on the host."""
+        cpu = lambda t: t.detach().cpu().clone()
+        st = dict(format=1, arena=int(self.net.arena), theta_main=cpu(self.theta_main), theta_target=cpu(self.theta_target),
+                  adam_m=cpu(self._adam_m), adam_v=cpu(self._adam_v), adam_t=(int(self.Q_adam.t), int(self.pi_adam.t)),
+                  step=int(self._step.item()), n_updates=int(self._n_updates),
+                  sampler=dict(calls=int(self.sample_transitions.calls), seed=int(self.sample_transitions.seed)),
+                  norm={k: dict(running=cpu(n._running), partial=cpu(n._partial), mean=cpu(n.mean), std=cpu(n.std))
+                        for k, n in (('o', self.o_stats), ('g', self.g_stats))})
+        if numpy_rng:
+            st['numpy_rng'] = np.random.get_state()
+        if buffers:
+            st['buffers'] = []
+            for i, b in self._unique_buffers():
+                L, n = b.layout, b.current_size
+                st['buffers'].append(dict(
+                    index=i, current_size=n, n_transitions_stored=b.n_transitions_stored, layout=bytes(L),
+                    hot=cpu(b.storage[:n * (L.T + 1) * L.row_stride]),
+                    cold=None if b.cold is None else cpu(b.cold[:n * L.T * L.cold_stride])))
+        torch.save(st, path)
+
+    def load_checkpoint(self, path):
+        """Inverse of save_checkpoint on an agent built with the same arguments (checked: arena size, buffer layouts)."""
+        st = torch.load(path, map_location='cpu', weights_only=False)
+        if st.get('format') != 1 or st['arena'] != int(self.net.arena):
+            raise ValueError('checkpoint %s does not fit this agent (arena %s vs %d)' % (path, st.get('arena'),
+                                                                                      self.net.arena))
+        if getattr(self, '_peer', None) is not None and st['step'] < int(self._step.item()):
+            # the peer-memory exchange counts updates in its NVLink flags (csrc/p2p.cu): they cannot run backwards
+            raise ValueError('load the checkpoint into a freshly built agent when the peer-memory exchange is active')
+        for dst, key in ((self.theta_main, 'theta_main'), (self.theta_target, 'theta_target'),
+                         (self._adam_m, 'adam_m'), (self._adam_v, 'adam_v')):
+            dst.copy_(st[key].to(self.device))
+        self.Q_adam.t, self.pi_adam.t = st['adam_t']
+        self._step.fill_(st['step'])
+        self._n_updates = st['n_updates']
+        self.sample_transitions.calls = st['sampler']['calls']
+        self.sample_transitions.seed = st['sampler']['seed']
+        for k, n in (('o', self.o_stats), ('g', self.g_stats)):
+            for dst, key in ((n._running, 'running'), (n._partial, 'partial'), (n.mean, 'mean'), (n.std, 'std')):
+                dst.copy_(st['norm'][k][key].to(self.device))
+        if 'buffers' in st:
+            mine = dict(self._unique_buffers())
+            for rec in st['buffers']:
+                b = mine.get(rec['index'])
+                if b is None or bytes(b.layout) != rec['layout'] or rec['current_size'] > b.size:
+                    raise ValueError('checkpoint buffer %d does not fit this agent' % rec['index'])
+                with b.lock:
+                    b.storage[:rec['hot'].numel()].copy_(rec['hot'].to(self.device))
+                    if rec['cold'] is not None:
+                        b.cold[:rec['cold'].numel()].copy_(rec['cold'].to(self.device))
+                    b.current_size = rec['current_size']
+                    b.n_transitions_stored = rec['n_transitions_stored']
+        if 'numpy_rng' in st:
+            np.random.set_state(st['numpy_rng'])
+        self._mark_weights_changed()
+        self._graph_sig = None            # buffer sizes changed: the graph's control block is rewritten on the next train()
+
     def __getstate__(self):
         """Policies can be pickled for playing; training state (Adam, buffers) is not saved (ddpg.py:511-521)."""
         excluded_subnames = ['_tf', '_op', '_vars', '_adam', 'buffer', 'sess', '_stats', 'main', 'target', 'lock',
-                             'env', 'sample_transitions', 'stage_shapes', 'create_actor_critic', 'theta_', 'grads',
-                             '_ws', '_batch', '_staged', 'net', 'device', 'comm', '_hyper', '_q_loss', '_pi_loss',
-                             'kwargs', '_graph', '_peer', '_dyn', '_gbatch', '_ghyper', '_gwant', '_q_ring', '_pi_ring',
-                             '_q_pi', '_her_keep', '_step', '_last_perm']
-        state = {k: v for k, v in self.__dict__.items() if all([subname not in k for subname in excluded_subnames])}
+                             'env', 'sample_transitions', 'stage_shapes', 'create_actor_critic']      # ddpg.py:514-516
+        device_state = ('net', 'device', 'comm', 'grads', 'kwargs')     # this implementation's own (exact names + _private)
+        state = {k: v for k, v in self.__dict__.items() if not k.startswith('_') and k not in device_state and
+                 all([subname not in k for subname in excluded_subnames])}
         state['weights'] = [self.get_flat('Q'), self.get_flat('pi'), self.get_flat('Q', True), self.get_flat('pi', True),
                             self.o_stats.state_list(), self.g_stats.state_list()]
         return state

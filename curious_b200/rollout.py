@@ -227,6 +227,9 @@ class RolloutWorker(object):
         if hasattr(self.policy, 'save_weights'):
             self.policy.save_weights(path)
 
+    def save_goal_task_history(self, path):
+        """No-op, like the reference's (rollout.py:437-449: body commented out); kept for the train loop's call."""
+
     def _prefixed(self, items, prefix):
         return [((prefix.rstrip('/') + '/' + k) if prefix else k, v) for k, v in items]
 
@@ -244,5 +247,7 @@ class RolloutWorker(object):
             for i in range(self.nb_tasks):
                 items.append(('C_task%d' % i, '%.3g' % C[i]))
                 if not self.eval:
-                    items += [('CP_task%d' % i, '%.3g' % CP[i]), ('p_task%d' % i, '%.3g' % self.p[i])]
+                    share = np.mean(np.array(self.task_history)[-100:] == i) if len(self.task_history) else 0.0
+                    items += [('CP_task%d' % i, '%.3g' % CP[i]), ('%%_task%d' % i, '%.3g' % share),
+                              ('p_task%d' % i, '%.3g' % self.p[i])]
         return self._prefixed(items, prefix)

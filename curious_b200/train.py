@@ -6,9 +6,14 @@ configure_dims) for environments with the gym_flowers attribute contract (SURVEY
                           task_replay='replay_task_cp_buffer')
     history = train(**exp, n_epochs=10)
 
-Process launch (`mpirun -np N` -> `python -m torch.distributed.run --nproc-per-node N`), logging to files and
-policy checkpoints are the caller's business; this module is the loop itself.
+Process launch (`mpirun -np N` -> `python -m torch.distributed.run --nproc-per-node N`) is the caller's business
+(INTEGRATION.md).  With `logdir=` the loop writes the reference's run records (progress.csv, params.json,
+policy_latest / policy_best / policy_<epoch>.pkl, train.py:53-55,171-206,264-266 - see runlog.py) and, beyond the
+reference, a resumable checkpoint per epoch (`checkpoint_interval`, DDPG.save_checkpoint).
 """
+import os
+import time
+
 import numpy as np
 
 from . import her
@@ -16,6 +21,7 @@ from .ddpg import DDPG
 from .envs import ModularPointEnv
 from .replay_buffer import ReplayBuffer
 from .rollout import RolloutWorker
+from .runlog import RunLog, mpi_average
 
 MULTI_TASK_PARAMS = {            # config.py:56-90
     'max_u': 1., 'layers': 3, 'hidden': 256, 'network_class': 'baselines.her.actor_critic:MultiTaskActorCritic',
@@ -27,6 +33,12 @@ MULTI_TASK_PARAMS = {            # config.py:56-90
 }
 FLAT_PARAMS = dict(MULTI_TASK_PARAMS, network_class='baselines.her.actor_critic:ActorCritic',
                    her_sampling_func='baselines.her.her:make_sample_her_transitions', queue_length=200)
+
+
+def simple_goal_subtract(a, b):
+    """config.py:177-179 (a module-level function, so that policies pickle)."""
+    assert a.shape == b.shape
+    return a - b
 
 
 def configure_dims(env, structure):
@@ -82,7 +94,7 @@ def make_experiment(nb_tasks=4, n_controllable=None, structure='curious', task_s
                    polyak=params['polyak'], batch_size=params['batch_size'], Q_lr=params['Q_lr'], pi_lr=params['pi_lr'],
                    norm_eps=params['norm_eps'], norm_clip=params['norm_clip'], max_u=params['max_u'],
                    action_l2=params['action_l2'], clip_obs=params['clip_obs'], scope=params['scope'], T=T,
-                   rollout_batch_size=params['rollout_batch_size'], subtract_goals=lambda a, b: a - b,
+                   rollout_batch_size=params['rollout_batch_size'], subtract_goals=simple_goal_subtract,
                    relative_goals=params['relative_goals'], clip_pos_returns=True, clip_return=1. / (1. - gamma),
                    normalize_obs=normalize_obs, sample_transitions=sampler, gamma=gamma, tasks_ag_id=ag_ids, tasks_g_id=g_ids,
                    task_replay=task_replay, eps_task=params.get('eps_task'), structure=structure, her_rng='philox',
@@ -103,9 +115,13 @@ def make_experiment(nb_tasks=4, n_controllable=None, structure='curious', task_s
     evaluator = RolloutWorker(make_env, policy, **test)
     for i, w in enumerate((rollout_worker if isinstance(rollout_worker, list) else [rollout_worker]) + [evaluator]):
         w.seed(seed + 10 * i)
+    run_params = dict(params, structure=structure, task_selection=task_selection, goal_selection='random',
+                      goal_replay=goal_replay, task_replay=task_replay, normalize_obs=normalize_obs, seed=seed,
+                      nb_tasks=nb_tasks, T=T, gamma=gamma, clip_return=1. / (1. - gamma),
+                      env_name=type(env).__name__, num_cpu=evaluator.nb_cpu)
     return dict(policy=policy, rollout_worker=rollout_worker, evaluator=evaluator, n_cycles=params['n_cycles'],
                 n_batches=params['n_batches'], n_test_rollouts=params['n_test_rollouts'], structure=structure,
-                task_selection=task_selection, eps_task=params.get('eps_task', 0.4))
+                task_selection=task_selection, eps_task=params.get('eps_task', 0.4), params=run_params)
 
 
 def _evaluate(evaluator, n_test_rollouts):
@@ -119,11 +135,65 @@ def _evaluate(evaluator, n_test_rollouts):
     return out
 
 
+class _EpochRecords(object):
+    """train.py:171-206 (`logs`): the tabular row of one epoch and the policy files, written by rank 0."""
+
+    def __init__(self, logdir, evaluator, params, policy_save_interval, save_policies, checkpoint_interval, echo):
+        self.evaluator = evaluator
+        self.rank = evaluator.rank
+        self.log = RunLog(logdir, rank=self.rank, echo=echo)
+        self.save_policies, self.interval = save_policies, policy_save_interval
+        self.checkpoint_interval = checkpoint_interval
+        self.best = -1
+        self.t0 = time.time()
+        if params is not None:
+            self.log.write_params(params)
+        self.log.info('Training...')
+
+    def _path(self, name):
+        return os.path.join(self.log.get_dir(), name)
+
+    def epoch(self, epoch, rollout_worker, policy, i_policy=None):
+        log, comm = self.log, self.evaluator.comm
+        log.record_tabular('epoch', epoch)
+        for key, val in self.evaluator.logs('test'):
+            log.record_tabular(key, '%.3g' % mpi_average(val, comm))
+        for key, val in rollout_worker.logs('train'):
+            log.record_tabular(key, '%.3g' % mpi_average(val, comm))
+        for key, val in (policy[i_policy] if isinstance(policy, list) else policy).logs():
+            log.record_tabular(key, '%.3g' % mpi_average(val, comm))
+        if i_policy is not None:
+            log.record_tabular('IND_TASK_rollout', i_policy)
+        for key, val in rollout_worker.additional_logs('train') + self.evaluator.additional_logs('test'):
+            log.record_tabular(key, val)
+        log.record_tabular('Time', time.time() - self.t0)
+        log.dump_tabular()
+        rollout_worker.save_goal_task_history(log.get_dir())
+        success = mpi_average(self.evaluator.current_success_rate(), comm)
+        if not log.active:
+            return
+        if self.save_policies and success >= self.best:
+            self.best = success
+            log.info('New best success rate: {}. Saving policy to {} ...'.format(success, self._path('policy_best.pkl')))
+            self.evaluator.save_policy(self._path('policy_best.pkl'))
+        if self.save_policies and self.interval > 0 and epoch % self.interval == 0:
+            self.evaluator.save_policy(self._path('policy_%d.pkl' % epoch))
+            self.evaluator.save_policy(self._path('policy_latest.pkl'))
+        if self.checkpoint_interval > 0 and epoch % self.checkpoint_interval == 0:
+            for i, pol in enumerate(policy if isinstance(policy, list) else [policy]):
+                pol.save_checkpoint(self._path('checkpoint_%d.pt' % i))
+
+
 def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles, n_batches, structure='curious',
-          task_selection='active_competence_progress', eps_task=0.4, log=None):
-    """train.py:48-170 without the file I/O: per epoch n_cycles x (rollouts -> store_episode -> n_batches x train ->
-    update_target_net), then n_test_rollouts evaluation rollouts.  Returns one dict per epoch."""
+          task_selection='active_competence_progress', eps_task=0.4, log=None, logdir=None, params=None,
+          policy_save_interval=5, save_policies=True, checkpoint_interval=0, echo=False):
+    """train.py:48-170: per epoch n_cycles x (rollouts -> store_episode -> n_batches x train -> update_target_net),
+    then n_test_rollouts evaluation rollouts.  Returns one dict per epoch; with `logdir` also writes the reference's
+    run records (see module docstring)."""
     history = []
+    records = None
+    if logdir is not None:
+        records = _EpochRecords(logdir, evaluator, params, policy_save_interval, save_policies, checkpoint_interval, echo)
     if structure == 'task_experts':
         nb_tasks = len(policy)
         p = 1 / nb_tasks * np.ones([nb_tasks])
@@ -153,6 +223,8 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
             history.append(rec)
             if log:
                 log(rec)
+            if records:
+                records.epoch(epoch, rollout_worker[i_policy], policy, i_policy)
         return history
     for epoch in range(n_epochs):                                            # train.py:125-166
         rollout_worker.clear_history()
@@ -170,4 +242,8 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
         history.append(rec)
         if log:
             log(rec)
+        if records:
+            records.epoch(epoch, rollout_worker, policy)
+    if records:
+        records.log.close()
     return history

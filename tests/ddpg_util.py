@@ -19,6 +19,10 @@ def ddpg_kwargs(n_modules=4, structure='curious', task_replay='replay_task_cp_bu
     return kw, dims, ag_ids, g_ids
 
 
+def goal_subtract(a, b):
+    return a - b
+
+
 def make_oracle_agent(kw, dims, ag_ids, g_ids, buffer_episodes=40, seed=0):
     from oracle import ddpg_oracle, her_oracle, replay_oracle
     from oracle.reward_oracle import ModuleDistanceReward
@@ -67,7 +71,7 @@ def make_gpu_agent(kw, dims, ag_ids, g_ids, buffer_episodes=40, seed=0, her_rng=
         buffers = [ReplayBuffer(shapes, buffer_episodes * T, T, sampler) for _ in range(len(g_ids) + 1)]
     else:
         buffers = ReplayBuffer(shapes, buffer_episodes * T, T, sampler)
-    agent = DDPG(network_class=net, scope='ddpg', subtract_goals=lambda a, b: a - b, sample_transitions=sampler,
+    agent = DDPG(network_class=net, scope='ddpg', subtract_goals=goal_subtract, sample_transitions=sampler,
                  buffers=buffers, seed=seed, her_rng=her_rng, **kw, **extra)
     return agent
 

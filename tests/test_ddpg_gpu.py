@@ -268,6 +268,88 @@ def test_rows_schedule_trajectory(structure, layers, batch_size):
             assert err.max() <= 5 * 1e-3 * 1.01, which
 
 
+def test_policy_pickle_roundtrip():
+    """Policies are pickled for playing (ddpg.py:511-537, rollout.py:429-431, experiment/play.py:30-33): weights and
+    normaliser statistics travel, buffers / optimiser / sampler do not."""
+    import pickle
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, hidden=64, normalize_obs=True)
+    a = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', seed=3)
+    _fill(a, episode_stream(dims, kw['T'], 3), np.array([0.05, 0.2, 0.1, 0.0]))
+    for _ in range(3):
+        a.train()
+    a.update_target_net()
+    b = pickle.loads(pickle.dumps(a))
+    assert b.sample_transitions is None and not hasattr(b, 'buffer')
+    for which in ('Q', 'pi'):
+        for tgt in (False, True):
+            assert np.array_equal(a.get_flat(which, tgt), b.get_flat(which, tgt))
+    rng = np.random.RandomState(0)
+    o, ag, g = rng.randn(7, dims['o']), rng.randn(7, dims['ag']), rng.randn(7, dims['g'])
+    td = np.eye(4)[rng.randint(0, 4, 7)]
+    for tgt in (False, True):
+        ua, qa = a.get_actions(o, ag, g, task_descr=td, use_target_net=tgt, compute_Q=True)
+        ub, qb = b.get_actions(o, ag, g, task_descr=td, use_target_net=tgt, compute_Q=True)
+        assert np.array_equal(ua, ub) and np.array_equal(qa, qb)
+
+
+@pytest.mark.parametrize('use_graph', [True, False])
+def test_checkpoint_resume_continues_bit_for_bit(use_graph, tmp_path):
+    """save_checkpoint / load_checkpoint (true resume: the reference only keeps weights + normaliser statistics,
+    ddpg.py:481-497): a fresh agent that loads the checkpoint - other initial weights, empty buffers - continues
+    exactly like the agent that never stopped: same losses, parameters, Adam moments, normaliser statistics and the same
+    buffer slots overwritten (the buffers are small enough to be full, so slot choice consumes np.random)."""
+    import torch
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, normalize_obs=True)
+    first = episode_stream(dims, kw['T'], 12, seed=5)
+    later = episode_stream(dims, kw['T'], 3, seed=6)
+    cp = np.array([0.05, 0.2, 0.1, 0.0])
+
+    def run_on(agent, n_ep0):
+        out = []
+        for k, ep in enumerate(later):
+            agent.store_episode({key: v.copy() for key, v in ep.items()}, cp, n_ep0 + 2 * (k + 1))
+            for _ in range(4):
+                loss, q = agent.train()
+                out.append((float(loss), np.asarray(q).copy()))
+            agent.update_target_net()
+        return out
+
+    a = make_gpu_agent(kw, dims, ag_ids, g_ids, buffer_episodes=10, her_rng='philox', seed=1, use_cuda_graph=use_graph)
+    np.random.seed(11)
+    _fill(a, first, cp)
+    for _ in range(9):
+        a.train()
+    a.update_target_net()
+    assert any(b.full for b in a.buffer[1:]), 'the test wants random slot overwrites after the resume'
+    path = str(tmp_path / 'ckpt.pt')
+    a.save_checkpoint(path)
+    cont = run_on(a, 24)
+
+    b = make_gpu_agent(kw, dims, ag_ids, g_ids, buffer_episodes=10, her_rng='philox', seed=2, use_cuda_graph=use_graph)
+    np.random.seed(99)
+    b.load_checkpoint(path)
+    assert b.Q_adam.t == 9 and int(b._step.item()) == 9
+    assert [x.current_size for x in b.buffer] == [x.current_size for x in a.buffer]
+    resumed = run_on(b, 24)
+    for k, ((la, qa), (lb, qb)) in enumerate(zip(cont, resumed)):
+        assert la == lb, k
+        assert np.array_equal(qa, qb), k
+    for which in ('Q', 'pi'):
+        for tgt in (False, True):
+            assert np.array_equal(a.get_flat(which, tgt), b.get_flat(which, tgt)), (which, tgt)
+    assert torch.equal(a._adam_m, b._adam_m) and torch.equal(a._adam_v, b._adam_v)
+    assert torch.equal(a.o_stats._running, b.o_stats._running) and torch.equal(a.g_stats.std, b.g_stats.std)
+    for x, y in zip(a.buffer, b.buffer):
+        assert x.n_transitions_stored == y.n_transitions_stored
+        n = x.current_size * (x.layout.T + 1) * x.layout.row_stride
+        assert torch.equal(x.storage[:n], y.storage[:n])
+    # a checkpoint of another architecture is refused
+    kw2, dims2, ag2, g2 = ddpg_kwargs(4, hidden=64)
+    c = make_gpu_agent(kw2, dims2, ag2, g2, her_rng='philox')
+    with pytest.raises(ValueError):
+        c.load_checkpoint(path)
+
+
 @pytest.mark.parametrize('schedule', ['levels', 'rows'])
 @pytest.mark.parametrize('task_replay', ['replay_task_cp_buffer', 'replay_cp_task_transition'])
 def test_cuda_graph_path_equals_eager_path(task_replay, schedule):

@@ -187,3 +187,17 @@ def test_competence_progress_is_gathered_on_rank0_and_broadcast(tmp_path):
             succ += s
         cp, p = tr.update(tasks, succ)
     assert np.array_equal(res[0], np.concatenate([cp, p]))
+
+
+def _body_mpi_average(rank, world):
+    """mpi_average pools values and counts over ranks (her/util.py:141-146 -> mpi_moments.py:6-17); only rank 0's
+    RunLog writes."""
+    from curious_b200.runlog import mpi_average
+    vals = [1.0, 2.0, 3.0] if rank == 0 else [10.0]
+    return [mpi_average(vals), mpi_average(0.25 * (rank + 1)), mpi_average([])]
+
+
+def test_mpi_average_pools_over_ranks(tmp_path):
+    r0, r1 = _run('_body_mpi_average', tmp_path)
+    assert np.array_equal(r0, r1)
+    assert np.allclose(r0, [16.0 / 4, 0.375, 0.0])

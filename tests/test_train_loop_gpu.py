@@ -32,12 +32,47 @@ def test_curious_agent_learns_reach_and_lp_follows():
 
 
 @pytest.mark.parametrize('structure,task_replay', [('task_experts', 'replay_current_task_buffer'), ('flat', '')])
-def test_other_structures_run_the_same_loop(structure, task_replay):
+def test_other_structures_run_the_same_loop(structure, task_replay, tmp_path):
     from curious_b200.train import make_experiment, train
     np.random.seed(1)
     exp = make_experiment(nb_tasks=3, structure=structure, task_selection='active_competence_progress',
                           task_replay=task_replay, buffer_size=50000, n_cycles=4, n_batches=10, n_test_rollouts=2, seed=1)
-    hist = train(n_epochs=3, **exp)
+    hist = train(n_epochs=3, logdir=str(tmp_path), policy_save_interval=2, checkpoint_interval=2, **exp)
+    _check_run_records(str(tmp_path), structure, exp)
     assert len(hist) == 3 and all(0.0 <= h['test_success_rate'] <= 1.0 for h in hist)
     pols = exp['policy'] if isinstance(exp['policy'], list) else [exp['policy']]
     assert all(np.isfinite(p.get_flat('pi')).all() for p in pols)
+
+
+def _check_run_records(logdir, structure, exp):
+    """The files the reference's train loop leaves behind (train.py:53-55,171-206,264-266), read the way its analysis
+    scripts read them (analysis/plot.py:29-75)."""
+    import json
+    import os
+    import pickle
+    import pandas as pd
+    data = pd.read_csv(os.path.join(logdir, 'progress.csv'))
+    assert list(data['epoch']) == [0, 1, 2]
+    for col in ('test/success_rate', 'test/mean_Q', 'train/success_rate', 'train/episode', 'stats_o/mean', 'stats_g/std',
+                'Time'):
+        assert col in data.columns and np.isfinite(data[col]).all(), col
+    if structure == 'task_experts':
+        for col in ('IND_TASK_rollout', 'train/C_task0', 'train/CP_task2', 'train/%_task1', 'train/p_task0',
+                    'test/C_task2'):
+            assert col in data.columns, col
+    params = json.load(open(os.path.join(logdir, 'params.json')))
+    assert params['structure'] == structure and params['n_cycles'] == 4 and params['num_cpu'] == 1
+    for name in ('policy_best.pkl', 'policy_latest.pkl', 'policy_0.pkl', 'policy_2.pkl'):
+        assert os.path.exists(os.path.join(logdir, name)), name
+    assert not os.path.exists(os.path.join(logdir, 'policy_1.pkl'))
+    # the pickled policy plays (experiment/play.py:30-33): same actions as the live one
+    with open(os.path.join(logdir, 'policy_latest.pkl'), 'rb') as f:
+        loaded = pickle.load(f)
+    live = exp['policy']
+    loaded0, live0 = (loaded[0], live[0]) if isinstance(live, list) else (loaded, live)
+    d = live0.input_dims
+    rng = np.random.RandomState(3)
+    o, ag, g = rng.randn(5, d['o']), rng.randn(5, d['ag']), rng.randn(5, d['g'])
+    td = np.eye(d['task_descr'])[rng.randint(0, d['task_descr'], 5)] if 'task_descr' in d else None
+    assert np.array_equal(loaded0.get_actions(o, ag, g, task_descr=td), live0.get_actions(o, ag, g, task_descr=td))
+    assert os.path.exists(os.path.join(logdir, 'checkpoint_0.pt'))
