@@ -136,6 +136,8 @@ SIGNATURES = {
                                       C.c_float, C.c_int32]),
     'cur_polyak': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double]),
     'cur_checksum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cur_action_noise': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_double,
+                                   C.c_uint64, C.c_uint64]),
     'cur_net_param_count': (C.c_int64, [C.POINTER(NetDesc), C.c_int]),
     'cur_theta_pi_offset': (C.c_int64, [C.POINTER(NetDesc), C.POINTER(C.c_int64)]),
     'cur_ddpg_workspace_floats': (C.c_int64, [C.POINTER(NetDesc), C.c_int64]),

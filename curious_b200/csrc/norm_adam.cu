@@ -7,6 +7,7 @@
 //   baselines/common/mpi_adam.py:30-35  Adam              -> cur_adam_step[_graph]
 //   baselines/her/ddpg.py:456-462       target update     -> cur_polyak
 //   baselines/common/mpi_adam.py:42-50  check_synced      -> cur_checksum
+//   baselines/her/ddpg.py:147-152       exploration noise -> cur_action_noise (device-side option)
 //
 // All of these are tiny, L2-resident, launch-latency-bound elementwise/reduction kernels.  The
 // arithmetic uses the explicitly rounded intrinsics (__fmul_rn, __fadd_rn, ...) so the compiler
@@ -184,6 +185,48 @@ static int grid_for(int64_t n, int threads, int max_waves = 4) {
   return (int)b;
 }
 
+
+// ---------------------------------------------------------------- exploration noise (device-side option)
+// ddpg.py:147-152 on the action matrix u [n, dimu] in place, with counter-based draws instead of the host's MT19937:
+//   u += noise_eps * max_u * randn(*u.shape); u = clip(u, -max_u, max_u)
+//   u += binomial(1, random_eps, n)[:, None] * (uniform(-max_u, max_u, (n, dimu)) - u)
+// One thread per (row, pair of action components).  x = philox(counter = (row, pair, call_lo, call_hi ^ TAG),
+// key = seed): (x0, x1) -> one Box-Muller pair, (x2, x3) -> the two uniform random-action components; the row's
+// eps-greedy draw comes from the block with pair = 0xFFFFFFFF.  Arithmetic in float64 like NumPy's (the float32
+// action array is updated in place by float64 operands), rounded to float32 where the reference's `+=` rounds.
+constexpr uint32_t ACTION_NOISE_TAG = 0x40000000u;
+
+__global__ void action_noise_kernel(float* __restrict__ u, int64_t n, int dimu, float max_u, double noise_eps,
+                                    double random_eps, uint64_t seed, uint64_t call) {
+  const int pairs = (dimu + 1) / 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * pairs) return;
+  const int64_t r = idx / pairs;
+  const int p = (int)(idx - r * pairs);
+  const uint32_t c2 = (uint32_t)call, c3 = (uint32_t)(call >> 32) ^ ACTION_NOISE_TAG;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const Philox x = philox4x32_10((uint32_t)r, (uint32_t)p, c2, c3, k0, k1);
+  const Philox b = philox4x32_10((uint32_t)r, 0xFFFFFFFFu, c2, c3, k0, k1);
+  const bool explore = u01_from_u32(b.x[0]) < random_eps;                       // binomial(1, random_eps)
+  const double rad = sqrt(-2.0 * log(u01_from_u32(x.x[0])));
+  const double ang = 6.283185307179586 * u01_from_u32(x.x[1]);
+  const double z[2] = {__dmul_rn(rad, cos(ang)), __dmul_rn(rad, sin(ang))};
+  const double mu = (double)max_u;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = 2 * p + e;
+    if (k >= dimu) break;
+    float v = u[r * dimu + k];
+    v = (float)__dadd_rn((double)v, __dmul_rn(noise_eps * mu, z[e]));           // ddpg.py:148-149 (no fma contraction)
+    v = fminf(fmaxf(v, -max_u), max_u);                                         // ddpg.py:150
+    if (explore) {
+      const double ra = __dadd_rn(-mu, __dmul_rn(mu - (-mu), u01_from_u32(x.x[2 + e])));   // _random_action, ddpg.py:114-116
+      v = (float)__dadd_rn((double)v, __dsub_rn(ra, (double)v));                // ddpg.py:151
+    }
+    u[r * dimu + k] = v;
+  }
+}
+
 }  // namespace cur
 
 using namespace cur;
@@ -290,6 +333,19 @@ extern "C" int cur_checksum(void* stream, const float* x, int64_t n, uint64_t* o
   CUR_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(uint64_t), (cudaStream_t)stream));
   if (n == 0) return CUR_OK;
   checksum_kernel<<<grid_for(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(x, n, (unsigned long long*)out);
+  CUR_CHECK_LAUNCH();
+  return CUR_OK;
+}
+
+extern "C" int cur_action_noise(void* stream, float* u, int64_t n, int dimu, float max_u, double noise_eps,
+                                double random_eps, uint64_t seed, uint64_t call) {
+  CUR_REQUIRE(u != nullptr, "NULL argument");
+  CUR_REQUIRE(n >= 0 && n < (1ll << 32) && dimu > 0, "bad shape");
+  CUR_REQUIRE(noise_eps >= 0.0 && random_eps >= 0.0 && random_eps <= 1.0, "bad noise parameters");
+  if (n == 0) return CUR_OK;
+  const int64_t threads = n * ((dimu + 1) / 2);
+  action_noise_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      u, n, dimu, max_u, noise_eps, random_eps, seed, call);
   CUR_CHECK_LAUNCH();
   return CUR_OK;
 }

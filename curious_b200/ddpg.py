@@ -13,6 +13,7 @@ the exploration noise of get_actions - they consume the caller's np.random strea
 
 Extra keyword arguments (all optional): device, comm (torch.distributed group; default WORLD when
 initialised), her_rng ('philox' default | 'numpy' = replay the reference's np.random draws),
+action_noise ('host' default | 'device': exploration noise of get_actions from counter-based draws on the device),
 seed (Xavier init seed; the reference uses TF's graph seed).
 """
 import ctypes as C
@@ -79,6 +80,11 @@ class DDPG(object):
         # takes workers x batch_size rows
         self.workers_mode = kwargs.get('workers_mode', 'auto')
         assert self.workers_mode in ('auto', 'wide', 'micro')
+        # exploration noise of get_actions (ddpg.py:147-152): 'host' = the caller's np.random stream in reference order,
+        # 'device' = counter-based draws applied on the device before the one D2H copy
+        self.action_noise = kwargs.get('action_noise', 'host')
+        assert self.action_noise in ('host', 'device')
+        self._action_calls = 0
         self.create_actor_critic = import_function(self.network_class)
 
         self.dimo = self.input_dims['o']
@@ -231,7 +237,8 @@ class DDPG(object):
 
     def get_actions(self, o, ag, g, task_descr=None, noise_eps=0., random_eps=0., use_target_net=False,
                     compute_Q=False):
-        """ddpg.py:129-161.  One H2D blob, prep + MLP kernels, one D2H; exploration noise on the host RNG."""
+        """ddpg.py:129-161.  One H2D blob, prep + MLP kernels, one D2H; exploration noise on the host RNG (default)
+        or on the device (`action_noise='device'`)."""
         o = np.asarray(o, np.float32).reshape(-1, self.dimo)
         g = np.asarray(g, np.float32).reshape(-1, self.dimg)
         n = o.shape[0]
@@ -266,16 +273,25 @@ class DDPG(object):
             _lib.stream_ptr(), C.byref(self.net.desc), theta.data_ptr(), C.byref(self._stats), p_o, p_ag, p_g, p_td, n,
             float(self.clip_obs), self._workspace(n).data_ptr(), out.data_ptr(),
             out.data_ptr() + 4 * n * self.dimu if compute_Q else None), 'cur_ddpg_actions')
+        device_noise = self.action_noise == 'device'
+        if device_noise:
+            # Q above was evaluated on the noise-free action, like the reference's Q_pi_tf (ddpg.py:138-146)
+            if noise_eps != 0. or random_eps != 0.:
+                _lib.check(_lib.load().cur_action_noise(_lib.stream_ptr(), out.data_ptr(), n, self.dimu, float(self.max_u),
+                                                        float(noise_eps), float(random_eps), int(self.seed) & (2 ** 64 - 1),
+                                                        self._action_calls), 'cur_action_noise')
+            self._action_calls += 1
         res = out.cpu().numpy()
         ret = [res[:n * self.dimu].reshape(n, self.dimu).copy()]
         if compute_Q:
             ret.append(res[n * self.dimu:].reshape(n, 1).copy())
         # action postprocessing (ddpg.py:147-155), host RNG in reference order
         u = ret[0]
-        noise = noise_eps * self.max_u * np.random.randn(*u.shape)
-        u += noise
-        u = np.clip(u, -self.max_u, self.max_u)
-        u += np.random.binomial(1, random_eps, u.shape[0]).reshape(-1, 1) * (self._random_action(u.shape[0]) - u)
+        if not device_noise:
+            noise = noise_eps * self.max_u * np.random.randn(*u.shape)
+            u += noise
+            u = np.clip(u, -self.max_u, self.max_u)
+            u += np.random.binomial(1, random_eps, u.shape[0]).reshape(-1, 1) * (self._random_action(u.shape[0]) - u)
         if u.shape[0] == 1:
             u = u[0]
         u = u.copy()

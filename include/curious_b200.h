@@ -248,6 +248,14 @@ int cur_ddpg_actions(void* stream, const cur_net_desc* d, const float* theta,
                      const float* g, const float* td, int64_t n, float clip_obs, float* workspace,
                      float* out_pi, float* out_q /* or NULL */);
 
+/* Device-side option for the exploration noise of get_actions (ddpg.py:147-152), in place on
+ * u [n, dimu] (the out_pi of cur_ddpg_actions): Gaussian noise noise_eps * max_u * N(0,1), clip to +-max_u, then with
+ * probability random_eps per row the action is replaced by a uniform one in [-max_u, max_u].  Draws are Philox4x32-10
+ * blocks keyed by `seed`, counter (row, component pair, call) - the caller passes a fresh `call` per get_actions.
+ * The default path keeps the noise on the host (the caller's np.random stream, like the reference). */
+int cur_action_noise(void* stream, float* u, int64_t n, int dimu, float max_u, double noise_eps,
+                     double random_eps, uint64_t seed, uint64_t call);
+
 typedef struct cur_batch {
   const float *o, *g, *u, *td, *o_2, *g_2, *r; /* staged batch (ddpg.py:75-83); td NULL if flat */
   int64_t n;

@@ -59,3 +59,37 @@ def draws(concat_rows, E_per_row, T, seed, call_offset, mode=None, n_tasks=0, cd
         else:
             out['choice'] = np.minimum(np.searchsorted(np.asarray(cdf), u01(y0), side='right'), n_tasks - 1)
     return out
+
+
+ACTION_NOISE_TAG = 0x40000000
+
+
+def action_noise(u, max_u, noise_eps, random_eps, seed, call):
+    """NumPy restatement of cur_action_noise (csrc/norm_adam.cu): the reference's exploration noise, ddpg.py:147-152,
+    with the counter-based draws documented in include/curious_b200.h instead of the host MT19937 stream.
+
+        x = philox(counter = (row, pair, call_lo, call_hi ^ TAG), key = seed)
+        z(2p), z(2p+1) = Box-Muller((x0 + .5) / 2^32, (x1 + .5) / 2^32);  random action components from x2, x3
+        eps-greedy draw of the row: philox(counter = (row, 0xFFFFFFFF, ...)).x0
+
+    float64 arithmetic on a float32 action array updated in place, like the reference."""
+    u = np.array(u, np.float32, copy=True).reshape(len(u), -1)
+    n, dimu = u.shape
+    pairs = (dimu + 1) // 2
+    rows = np.repeat(np.arange(n, dtype=np.uint64), pairs)
+    pidx = np.tile(np.arange(pairs, dtype=np.uint64), n)
+    c2, c3 = int(call) & 0xFFFFFFFF, ((int(call) >> 32) & 0xFFFFFFFF) ^ ACTION_NOISE_TAG
+    k0, k1 = int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF
+    m = rows.shape[0]
+    x0, x1, x2, x3 = philox4x32_10(rows, pidx, np.full(m, c2), np.full(m, c3), k0, k1)
+    b0, _, _, _ = philox4x32_10(np.arange(n, dtype=np.uint64), np.full(n, 0xFFFFFFFF), np.full(n, c2), np.full(n, c3),
+                                k0, k1)
+    rad = np.sqrt(-2.0 * np.log(u01(x0)))
+    ang = 6.283185307179586 * u01(x1)
+    z = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1).reshape(n, 2 * pairs)[:, :dimu]
+    ra = (-max_u + (max_u - (-max_u)) * np.stack([u01(x2), u01(x3)], axis=1)).reshape(n, 2 * pairs)[:, :dimu]
+    u += noise_eps * max_u * z                                           # ddpg.py:148-149
+    u = np.clip(u, -max_u, max_u)                                        # ddpg.py:150
+    explore = (u01(b0) < random_eps).astype(np.int64).reshape(-1, 1)
+    u += explore * (ra - u)                                              # ddpg.py:151
+    return u, explore.reshape(-1).astype(bool)

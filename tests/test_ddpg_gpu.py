@@ -175,6 +175,41 @@ def test_get_actions_against_oracle():
                            rtol=1e-5, atol=1e-5)
 
 
+def test_device_side_exploration_noise_against_oracle():
+    """action_noise='device' (SURVEY 8f row 1): ddpg.py:147-152 applied on the device from Philox draws, checked against the
+    NumPy restatement on the same counters; the host np.random stream is left alone and every call draws afresh."""
+    from oracle.philox_oracle import action_noise
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, hidden=64)
+    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids, seed=5, action_noise='device')
+    rng = np.random.RandomState(1)
+    call = 0
+    for n in (1, 3, 38, 5000):
+        o = rng.standard_normal((n, dims['o'])).astype(np.float32)
+        g = rng.uniform(-1, 1, (n, dims['g'])).astype(np.float32)
+        ag = rng.uniform(-1, 1, (n, dims['ag'])).astype(np.float32)
+        td = np.eye(4, dtype=np.float32)[rng.randint(0, 4, n)]
+        np.random.seed(3)
+        before = np.random.get_state()[1].copy()
+        clean, q_clean = gpu.get_actions(o, ag, g, task_descr=td, compute_Q=True)             # call `call`: no noise asked
+        noisy, q = gpu.get_actions(o, ag, g, task_descr=td, noise_eps=0.2, random_eps=0.3, compute_Q=True)
+        assert np.array_equal(np.random.get_state()[1], before), 'device noise must not touch the host stream'
+        assert np.array_equal(q, q_clean)                                                     # Q of the noise-free action
+        want, explored = action_noise(np.asarray(clean, np.float32).reshape(n, -1), 1.0, 0.2, 0.3, 5, call + 1)
+        noisy = np.asarray(noisy).reshape(n, -1)
+        assert np.allclose(noisy, want, rtol=0, atol=1e-6), np.abs(noisy - want).max()
+        assert np.abs(noisy).max() <= 1.0
+        again = np.asarray(gpu.get_actions(o, ag, g, task_descr=td, noise_eps=0.2, random_eps=0.3)).reshape(n, -1)
+        assert not np.array_equal(again, noisy)                                               # a fresh counter per call
+        call += 3
+        if n == 5000:
+            assert abs(explored.mean() - 0.3) < 0.03
+            kept = ~explored
+            resid = (noisy - np.asarray(clean).reshape(n, -1))[kept]
+            inside = np.abs(np.asarray(clean).reshape(n, -1)[kept]) < 0.3                       # clipping cannot bite there
+            assert abs(resid[inside].std() - 0.2) < 0.01 and abs(resid[inside].mean()) < 0.01
+            assert np.abs(noisy[explored]).mean() > 0.4                                       # uniform in [-1, 1]: mean |u| = 0.5
+
+
 def test_normalizer_and_adam_primitives():
     import torch
     from curious_b200.mpi_adam import MpiAdam

@@ -208,3 +208,22 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     with pytest.raises((OSError, RuntimeError)):
         _lib.load()
+
+
+def test_action_noise_oracle_statistics():
+    """The NumPy restatement of the device-side exploration noise (oracle/philox_oracle.action_noise, ddpg.py:147-152):
+    standard-normal Box-Muller pairs, eps-greedy rate, clipping, determinism in (seed, call)."""
+    from oracle.philox_oracle import action_noise
+    u = np.zeros((40000, 4), np.float32)
+    a, explored = action_noise(u, 1.0, 0.2, 0.0, seed=7, call=3)
+    assert a.dtype == np.float32 and not explored.any()
+    assert abs(a.std() - 0.2) < 2e-3 and abs(a.mean()) < 2e-3
+    assert abs(np.corrcoef(a[:, 0], a[:, 1])[0, 1]) < 0.02 and abs(np.corrcoef(a[:-1, 0], a[1:, 0])[0, 1]) < 0.02
+    b, explored = action_noise(u, 1.0, 0.2, 0.3, seed=7, call=3)
+    assert abs(explored.mean() - 0.3) < 0.01
+    assert np.array_equal(b[~explored], a[~explored]) and np.abs(b).max() <= 1.0
+    assert abs(np.abs(b[explored]).mean() - 0.5) < 0.01
+    c, _ = action_noise(u, 1.0, 0.2, 0.3, seed=7, call=4)
+    assert not np.array_equal(b, c)
+    d, _ = action_noise(u[:, :3], 1.0, 5.0, 0.0, seed=7, call=3)          # odd dimu; heavy noise is clipped
+    assert d.shape == (40000, 3) and np.abs(d).max() == 1.0
