@@ -216,3 +216,40 @@ def test_full_size_properties():
     L = buf.layout
     fut = host[torch.from_numpy(ep[sel]).long().cuda(), torch.from_numpy(ft[sel]).long().cuda()][:, L.off_ag:L.off_ag + dims['ag']]
     assert torch.equal(a['g'][torch.from_numpy(sel).cuda()][:, g_ids[2]], fut[:, ag_ids[2]])
+
+
+def test_error_behaviour_follows_the_reference():
+    """The reference signals misuse with Python asserts / KeyErrors (SURVEY 8b "Errors"); the drop-in raises the same
+    exception types at the same call sites, and both sides agree case by case."""
+    from curious_b200.replay_buffer import ReplayBuffer
+    from oracle import replay_oracle
+    T = 50
+    dims, ag_ids, g_ids, eps = _arm_setup(4, 7, T, seed=4)
+    shapes = {k: v.shape[1:] for k, v in eps.items()}
+    meta = dict(tasks_ag_id=ag_ids, tasks_g_id=g_ids, threshold=0.05, flat=False, goal_replay='her', her_replay_k=4,
+                task_replay='replay_task_cp_buffer')
+    for make in (lambda: ReplayBuffer(shapes, 5 * T, T, _mk_sampler(meta, rng='philox')),
+                 lambda: replay_oracle.ReplayBufferOracle(shapes, 5 * T, T, None)):
+        buf = make()
+        with pytest.raises(AssertionError):                       # replay_buffer.py:43: sampling an empty buffer
+            buf.sample(8)
+        with pytest.raises(AssertionError):                       # replay_buffer.py:62: ragged episode batch
+            buf.store_episode({k: (v[:2] if k != 'u' else v[:1]) for k, v in eps.items()})
+        with pytest.raises(AssertionError):                       # replay_buffer.py:92: more episodes than slots
+            buf.store_episode({k: v[:6] for k, v in eps.items()})
+        with pytest.raises(KeyError):                             # replay_buffer.py:70: a key of buffer_shapes is missing
+            buf.store_episode({k: v[:1] for k, v in eps.items() if k != 'g'})
+        assert buf.get_current_size() == 0 or buf.get_current_size() == T   # (the reference reserves the slot first)
+        buf.clear_buffer()
+        assert buf.get_current_size() == 0 and not buf.full
+    # sampler: a segment table that does not add up to the batch (ddpg.py:323) and an empty segment (replay_buffer.py:43)
+    gbuf = ReplayBuffer(shapes, 5 * T, T, _mk_sampler(meta, rng='philox'))
+    gbuf.store_episode({k: v[:2] for k, v in eps.items()})
+    s = gbuf.sample_transitions
+    with pytest.raises(AssertionError):
+        s.sample_device([(gbuf.device_view(), 5, 0)], 8)
+    empty = ReplayBuffer(shapes, 5 * T, T, s)
+    with pytest.raises(AssertionError):
+        s.sample_device([(empty.device_view(), 8, 0)], 8)
+    out = gbuf.sample(8, task_to_replay=1)                        # and the well-formed call still works afterwards
+    assert out['r'].shape == (8, 1) and set(shapes) <= set(out)
