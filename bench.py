@@ -47,23 +47,56 @@ def algorithmic_bytes_per_transition(dims, n_modules, g_len=3):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons while the timed region runs (B200_PROFILING.md's clocks line).  Sampled through NVML
+    in-process every 4 ms (the HER region lasts ~10 ms; one `nvidia-smi` call takes longer than that), falling back to
+    an `nvidia-smi --query-gpu` loop when pynvml is unavailable."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    REASON_BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20),
+                   ('sw_power_cap', 0x4))
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.source = 'nvidia-smi'
+        self._nvml = self._handle = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            handle = None
+            try:                                     # CUDA_VISIBLE_DEVICES may renumber: go by UUID when torch exposes it
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            self._nvml, self._handle, self.source = pynvml, handle, 'nvml'
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        return [str(sm), str(mx)] + ['Active' if mask & bit else 'Not Active' for _, bit in self.REASON_BITS]
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.check_output(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                               '--format=csv,noheader,nounits'], timeout=5).decode().strip()
-                self.samples.append([x.strip() for x in out.split(',')])
+                if self._nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.check_output(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                                   '--format=csv,noheader,nounits'], timeout=5).decode().strip()
+                    self.samples.append([x.strip() for x in out.split(',')])
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.004 if self._nvml is not None else 0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -79,7 +112,7 @@ class ClockSampler(threading.Thread):
                 if val.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'source': self.source}
 
 
 def her_traffic_per_launch(rows_per_step):

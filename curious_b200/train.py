@@ -69,7 +69,7 @@ def configure_buffer(dims, T, sampler, buffer_size, structure, task_replay, nb_t
 
 def make_experiment(nb_tasks=4, n_controllable=None, structure='curious', task_selection='active_competence_progress',
                     goal_replay='her', task_replay='replay_task_cp_buffer', seed=0, device=None, normalize_obs=False,
-                    make_env=None, **overrides):
+                    make_env=None, policy_kwargs=None, **overrides):
     """config.prepare_params + configure_* + the RolloutWorker pair of train.py:268-337.  Returns the keyword
     arguments of train()."""
     params = dict(FLAT_PARAMS if structure == 'flat' else MULTI_TASK_PARAMS)
@@ -99,6 +99,7 @@ def make_experiment(nb_tasks=4, n_controllable=None, structure='curious', task_s
                    normalize_obs=normalize_obs, sample_transitions=sampler, gamma=gamma, tasks_ag_id=ag_ids, tasks_g_id=g_ids,
                    task_replay=task_replay, eps_task=params.get('eps_task'), structure=structure, her_rng='philox',
                    seed=seed, device=device)
+    ddpg_kw.update(policy_kwargs or {})             # this implementation's extras: action_noise, update_schedule, comm, ...
     buffers = configure_buffer({k: v for k, v in dims.items() if structure != 'flat' or k != 'task_descr'}, T, sampler,
                                params['buffer_size'], structure, task_replay, nb_tasks, device=device)
     rollout_kw = dict(dims=dims, logger=None, T=T, rollout_batch_size=params['rollout_batch_size'], structure=structure,

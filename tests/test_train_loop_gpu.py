@@ -36,7 +36,8 @@ def test_other_structures_run_the_same_loop(structure, task_replay, tmp_path):
     from curious_b200.train import make_experiment, train
     np.random.seed(1)
     exp = make_experiment(nb_tasks=3, structure=structure, task_selection='active_competence_progress',
-                          task_replay=task_replay, buffer_size=50000, n_cycles=4, n_batches=10, n_test_rollouts=2, seed=1)
+                          task_replay=task_replay, buffer_size=50000, n_cycles=4, n_batches=10, n_test_rollouts=2, seed=1,
+                          policy_kwargs=dict(action_noise='device') if structure == 'flat' else None)
     hist = train(n_epochs=3, logdir=str(tmp_path), policy_save_interval=2, checkpoint_interval=2, **exp)
     _check_run_records(str(tmp_path), structure, exp)
     assert len(hist) == 3 and all(0.0 <= h['test_success_rate'] <= 1.0 for h in hist)
