@@ -267,7 +267,7 @@ class DDPG(object):
             p_ag = ptrs[idx]
             idx += 1
         p_td = ptrs[idx] if self.modular else None
-        out = torch.empty(n * (self.dimu + 1), dtype=torch.float32, device=self.device)
+        out = torch.empty(n * (self.dimu + (1 if compute_Q else 0)), dtype=torch.float32, device=self.device)
         theta = self.theta_target if use_target_net else self.theta_main
         _lib.check(_lib.load().cur_ddpg_actions(
             _lib.stream_ptr(), C.byref(self.net.desc), theta.data_ptr(), C.byref(self._stats), p_o, p_ag, p_g, p_td, n,

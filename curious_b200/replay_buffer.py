@@ -248,14 +248,17 @@ class ReplayBuffer:
     def buffers(self):
         """Host copy in the reference's layout {key: float64 [size, T(+1), dim]} (debug / export only)."""
         L, T = self.layout, self.T
-        rows = self.storage.view(self.size, T + 1, L.row_stride).cpu().numpy().astype(np.float64)
+        n = self.current_size              # only the filled slots are copied; the rest reads as zeros (np.empty in the reference)
+        rows = np.zeros((self.size, T + 1, L.row_stride), np.float64)
+        rows[:n] = self.storage[:n * (T + 1) * L.row_stride].view(n, T + 1, L.row_stride).cpu().numpy()
         out = {'o': rows[:, :, L.off_o:L.off_o + L.dimo], 'ag': rows[:, :, L.off_ag:L.off_ag + L.dimag],
                # g/u/task_descr of step t are stored in hot row t+1 (shifted layout)
                'g': rows[:, 1:, L.off_g:L.off_g + L.dimg], 'u': rows[:, 1:, L.off_u:L.off_u + L.dimu]}
         if self.has_td:
             out['task_descr'] = rows[:, 1:, L.off_td:L.off_td + L.dimtd]
         if self.cold is not None:
-            cold = self.cold.view(self.size, T, L.cold_stride).cpu().numpy().astype(np.float64)
+            cold = np.zeros((self.size, T, L.cold_stride), np.float64)
+            cold[:n] = self.cold[:n * T * L.cold_stride].view(n, T, L.cold_stride).cpu().numpy()
             if self.has_change:
                 out['change'] = cold[:, :, L.off_change:L.off_change + L.dimchange]
             k0 = L.off_info
