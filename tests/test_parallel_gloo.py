@@ -201,3 +201,54 @@ def test_mpi_average_pools_over_ranks(tmp_path):
     r0, r1 = _run('_body_mpi_average', tmp_path)
     assert np.array_equal(r0, r1)
     assert np.allclose(r0, [16.0 / 4, 0.375, 0.0])
+
+
+class _StubPolicy(object):
+    """Stands in for DDPG.get_actions on CPU: the rollout plumbing is what is under test."""
+
+    def __init__(self, dimu):
+        self.dimu = dimu
+
+    def get_actions(self, o, ag, g, task_descr=None, compute_Q=False, **kw):
+        u = np.random.uniform(-1, 1, (len(o), self.dimu))
+        return (u, np.zeros((len(o), 1))) if compute_Q else u
+
+
+def _body_rollouts(rank, world):
+    """RolloutWorker on two ranks (rollout.py:118-140,316-404): rank 0 draws task and goal for every slot of every rank,
+    the competence queues live on rank 0, CP and p come back to everybody."""
+    from curious_b200.envs import ModularPointEnv
+    from curious_b200.rollout import RolloutWorker
+    from curious_b200.train import configure_dims
+    np.random.seed(100 + rank)
+
+    def make_env():
+        return ModularPointEnv(3, max_episode_steps=10)
+    dims = configure_dims(make_env(), 'curious')
+    w = RolloutWorker(make_env, _StubPolicy(dims['u']), dims, None, T=10, rollout_batch_size=2, structure='curious',
+                      task_selection='active_competence_progress', queue_length=20)
+    w.seed(7 + rank)
+    for _ in range(8):
+        ep, cp, n = w.generate_rollouts()
+    assert ep['o'].shape == (2, 11, dims['o']) and ep['task_descr'].shape == (2, 10, 3)
+    mine = [int(e.unwrapped.task) for e in w.envs]
+    goals = [float(np.abs(e.unwrapped.goal).sum()) for e in w.envs]
+    drawn = [(-1 if t is None else int(t)) for t in w.tasks]            # filled on rank 0 only
+    drawn_goals = [(-1.0 if g is None else float(np.abs(g).sum())) for g in w.goals]
+    return [n] + list(np.asarray(w.p, np.float64)) + list(np.asarray(cp, np.float64)) + mine + goals + drawn + drawn_goals
+
+
+def test_rollout_worker_assignments_come_from_rank0(tmp_path):
+    r0, r1 = _run('_body_rollouts', tmp_path)
+    B, N, world = 2, 3, 2
+    assert r0[0] == r1[0] == 8 * B * world                              # n_episodes counts every rank's rollouts
+    assert np.array_equal(r0[1:1 + 2 * N], r1[1:1 + 2 * N])             # p and CP identical everywhere
+    assert abs(r0[1:1 + N].sum() - 1.0) < 1e-12
+    k = 1 + 2 * N
+    mine0, mine1 = r0[k:k + B], r1[k:k + B]
+    goals0, goals1 = r0[k + B:k + 2 * B], r1[k + B:k + 2 * B]
+    drawn = r0[k + 2 * B:k + 2 * B + B * world]
+    drawn_goals = r0[k + 2 * B + B * world:]
+    assert np.array_equal(drawn[:B], mine0) and np.array_equal(drawn[B:], mine1)          # slot = cpu * B + i
+    assert np.allclose(drawn_goals[:B], goals0) and np.allclose(drawn_goals[B:], goals1)
+    assert np.all(r1[k + 2 * B:k + 2 * B + B * world] == -1)           # the other rank never draws

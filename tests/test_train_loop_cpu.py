@@ -1,0 +1,106 @@
+"""The driver loop (curious_b200/train.py, reference experiment/train.py:48-206) with a stub policy: control flow, expert
+selection arithmetic and run records need no GPU.  (The real agent runs the same loop in tests/test_train_loop_gpu.py.)"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from curious_b200.envs import ModularPointEnv
+from curious_b200.rollout import RolloutWorker
+from curious_b200.train import configure_dims, train
+
+
+class StubPolicy(object):
+    def __init__(self, dimu, name='p'):
+        self.dimu, self.name = dimu, name
+        self.stored, self.trained, self.target_updates = [], 0, 0
+
+    def get_actions(self, o, ag, g, task_descr=None, compute_Q=False, **kw):
+        u = np.random.uniform(-1, 1, (len(o), self.dimu))
+        return (u, np.full((len(o), 1), -3.0)) if compute_Q else u
+
+    def store_episode(self, episode, cp, n_ep):
+        self.stored.append((episode['o'].shape, np.array(cp, np.float64).copy(), n_ep))
+
+    def train(self):
+        self.trained += 1
+
+    def update_target_net(self):
+        self.target_updates += 1
+
+    def logs(self, prefix=''):
+        return [('stats_o/mean', 0.25), ('stats_g/std', 1.0)]
+
+    def save_checkpoint(self, path):
+        with open(path, 'w') as f:
+            f.write(self.name)
+
+
+def _workers(structure, nb_tasks=3, T=8):
+    def make_env():
+        return ModularPointEnv(nb_tasks, max_episode_steps=T)
+    dims = configure_dims(make_env(), structure)
+    kw = dict(dims=dims, logger=None, T=T, rollout_batch_size=2, structure=structure,
+              task_selection='active_competence_progress', queue_length=10)
+    if structure == 'task_experts':
+        policy = [StubPolicy(dims['u'], 'p%d' % i) for i in range(nb_tasks)]
+        rollout = [RolloutWorker(make_env, policy[i], unique_task=i, **kw) for i in range(nb_tasks)]
+    else:
+        policy = StubPolicy(dims['u'])
+        rollout = RolloutWorker(make_env, policy, **kw)
+    evaluator = RolloutWorker(make_env, policy, exploit=True, compute_Q=True, eval=True, **kw)
+    return policy, rollout, evaluator, dims
+
+
+@pytest.mark.parametrize('structure', ['curious', 'flat'])
+def test_loop_counts_and_records(structure, tmp_path):
+    np.random.seed(0)
+    policy, rollout, evaluator, dims = _workers(structure)
+    hist = train(policy, rollout, evaluator, n_epochs=3, n_test_rollouts=2, n_cycles=4, n_batches=5, structure=structure,
+                 logdir=str(tmp_path), params={'structure': structure, 'n_cycles': 4}, policy_save_interval=2,
+                 checkpoint_interval=1)
+    assert len(hist) == 3
+    # train.py:148-155: per cycle one store_episode, n_batches updates, one target update
+    assert len(policy.stored) == 12 and policy.trained == 60 and policy.target_updates == 12
+    assert policy.stored[0][0] == (2, 9, dims['o']) and policy.stored[-1][2] == 12 * 2
+    lines = open(str(tmp_path / 'progress.csv')).read().splitlines()
+    header = lines[0].split(',')
+    assert len(lines) == 4 and header[0] == 'epoch' and header[-1] == 'Time'
+    for col in ('test/success_rate', 'test/mean_Q', 'train/success_rate', 'train/episode', 'stats_o/mean'):
+        assert col in header, col
+    row = dict(zip(header, lines[-1].split(',')))
+    assert row['epoch'] == '2' and row['test/mean_Q'] == '-3' and row['train/episode'] == '24' and row['stats_o/mean'] == '0.25'
+    if structure == 'curious':
+        for col in ('train/C_task0', 'train/CP_task2', 'train/%_task1', 'train/p_task0', 'test/C_task2'):
+            assert col in header, col
+        assert all('CP' in h and 'p' in h for h in hist)
+    else:
+        assert not any('task' in h for h in header)
+    assert json.load(open(str(tmp_path / 'params.json'))) == {'structure': structure, 'n_cycles': 4}
+    files = set(os.listdir(str(tmp_path)))
+    assert {'policy_best.pkl', 'policy_latest.pkl', 'policy_0.pkl', 'policy_2.pkl', 'checkpoint_0.pt', 'log.txt'} <= files
+    assert 'policy_1.pkl' not in files
+
+
+def test_task_experts_selection_follows_competence_progress(tmp_path):
+    """train.py:79-101: the expert trained in an epoch is drawn with p = eps / N + (1 - eps) CP / sum(CP) over the experts' own
+    competence progress (uniform while nobody progressed)."""
+    np.random.seed(1)
+    policy, rollout, evaluator, dims = _workers('task_experts')
+    hist = train(policy, rollout, evaluator, n_epochs=4, n_test_rollouts=1, n_cycles=2, n_batches=3,
+                 structure='task_experts', logdir=str(tmp_path), checkpoint_interval=1)
+    assert len(hist) == 4
+    for h in hist:
+        assert np.allclose(h['p'], 1.0 / 3)                          # random stub actions: no learning progress yet
+    chosen = [h['i_policy'] for h in hist]
+    for i, pol in enumerate(policy):
+        assert pol.trained == 6 * chosen.count(i) and pol.target_updates == 2 * chosen.count(i)
+    header = open(str(tmp_path / 'progress.csv')).read().splitlines()[0].split(',')
+    assert 'IND_TASK_rollout' in header
+    assert {'checkpoint_0.pt', 'checkpoint_1.pt', 'checkpoint_2.pt'} <= set(os.listdir(str(tmp_path)))
+    # a progressing expert pulls the draw towards itself
+    rollout[1].tracker.competence_computers[1].CP = 0.5
+    np.random.seed(2)
+    hist = train(policy, rollout, evaluator, n_epochs=1, n_test_rollouts=1, n_cycles=1, n_batches=1, structure='task_experts')
+    assert np.allclose(hist[0]['p'], [0.4 / 3, 0.4 / 3 + 0.6, 0.4 / 3])
