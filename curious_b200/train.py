@@ -171,6 +171,12 @@ class _EpochRecords(object):
         log.dump_tabular()
         rollout_worker.save_goal_task_history(log.get_dir())
         success = mpi_average(self.evaluator.current_success_rate(), comm)
+        if self.checkpoint_interval > 0 and epoch % self.checkpoint_interval == 0 and log.get_dir() is not None:
+            # every rank owns its replay buffers and RNG streams: one resumable file per rank
+            os.makedirs(log.get_dir(), exist_ok=True)
+            suffix = '' if self.rank == 0 else '_rank%d' % self.rank
+            for i, pol in enumerate(policy if isinstance(policy, list) else [policy]):
+                pol.save_checkpoint(self._path('checkpoint_%d%s.pt' % (i, suffix)))
         if not log.active:
             return
         if self.save_policies and success >= self.best:
@@ -180,9 +186,6 @@ class _EpochRecords(object):
         if self.save_policies and self.interval > 0 and epoch % self.interval == 0:
             self.evaluator.save_policy(self._path('policy_%d.pkl' % epoch))
             self.evaluator.save_policy(self._path('policy_latest.pkl'))
-        if self.checkpoint_interval > 0 and epoch % self.checkpoint_interval == 0:
-            for i, pol in enumerate(policy if isinstance(policy, list) else [policy]):
-                pol.save_checkpoint(self._path('checkpoint_%d.pt' % i))
 
 
 def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles, n_batches, structure='curious',

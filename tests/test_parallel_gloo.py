@@ -252,3 +252,59 @@ def test_rollout_worker_assignments_come_from_rank0(tmp_path):
     assert np.array_equal(drawn[:B], mine0) and np.array_equal(drawn[B:], mine1)          # slot = cpu * B + i
     assert np.allclose(drawn_goals[:B], goals0) and np.allclose(drawn_goals[B:], goals1)
     assert np.all(r1[k + 2 * B:k + 2 * B + B * world] == -1)           # the other rank never draws
+
+
+def _body_epoch_records(rank, world):
+    """train.py's per-epoch records on two ranks: tabular values are averaged over ranks (mpi_average), only rank 0 writes
+    progress.csv / policies (train.py:171-206), every rank writes its own resumable checkpoint."""
+    import tempfile
+    from curious_b200.train import _EpochRecords
+
+    class Worker(object):
+        comm = None
+
+        def __init__(self, rank):
+            self.rank = rank
+
+        def logs(self, prefix):
+            return [(prefix + '/success_rate', 0.25 + 0.5 * self.rank), (prefix + '/episode', 40)]
+
+        def additional_logs(self, prefix):
+            return [(prefix + '/C_task0', '0.5')]
+
+        def current_success_rate(self):
+            return 0.25 + 0.5 * self.rank
+
+        def save_policy(self, path):
+            open(path, 'w').write('policy')
+
+        def save_goal_task_history(self, path):
+            pass
+
+    class Policy(object):
+        def logs(self):
+            return [('stats_o/mean', 1.0 + rank)]
+
+        def save_checkpoint(self, path):
+            open(path, 'w').write('rank %d' % rank)
+
+    box = [tempfile.mkdtemp() if rank == 0 else None]
+    torch.distributed.broadcast_object_list(box, src=0)
+    rec = _EpochRecords(box[0], Worker(rank), {'a': 1}, 1, True, 1, False)
+    rec.epoch(0, Worker(rank), Policy())
+    rec.log.close()
+    torch.distributed.barrier()
+    files = sorted(os.listdir(box[0]))
+    want = ['checkpoint_0.pt', 'checkpoint_0_rank1.pt', 'log.txt', 'params.json', 'policy_0.pkl', 'policy_best.pkl',
+            'policy_latest.pkl', 'progress.csv']
+    assert files == want, files
+    assert open(os.path.join(box[0], 'checkpoint_0_rank1.pt')).read() == 'rank 1'
+    lines = open(os.path.join(box[0], 'progress.csv')).read().splitlines()
+    row = dict(zip(lines[0].split(','), lines[1].split(',')))
+    return [float(row['test/success_rate']), float(row['stats_o/mean']), float(row['train/episode']), rec.best]
+
+
+def test_epoch_records_on_two_ranks(tmp_path):
+    r0, r1 = _run('_body_epoch_records', tmp_path)
+    assert np.array_equal(r0[:3], [0.5, 1.5, 40.0]) and np.array_equal(r0[:3], r1[:3])
+    assert r0[3] == 0.5 and r1[3] == -1                                    # only rank 0 tracks / saves the best policy
