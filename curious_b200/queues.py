@@ -90,6 +90,18 @@ class CompetenceTracker(object):
         for cq in self.competence_computers:
             cq.clear_queue()
 
+    # resume support (beyond the reference, which restarts its queues from scratch)
+    def state(self):
+        return dict(queues=[(list(cq.successes), cq.CP, cq.C) for cq in self.competence_computers],
+                    CP=np.array(self.CP, np.float64), C=np.array(self.C, np.float64), p=np.array(self.p, np.float64))
+
+    def load_state(self, st):
+        assert len(st['queues']) == self.nb_tasks
+        for cq, (succ, cp, c) in zip(self.competence_computers, st['queues']):
+            cq.successes = deque(succ, maxlen=2 * cq.window)
+            cq.CP, cq.C = cp, c
+        self.CP, self.C, self.p = st['CP'].copy(), st['C'].copy(), st['p'].copy()
+
     def update(self, tasks, successes):
         """tasks / successes: this rank's exploit rollouts ([] when exploration noise was used, rollout.py:318-330).
         Rank 0 gathers, updates the queues and the probabilities; p and CP are broadcast (rollout.py:332-404)."""

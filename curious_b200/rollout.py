@@ -227,6 +227,33 @@ class RolloutWorker(object):
         if hasattr(self.policy, 'save_weights'):
             self.policy.save_weights(path)
 
+    # resume support (beyond the reference): what generate_rollouts carries from one call to the next
+    def state(self):
+        st = dict(n_episodes=self.n_episodes, count=self.count, p=np.array(self.p, np.float64) if self.modular else None,
+                  CP=np.array(self.CP, np.float64), C=np.array(self.C, np.float64), exploit=self.exploit,
+                  histories=[list(h) for h in (self.success_history, self.reward_history, self.Q_history,
+                                               self.task_history, self.goal_history)],
+                  initial_o=self.initial_o.copy(), initial_ag=self.initial_ag.copy(), g=self.g.copy(),
+                  tracker=self.tracker.state() if self.modular else None,
+                  env_rng=[e.unwrapped.rng.get_state() if hasattr(getattr(e.unwrapped, 'rng', None), 'get_state') else None
+                           for e in self.envs])
+        return st
+
+    def load_state(self, st):
+        self.n_episodes, self.count, self.exploit = st['n_episodes'], st['count'], st['exploit']
+        self.CP, self.C = st['CP'].copy(), st['C'].copy()
+        for h, saved in zip((self.success_history, self.reward_history, self.Q_history, self.task_history,
+                             self.goal_history), st['histories']):
+            h.clear()
+            h.extend(saved)
+        self.initial_o[:], self.initial_ag[:], self.g[:] = st['initial_o'], st['initial_ag'], st['g']
+        if self.modular:
+            self.p = st['p'].copy()
+            self.tracker.load_state(st['tracker'])
+        for e, rng in zip(self.envs, st['env_rng']):
+            if rng is not None:
+                e.unwrapped.rng.set_state(rng)
+
     def save_goal_task_history(self, path):
         """No-op, like the reference's (rollout.py:437-449: body commented out); kept for the train loop's call."""
 

@@ -21,11 +21,25 @@ class ProgressCSV(object):
     """progress.csv writer.  Rows are kept in memory (one per epoch) and the file is rewritten when a new key appears,
     which produces the same bytes as the reference's in-place header rewrite + comma padding."""
 
-    def __init__(self, filename):
+    def __init__(self, filename, resume=False, keep=None):
+        """resume: continue an existing file; keep(row) -> bool drops the rows a resumed run is going to write again."""
         self.filename = filename
         self.columns = []
         self.rows = []
+        if resume and os.path.exists(filename):
+            lines = open(filename).read().splitlines()
+            if lines:
+                self.columns = lines[0].split(',')
+                for line in lines[1:]:
+                    row = {c: (v if v != '' else None) for c, v in zip(self.columns, line.split(','))}
+                    if keep is None or keep(row):
+                        self.rows.append(row)
         self.file = open(filename, 'w')
+        if self.columns:
+            self.file.write(','.join(self.columns) + '\n')
+            for row in self.rows:
+                self.file.write(self._line(self.columns, row))
+            self.file.flush()
 
     @staticmethod
     def _line(columns, row):
@@ -53,7 +67,8 @@ class RunLog(object):
     """The slice of baselines.logger the HER driver uses: get_dir / record_tabular / dump_tabular / info
     (logger.py:192-245), plus params.json."""
 
-    def __init__(self, directory, rank=0, echo=False):
+    def __init__(self, directory, rank=0, echo=False, resume_after_epoch=None):
+        """resume_after_epoch: continue the files of an earlier run, keeping its rows up to that epoch."""
         self.dir = directory
         self.active = rank == 0 and directory is not None
         self.echo = echo
@@ -61,8 +76,10 @@ class RunLog(object):
         self.csv = self.txt = None
         if self.active:
             os.makedirs(directory, exist_ok=True)
-            self.csv = ProgressCSV(os.path.join(directory, 'progress.csv'))
-            self.txt = open(os.path.join(directory, 'log.txt'), 'w')
+            resume = resume_after_epoch is not None
+            self.csv = ProgressCSV(os.path.join(directory, 'progress.csv'), resume=resume,
+                                   keep=(lambda row: int(float(row.get('epoch') or 0)) <= resume_after_epoch) if resume else None)
+            self.txt = open(os.path.join(directory, 'log.txt'), 'a' if resume else 'w')
         self.t0 = time.time()
 
     def get_dir(self):

@@ -12,6 +12,7 @@ policy_latest / policy_best / policy_<epoch>.pkl, train.py:53-55,171-206,264-266
 reference, a resumable checkpoint per epoch (`checkpoint_interval`, DDPG.save_checkpoint).
 """
 import os
+import pickle
 import time
 
 import numpy as np
@@ -137,22 +138,50 @@ def _evaluate(evaluator, n_test_rollouts):
 
 
 class _EpochRecords(object):
-    """train.py:171-206 (`logs`): the tabular row of one epoch and the policy files, written by rank 0."""
+    """train.py:171-206 (`logs`): the tabular row of one epoch and the policy files, written by rank 0; plus (beyond the
+    reference) the resumable state of the run, written by every rank for its own buffers, RNG streams and workers."""
 
-    def __init__(self, logdir, evaluator, params, policy_save_interval, save_policies, checkpoint_interval, echo):
+    def __init__(self, logdir, evaluator, params, policy_save_interval, save_policies, checkpoint_interval, echo,
+                 workers=(), resumed=None):
         self.evaluator = evaluator
+        self.workers = list(workers)
         self.rank = evaluator.rank
-        self.log = RunLog(logdir, rank=self.rank, echo=echo)
+        self.suffix = '' if self.rank == 0 else '_rank%d' % self.rank
+        self.log = RunLog(logdir, rank=self.rank, echo=echo,
+                          resume_after_epoch=None if resumed is None else resumed['epoch'])
         self.save_policies, self.interval = save_policies, policy_save_interval
         self.checkpoint_interval = checkpoint_interval
-        self.best = -1
-        self.t0 = time.time()
+        self.best = -1 if resumed is None else resumed['best']
+        self.t0 = time.time() - (0.0 if resumed is None else resumed['elapsed'])
         if params is not None:
             self.log.write_params(params)
-        self.log.info('Training...')
+        self.log.info('Training...' if resumed is None else 'Resuming after epoch %d...' % resumed['epoch'])
 
     def _path(self, name):
         return os.path.join(self.log.get_dir(), name)
+
+    @staticmethod
+    def load_run_state(logdir, rank):
+        path = os.path.join(logdir, 'run_state%s.pkl' % ('' if rank == 0 else '_rank%d' % rank))
+        if not os.path.exists(path):
+            return None
+        with open(path, 'rb') as f:
+            return pickle.load(f)
+
+    def _save_run_state(self, epoch, policy):
+        """One resumable file per policy and one run_state per rank (every rank owns its replay buffers and RNG streams);
+        written to a temporary name first so that a crash mid-write leaves the previous checkpoint intact."""
+        os.makedirs(self.log.get_dir(), exist_ok=True)
+        for i, pol in enumerate(policy if isinstance(policy, list) else [policy]):
+            path = self._path('checkpoint_%d%s.pt' % (i, self.suffix))
+            pol.save_checkpoint(path + '.tmp')
+            os.replace(path + '.tmp', path)
+        state = dict(epoch=epoch, best=self.best, elapsed=time.time() - self.t0,
+                     workers=[w.state() for w in self.workers], evaluator=self.evaluator.state())
+        path = self._path('run_state%s.pkl' % self.suffix)
+        with open(path + '.tmp', 'wb') as f:
+            pickle.dump(state, f)
+        os.replace(path + '.tmp', path)
 
     def epoch(self, epoch, rollout_worker, policy, i_policy=None):
         log, comm = self.log, self.evaluator.comm
@@ -171,37 +200,46 @@ class _EpochRecords(object):
         log.dump_tabular()
         rollout_worker.save_goal_task_history(log.get_dir())
         success = mpi_average(self.evaluator.current_success_rate(), comm)
+        if log.active and self.save_policies:
+            if success >= self.best:
+                self.best = success
+                log.info('New best success rate: {}. Saving policy to {} ...'.format(success, self._path('policy_best.pkl')))
+                self.evaluator.save_policy(self._path('policy_best.pkl'))
+            if self.interval > 0 and epoch % self.interval == 0:
+                self.evaluator.save_policy(self._path('policy_%d.pkl' % epoch))
+                self.evaluator.save_policy(self._path('policy_latest.pkl'))
         if self.checkpoint_interval > 0 and epoch % self.checkpoint_interval == 0 and log.get_dir() is not None:
-            # every rank owns its replay buffers and RNG streams: one resumable file per rank
-            os.makedirs(log.get_dir(), exist_ok=True)
-            suffix = '' if self.rank == 0 else '_rank%d' % self.rank
-            for i, pol in enumerate(policy if isinstance(policy, list) else [policy]):
-                pol.save_checkpoint(self._path('checkpoint_%d%s.pt' % (i, suffix)))
-        if not log.active:
-            return
-        if self.save_policies and success >= self.best:
-            self.best = success
-            log.info('New best success rate: {}. Saving policy to {} ...'.format(success, self._path('policy_best.pkl')))
-            self.evaluator.save_policy(self._path('policy_best.pkl'))
-        if self.save_policies and self.interval > 0 and epoch % self.interval == 0:
-            self.evaluator.save_policy(self._path('policy_%d.pkl' % epoch))
-            self.evaluator.save_policy(self._path('policy_latest.pkl'))
+            self._save_run_state(epoch, policy)
 
 
 def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles, n_batches, structure='curious',
           task_selection='active_competence_progress', eps_task=0.4, log=None, logdir=None, params=None,
-          policy_save_interval=5, save_policies=True, checkpoint_interval=0, echo=False):
+          policy_save_interval=5, save_policies=True, checkpoint_interval=0, echo=False, resume=False):
     """train.py:48-170: per epoch n_cycles x (rollouts -> store_episode -> n_batches x train -> update_target_net),
     then n_test_rollouts evaluation rollouts.  Returns one dict per epoch; with `logdir` also writes the reference's
-    run records (see module docstring)."""
+    run records (see module docstring).  `resume=True` continues the run whose checkpoints (`checkpoint_interval`) are in
+    `logdir` from the epoch after the last one: policies, buffers, optimiser, RNG streams, competence queues and the
+    files pick up where they were (the returned history covers the new epochs)."""
     history = []
     records = None
+    start_epoch = 0
+    workers = rollout_worker if isinstance(rollout_worker, list) else [rollout_worker]
     if logdir is not None:
-        records = _EpochRecords(logdir, evaluator, params, policy_save_interval, save_policies, checkpoint_interval, echo)
+        resumed = _EpochRecords.load_run_state(logdir, evaluator.rank) if resume else None
+        if resumed is not None:
+            suffix = '' if evaluator.rank == 0 else '_rank%d' % evaluator.rank
+            for i, pol in enumerate(policy if isinstance(policy, list) else [policy]):
+                pol.load_checkpoint(os.path.join(logdir, 'checkpoint_%d%s.pt' % (i, suffix)))
+            for w, st in zip(workers, resumed['workers']):
+                w.load_state(st)
+            evaluator.load_state(resumed['evaluator'])
+            start_epoch = resumed['epoch'] + 1
+        records = _EpochRecords(logdir, evaluator, params, policy_save_interval, save_policies, checkpoint_interval, echo,
+                                workers=workers, resumed=resumed)
     if structure == 'task_experts':
         nb_tasks = len(policy)
         p = 1 / nb_tasks * np.ones([nb_tasks])
-        for epoch in range(n_epochs):
+        for epoch in range(start_epoch, n_epochs):
             if task_selection == 'random':
                 i_policy = epoch % nb_tasks                                  # train.py:79-81
             else:
@@ -230,7 +268,7 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
             if records:
                 records.epoch(epoch, rollout_worker[i_policy], policy, i_policy)
         return history
-    for epoch in range(n_epochs):                                            # train.py:125-166
+    for epoch in range(start_epoch, n_epochs):                                            # train.py:125-166
         rollout_worker.clear_history()
         for _ in range(n_cycles):
             episode, cp, n_ep = rollout_worker.generate_rollouts()

@@ -281,6 +281,9 @@ def _body_epoch_records(rank, world):
         def save_goal_task_history(self, path):
             pass
 
+        def state(self):
+            return {'rank': self.rank}
+
     class Policy(object):
         def logs(self):
             return [('stats_o/mean', 1.0 + rank)]
@@ -296,7 +299,7 @@ def _body_epoch_records(rank, world):
     torch.distributed.barrier()
     files = sorted(os.listdir(box[0]))
     want = ['checkpoint_0.pt', 'checkpoint_0_rank1.pt', 'log.txt', 'params.json', 'policy_0.pkl', 'policy_best.pkl',
-            'policy_latest.pkl', 'progress.csv']
+            'policy_latest.pkl', 'progress.csv', 'run_state.pkl', 'run_state_rank1.pkl']
     assert files == want, files
     assert open(os.path.join(box[0], 'checkpoint_0_rank1.pt')).read() == 'rank 1'
     lines = open(os.path.join(box[0], 'progress.csv')).read().splitlines()

@@ -33,8 +33,20 @@ class StubPolicy(object):
         return [('stats_o/mean', 0.25), ('stats_g/std', 1.0)]
 
     def save_checkpoint(self, path):
-        with open(path, 'w') as f:
-            f.write(self.name)
+        """Like DDPG.save_checkpoint: the agent's own state plus the host np.random state."""
+        import pickle
+        with open(path, 'wb') as f:
+            pickle.dump(dict(name=self.name, trained=self.trained, target_updates=self.target_updates,
+                             stored=len(self.stored), numpy_rng=np.random.get_state()), f)
+
+    def load_checkpoint(self, path):
+        import pickle
+        with open(path, 'rb') as f:
+            st = pickle.load(f)
+        assert st['name'] == self.name
+        self.trained, self.target_updates = st['trained'], st['target_updates']
+        self.stored = [None] * st['stored']
+        np.random.set_state(st['numpy_rng'])
 
 
 def _workers(structure, nb_tasks=3, T=8):
@@ -104,3 +116,38 @@ def test_task_experts_selection_follows_competence_progress(tmp_path):
     np.random.seed(2)
     hist = train(policy, rollout, evaluator, n_epochs=1, n_test_rollouts=1, n_cycles=1, n_batches=1, structure='task_experts')
     assert np.allclose(hist[0]['p'], [0.4 / 3, 0.4 / 3 + 0.6, 0.4 / 3])
+
+
+@pytest.mark.parametrize('structure', ['curious', 'task_experts'])
+def test_resumed_run_equals_uninterrupted_run(structure, tmp_path):
+    """train(resume=True): 2 epochs, a fresh process' worth of new objects, then 3 more epochs == 5 epochs in one go -
+    same evaluation results, competence, probabilities, expert choices and progress.csv (except the Time column)."""
+    def run(logdir, n_epochs, seed, resume=False):
+        np.random.seed(seed)
+        policy, rollout, evaluator, _ = _workers(structure)
+        for i, w in enumerate((rollout if isinstance(rollout, list) else [rollout]) + [evaluator]):
+            w.seed(50 + 10 * i)
+        hist = train(policy, rollout, evaluator, n_epochs=n_epochs, n_test_rollouts=2, n_cycles=3, n_batches=2,
+                     structure=structure, logdir=logdir, policy_save_interval=0, checkpoint_interval=1, resume=resume)
+        return hist, policy
+
+    full, pol_full = run(str(tmp_path / 'full'), 5, seed=3)
+    run(str(tmp_path / 'split'), 2, seed=3)
+    tail, pol_tail = run(str(tmp_path / 'split'), 5, seed=99, resume=True)        # another seed: everything comes from the files
+    assert [h['epoch'] for h in tail] == [2, 3, 4]
+    for a, b in zip(full[2:], tail):
+        assert set(a) == set(b)
+        for key in a:
+            assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), key
+    pf, pt = (pol_full, pol_tail) if isinstance(pol_full, list) else ([pol_full], [pol_tail])
+    assert [p.trained for p in pf] == [p.trained for p in pt]
+
+    def table(path):
+        lines = open(path).read().splitlines()
+        t = lines[0].split(',').index('Time')
+        return [[v for i, v in enumerate(line.split(',')) if i != t] for line in lines]
+    assert table(str(tmp_path / 'full' / 'progress.csv')) == table(str(tmp_path / 'split' / 'progress.csv'))
+    assert 'Resuming after epoch 1' in open(str(tmp_path / 'split' / 'log.txt')).read()
+    # resume=True without checkpoints starts from scratch
+    fresh, _ = run(str(tmp_path / 'empty'), 1, seed=3, resume=True)
+    assert [h['epoch'] for h in fresh] == [0]
