@@ -77,3 +77,29 @@ def _check_run_records(logdir, structure, exp):
     td = np.eye(d['task_descr'])[rng.randint(0, d['task_descr'], 5)] if 'task_descr' in d else None
     assert np.array_equal(loaded0.get_actions(o, ag, g, task_descr=td), live0.get_actions(o, ag, g, task_descr=td))
     assert os.path.exists(os.path.join(logdir, 'checkpoint_0.pt'))
+
+
+def test_resumed_training_equals_uninterrupted(tmp_path):
+    """train(resume=True) with the real agent: 2 epochs, then everything rebuilt from scratch (other seeds) and resumed from
+    the files for 2 more == 4 epochs in one go - evaluation results, competence, probabilities and parameters bit for bit."""
+    from curious_b200.train import make_experiment, train
+
+    def run(logdir, n_epochs, seed, resume=False):
+        np.random.seed(seed)
+        exp = make_experiment(nb_tasks=3, structure='curious', task_selection='active_competence_progress',
+                              task_replay='replay_task_cp_buffer', buffer_size=2000, n_cycles=3, n_batches=8,
+                              n_test_rollouts=2, seed=4)
+        hist = train(n_epochs=n_epochs, logdir=logdir, policy_save_interval=0, checkpoint_interval=1, resume=resume, **exp)
+        return hist, exp['policy']
+
+    full, pol_full = run(str(tmp_path / 'full'), 4, seed=3)
+    run(str(tmp_path / 'split'), 2, seed=3)
+    tail, pol_tail = run(str(tmp_path / 'split'), 4, seed=99, resume=True)
+    assert [h['epoch'] for h in tail] == [2, 3]
+    for a, b in zip(full[2:], tail):
+        for key in a:
+            assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), (a['epoch'], key)
+    for which in ('Q', 'pi'):
+        for tgt in (False, True):
+            assert np.array_equal(pol_full.get_flat(which, tgt), pol_tail.get_flat(which, tgt)), (which, tgt)
+    assert [b.current_size for b in pol_full.buffer] == [b.current_size for b in pol_tail.buffer]
