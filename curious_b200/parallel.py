@@ -70,6 +70,39 @@ def rank_seed(seed, r):
     return seed + 1000000 * r
 
 
+def assert_rank_streams_differ(comm=None):
+    """train.py:207-212: once per epoch every rank draws one uniform from its np.random stream and compares with rank 0's -
+    ranks that were seeded alike (identical exploration, identical replay slots) fail here instead of silently
+    training on duplicated data.  Consumes one draw on every rank, like the reference."""
+    import numpy as np
+    local = float(np.random.uniform(size=(1,))[0])
+    group, n = world(comm)
+    if n > 1:
+        import torch.distributed as dist
+        box = [local]
+        dist.broadcast_object_list(box, src=_root(group), group=group)
+        if rank(comm) != 0:
+            assert local != box[0], 'this rank draws the same np.random stream as rank 0 (train.py:211-212)'
+    return local
+
+
+def install_excepthook():
+    """her/util.py:129-139 (`install_mpi_excepthook`): an uncaught exception on one rank must not leave the others
+    waiting in a collective.  The reference calls MPI.COMM_WORLD.Abort(); under torchrun the equivalent is to print the
+    traceback and leave at once with a non-zero status - the launcher then tears the whole group down."""
+    import os
+    import sys
+    previous = sys.excepthook
+
+    def hook(kind, value, tb):
+        previous(kind, value, tb)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
+    sys.excepthook = hook
+    return hook
+
+
 class PeerGradExchange(object):
     """Gradient exchange over NVLink peer memory, fused with Adam (csrc/p2p.cu; replaces the Allreduce + Adam of
     mpi_adam.py:24-35 on the CUDA-graph path).  Every rank allocates a region [flags | grads 0 | grads 1],

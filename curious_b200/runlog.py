@@ -8,7 +8,8 @@
   <dir>/policy_latest.pkl, policy_best.pkl, policy_<epoch>.pkl   pickled policies (train.py:53-55,196-206) - written by
                        RolloutWorker.save_policy, next to DDPG.save_weights' <path>_weights.pkl (ddpg.py:481-497)
 
-Only rank 0 writes (train.py:51-59,182,264); the other ranks' RunLog swallows everything.
+Only rank 0 writes these (train.py:51-59,182,264); the other ranks keep their free-text lines in log-rank<NNN>.txt
+(logger.py:359-367) and swallow the rest.
 """
 import json
 import os
@@ -80,6 +81,11 @@ class RunLog(object):
             self.csv = ProgressCSV(os.path.join(directory, 'progress.csv'), resume=resume,
                                    keep=(lambda row: int(float(row.get('epoch') or 0)) <= resume_after_epoch) if resume else None)
             self.txt = open(os.path.join(directory, 'log.txt'), 'a' if resume else 'w')
+        elif directory is not None:
+            # the other ranks keep their free-text lines in log-rank<NNN>.txt (logger.py:359-367)
+            os.makedirs(directory, exist_ok=True)
+            self.txt = open(os.path.join(directory, 'log-rank%03i.txt' % rank),
+                            'a' if resume_after_epoch is not None else 'w')
         self.t0 = time.time()
 
     def get_dir(self):
@@ -97,11 +103,11 @@ class RunLog(object):
         self.row = {}
 
     def info(self, *args):
-        if self.active:
+        if self.txt is not None:
             line = ' '.join(str(a) for a in args)
             self.txt.write(line + '\n')
             self.txt.flush()
-            if self.echo:
+            if self.echo and self.active:
                 print(line, flush=True)
 
     def write_params(self, params):
@@ -121,8 +127,9 @@ class RunLog(object):
             json.dump(params, f, default=plain)
 
     def close(self):
-        if self.active:
+        if self.csv is not None:
             self.csv.close()
+        if self.txt is not None:
             self.txt.close()
 
 

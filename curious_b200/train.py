@@ -22,6 +22,7 @@ from .ddpg import DDPG
 from .envs import ModularPointEnv
 from .replay_buffer import ReplayBuffer
 from .rollout import RolloutWorker
+from .parallel import assert_rank_streams_differ
 from .runlog import RunLog, mpi_average
 
 MULTI_TASK_PARAMS = {            # config.py:56-90
@@ -200,6 +201,7 @@ class _EpochRecords(object):
         log.dump_tabular()
         rollout_worker.save_goal_task_history(log.get_dir())
         success = mpi_average(self.evaluator.current_success_rate(), comm)
+        assert_rank_streams_differ(comm)                                       # train.py:207-212
         if log.active and self.save_policies:
             if success >= self.best:
                 self.best = success

@@ -298,7 +298,7 @@ def _body_epoch_records(rank, world):
     rec.log.close()
     torch.distributed.barrier()
     files = sorted(os.listdir(box[0]))
-    want = ['checkpoint_0.pt', 'checkpoint_0_rank1.pt', 'log.txt', 'params.json', 'policy_0.pkl', 'policy_best.pkl',
+    want = ['checkpoint_0.pt', 'checkpoint_0_rank1.pt', 'log-rank001.txt', 'log.txt', 'params.json', 'policy_0.pkl', 'policy_best.pkl',
             'policy_latest.pkl', 'progress.csv', 'run_state.pkl', 'run_state_rank1.pkl']
     assert files == want, files
     assert open(os.path.join(box[0], 'checkpoint_0_rank1.pt')).read() == 'rank 1'
@@ -311,3 +311,34 @@ def test_epoch_records_on_two_ranks(tmp_path):
     r0, r1 = _run('_body_epoch_records', tmp_path)
     assert np.array_equal(r0[:3], [0.5, 1.5, 40.0]) and np.array_equal(r0[:3], r1[:3])
     assert r0[3] == 0.5 and r1[3] == -1                                    # only rank 0 tracks / saves the best policy
+
+
+def _body_streams(rank, world):
+    """train.py:207-212: ranks seeded alike are caught, ranks seeded with rank_seed pass."""
+    from curious_b200 import parallel
+    np.random.seed(parallel.rank_seed(5, rank))
+    parallel.assert_rank_streams_differ()
+    np.random.seed(5)                      # the mistake the check exists for
+    try:
+        parallel.assert_rank_streams_differ()
+        caught = 0.0
+    except AssertionError:
+        caught = 1.0
+    return [caught]
+
+
+def test_identically_seeded_ranks_are_detected(tmp_path):
+    r0, r1 = _run('_body_streams', tmp_path)
+    assert r0[0] == 0.0 and r1[0] == 1.0          # rank 0 is the reference point, rank 1 notices
+
+
+def test_excepthook_leaves_with_nonzero_status():
+    """her/util.py:129-139: an uncaught exception ends the rank at once (the reference aborts MPI_COMM_WORLD)."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from curious_b200.parallel import install_excepthook\n"
+            "install_excepthook()\n"
+            "import atexit; atexit.register(lambda: print('atexit ran'))\n"
+            "raise ValueError('boom')\n") % ROOT
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 1 and 'ValueError: boom' in res.stderr and 'atexit ran' not in res.stdout
