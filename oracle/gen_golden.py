@@ -174,8 +174,8 @@ def run_storage_case(name, ref_rb, *, size_ep, T, increments, seed, outdir):
     np.savez_compressed(os.path.join(outdir, name + '.npz'), **arrays)
 
 
-def main():
-    outdir = os.path.join(ROOT, 'tests', 'golden')
+def main(outdir=None):
+    outdir = outdir or os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(outdir, exist_ok=True)
     ref_her, ref_rb = import_reference()
     kw = dict(ref_her=ref_her, ref_rb=ref_rb, outdir=outdir)

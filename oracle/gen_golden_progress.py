@@ -23,16 +23,17 @@ ROWS = [
 ]
 
 
-def main():
+def main(outdir=None):
+    outdir = outdir or os.path.join(ROOT, 'tests', 'golden')
     spec = importlib.util.spec_from_file_location('ref_logger', os.path.join(REF, 'baselines/logger.py'))
     ref = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ref)
-    out = os.path.join(ROOT, 'tests', 'golden', 'progress_golden.csv')
+    out = os.path.join(outdir, 'progress_golden.csv')
     w = ref.CSVOutputFormat(out)
     for row in ROWS:
         w.writekvs(dict(row))
     w.close()
-    with open(os.path.join(ROOT, 'tests', 'golden', 'progress_rows.json'), 'w') as f:
+    with open(os.path.join(outdir, 'progress_rows.json'), 'w') as f:
         json.dump(ROWS, f)
     print(open(out).read())
 

@@ -35,7 +35,7 @@ def import_reference_queue():
     return mod
 
 
-def main():
+def main(outdir=None):
     ref = import_reference_queue()
     rng = np.random.RandomState(2024)
     arrays = {}
@@ -59,7 +59,7 @@ def main():
         arrays['c%d_full' % case] = np.array(fulls)
         arrays['c%d_after_clear' % case] = np.array([float(q.CP), float(q.C), float(q.size)])
     arrays['n_cases'] = np.array(3)
-    out = os.path.join(ROOT, 'tests', 'golden', 'competence_queue.npz')
+    out = os.path.join(outdir or os.path.join(ROOT, 'tests', 'golden'), 'competence_queue.npz')
     np.savez_compressed(out, **arrays)
     print('wrote', out)
 

@@ -109,3 +109,48 @@ def test_invariants_on_golden():
         assert set(np.unique(ref['r'])) <= {-1.0, 0.0}
         if not meta['flat']:
             assert np.array_equal(ref['task_descr'].sum(1), np.ones(meta['B']))
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/baselines/her'), reason='needs the reference checkout (build container)')
+def test_committed_fixtures_are_what_the_unmodified_reference_produces(tmp_path):
+    """Re-runs oracle/gen_golden.py (which imports her.py / replay_buffer.py from /root/reference unmodified) into a scratch
+    directory and compares every array of every fixture with the committed tests/golden/*.npz: the fixtures the GPU box
+    tests against are the reference's outputs, not something edited by hand."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('gen_golden', os.path.join(os.path.dirname(GOLDEN), '..', 'oracle',
+                                                                             'gen_golden.py'))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    state = np.random.get_state()
+    try:
+        gen.main(str(tmp_path))
+    finally:
+        np.random.set_state(state)
+    manifest = json.load(open(os.path.join(GOLDEN, 'MANIFEST.json')))
+    assert len(manifest['cases']) >= 15
+    for name in manifest['cases']:
+        new, old = np.load(str(tmp_path / (name + '.npz')), allow_pickle=True), np.load(os.path.join(GOLDEN, name + '.npz'),
+                                                                                       allow_pickle=True)
+        assert sorted(new.files) == sorted(old.files), name
+        for key in old.files:
+            a, b = new[key], old[key]
+            assert a.dtype == b.dtype and a.shape == b.shape, (name, key)
+            assert np.array_equal(a, b) or (a.dtype.kind == 'f' and np.array_equal(a, b, equal_nan=True)), (name, key)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/baselines/her'), reason='needs the reference checkout (build container)')
+def test_queue_and_logger_fixtures_regenerate_identically(tmp_path):
+    """Same for tests/golden/competence_queue.npz (reference queues.py) and progress_golden.csv (reference logger.py)."""
+    import importlib.util
+    oracle_dir = os.path.join(os.path.dirname(GOLDEN), '..', 'oracle')
+    for script in ('gen_golden_queue.py', 'gen_golden_progress.py'):
+        spec = importlib.util.spec_from_file_location(script[:-3], os.path.join(oracle_dir, script))
+        gen = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(gen)
+        gen.main(str(tmp_path))
+    new, old = np.load(str(tmp_path / 'competence_queue.npz')), np.load(os.path.join(GOLDEN, 'competence_queue.npz'))
+    assert sorted(new.files) == sorted(old.files)
+    for key in old.files:
+        assert np.array_equal(new[key], old[key]), key
+    for name in ('progress_golden.csv', 'progress_rows.json'):
+        assert open(str(tmp_path / name)).read() == open(os.path.join(GOLDEN, name)).read(), name
