@@ -227,3 +227,24 @@ def test_action_noise_oracle_statistics():
     assert not np.array_equal(b, c)
     d, _ = action_noise(u[:, :3], 1.0, 5.0, 0.0, seed=7, call=3)          # odd dimu; heavy noise is clipped
     assert d.shape == (40000, 3) and np.abs(d).max() == 1.0
+
+
+def test_bench_roofline_arithmetic_matches_the_survey():
+    """828 B / transition (Arm4-shaped), 1340 B (Arm8-shaped), ~0.73 GFLOP per batch-256 update - the
+    figures `roofline.achieved` and the TFLOP/s columns of bench.py are computed from."""
+    import bench
+    from curious_b200 import synth
+    d4, d8 = synth.arm_dims(4), synth.arm_dims(8)
+    assert (d4['o'], d4['g'], d4['ag'], d4['u']) == (40, 12, 12, 4) and (d8['o'], d8['g']) == (64, 24)
+    assert bench.algorithmic_bytes_per_transition(d4, 4) == 424 + 404 == 828
+    assert bench.algorithmic_bytes_per_transition(d8, 8) == 680 + 660 == 1340
+    f = bench.update_flops(d4, 4, 256)
+    f_pi = 2 * 256 * ((44 + 12) * 256 + 2 * 256 * 256 + 256 * 4)
+    f_q = 2 * 256 * ((48 + 12) * 256 + 2 * 256 * 256 + 256)
+    assert abs(f_pi - 75.0e6) < 0.1e6 and abs(f_q - 75.1e6) < 0.1e6          # SURVEY: F_pi = 75.0 M, F_Q = 75.1 M
+    assert 0.72e9 < f < 0.74e9 and bench.update_flops(d4, 4, 512) == 2 * f
+    # the clocks object of the JSON line keeps its keys without a GPU (no samples, no crash)
+    sampler = bench.ClockSampler(0)
+    sampler.start()
+    line = sampler.stop()
+    assert set(line) >= {'sm_mhz', 'sm_max_mhz', 'reasons', 'samples', 'source'}
