@@ -17,8 +17,8 @@ def sampler_cases():
     return names
 
 
-def load_case(name):
-    z = np.load(os.path.join(GOLDEN, name + '.npz'))
+def load_case(name, directory=None):
+    z = np.load(os.path.join(directory or GOLDEN, name + '.npz'))
     meta = json.loads(str(z['meta']))
     eps = {k[3:]: z[k] for k in z.files if k.startswith('in_')}
     out = {k[4:]: z[k] for k in z.files if k.startswith('out_')}

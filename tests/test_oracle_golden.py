@@ -154,3 +154,49 @@ def test_queue_and_logger_fixtures_regenerate_identically(tmp_path):
         assert np.array_equal(new[key], old[key]), key
     for name in ('progress_golden.csv', 'progress_rows.json'):
         assert open(str(tmp_path / name)).read() == open(os.path.join(GOLDEN, name)).read(), name
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/baselines/her'), reason='needs the reference checkout (build container)')
+def test_oracle_equals_the_live_reference_on_random_scenarios(tmp_path):
+    """Beyond the 15 committed fixtures: 60 randomly drawn scenarios (sizes, modules, every task_replay mode, with and
+    without HER, flat, longer ag slices, buffer / direct calls) run through the UNMODIFIED reference here and through the
+    oracle with the same seed - draws, outputs, dtypes and reward-call contract must agree bit for bit."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('gen_golden', os.path.join(os.path.dirname(GOLDEN), '..', 'oracle',
+                                                                             'gen_golden.py'))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    ref_her, ref_rb = gen.import_reference()
+    rng = np.random.RandomState(20241017)
+    state = np.random.get_state()
+    modes = ['replay_task_cp_buffer', 'replay_task_random_buffer', 'replay_random_task_transition',
+             'replay_cp_task_transition', 'replay_current_task_transition']
+    try:
+        for i in range(60):
+            flat = bool(rng.rand() < 0.2)
+            n_modules = int(rng.randint(1, 7))
+            mode = '' if flat else modes[int(rng.randint(len(modes)))]
+            kw = dict(n_modules=n_modules, dimo=int(rng.randint(1, 12)), E=int(rng.randint(1, 9)), T=int(rng.randint(1, 14)),
+                      B=int(rng.randint(1, 130)), seed=int(rng.randint(1 << 30)), data_seed=int(rng.randint(1 << 30)),
+                      goal_replay='her' if rng.rand() < 0.8 else 'none', task_replay=mode, flat=flat,
+                      longer_ag=bool(rng.rand() < 0.3) and not flat, via_buffer=bool(rng.rand() < 0.7))
+            if not flat:
+                if 'buffer' in mode and rng.rand() < 0.7:
+                    kw['task_to_replay'] = int(rng.randint(n_modules))
+                if mode == 'replay_cp_task_transition':
+                    p = rng.rand(n_modules) + 0.05
+                    kw['cp_proba'] = list(p / p.sum())
+            name = 'rand_%02d' % i
+            gen.run_sampler_case(name, ref_her, ref_rb, outdir=str(tmp_path), **kw)
+            meta, eps, stream, ref = load_case(name, str(tmp_path))
+            out, sampler, reward = run_oracle(meta, eps)
+            s = sampler.last_stream
+            assert np.array_equal(s.ep, stream['s_ep']) and np.array_equal(s.t, stream['s_t']), (i, kw)
+            assert np.array_equal(s.u_her, stream['s_uher']) and np.array_equal(s.u_off, stream['s_uoff']), (i, kw)
+            assert set(out.keys()) == set(ref.keys()), (i, kw)
+            for k in ref:
+                assert out[k].shape == ref[k].shape and out[k].dtype == ref[k].dtype, (i, k, kw)
+                assert np.array_equal(out[k], ref[k]), (i, k, kw)
+            assert reward.n_calls == meta['reward_calls'], (i, kw)
+    finally:
+        np.random.set_state(state)
