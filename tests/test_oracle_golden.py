@@ -200,3 +200,46 @@ def test_oracle_equals_the_live_reference_on_random_scenarios(tmp_path):
             assert reward.n_calls == meta['reward_calls'], (i, kw)
     finally:
         np.random.set_state(state)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/baselines/her'), reason='needs the reference checkout (build container)')
+def test_storage_oracle_equals_the_live_reference_on_random_sequences():
+    """ReplayBuffer slot policy and counters (replay_buffer.py:57-109) on 40 random capacity / batch-size sequences,
+    reference and oracle seeded alike: same slots, same sizes, same stored data, same failure on an oversize batch."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('gen_golden', os.path.join(os.path.dirname(GOLDEN), '..', 'oracle',
+                                                                             'gen_golden.py'))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    _, ref_rb = gen.import_reference()
+    rng = np.random.RandomState(99)
+    state = np.random.get_state()
+    try:
+        for case in range(40):
+            T, size_ep = int(rng.randint(1, 6)), int(rng.randint(1, 12))
+            shapes = {'o': (T + 1, 2), 'u': (T, 1)}
+            bufs = [ref_rb.ReplayBuffer(shapes, size_ep * T, T, None), replay_oracle.ReplayBufferOracle(shapes, size_ep * T, T, None)]
+            seed = int(rng.randint(1 << 30))
+            incs = [int(rng.randint(1, size_ep + 2)) for _ in range(int(rng.randint(3, 25)))]
+            results = []
+            for buf in bufs:
+                np.random.seed(seed)
+                log = []
+                for k, inc in enumerate(incs):
+                    ep = {'o': np.full((inc, T + 1, 2), float(k)), 'u': np.full((inc, T, 1), float(k))}
+                    try:
+                        buf.store_episode(ep)
+                        log.append(('ok', buf.get_current_episode_size(), buf.get_current_size(), buf.get_transitions_stored(),
+                                    bool(buf.full)))
+                    except AssertionError:
+                        log.append(('too large',))
+                n = buf.get_current_episode_size()
+                results.append((log, buf.buffers['u'][:n, 0, 0].copy(), buf.buffers['o'][:n, -1, 1].copy(),
+                                np.random.get_state()[1].copy()))
+            (la, ua, oa, sa), (lb, ub, ob, sb) = results
+            assert la == lb, (case, incs)
+            assert np.array_equal(ua, ub) and np.array_equal(oa, ob), (case, incs)
+            assert np.array_equal(sa, sb), 'np.random consumed differently'
+            assert any(inc > size_ep for inc in incs) == any(x == ('too large',) for x in la)
+    finally:
+        np.random.set_state(state)
