@@ -248,3 +248,39 @@ def test_bench_roofline_arithmetic_matches_the_survey():
     sampler.start()
     line = sampler.stop()
     assert set(line) >= {'sm_mhz', 'sm_max_mhz', 'reasons', 'samples', 'source'}
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/baselines/her'), reason='needs the reference checkout (build container)')
+def test_product_slot_policy_equals_the_live_reference():
+    """ReplayBuffer._get_storage_idx of the drop-in (host logic, consumes the caller's np.random) against the unmodified
+    reference method on random sequences - no device needed: the object is built without its CUDA storage."""
+    import importlib.util
+    from curious_b200.replay_buffer import ReplayBuffer
+    spec = importlib.util.spec_from_file_location('gen_golden', os.path.join(ROOT, 'oracle', 'gen_golden.py'))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    _, ref_rb = gen.import_reference()
+    rng = np.random.RandomState(5)
+    state = np.random.get_state()
+    try:
+        for case in range(40):
+            T, size_ep = int(rng.randint(1, 6)), int(rng.randint(1, 12))
+            ref = ref_rb.ReplayBuffer({'u': (T, 1)}, size_ep * T, T, None)
+            mine = ReplayBuffer.__new__(ReplayBuffer)
+            mine.size, mine.T, mine.current_size, mine.n_transitions_stored = size_ep, T, 0, 0
+            seed = int(rng.randint(1 << 30))
+            incs = [int(rng.randint(1, size_ep + 1)) for _ in range(int(rng.randint(3, 30)))]
+            out = []
+            for buf in (ref, mine):
+                np.random.seed(seed)
+                seq = []
+                for inc in incs:
+                    idx = buf._get_storage_idx(inc)
+                    seq.append((np.atleast_1d(idx).tolist(), np.ndim(idx), buf.current_size))
+                out.append((seq, np.random.get_state()[1].copy()))
+            assert out[0][0] == out[1][0], (case, incs)
+            assert np.array_equal(out[0][1], out[1][1])
+            with pytest.raises(AssertionError):
+                mine._get_storage_idx(size_ep + 1)
+    finally:
+        np.random.set_state(state)
