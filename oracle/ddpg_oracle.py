@@ -1,10 +1,16 @@
 """NumPy float32 restatement of Normalizer / networks / DDPG graph / MpiAdam
 (test infrastructure; see oracle/__init__.py).
 
-PARITY UNPINNED by reference tests (there are none for baselines/her/, and TensorFlow 1.x /
-mpi4py cannot be installed here).  Each function cites the reference lines it restates;
-tests/test_oracle_ddpg.py cross-checks the hand-written backward pass against torch autograd
-and Adam against the reference's `test_MpiAdam` problem definition (mpi_adam.py:54-63).
+Pinning (the reference has no tests for baselines/her/, and TensorFlow 1.x / mpi4py cannot be installed here):
+  * PINNED against the reference's own code executed live (tests/test_reference_live.py cuts the NumPy-only methods out of
+    the unmodified ddpg.py / normalizer.py and runs them on recording stubs): sample_batch incl. the LP apportioning,
+    concatenation and shuffle, store_episode routing and its normaliser batch, get_actions post-processing,
+    _preprocess_og, Normalizer.update / synchronize / snapshot-and-reset;
+  * PARITY UNPINNED (restated from the TF1 graph definitions): network forward, losses and gradients, the running-sum /
+    mean / std half of Normalizer, MpiAdam arithmetic, polyak.  tests/test_host_logic.py cross-checks the hand-written
+    backward pass against torch autograd and Adam against the reference's `test_MpiAdam` problem definition
+    (mpi_adam.py:54-63).
+Each function cites the reference lines it restates.
 
 Conventions
 -----------

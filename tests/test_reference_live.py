@@ -1,0 +1,374 @@
+"""The NumPy-only methods of the UNMODIFIED reference executed live against the oracle restatement and the product's host
+arithmetic: DDPG.sample_batch (ddpg.py:251-360), DDPG.store_episode (:163-223), DDPG.get_actions post-processing (:129-161),
+DDPG._preprocess_og (:118-127) and the NumPy half of Normalizer (normalizer.py:64-70,84-118).
+
+baselines/her/ddpg.py and normalizer.py cannot be imported (TensorFlow 1.x), but these methods are plain NumPy: their
+source text is cut out of the files with `ast`, compiled as it stands and run on a stand-in `self` whose buffers, TF
+session and MPI communicator are recording stubs.  The only shim is `np.int` (removed from NumPy >= 1.24, used at
+ddpg.py:282,286,314,318) -> `int`.  Build container only (needs /root/reference); CPU."""
+import ast
+import os
+import textwrap
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+from curious_b200 import apportion
+from oracle.ddpg_oracle import DDPGOracle
+
+REF = '/root/reference/baselines/her/ddpg.py'
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason='needs the reference checkout (build container)')
+
+
+class _NumpyWithInt(object):
+    int = int
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+class _FakeMPI(object):
+    """ddpg.py:185 all-reduces a counter whose result is never read."""
+    SUM = 'sum'
+
+    class COMM_WORLD(object):
+        @staticmethod
+        def Allreduce(src, dst, op=None):
+            dst[...] = src
+
+
+def _reference_namespace():
+    """sample_batch / _preprocess_og / store_episode / get_actions / _random_action of the reference class and
+    transitions_in_episode_batch of her/util.py, compiled from their unmodified source text."""
+    ns = {'np': _NumpyWithInt(), 'MPI': _FakeMPI}
+    src = open(REF).read()
+    cls = [n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == 'DDPG'][0]
+    wanted = ('sample_batch', '_preprocess_og', 'store_episode', 'get_actions', '_random_action')
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in wanted:
+            exec(compile(textwrap.dedent(ast.get_source_segment(src, fn)), REF, 'exec'), ns)
+    util = os.path.join(os.path.dirname(REF), 'util.py')
+    usrc = open(util).read()
+    for fn in ast.parse(usrc).body:
+        if isinstance(fn, ast.FunctionDef) and fn.name == 'transitions_in_episode_batch':
+            exec(compile(ast.get_source_segment(usrc, fn), util, 'exec'), ns)
+    assert all(k in ns for k in wanted + ('transitions_in_episode_batch',))
+    return ns
+
+
+def _reference_methods():
+    ns = _reference_namespace()
+    return ns['sample_batch'], ns['_preprocess_og']
+
+
+class _Buffer(object):
+    """Records sample() calls and returns transitions whose values say where they came from."""
+
+    def __init__(self, index, episodes, dims, log):
+        self.index, self.current_size, self.dims, self.log = index, episodes, dims, log
+
+    def sample(self, n, task_to_replay=None, cp_proba=None):
+        n = int(n)
+        self.log.append((self.index, n, task_to_replay, None if cp_proba is None else np.array(cp_proba).tolist()))
+        base = 1000.0 * self.index + np.arange(n, dtype=np.float64).reshape(-1, 1)
+        out = {}
+        for k, d in self.dims.items():
+            out[k] = base + 0.001 * np.arange(d) - (500.0 if k in ('o', 'g') else 0.0)      # some beyond +-clip_obs
+        out['o_2'], out['ag_2'], out['r'] = out['o'] + 0.5, out['ag'] + 0.25, -np.ones((n, 1))
+        return out
+
+
+class _Self(object):
+    pass
+
+
+def _make(structure, task_replay, rng, log, relative_goals):
+    nb = int(rng.randint(1, 7))
+    dims = OrderedDict(o=int(rng.randint(1, 6)), g=3 * nb, ag=3 * nb, u=2)
+    if structure != 'flat':
+        dims['task_descr'] = nb
+    s = _Self()
+    s.structure, s.task_replay, s.nb_tasks, s.T = structure, task_replay, nb, int(rng.randint(1, 60))
+    s.batch_size = int(rng.randint(1, 300))
+    s.eps_task, s.t_id = float(rng.choice([0.0, 0.4, 1.0])), int(rng.randint(nb))
+    s.cp = rng.rand(nb) * (rng.rand(nb) < 0.7) if rng.rand() < 0.8 else np.zeros(nb)
+    s.clip_obs, s.relative_goals, s.dimg, s.dimag = 200.0, relative_goals, dims['g'], dims['ag']
+    s.subtract_goals = lambda a, b: a - b
+    keys = sorted(k for k in dims) + ['o_2', 'g_2', 'r']                   # ddpg.py:73-83
+    s.stage_shapes = OrderedDict((k, None) for k in keys)
+    s.stage_keys = keys
+    s.modular = structure != 'flat'
+    if structure != 'flat' and ('buffer' in task_replay):
+        sizes = [0] + [int(rng.randint(0, 4)) * int(rng.rand() < 0.7) for _ in range(nb)]
+        if structure == 'task_experts' and rng.rand() < 0.5:
+            sizes[0] = int(rng.randint(0, 3))                               # never filled in practice; the code allows it
+        if sum(sizes[1:]) == 0:
+            sizes[1 + int(rng.randint(nb))] = 2
+        s.buffer = [_Buffer(i, n, dims, log) for i, n in enumerate(sizes)]
+    else:
+        s.buffer = _Buffer(0, 3, dims, log)
+    return s
+
+
+CASES = [('curious', 'replay_task_cp_buffer'), ('curious', 'replay_task_random_buffer'),
+         ('curious', 'replay_cp_task_transition'), ('curious', 'replay_random_task_transition'),
+         ('curious', 'replay_current_task_transition'), ('task_experts', 'replay_current_task_buffer'), ('flat', '')]
+
+
+@pytest.mark.parametrize('structure,task_replay', CASES)
+def test_oracle_sample_batch_equals_reference_method(structure, task_replay):
+    ref_sample_batch, ref_preprocess = _reference_methods()
+    import zlib
+    rng = np.random.RandomState(zlib.crc32((structure + task_replay).encode()))
+    state = np.random.get_state()
+    try:
+        for case in range(50):
+            seed = int(rng.randint(1 << 30))
+            snapshot = rng.get_state()
+            runs = []
+            for which in ('reference', 'oracle'):
+                rng.set_state(snapshot)
+                log = []
+                s = _make(structure, task_replay, rng, log, relative_goals=bool(case % 3 == 0))
+                np.random.seed(seed)
+                if which == 'reference':
+                    s._preprocess_og = lambda o, ag, g, s=s: ref_preprocess(s, o, ag, g)
+                    batch = ref_sample_batch(s)
+                else:
+                    batch = DDPGOracle.sample_batch(s)
+                prop = None if not hasattr(s, 'proportions') else np.asarray(s.proportions).tolist()
+                runs.append((batch, log, prop, np.random.get_state()[1].copy(), s))
+            (rb, rlog, rprop, rstate, rs), (ob, olog, oprop, ostate, _) = runs
+            assert rlog == olog, (case, rlog, olog)
+            assert rprop == oprop, case
+            assert np.array_equal(rstate, ostate), 'np.random consumed differently'
+            assert len(rb) == len(ob) == len(rs.stage_keys)
+            for key, a, b in zip(rs.stage_keys, rb, ob):
+                assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b), (case, key)
+            # the product's host arithmetic (curious_b200/apportion.py) against the same reference run
+            if rprop is not None:
+                sizes = [b.current_size for b in rs.buffer]
+                if structure == 'curious':
+                    mine = apportion.proportions_curious(sizes, rs.T, rs.batch_size, task_replay, rs.cp, rs.eps_task)
+                else:
+                    mine = apportion.proportions_task_expert(sizes, rs.T, rs.batch_size, rs.t_id)
+                assert np.asarray(mine).tolist() == rprop, (case, sizes)
+            elif task_replay == 'replay_cp_task_transition':
+                assert np.array(apportion.cp_probabilities(rs.cp, rs.eps_task)).tolist() == rlog[0][3]
+    finally:
+        np.random.set_state(state)
+
+
+class _RecordingBuffer(object):
+    def __init__(self, index, log):
+        self.index, self.log = index, log
+
+    def store_episode(self, ep):
+        self.log.append((self.index, {k: np.array(v, copy=True) for k, v in ep.items()}))
+
+
+class _RecordingStats(object):
+    def __init__(self, name, log):
+        self.name, self.log = name, log
+
+    def update(self, v):
+        self.log.append((self.name, 'update', np.array(v, copy=True)))
+
+    def recompute_stats(self):
+        self.log.append((self.name, 'recompute', None))
+
+
+@pytest.mark.parametrize('structure,task_replay', [('curious', 'replay_task_cp_buffer'), ('curious', 'replay_cp_task_transition'),
+                                                   ('task_experts', 'replay_current_task_buffer'), ('flat', '')])
+@pytest.mark.parametrize('nb_tasks', [3, 8])
+def test_oracle_store_episode_equals_reference_method(structure, task_replay, nb_tasks):
+    """DDPG.store_episode (ddpg.py:163-223) live: per-module routing by `change`, the j < 5 cap for 5+ modules, the
+    duplication into every active module's buffer, and the normaliser batch drawn by the (reference) HER sampler."""
+    import importlib.util
+    from curious_b200 import synth
+    from oracle.reward_oracle import ModuleDistanceReward
+    ns = _reference_namespace()
+    spec = importlib.util.spec_from_file_location('gen_golden', os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), 'oracle', 'gen_golden.py'))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    ref_her, _ = gen.import_reference()
+    dims = synth.arm_dims(nb_tasks, 7)
+    ag_ids, g_ids = synth.arm_task_ids(nb_tasks)
+    if structure == 'flat':
+        dims = {k: v for k, v in dims.items() if k != 'task_descr'}
+    rng = np.random.RandomState(17 + nb_tasks)
+    state = np.random.get_state()
+    try:
+        for case in range(12):
+            eps = synth.make_episodes(rng, 2, 6, dims, still_prob=0.5, change_dtype=bool)
+            if structure == 'flat':
+                eps = {k: v for k, v in eps.items() if k not in ('task_descr', 'change')}
+            seed = int(rng.randint(1 << 30))
+            runs = []
+            for which in ('reference', 'oracle'):
+                log, slog = [], []
+                s = _Self()
+                s.structure, s.task_replay, s.nb_tasks = structure, task_replay, nb_tasks
+                s.tasks_ag_id, s.tasks_g_id, s.modular = ag_ids, g_ids, structure != 'flat'
+                s.clip_obs, s.relative_goals, s.dimg, s.dimag = 200.0, False, dims['g'], dims['ag']
+                s.subtract_goals = lambda a, b: a - b
+                reward = ModuleDistanceReward(ag_ids, g_ids, 0.05)
+                if structure == 'flat':
+                    s.sample_transitions = ref_her.make_sample_her_transitions('her', 4, reward, '', tasks_ag_id=ag_ids,
+                                                                               tasks_g_id=g_ids)
+                else:
+                    s.sample_transitions = ref_her.make_sample_multi_task_her_transitions(
+                        'her', 4, task_replay, reward, tasks_ag_id=ag_ids, tasks_g_id=g_ids)
+                multi = 'buffer' in task_replay
+                s.buffer = [_RecordingBuffer(i, log) for i in range(nb_tasks + 1)] if multi else _RecordingBuffer(0, log)
+                s.o_stats, s.g_stats = _RecordingStats('o', slog), _RecordingStats('g', slog)
+                batch = {k: v.copy() for k, v in eps.items()}
+                np.random.seed(seed)
+                if which == 'reference':
+                    s._preprocess_og = lambda o, ag, g, s=s: ns['_preprocess_og'](s, o, ag, g)
+                    ns['store_episode'](s, batch, np.arange(nb_tasks) / 10.0, 40 + case)
+                else:
+                    DDPGOracle.store_episode(s, batch, np.arange(nb_tasks) / 10.0, 40 + case)
+                runs.append((log, slog, s.n_episodes, np.random.get_state()[1].copy(), sorted(batch.keys())))
+            (rl, rs, rn, rstate, rkeys), (ol, os_, on, ostate, okeys) = runs
+            assert [i for i, _ in rl] == [i for i, _ in ol], case                     # same buffers, same order
+            for (_, a), (_, b) in zip(rl, ol):
+                assert a.keys() == b.keys()
+                for k in a:
+                    assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), (case, k)
+            if nb_tasks >= 5 and 'buffer' in task_replay:
+                assert all(i <= 5 for i, _ in rl)                                   # ddpg.py:183: modules 5.. are never stored
+            assert [(n, what) for n, what, _ in rs] == [(n, what) for n, what, _ in os_]
+            for (_, _, a), (_, _, b) in zip(rs, os_):
+                assert (a is None and b is None) or (a.dtype == b.dtype and np.array_equal(a, b)), case
+            assert rn == on and rkeys == okeys and np.array_equal(rstate, ostate)
+    finally:
+        np.random.set_state(state)
+
+
+def test_oracle_get_actions_postprocessing_equals_reference_method():
+    """DDPG.get_actions (ddpg.py:129-161) live with the TF session stubbed out by the oracle's own network output: the feed
+    (preprocessed o, g, zero u, task_descr), Gaussian noise added in place to the float32 action, clipping, eps-greedy
+    replacement, the single-row squeeze and the host RNG consumption."""
+    from tests.ddpg_util import ddpg_kwargs, make_oracle_agent
+    ns = _reference_namespace()
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(3, hidden=16, layers=2, dimo=9)
+    ora = make_oracle_agent(kw, dims, ag_ids, g_ids, buffer_episodes=2)
+    rng = np.random.RandomState(3)
+    state = np.random.get_state()
+
+    class Net(object):
+        pi_tf, Q_pi_tf, o_tf, g_tf, u_tf, td_tf = 'pi', 'Q_pi', 'o', 'g', 'u', 'td'
+
+    class Session(object):
+        def run(self, vals, feed_dict):
+            self.feed = feed_dict
+            return [self.outputs[v].copy() for v in vals]
+    try:
+        for n in (1, 2, 17):
+            for use_target in (False, True):
+                for compute_Q in (False, True):
+                    o = (rng.standard_normal((n, dims['o'])) * 150).astype(np.float32)
+                    ag = rng.uniform(-1, 1, (n, dims['ag'])).astype(np.float32)
+                    g = rng.uniform(-1, 1, (n, dims['g'])).astype(np.float32)
+                    td = np.eye(3, dtype=np.float32)[rng.randint(0, 3, n)]
+                    clean = ora.get_actions(o, ag, g, task_descr=td, use_target_net=use_target, compute_Q=True)
+                    pi, q = np.asarray(clean[0], np.float32).reshape(n, -1), np.asarray(clean[1])
+                    s = _Self()
+                    s.main, s.target, s.sess = Net(), Net(), Session()
+                    s.sess.outputs = {'pi': pi, 'Q_pi': q}
+                    s.structure, s.dimo, s.dimg, s.dimu, s.dimtd, s.dimag = 'curious', dims['o'], dims['g'], dims['u'], 3, dims['ag']
+                    s.max_u, s.clip_obs, s.relative_goals = 1.0, 200.0, False
+                    s._preprocess_og = lambda o, ag, g, s=s: ns['_preprocess_og'](s, o, ag, g)
+                    s._random_action = lambda k, s=s: ns['_random_action'](s, k)
+                    seed = int(rng.randint(1 << 30))
+                    np.random.seed(seed)
+                    ref = ns['get_actions'](s, o, ag, g, task_descr=td, noise_eps=0.2, random_eps=0.3,
+                                            use_target_net=use_target, compute_Q=compute_Q)
+                    ref_state = np.random.get_state()[1].copy()
+                    np.random.seed(seed)
+                    mine = ora.get_actions(o, ag, g, task_descr=td, noise_eps=0.2, random_eps=0.3,
+                                           use_target_net=use_target, compute_Q=compute_Q)
+                    assert np.array_equal(np.random.get_state()[1], ref_state)
+                    ref_u, mine_u = (ref[0], mine[0]) if compute_Q else (ref, mine)
+                    assert ref_u.shape == mine_u.shape == ((dims['u'],) if n == 1 else (n, dims['u']))
+                    assert ref_u.dtype == mine_u.dtype and np.array_equal(ref_u, mine_u)
+                    if compute_Q:
+                        assert np.array_equal(ref[1], mine[1])
+                    feed = s.sess.feed
+                    assert np.array_equal(feed['o'], np.clip(o, -200, 200)) and np.array_equal(feed['g'], g)
+                    assert feed['u'].shape == (n, dims['u']) and not feed['u'].any() and np.array_equal(feed['td'], td)
+    finally:
+        np.random.set_state(state)
+
+
+def test_oracle_normalizer_accumulation_equals_reference_methods():
+    """Normalizer.update / _mpi_average / synchronize / recompute_stats (normalizer.py:64-70,84-118) live - the NumPy half
+    of the class (float32 accumulators fed with float64 or float32 batches, snapshot + reset, mean over ranks of sum, sumsq,
+    count in that order) with a 3-rank world emulated by the fake communicator; the TF half (running sums, mean, std) is
+    restated in the oracle and checked bit for bit against the CUDA kernels elsewhere."""
+    import threading
+    from oracle.ddpg_oracle import NormalizerOracle
+    nsrc = open(os.path.join(os.path.dirname(REF), 'normalizer.py')).read()
+    cls = [n for n in ast.parse(nsrc).body if isinstance(n, ast.ClassDef) and n.name == 'Normalizer'][0]
+    rng = np.random.RandomState(8)
+    contributions = []
+
+    class World3(object):
+        SUM = 'sum'
+
+        class COMM_WORLD(object):
+            @staticmethod
+            def Allreduce(src, dst, op=None):
+                other = contributions.pop(0)
+                dst[...] = src + other
+
+            @staticmethod
+            def Get_size():
+                return 3
+    ns = {'np': np, 'MPI': World3}
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ('update', '_mpi_average', 'synchronize', 'recompute_stats'):
+            exec(compile(textwrap.dedent(ast.get_source_segment(nsrc, fn)), REF, 'exec'), ns)
+    size = 5
+    ref = _Self()
+    ref.size, ref.lock = size, threading.Lock()
+    ref.local_sum, ref.local_sumsq, ref.local_count = np.zeros(size, np.float32), np.zeros(size, np.float32), np.zeros(1, np.float32)
+    ref.count_pl, ref.sum_pl, ref.sumsq_pl, ref.update_op, ref.recompute_op = 'count', 'sum', 'sumsq', 'update', 'recompute'
+    feeds = []
+
+    class Session(object):
+        def run(self, op, feed_dict=None):
+            if feed_dict is not None:
+                feeds.append({k: np.array(v, copy=True) for k, v in feed_dict.items()})
+    ref.sess = Session()
+    ref._mpi_average = lambda x: ns['_mpi_average'](ref, x)
+    ref.synchronize = lambda **kw: ns['synchronize'](ref, **kw)
+    synced = []
+    others = []
+
+    def mean_over_ranks(x):
+        out = (x + others.pop(0)) / 3
+        synced.append(np.array(out, copy=True))
+        return out
+    ora = NormalizerOracle(size, mean_over_ranks=mean_over_ranks)
+    for round_ in range(6):
+        for _ in range(int(rng.randint(1, 4))):
+            v = rng.standard_normal((int(rng.randint(1, 40)), size)) * 3
+            v = v.astype(np.float32) if rng.rand() < 0.5 else v
+            ns['update'](ref, v.copy())
+            ora.update(v.copy())
+        assert np.array_equal(ref.local_sum, ora.local_sum) and np.array_equal(ref.local_sumsq, ora.local_sumsq)
+        assert np.array_equal(ref.local_count, ora.local_count) and ref.local_sum.dtype == ora.local_sum.dtype == np.float32
+        peers = [rng.standard_normal(size).astype(np.float32), np.abs(rng.standard_normal(size)).astype(np.float32),
+                 np.array([float(rng.randint(1, 50))], np.float32)]
+        contributions[:] = [p.copy() for p in peers]
+        others[:] = [p.copy() for p in peers]
+        ns['recompute_stats'](ref)
+        ora.recompute_stats()
+        feed = feeds[-1]
+        assert np.array_equal(feed['sum'], synced[-3]) and np.array_equal(feed['sumsq'], synced[-2]), round_
+        assert np.array_equal(feed['count'], synced[-1]) and feed['sum'].dtype == np.float32
+        assert not ref.local_sum.any() and not ora.local_sum.any() and ref.local_count[0] == ora.local_count[0] == 0
