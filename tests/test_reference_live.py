@@ -372,3 +372,34 @@ def test_oracle_normalizer_accumulation_equals_reference_methods():
         assert np.array_equal(feed['sum'], synced[-3]) and np.array_equal(feed['sumsq'], synced[-2]), round_
         assert np.array_equal(feed['count'], synced[-1]) and feed['sum'].dtype == np.float32
         assert not ref.local_sum.any() and not ora.local_sum.any() and ref.local_count[0] == ora.local_count[0] == 0
+
+
+def test_util_glue_equals_reference_functions():
+    """her/util.py store_args / convert_episode_to_batch_major / transitions_in_episode_batch (plain Python, cut out of the
+    unmodified file) against curious_b200/util.py."""
+    import functools
+    import inspect
+    from curious_b200 import util as mine
+    upath = os.path.join(os.path.dirname(REF), 'util.py')
+    usrc = open(upath).read()
+    ns = {'np': np, 'inspect': inspect, 'functools': functools}
+    for fn in ast.parse(usrc).body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ('store_args', 'convert_episode_to_batch_major',
+                                                           'transitions_in_episode_batch'):
+            exec(compile(ast.get_source_segment(usrc, fn), upath, 'exec'), ns)
+
+    def make(decorator):
+        class K(object):
+            @decorator
+            def __init__(self, a, b, c=3, *, d=4, **kwargs):
+                self.seen = dict(kwargs)
+        return K
+    for args, kwargs in (((1, 2), {}), ((1,), {'b': 5, 'd': 6}), ((1, 2, 9), {'extra': 'x', 'structure': 'curious'})):
+        r, m = make(ns['store_args'])(*args, **kwargs), make(mine.store_args)(*args, **kwargs)
+        assert r.__dict__ == m.__dict__
+    rng = np.random.RandomState(0)
+    episode = {'o': [rng.rand(2, 3) for _ in range(5)], 'u': [rng.rand(2, 1) for _ in range(4)]}
+    a, b = ns['convert_episode_to_batch_major'](episode), mine.convert_episode_to_batch_major(episode)
+    assert a.keys() == b.keys() and all(np.array_equal(a[k], b[k]) and a[k].shape == b[k].shape for k in a)
+    assert a['o'].shape == (2, 5, 3)
+    assert ns['transitions_in_episode_batch'](a) == mine.transitions_in_episode_batch(b) == 8
