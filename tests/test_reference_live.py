@@ -403,3 +403,79 @@ def test_util_glue_equals_reference_functions():
     assert a.keys() == b.keys() and all(np.array_equal(a[k], b[k]) and a[k].shape == b[k].shape for k in a)
     assert a['o'].shape == (2, 5, 3)
     assert ns['transitions_in_episode_batch'](a) == mine.transitions_in_episode_batch(b) == 8
+
+
+def _reference_lp_block():
+    """The learning-progress block at the end of RolloutWorker.generate_rollouts (rollout.py:316-404), cut out of the
+    unmodified file and wrapped into a function of (self, successful, achieved_goals)."""
+    rpath = os.path.join(os.path.dirname(REF), 'rollout.py')
+    rsrc = open(rpath).read()
+    cls = [n for n in ast.parse(rsrc).body if isinstance(n, ast.ClassDef) and n.name == 'RolloutWorker'][0]
+    fn = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == 'generate_rollouts'][0]
+    blocks = [n for n in fn.body if isinstance(n, ast.If) and 'task_experts' in ast.get_source_segment(rsrc, n.test)
+              and 'competence_computers' in ast.get_source_segment(rsrc, n)]
+    assert len(blocks) == 1
+    lines = rsrc.splitlines()[blocks[0].lineno - 1:blocks[0].end_lineno]
+    body = textwrap.indent(textwrap.dedent('\n'.join(lines)), '    ')
+    ns = {}
+    exec(compile('def lp_block(self, successful, achieved_goals, MPI, np):\n' + body + '\n', rpath, 'exec'), ns)
+    return ns['lp_block']
+
+
+@pytest.mark.parametrize('structure,task_selection,eval_', [('curious', 'active_competence_progress', False),
+                                                            ('curious', 'random', False),
+                                                            ('curious', 'active_competence_progress', True),
+                                                            ('task_experts', 'active_competence_progress', False)])
+def test_competence_tracker_equals_reference_lp_block(structure, task_selection, eval_):
+    """curious_b200.queues.CompetenceTracker.update against the reference's own LP block run live with the reference's own
+    CompetenceQueue objects: C, CP and the task-selection probabilities p after every rollout."""
+    import importlib.util
+    from curious_b200.queues import CompetenceTracker
+    spec = importlib.util.spec_from_file_location('gen_golden_queue', os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), 'oracle', 'gen_golden_queue.py'))
+    gq = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gq)
+    ref_queue = gq.import_reference_queue().CompetenceQueue
+    lp_block = _reference_lp_block()
+
+    class OneRank(object):
+        class COMM_WORLD(object):
+            gather = staticmethod(lambda x, root=0: [x])
+            bcast = staticmethod(lambda x, root=0: x)
+    nb, B, window = 4, 3, 6
+    rng = np.random.RandomState(11)
+
+    class Env(object):
+        def __init__(self):
+            self.unwrapped = self
+            self.task, self.goal = 0, np.zeros(3 * nb)
+    s = _Self()
+    s.structure, s.task_selection, s.eval, s.goal_selection = structure, task_selection, eval_, 'random'
+    s.rollout_batch_size, s.rank, s.nb_tasks, s.unique_task = B, 0, nb, 2
+    s.envs = [Env() for _ in range(B)]
+    s.tasks_g_id = [[3 * j, 3 * j + 1, 3 * j + 2] for j in range(nb)]
+    s.competence_computers = [ref_queue(window=window) for _ in range(nb)]
+    s.get_C = lambda: [q.C for q in s.competence_computers]
+    s.get_CP = lambda: [q.CP for q in s.competence_computers]
+    s.task_history, s.goal_history, s.tasks, s.goals = [], [], [0] * B, [None] * B
+    s.p, s.CP, s.C = np.ones(nb) / nb, np.zeros(nb), np.zeros(nb)
+    mine = CompetenceTracker(nb, queue_length=window, task_selection=task_selection, structure=structure,
+                             unique_task=2, eval=eval_, comm=False)
+    skill = np.array([0.9, 0.5, 0.1, 0.0])
+    seen_cp, seen_skewed = 0.0, False
+    for step in range(80):
+        s.exploit = bool(rng.rand() < 0.6) or eval_
+        for e in s.envs:
+            e.task = int(rng.randint(nb)) if structure == 'curious' else 2
+        skill = np.clip(skill + rng.uniform(-0.1, 0.15, nb), 0, 1)                  # competence drifts: CP becomes non-zero
+        successful = (rng.rand(B) < skill[[e.task for e in s.envs]]).astype(np.float64)
+        lp_block(s, successful, [np.zeros((B, 3 * nb))], OneRank, np)
+        tasks, succ = ([e.task for e in s.envs], successful.tolist()) if s.exploit else ([], [])
+        CP, p = mine.update(tasks, succ)
+        assert np.array_equal(np.asarray(mine.C, np.float64), np.asarray(s.C, np.float64)), step
+        if not eval_:
+            assert np.array_equal(np.asarray(CP, np.float64), np.asarray(s.CP, np.float64)), step
+            assert np.array_equal(np.asarray(p, np.float64), np.asarray(s.p, np.float64)), step
+            assert abs(np.sum(p) - 1.0) < 1e-12
+    if structure == 'curious' and task_selection == 'active_competence_progress' and not eval_:
+        assert seen_cp > 0 and seen_skewed                                          # the interesting branch was exercised
