@@ -477,5 +477,7 @@ def test_competence_tracker_equals_reference_lp_block(structure, task_selection,
             assert np.array_equal(np.asarray(CP, np.float64), np.asarray(s.CP, np.float64)), step
             assert np.array_equal(np.asarray(p, np.float64), np.asarray(s.p, np.float64)), step
             assert abs(np.sum(p) - 1.0) < 1e-12
+            seen_cp = max(seen_cp, float(np.max(s.CP)))
+            seen_skewed = seen_skewed or not np.allclose(s.p, 1.0 / nb)
     if structure == 'curious' and task_selection == 'active_competence_progress' and not eval_:
         assert seen_cp > 0 and seen_skewed                                          # the interesting branch was exercised
