@@ -70,6 +70,17 @@ def rank_seed(seed, r):
     return seed + 1000000 * r
 
 
+def bcast_object(obj, comm=None):
+    """MPI.COMM_WORLD.bcast(obj, root=0) (train.py:104, rollout.py:403-404): rank 0's picklable object on every rank."""
+    group, n = world(comm)
+    if n <= 1:
+        return obj
+    import torch.distributed as dist
+    box = [obj]
+    dist.broadcast_object_list(box, src=_root(group), group=group)
+    return box[0]
+
+
 def assert_rank_streams_differ(comm=None):
     """train.py:207-212: once per epoch every rank draws one uniform from its np.random stream and compares with rank 0's -
     ranks that were seeded alike (identical exploration, identical replay slots) fail here instead of silently

@@ -22,7 +22,7 @@ from .ddpg import DDPG
 from .envs import ModularPointEnv
 from .replay_buffer import ReplayBuffer
 from .rollout import RolloutWorker
-from .parallel import assert_rank_streams_differ
+from .parallel import assert_rank_streams_differ, bcast_object
 from .runlog import RunLog, mpi_average
 
 MULTI_TASK_PARAMS = {            # config.py:56-90
@@ -216,7 +216,8 @@ class _EpochRecords(object):
 
 def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles, n_batches, structure='curious',
           task_selection='active_competence_progress', eps_task=0.4, log=None, logdir=None, params=None,
-          policy_save_interval=5, save_policies=True, checkpoint_interval=0, echo=False, resume=False):
+          policy_save_interval=5, save_policies=True, checkpoint_interval=0, echo=False, resume=False,
+          experts_follow_cp=False):
     """train.py:48-170: per epoch n_cycles x (rollouts -> store_episode -> n_batches x train -> update_target_net),
     then n_test_rollouts evaluation rollouts.  Returns one dict per epoch; with `logdir` also writes the reference's
     run records (see module docstring).  `resume=True` continues the run whose checkpoints (`checkpoint_interval`) are in
@@ -242,20 +243,31 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
         nb_tasks = len(policy)
         p = 1 / nb_tasks * np.ones([nb_tasks])
         for epoch in range(start_epoch, n_epochs):
+            proba = p.copy()
             if task_selection == 'random':
                 i_policy = epoch % nb_tasks                                  # train.py:79-81
             else:
-                cps = [np.array([rollout_worker[i].get_CP()]).squeeze()[i] for i in range(nb_tasks)]   # train.py:84-101
-                CP = np.array(cps).copy()
-                if CP.sum() == 0:
-                    p = (1 / nb_tasks) * np.ones([nb_tasks])
+                # train.py:83-104: rank 0 draws the expert, everybody follows
+                if evaluator.rank == 0:
+                    cps = [np.array([rollout_worker[i].get_CP()]).squeeze()[i] for i in range(nb_tasks)]
+                    CP = np.array(cps).copy()
+                    if CP.sum() == 0:
+                        proba = (1 / nb_tasks) * np.ones([nb_tasks])
+                    else:
+                        proba = eps_task * (1 / nb_tasks) * np.ones([nb_tasks]) + (1 - eps_task) * CP / CP.sum()
+                    # The reference computes `proba` and then normalises and draws from `p`, which is never assigned from it
+                    # (train.py:91-100): its experts are picked uniformly whatever their competence progress.  Kept as it
+                    # behaves; experts_follow_cp=True draws from `proba`, which is what the code reads like it meant.
+                    if experts_follow_cp:
+                        p = proba.copy()
+                    if p.sum() > 1:
+                        p[np.argmax(p)] -= p.sum() - 1
+                    elif p.sum() < 1:
+                        p[-1] = 1 - p[:-1].sum()
+                    i_policy = int(np.random.choice(range(nb_tasks), p=p))
                 else:
-                    p = eps_task * (1 / nb_tasks) * np.ones([nb_tasks]) + (1 - eps_task) * CP / CP.sum()
-                if p.sum() > 1:
-                    p[np.argmax(p)] -= p.sum() - 1
-                elif p.sum() < 1:
-                    p[-1] = 1 - p[:-1].sum()
-                i_policy = int(np.random.choice(range(nb_tasks), p=p))
+                    i_policy = 0
+                i_policy = int(bcast_object(i_policy, evaluator.comm))
             rollout_worker[i_policy].clear_history()
             for _ in range(n_cycles):
                 episode, cp, n_ep = rollout_worker[i_policy].generate_rollouts()
@@ -263,7 +275,7 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
                 for _ in range(n_batches):
                     policy[i_policy].train()
                 policy[i_policy].update_target_net()
-            rec = dict(epoch=epoch, i_policy=i_policy, p=p.copy(), **_evaluate(evaluator, n_test_rollouts))
+            rec = dict(epoch=epoch, i_policy=i_policy, p=p.copy(), proba=proba.copy(), **_evaluate(evaluator, n_test_rollouts))
             history.append(rec)
             if log:
                 log(rec)

@@ -481,3 +481,51 @@ def test_competence_tracker_equals_reference_lp_block(structure, task_selection,
             seen_skewed = seen_skewed or not np.allclose(s.p, 1.0 / nb)
     if structure == 'curious' and task_selection == 'active_competence_progress' and not eval_:
         assert seen_cp > 0 and seen_skewed                                          # the interesting branch was exercised
+
+
+def test_expert_selection_equals_reference_block():
+    """The expert-selection statement of the reference's train loop (experiment/train.py:79-104) cut out and run live
+    against curious_b200.train.train: same experts drawn from the same np.random stream, epoch after epoch.  (The
+    reference computes a CP-weighted `proba` but draws from `p`, which stays uniform - mirrored as it behaves.)"""
+    import warnings
+    from tests.test_train_loop_cpu import _workers
+    from curious_b200.train import train
+    tpath = os.path.join(os.path.dirname(REF), 'experiment', 'train.py')
+    tsrc = open(tpath).read()
+    fn = [n for n in ast.parse(tsrc).body if isinstance(n, ast.FunctionDef) and n.name == 'train'][0]
+    branch = [n for n in fn.body if isinstance(n, ast.If) and 'task_experts' in ast.get_source_segment(tsrc, n.test)][0]
+    loop = [n for n in branch.body if isinstance(n, ast.For) and getattr(n.target, 'id', '') == 'epoch'][0]
+    select = [n for n in loop.body if isinstance(n, ast.If)][0]
+    assert isinstance(select, ast.If) and 'task_selection' in ast.get_source_segment(tsrc, select.test)
+    lines = tsrc.splitlines()[select.lineno - 1:select.end_lineno]
+    body = textwrap.indent(textwrap.dedent('\n'.join(lines)), '    ')
+    ns = {}
+    exec(compile('def select(task_selection, epoch, nb_tasks, rank, rollout_worker, params, p, np, MPI):\n' + body +
+                 '\n    return i_policy, p\n', tpath, 'exec'), ns)
+
+    class OneRank(object):
+        class COMM_WORLD(object):
+            bcast = staticmethod(lambda x, root=0: x)
+    state = np.random.get_state()
+    try:
+        for task_selection in ('active_competence_progress', 'random'):
+            np.random.seed(4)
+            policy, rollout, evaluator, _ = _workers('task_experts')
+            for i, cp in enumerate([0.05, 0.4, 0.0]):
+                rollout[i].tracker.competence_computers[i].CP = cp
+            np.random.seed(21)
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                hist = train(policy, rollout, evaluator, n_epochs=15, n_test_rollouts=0, n_cycles=0, n_batches=0,
+                             structure='task_experts', task_selection=task_selection)
+            np.random.seed(21)
+            p = 1 / 3 * np.ones([3])
+            for epoch in range(15):
+                i_policy, p = ns['select'](task_selection, epoch, 3, 0, rollout, {'eps_task': 0.4}, p, np, OneRank)
+                assert int(i_policy) == hist[epoch]['i_policy'], (task_selection, epoch)
+                assert np.array_equal(p, hist[epoch]['p'])
+            if task_selection == 'active_competence_progress':
+                assert len(set(h['i_policy'] for h in hist)) == 3 and np.allclose(hist[-1]['p'], 1 / 3)
+                assert np.allclose(hist[-1]['proba'], 0.4 / 3 + 0.6 * np.array([0.05, 0.4, 0.0]) / 0.45)
+    finally:
+        np.random.set_state(state)

@@ -95,27 +95,37 @@ def test_loop_counts_and_records(structure, tmp_path):
     assert 'policy_1.pkl' not in files
 
 
-def test_task_experts_selection_follows_competence_progress(tmp_path):
-    """train.py:79-101: the expert trained in an epoch is drawn with p = eps / N + (1 - eps) CP / sum(CP) over the experts' own
-    competence progress (uniform while nobody progressed)."""
+def test_task_experts_selection_like_the_reference(tmp_path):
+    """train.py:79-104: the reference computes proba = eps / N + (1 - eps) CP / sum(CP) over the experts' own competence
+    progress but draws the expert from `p`, which it never updates - uniform selection.  The drop-in behaves the same by
+    default and draws from proba with experts_follow_cp=True."""
     np.random.seed(1)
     policy, rollout, evaluator, dims = _workers('task_experts')
     hist = train(policy, rollout, evaluator, n_epochs=4, n_test_rollouts=1, n_cycles=2, n_batches=3,
                  structure='task_experts', logdir=str(tmp_path), checkpoint_interval=1)
     assert len(hist) == 4
     for h in hist:
-        assert np.allclose(h['p'], 1.0 / 3)                          # random stub actions: no learning progress yet
+        assert np.allclose(h['p'], 1.0 / 3)
     chosen = [h['i_policy'] for h in hist]
     for i, pol in enumerate(policy):
         assert pol.trained == 6 * chosen.count(i) and pol.target_updates == 2 * chosen.count(i)
     header = open(str(tmp_path / 'progress.csv')).read().splitlines()[0].split(',')
     assert 'IND_TASK_rollout' in header
     assert {'checkpoint_0.pt', 'checkpoint_1.pt', 'checkpoint_2.pt'} <= set(os.listdir(str(tmp_path)))
-    # a progressing expert pulls the draw towards itself
+    # an expert that progresses: proba follows it, the draw does not (reference behaviour) unless asked to
     rollout[1].tracker.competence_computers[1].CP = 0.5
+    want = [0.4 / 3, 0.4 / 3 + 0.6, 0.4 / 3]
     np.random.seed(2)
     hist = train(policy, rollout, evaluator, n_epochs=1, n_test_rollouts=1, n_cycles=1, n_batches=1, structure='task_experts')
-    assert np.allclose(hist[0]['p'], [0.4 / 3, 0.4 / 3 + 0.6, 0.4 / 3])
+    assert np.allclose(hist[0]['proba'], want) and np.allclose(hist[0]['p'], 1.0 / 3)
+    np.random.seed(2)
+    hist = train(policy, rollout, evaluator, n_epochs=1, n_test_rollouts=1, n_cycles=1, n_batches=1, structure='task_experts',
+                 experts_follow_cp=True)
+    assert np.allclose(hist[0]['proba'], want) and np.allclose(hist[0]['p'], want)
+    # task_selection='random': round robin over the experts (train.py:79-81)
+    hist = train(policy, rollout, evaluator, n_epochs=4, n_test_rollouts=1, n_cycles=1, n_batches=1, structure='task_experts',
+                 task_selection='random')
+    assert [h['i_policy'] for h in hist] == [0, 1, 2, 0]
 
 
 @pytest.mark.parametrize('structure', ['curious', 'task_experts'])
