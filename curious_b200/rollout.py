@@ -76,24 +76,28 @@ class RolloutWorker(object):
         return box[0][self.rank]
 
     def _draw_assignment(self, i):
-        """Rank 0 picks (task, goal) for rollout slot i of every rank: task ~ p, goal uniform in [-1, 1]^len(g_id)."""
-        out = []
+        """Rank 0 picks (task, goal) for rollout slot i of every rank, in the reference's draw order (rollout.py:118-140):
+        all tasks in one np.random.choice(p=self.p, size=nb_cpu), then one uniform goal in [-1, 1]^len(g_id) per rank."""
+        core = self.envs[i].unwrapped
+        if self.modular:
+            tasks = np.random.choice(range(self.nb_tasks), p=self.p, size=self.nb_cpu).tolist()
+            goals = [np.random.uniform(-1, 1, len(self.tasks_g_id[tasks[cpu]])) for cpu in range(self.nb_cpu)]
+        else:
+            tasks = [0] * self.nb_cpu
+            goals = [np.random.uniform(-1, 1, self.dims['g']) for _ in range(self.nb_cpu)]
         for cpu in range(self.nb_cpu):
-            if self.modular:
-                task = int(np.random.choice(self.nb_tasks, p=self.p))
-                goal = np.random.uniform(-1, 1, len(self.tasks_g_id[task]))
-            else:
-                task, goal = 0, np.random.uniform(-1, 1, self.dims['g'])
             slot = cpu * self.rollout_batch_size + i
-            self.tasks[slot] = task
-            self.goals[slot] = self.envs[i].unwrapped._compute_goal(goal, task, eval=self.eval)[0]
-            out.append((task, goal))
-        return out
+            if self.modular:
+                self.tasks[slot] = tasks[cpu]
+                self.goals[slot] = core._compute_goal(goals[cpu], tasks[cpu], eval=self.eval)[0][self.tasks_g_id[tasks[cpu]]]
+            else:
+                self.goals[slot] = core._compute_goal(goals[cpu], 0)[0]
+        return list(zip(tasks, goals))
 
     def reset_rollout(self, i):
         """Reset environment i and give it its next task and goal (rollout.py:104-165)."""
         env = self.envs[i]
-        if self.eval or self.exploit or not self.stochastic_reset or np.random.rand() < 0.3:
+        if self.eval or not self.stochastic_reset or np.random.rand() < 0.3 or self.exploit:
             env.reset()
         task, goal = self._from_rank0(lambda: self._draw_assignment(i))
         self.count += 1
@@ -143,21 +147,25 @@ class RolloutWorker(object):
             self.p = np.ones(self.nb_tasks) / self.nb_tasks
         self.reset_all_rollouts()
         B, T, d = self.rollout_batch_size, self.T, self.dims
-        ep = {'o': np.zeros((B, T + 1, d['o'])), 'ag': np.zeros((B, T + 1, d['ag'])), 'u': np.zeros((B, T, d['u'])),
-              'g': np.zeros((B, T, d['g']))}
+        # observations, achieved goals, goals and task descriptors are float32 like the reference's working arrays
+        # (rollout.py:50-52,194-197); actions keep the dtype the policy returns
+        ep = {'o': np.zeros((B, T + 1, d['o']), np.float32), 'ag': np.zeros((B, T + 1, d['ag']), np.float32), 'u': None,
+              'g': np.zeros((B, T, d['g']), np.float32)}
         if self.modular:
-            ep['task_descr'] = np.zeros((B, T, self.nb_tasks))
+            ep['task_descr'] = np.zeros((B, T, self.nb_tasks), np.float32)
             ep['change'] = np.zeros((B, T, d['ag']), bool)
         for key in self.info_keys:
             ep['info_' + key] = np.zeros((B, T, d['info_' + key]), np.float32)
         ep['o'][:, 0], ep['ag'][:, 0] = self.initial_o, self.initial_ag
         success = np.zeros(B)
         env_reward = np.zeros(B)
-        q_sum = 0.0
+        Qs = []
         for t in range(T):
-            u, q = self._act(ep['o'][:, t].astype(np.float32), ep['ag'][:, t].astype(np.float32))
+            u, q = self._act(ep['o'][:, t].copy(), ep['ag'][:, t].copy())
             if q is not None:
-                q_sum += float(np.mean(q))
+                Qs.append(q)
+            if ep['u'] is None:
+                ep['u'] = np.zeros((B, T, d['u']), np.asarray(u).dtype)
             ep['u'][:, t], ep['g'][:, t] = u, self.g
             if self.modular:
                 ep['task_descr'][:, t] = self.task_descr
@@ -177,7 +185,7 @@ class RolloutWorker(object):
         self.success_history.append(float(success.mean()))
         self.reward_history.append(env_reward.copy())
         if self.compute_Q:
-            self.Q_history.append(q_sum / T)
+            self.Q_history.append(np.mean(Qs))
         self.n_episodes += B * self.nb_cpu
         if self.modular:
             self._update_competence(success)

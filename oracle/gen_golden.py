@@ -174,6 +174,31 @@ def run_storage_case(name, ref_rb, *, size_ep, T, increments, seed, outdir):
     np.savez_compressed(os.path.join(outdir, name + '.npz'), **arrays)
 
 
+def random_cases(kw, n=24, seed=777):
+    """Randomly drawn scenarios (sizes, modules, every task_replay mode, with / without HER, flat, longer ag slices,
+    buffer / direct calls) on top of the hand-picked ones: rnd_00 .. rnd_23."""
+    rng = np.random.RandomState(seed)
+    modes = ['replay_task_cp_buffer', 'replay_task_random_buffer', 'replay_random_task_transition',
+             'replay_cp_task_transition', 'replay_current_task_transition']
+    out = []
+    for i in range(n):
+        flat = bool(rng.rand() < 0.2)
+        n_modules = int(rng.randint(1, 7))
+        mode = '' if flat else modes[int(rng.randint(len(modes)))]
+        case = dict(n_modules=n_modules, dimo=int(rng.randint(1, 12)), E=int(rng.randint(1, 9)), T=int(rng.randint(1, 14)),
+                    B=int(rng.randint(1, 130)), seed=int(rng.randint(1 << 30)), data_seed=int(rng.randint(1 << 30)),
+                    goal_replay='her' if rng.rand() < 0.8 else 'none', task_replay=mode, flat=flat,
+                    longer_ag=bool(rng.rand() < 0.3) and not flat, via_buffer=bool(rng.rand() < 0.7))
+        if not flat:
+            if 'buffer' in mode and rng.rand() < 0.7:
+                case['task_to_replay'] = int(rng.randint(n_modules))
+            if mode == 'replay_cp_task_transition':
+                p = rng.rand(n_modules) + 0.05
+                case['cp_proba'] = list(p / p.sum())
+        out.append(run_sampler_case('rnd_%02d' % i, **case, **kw))
+    return out
+
+
 def main(outdir=None):
     outdir = outdir or os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(outdir, exist_ok=True)
@@ -214,6 +239,7 @@ def main(outdir=None):
                                   task_replay='', **kw))
     cases.append(run_sampler_case('flat_no_her', n_modules=3, dimo=7, E=6, T=10, B=32, seed=42,
                                   flat=True, goal_replay='none', task_replay='', **kw))
+    cases.extend(random_cases(kw))
     # storage index policy
     run_storage_case('storage_single', ref_rb, size_ep=5, T=3, increments=[1] * 12, seed=51,
                      outdir=outdir)

@@ -529,3 +529,113 @@ def test_expert_selection_equals_reference_block():
                 assert np.allclose(hist[-1]['proba'], 0.4 / 3 + 0.6 * np.array([0.05, 0.4, 0.0]) / 0.45)
     finally:
         np.random.set_state(state)
+
+
+def _reference_rollout_worker():
+    """The reference RolloutWorker class (rollout.py:13-491) compiled from its unmodified source; its module-level imports
+    (mpi4py, mujoco_py, baselines.*) are replaced by a one-rank communicator, the reference's own util / queue functions and
+    placeholders for what `goal_selection='random'` never touches."""
+    import functools
+    import importlib.util
+    import inspect
+    import pickle
+    from collections import deque
+    rpath = os.path.join(os.path.dirname(REF), 'rollout.py')
+    rsrc = open(rpath).read()
+    cls = [n for n in ast.parse(rsrc).body if isinstance(n, ast.ClassDef) and n.name == 'RolloutWorker'][0]
+    upath = os.path.join(os.path.dirname(REF), 'util.py')
+    usrc = open(upath).read()
+    ns = {'np': np, 'inspect': inspect, 'functools': functools, 'deque': deque, 'pickle': pickle}
+    for fn in ast.parse(usrc).body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ('store_args', 'convert_episode_to_batch_major'):
+            exec(compile(ast.get_source_segment(usrc, fn), upath, 'exec'), ns)
+    spec = importlib.util.spec_from_file_location('gen_golden_queue', os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), 'oracle', 'gen_golden_queue.py'))
+    gq = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gq)
+
+    class OneRank(object):
+        class COMM_WORLD(object):
+            Get_rank = staticmethod(lambda: 0)
+            Get_size = staticmethod(lambda: 1)
+            gather = staticmethod(lambda x, root=0: [x])
+            bcast = staticmethod(lambda x, root=0: x)
+            scatter = staticmethod(lambda x, root=0: x[0])
+    ns.update(MPI=OneRank, MujocoException=KeyboardInterrupt, CompetenceQueue=gq.import_reference_queue().CompetenceQueue,
+              logger=None, SAGG_RIAC=None)
+    exec(compile(ast.get_source_segment(rsrc, cls), rpath, 'exec'), ns)
+    return ns['RolloutWorker']
+
+
+class _SeededPolicy(object):
+    """get_actions stand-in: float32 actions from the host stream (like DDPG.get_actions, which returns float32)."""
+
+    def __init__(self, dimu):
+        self.dimu = dimu
+
+    def get_actions(self, o, ag, g, task_descr=None, compute_Q=False, noise_eps=0., random_eps=0., use_target_net=False):
+        n = len(np.atleast_2d(o))
+        u = np.random.uniform(-1, 1, (n, self.dimu)).astype(np.float32)
+        u += noise_eps * np.random.randn(n, self.dimu)
+        if n == 1:
+            u = u[0]
+        return [u, np.full((n, 1), float(np.sum(o)), np.float32)] if compute_Q else u
+
+
+@pytest.mark.parametrize('structure,eval_', [('curious', False), ('curious', True), ('flat', False), ('flat', True),
+                                             ('task_experts', False), ('task_experts', True)])
+def test_rollout_worker_equals_reference_class(structure, eval_):
+    """curious_b200.rollout.RolloutWorker against the reference class run live on the same environments, policy stand-in
+    and np.random stream: episodes (values, shapes), CP, episode counter, task / goal assignment, competence, probabilities
+    and the logged statistics after every generate_rollouts call."""
+    from curious_b200.envs import ModularPointEnv
+    from curious_b200.rollout import RolloutWorker
+    from curious_b200.train import configure_dims
+    Ref = _reference_rollout_worker()
+    nb, T, B = 3, 7, 2
+
+    def make_env():
+        return ModularPointEnv(nb, n_controllable=2, max_episode_steps=T)
+    dims = configure_dims(make_env(), structure)
+    state = np.random.get_state()
+    try:
+        workers = []
+        for cls in (Ref, RolloutWorker):
+            np.random.seed(12)
+            if structure == 'task_experts' and eval_:
+                policy = [_SeededPolicy(dims['u']) for _ in range(nb)]
+            else:
+                policy = _SeededPolicy(dims['u'])
+            kw = dict(exploit=eval_, compute_Q=eval_, noise_eps=0.2, random_eps=0.3, structure=structure,
+                      task_selection='active_competence_progress', queue_length=4, eval=eval_, history_len=5,
+                      unique_task=None if eval_ or structure != 'task_experts' else 1)
+            w = cls(make_env, policy, dims, None, T, rollout_batch_size=B, **kw)
+            w.seed(3)
+            workers.append(w)
+        ref, mine = workers
+        for call in range(25):
+            outs = []
+            for w in (ref, mine):
+                np.random.seed(1000 + call)
+                outs.append(w.generate_rollouts() + (np.random.get_state()[1].copy(),))
+            (re, rcp, rn, rstate), (me, mcp, mn, mstate) = outs
+            assert np.array_equal(rstate, mstate), 'np.random consumed differently'
+            assert rn == mn and np.array_equal(np.asarray(rcp, np.float64), np.asarray(mcp, np.float64)), call
+            assert sorted(re.keys()) == sorted(me.keys()), call
+            for k in re:
+                assert np.asarray(re[k]).shape == np.asarray(me[k]).shape, (call, k)
+                assert np.array_equal(np.asarray(re[k], np.float64), np.asarray(me[k], np.float64)), (call, k)
+            assert ref.exploit == mine.exploit
+            if structure != 'flat':
+                assert np.array_equal(np.asarray(ref.p, np.float64), np.asarray(mine.p, np.float64)), call
+                assert np.array_equal(np.asarray(ref.get_C(), np.float64), np.asarray(mine.get_C(), np.float64))
+                assert np.array_equal(np.asarray(ref.get_CP(), np.float64), np.asarray(mine.get_CP(), np.float64))
+                assert [int(t) for t in ref.tasks] == [int(t) for t in mine.tasks]
+                assert all(np.array_equal(a, b) for a, b in zip(ref.goals, mine.goals))
+                assert [int(t) for t in ref.task_history] == [int(t) for t in mine.task_history]
+            assert dict(ref.logs('x')) == dict(mine.logs('x')) and ref.additional_logs('x') == mine.additional_logs('x')
+            assert ref.current_success_rate() == mine.current_success_rate()
+            if eval_:
+                assert ref.current_mean_Q() == mine.current_mean_Q()
+    finally:
+        np.random.set_state(state)
