@@ -13,6 +13,9 @@ are absent).  Built around fixed batch-major arrays instead of per-step Python l
     (rollout.py:316-404) lives in curious_b200.queues.CompetenceTracker; MPI collectives become torch.distributed
     object collectives,
   * SAGG-RIAC goal selection (`goal_selection='active'`) is not supported (readme.md:19 marks it unsupported).
+
+Pinned against the reference class itself, compiled from its unmodified source and run on the same environments and
+np.random stream (tests/test_reference_live.py::test_rollout_worker_equals_reference_class).
 """
 import pickle
 from collections import deque
