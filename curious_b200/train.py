@@ -127,9 +127,12 @@ def make_experiment(nb_tasks=4, n_controllable=None, structure='curious', task_s
                 task_selection=task_selection, eps_task=params.get('eps_task', 0.4), params=run_params)
 
 
-def _evaluate(evaluator, n_test_rollouts):
+def _evaluate(evaluator, n_test_rollouts, clear_competence=False):
+    """train.py:157-160: the evaluator's histories restart every epoch, its competence queues do not (they keep a running
+    window over the evaluation rollouts of all epochs) unless `clear_competence` asks for a per-epoch measurement."""
     evaluator.clear_history()
-    evaluator.clear_competence_queue() if evaluator.modular else None
+    if clear_competence and evaluator.modular:
+        evaluator.clear_competence_queue()
     for _ in range(n_test_rollouts):
         evaluator.generate_rollouts()
     out = dict(test_success_rate=float(evaluator.current_success_rate()), test_mean_Q=float(evaluator.current_mean_Q()))
@@ -217,12 +220,15 @@ class _EpochRecords(object):
 def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles, n_batches, structure='curious',
           task_selection='active_competence_progress', eps_task=0.4, log=None, logdir=None, params=None,
           policy_save_interval=5, save_policies=True, checkpoint_interval=0, echo=False, resume=False,
-          experts_follow_cp=False):
+          experts_follow_cp=False, initial_evaluation=True, clear_eval_competence=False):
     """train.py:48-170: per epoch n_cycles x (rollouts -> store_episode -> n_batches x train -> update_target_net),
     then n_test_rollouts evaluation rollouts.  Returns one dict per epoch; with `logdir` also writes the reference's
     run records (see module docstring).  `resume=True` continues the run whose checkpoints (`checkpoint_interval`) are in
     `logdir` from the epoch after the last one: policies, buffers, optimiser, RNG streams, competence queues and the
-    files pick up where they were (the returned history covers the new epochs)."""
+    files pick up where they were (the returned history covers the new epochs).
+    Like the reference, a fresh run starts with one evaluation of the untrained policy, recorded as epoch -1
+    (train.py:62-75,125-135; `initial_evaluation=False` skips it), and the evaluator's competence queues run over all epochs
+    (`clear_eval_competence=True` restarts them at every evaluation instead)."""
     history = []
     records = None
     start_epoch = 0
@@ -239,6 +245,19 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
             start_epoch = resumed['epoch'] + 1
         records = _EpochRecords(logdir, evaluator, params, policy_save_interval, save_policies, checkpoint_interval, echo,
                                 workers=workers, resumed=resumed)
+    if initial_evaluation and start_epoch == 0:
+        # train.py:62-75 / 125-135: epoch -1.  The experts' branch also restarts the evaluator's competence queues here and
+        # logs the LAST expert's worker and policy (i_policy = -1 indexes the lists from the end)
+        evaluator.clear_history()
+        if structure == 'task_experts' and evaluator.modular:
+            evaluator.clear_competence_queue()
+        for _ in range(n_test_rollouts):
+            evaluator.generate_rollouts()
+        if records:
+            if structure == 'task_experts':
+                records.epoch(-1, rollout_worker[-1], policy, -1)
+            else:
+                records.epoch(-1, rollout_worker, policy)
     if structure == 'task_experts':
         nb_tasks = len(policy)
         p = 1 / nb_tasks * np.ones([nb_tasks])
@@ -275,7 +294,7 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
                 for _ in range(n_batches):
                     policy[i_policy].train()
                 policy[i_policy].update_target_net()
-            rec = dict(epoch=epoch, i_policy=i_policy, p=p.copy(), proba=proba.copy(), **_evaluate(evaluator, n_test_rollouts))
+            rec = dict(epoch=epoch, i_policy=i_policy, p=p.copy(), proba=proba.copy(), **_evaluate(evaluator, n_test_rollouts, clear_eval_competence))
             history.append(rec)
             if log:
                 log(rec)
@@ -291,7 +310,7 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
                 policy.train()
             policy.update_target_net()
         rec = dict(epoch=epoch, train_success_rate=float(rollout_worker.current_success_rate()),
-                   **_evaluate(evaluator, n_test_rollouts))
+                   **_evaluate(evaluator, n_test_rollouts, clear_eval_competence))
         if rollout_worker.modular:
             rec['CP'] = np.asarray(rollout_worker.get_CP(), np.float64).copy()
             rec['p'] = np.asarray(rollout_worker.p, np.float64).copy()

@@ -639,3 +639,103 @@ def test_rollout_worker_equals_reference_class(structure, eval_):
                 assert ref.current_mean_Q() == mine.current_mean_Q()
     finally:
         np.random.set_state(state)
+
+
+def _reference_train_functions(rows, infos, logdir):
+    """train() and logs() of experiment/train.py plus mpi_average / mpi_moments / mpi_mean, compiled from their unmodified
+    source; the logger is a recorder, the communicator has one rank."""
+    import time
+
+    class OneRank(object):
+        SUM = 'sum'
+
+        class COMM_WORLD(object):
+            Get_rank = staticmethod(lambda: 0)
+            Get_size = staticmethod(lambda: 1)
+            bcast = staticmethod(lambda x, root=0: x)
+
+            @staticmethod
+            def Bcast(buf, root=0):
+                pass
+
+            @staticmethod
+            def Allreduce(src, dst, op=None):
+                dst[...] = src
+
+    class Logger(object):
+        row = {}
+        get_dir = staticmethod(lambda: logdir)
+        info = staticmethod(lambda *a: infos.append(' '.join(str(x) for x in a)))
+
+        @classmethod
+        def record_tabular(cls, k, v):
+            cls.row[k] = v
+
+        @classmethod
+        def dump_tabular(cls):
+            rows.append(dict(cls.row))
+            cls.row = {}
+    ns = {'np': np, 'os': os, 'time': time, 'MPI': OneRank, 'logger': Logger, 't0': time.time()}
+    here = os.path.dirname(REF)
+    for path, names in ((os.path.join(here, '..', 'common', 'mpi_moments.py'), ('mpi_mean', 'mpi_moments')),
+                        (os.path.join(here, 'util.py'), ('mpi_average',)),
+                        (os.path.join(here, 'experiment', 'train.py'), ('train', 'logs'))):
+        src = open(path).read()
+        for fn in ast.parse(src).body:
+            if isinstance(fn, ast.FunctionDef) and fn.name in names:
+                exec(compile(ast.get_source_segment(src, fn), path, 'exec'), ns)
+    return ns['train']
+
+
+@pytest.mark.parametrize('structure', ['curious', 'flat', 'task_experts'])
+def test_train_loop_and_records_equal_reference_functions(structure, tmp_path):
+    """curious_b200.train.train against the reference's train() + logs() run live (experiment/train.py:48-215) with the same
+    workers, policy stand-ins and np.random stream: the order of rollouts / store / updates / evaluations (through the RNG
+    stream and the call counters), every tabular row key by key (except Time), and the policy files written."""
+    from tests.test_train_loop_cpu import _workers
+    from curious_b200.train import train
+    n_epochs, kw = 4, dict(n_test_rollouts=2, n_cycles=3, n_batches=2)
+    results = []
+    state = np.random.get_state()
+    try:
+        for which in ('reference', 'mine'):
+            logdir = str(tmp_path / which)
+            os.makedirs(logdir)
+            np.random.seed(6)
+            policy, rollout, evaluator, _ = _workers(structure)
+            for i, w in enumerate((rollout if isinstance(rollout, list) else [rollout]) + [evaluator]):
+                w.seed(70 + i)
+            np.random.seed(31)
+            rows, infos = [], []
+            if which == 'reference':
+                # NumPy >= 2 shim at the boundary, the reference code itself stays untouched: its mpi_average starts with
+                # `if value == []`, which raises for an np.float64 operand today (it was False with a warning in NumPy 1),
+                # so the workers hand it plain Python floats
+                for w in (rollout if isinstance(rollout, list) else [rollout]) + [evaluator]:
+                    w.logs = (lambda prefix, w=w, f=w.logs: [(k, float(v) if isinstance(v, np.floating) else v)
+                                                             for k, v in f(prefix)])
+                    w.current_success_rate = (lambda w=w, f=w.current_success_rate: float(f()))
+                ref_train = _reference_train_functions(rows, infos, logdir)
+                ref_train(policy, rollout, evaluator, n_epochs, policy_save_interval=2, save_policies=True, structure=structure,
+                          task_selection='active_competence_progress', params={'nb_tasks': 3, 'eps_task': 0.4},
+                          perturbation_study=False, **kw)
+            else:
+                train(policy, rollout, evaluator, n_epochs, structure=structure, logdir=logdir, policy_save_interval=2, **kw)
+                lines = open(os.path.join(logdir, 'progress.csv')).read().splitlines()
+                header = lines[0].split(',')
+                rows = [{k: v for k, v in zip(header, line.split(',')) if v != ''} for line in lines[1:]]
+            pols = policy if isinstance(policy, list) else [policy]
+            results.append(dict(rows=rows, counters=[(p.trained, p.target_updates, len(p.stored)) for p in pols],
+                                rng=np.random.get_state()[1].copy(),
+                                files=sorted(f for f in os.listdir(logdir) if f.startswith('policy_'))))
+        ref, mine = results
+        assert ref['counters'] == mine['counters'] and np.array_equal(ref['rng'], mine['rng'])
+        assert ref['files'] == mine['files'] and 'policy_best.pkl' in mine['files'] and 'policy_2.pkl' in mine['files']
+        assert len(ref['rows']) == len(mine['rows']) == n_epochs + 1                      # epoch -1 .. 3
+        for r, m in zip(ref['rows'], mine['rows']):
+            assert [k for k in r if k != 'Time'] == [k for k in m if k != 'Time'], (r, m)
+            for k in r:
+                if k != 'Time':
+                    assert str(r[k]) == m[k], (k, r[k], m[k])
+    finally:
+        np.random.set_state(state)

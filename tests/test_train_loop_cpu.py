@@ -78,7 +78,9 @@ def test_loop_counts_and_records(structure, tmp_path):
     assert policy.stored[0][0] == (2, 9, dims['o']) and policy.stored[-1][2] == 12 * 2
     lines = open(str(tmp_path / 'progress.csv')).read().splitlines()
     header = lines[0].split(',')
-    assert len(lines) == 4 and header[0] == 'epoch' and header[-1] == 'Time'
+    assert len(lines) == 5 and header[0] == 'epoch' and header[-1] == 'Time'          # epoch -1 (untrained policy), 0, 1, 2
+    first = dict(zip(header, lines[1].split(',')))
+    assert first['epoch'] == '-1' and first['train/success_rate'] == 'nan' and first['train/episode'] == '0'
     for col in ('test/success_rate', 'test/mean_Q', 'train/success_rate', 'train/episode', 'stats_o/mean'):
         assert col in header, col
     row = dict(zip(header, lines[-1].split(',')))

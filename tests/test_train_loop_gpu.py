@@ -14,7 +14,8 @@ def test_curious_agent_learns_reach_and_lp_follows():
     exp = make_experiment(nb_tasks=4, n_controllable=3, structure='curious', task_selection='active_competence_progress',
                           task_replay='replay_task_cp_buffer', buffer_size=100000, n_cycles=10, n_batches=40,
                           n_test_rollouts=10, seed=0)
-    hist = train(n_epochs=12, **exp)
+    # (per-epoch competence of the evaluator and no epoch -1 evaluation: the sharper signal for this behavioural check)
+    hist = train(n_epochs=12, initial_evaluation=False, clear_eval_competence=True, **exp)
     assert len(hist) == 12
     C = np.array([h['C'] for h in hist])
     # module 0 (reach) is learned, the distractor (module 3: the object moves on its own) is not
@@ -38,7 +39,8 @@ def test_other_structures_run_the_same_loop(structure, task_replay, tmp_path):
     exp = make_experiment(nb_tasks=3, structure=structure, task_selection='active_competence_progress',
                           task_replay=task_replay, buffer_size=50000, n_cycles=4, n_batches=10, n_test_rollouts=2, seed=1,
                           policy_kwargs=dict(action_noise='device') if structure == 'flat' else None)
-    hist = train(n_epochs=3, logdir=str(tmp_path), policy_save_interval=2, checkpoint_interval=2, **exp)
+    hist = train(n_epochs=3, logdir=str(tmp_path), policy_save_interval=2, checkpoint_interval=2, initial_evaluation=False,
+                 clear_eval_competence=True, **exp)
     _check_run_records(str(tmp_path), structure, exp)
     assert len(hist) == 3 and all(0.0 <= h['test_success_rate'] <= 1.0 for h in hist)
     pols = exp['policy'] if isinstance(exp['policy'], list) else [exp['policy']]
@@ -89,7 +91,8 @@ def test_resumed_training_equals_uninterrupted(tmp_path):
         exp = make_experiment(nb_tasks=3, structure='curious', task_selection='active_competence_progress',
                               task_replay='replay_task_cp_buffer', buffer_size=2000, n_cycles=3, n_batches=8,
                               n_test_rollouts=2, seed=4)
-        hist = train(n_epochs=n_epochs, logdir=logdir, policy_save_interval=0, checkpoint_interval=1, resume=resume, **exp)
+        hist = train(n_epochs=n_epochs, logdir=logdir, policy_save_interval=0, checkpoint_interval=1, resume=resume,
+                     initial_evaluation=False, clear_eval_competence=True, **exp)
         return hist, exp['policy']
 
     full, pol_full = run(str(tmp_path / 'full'), 4, seed=3)
