@@ -102,8 +102,9 @@ def make_experiment(nb_tasks=4, n_controllable=None, structure='curious', task_s
                    task_replay=task_replay, eps_task=params.get('eps_task'), structure=structure, her_rng='philox',
                    seed=seed, device=device)
     ddpg_kw.update(policy_kwargs or {})             # this implementation's extras: action_noise, update_schedule, comm, ...
+    buffer_size = (params['buffer_size'] // params['rollout_batch_size']) * params['rollout_batch_size']    # config.py:204
     buffers = configure_buffer({k: v for k, v in dims.items() if structure != 'flat' or k != 'task_descr'}, T, sampler,
-                               params['buffer_size'], structure, task_replay, nb_tasks, device=device)
+                               buffer_size, structure, task_replay, nb_tasks, device=device)
     rollout_kw = dict(dims=dims, logger=None, T=T, rollout_batch_size=params['rollout_batch_size'], structure=structure,
                       task_selection=task_selection, queue_length=params['queue_length'])
     explore = dict(rollout_kw, exploit=False, use_target_net=False, compute_Q=False, noise_eps=params['noise_eps'],
