@@ -5,9 +5,10 @@ Pinning (the reference has no tests for baselines/her/, and TensorFlow 1.x / mpi
   * PINNED against the reference's own code executed live (tests/test_reference_live.py cuts the NumPy-only methods out of
     the unmodified ddpg.py / normalizer.py and runs them on recording stubs): sample_batch incl. the LP apportioning,
     concatenation and shuffle, store_episode routing and its normaliser batch, get_actions post-processing,
-    _preprocess_og, Normalizer.update / synchronize / snapshot-and-reset;
+    _preprocess_og, Normalizer.update / synchronize / snapshot-and-reset, MpiAdam.update (with NumPy-1 scalar casting
+    reproduced at the boundary);
   * PARITY UNPINNED (restated from the TF1 graph definitions): network forward, losses and gradients, the running-sum /
-    mean / std half of Normalizer, MpiAdam arithmetic, polyak.  tests/test_host_logic.py cross-checks the hand-written
+    mean / std half of Normalizer, polyak.  tests/test_host_logic.py cross-checks the hand-written
     backward pass against torch autograd and Adam against the reference's `test_MpiAdam` problem definition
     (mpi_adam.py:54-63).
 Each function cites the reference lines it restates.

@@ -739,3 +739,66 @@ def test_train_loop_and_records_equal_reference_functions(structure, tmp_path):
                     assert str(r[k]) == m[k], (k, r[k], m[k])
     finally:
         np.random.set_state(state)
+
+
+@pytest.mark.parametrize('scale_grad_by_procs', [False, True])
+def test_adam_oracle_equals_reference_update(scale_grad_by_procs):
+    """MpiAdam.update (common/mpi_adam.py:21-35) live against oracle.ddpg_oracle.MpiAdamOracle over 150 steps of a 3-rank
+    world.  The reference ran on NumPy 1.x, whose value-based casting kept `(-a) * self.m` in float32 although `a` is an
+    np.float64; NumPy >= 2 would promote that product to float64.  The one shim reproduces the old rule at the boundary:
+    np.sqrt of a Python float hands back a Python float (a weak scalar today), everything else is NumPy as is."""
+    from oracle.ddpg_oracle import MpiAdamOracle
+    apath = os.path.join(os.path.dirname(REF), '..', 'common', 'mpi_adam.py')
+    asrc = open(apath).read()
+    cls = [n for n in ast.parse(asrc).body if isinstance(n, ast.ClassDef) and n.name == 'MpiAdam'][0]
+    update_src = [ast.get_source_segment(asrc, fn) for fn in cls.body if isinstance(fn, ast.FunctionDef) and fn.name == 'update'][0]
+
+    class NumPy1Scalars(object):
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+        @staticmethod
+        def sqrt(x):
+            return float(np.sqrt(x)) if isinstance(x, float) else np.sqrt(x)
+    peers = []
+
+    class Comm(object):
+        @staticmethod
+        def Allreduce(src, dst, op=None):
+            dst[...] = src + peers[0] + peers[1]
+
+        @staticmethod
+        def Get_size():
+            return 3
+
+    class MPI(object):
+        SUM = 'sum'
+    ns = {'np': NumPy1Scalars(), 'MPI': MPI}
+    exec(compile(textwrap.dedent(update_src), apath, 'exec'), ns)
+    rng = np.random.RandomState(2)
+    n = 4097
+    theta0 = rng.standard_normal(n).astype(np.float32)
+    ref = _Self()
+    ref.beta1, ref.beta2, ref.epsilon, ref.scale_grad_by_procs, ref.comm = 0.9, 0.999, 1e-08, scale_grad_by_procs, Comm
+    ref.m, ref.v, ref.t = np.zeros(n, 'float32'), np.zeros(n, 'float32'), 0
+    ref.theta = theta0.copy()
+    ref.check_synced = lambda: None
+    ref.getflat = lambda: ref.theta.copy()
+
+    def setfromflat(x):
+        assert x.dtype == np.float32, 'the NumPy-1 rule keeps the step in float32'
+        ref.theta = np.asarray(x, np.float32)
+    ref.setfromflat = setfromflat
+    ora = MpiAdamOracle(theta0, scale_grad_by_procs=scale_grad_by_procs, world_size=3,
+                        allreduce_sum=lambda g: g + peers[0] + peers[1])
+    for step in range(150):
+        grads = [(rng.standard_normal(n) * 10 ** rng.uniform(-6, 1)).astype(np.float32) for _ in range(3)]
+        if step % 17 == 0:
+            grads[0][::5] = 0.0                                  # exact zeros: sqrt(v) + eps carries the step
+        peers[:] = grads[1:]
+        ns['update'](ref, grads[0].astype(np.float64) if step % 2 else grads[0], 1e-3)
+        ora.update(grads[0], 1e-3)
+        assert ref.t == ora.t
+        assert np.array_equal(ref.m, ora.m) and np.array_equal(ref.v, ora.v), step
+        assert np.array_equal(ref.theta, ora.theta), step
+    assert not np.array_equal(ref.theta, theta0)
