@@ -284,3 +284,30 @@ def test_product_slot_policy_equals_the_live_reference():
                 mine._get_storage_idx(size_ep + 1)
     finally:
         np.random.set_state(state)
+
+
+def test_host_draws_replay_the_reference_stream():
+    """curious_b200.her.HostDraws (the `her_rng='numpy'` path: the reference's np.random draws made on the host in reference
+    order, her.py:108-116,129-142) against the RNG stream recorded from the unmodified reference in every fixture."""
+    from curious_b200 import her
+    from tests.golden_util import load_case, sampler_cases
+    state = np.random.get_state()
+    try:
+        n_choice_cases = 0
+        for name in sampler_cases():
+            meta, eps, stream, ref = load_case(name)
+            np.random.seed(meta['seed'])
+            d = her.HostDraws(meta['E'], meta['T'], meta['B'])
+            d.draw_choices(her.mode_of(meta['task_replay'], meta['flat']),
+                           her.future_probability(meta['goal_replay'], meta['her_replay_k']), meta['n_modules'], meta['cp_proba'])
+            assert np.array_equal(d.ep, stream['s_ep']) and np.array_equal(d.t, stream['s_t']), name
+            assert np.array_equal(d.u_her, stream['s_uher']) and np.array_equal(d.u_off, stream['s_uoff']), name
+            seq = stream['s_choice_seq']
+            if seq.size:
+                n_choice_cases += 1
+                assert np.array_equal(d.choice[d.choice >= 0], seq), name
+            else:
+                assert d.choice is None or (d.choice < 0).all(), name
+        assert n_choice_cases >= 5
+    finally:
+        np.random.set_state(state)
