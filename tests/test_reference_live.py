@@ -238,6 +238,9 @@ def test_oracle_store_episode_equals_reference_method(structure, task_replay, nb
                 assert a.keys() == b.keys()
                 for k in a:
                     assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), (case, k)
+            if 'buffer' in task_replay:                                             # the product's routing rule as well
+                want = [j + 1 for e in range(2) for j in apportion.active_modules(eps['change'][e, -1], ag_ids, g_ids)]
+                assert [i for i, _ in rl] == want, case
             if nb_tasks >= 5 and 'buffer' in task_replay:
                 assert all(i <= 5 for i, _ in rl)                                   # ddpg.py:183: modules 5.. are never stored
             assert [(n, what) for n, what, _ in rs] == [(n, what) for n, what, _ in os_]
