@@ -170,7 +170,7 @@ def test_oracle_equals_the_live_reference_on_random_scenarios(tmp_path):
     rng = np.random.RandomState(20241017)
     state = np.random.get_state()
     modes = ['replay_task_cp_buffer', 'replay_task_random_buffer', 'replay_random_task_transition',
-             'replay_cp_task_transition', 'replay_current_task_transition']
+             'replay_cp_task_transition', 'replay_current_task_transition', 'hand_designed']
     try:
         for i in range(60):
             flat = bool(rng.rand() < 0.2)
@@ -181,7 +181,7 @@ def test_oracle_equals_the_live_reference_on_random_scenarios(tmp_path):
                       goal_replay='her' if rng.rand() < 0.8 else 'none', task_replay=mode, flat=flat,
                       longer_ag=bool(rng.rand() < 0.3) and not flat, via_buffer=bool(rng.rand() < 0.7))
             if not flat:
-                if 'buffer' in mode and rng.rand() < 0.7:
+                if ('buffer' in mode or mode == 'hand_designed') and rng.rand() < 0.7:
                     kw['task_to_replay'] = int(rng.randint(n_modules))
                 if mode == 'replay_cp_task_transition':
                     p = rng.rand(n_modules) + 0.05
