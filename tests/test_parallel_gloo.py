@@ -342,3 +342,45 @@ def test_excepthook_leaves_with_nonzero_status():
             "raise ValueError('boom')\n") % ROOT
     res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
     assert res.returncode == 1 and 'ValueError: boom' in res.stderr and 'atexit ran' not in res.stdout
+
+
+def _body_resume(rank, world):
+    """train(resume=True) on two ranks: every rank restores its own checkpoint / run_state files and the run continues
+    exactly like the uninterrupted one (tasks and goals keep coming from rank 0, CP / p stay identical everywhere)."""
+    import tempfile
+    from curious_b200 import parallel
+    from curious_b200.train import train
+    from tests.test_train_loop_cpu import _workers
+    box = [[tempfile.mkdtemp(), tempfile.mkdtemp()] if rank == 0 else None]
+    torch.distributed.broadcast_object_list(box, src=0)
+    full_dir, split_dir = box[0]
+
+    def run(logdir, n_epochs, seed, resume=False):
+        np.random.seed(parallel.rank_seed(seed, rank))
+        policy, rollout, evaluator, _ = _workers('curious')
+        for i, w in enumerate([rollout, evaluator]):
+            w.seed(50 + 10 * i + 100 * rank)
+        hist = train(policy, rollout, evaluator, n_epochs=n_epochs, n_test_rollouts=2, n_cycles=2, n_batches=1,
+                     structure='curious', logdir=logdir, policy_save_interval=0, checkpoint_interval=1, resume=resume)
+        return hist, policy
+    full, pol_full = run(full_dir, 4, seed=3)
+    run(split_dir, 2, seed=3)
+    tail, pol_tail = run(split_dir, 4, seed=77, resume=True)
+    assert [h['epoch'] for h in tail] == [2, 3]
+    for a, b in zip(full[2:], tail):
+        for key in a:
+            assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), (rank, a['epoch'], key)
+    assert pol_full.trained == pol_tail.trained
+    torch.distributed.barrier()
+    files = sorted(os.listdir(split_dir))
+    assert 'checkpoint_0.pt' in files and 'checkpoint_0_rank1.pt' in files and 'run_state_rank1.pkl' in files
+    out = [h['test_success_rate'] for h in tail] + list(tail[-1]['p']) + list(tail[-1]['CP'])
+    if rank == 0:
+        rows = open(os.path.join(split_dir, 'progress.csv')).read().splitlines()
+        assert [r.split(',')[0] for r in rows[1:]] == ['-1', '0', '1', '2', '3']
+    return out
+
+
+def test_resume_on_two_ranks(tmp_path):
+    r0, r1 = _run('_body_resume', tmp_path)
+    assert np.array_equal(r0[2:], r1[2:])                  # p and CP are broadcast: identical on both ranks
