@@ -311,3 +311,23 @@ def test_host_draws_replay_the_reference_stream():
         assert n_choice_cases >= 5
     finally:
         np.random.set_state(state)
+
+
+def test_library_sass_is_blackwell_native():
+    """B200_PROFILING.md "What proves a Blackwell-native kernel": the SASS of the in-tree library holds tcgen05 MMAs
+    (UTC*MMA) with TMEM loads (LDTM), TMA tensor and bulk copies (UTMALDG / UBLKCP) with their mbarrier waits (SYNCS), the
+    cta_group::2 commit of the pair kernel (UTCBAR.2CTA) and packed FP32 FMAs (FFMA2) - and no legacy HMMA tensor path."""
+    import shutil
+    import subprocess
+    from curious_b200 import _lib
+    tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(tool) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip('cuobjdump or the built library is not available')
+    sass = subprocess.run([tool, '-sass', _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert 'sm_100a' in sass
+    import re
+    count = lambda pattern: len(re.findall(pattern, sass))
+    assert count(r'\bUTC[A-Z]*MMA') >= 6                 # 3xTF32: three MMAs per k-step, single-CTA and pair kernels
+    assert count(r'\bLDTM') >= 8 and count(r'\bUTMALDG') >= 8 and count(r'\bUBLKCP') >= 1
+    assert count(r'\bUTCBAR\.2CTA') >= 1 and count(r'\bSYNCS\.') >= 20 and count(r'\bFFMA2\b') >= 500
+    assert count(r'\bHMMA\b') == 0 and count(r'\bHGMMA\b') == 0
