@@ -805,3 +805,19 @@ def test_adam_oracle_equals_reference_update(scale_grad_by_procs):
         assert np.array_equal(ref.m, ora.m) and np.array_equal(ref.v, ora.v), step
         assert np.array_equal(ref.theta, ora.theta), step
     assert not np.array_equal(ref.theta, theta0)
+
+
+def test_default_hyperparameters_equal_reference_config():
+    """experiment/config.py:18-87 DEFAULT_PARAMS / MULTI_TASK_PARAMS (evaluated from the unmodified assignments) against
+    the dictionaries curious_b200.train.make_experiment starts from."""
+    from curious_b200 import train as mine
+    cpath = os.path.join(os.path.dirname(REF), 'experiment', 'config.py')
+    csrc = open(cpath).read()
+    ns = {}
+    for node in ast.parse(csrc).body:
+        if isinstance(node, ast.Assign) and getattr(node.targets[0], 'id', '') in ('DEFAULT_PARAMS', 'MULTI_TASK_PARAMS'):
+            exec(compile(ast.get_source_segment(csrc, node), cpath, 'exec'), ns)
+    assert mine.MULTI_TASK_PARAMS == ns['MULTI_TASK_PARAMS']
+    flat = dict(mine.FLAT_PARAMS)
+    assert flat.pop('eps_task') == 0.4                     # not in the reference's flat defaults; unused by the flat agent
+    assert flat == ns['DEFAULT_PARAMS']
