@@ -91,12 +91,19 @@ class DdpgExpert(C.Structure):
                 ('grads', C.c_void_p), ('q_loss', C.c_void_p), ('pi_loss', C.c_void_p), ('q_pi', C.c_void_p)]
 
 
+CUR_MAX_RANKS = 8
+
+
+class XchgCtx(C.Structure):
+    _fields_ = [('rank', C.c_int32), ('world', C.c_int32), ('mode', C.c_int32), ('_pad', C.c_int32),
+                ('region', C.c_void_p * CUR_MAX_RANKS), ('arena', C.c_int64), ('timeline', C.c_void_p),
+                ('error_flag', C.c_void_p)]
+
+
 class AdamFused(C.Structure):
     _fields_ = [('m', C.c_void_p), ('v', C.c_void_p), ('neg_a_table', C.c_void_p), ('table_len', C.c_int32),
-                ('transposes_valid', C.c_int32), ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double)]
-
-
-CUR_MAX_RANKS = 8
+                ('transposes_valid', C.c_int32), ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double),
+                ('xchg', C.POINTER(XchgCtx))]
 
 
 CUR_P2P_MAX_TRANSPOSES = 8
@@ -163,11 +170,14 @@ SIGNATURES = {
     'cur_tc_gemm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                               C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                               C.c_void_p]),
+    'cur_ddpg_rows_owner_map': (C.c_int, [C.POINTER(NetDesc), C.c_int64, C.c_int, C.c_void_p]),
+    'cur_xchg_region_bytes': (C.c_int64, [C.c_int64, C.c_int]),
     'cur_p2p_region_bytes': (C.c_int64, [C.c_int64]),
     'cur_p2p_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
     'cur_p2p_open': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     'cur_p2p_close': (C.c_int, [C.c_void_p]),
     'cur_p2p_free': (C.c_int, [C.c_void_p]),
+    'cur_p2p_zero': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     'cur_p2p_allreduce_adam': (C.c_int, [C.c_void_p, C.POINTER(P2PCtx), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
                                          C.c_void_p]),

@@ -690,6 +690,42 @@ __global__ void __launch_bounds__(256) transpose_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // launch 2: all weight gradients (+ optional Adam), loss fold, step counter
 // ------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------- tile-level gradient exchange (several ranks)
+// cur_xchg_ctx resolved for the device: every element travels as ONE naturally aligned 8-byte word
+// {float32 bits | update number << 32} ("LL" protocol): a scalar 64-bit store is single-copy atomic, so the
+// receiver polls the data words themselves - no flag round, no system fence on the critical path.
+struct XchgDev {
+  int rank, world, mode;
+  unsigned long long* part[CUR_MAX_RANKS];   // partial slots of rank r's region: [world][arena]
+  unsigned long long* res[CUR_MAX_RANKS];    // result slots of rank r's region: [arena]
+  int64_t arena;
+  long long* tl;                             // optional [tiles][4] %globaltimer stamps
+  int* error_flag;
+};
+
+__device__ __forceinline__ void st_ll(unsigned long long* p, float v, uint32_t flag) {
+  const unsigned long long w = ((unsigned long long)flag << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// a peer that does not show up for ~20 s is dead or diverged: fail loudly (the host sees a launch failure)
+__device__ __noinline__ void xchg_timeout_check(unsigned long long t0, int* error_flag) {
+  if (globaltimer_ns() - t0 > 20000000000ull) {
+    if (error_flag) *error_flag = 1;
+    __threadfence_system();
+    __trap();
+  }
+}
+
 struct DwTail {
   AdamCtx ax;                      // ax.theta == NULL: gradients only
   const float* neg_a_table;
@@ -709,7 +745,160 @@ struct DwTail {
   int micro;                       // micro-batches (workers) per update: launch j = step % micro accumulates for j > 0
   int chunk, last_chunk;           // batches > 256 rows: one launch per 256-row K chunk; chunks > 0 accumulate, only the
                                    // last one runs the optimiser epilogue, folds the losses and bumps the step counter
+  int xc_on;                       // several ranks: exchange the tiles with the peers before the step (xc)
+  XchgDev xc;
 };
+
+// Epilogue context of one CTA (shared memory), resolved once from DwTail and the device step counter.
+struct DwCtx {
+  AdamCtx ax;
+  int opt;                         // the optimiser runs in this launch (last chunk, last micro-batch of the update)
+  int xc_on;                       // ... after the tile went through the exchange
+  int own;                         // this rank reduces the tile
+  int owner;                       // the rank that does (mode 1)
+  uint32_t flag;                   // update number travelling with the data
+  long long* tl;                   // this tile's stamps or NULL
+};
+
+// Sum of the world's partial tiles in rank order (bit-identical on every reducer): g[e] holds this rank's partial on
+// entry and the sum on return.  All peers' words of two elements are requested before the first check, so a tile
+// whose data has landed costs two L2 round trips, not 4 x (W - 1).
+template <int NE>
+__device__ __forceinline__ void xchg_reduce(const XchgDev& xc, uint32_t flag, const int64_t (&off)[NE],
+                                            const bool (&ok)[NE], float (&g)[NE]) {
+  const unsigned long long* mine = xc.part[xc.rank];
+  constexpr int EB = NE >= 2 ? 2 : 1;
+#pragma unroll
+  for (int e0 = 0; e0 < NE; e0 += EB) {
+    unsigned long long x[EB][CUR_MAX_RANKS];
+    bool all;
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    do {
+      all = true;
+#pragma unroll
+      for (int q = 0; q < EB; ++q)
+#pragma unroll
+        for (int r = 0; r < CUR_MAX_RANKS; ++r)
+          if (r < xc.world && r != xc.rank && ok[e0 + q]) x[q][r] = ld_ll(mine + (int64_t)r * xc.arena + off[e0 + q]);
+#pragma unroll
+      for (int q = 0; q < EB; ++q)
+#pragma unroll
+        for (int r = 0; r < CUR_MAX_RANKS; ++r)
+          if (r < xc.world && r != xc.rank && ok[e0 + q]) all = all && ((uint32_t)(x[q][r] >> 32) == flag);
+      if (!all && (++spins & 0x3FFFu) == 0) {
+        if (t0 == 0) t0 = globaltimer_ns();
+        xchg_timeout_check(t0, xc.error_flag);
+      }
+    } while (!all);
+#pragma unroll
+    for (int q = 0; q < EB; ++q) {
+      if (!ok[e0 + q]) continue;
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < CUR_MAX_RANKS; ++r)
+        if (r < xc.world) {
+          const float xr = (r == xc.rank) ? g[e0 + q] : __uint_as_float((uint32_t)x[q][r]);
+          s = (r == 0) ? xr : __fadd_rn(s, xr);
+        }
+      g[e0 + q] = s;
+    }
+  }
+}
+
+// mode 1, not the owner: the stepped parameters of the tile as pushed by the owner
+template <int NE>
+__device__ __forceinline__ void xchg_wait_result(const XchgDev& xc, uint32_t flag, const int64_t (&off)[NE],
+                                                 const bool (&ok)[NE], float (&th)[NE]) {
+  const unsigned long long* mine = xc.res[xc.rank];
+  unsigned long long x[NE];
+  bool all;
+  unsigned int spins = 0;
+  unsigned long long t0 = 0;
+  do {
+    all = true;
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (ok[e]) x[e] = ld_ll(mine + off[e]);
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (ok[e]) all = all && ((uint32_t)(x[e] >> 32) == flag);
+    if (!all && (++spins & 0x3FFFu) == 0) {
+      if (t0 == 0) t0 = globaltimer_ns();
+      xchg_timeout_check(t0, xc.error_flag);
+    }
+  } while (!all);
+#pragma unroll
+  for (int e = 0; e < NE; ++e)
+    if (ok[e]) th[e] = __uint_as_float((uint32_t)x[e]);
+}
+
+// The end of every weight-gradient element: local gradient (accumulated over micro-batches / K chunks), exchange with
+// the peers, Adam.  v[e] is the tile value of this launch, c[e] its place in the local gradient arena; th[e] returns
+// the stepped parameter (undefined unless cx.opt).
+template <int NE>
+__device__ __forceinline__ void dw_finish(const DwTail& T, const DwCtx& cx, float* const (&c)[NE], const bool (&ok)[NE],
+                                          bool accumulate, float (&v)[NE], float (&th)[NE]) {
+  int64_t off[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    off[e] = 0; th[e] = 0.f;
+    if (ok[e]) {
+      if (accumulate) v[e] += *c[e];   // micro-batch j > 0 / K chunk > 0 adds to the running sum
+      *c[e] = v[e];
+      off[e] = c[e] - cx.ax.grads;
+    }
+  }
+  if (!cx.opt) return;
+  if (cx.xc_on) {
+    const XchgDev& xc = T.xc;
+    if (cx.tl && threadIdx.x == 0) cx.tl[1] = (long long)globaltimer_ns();
+    if (xc.mode == 0) {
+#pragma unroll
+      for (int r = 0; r < CUR_MAX_RANKS; ++r)
+        if (r < xc.world && r != xc.rank) {
+          unsigned long long* dst = xc.part[r] + (int64_t)xc.rank * xc.arena;
+#pragma unroll
+          for (int e = 0; e < NE; ++e)
+            if (ok[e]) st_ll(dst + off[e], v[e], cx.flag);
+        }
+    } else if (!cx.own) {
+      unsigned long long* dst = xc.part[cx.owner] + (int64_t)xc.rank * xc.arena;
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        if (ok[e]) st_ll(dst + off[e], v[e], cx.flag);
+    }
+    if (cx.own) {
+      xchg_reduce<NE>(xc, cx.flag, off, ok, v);
+      if (cx.tl && threadIdx.x == 0) cx.tl[2] = (long long)globaltimer_ns();
+    } else {
+      xchg_wait_result<NE>(xc, cx.flag, off, ok, th);
+      if (cx.tl && threadIdx.x == 0) cx.tl[2] = (long long)globaltimer_ns();
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        if (ok[e]) cx.ax.theta[off[e]] = th[e];
+      return;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e)
+    if (ok[e]) {
+      float t = cx.ax.theta[off[e]], mm = cx.ax.m[off[e]], vv = cx.ax.v[off[e]];
+      adam_elem(t, v[e], mm, vv, cx.ax.neg_a, cx.ax.b1, cx.ax.omb1, cx.ax.b2, cx.ax.omb2, cx.ax.eps);
+      cx.ax.theta[off[e]] = t; cx.ax.m[off[e]] = mm; cx.ax.v[off[e]] = vv;
+      th[e] = t;
+    }
+  if (cx.xc_on && T.xc.mode == 1) {
+    const XchgDev& xc = T.xc;
+#pragma unroll
+    for (int r = 0; r < CUR_MAX_RANKS; ++r)
+      if (r < xc.world && r != xc.rank) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+          if (ok[e]) st_ll(xc.res[r] + off[e], th[e], cx.flag);
+      }
+  }
+}
 
 // Tile kinds of the weight-gradient launch (K = batch <= 256 is the reduction dimension):
 //   DW_FULLK   C[32x32 tile] = A^T B, A = X [K][M] and B = dY [K][N] both staged for the WHOLE K with one burst of
@@ -724,22 +913,8 @@ constexpr int DW_KMAX = 256;
 constexpr int DW_LD = GT + 4;                                   // row stride of a staged [k][32] tile
 constexpr size_t DW_SMEM_BYTES = (size_t)2 * DW_KMAX * DW_LD * 4;
 
-// Returns the parameter after the fused Adam step (undefined without `ax`).
-__device__ __forceinline__ float dw_store(float* c, float v, const AdamCtx* ax, bool accumulate = false) {
-  if (accumulate) v += *c;         // micro-batch j > 0 of a several-workers-per-rank update adds to the running sum
-  *c = v;
-  float th = 0.f;
-  if (ax) {
-    const int64_t off = c - ax->grads;
-    th = ax->theta[off];
-    float mm = ax->m[off], vv = ax->v[off];
-    adam_elem(th, v, mm, vv, ax->neg_a, ax->b1, ax->omb1, ax->b2, ax->omb2, ax->eps);
-    ax->theta[off] = th; ax->m[off] = mm; ax->v[off] = vv;
-  }
-  return th;
-}
-
-__device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, float* Bs, int m0, int n0, const AdamCtx* ax) {
+__device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, float* Bs, int m0, int n0, const DwTail& T,
+                                              const DwCtx& cx) {
   const int tid = threadIdx.x;
   // ---- stage A[k][m0..m0+32) and B[k][n0..n0+32) for every k (zero fill past the edges)
 #pragma unroll
@@ -784,22 +959,30 @@ __device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, floa
   // hidden layers with the fused optimiser: keep W^T (the backward operand of the next update's stream kernel) current
   // right here instead of re-transposing every update; the stepped tile is turned in shared memory (Bs is free by
   // now) so that the transposed stores are as coalesced as the direct ones
-  const bool keep_t = ax != nullptr && P.C2 != nullptr;
+  const bool keep_t = cx.opt && P.C2 != nullptr;
   float* tt = Bs;                        // [32 n][33]
+  constexpr int NE = (GT * GT) / GEMM_THREADS;
+  float* c[NE];
+  bool ok[NE];
+  float v[NE], th[NE];
 #pragma unroll
-  for (int j = 0; j < (GT * GT) / GEMM_THREADS; ++j) {
+  for (int j = 0; j < NE; ++j) {
     const int i = tid + j * GEMM_THREADS;
     const int gm = m0 + (i >> 5), gn = n0 + (i & 31);
-    if (gm < P.M && gn < P.N) {
-      const float v = (red[i] + red[GT * GT + i]) + (red[2 * GT * GT + i] + red[3 * GT * GT + i]);
-      const float th = dw_store(P.C + (int64_t)gm * P.ldc + gn, v, ax, P.accumulate != 0);
-      if (keep_t) tt[(i & 31) * (GT + 1) + (i >> 5)] = th;
-    }
+    ok[j] = gm < P.M && gn < P.N;
+    c[j] = P.C + (int64_t)gm * P.ldc + gn;
+    v[j] = (red[i] + red[GT * GT + i]) + (red[2 * GT * GT + i] + red[3 * GT * GT + i]);
   }
+  dw_finish<NE>(T, cx, c, ok, P.accumulate != 0, v, th);
   if (keep_t) {
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      const int i = tid + j * GEMM_THREADS;
+      if (ok[j]) tt[(i & 31) * (GT + 1) + (i >> 5)] = th[j];
+    }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < (GT * GT) / GEMM_THREADS; ++j) {
+    for (int j = 0; j < NE; ++j) {
       const int i = tid + j * GEMM_THREADS;
       const int gn = n0 + (i >> 5), gm = m0 + (i & 31);
       if (gm < P.M && gn < P.N) P.C2[(int64_t)gn * P.ldc2 + gm] = tt[(i >> 5) * (GT + 1) + (i & 31)];
@@ -809,7 +992,7 @@ __device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, floa
 
 // C[m][j] = sum_k A[k][m] * B[k*ldb + j], j < N <= 4, for the 32 rows m0.. of C; 8 interleaved k-parts per row,
 // loads of 8 k steps in flight per thread
-__device__ __forceinline__ void dw_tile_skinny(const GemmProb& P, float* red, int m0, const AdamCtx* ax) {
+__device__ __forceinline__ void dw_tile_skinny(const GemmProb& P, float* red, int m0, const DwTail& T, const DwCtx& cx) {
   const int tid = threadIdx.x, m = tid & 31, kp = tid >> 5;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const bool on = m0 + m < P.M;
@@ -835,17 +1018,19 @@ __device__ __forceinline__ void dw_tile_skinny(const GemmProb& P, float* red, in
   __syncthreads();
   if (tid < 32 * 4) {
     const int mm = tid >> 2, j = tid & 3;
-    if (m0 + mm < P.M && j < P.N) {
-      float v = 0.f;
+    float* c[1] = {P.C + (int64_t)(m0 + mm) * P.ldc + j};
+    const bool ok[1] = {m0 + mm < P.M && j < P.N};
+    float v[1] = {0.f}, th[1];
+    if (ok[0]) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v += red[(q * 32 + mm) * 4 + j];
-      dw_store(P.C + (int64_t)(m0 + mm) * P.ldc + j, v, ax, P.accumulate != 0);
+      for (int q = 0; q < 8; ++q) v[0] += red[(q * 32 + mm) * 4 + j];
     }
+    dw_finish<1>(T, cx, c, ok, P.accumulate != 0, v, th);
   }
 }
 
 // C[n] = sum_k B[k][n] for 256 columns n0.. : one thread per column, 4 independent partial sums
-__device__ __forceinline__ void dw_tile_colsum(const GemmProb& P, float* red, int n0, const AdamCtx* ax) {
+__device__ __forceinline__ void dw_tile_colsum(const GemmProb& P, float* red, int n0, const DwTail& T, const DwCtx& cx) {
   const int n = n0 + threadIdx.x;
   if (n >= P.N) return;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -857,7 +1042,10 @@ __device__ __forceinline__ void dw_tile_colsum(const GemmProb& P, float* red, in
     s3 += P.B[(int64_t)(k + 3) * P.ldb + n];
   }
   for (; k < P.K; ++k) s0 += P.B[(int64_t)k * P.ldb + n];
-  dw_store(P.C + n, (s0 + s1) + (s2 + s3), ax, P.accumulate != 0);
+  float* c[1] = {P.C + n};
+  const bool ok[1] = {true};
+  float v[1] = {(s0 + s1) + (s2 + s3)}, th[1];
+  dw_finish<1>(T, cx, c, ok, P.accumulate != 0, v, th);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 3)
@@ -866,7 +1054,7 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
   float* As = dw_smem;
   float* Bs = dw_smem + DW_KMAX * DW_LD;
   __shared__ GemmProb Ps;
-  __shared__ AdamCtx ax;
+  __shared__ DwCtx cx;
   __shared__ unsigned int s_last;
   long long* tl = nullptr;
   if (T.tl != nullptr && threadIdx.x == 0) {
@@ -876,12 +1064,22 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
   }
   if (tl) tl[0] = clock64();
   const long long st = T.step_counter ? *T.step_counter : 0;     // value BEFORE this update's bump
+  // several workers per rank (19-worker-equivalent batches): the device counter counts micro-batches,
+  // update u = st / micro, launch j = st % micro of it adds its gradient to the sum of launches 0..j-1
+  const long long upd = st / T.micro, mb = st - upd * T.micro;
   if (threadIdx.x == 0) {
-    ax = T.ax;
-    if (T.ax.theta != nullptr && T.neg_a_table != nullptr) {
-      long long t = st + 1;                                       // Adam's 1-based step of this update
-      ax.neg_a = T.neg_a_table[(t <= T.table_len ? t : (long long)T.table_len) - 1];
+    cx.ax = T.ax;
+    cx.opt = (T.ax.theta != nullptr && T.last_chunk && mb == T.micro - 1) ? 1 : 0;
+    if (cx.opt && T.neg_a_table != nullptr) {
+      long long t = upd + 1;                                      // Adam's 1-based step of this update
+      cx.ax.neg_a = T.neg_a_table[(t <= T.table_len ? t : (long long)T.table_len) - 1];
     }
+    cx.xc_on = (cx.opt && T.xc_on) ? 1 : 0;
+    cx.owner = (int)(blockIdx.x % (unsigned)(T.xc_on ? T.xc.world : 1));
+    cx.own = (!T.xc_on || T.xc.mode == 0 || cx.owner == T.xc.rank) ? 1 : 0;
+    cx.flag = (uint32_t)(upd + 1);
+    cx.tl = (cx.xc_on && T.xc.tl != nullptr) ? T.xc.tl + 4 * (int64_t)blockIdx.x : nullptr;
+    if (cx.tl) cx.tl[0] = (long long)globaltimer_ns();
   }
   int pi = 0;
 #pragma unroll 1
@@ -893,30 +1091,27 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    // several workers per rank (19-worker-equivalent batches): the device counter counts micro-batches,
-    // update u = st / micro, launch j = st % micro of it adds its gradient to the sum of launches 0..j-1
-    const long long u = st / T.micro, j = st - u * T.micro;
-    if (T.parity_stride > 0) Ps.C += ((u + 1) & 1) * T.parity_stride;
-    Ps.accumulate = (j > 0 || T.chunk > 0) ? 1 : 0;
+    if (T.parity_stride > 0) Ps.C += ((upd + 1) & 1) * T.parity_stride;
+    Ps.accumulate = (mb > 0 || T.chunk > 0) ? 1 : 0;
   }
   __syncthreads();
   {
     const GemmProb& P = Ps;
-    const AdamCtx* axp = T.ax.theta != nullptr ? &ax : nullptr;
     const int tile = blockIdx.x - P.tile_begin;
     if (tl) tl[1] = clock64();
     if (P.variant == DW_FULLK) {
       const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
-      dw_tile_fullk(P, As, Bs, tm * GT, tn * GT, axp);
+      dw_tile_fullk(P, As, Bs, tm * GT, tn * GT, T, cx);
     } else if (P.variant == DW_SKINNY) {
-      dw_tile_skinny(P, As, tile * GT, axp);
+      dw_tile_skinny(P, As, tile * GT, T, cx);
     } else {
-      dw_tile_colsum(P, As, tile * GEMM_THREADS, axp);
+      dw_tile_colsum(P, As, tile * GEMM_THREADS, T, cx);
     }
   }
   // ---- the last CTA to finish folds the loss partials and bumps the step counter
   __syncthreads();
   if (tl) tl[2] = clock64();
+  if (cx.tl && threadIdx.x == 0) cx.tl[3] = (long long)globaltimer_ns();
   if (!T.last_chunk) return;
   if (threadIdx.x == 0) {
     __threadfence();
@@ -1022,9 +1217,72 @@ static bool rows_supported(const cur_net_desc* d, int64_t n) {
   return true;
 }
 
+// the weight-gradient problems of both nets for the batch rows [r0, r0 + rows), in launch order
+static void build_dw_batch(GemmBatch& G, const NetLayout& LQ, const NetLayout& LP, const RowsWorkspace& w, int L, int H,
+                           float* gQ, float* gP, int64_t r0, int64_t rows, bool keep_transposes) {
+  G.n = 0; G.total_tiles = 0;
+  auto add = [&](const GemmProb& p) { G.p[G.n++] = p; };
+  auto net_grads = [&](const NetLayout& NL, float* gN, const float* X0, float* const* hN, float* const* dN,
+                       const float* dOut, int lddo) {
+    const float* dO = dOut + r0 * lddo;
+    add(bwd_dw(hN[L - 1] + r0 * H, H, H, dO, lddo, NL.out, gN + NL.off_Wout, rows));
+    add(bwd_db(dO, lddo, NL.out, gN + NL.off_bout, rows));
+    for (int l = L - 1; l >= 1; --l) {
+      GemmProb p = bwd_dw(hN[l - 1] + r0 * H, H, H, dN[l] + r0 * H, H, H, gN + NL.off_W[l], rows);
+      if (keep_transposes) { p.C2 = (&NL == &LQ) ? w.TQ[l] : w.TP[l]; p.ldc2 = H; }   // transposed copy of the stepped weights
+      add(p);
+      add(bwd_db(dN[l] + r0 * H, H, H, gN + NL.off_b[l], rows));
+    }
+    add(bwd_dw(X0 + r0 * w.KP, w.KP, NL.in_s, dN[0] + r0 * H, H, H, gN + NL.off_W0, rows));
+    add(bwd_db(dN[0] + r0 * H, H, H, gN + NL.off_b0, rows));
+    if (NL.in_g > 0) add(bwd_dw(X0 + r0 * w.KP + NL.in_s, w.KP, NL.in_g, dN[0] + r0 * H, H, H, gN + NL.off_W0g, rows));
+  };
+  net_grads(LQ, gQ, w.Xq, w.hq, w.dc, w.dQ, 1);
+  net_grads(LP, gP, w.Xp, w.hp, w.dp, w.dy, w.lddy);
+}
+
 }  // namespace cur
 
 using namespace cur;
+
+extern "C" int cur_ddpg_rows_owner_map(const cur_net_desc* d, int64_t batch, int world, int32_t* owner) {
+  CUR_TRY(check_desc(d));
+  CUR_REQUIRE(owner != nullptr && world >= 1 && world <= CUR_MAX_RANKS, "bad argument");
+  CUR_REQUIRE(rows_supported(d, batch), "shape not supported by the rows schedule");
+  const NetLayout LQ = net_layout(*d, 0), LP = net_layout(*d, 1);
+  const int64_t offP = r4(LQ.total), arena = offP + r4(LP.total);
+  // the plan only depends on shapes: build it over a dummy workspace / gradient arena that is never dereferenced
+  float* ws = reinterpret_cast<float*>(malloc(16));
+  float* grads = reinterpret_cast<float*>(malloc((size_t)arena * 4));
+  CUR_REQUIRE(ws && grads, "out of host memory");
+  const RowsWorkspace w = carve_rows(*d, batch, ws);
+  GemmBatch G;
+  const int64_t rows = batch < DW_KMAX ? batch : DW_KMAX;
+  build_dw_batch(G, LQ, LP, w, d->layers, d->hidden, grads, grads + offP, 0, rows, false);
+  const int tiles = plan_dw_batch(G);
+  if (tiles <= 0) { free(ws); free(grads); return invalid("weight-gradient problems do not fit the rows schedule"); }
+  for (int64_t i = 0; i < arena; ++i) owner[i] = -1;
+  for (int pi = 0; pi < G.n; ++pi) {
+    const GemmProb& P = G.p[pi];
+    const int64_t base = P.C - grads;
+    const int n_tiles = (pi + 1 < G.n ? G.p[pi + 1].tile_begin : tiles) - P.tile_begin;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int own = (P.tile_begin + t) % world;
+      if (P.variant == DW_FULLK) {
+        const int tm = t / P.tiles_n, tn = t - tm * P.tiles_n;
+        for (int m = tm * GT; m < (tm + 1) * GT && m < P.M; ++m)
+          for (int n = tn * GT; n < (tn + 1) * GT && n < P.N; ++n) owner[base + (int64_t)m * P.ldc + n] = own;
+      } else if (P.variant == DW_SKINNY) {
+        for (int m = t * GT; m < (t + 1) * GT && m < P.M; ++m)
+          for (int n = 0; n < P.N; ++n) owner[base + (int64_t)m * P.ldc + n] = own;
+      } else {
+        for (int n = t * GEMM_THREADS; n < (t + 1) * GEMM_THREADS && n < P.N; ++n) owner[base + n] = own;
+      }
+    }
+  }
+  free(ws); free(grads);
+  return CUR_OK;
+}
 
 extern "C" int cur_ddpg_rows_supported(const cur_net_desc* d, int64_t batch) { return rows_supported(d, batch) ? 1 : 0; }
 
@@ -1185,14 +1443,31 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   T.action_l2 = h->action_l2; T.q_loss = q_loss; T.pi_loss = pi_loss;
   T.parity_stride = h->grads_parity_stride;
   T.micro = h->micro_batches > 1 ? h->micro_batches : 1;
-  CUR_REQUIRE(T.micro == 1 || (h->step_counter != nullptr && adam == nullptr),
-              "several micro-batches per update need the step counter and exclude the fused Adam epilogue");
+  CUR_REQUIRE(T.micro == 1 || h->step_counter != nullptr, "several micro-batches per update need the step counter");
   CUR_REQUIRE(T.parity_stride == 0 || (h->step_counter != nullptr && adam == nullptr),
               "gradient double buffering needs the step counter and excludes the fused Adam epilogue");
   static bool dw_configured = false;
+  static int dw_resident = 0;              // CTAs of the weight-gradient launch that are co-resident on the device
   if (!dw_configured) {
     CUR_CUDA_TRY(cudaFuncSetAttribute(rows_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_SMEM_BYTES));
+    int per_sm = 0;
+    CUR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_dw_kernel, GEMM_THREADS, DW_SMEM_BYTES));
+    dw_resident = per_sm * sm_count();
     dw_configured = true;
+  }
+  if (adam != nullptr && adam->xchg != nullptr && adam->xchg->world > 1) {
+    const cur_xchg_ctx* x = adam->xchg;
+    CUR_REQUIRE(x->world <= CUR_MAX_RANKS && x->rank >= 0 && x->rank < x->world, "bad rank / world of the exchange");
+    CUR_REQUIRE(x->mode == 0 || x->mode == 1, "bad exchange mode");
+    CUR_REQUIRE(x->arena >= r4(LQ.total) + r4(LP.total), "exchange arena smaller than the gradient arena");
+    T.xc_on = 1;
+    T.xc.rank = x->rank; T.xc.world = x->world; T.xc.mode = x->mode; T.xc.arena = x->arena;
+    T.xc.tl = reinterpret_cast<long long*>(x->timeline); T.xc.error_flag = x->error_flag;
+    for (int r = 0; r < x->world; ++r) {
+      CUR_REQUIRE(x->region[r] != nullptr, "peer region not mapped");
+      T.xc.part[r] = reinterpret_cast<unsigned long long*>(x->region[r]);
+      T.xc.res[r] = T.xc.part[r] + (int64_t)x->world * x->arena;
+    }
   }
   T.tl = tl_on ? tl_dev : nullptr;
   const AdamCtx ax_full = T.ax;
@@ -1202,27 +1477,11 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     const int64_t rows = (n - r0 < DW_KMAX) ? n - r0 : DW_KMAX;
     const bool last = c == n_chunks - 1;
     GemmBatch G;
-    G.n = 0; G.total_tiles = 0;
-    auto add = [&](const GemmProb& p) { G.p[G.n++] = p; };
-    auto net_grads = [&](const NetLayout& NL, float* gN, const float* X0, float* const* hN, float* const* dN,
-                         const float* dOut, int lddo) {
-      const float* dO = dOut + r0 * lddo;
-      add(bwd_dw(hN[L - 1] + r0 * H, H, H, dO, lddo, NL.out, gN + NL.off_Wout, rows));
-      add(bwd_db(dO, lddo, NL.out, gN + NL.off_bout, rows));
-      for (int l = L - 1; l >= 1; --l) {
-        GemmProb p = bwd_dw(hN[l - 1] + r0 * H, H, H, dN[l] + r0 * H, H, H, gN + NL.off_W[l], rows);
-        if (adam && last) { p.C2 = (&NL == &LQ) ? w.TQ[l] : w.TP[l]; p.ldc2 = H; }   // transposed copy of the stepped weights
-        add(p);
-        add(bwd_db(dN[l] + r0 * H, H, H, gN + NL.off_b[l], rows));
-      }
-      add(bwd_dw(X0 + r0 * w.KP, w.KP, NL.in_s, dN[0] + r0 * H, H, H, gN + NL.off_W0, rows));
-      add(bwd_db(dN[0] + r0 * H, H, H, gN + NL.off_b0, rows));
-      if (NL.in_g > 0) add(bwd_dw(X0 + r0 * w.KP + NL.in_s, w.KP, NL.in_g, dN[0] + r0 * H, H, H, gN + NL.off_W0g, rows));
-    };
-    net_grads(LQ, gQ, w.Xq, w.hq, w.dc, w.dQ, 1);
-    net_grads(LP, gP, w.Xp, w.hp, w.dp, w.dy, w.lddy);
+    build_dw_batch(G, LQ, LP, w, L, H, gQ, gP, r0, rows, adam != nullptr && last);
     const int tiles = plan_dw_batch(G);
     CUR_REQUIRE(tiles > 0, "weight-gradient problems do not fit the rows schedule (unaligned dims)");
+    // CTAs of the exchange spin on their peers: every tile of the launch must be resident at once
+    CUR_REQUIRE(!T.xc_on || tiles <= dw_resident, "too many weight-gradient tiles for the in-launch gradient exchange");
     T.chunk = c; T.last_chunk = last ? 1 : 0;
     T.ax = ax_full;
     if (!last) T.ax.theta = nullptr;             // the optimiser runs once, on the complete sum

@@ -236,6 +236,12 @@ extern "C" int64_t cur_p2p_region_bytes(int64_t arena_floats) {
   return P2P_FLAG_BYTES + 3 * arena_floats * 4;      // flags | grads 0 | grads 1 | parameter staging
 }
 
+// region of the tile-level exchange of ddpg_rows.cu: [ partial slots: world x arena x 8 B | result slots: arena x 8 B ]
+extern "C" int64_t cur_xchg_region_bytes(int64_t arena_floats, int world) {
+  if (arena_floats <= 0 || world < 1 || world > CUR_MAX_RANKS) return -1;
+  return ((int64_t)world + 1) * arena_floats * 8;
+}
+
 extern "C" int cur_p2p_alloc(int64_t bytes, void** ptr, unsigned char* handle64) {
   CUR_REQUIRE(ptr && handle64 && bytes > 0, "bad argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -257,6 +263,12 @@ extern "C" int cur_p2p_open(const unsigned char* handle64, void** ptr) {
 
 extern "C" int cur_p2p_close(void* ptr) {
   CUR_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return CUR_OK;
+}
+
+extern "C" int cur_p2p_zero(void* stream, void* ptr, int64_t bytes) {
+  CUR_REQUIRE(ptr && bytes > 0, "bad argument");
+  CUR_CUDA_TRY(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
   return CUR_OK;
 }
 

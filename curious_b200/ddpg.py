@@ -60,16 +60,23 @@ class DDPG(object):
         self.comm = kwargs.get('comm')
         self.her_rng = kwargs.get('her_rng', 'philox')
         self.seed = kwargs.get('seed', 0)
+        # key of the device-side exploration noise (action_noise='device'); per rank in make_experiment, like the
+        # reference's rank_seed (train.py:242), while `seed` (weight init) is the same on every rank
+        self.noise_seed = kwargs.get('noise_seed', self.seed)
         self.use_cuda_graph = kwargs.get('use_cuda_graph', True)
         # 'rows' (cluster kernel + fused dW/Adam, 2 launches), 'levels' (one grouped GEMM per dependency
         # level) or 'auto' (rows whenever the shape is supported)
         self.update_schedule = kwargs.get('update_schedule', 'auto')
         self.fuse_her = kwargs.get('fuse_her', True)      # rows schedule: sample inside the update kernel
-        # several ranks: 'p2p' = gradient exchange over NVLink peer memory fused with Adam inside the update's
-        # CUDA graph (csrc/p2p.cu: every rank sums all peers' gradients in rank order), 'p2p_sharded' = reduce-scatter
-        # by loads, Adam on the own slice, all-gather by stores, 'nccl' = NCCL all-reduce + Adam launch after the
-        # graph, 'auto' = p2p when the rows schedule runs on an NCCL (one GPU per rank) group
+        # several ranks: 'tile' = the gradient tiles are exchanged over NVLink peer memory INSIDE the weight-gradient
+        # launch, Adam and W^T stay in its epilogue (csrc/ddpg_rows.cu, parallel.TileGradExchange: 2 launches per update
+        # like one rank), 'p2p' = one exchange + Adam kernel after the weight-gradient launch (csrc/p2p.cu: every rank
+        # sums all peers' gradients in rank order), 'p2p_sharded' = reduce-scatter by loads, Adam on the own slice,
+        # all-gather by stores, 'nccl' = NCCL all-reduce + Adam launch after the graph, 'auto' = tile when the rows
+        # schedule runs on an NCCL (one GPU per rank) group
         self.grad_exchange = kwargs.get('grad_exchange', 'auto')
+        assert self.grad_exchange in ('auto', 'tile', 'p2p', 'p2p_sharded', 'nccl')
+        self.xchg_timeline_tiles = int(kwargs.get('xchg_timeline_tiles', 0))      # debug: per-tile %globaltimer stamps
         # reference workers hosted by this rank (the 19 MPI workers become ceil(19 / G) workers per GPU):
         # every update is the SUM of `workers_per_rank` batch-256 gradients, each with its own loss mean, exactly what
         # the reference's SUM all-reduce over that many single-batch workers produces (ddpg.py:452-453)
@@ -82,6 +89,8 @@ class DDPG(object):
         assert self.workers_mode in ('auto', 'wide', 'micro')
         # exploration noise of get_actions (ddpg.py:147-152): 'host' = the caller's np.random stream in reference order,
         # 'device' = counter-based draws applied on the device before the one D2H copy
+        # train() on the CUDA-graph path returns views of fixed device buffers (no copy per update); True = owned copies
+        self.own_train_outputs = bool(kwargs.get('own_train_outputs', False))
         self.action_noise = kwargs.get('action_noise', 'host')
         assert self.action_noise in ('host', 'device')
         self._action_calls = 0
@@ -278,7 +287,7 @@ class DDPG(object):
             # Q above was evaluated on the noise-free action, like the reference's Q_pi_tf (ddpg.py:138-146)
             if noise_eps != 0. or random_eps != 0.:
                 _lib.check(_lib.load().cur_action_noise(_lib.stream_ptr(), out.data_ptr(), n, self.dimu, float(self.max_u),
-                                                        float(noise_eps), float(random_eps), int(self.seed) & (2 ** 64 - 1),
+                                                        float(noise_eps), float(random_eps), int(self.noise_seed) & (2 ** 64 - 1),
                                                         self._action_calls), 'cur_action_noise')
             self._action_calls += 1
         res = out.cpu().numpy()
@@ -565,7 +574,12 @@ class DDPG(object):
                              'tensor-core levels schedule takes (workers x batch_size >= 1024, a multiple of 128)')
         self._workspace_rows(B) if self._use_rows(B) else self._workspace(B)
         self._peer = None
-        if self._want_peer_exchange():
+        self._xchg = None
+        kind = self._exchange_kind()
+        if kind == 'tile':
+            from .parallel import TileGradExchange
+            self._xchg = TileGradExchange(self.net.arena, self.comm, timeline_tiles=self.xchg_timeline_tiles)
+        elif kind is not None:
             from .parallel import PeerGradExchange
             # the sharded exchange moves 8x fewer bytes at 8 GPUs but measured no faster (2 GPUs: 83 us full / 91 us
             # sharded, 8 GPUs: 97.3 / 98.2): the exchange is latency / straggler bound, so the one-round kernel is default
@@ -594,7 +608,7 @@ class DDPG(object):
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            fused = self._launch_sample_and_grads()
+            fused = self._launch_sample_and_grads(solo=True)
             if not fused:
                 self._launch_adam(warmup=True)
         torch.cuda.current_stream().wait_stream(side)
@@ -606,7 +620,7 @@ class DDPG(object):
         # NCCL all-reduce and the Adam launch follow on the same stream (collectives are kept out of the
         # capture: a captured torch NCCL all-reduce dead-locked on the 2-GPU box).
         # With the peer-memory exchange the all-reduce IS the Adam kernel and the whole update is one graph again.
-        self._graph_has_adam = _world(self.comm)[1] == 1 or self._peer is not None
+        self._graph_has_adam = _world(self.comm)[1] == 1 or self._peer is not None or self._xchg is not None
         keeps_wT = self._peer is not None and getattr(self, '_peer_wT', None) is not None
         if keeps_wT:
             self._ghyper.transposes_valid = 1
@@ -619,30 +633,35 @@ class DDPG(object):
         self._graph = g
         self._graph_fused = fused or keeps_wT
         self._wT_dirty = True            # the warm-up stepped (and we restored) theta: rebuild W^T before the first replay
-        if self._peer is not None:
+        if self._peer is not None or self._xchg is not None:
             import torch.distributed as dist
+            torch.cuda.synchronize(dev)
             dist.barrier(group=_world(self.comm)[0])
 
-    def _want_peer_exchange(self):
+    def _exchange_kind(self):
+        """None (one rank, or NCCL after the graph) | 'tile' | 'p2p' | 'p2p_sharded'."""
         group, n = _world(self.comm)
         if n <= 1 or self.grad_exchange == 'nccl':
-            return False
+            return None
         import torch.distributed as dist
         ok = (self._use_rows(self._graph_rows) and self._same_rule() and n <= _lib.CUR_MAX_RANKS and
               dist.get_backend(group) == 'nccl')
-        if self.grad_exchange in ('p2p', 'p2p_sharded') and not ok:
-            raise ValueError('grad_exchange="p2p" needs the rows schedule, one Adam rule for both nets and an NCCL '
-                             'group of <= %d ranks' % _lib.CUR_MAX_RANKS)
-        return ok
+        if self.grad_exchange != 'auto' and not ok:
+            raise ValueError('grad_exchange=%r needs the rows schedule, one Adam rule for both nets and an NCCL '
+                             'group of <= %d ranks' % (self.grad_exchange, _lib.CUR_MAX_RANKS))
+        if not ok:
+            return None
+        return 'tile' if self.grad_exchange == 'auto' else self.grad_exchange
 
     def _same_rule(self):
         qa, pa = self.Q_adam, self.pi_adam
         return (self.Q_lr, qa.beta1, qa.beta2, qa.epsilon) == (self.pi_lr, pa.beta1, pa.beta2, pa.epsilon)
 
-    def _launch_sample_and_grads(self, keep_wT=False):
+    def _launch_sample_and_grads(self, keep_wT=False, solo=False):
         """HER sample + gradients of one update, all parameters frozen / device-resident (capturable).
         Returns True when Adam was fused into the weight-gradient launch.  keep_wT: the transposed hidden-layer
-        weights in the rows workspace are current (maintained by the fused Adam epilogue, see _refresh_wT)."""
+        weights in the rows workspace are current (maintained by the fused Adam epilogue, see _refresh_wT).
+        solo: the warm-up run outside capture - no peer is touched with an update that is discarded afterwards."""
         lib = _lib.load()
         sampler = self.sample_transitions
         segs = [(buf.device_view(), 0, ttr) for buf, ttr in self._all_segments()]
@@ -666,13 +685,19 @@ class DDPG(object):
         if self._use_rows(n):
             # with one rank there is no all-reduce between _grads and _update: Adam runs in the epilogue of
             # the weight-gradient launch (2 launches per update after the HER kernel)
-            fuse = self._same_rule() and _world(self.comm)[1] == 1 and self._micro == 1
+            # ... and with several ranks when the tiles are exchanged inside that launch (TileGradExchange); with
+            # several workers per rank the epilogue of the update's last launch steps the complete sum
+            fuse = self._same_rule() and (_world(self.comm)[1] == 1 or self._xchg is not None)
             adam = _lib.AdamFused(self._adam_m.data_ptr(), self._adam_v.data_ptr(), self._adam_tables[0].data_ptr(),
-                                  self.ADAM_TABLE, 1 if keep_wT else 0, qa.beta1, qa.beta2, qa.epsilon) if fuse else None
+                                  self.ADAM_TABLE, 1 if keep_wT else 0, qa.beta1, qa.beta2, qa.epsilon,
+                                  C.pointer(self._xchg.ctx) if (self._xchg is not None and not solo) else None) \
+                if fuse else None
             base_valid = self._ghyper.transposes_valid
             for j in range(self._micro):
                 # the weights do not change between the workers of one update: only the first launch re-transposes
                 self._ghyper.transposes_valid = 1 if (j > 0 or base_valid) else 0
+                if fuse:
+                    adam.transposes_valid = 1 if (j > 0 or keep_wT) else 0
                 if j > 0 and her_args is None:            # unfused sampling: a fresh batch for every worker
                     sampler.sample_device(segs, self._graph_rows, clip_obs=self.clip_obs,
                                           relative_goals=self.relative_goals, want=self._gwant, out=self._gbatch,
@@ -757,7 +782,13 @@ class DDPG(object):
         self._n_updates += 1
         self.Q_adam.t += 1
         self.pi_adam.t += 1
-        return LazyHost(self._q_ring[slot]), LazyHost(self._q_pi)
+        if self.own_train_outputs:        # owned copies like the reference's arrays (one small device copy per update)
+            return LazyHost(self._q_ring[slot].clone()), LazyHost(self._q_pi.clone())
+        # views of the graph's fixed output buffers: the loss slot is reused after LOSS_RING updates, Q_pi by the very
+        # next one - a stale read raises (LazyHost) instead of returning a later update's values
+        n = self._n_updates
+        return (LazyHost(self._q_ring[slot], lambda: self._n_updates - n < self.LOSS_RING),
+                LazyHost(self._q_pi, lambda: self._n_updates == n))
 
     def train(self, stage=True):
         """One DDPG update (ddpg.py:368-373).  Returns (critic_loss, actor_loss) as lazily synchronising
@@ -839,11 +870,27 @@ class DDPG(object):
                 out.append((i, b))
         return out
 
+    def _gather_adam_state(self):
+        """Owner mode of the tile exchange (cur_xchg_ctx mode 1) keeps the Adam moments of an element only on the rank
+        that reduces it: assemble the full vectors on every rank (COLLECTIVE - every rank saves its own checkpoint,
+        train.py of this package; also needed before switching to another update path)."""
+        x = getattr(self, '_xchg', None)
+        if x is None or x.mode != 1:
+            return
+        owner = np.empty(int(self.net.arena), np.int32)
+        _lib.check(_lib.load().cur_ddpg_rows_owner_map(C.byref(self.net.desc), self._graph_rows, x.world,
+                                                       owner.ctypes.data), 'cur_ddpg_rows_owner_map')
+        mine = torch.from_numpy((owner == x.rank).astype(np.float32)).to(self.device)
+        for t in (self._adam_m, self._adam_v):
+            t.mul_(mine)
+            allreduce_sum_(t, self.comm)        # x + 0 + ... + 0 is exact
+
     def save_checkpoint(self, path, buffers=True, numpy_rng=True):
         """Everything a run needs to continue bit for bit: parameters, Adam moments and step counters, normaliser
         accumulators, the Philox stream positions and (optionally) the replay buffers and the host np.random state.
         The reference can only save weights + normaliser statistics (ddpg.py:481-497): its Adam
         state, replay data and RNG position are lost on restart.  One torch.save file, tensors on the host."""
+        self._gather_adam_state()
         cpu = lambda t: t.detach().cpu().clone()
         st = dict(format=1, arena=int(self.net.arena), theta_main=cpu(self.theta_main), theta_target=cpu(self.theta_target),
                   adam_m=cpu(self._adam_m), adam_v=cpu(self._adam_v), adam_t=(int(self.Q_adam.t), int(self.pi_adam.t)),
@@ -872,6 +919,8 @@ class DDPG(object):
         if getattr(self, '_peer', None) is not None and st['step'] < int(self._step.item()):
             # the peer-memory exchange counts updates in its NVLink flags (csrc/p2p.cu): they cannot run backwards
             raise ValueError('load the checkpoint into a freshly built agent when the peer-memory exchange is active')
+        if getattr(self, '_xchg', None) is not None:
+            self._xchg.reset()            # (collective) the update numbers travelling with the tiles start over
         for dst, key in ((self.theta_main, 'theta_main'), (self.theta_target, 'theta_target'),
                          (self._adam_m, 'adam_m'), (self._adam_v, 'adam_v')):
             dst.copy_(st[key].to(self.device))
@@ -916,7 +965,8 @@ class DDPG(object):
             state['sample_transitions'] = None      # not needed for playing the policy
         weights = state.pop('weights')
         extra = {k: state.pop(k) for k in list(state.keys())
-                 if k not in DDPG.__init__.__wrapped__.__code__.co_varnames and k not in ('structure', 'her_rng', 'seed')}
+                 if k not in DDPG.__init__.__wrapped__.__code__.co_varnames and
+                 k not in ('structure', 'her_rng', 'seed', 'noise_seed')}
         self.__init__(**state)
         self.__dict__.update(extra)
         for i, (which, target) in enumerate((('Q', False), ('pi', False), ('Q', True), ('pi', True))):

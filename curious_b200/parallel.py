@@ -36,13 +36,29 @@ def _root(group):
     return dist.get_global_rank(group, 0) if group is not None and group is not dist.group.WORLD else 0
 
 
+# True: sums over ranks are evaluated in RANK ORDER ((x0 + x1) + x2 ...) from an all-gather instead of NCCL's
+# all-reduce, whose summation order depends on its algorithm.  With more than two ranks this is the reference result
+# the peer-memory exchanges (csrc/p2p.cu, the tile exchange of csrc/ddpg_rows.cu) reproduce bit for bit; the parity
+# checks of tests/test_multi_gpu.py and bench.py switch it on for the NCCL arm (CUR_ORDERED_ALLREDUCE=1 does the same).
+import os as _os
+ORDERED_ALLREDUCE = _os.environ.get('CUR_ORDERED_ALLREDUCE', '0') == '1'
+
+
 def allreduce_sum_(t, comm=None):
     """In-place SUM over ranks - gradients are summed, NOT averaged (scale_grad_by_procs=False,
     ddpg.py:452-453).  Returns the world size."""
     group, n = world(comm)
     if n > 1:
         import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        if ORDERED_ALLREDUCE:
+            parts = [torch.empty_like(t) for _ in range(n)]
+            dist.all_gather(parts, t.contiguous(), group=group)
+            acc = parts[0].clone()
+            for p in parts[1:]:
+                acc += p
+            t.copy_(acc)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return n
 
 
@@ -181,6 +197,81 @@ class PeerGradExchange(object):
         """Raises if a peer did not show up within the kernel's spin budget (a rank died or diverged)."""
         if int(self.error_flag.item()) != 0:
             raise RuntimeError('peer gradient exchange timed out waiting for another rank')
+
+    def close(self):
+        for p in self.opened:
+            self.lib.cur_p2p_close(p)
+        self.opened = []
+        if self.own:
+            self.lib.cur_p2p_free(self.own)
+            self.own = None
+
+
+class TileGradExchange(object):
+    """Gradient exchange INSIDE the weight-gradient launch of the rows schedule (csrc/ddpg_rows.cu, `cur_xchg_ctx`;
+    replaces the Allreduce(SUM) of mpi_adam.py:24-28): every CTA pushes its tile of dW to the reducing rank(s) as
+    8-byte {value, update number} words over NVLink peer memory, the reducer sums the world's tiles in rank order and
+    applies Adam in the same epilogue.  mode 0: every rank reduces every tile (one hop, full Adam state everywhere);
+    mode 1: tile t is reduced by rank t % world, which pushes the stepped parameters back (two hops, 1/W of the bytes
+    per rank at large W, Adam moments only on the owner).  'auto' = 0 for two ranks, 1 above.
+    One process per GPU on one NVLink domain (cudaIpcOpenMemHandle)."""
+
+    def __init__(self, arena_floats, comm=None, mode='auto', timeline_tiles=0):
+        import ctypes as C
+        import os
+        import torch.distributed as dist
+        from . import _lib
+        lib = _lib.load()
+        group, n = world(comm)
+        assert 1 < n <= _lib.CUR_MAX_RANKS, 'the tile exchange needs 2..%d ranks' % _lib.CUR_MAX_RANKS
+        self.lib, self.group, self.world = lib, group, n
+        self.rank = dist.get_rank(group)
+        self.arena = int(arena_floats)
+        env = os.environ.get('CUR_XCHG_MODE')
+        if env in ('0', '1'):
+            mode = int(env)
+        if mode == 'auto':
+            mode = 0 if n == 2 else 1
+        assert mode in (0, 1)
+        self.mode = mode
+        self.nbytes = lib.cur_xchg_region_bytes(self.arena, n)
+        assert self.nbytes > 0
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(lib.cur_p2p_alloc(self.nbytes, C.byref(own), handle), 'cur_p2p_alloc')
+        self.own = own.value
+        self.opened = []
+        handles = [None] * n
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ctx = _lib.XchgCtx()
+        self.ctx.rank, self.ctx.world, self.ctx.mode, self.ctx.arena = self.rank, n, mode, self.arena
+        for r in range(n):
+            if r == self.rank:
+                self.ctx.region[r] = self.own
+                continue
+            p = C.c_void_p()
+            _lib.check(lib.cur_p2p_open(handles[r], C.byref(p)), 'cur_p2p_open')
+            self.opened.append(p.value)
+            self.ctx.region[r] = p.value
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+        self.ctx.error_flag = self.error_flag.data_ptr()
+        self.timeline = None
+        if timeline_tiles > 0:
+            self.timeline = torch.zeros(4 * int(timeline_tiles), dtype=torch.int64, device='cuda')
+            self.ctx.timeline = self.timeline.data_ptr()
+        torch.cuda.synchronize()
+        dist.barrier(group=group)                       # every region is mapped and zeroed before anyone pushes
+
+    def reset(self):
+        """Collective: forget every word in flight (needed before the device step counter moves backwards, e.g. when a
+        checkpoint is loaded into a running agent - the update number travelling with the data must never repeat)."""
+        import torch.distributed as dist
+        from . import _lib
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        _lib.check(self.lib.cur_p2p_zero(_lib.stream_ptr(), self.own, self.nbytes), 'cur_p2p_zero')
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
 
     def close(self):
         for p in self.opened:

@@ -20,6 +20,22 @@ from .her import DeviceEpisodes
 
 BASE_KEYS = ('o', 'ag', 'g', 'u')
 
+# The device rows are float32 while the reference stores float64 (replay_buffer.py:23-24).  Everything its rollouts
+# produce is float32 already (rollout.py:50-52,194-195), so nothing is lost - and this switch makes sure of it: a
+# float64 episode whose values do not survive the round trip through float32 raises instead of being rounded silently.
+CHECK_FLOAT32_REPRESENTABLE = True
+
+
+def _as_float32(key, arr):
+    arr = np.asarray(arr)
+    if CHECK_FLOAT32_REPRESENTABLE and arr.dtype == np.float64:
+        f = arr.astype(np.float32)
+        if not np.array_equal(f.astype(np.float64), arr, equal_nan=True):
+            raise ValueError('episode key %r holds float64 values that are not float32-representable (max round-off '
+                             '%.3g); the device replay rows are float32' % (key, float(np.nanmax(np.abs(f - arr)))))
+        return f
+    return arr
+
 
 def split_keys(shapes_or_batch):
     """Classify keys: returns (has_td, has_change, [info keys] sorted)."""
@@ -75,13 +91,13 @@ class StagedEpisodes:
         h = host.numpy()
         offs, k0 = {}, 0
         for key, sz in parts:
-            arr = np.asarray(episode_batch[key])
+            arr = _as_float32(key, episode_batch[key])
             assert arr.shape[0] == n and arr[0].size == sz, 'bad shape for %s: %s' % (key, arr.shape)
             h[k0:k0 + n * sz] = arr.reshape(-1)          # casts bool / float64 to float32
             offs[key] = k0
             k0 += n * sz
         if info_keys:
-            info = np.concatenate([np.asarray(episode_batch[k], np.float32).reshape(n, T, d)
+            info = np.concatenate([np.asarray(_as_float32(k, episode_batch[k]), np.float32).reshape(n, T, d)
                                    for k, d in info_keys], axis=2)
             h[k0:k0 + info.size] = info.reshape(-1)
             offs['info'] = k0
@@ -117,6 +133,13 @@ class StagedEpisodes:
 
     def store(self, copies, stream=None):
         """copies: list of (src_episode, hot_tensor, cold_tensor_or_None, slot)."""
+        # Two copies of one call may target the same slot of the same buffer (random overwrite once a buffer is full,
+        # replay_buffer.py:99-102).  The reference stores one after the other, so the later episode wins as a whole;
+        # the kernel writes all copies concurrently, so the earlier ones are dropped here (last writer kept).
+        last = {}
+        for i, c in enumerate(copies):
+            last[(c[1].data_ptr(), int(c[3]))] = i
+        copies = [c for i, c in enumerate(copies) if last[(c[1].data_ptr(), int(c[3]))] == i]
         n = len(copies)
         if n == 0:
             return

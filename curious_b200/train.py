@@ -22,7 +22,7 @@ from .ddpg import DDPG
 from .envs import ModularPointEnv
 from .replay_buffer import ReplayBuffer
 from .rollout import RolloutWorker
-from .parallel import assert_rank_streams_differ, bcast_object
+from .parallel import assert_rank_streams_differ, bcast_object, rank as _rank, rank_seed
 from .runlog import RunLog, mpi_average
 
 MULTI_TASK_PARAMS = {            # config.py:56-90
@@ -76,6 +76,13 @@ def make_experiment(nb_tasks=4, n_controllable=None, structure='curious', task_s
     arguments of train()."""
     params = dict(FLAT_PARAMS if structure == 'flat' else MULTI_TASK_PARAMS)
     params.update(overrides)
+    # train.py:241-243: every rank seeds everything with rank_seed = seed + 1000000 * rank (set_global_seeds: np.random
+    # and random), so that ranks explore, draw tasks / goals / replay slots and sample replay differently; only the weight
+    # initialisation keeps `seed` (rank 0's weights are broadcast anyway, ddpg.py:466)
+    import random
+    rs = rank_seed(seed, _rank((policy_kwargs or {}).get('comm')))
+    np.random.seed(rs % (2 ** 32))
+    random.seed(rs)
     if make_env is None:
         def make_env():
             return ModularPointEnv(nb_tasks, n_controllable)
@@ -101,7 +108,9 @@ def make_experiment(nb_tasks=4, n_controllable=None, structure='curious', task_s
                    normalize_obs=normalize_obs, sample_transitions=sampler, gamma=gamma, tasks_ag_id=ag_ids, tasks_g_id=g_ids,
                    task_replay=task_replay, eps_task=params.get('eps_task'), structure=structure, her_rng='philox',
                    seed=seed, device=device)
+    ddpg_kw['noise_seed'] = rs                      # key of the device-side exploration noise (action_noise='device')
     ddpg_kw.update(policy_kwargs or {})             # this implementation's extras: action_noise, update_schedule, comm, ...
+    sampler.seed = rs                               # Philox key of the HER draws
     buffer_size = (params['buffer_size'] // params['rollout_batch_size']) * params['rollout_batch_size']    # config.py:204
     buffers = configure_buffer({k: v for k, v in dims.items() if structure != 'flat' or k != 'task_descr'}, T, sampler,
                                buffer_size, structure, task_replay, nb_tasks, device=device)
@@ -112,13 +121,19 @@ def make_experiment(nb_tasks=4, n_controllable=None, structure='curious', task_s
     test = dict(rollout_kw, exploit=True, use_target_net=params['test_with_polyak'], compute_Q=True, eval=True)
     if structure == 'task_experts':                                 # train.py:287-289,325-331
         policy = [DDPG(buffers=buffers, t_id=i, **ddpg_kw) for i in range(nb_tasks)]
+        for i, pol in enumerate(policy):
+            # the experts share one sampler (one Philox key): give each its own counter range on the train-step stream
+            pol.GRAPH_STREAM_OFFSET = DDPG.GRAPH_STREAM_OFFSET + (i << 36)
+            pol.noise_seed = rs + i
         rollout_worker = [RolloutWorker(make_env, policy[i], unique_task=i, **explore) for i in range(nb_tasks)]
+        for i, w in enumerate(rollout_worker):
+            w.seed(rs + i)                                          # train.py:328-329
     else:
         policy = DDPG(buffers=buffers, **ddpg_kw)
         rollout_worker = RolloutWorker(make_env, policy, **explore)
+        rollout_worker.seed(rs)                                     # train.py:332
     evaluator = RolloutWorker(make_env, policy, **test)
-    for i, w in enumerate((rollout_worker if isinstance(rollout_worker, list) else [rollout_worker]) + [evaluator]):
-        w.seed(seed + 10 * i)
+    evaluator.seed(rs + 100)                                        # train.py:335
     run_params = dict(params, structure=structure, task_selection=task_selection, goal_selection='random',
                       goal_replay=goal_replay, task_replay=task_replay, normalize_obs=normalize_obs, seed=seed,
                       nb_tasks=nb_tasks, T=T, gamma=gamma, clip_return=1. / (1. - gamma),

@@ -71,8 +71,19 @@ class LazyHost:
     own loop ignores them (train.py:152-153), so forcing a device sync per update would only cost time.
     float(x), np.asarray(x), x.item() and arithmetic all work and synchronise on demand."""
 
-    def __init__(self, tensor):
-        self.tensor = tensor
+    def __init__(self, tensor, still_valid=None):
+        self._tensor = tensor
+        # optional callable: False once the device buffer behind `tensor` has been reused by a later update (the CUDA-graph
+        # path of DDPG.train hands out views of its fixed output buffers); reading then raises instead of returning
+        # another update's numbers
+        self._still_valid = still_valid
+
+    @property
+    def tensor(self):
+        if self._still_valid is not None and not self._still_valid():
+            raise RuntimeError('this train() result was overwritten by a later update: read it before the next '
+                               'train() call, or build the agent with own_train_outputs=True')
+        return self._tensor
 
     def numpy(self):
         return self.tensor.detach().cpu().numpy()

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CUR_ABI_VERSION 1
+#define CUR_ABI_VERSION 2
 
 #define CUR_OK 0
 #define CUR_ERR_INVALID 1   /* bad argument (dims, null pointer, table overflow)   */
@@ -339,6 +339,35 @@ int cur_ddpg_grads_group(void* stream, const cur_net_desc* d, int n_experts, con
  * Philox counters / injected draws / control block, bit-identical transitions); output pointers
  * inside `her` are ignored.
  * ------------------------------------------------------------------------------------------ */
+/* Tile-level gradient exchange INSIDE the weight-gradient launch (csrc/ddpg_rows.cu, several ranks; replaces the
+ * Allreduce(SUM) of mpi_adam.py:24-28 between _grads and _update, scale_grad_by_procs=False).  Every rank runs the same
+ * tile grid; as soon as a CTA has its tile of dW it pushes the tile to the rank(s) that reduce it with "LL" stores over
+ * NVLink peer memory - each element travels as one 8-byte {float32 bits, update number} word, so the receiver polls the
+ * data words themselves and no flag round / memory fence sits on the critical path.  The reducer adds the world's tiles in
+ * rank order (bit-identical on every reducer), applies Adam in the same epilogue and keeps W^T current, exactly like
+ * the one-rank launch.
+ *   mode 0  every rank reduces every tile: partials are pushed to ALL peers (one NVLink hop; (W-1) x arena x 8 bytes
+ *           out per rank and update) and every rank keeps the full Adam state - best for 2 ranks;
+ *   mode 1  tile t is reduced by rank t % world, which pushes the stepped parameters back to all peers (two hops,
+ *           2 x (W-1)/W x arena x 8 bytes out per rank); Adam moments exist only on the owner of an element
+ *           (cur_ddpg_rows_owner_map tells which) - best for 4..8 ranks.
+ * Region of a rank (cur_p2p_alloc / cur_p2p_open, zero-initialised, cur_xchg_region_bytes bytes):
+ *   [ partial slots: world x arena x 8 bytes, block s written by rank s | result slots: arena x 8 bytes ]
+ * The update number travelling with the data is (device step counter / micro_batches) + 1; it never repeats as long
+ * as the counter only grows (zero the regions collectively before moving the counter backwards).  A rank that waits
+ * longer than ~20 s for a peer sets *error_flag (if given) and traps. */
+typedef struct cur_xchg_ctx {
+  int32_t rank, world;
+  int32_t mode;
+  int32_t _pad;
+  void* region[CUR_MAX_RANKS]; /* region[r] as mapped in this process; region[rank] is the local one */
+  int64_t arena;               /* floats of the gradient / parameter arena */
+  int64_t* timeline;           /* optional DEVICE buffer [tiles][4] of %globaltimer stamps (ns): CTA start, tile computed and
+                                  pushed, reduced tile available (partials landed / result landed), CTA end */
+  int32_t* error_flag;         /* optional device int */
+} cur_xchg_ctx;
+int64_t cur_xchg_region_bytes(int64_t arena_floats, int world);
+
 typedef struct cur_adam_fused {
   float *m, *v;               /* Adam moments, same arena layout as theta */
   const float* neg_a_table;   /* float32(-a_t), t = 1..table_len (see cur_adam_step_graph) */
@@ -348,6 +377,7 @@ typedef struct cur_adam_fused {
    * last outside change of theta_main) - the transpose launch is skipped.  0: re-transpose first. */
   int32_t transposes_valid;
   double beta1, beta2, eps;
+  const cur_xchg_ctx* xchg;   /* several ranks: exchange the gradient tiles before the step (see cur_xchg_ctx); NULL: one rank */
 } cur_adam_fused;
 
 int cur_ddpg_rows_supported(const cur_net_desc* d, int64_t batch);
@@ -356,6 +386,9 @@ int cur_ddpg_rows_supported(const cur_net_desc* d, int64_t batch);
 int cur_ddpg_rows_refresh(void* stream, const cur_net_desc* d, const float* theta_main, float* workspace,
                           int64_t batch);
 int64_t cur_ddpg_rows_workspace_floats(const cur_net_desc* d, int64_t batch);
+/* Which rank reduces (and holds the Adam moments of) every element of the arena under cur_xchg_ctx mode 1: writes
+ * owner[arena] (HOST int32; -1 for padding) for the tile plan of this net / batch. */
+int cur_ddpg_rows_owner_map(const cur_net_desc* d, int64_t batch, int world, int32_t* owner /* host */);
 int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* theta_main,
                        const float* theta_target, const cur_norm_stats* stats,
                        const cur_batch* batch, const cur_ddpg_hyper* h, float* workspace,
@@ -391,6 +424,7 @@ int cur_p2p_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
 int cur_p2p_open(const unsigned char* handle64, void** ptr);
 int cur_p2p_close(void* ptr);
 int cur_p2p_free(void* ptr);
+int cur_p2p_zero(void* stream, void* ptr, int64_t bytes); /* cudaMemsetAsync(0) of (a part of) an own region */
 int cur_p2p_allreduce_adam(void* stream, const cur_p2p_ctx* ctx, float* theta, float* m, float* v,
                            const float* neg_a_table, int table_len, const int64_t* step_counter,
                            double beta1, double beta2, double eps, int32_t* error_flag /* or NULL */);

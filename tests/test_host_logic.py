@@ -21,22 +21,22 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
         assert name in _lib.SIGNATURES, 'ctypes signature missing for ' + name
-    assert lib.cur_abi_version() == 1
+    assert lib.cur_abi_version() == 2
 
 
 def test_ctypes_structs_match_header(tmp_path):
     from curious_b200 import _lib
     src = tmp_path / 'sz.cpp'
-    src.write_text('#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
+    src.write_text('#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
                    'sizeof(cur_layout),sizeof(cur_task_table),sizeof(cur_segment),sizeof(cur_her_args),'
                    'sizeof(cur_net_desc),sizeof(cur_batch),sizeof(cur_ddpg_hyper),sizeof(cur_norm_stats),'
-                   'sizeof(cur_episode_src),sizeof(cur_her_dyn),sizeof(cur_adam_fused),sizeof(cur_p2p_ctx),sizeof(cur_ddpg_expert));}\n' % os.path.join(ROOT, 'include', 'curious_b200.h'))
+                   'sizeof(cur_episode_src),sizeof(cur_her_dyn),sizeof(cur_adam_fused),sizeof(cur_p2p_ctx),sizeof(cur_ddpg_expert),sizeof(cur_xchg_ctx));}\n' % os.path.join(ROOT, 'include', 'curious_b200.h'))
     exe = tmp_path / 'sz'
     subprocess.check_call(['g++', str(src), '-o', str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(t) for t in (_lib.Layout, _lib.TaskTable, _lib.Segment, _lib.HerArgs, _lib.NetDesc, _lib.Batch,
                                   _lib.DdpgHyper, _lib.NormStats, _lib.EpisodeSrc, _lib.HerDyn, _lib.AdamFused,
-                                  _lib.P2PCtx, _lib.DdpgExpert)]
+                                  _lib.P2PCtx, _lib.DdpgExpert, _lib.XchgCtx)]
     assert got == want
 
 
@@ -331,3 +331,25 @@ def test_library_sass_is_blackwell_native():
     assert count(r'\bLDTM') >= 8 and count(r'\bUTMALDG') >= 8 and count(r'\bUBLKCP') >= 1
     assert count(r'\bUTCBAR\.2CTA') >= 1 and count(r'\bSYNCS\.') >= 20 and count(r'\bFFMA2\b') >= 500
     assert count(r'\bHMMA\b') == 0 and count(r'\bHGMMA\b') == 0
+
+
+def test_owner_map_of_the_tile_exchange_covers_every_parameter():
+    """cur_ddpg_rows_owner_map (host only): under mode 1 of the tile exchange every real parameter of the arena is reduced
+    by exactly one rank, the padding by none, and the tiles are spread round-robin (balanced to a few percent)."""
+    from curious_b200 import _lib
+    lib = _lib.load()
+    for d in (_lib.NetDesc(1, 40, 12, 4, 4, 256, 3, 1.0, 0, 5.0), _lib.NetDesc(1, 64, 24, 4, 8, 256, 3, 1.0, 1, 5.0),
+              _lib.NetDesc(0, 40, 12, 4, 0, 256, 2, 1.0, 0, 5.0)):
+        total = C.c_int64()
+        off_pi = lib.cur_theta_pi_offset(C.byref(d), C.byref(total))
+        nq, npi = lib.cur_net_param_count(C.byref(d), 0), lib.cur_net_param_count(C.byref(d), 1)
+        for world in (1, 2, 8):
+            owner = np.full(total.value, -7, np.int32)
+            _lib.check(lib.cur_ddpg_rows_owner_map(C.byref(d), 256, world, owner.ctypes.data), 'cur_ddpg_rows_owner_map')
+            real = np.zeros(total.value, bool)
+            real[:nq] = True
+            real[off_pi:off_pi + npi] = True
+            assert ((owner >= 0) == real).all()
+            assert owner[real].max() == world - 1
+            counts = np.bincount(owner[real], minlength=world)
+            assert counts.min() > 0.8 * counts.mean()

@@ -26,18 +26,24 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto', workers_per_rank=1, workers_mode='micro'):
+def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto', workers_per_rank=1, workers_mode='micro',
+            xchg_mode=None):
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
+    if xchg_mode is not None:
+        os.environ['CUR_XCHG_MODE'] = str(xchg_mode)
+    else:
+        os.environ.pop('CUR_XCHG_MODE', None)
     torch.cuda.set_device(rank)
     dev = torch.device('cuda', rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     try:
         from curious_b200 import parallel
         from tests.ddpg_util import ddpg_kwargs, episode_stream, make_gpu_agent
+        parallel.ORDERED_ALLREDUCE = True      # the NCCL arm sums in rank order (the reference for > 2 ranks)
         kw, dims, ag_ids, g_ids = ddpg_kwargs(4)
         # rank 1 starts from different weights: _sync_optimizers must broadcast rank 0's (ddpg.py:466)
         agent = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='philox', seed=rank, use_cuda_graph=use_graph,
@@ -47,7 +53,7 @@ def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto', workers
         theta0 = agent.theta_main.clone()
         gathered = [torch.empty_like(theta0) for _ in range(world)]
         dist.all_gather(gathered, theta0)
-        assert torch.equal(gathered[0], gathered[1]), 'init broadcast from rank 0 failed'
+        assert all(torch.equal(gathered[0], g) for g in gathered[1:]), 'init broadcast from rank 0 failed'
         np.random.seed(parallel.rank_seed(0, rank))                       # train.py:242
         n = 0
         for ep in episode_stream(dims, kw['T'], 6, seed=123 + rank):     # each rank owns its replay data
@@ -65,13 +71,20 @@ def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto', workers
             parts = [torch.empty_like(local) for _ in range(world)]
             dist.all_gather(parts, local)
             assert not torch.equal(parts[0], parts[1]), 'ranks must train on different batches'
-            expect = (parts[0] + parts[1])
+            expect = parts[0].clone()
+            for p in parts[1:]:
+                expect += p
             agent._update(agent._view(agent.grads, 'Q'), agent._view(agent.grads, 'pi'))
             assert torch.equal(agent.grads, expect), 'all-reduce must be a plain SUM'
         for _ in range(120):                                              # crosses the every-100 check_synced
             agent.train()
         if use_graph:
-            assert (agent._peer is not None) == (grad_exchange != 'nccl'), 'wrong gradient exchange path'
+            kind = 'tile' if grad_exchange == 'auto' else grad_exchange
+            assert (agent._xchg is not None) == (kind == 'tile'), 'wrong gradient exchange path'
+            assert (agent._peer is not None) == (kind in ('p2p', 'p2p_sharded')), 'wrong gradient exchange path'
+            if agent._xchg is not None:
+                assert agent._xchg.mode == (xchg_mode if xchg_mode is not None else (0 if world == 2 else 1))
+                assert int(agent._xchg.error_flag.item()) == 0
             if agent._peer is not None:
                 agent._peer.check()
         agent.update_target_net()
@@ -112,6 +125,25 @@ def test_peer_memory_exchange_equals_nccl_allreduce(tmp_path):
     assert np.array_equal(thetas['p2p_sharded'][0], thetas['nccl'][0])
 
 
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_tile_exchange_equals_rank_ordered_allreduce(world, tmp_path):
+    """The gradient exchange inside the weight-gradient launch (csrc/ddpg_rows.cu `cur_xchg_ctx`: LL pushes over NVLink
+    peer memory, sum in rank order, Adam + W^T in the same epilogue) in both modes - every rank reduces every tile /
+    tile t reduced by rank t % world - against an all-gather + rank-ordered sum + Adam launch after the graph:
+    120 updates, bit-identical parameters on every rank and between the three paths."""
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs %d GPUs' % world)
+    thetas = {}
+    for name, mode, xm in (('tile_all', 'tile', 0), ('tile_owner', 'tile', 1), ('nccl', 'nccl', None)):
+        d = tmp_path / name
+        d.mkdir()
+        mp.spawn(_worker, args=(world, _free_port(), True, str(d), mode, 1, 'micro', xm), nprocs=world, join=True)
+        thetas[name] = [np.load(os.path.join(str(d), 'theta%d.npy' % r)) for r in range(world)]
+        assert all(np.array_equal(thetas[name][0], t) for t in thetas[name][1:])
+    assert np.array_equal(thetas['tile_all'][0], thetas['nccl'][0])
+    assert np.array_equal(thetas['tile_owner'][0], thetas['nccl'][0])
+
+
 def test_two_ranks_with_two_workers_each(tmp_path):
     """4-worker-equivalent on 2 GPUs: every rank sums the gradients of its 2 batch-256 workers in the
     weight-gradient epilogue, the peer-memory kernel sums the ranks and steps Adam with t = launches / 2; the NCCL
@@ -121,13 +153,14 @@ def test_two_ranks_with_two_workers_each(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     thetas = {}
-    for mode, graph in (('p2p', True), ('nccl', True)):
+    for mode, graph in (('p2p', True), ('nccl', True), ('tile', True)):
         d = tmp_path / ('%s_%d' % (mode, graph))
         d.mkdir()
         mp.spawn(_worker, args=(2, _free_port(), graph, str(d), mode, 2), nprocs=2, join=True)
         thetas[(mode, graph)] = [np.load(os.path.join(str(d), 'theta%d.npy' % r)) for r in range(2)]
         assert np.array_equal(thetas[(mode, graph)][0], thetas[(mode, graph)][1])
     assert np.array_equal(thetas[('p2p', True)][0], thetas[('nccl', True)][0])
+    assert np.array_equal(thetas[('tile', True)][0], thetas[('nccl', True)][0])
 
 
 def test_two_ranks_wide_worker_batches(tmp_path):
@@ -136,10 +169,12 @@ def test_two_ranks_wide_worker_batches(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     thetas = {}
-    for mode in ('p2p', 'nccl'):
+    for mode in ('p2p', 'nccl', 'tile'):
         d = tmp_path / mode
         d.mkdir()
-        mp.spawn(_worker, args=(2, _free_port(), True, str(d), mode, 3, 'auto'), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, _free_port(), True, str(d), mode, 3, 'auto', 1 if mode == 'tile' else None),
+                 nprocs=2, join=True)
         thetas[mode] = [np.load(os.path.join(str(d), 'theta%d.npy' % r)) for r in range(2)]
         assert np.array_equal(thetas[mode][0], thetas[mode][1])
     assert np.array_equal(thetas['p2p'][0], thetas['nccl'][0])
+    assert np.array_equal(thetas['tile'][0], thetas['nccl'][0])

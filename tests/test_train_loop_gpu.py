@@ -106,3 +106,39 @@ def test_resumed_training_equals_uninterrupted(tmp_path):
         for tgt in (False, True):
             assert np.array_equal(pol_full.get_flat(which, tgt), pol_tail.get_flat(which, tgt)), (which, tgt)
     assert [b.current_size for b in pol_full.buffer] == [b.current_size for b in pol_tail.buffer]
+
+
+def test_make_experiment_applies_the_reference_rank_seeding(monkeypatch):
+    """train.py:241-243,328-335: rank_seed = seed + 1000000 * rank seeds np.random, the rollout workers (rank_seed, or
+    rank_seed + i per expert) and the evaluator (rank_seed + 100); here it also keys the Philox HER draws and the
+    device-side exploration noise.  Two ranks built from the same `seed` must therefore differ in every stream but start
+    from the same weights (rank 0's are broadcast, ddpg.py:466)."""
+    import curious_b200.train as tr
+    built = {}
+    for r in (0, 1):
+        monkeypatch.setattr(tr, '_rank', lambda comm=None, r=r: r)
+        exp = tr.make_experiment(nb_tasks=3, structure='curious', task_replay='replay_task_cp_buffer',
+                                 buffer_size=5000, seed=7)
+        pol, w, ev = exp['policy'], exp['rollout_worker'], exp['evaluator']
+        built[r] = dict(np_draw=float(np.random.uniform()), env_draw=float(w.envs[0].rng.uniform()),
+                        env1_draw=float(w.envs[1].rng.uniform()), eval_draw=float(ev.envs[0].rng.uniform()),
+                        philox=int(pol.sample_transitions.seed), noise=int(pol.noise_seed), theta=pol.get_flat('Q'))
+    a, b = built[0], built[1]
+    assert (a['philox'], a['noise']) == (7, 7) and (b['philox'], b['noise']) == (1000007, 1000007)
+    for key in ('np_draw', 'env_draw', 'env1_draw', 'eval_draw'):
+        assert a[key] != b[key], key
+    assert a['env_draw'] != a['env1_draw'] and a['env_draw'] != a['eval_draw']
+    assert np.array_equal(a['theta'], b['theta'])
+    # the same seed reproduces the streams (rank 0 again)
+    monkeypatch.setattr(tr, '_rank', lambda comm=None: 0)
+    exp = tr.make_experiment(nb_tasks=3, structure='curious', task_replay='replay_task_cp_buffer', buffer_size=5000, seed=7)
+    assert float(np.random.uniform()) == a['np_draw']
+    assert float(exp['rollout_worker'].envs[0].rng.uniform()) == a['env_draw']
+    # experts: worker i is seeded with rank_seed + i and draws its own Philox counter range
+    monkeypatch.setattr(tr, '_rank', lambda comm=None: 1)
+    exp = tr.make_experiment(nb_tasks=3, structure='task_experts', task_replay='replay_current_task_buffer',
+                             buffer_size=5000, seed=7)
+    offs = [p.GRAPH_STREAM_OFFSET for p in exp['policy']]
+    assert len(set(offs)) == 3 and [p.noise_seed for p in exp['policy']] == [1000007, 1000008, 1000009]
+    draws = [float(w.envs[0].rng.uniform()) for w in exp['rollout_worker']]
+    assert len(set(draws)) == 3
