@@ -8,11 +8,15 @@ step     ONE launch of the fused HER relabel+gather+reward+clip kernel over ROWS
          (4096 batches of 256), LP-apportioned over the module buffers, Philox draws, producing the
          staged training batch (o, g, u, task_descr, o_2, r).
 value    rows / device time (CUDA events), inputs resident in HBM, max over ranks, whole job.
-e2e      the reference's training cycle through the public plugin API with HOST episode buffers:
-         DDPG.store_episode(host episodes) + n_batches x DDPG.train() + DDPG.update_target_net()
-         + device->host read of the critic losses; transitions consumed per second.
---impl reference   the oracle port of that same cycle on the host cores (the reference is pure Python;
-         TF1/mpi4py/gym_flowers are not installable), one process per core up to 19.
+e2e      the reference's training cycle (experiment/train.py:148-155) through the public plugin API with HOST episode
+         buffers: DDPG.store_episode(host episodes) + 100 x DDPG.train() + DDPG.update_target_net() + device->host read
+         of the critic losses; transitions consumed per second.
+--impl reference   the oracle port of that SAME cycle (same n_batches) on the host cores (the reference is pure
+         Python; TF1/mpi4py/gym_flowers are not installable), one process per core up to 19.
+Also on the line: update_us / updates_per_s (device-timed train()), get_actions latency (n = 2, 38; host in -> host
+out), a rollout-inclusive cycle (50 x get_actions + store + 100 x train), the 19-worker-equivalent update, all of it
+again on the Arm8 shape (BASELINE config 4), and - several ranks - the bit-exact parity of the in-launch gradient
+exchange against an all-gather + rank-ordered sum (`exchange_parity`) and the per-rank scaling of the update.
 """
 import argparse
 import json
@@ -34,9 +38,22 @@ BUFFER_TRANSITIONS = 1000000
 BATCH = 256
 ROWS_PER_STEP = 1 << 20
 CP = [0.05, 0.2, 0.1, 0.0]
+CP8 = [0.05, 0.2, 0.1, 0.0, 0.0, 0.0, 0.0, 0.0]
 EPS_TASK = 0.4
-N_BATCHES_E2E = 100            # config.py:72
-REF_UPDATES_PER_STEP = 10      # bounded sample of the cycle for the CPU arm
+N_BATCHES = 100                # config.py:72 - the SAME cycle in both arms: store_episode + N_BATCHES x train + polyak
+ROLLOUT_STEPS = T              # get_actions calls per rollout (rollout.py:217,226: one per env step)
+
+
+def workload_config():
+    """The `config` of the JSON line - identical in both arms (--impl ours / reference)."""
+    return {'workload': 'arm4-shaped: 4 module buffers x 1e6 transitions (T=50, dimo=40, dimg=12, dimu=4, N=4), '
+                        'LP-apportioned (replay_task_cp_buffer, cp=%s, eps_task=%s), batch 256' % (CP, EPS_TASK),
+            'cycle': 'store_episode(2 host episodes) + %d x train + update_target_net (experiment/train.py:148-155)'
+                     % N_BATCHES,
+            'her_step': '%d rows per fused HER launch (= %d batches of 256), Philox draws' % (ROWS_PER_STEP,
+                                                                                              ROWS_PER_STEP // BATCH),
+            'l2': 'inputs (1.44 GB of replay rows per rank) and outputs (0.42 GB) exceed the 126 MB L2',
+            'rows_per_step': ROWS_PER_STEP, 'batch': BATCH, 'n_batches': N_BATCHES}
 
 
 def algorithmic_bytes_per_transition(dims, n_modules, g_len=3):
@@ -115,10 +132,13 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm), 'source': self.source}
 
 
+TRAFFIC_FILE = 'profiles/r01_her_traffic.json'
+
+
 def her_traffic_per_launch(rows_per_step):
     """DRAM bytes of one fused HER launch from the committed `ncu --set full` capture (profiles/), scaled to the
     rows of this launch; None if the capture is missing."""
-    p = os.path.join(ROOT, 'profiles', 'r01_her_traffic.json')
+    p = os.path.join(ROOT, TRAFFIC_FILE)
     try:
         t = json.load(open(p))
         return (t['dram_bytes_read'] + t['dram_bytes_write']) * rows_per_step / t['rows_per_launch']
@@ -139,10 +159,10 @@ def measured_peak_hbm():
 # ------------------------------------------------------------------------------------------------
 # workload construction
 # ------------------------------------------------------------------------------------------------
-def synth_dims():
+def synth_dims(n_modules=N_MODULES):
     from curious_b200 import synth
-    dims = synth.arm_dims(N_MODULES)
-    ag_ids, g_ids = synth.arm_task_ids(N_MODULES)
+    dims = synth.arm_dims(n_modules)
+    ag_ids, g_ids = synth.arm_task_ids(n_modules)
     return dims, ag_ids, g_ids
 
 
@@ -179,38 +199,45 @@ def fill_buffer_on_device(buf, dims, seed):
     buf.n_transitions_stored = E * T
 
 
-def build_gpu_workload(device, seed):
+def build_gpu_workload(device, seed, n_modules=N_MODULES):
+    """Arm4-shaped (BASELINE configs 2/3) or Arm8-shaped (config 4: 4 distractor modules, buffers 6..8 alias buffer 5,
+    ddpg.py:104-110) replay + agent factory."""
     from curious_b200 import her, synth
     from curious_b200.ddpg import DDPG
     from curious_b200.replay_buffer import ReplayBuffer
     from curious_b200.reward import ModuleDistanceReward
-    dims, ag_ids, g_ids = synth_dims()
+    dims, ag_ids, g_ids = synth_dims(n_modules)
     sampler = her.make_sample_multi_task_her_transitions('her', 4, 'replay_task_cp_buffer',
                                                          ModuleDistanceReward(ag_ids, g_ids), tasks_ag_id=ag_ids,
                                                          tasks_g_id=g_ids)
     sampler.rng = 'philox'
     sampler.seed = seed
     shapes = synth.buffer_shapes(dims, T)
-    buffers = [ReplayBuffer(shapes, BUFFER_TRANSITIONS if i > 0 else T, T, sampler, device=device)
-               for i in range(N_MODULES + 1)]          # buffer 0 is never written by the reference (ddpg.py:191)
-    for i in range(1, N_MODULES + 1):
-        fill_buffer_on_device(buffers[i], dims, seed * 100 + i)
+    n_real = min(n_modules, 5)                         # modules >= 5 are never stored (ddpg.py:183): buffers 6.. alias 5
+    buffers = [ReplayBuffer(shapes, BUFFER_TRANSITIONS if 0 < i <= n_real else T, T, sampler, device=device)
+               for i in range(n_modules + 1)]          # buffer 0 is never written by the reference (ddpg.py:191)
+    for i in range(1, n_real + 1):
+        fill_buffer_on_device(buffers[i], dims, seed * 100 + i + 10 * n_modules)
+    for i in range(6, n_modules + 1):
+        buffers[i] = buffers[5]
     gamma = 1. - 1. / T
+    cp = np.array(CP if n_modules == 4 else CP8)
 
     def make_agent(batch_size=BATCH, structure='curious', task_replay='replay_task_cp_buffer', **extra):
+        extra.setdefault('grad_exchange', os.environ.get('CUR_GRAD_EXCHANGE', 'auto'))
         a = DDPG(input_dims=dims, hidden=256, layers=3, network_class='baselines.her.actor_critic:MultiTaskActorCritic',
                  polyak=0.95, batch_size=batch_size, Q_lr=0.001, pi_lr=0.001, norm_eps=0.01, norm_clip=5, max_u=1.,
                  action_l2=1.0, clip_obs=200., scope='ddpg', T=T, rollout_batch_size=2,
                  subtract_goals=lambda a, b: a - b, relative_goals=False, clip_pos_returns=True,
                  clip_return=1. / (1. - gamma), normalize_obs=False, sample_transitions=sampler, gamma=gamma,
-                 buffers=buffers, tasks_ag_id=ag_ids, tasks_g_id=g_ids, task_replay=task_replay,
-                 eps_task=EPS_TASK, structure=structure, her_rng='philox', seed=0, device=device,
-                 grad_exchange=os.environ.get('CUR_GRAD_EXCHANGE', 'auto'), **extra)
-        a.cp = np.array(CP)
+                 buffers=list(buffers), tasks_ag_id=ag_ids, tasks_g_id=g_ids, task_replay=task_replay,
+                 eps_task=EPS_TASK, structure=structure, her_rng='philox', seed=0, device=device, **extra)
+        a.cp = cp
         return a
 
     agent = make_agent()
     agent.make_agent = make_agent
+    agent.bench_cp = cp
     return agent, sampler, buffers, dims, ag_ids, g_ids
 
 
@@ -279,53 +306,30 @@ def large_batch_sweep(agent, dims, torch):
     return {'batch_sweep': sweep, 'task_experts': experts, 'tf32_peak_tflops_assumed': bf16 / 2}
 
 
-def her_arm8_line(device, torch):
-    """BASELINE config 4 shape: MultiTaskFetchArm8-v5 (4 distractor modules; buffers 6..8 alias 5, ddpg.py:107-110),
-    dimo=64, dimg=dimag=24, N=8 -> 1340 algorithmic bytes per transition.  Same fused kernel, same launch."""
-    from curious_b200 import apportion, her, synth
-    from curious_b200.replay_buffer import ReplayBuffer
-    from curious_b200.reward import ModuleDistanceReward
-    n_mod = 8
-    dims = synth.arm_dims(n_mod)
-    ag_ids, g_ids = synth.arm_task_ids(n_mod)
-    sampler = her.make_sample_multi_task_her_transitions('her', 4, 'replay_task_cp_buffer',
-                                                         ModuleDistanceReward(ag_ids, g_ids), tasks_ag_id=ag_ids,
-                                                         tasks_g_id=g_ids)
-    sampler.rng = 'philox'
-    sampler.seed = 5
-    shapes = synth.buffer_shapes(dims, T)
-    buffers = [ReplayBuffer(shapes, BUFFER_TRANSITIONS if 0 < i <= 5 else T, T, sampler, device=device) for i in range(6)]
-    for i in range(1, 6):
-        fill_buffer_on_device(buffers[i], dims, 700 + i)
-    buffers += [buffers[5]] * 3                                       # distractor modules share one buffer
-    cp = np.array([0.05, 0.2, 0.1, 0.0, 0.0, 0.0, 0.0, 0.0])
-    sizes = [b.current_size for b in buffers]
-    prop = apportion.proportions_curious(sizes, T, ROWS_PER_STEP, 'replay_task_cp_buffer', cp, EPS_TASK)
-    segs = [(buffers[i].device_view(), int(prop[i]), i - 1) for i in range(1, len(buffers)) if prop[i] > 0]
-    out = {}
-    want = ('o', 'g', 'u', 'td', 'o_2', 'r')
-    ms = time_updates(lambda: sampler.sample_device(segs, ROWS_PER_STEP, clip_obs=200.0, want=want, out=out), 20, torch)
-    bpt = algorithmic_bytes_per_transition(dims, n_mod)
-    peak, _ = measured_peak_hbm()
-    achieved = bpt * ROWS_PER_STEP / (ms * 1e-3) / 1e9
-    del buffers, out
-    torch.cuda.empty_cache()
-    return {'transitions_per_s': ROWS_PER_STEP / (ms * 1e-3), 'ms_per_launch': ms, 'algorithmic_bytes_per_transition': bpt,
-            'achieved_gbs': achieved, 'frac_of_hbm_peak': achieved / peak,
-            'workload': 'arm8-shaped: 5 distinct module buffers x 1e6 transitions (dimo=64, dimg=24, dimu=4, N=8), '
-                        '%d rows per launch' % ROWS_PER_STEP}
-
-
-def her_step_segments(buffers, rows):
+def her_step_segments(buffers, rows, cp):
+    """LP apportioning of `rows` over the DISTINCT module buffers (aliased distractor buffers are sampled through every
+    module that points at them, like DDPG.sample_batch does, ddpg.py:326-336)."""
     from curious_b200 import apportion
     sizes = [b.current_size for b in buffers]
-    prop = apportion.proportions_curious(sizes, T, rows, 'replay_task_cp_buffer', np.array(CP), EPS_TASK)
+    prop = apportion.proportions_curious(sizes, T, rows, 'replay_task_cp_buffer', np.array(cp), EPS_TASK)
     return [(buffers[i].device_view(), int(prop[i]), i - 1) for i in range(1, len(buffers)) if prop[i] > 0]
 
 
-# ------------------------------------------------------------------------------------------------
-# CPU baseline (oracle port) - used by cpu_baseline and by --impl reference
-# ------------------------------------------------------------------------------------------------
+def her_line(sampler, buffers, dims, n_modules, cp, torch, label):
+    """One fused HER launch over ROWS_PER_STEP rows on this shape: transitions/s and fraction of the HBM roofline."""
+    segs = her_step_segments(buffers, ROWS_PER_STEP, cp)
+    out = {}
+    want = ('o', 'g', 'u', 'td', 'o_2', 'r')
+    ms = time_updates(lambda: sampler.sample_device(segs, ROWS_PER_STEP, clip_obs=200.0, want=want, out=out), 20, torch)
+    bpt = algorithmic_bytes_per_transition(dims, n_modules)
+    peak, _ = measured_peak_hbm()
+    achieved = bpt * ROWS_PER_STEP / (ms * 1e-3) / 1e9
+    del out
+    torch.cuda.empty_cache()
+    return {'transitions_per_s': ROWS_PER_STEP / (ms * 1e-3), 'ms_per_launch': ms, 'algorithmic_bytes_per_transition': bpt,
+            'achieved_gbs': achieved, 'frac_of_hbm_peak': achieved / peak, 'workload': label}
+
+
 def build_cpu_workload(seed, episodes_per_buffer):
     from curious_b200 import synth
     from oracle import ddpg_oracle, her_oracle, replay_oracle
@@ -404,7 +408,8 @@ def _ref_worker(rank, n_steps, n_warm, updates, episodes_per_buffer, q):
 def run_reference_arm(args):
     """The training cycle of the reference restated on the CPU (oracle port), one single-threaded process per
     worker like the reference's `mpirun -np 19 --bind-to core` (train.py:221-231); no all-reduce is modelled, so
-    this over-estimates the CPU arm.  Each step is a bounded sample of the cycle: REF_UPDATES_PER_STEP updates."""
+    this over-estimates the CPU arm.  Each step is ONE cycle of the ours-arm's e2e: store_episode + N_BATCHES x train +
+    update_target_net (a bounded sample of the job: `steps` cycles per worker)."""
     import multiprocessing as mp
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -421,7 +426,7 @@ def run_reference_arm(args):
         pass
     ctx = mp.get_context('fork')
     q = ctx.Queue()
-    workers = [ctx.Process(target=_ref_worker, args=(r, args.steps, args.warmup, REF_UPDATES_PER_STEP, episodes, q))
+    workers = [ctx.Process(target=_ref_worker, args=(r, args.steps, args.warmup, N_BATCHES, episodes, q))
                for r in range(procs)]
     for w in workers:
         w.start()
@@ -434,27 +439,187 @@ def run_reference_arm(args):
         w.join()
     per_step = np.max(np.array([done[r] for r in range(procs)]), axis=0)      # slowest worker per step
     total = float(per_step.sum())
-    value = procs * REF_UPDATES_PER_STEP * BATCH * args.steps / total
-    dims, _, _ = synth_dims()
+    value = procs * N_BATCHES * BATCH * args.steps / total
     line = {
         'impl': 'reference', 'metric': 'HER-relabelled transitions/s', 'value': value, 'unit': 'transitions/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'arm4-shaped: 4 module buffers x 1e6 transitions (T=50, dimo=40, dimg=12, dimu=4, N=4), '
-                               'batch 256, replay_task_cp_buffer; CPU arm = training cycle store_episode + %d x train + '
-                               'update_target_net per step' % REF_UPDATES_PER_STEP},
+        'config': workload_config(),
+        'what': 'CPU arm: the training cycle of `config.cycle` on %d single-threaded worker processes (one per core up '
+                'to 19, like mpirun -np 19 --bind-to core); value = transitions consumed by the updates per second, '
+                'all workers' % procs,
         'cpu_baseline': {'value': value, 'unit': 'transitions/s', 'cores': procs, 'kind': 'port',
-                         'sample': '%d single-threaded worker processes x %d steps x %d updates of batch %d (oracle '
+                         'sample': '%d single-threaded worker processes x %d cycles x %d updates of batch %d (oracle '
                                    'NumPy port of her.py/replay_buffer.py/ddpg.py/mpi_adam.py; TF1 graph restated in '
-                                   'float32 NumPy/BLAS)' % (procs, args.steps, REF_UPDATES_PER_STEP, BATCH)},
+                                   'float32 NumPy/BLAS; no all-reduce modelled)' % (procs, args.steps, N_BATCHES, BATCH)},
         'e2e': {'value': value, 'unit': 'transitions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'updates_per_s': procs * REF_UPDATES_PER_STEP * args.steps / total,
+        'updates_per_s': procs * N_BATCHES * args.steps / total,
+        'update_us_per_worker': 1e6 * total / (N_BATCHES * args.steps),
         'host_cores': cores,
     }
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
+def measure_agent(agent, dims, n_modules, world, rank, barrier, torch, dist, device, full=True):
+    """Everything the line reports per shape (Arm4 / Arm8): device-timed update, the e2e training cycle through the
+    plugin API with host episodes, get_actions latency, the rollout-inclusive cycle, the 19-worker-equivalent update."""
+    from curious_b200 import synth
+    cp = agent.bench_cp
+    res = {}
+    # ---- DDPG updates/s: device-timed train() (sample + grads + gradient exchange + Adam) through the public API
+    for _ in range(5):
+        agent.train()
+    barrier()
+    n_upd = 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_upd):
+        agent.train()
+    e1.record()
+    barrier()
+    upd_ms = e0.elapsed_time(e1)
+    # ---- e2e: training cycles through the plugin API with host episode buffers
+    rng = np.random.RandomState(99 + rank)
+    host_eps = [synth.make_episodes(rng, 2, T, dims, change_dtype=bool) for _ in range(8)]
+    h2d = sum(np.asarray(v).size * 4 for v in host_eps[0].values())
+
+    def cycle(i):
+        agent.store_episode({k: v for k, v in host_eps[i % len(host_eps)].items()}, cp, 2 * (i + 1))
+        losses = [agent.train()[0] for _ in range(N_BATCHES)]
+        agent.update_target_net()
+        return torch.stack([l.tensor for l in losses]).cpu().numpy()          # device->host read of the results
+
+    for i in range(3):
+        cycle(i)
+    barrier()
+    n_cyc = 10
+    t0 = time.perf_counter()
+    for i in range(n_cyc):
+        out = cycle(3 + i)
+    barrier()
+    cyc_s = time.perf_counter() - t0
+    # ---- get_actions latency, host arrays in -> host actions out (rollout.py:217,226: one call per env step; n = 2 is
+    # the reference's rollout_batch_size, n = 38 the 19 workers' environments batched on one rank)
+    ga = {}
+    for n in (2, 38):
+        o = rng.standard_normal((n, dims['o'])).astype(np.float32)
+        ag = rng.uniform(-0.15, 0.15, (n, dims['ag'])).astype(np.float32)
+        g = rng.uniform(-0.15, 0.15, (n, dims['g'])).astype(np.float32)
+        td = np.eye(n_modules, dtype=np.float32)[rng.randint(0, n_modules, n)]
+        for _ in range(20):
+            agent.get_actions(o, ag, g, task_descr=td, noise_eps=0.2, random_eps=0.3)
+        reps = 300
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            agent.get_actions(o, ag, g, task_descr=td, noise_eps=0.2, random_eps=0.3)
+        dt = time.perf_counter() - t0
+        ga['n%d' % n] = {'us_per_call': 1e6 * dt / reps, 'actions_per_s': n * reps / dt}
+    # ---- rollout-inclusive cycle: ROLLOUT_STEPS x get_actions(n = 2) (the device round trips of one rollout; the
+    # environment itself stays on the host and is not modelled) + store_episode + N_BATCHES x train + update_target_net
+    o2 = rng.standard_normal((2, dims['o'])).astype(np.float32)
+    ag2 = rng.uniform(-0.15, 0.15, (2, dims['ag'])).astype(np.float32)
+    g2 = rng.uniform(-0.15, 0.15, (2, dims['g'])).astype(np.float32)
+    td2 = np.eye(n_modules, dtype=np.float32)[[0, 1]]
+
+    def rollout_cycle(i):
+        for _ in range(ROLLOUT_STEPS):
+            agent.get_actions(o2, ag2, g2, task_descr=td2, noise_eps=0.2, random_eps=0.3)
+        return cycle(i)
+
+    rollout_cycle(0)
+    barrier()
+    n_rc = 5
+    t0 = time.perf_counter()
+    for i in range(n_rc):
+        rollout_cycle(20 + i)
+    barrier()
+    rc_s = time.perf_counter() - t0
+    # ---- 19-worker-equivalent (BASELINE config 4 / SURVEY 8e): the reference's 19 MPI workers spread over the ranks,
+    # ceil(19 / world) batch-256 workers per GPU, gradients summed per rank and across ranks, one Adam step
+    k19 = -(-19 // world)
+    agent19 = agent.make_agent(workers_per_rank=k19)
+    for _ in range(3):
+        agent19.train()
+    barrier()
+    n19 = 30
+    e0.record()
+    for _ in range(n19):
+        agent19.train()
+    e1.record()
+    barrier()
+    upd19_ms = e0.elapsed_time(e1)
+    sched19 = 'rows' if agent19._use_rows(agent19._graph_rows) else 'levels (tcgen05)'
+    exch19 = 'tile' if agent19._xchg is not None else ('p2p' if agent19._peer is not None else ('nccl' if world > 1 else None))
+    del agent19
+    torch.cuda.empty_cache()
+    vals = [upd_ms, cyc_s, upd19_ms, rc_s, ga['n2']['us_per_call'], ga['n38']['us_per_call']]
+    if world > 1:
+        tt = torch.tensor(vals, device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        vals = [float(x) for x in tt.cpu()]
+    upd_ms, cyc_s, upd19_ms, rc_s, ga2, ga38 = vals
+    res['update_us'] = 1e3 * upd_ms / n_upd
+    res['updates_per_s'] = world * n_upd / (upd_ms * 1e-3)
+    res['update_schedule'] = 'rows' if agent._use_rows(BATCH) else 'levels'
+    res['grad_exchange'] = ('tile' if getattr(agent, '_xchg', None) is not None else
+                            'p2p' if getattr(agent, '_peer', None) is not None else 'nccl') if world > 1 else None
+    if getattr(agent, '_xchg', None) is not None:
+        res['grad_exchange_mode'] = int(agent._xchg.mode)
+    res['e2e'] = {'value': world * n_cyc * N_BATCHES * BATCH / cyc_s, 'unit': 'transitions/s',
+                  'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(out.nbytes),
+                  'what': 'DDPG.store_episode(host) + %d x DDPG.train() + update_target_net + loss readback per cycle'
+                          % N_BATCHES, 'cycle_ms': 1e3 * cyc_s / n_cyc,
+                  'updates_per_s': world * n_cyc * N_BATCHES / cyc_s}
+    res['get_actions'] = {'n2_us_per_call': ga2, 'n38_us_per_call': ga38, 'n38_actions_per_s': 38 * 1e6 / ga38,
+                          'what': 'DDPG.get_actions(host o, ag, g, task_descr; noise_eps 0.2, random_eps 0.3) -> host '
+                                  'actions, wall clock per call, max over ranks'}
+    res['rollout_cycle'] = {'cycle_ms': 1e3 * rc_s / n_rc,
+                            'transitions_per_s': world * n_rc * N_BATCHES * BATCH / rc_s,
+                            'what': '%d x get_actions(n = 2) + store_episode + %d x train + update_target_net + loss '
+                                    'readback (environment stepping not modelled)' % (ROLLOUT_STEPS, N_BATCHES)}
+    res['workers19_equivalent'] = {'workers_per_rank': k19, 'workers': k19 * world, 'global_batch': k19 * world * BATCH,
+                                   'update_us': 1e3 * upd19_ms / n19, 'updates_per_s': n19 / (upd19_ms * 1e-3),
+                                   'transitions_per_s': k19 * world * BATCH * n19 / (upd19_ms * 1e-3),
+                                   'schedule': sched19, 'grad_exchange': exch19}
+    return res
+
+
+def exchange_parity(agent, world, rank, torch, dist, device, n_updates=8):
+    """Several ranks: the same updates through the in-launch tile exchange and through an all-gather + RANK-ORDERED sum +
+    Adam launch on identical gradients (fresh twin agents: same weights, same replay, same Philox counters) must end on
+    bit-identical parameters on every rank.  Also reports the distance to NCCL's own all-reduce, whose summation order
+    is its algorithm's (equal for 2 ranks, a few ulp otherwise)."""
+    from curious_b200 import parallel
+    thetas = {}
+    for name, ge, ordered in (('tile', 'auto', False), ('ordered', 'nccl', True), ('nccl', 'nccl', False)):
+        parallel.ORDERED_ALLREDUCE = ordered
+        a = agent.make_agent(grad_exchange=ge)
+        for _ in range(n_updates):
+            a.train()
+        a.update_target_net()
+        torch.cuda.synchronize()
+        thetas[name] = a.theta_main.clone()
+        kind = 'tile' if a._xchg is not None else ('p2p' if a._peer is not None else 'nccl')
+        if name == 'tile':
+            used = kind
+        del a
+        torch.cuda.empty_cache()
+        dist.barrier()
+    parallel.ORDERED_ALLREDUCE = False
+    bad = torch.tensor([0 if torch.equal(thetas['tile'], thetas['ordered']) else 1], device=device)
+    # ... and every rank holds rank 0's parameters
+    ref = thetas['tile'].clone()
+    dist.broadcast(ref, src=0)
+    bad += 0 if torch.equal(ref, thetas['tile']) else 1
+    dist.all_reduce(bad)
+    diff = (thetas['tile'] - thetas['nccl']).abs().max()
+    dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    return {'exchange_parity': int(bad.item()) == 0, 'exchange': used, 'updates': n_updates,
+            'max_abs_diff_vs_nccl_allreduce': float(diff.item()),
+            'against': 'all-gather + rank-ordered float32 sum + Adam launch (parallel.ORDERED_ALLREDUCE)'}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -469,7 +634,7 @@ def run_ours(args):
     from curious_b200 import _lib
     _lib.load()
     agent, sampler, buffers, dims, ag_ids, g_ids = build_gpu_workload(device, seed=1 + rank)
-    segs = her_step_segments(buffers, ROWS_PER_STEP)
+    segs = her_step_segments(buffers, ROWS_PER_STEP, CP)
     want = ('o', 'g', 'u', 'td', 'o_2', 'r')
     out = {}
 
@@ -494,59 +659,42 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    # ---- DDPG updates/s: device-timed train() (sample + grads + all-reduce + Adam) through the public API
-    for _ in range(5):
-        agent.train()
-    barrier()
-    n_upd = 200
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n_upd):
-        agent.train()
-    e1.record()
-    barrier()
-    upd_ms = e0.elapsed_time(e1)
-    # ---- 19-worker-equivalent (BASELINE config 4 / SURVEY 8e): the reference's 19 MPI workers spread over the ranks,
-    # ceil(19 / world) batch-256 workers per GPU, gradients summed per rank and across ranks, one Adam step
-    k19 = -(-19 // world)
-    agent19 = agent.make_agent(workers_per_rank=k19)
-    for _ in range(3):
-        agent19.train()
-    barrier()
-    n19 = 30
-    e0.record()
-    for _ in range(n19):
-        agent19.train()
-    e1.record()
-    barrier()
-    upd19_ms = e0.elapsed_time(e1)
-    del agent19
-    # ---- e2e: training cycles through the plugin API with host episode buffers
-    from curious_b200 import synth
-    rng = np.random.RandomState(99 + rank)
-    host_eps = [synth.make_episodes(rng, 2, T, dims, change_dtype=bool) for _ in range(8)]
-    h2d = sum(np.asarray(v).size * 4 for v in host_eps[0].values())
-
-    def cycle(i):
-        agent.store_episode({k: v for k, v in host_eps[i % len(host_eps)].items()}, np.array(CP), 2 * (i + 1))
-        losses = [agent.train()[0] for _ in range(N_BATCHES_E2E)]
-        agent.update_target_net()
-        return torch.stack([l.tensor for l in losses]).cpu().numpy()          # device->host read of the results
-
-    for i in range(3):
-        cycle(i)
-    barrier()
-    n_cyc = 10
-    t0 = time.perf_counter()
-    for i in range(n_cyc):
-        res = cycle(3 + i)
-    barrier()
-    cyc_s = time.perf_counter() - t0
+    del out
+    arm4 = measure_agent(agent, dims, N_MODULES, world, rank, barrier, torch, dist, device)
     clock_info = clocks.stop()
     if world > 1:
-        tt = torch.tensor([ms, upd_ms, cyc_s, upd19_ms], device=device, dtype=torch.float64)
+        tt = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, upd_ms, cyc_s, upd19_ms = [float(x) for x in tt.cpu()]
+        ms = float(tt.item())
+    # ---- several ranks: how much one rank's update costs next to a world of one on the same GPU, and the parity check
+    scaling = parity = None
+    if world > 1:
+        solo = agent.make_agent(comm=False)
+        for _ in range(5):
+            solo.train()
+        solo_ms = time_updates(solo.train, 200, torch)
+        del solo
+        tt = torch.tensor([solo_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        solo_us = 1e3 * float(tt.item())
+        scaling = {'single_rank_update_us': solo_us, 'per_rank_update_us': arm4['update_us'],
+                   'efficiency': solo_us / arm4['update_us'],
+                   'what': 'device-timed train() of one rank alone (comm=False, same GPU, same run) / the same inside the '
+                           '%d-rank job: the weak-scaling efficiency of the path that has a collective' % world}
+        parity = exchange_parity(agent, world, rank, torch, dist, device)
+    # ---- BASELINE config 4: the Arm8 shape (dimo 64, dimg 24, N 8, buffers 6..8 aliased), same measurements
+    agent8, sampler8, buffers8, dims8, _, _ = build_gpu_workload(device, seed=50 + rank, n_modules=8)
+    arm8 = measure_agent(agent8, dims8, 8, world, rank, barrier, torch, dist, device)
+    her8 = None
+    if world == 1:
+        her8 = her_line(sampler8, buffers8, dims8, 8, CP8, torch,
+                        'arm8-shaped: 5 distinct module buffers x 1e6 transitions (dimo=64, dimg=24, dimu=4, N=8), '
+                        '%d rows per launch' % ROWS_PER_STEP)
+    if world > 1 and parity is not None and not parity['exchange_parity']:
+        if rank == 0:
+            print(json.dumps({'error': 'exchange_parity failed', 'detail': parity}))
+        dist.destroy_process_group()
+        sys.exit(3)
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         bpt = algorithmic_bytes_per_transition(dims, N_MODULES)
@@ -557,35 +705,38 @@ def run_ours(args):
             'unit': 'transitions/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': kernel_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'arm4-shaped: 4 module buffers x 1e6 transitions (T=50, dimo=40, dimg=12, dimu=4, '
-                                   'N=4), LP-apportioned (replay_task_cp_buffer, cp=%s), %d rows per fused launch '
-                                   '(= %d batches of 256), Philox draws' % (CP, ROWS_PER_STEP, ROWS_PER_STEP // BATCH),
-                       'l2': 'inputs (1.44 GB of replay rows per rank) and outputs (0.42 GB) exceed the 126 MB L2',
-                       'rows_per_step': ROWS_PER_STEP, 'batch': BATCH},
+            'config': workload_config(),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': her_traffic_per_launch(ROWS_PER_STEP), 'peak_source': peak_src,
+                         'traffic': her_traffic_per_launch(ROWS_PER_STEP),
+                         'traffic_source': 'static: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` '
+                                           'capture of this kernel on this workload (%s), scaled to the rows of a '
+                                           'launch; not measured in this run' % TRAFFIC_FILE,
+                         'peak_source': peak_src,
                          'algorithmic_bytes': bpt * ROWS_PER_STEP, 'algorithmic_bytes_per_transition': bpt,
                          'kernel': 'her_sample_kernel'},
-            'e2e': {'value': world * n_cyc * N_BATCHES_E2E * BATCH / cyc_s, 'unit': 'transitions/s',
-                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(res.nbytes),
-                    'what': 'DDPG.store_episode(host) + %d x DDPG.train() + update_target_net + loss readback per cycle'
-                            % N_BATCHES_E2E, 'cycle_ms': 1e3 * cyc_s / n_cyc,
-                    'updates_per_s': world * n_cyc * N_BATCHES_E2E / cyc_s},
+            'e2e': arm4['e2e'],
             'gpu_launches': args.steps,
             'clocks': clock_info,
-            'updates_per_s': world * n_upd / (upd_ms * 1e-3),
-            'update_us': 1e3 * upd_ms / n_upd,
-            'update_schedule': 'rows' if agent._use_rows(BATCH) else 'levels',
-            'workers19_equivalent': {'workers_per_rank': k19, 'workers': k19 * world, 'global_batch': k19 * world * BATCH,
-                                     'update_us': 1e3 * upd19_ms / n19, 'updates_per_s': n19 / (upd19_ms * 1e-3),
-                                     'transitions_per_s': k19 * world * BATCH * n19 / (upd19_ms * 1e-3)},
+            'updates_per_s': arm4['updates_per_s'], 'update_us': arm4['update_us'],
+            'update_schedule': arm4['update_schedule'], 'grad_exchange': arm4['grad_exchange'],
+            'get_actions': arm4['get_actions'], 'rollout_cycle': arm4['rollout_cycle'],
+            'workers19_equivalent': arm4['workers19_equivalent'],
+            'arm8': dict(arm8, workload='arm8-shaped (BASELINE config 4): dimo=64, dimg=dimag=24, dimu=4, N=8, 5 distinct '
+                                        'module buffers x 1e6 transitions, buffers 6..8 alias buffer 5, modules >= 5 never '
+                                        'stored (ddpg.py:104-110,183), cp=%s' % CP8),
         }
+        if 'grad_exchange_mode' in arm4:
+            line['grad_exchange_mode'] = arm4['grad_exchange_mode']
+        if scaling is not None:
+            line['scaling_e2e'] = scaling
+            line.update(parity)
+        if her8 is not None:
+            line['her_arm8'] = her8
         if world == 1 and not args.no_sweep:
             line['ddpg_update'] = large_batch_sweep(agent, dims, torch)
-            line['her_arm8'] = her_arm8_line(device, torch)
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_sampler_baseline()
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

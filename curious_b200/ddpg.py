@@ -29,7 +29,7 @@ from .mpi_adam import MpiAdam, adam_step_scale
 from .normalizer import Normalizer
 from .parallel import allreduce_sum_, world as _world
 from .replay_buffer import StagedEpisodes, episodes_to_device
-from .util import LazyHost, dims_to_shapes, import_function, store_args, transitions_in_episode_batch
+from .util import LazyHost, capture_graph, dims_to_shapes, import_function, store_args, transitions_in_episode_batch
 
 
 _ADAM_TABLES = {}
@@ -625,7 +625,7 @@ class DDPG(object):
         if keeps_wT:
             self._ghyper.transposes_valid = 1
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with capture_graph(g):
             # fused Adam: its epilogue keeps W^T current, so the captured update has no transpose launch
             fused = self._launch_sample_and_grads(keep_wT=fused)
             if self._graph_has_adam and not fused:

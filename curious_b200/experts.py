@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .parallel import allreduce_sum_, world as _world
-from .util import LazyHost
+from .util import LazyHost, capture_graph
 
 
 class TaskExperts(object):
@@ -103,7 +103,7 @@ class TaskExperts(object):
                 dst.copy_(src)
         self._single_rank = _world(self.policies[0].comm)[1] == 1
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with capture_graph(g):
             self._launch(True)
             if self._single_rank:
                 for p in self.policies:

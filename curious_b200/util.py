@@ -1,5 +1,7 @@
 """Thin glue kept from reference baselines/her/util.py (only what the hot path's callers use)."""
+import contextlib
 import functools
+import gc
 import importlib
 import inspect
 
@@ -112,3 +114,20 @@ class LazyHost:
     @property
     def shape(self):
         return tuple(self.tensor.shape)
+
+
+@contextlib.contextmanager
+def capture_graph(graph):
+    """torch.cuda.graph(graph) with the Python garbage collector held off: a CUDAGraph of a dropped agent that the
+    collector frees while this capture is open calls cudaGraphExecDestroy on the capturing thread, which CUDA answers
+    by invalidating the capture (cudaErrorStreamCaptureInvalidated)."""
+    import torch
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph):
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
