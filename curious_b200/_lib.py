@@ -37,12 +37,19 @@ class Segment(C.Structure):
                 ('task_to_replay', C.c_int32), ('_pad', C.c_int32)]
 
 
+REWARD_DISTANCE, REWARD_PAIR, REWARD_INFO = 0, 1, 2
+
+
 class TaskTable(C.Structure):
-    _fields_ = [('n_tasks', C.c_int32), ('reward_kind', C.c_int32),
+    _fields_ = [('n_tasks', C.c_int32), ('_pad', C.c_int32),
                 ('len', C.c_int32 * CUR_MAX_TASKS),
                 ('g_idx', (C.c_int16 * CUR_MAX_SLICE) * CUR_MAX_TASKS),
                 ('ag_idx', (C.c_int16 * CUR_MAX_SLICE) * CUR_MAX_TASKS),
-                ('threshold', C.c_double),
+                ('ref_idx', (C.c_int16 * CUR_MAX_SLICE) * CUR_MAX_TASKS),
+                ('kind', C.c_int32 * CUR_MAX_TASKS),
+                ('info_col', C.c_int32 * CUR_MAX_TASKS),
+                ('threshold', C.c_double * CUR_MAX_TASKS),
+                ('flat_threshold', C.c_double),
                 ('cdf', C.c_double * CUR_MAX_TASKS)]
 
 
@@ -129,6 +136,7 @@ SIGNATURES = {
                                      C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_int64)]),
     'cur_her_sample': (C.c_int, [C.c_void_p, C.POINTER(HerArgs)]),
+    'cur_philox4x32_10': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'cur_norm_accumulate': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     'cur_norm_recompute': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int,
                                      C.c_void_p, C.c_void_p]),
@@ -239,23 +247,35 @@ def make_layout(T, dimo, dimag, dimg, dimu, dimtd=0, dimchange=0, diminfo=0):
     return L
 
 
-def make_task_table(tasks_ag_id, tasks_g_id, threshold=0.05, cp_proba=None, reward_kind=0):
+def make_task_table(tasks_ag_id, tasks_g_id, threshold=0.05, cp_proba=None, kinds=None, ref_ag_id=None, info_cols=None,
+                    flat_threshold=None):
+    """cur_task_table: per module the goal / achieved-goal columns and its reward rule (kind, threshold, and for PAIR the
+    second achieved-goal slice, for INFO the column of the stored info row).  `threshold` is a scalar or one per module."""
     tt = TaskTable()
     n = len(tasks_g_id) if tasks_g_id is not None else 0
     if n > CUR_MAX_TASKS:
         raise ValueError('at most %d modules are supported' % CUR_MAX_TASKS)
     tt.n_tasks = n
-    tt.reward_kind = reward_kind
-    tt.threshold = float(threshold)
+    thr = np.broadcast_to(np.asarray(threshold, np.float64), (n,)) if n else np.zeros(0)
+    tt.flat_threshold = float(flat_threshold if flat_threshold is not None else (thr[0] if n else 0.05))
     for m in range(n):
         g_ids = list(tasks_g_id[m])
         ag_ids = list(tasks_ag_id[m])[:len(g_ids)]     # her.py:147-148
         if len(g_ids) > CUR_MAX_SLICE:
             raise ValueError('module goal slices longer than %d are not supported' % CUR_MAX_SLICE)
         tt.len[m] = len(g_ids)
+        tt.kind[m] = int(kinds[m]) if kinds is not None else REWARD_DISTANCE
+        tt.threshold[m] = float(thr[m])
+        tt.info_col[m] = int(info_cols[m]) if info_cols is not None and info_cols[m] is not None else 0
         for k, (gi, ai) in enumerate(zip(g_ids, ag_ids)):
             tt.g_idx[m][k] = int(gi)
             tt.ag_idx[m][k] = int(ai)
+        if tt.kind[m] == REWARD_PAIR:
+            ref = list(ref_ag_id[m])[:len(g_ids)]
+            if len(ref) != len(g_ids):
+                raise ValueError('module %d: the PAIR reward needs a reference slice as long as the goal slice' % m)
+            for k, ri in enumerate(ref):
+                tt.ref_idx[m][k] = int(ri)
     if cp_proba is not None:
         set_cdf(tt, cp_proba)
     return tt

@@ -340,13 +340,14 @@ __device__ __forceinline__ void sample_rows(const StreamParams& P, int64_t row0,
   if (tid < S_ROWS) her_draw_row(P.her, pl, row0 + tid, row, m_src + 3 * tid);
   consumer_sync();
   if (warp < S_ROWS) {
-    const int per_row = pl.img4 + pl.fut4;           // (cold rows are never needed here)
+    const int per_row = pl.img4 + pl.fut4 + pl.cold4;   // (cold rows only when a module's reward reads `info`)
     float* dst = stage + warp * pl.stage_stride;
     for (int c = lane; c < per_row; c += 32) {
-      const bool fut = c >= pl.img4;
-      const int q = fut ? c - pl.img4 : c;
-      const float* src = m_src[3 * warp + (fut ? 1 : 0)];
-      if (src != nullptr) cp16_zfill(dst + (fut ? pl.fut_off : 0) + 4 * q, src + 4 * q, true);
+      int sel = 0, q = c, doff = 4 * c;
+      if (c >= pl.img4 + pl.fut4) { sel = 2; q = c - pl.img4 - pl.fut4; doff = pl.cold_off + 4 * q; }
+      else if (c >= pl.img4) { sel = 1; q = c - pl.img4; doff = pl.fut_off + 4 * q; }
+      const float* src = m_src[3 * warp + sel];
+      if (src != nullptr) cp16_zfill(dst + doff, src + 4 * q, true);
     }
   }
   cp_commit();
@@ -1367,10 +1368,13 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
                 her->L.dimtd == (d->modular ? d->dimtd : her->L.dimtd), "HER layout does not match the networks");
     CUR_REQUIRE(!her->relative_goals || her->L.dimag == her->L.dimg, "relative goals need dimg == dimag");
     P.her = *her;
-    P.her.change = nullptr; P.her.info = nullptr;         // cold rows are not needed
+    P.her.change = nullptr; P.her.info = nullptr;         // cold rows travel only for an INFO reward (make_plan)
     P.her.ag = nullptr;                                    // (ag_t is staged iff relative_goals)
     make_plan(P.her, &P.plan);
     CUR_REQUIRE(S_ROWS * P.plan.stage_stride <= S_MISC - S_STAGE_OFF, "transition too wide for the fused HER stage");
+    if (P.plan.cold4 > 0)
+      for (int i = 0; i < her->n_segments; ++i)
+        CUR_REQUIRE(her->seg[i].cold != nullptr, "an INFO reward needs the cold rows of every segment");
     P.fused_her = 1;
   }
 

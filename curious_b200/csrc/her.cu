@@ -396,7 +396,12 @@ extern "C" int cur_her_sample(void* stream, const cur_her_args* args) {
     for (int k = 0; k < a.tasks.len[m]; ++k) {
       CUR_REQUIRE(a.tasks.g_idx[m][k] >= 0 && a.tasks.g_idx[m][k] < a.L.dimg, "g index out of range");
       CUR_REQUIRE(a.tasks.ag_idx[m][k] >= 0 && a.tasks.ag_idx[m][k] < a.L.dimag, "ag index out of range");
+      if (a.tasks.kind[m] == CUR_REWARD_PAIR)
+        CUR_REQUIRE(a.tasks.ref_idx[m][k] >= 0 && a.tasks.ref_idx[m][k] < a.L.dimag, "reference ag index out of range");
     }
+    CUR_REQUIRE(a.tasks.kind[m] >= CUR_REWARD_DISTANCE && a.tasks.kind[m] <= CUR_REWARD_INFO, "unknown reward kind");
+    if (a.tasks.kind[m] == CUR_REWARD_INFO)
+      CUR_REQUIRE(a.tasks.info_col[m] >= 0 && a.tasks.info_col[m] < a.L.diminfo, "info column out of range");
   }
   if (a.inj_ep != nullptr)
     CUR_REQUIRE(a.inj_t && a.inj_u_her && a.inj_u_off, "incomplete injected stream");
@@ -419,6 +424,23 @@ extern "C" int cur_her_sample(void* stream, const cur_her_args* args) {
   const int64_t blocks = (a.batch + TILE - 1) / TILE;
   CUR_REQUIRE(blocks <= 0x7fffffff, "batch too large for one launch");
   her_sample_kernel<<<(unsigned)blocks, HER_THREADS, smem, (cudaStream_t)stream>>>(P);
+  CUR_CHECK_LAUNCH();
+  return CUR_OK;
+}
+
+// ---------------------------------------------------------------- known-answer access to the generator
+__global__ void philox_kat_kernel(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* c = in + 6 * i;
+  const cur::Philox x = cur::philox4x32_10(c[0], c[1], c[2], c[3], c[4], c[5]);
+  for (int k = 0; k < 4; ++k) out[4 * i + k] = x.x[k];
+}
+
+extern "C" int cur_philox4x32_10(void* stream, const uint32_t* in, int64_t n, uint32_t* out) {
+  CUR_REQUIRE(n >= 0 && (n == 0 || (in != nullptr && out != nullptr)), "bad arguments");
+  if (n == 0) return CUR_OK;
+  philox_kat_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(in, n, out);
   CUR_CHECK_LAUNCH();
   return CUR_OK;
 }

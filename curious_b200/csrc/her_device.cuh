@@ -86,6 +86,20 @@ __device__ __forceinline__ void her_draw_row(const cur_her_args& a, const HerPla
   src[2] = (pl.cold4 > 0) ? a.seg[s].cold + ((int64_t)row.ep * L.T + row.t) * (int64_t)L.cold_stride : nullptr;
 }
 
+// Squared distance of module m (float64, NumPy's operation order: difference, square, running sum - no FMA
+// contraction), added to d2.  PAIR compares the OFFSET between two achieved-goal sub-slices with the goal slice.
+__device__ __forceinline__ double reward_d2(const cur_task_table& tt, int m, const float* ag2, const float* gf, double d2) {
+  const int kind = tt.kind[m];
+  if (kind == CUR_REWARD_INFO) return d2;
+  for (int k = 0; k < tt.len[m]; ++k) {
+    double av = (double)ag2[tt.ag_idx[m][k]];
+    if (kind == CUR_REWARD_PAIR) av = av - (double)ag2[tt.ref_idx[m][k]];
+    const double diff = av - (double)gf[tt.g_idx[m][k]];
+    d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+  }
+  return d2;
+}
+
 // Relabel the staged image of one row in place (g, task_descr) and return its reward.
 // image indices: row t sections at (off - img_off); row t+1 sections at (i0 + off); g/u/td of step t live in
 // row t+1 (shifted layout).  *relab_out receives the module whose goal slice was relabelled (-1: none).
@@ -126,31 +140,33 @@ __device__ __forceinline__ float her_relabel_row(const cur_her_args& a, const He
     }
   }
   *relab_out = relab;
-  // reward on (ag_2, relabelled g, final task_descr) in float64, NumPy's operation order
+  // reward on (ag_2, relabelled g, final task_descr[, info]) - the module's row of the reward table
   const float* ag2 = st + iAG2;
   const float* gf = st + iG;
-  double d2 = 0.0;
   if (a.mode == CUR_MODE_FLAT) {
-    for (int m = 0; m < a.tasks.n_tasks; ++m)
-      for (int k = 0; k < a.tasks.len[m]; ++k) {
-        double diff = (double)ag2[a.tasks.ag_idx[m][k]] - (double)gf[a.tasks.g_idx[m][k]];
-        d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
-      }
-  } else {
-    const int m = (newtd >= 0) ? newtd : own;
-    if (m >= 0)
-      for (int k = 0; k < a.tasks.len[m]; ++k) {
-        double diff = (double)ag2[a.tasks.ag_idx[m][k]] - (double)gf[a.tasks.g_idx[m][k]];
-        d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
-      }
+    double d2 = 0.0;
+    for (int m = 0; m < a.tasks.n_tasks; ++m) d2 = reward_d2(a.tasks, m, ag2, gf, d2);
+    return (sqrt(d2) > a.tasks.flat_threshold) ? -1.0f : 0.0f;
   }
-  return (sqrt(d2) > a.tasks.threshold) ? -1.0f : 0.0f;
+  const int m = (newtd >= 0) ? newtd : own;
+  if (m >= 0 && a.tasks.kind[m] == CUR_REWARD_INFO)
+    return (float)((double)st[pl.cold_off + L.off_info + a.tasks.info_col[m]] - 1.0);
+  const double d2 = (m >= 0) ? reward_d2(a.tasks, m, ag2, gf, 0.0) : 0.0;
+  return (sqrt(d2) > a.tasks.threshold[m >= 0 ? m : 0]) ? -1.0f : 0.0f;
+}
+
+// true when some module's reward reads the stored info row (the cold row then travels with every transition)
+inline bool reward_needs_info(const cur_task_table& tt) {
+  for (int m = 0; m < tt.n_tasks; ++m)
+    if (tt.kind[m] == CUR_REWARD_INFO) return true;
+  return false;
 }
 
 inline int make_plan(const cur_her_args& a, HerPlan* p) {
   const cur_layout& L = a.L;
   const bool need_ag_t = (a.ag != nullptr) || a.relative_goals;
-  const bool need_cold = (a.change != nullptr && L.dimchange > 0) || (a.info != nullptr && L.diminfo > 0);
+  const bool need_cold = (a.change != nullptr && L.dimchange > 0) || (a.info != nullptr && L.diminfo > 0) ||
+                         (reward_needs_info(a.tasks) && L.diminfo > 0);
   p->img_off = need_ag_t ? L.off_ag : L.off_o;
   p->i0 = L.row_stride - p->img_off;
   p->img4 = (p->i0 + L.row_stride) / 4;

@@ -26,7 +26,7 @@ import torch
 from . import _lib, apportion
 from .her import HostDraws
 from .mpi_adam import MpiAdam, adam_step_scale
-from .normalizer import Normalizer
+from .normalizer import Normalizer, recompute_stats_packed
 from .parallel import allreduce_sum_, world as _world
 from .replay_buffer import StagedEpisodes, episodes_to_device
 from .util import LazyHost, capture_graph, dims_to_shapes, import_function, store_args, transitions_in_episode_batch
@@ -143,8 +143,14 @@ class DDPG(object):
             raise ValueError('network_class %s does not fit structure %r' % (self.network_class, self.structure))
         net = self.net
         # running averages (ddpg.py:402-409)
-        self.o_stats = Normalizer(self.dimo, self.norm_eps, self.norm_clip, device=dev, comm=self.comm)
-        self.g_stats = Normalizer(self.dimg, self.norm_eps, self.norm_clip, device=dev, comm=self.comm)
+        # both normalisers accumulate into ONE packed buffer [sum_o|sumsq_o|count_o|sum_g|sumsq_g|count_g]: one collective
+        # per store_episode (normalizer.recompute_stats_packed)
+        no, ng = 2 * self.dimo + 1, 2 * self.dimg + 1
+        self._stats_partial = torch.zeros(no + ng, dtype=torch.float32, device=dev)
+        self.o_stats = Normalizer(self.dimo, self.norm_eps, self.norm_clip, device=dev, comm=self.comm,
+                                  partial=self._stats_partial[:no])
+        self.g_stats = Normalizer(self.dimg, self.norm_eps, self.norm_clip, device=dev, comm=self.comm,
+                                  partial=self._stats_partial[no:])
         self._stats = _lib.NormStats(self.o_stats.mean.data_ptr(), self.o_stats.std.data_ptr(),
                                      self.g_stats.mean.data_ptr(), self.g_stats.std.data_ptr())
         # flat arenas: [Q | pad | pi | pad]
@@ -356,8 +362,7 @@ class DDPG(object):
                                         relative_goals=self.relative_goals, want=('o', 'g'))
             self.o_stats.update(res['o'])
             self.g_stats.update(res['g'])
-            self.o_stats.recompute_stats()
-            self.g_stats.recompute_stats()
+            recompute_stats_packed((self.o_stats, self.g_stats), self._stats_partial, self.comm)
 
     def get_current_buffer_size(self):
         return sum([self.buffer[i].get_current_size() for i in range(self.nb_tasks)])

@@ -115,8 +115,8 @@ class HerSampler:
         self.nb_tasks = len(tasks_ag_id) if tasks_ag_id is not None else 0
         self.reward = as_reward_spec(reward_fun, tasks_ag_id, tasks_g_id)
         self.mode = mode_of(task_replay, flat) if (flat or task_replay != '') else None
-        self.task_table = _lib.make_task_table(self.reward.tasks_ag_id, self.reward.tasks_g_id,
-                                               self.reward.threshold, reward_kind=self.reward.kind)
+        self.task_table = self.reward.task_table()
+        self._info_layout = None        # 'info' reward rules: columns resolved against the first buffer sampled
         self.rng = 'numpy'
         self.seed = 0
         self.calls = 0
@@ -136,6 +136,9 @@ class HerSampler:
         first = segments[0][0]
         L = first.layout
         dev = first.storage.device
+        if self.reward.needs_info() and self._info_layout != first.info_keys:
+            self._info_layout = first.info_keys
+            self.task_table = self.reward.task_table(first.info_keys)
         a = _lib.HerArgs()
         a.L = L
         a.tasks = self.task_table

@@ -17,8 +17,10 @@ from .parallel import allreduce_sum_, world as _world
 
 
 class Normalizer:
-    def __init__(self, size, eps=1e-2, default_clip_range=np.inf, sess=None, device=None, comm=None):
-        """Same arguments as the reference (normalizer.py:11); `sess` is accepted and ignored."""
+    def __init__(self, size, eps=1e-2, default_clip_range=np.inf, sess=None, device=None, comm=None, partial=None):
+        """Same arguments as the reference (normalizer.py:11); `sess` is accepted and ignored.  `partial`: a float32
+        device view of 2 * size + 1 zeros to accumulate into - several normalisers handed slices of ONE buffer are
+        synchronised with a single collective (`recompute_stats_packed`)."""
         self.size = size
         self.eps = eps
         self.default_clip_range = default_clip_range
@@ -26,7 +28,8 @@ class Normalizer:
         self.device = device or torch.device('cuda', torch.cuda.current_device())
         self.comm = comm
         # [sum | sumsq | count]; count starts at ONE with sum = 0 (normalizer.py:31-39)
-        self._partial = torch.zeros(2 * size + 1, dtype=torch.float32, device=self.device)
+        self._partial = partial if partial is not None else torch.zeros(2 * size + 1, dtype=torch.float32, device=self.device)
+        assert self._partial.numel() == 2 * size + 1 and self._partial.dtype == torch.float32
         self._running = torch.zeros(2 * size + 1, dtype=torch.float32, device=self.device)
         self._running[2 * size] = 1.0
         self.mean = torch.zeros(size, dtype=torch.float32, device=self.device)
@@ -94,9 +97,11 @@ class Normalizer:
         is what is reduced."""
         return allreduce_sum_(self._partial, self.comm)
 
-    def recompute_stats(self):
+    def recompute_stats(self, world=None):
+        """normalizer.py:96-118.  `world`: the partials were already summed over that many ranks (packed path)."""
         with self.lock:
-            world = self.synchronize()
+            if world is None:
+                world = self.synchronize()
             _lib.check(_lib.load().cur_norm_recompute(_lib.stream_ptr(), self._running.data_ptr(),
                                                       self._partial.data_ptr(), float(world), float(self.eps),
                                                       self.size, self.mean.data_ptr(), self.std.data_ptr()),
@@ -114,6 +119,16 @@ class Normalizer:
         self._running[2 * self.size:] = torch.from_numpy(c.reshape(1)).to(self.device)
         self.mean.copy_(torch.from_numpy(m).to(self.device))
         self.std.copy_(torch.from_numpy(sd).to(self.device))
+
+
+def recompute_stats_packed(normalizers, packed, comm=None):
+    """`recompute_stats` of several normalisers whose partials are slices of `packed`: ONE all-reduce for all of them
+    per store_episode (the reference issues three blocking all-reduces per normaliser, normalizer.py:84-94, six per
+    store; SURVEY 8e asks for one packed collective), then each one's `+=` / mean / std kernel."""
+    world = allreduce_sum_(packed, comm)
+    for nz in normalizers:
+        nz.recompute_stats(world=world)
+    return world
 
 
 class IdentityNormalizer:

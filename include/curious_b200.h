@@ -121,13 +121,26 @@ typedef struct cur_segment {
   int32_t _pad;
 } cur_segment;
 
+/* Reward rule of one module (config.py:158-159 hands the sampler gym_flowers' compute_reward; the rule arrives here as
+ * DATA, one row of this table per module - SURVEY 8c).  All kinds yield r in {-1, 0}, evaluated in float64:
+ *   DISTANCE  d = || ag_2[ag_idx[m]] - g[g_idx[m]] ||_2                       r = -1 if d > threshold[m] else 0
+ *   PAIR      d = || (ag_2[ag_idx[m]] - ag_2[ref_idx[m]]) - g[g_idx[m]] ||_2  same compare: the goal is the wanted
+ *             OFFSET between two achieved-goal sub-slices (one object placed relative to another, Stack-style)
+ *   INFO      r = info[info_col[m]] - 1: the success flag stored with the transition passes through             */
+enum { CUR_REWARD_DISTANCE = 0, CUR_REWARD_PAIR = 1, CUR_REWARD_INFO = 2 };
+
 typedef struct cur_task_table {
   int32_t n_tasks;
-  int32_t reward_kind;               /* 0: module L2 distance > threshold -> -1 else 0        */
+  int32_t _pad;
   int32_t len[CUR_MAX_TASKS];        /* len(tasks_g_id[m])                                    */
   int16_t g_idx[CUR_MAX_TASKS][CUR_MAX_SLICE];  /* tasks_g_id[m][k]                           */
   int16_t ag_idx[CUR_MAX_TASKS][CUR_MAX_SLICE]; /* tasks_ag_id[m][k], truncated to len[m]     */
-  double threshold;
+  int16_t ref_idx[CUR_MAX_TASKS][CUR_MAX_SLICE]; /* PAIR: second achieved-goal slice           */
+  int32_t kind[CUR_MAX_TASKS];       /* CUR_REWARD_*                                          */
+  int32_t info_col[CUR_MAX_TASKS];   /* INFO: column inside the concatenated info_* row       */
+  double threshold[CUR_MAX_TASKS];   /* per module                                            */
+  double flat_threshold;             /* task_descr = None (flat sampler, her.py:56-59): every module's difference
+                                        vector enters ONE distance, compared with this           */
   double cdf[CUR_MAX_TASKS];         /* CP_TASK: normalised cumsum(cp_proba) (np.random.choice) */
 } cur_task_table;
 
@@ -166,6 +179,11 @@ typedef struct cur_her_args {
 } cur_her_args;
 
 int cur_her_sample(void* stream, const cur_her_args* args);
+
+/* The kernels' counter-based generator on its own: out[i] = Philox4x32-10(counter = in[i][0..3], key = in[i][4..5])
+ * evaluated ON THE DEVICE by the same device function the sampling and exploration-noise kernels call (known-answer
+ * tests against the Random123 vectors; the reference draws from np.random, her.py:108-116, which this mode replaces). */
+int cur_philox4x32_10(void* stream, const uint32_t* in /* [n][6] device */, int64_t n, uint32_t* out /* [n][4] device */);
 
 /* ------------------------------------------------------------------------------------------
  * Normalizer (baselines/her/normalizer.py:10-118).  State is float32 on the device.

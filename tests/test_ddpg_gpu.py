@@ -3,10 +3,11 @@ Normalizer, MpiAdam) against the CPU oracle.
 
 Tolerances (float32 path, summation order differs from NumPy/Eigen):
   losses                 rel 1e-5
-  gradients              max-abs error <= 2e-5 * max|grad|   (per flat vector) whenever no hidden
-                         pre-activation of the oracle lies within 2e-6 of the ReLU kink; such a unit may
-                         land on the other side of the kink in any float32 re-implementation (different
-                         summation order) and flips a whole row of dW, so those updates get 2e-3
+  gradients              max-abs error <= 2e-5 * max|grad| (per flat vector).  ONLY when that bound fails and a hidden
+                         pre-activation of the oracle lies within 2e-6 of the ReLU kink (such a unit may land on the
+                         other side of the kink in any float32 re-implementation - different summation order - and
+                         flips a whole row of dW) the update is held to 5e-4 instead; how often that fallback is TAKEN is
+                         counted, reported and bounded (<= 10 % of the checks) by the last test of this file
   weights after a step   rel 1e-5 of max|theta| ... Adam's m/sqrt(v) normalisation can flip tiny gradients,
                          so the step itself is additionally checked with the ORACLE's gradient (bit exact)
 """
@@ -18,6 +19,23 @@ from tests.ddpg_util import ddpg_kwargs, episode_stream, make_gpu_agent, make_or
 pytestmark = pytest.mark.gpu
 LOSS_RTOL = 1e-5
 GRAD_RTOL = 2e-5
+ESCAPES = {'checks': 0, 'near_kink': 0, 'escapes': 0, 'worst_strict': 0.0, 'taken': []}   # reported by the last test
+
+
+def _check_grad(got, want, relu_margin, what=''):
+    """max-abs error of a flat gradient <= GRAD_RTOL * max|grad|.  Only when that fails AND a hidden pre-activation of
+    the oracle sits within 2e-6 of the ReLU kink (module docstring) the comparison falls back to 5e-4; how often that
+    fallback is actually TAKEN is counted and bounded in test_zz_gradient_escape_frequency."""
+    err = rel_err(got, want)
+    ESCAPES['checks'] += 1
+    ESCAPES['near_kink'] += int(relu_margin <= 2e-6)
+    if err <= GRAD_RTOL:
+        ESCAPES['worst_strict'] = max(ESCAPES['worst_strict'], float(err))
+        return
+    assert relu_margin <= 2e-6, (what, err, relu_margin)
+    ESCAPES['escapes'] += 1
+    ESCAPES['taken'].append((what, float(err), float(relu_margin)))
+    assert err <= 5e-4, (what, err, relu_margin)
 
 
 def _fill(agent, episodes, cp):
@@ -84,9 +102,8 @@ def test_store_sample_train_against_oracle(normalize_obs, n_modules, schedule):
         assert abs(float(ql) - ref['Q_loss']) <= LOSS_RTOL * abs(ref['Q_loss']) + 1e-7
         assert abs(float(gpu._pi_loss) - ref['pi_loss']) <= LOSS_RTOL * abs(ref['pi_loss']) + 1e-7
         assert rel_err(qpi.cpu().numpy(), ref['Q_pi']) <= 1e-5
-        tol = GRAD_RTOL if ref['relu_margin'] > 2e-6 else 2e-3
-        assert rel_err(gq.cpu().numpy(), ref['Q_grad']) <= tol, ref['relu_margin']
-        assert rel_err(gp.cpu().numpy(), ref['pi_grad']) <= tol, ref['relu_margin']
+        _check_grad(gq.cpu().numpy(), ref['Q_grad'], ref['relu_margin'], 'Q')
+        _check_grad(gp.cpu().numpy(), ref['pi_grad'], ref['relu_margin'], 'pi')
         # Adam with the oracle's own gradient: bit exact
         gpu.grads.zero_()
         gpu._view(gpu.grads, 'Q').copy_(torch.from_numpy(ref['Q_grad']).cuda())
@@ -101,6 +118,55 @@ def test_store_sample_train_against_oracle(normalize_obs, n_modules, schedule):
     ora.update_target_net()
     from oracle.ddpg_oracle import flatten
     assert np.array_equal(gpu.get_flat('Q', target=True), flatten(ora.target_Q))      # polyak: bit exact
+    assert np.array_equal(gpu.get_flat('pi', target=True), flatten(ora.target_pi))
+
+
+@pytest.mark.parametrize('schedule', ['levels', 'rows'])
+@pytest.mark.parametrize('normalize_obs', [False, True])
+def test_flat_network_step_against_oracle(normalize_obs, schedule):
+    """The flat `ActorCritic` + `nn` (actor_critic.py:5-48, util.py:56-71) at the default width (hidden 256, batch 256),
+    per step: staged batch bit-exact, losses rel 1e-5, Q_pi, both gradients, Adam with the oracle's gradient bit-exact."""
+    import torch
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, structure='flat', task_replay='', normalize_obs=normalize_obs)
+    episodes = episode_stream(dims, kw['T'], 10, flat=True)
+    cp = np.zeros(4)
+    ora = make_oracle_agent(kw, dims, ag_ids, g_ids)
+    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy', update_schedule=schedule)
+    assert gpu._use_rows(kw['batch_size']) == (schedule == 'rows')
+    np.random.seed(31)
+    _fill(ora, episodes, cp)
+    np.random.seed(31)
+    _fill(gpu, episodes, cp)
+    if normalize_obs:
+        for a, b in ((gpu.o_stats, ora.o_stats), (gpu.g_stats, ora.g_stats)):
+            a.load_state_list([b.sum, b.sumsq, b.count, b.mean, b.std])
+    assert np.array_equal(gpu.get_flat('Q'), ora.Q_adam.theta) and np.array_equal(gpu.get_flat('pi'), ora.pi_adam.theta)
+    for step in range(4):
+        np.random.seed(500 + step)
+        ob = ora.sample_batch()
+        np.random.seed(500 + step)
+        gb = gpu.sample_batch()
+        for key, x, y in zip(ora.stage_keys, gb, ob):
+            assert np.array_equal(x, np.asarray(y, np.float64)), key
+        gpu.stage_batch(gb)
+        ql, qpi, gq, gp = gpu._grads()
+        ref = ora.grads(ob)
+        assert abs(float(ql) - ref['Q_loss']) <= LOSS_RTOL * abs(ref['Q_loss']) + 1e-7
+        assert abs(float(gpu._pi_loss) - ref['pi_loss']) <= LOSS_RTOL * abs(ref['pi_loss']) + 1e-7
+        assert rel_err(qpi.cpu().numpy(), ref['Q_pi']) <= 1e-5
+        _check_grad(gq.cpu().numpy(), ref['Q_grad'], ref['relu_margin'], 'Q')
+        _check_grad(gp.cpu().numpy(), ref['pi_grad'], ref['relu_margin'], 'pi')
+        gpu.grads.zero_()
+        gpu._view(gpu.grads, 'Q').copy_(torch.from_numpy(ref['Q_grad']).cuda())
+        gpu._view(gpu.grads, 'pi').copy_(torch.from_numpy(ref['pi_grad']).cuda())
+        gpu._update(gpu._view(gpu.grads, 'Q'), gpu._view(gpu.grads, 'pi'))
+        ora.train(ob)
+        assert np.array_equal(gpu.get_flat('Q'), ora.Q_adam.theta)
+        assert np.array_equal(gpu.get_flat('pi'), ora.pi_adam.theta)
+    gpu.update_target_net()
+    ora.update_target_net()
+    from oracle.ddpg_oracle import flatten
+    assert np.array_equal(gpu.get_flat('Q', target=True), flatten(ora.target_Q))
     assert np.array_equal(gpu.get_flat('pi', target=True), flatten(ora.target_pi))
 
 
@@ -474,11 +540,10 @@ def test_large_batch_tensor_core_update_against_oracle(batch_size):
                 assert abs(ql - ref['Q_loss']) <= LOSS_RTOL * abs(ref['Q_loss']) + 1e-7, mode
                 assert abs(pl - ref['pi_loss']) <= LOSS_RTOL * abs(ref['pi_loss']) + 1e-7, mode
                 assert rel_err(qpi, ref['Q_pi']) <= 1e-5, mode
-                tol = GRAD_RTOL if ref['relu_margin'] > 2e-6 else 2e-3        # see the module docstring
-                assert rel_err(gq, ref['Q_grad']) <= tol, (mode, ref['relu_margin'])
-                assert rel_err(gp, ref['pi_grad']) <= tol, (mode, ref['relu_margin'])
-            assert rel_err(got[1][3], got[0][3]) <= tol
-            assert rel_err(got[1][4], got[0][4]) <= tol
+                _check_grad(gq, ref['Q_grad'], ref['relu_margin'], 'Q tc=%d' % mode)        # see the module docstring
+                _check_grad(gp, ref['pi_grad'], ref['relu_margin'], 'pi tc=%d' % mode)
+            _check_grad(got[1][3], got[0][3], ref['relu_margin'], 'Q tc vs ffma')
+            _check_grad(got[1][4], got[0][4], ref['relu_margin'], 'pi tc vs ffma')
             # step both sides with the ORACLE's gradient (Adam's m / sqrt(v) turns last-bit gradient noise into
             # +-lr parameter differences on the first steps, see the module docstring): bit exact
             import torch
@@ -562,9 +627,9 @@ def test_workers_per_rank_sums_single_batch_gradients():
         gp = np.sum([o['pi_grad'] for o in outs], axis=0, dtype=np.float32)
         np.random.seed(500 + step)
         gpu.train()
-        tol = GRAD_RTOL if min(o['relu_margin'] for o in outs) > 2e-6 else 2e-3
-        assert rel_err(gpu._view(gpu.grads, 'Q').cpu().numpy(), gq) <= tol
-        assert rel_err(gpu._view(gpu.grads, 'pi').cpu().numpy(), gp) <= tol
+        margin = min(o['relu_margin'] for o in outs)
+        _check_grad(gpu._view(gpu.grads, 'Q').cpu().numpy(), gq, margin, 'Q workers')
+        _check_grad(gpu._view(gpu.grads, 'pi').cpu().numpy(), gp, margin, 'pi workers')
         # keep both sides on the oracle's trajectory (see the module docstring about Adam and tiny gradients)
         ora.main_Q = unflatten(ora.Q_adam.update(gq, ora.Q_lr), ora.ac.Q_shapes)
         ora.main_pi = unflatten(ora.pi_adam.update(gp, ora.pi_lr), ora.ac.pi_shapes)
@@ -652,3 +717,57 @@ def test_wide_batch_of_workers_equals_sum_of_single_batch_gradients():
     np.random.seed(21)
     _fill(big, episode_stream(dims, kw['T'], 8), cp)
     assert np.isfinite(float(big.train()[0])) and big._wide and not big._use_rows(big._graph_rows)
+
+
+
+def test_store_episode_issues_one_packed_statistics_collective(monkeypatch):
+    """per store_episode ONE all-reduce of [sum_o|sumsq_o|count_o|sum_g|sumsq_g|count_g] (the reference: six,
+    normalizer.py:84-94), and the statistics equal those of two separately synchronised normalisers."""
+    import torch
+    from curious_b200 import normalizer
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4)
+    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy')
+    calls = []
+    real = normalizer.allreduce_sum_
+
+    def counting(t, comm=None):
+        calls.append(int(t.numel()))
+        return real(t, comm)
+
+    monkeypatch.setattr(normalizer, 'allreduce_sum_', counting)
+    eps = episode_stream(dims, kw['T'], 3)
+    np.random.seed(3)
+    for i, ep in enumerate(eps):
+        gpu.store_episode({k: v.copy() for k, v in ep.items()}, np.array([0.05, 0.2, 0.1, 0.0]), 2 * (i + 1))
+    assert calls == [2 * (dims['o'] + dims['g']) + 2] * 3
+    # the same updates through stand-alone normalisers (one collective each)
+    ref_o = normalizer.Normalizer(dims['o'], kw['norm_eps'], kw['norm_clip'])
+    ref_g = normalizer.Normalizer(dims['g'], kw['norm_eps'], kw['norm_clip'])
+    twin = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy')
+    twin.o_stats.update = lambda v, _u=twin.o_stats.update: (ref_o.update(v.clone()), _u(v))[1]
+    twin.g_stats.update = lambda v, _u=twin.g_stats.update: (ref_g.update(v.clone()), _u(v))[1]
+    np.random.seed(3)
+    for i, ep in enumerate(eps):
+        twin.store_episode({k: v.copy() for k, v in ep.items()}, np.array([0.05, 0.2, 0.1, 0.0]), 2 * (i + 1))
+        ref_o.recompute_stats()
+        ref_g.recompute_stats()
+    for a, b in ((gpu.o_stats, ref_o), (gpu.g_stats, ref_g)):
+        assert torch.equal(a.mean, b.mean) and torch.equal(a.std, b.std) and torch.equal(a.count, b.count)
+
+
+def test_zz_gradient_escape_frequency():
+    """Runs last in this file: how many of the per-step gradient comparisons above needed the ReLU-kink fallback (5e-4)
+    because the strict bound (2e-5 of max|grad|) failed.  Printed (pytest -rP), written next to the other run records
+    when the directory exists, and bounded: the fallback is for the rare flipped unit, not a second tolerance."""
+    import json
+    import os
+    n, k = ESCAPES['checks'], ESCAPES['escapes']
+    print('gradient checks: %d; with a pre-activation within 2e-6 of the kink: %d; strict bound failed and the fallback '
+          'was taken: %d %s; worst error among the strict passes: %.3g' % (n, ESCAPES['near_kink'], k, ESCAPES['taken'],
+                                                                           ESCAPES['worst_strict']))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(out):
+        json.dump(dict(ESCAPES, tolerance=GRAD_RTOL, escape_tolerance=5e-4, margin_threshold=2e-6),
+                  open(os.path.join(out, 'grad_escape_frequency.json'), 'w'))
+    if n >= 20:
+        assert k <= 0.1 * n, (n, k, ESCAPES['taken'])

@@ -95,6 +95,54 @@ def test_kernel_vs_oracle_large(task_replay, ttr, n_modules):
     assert 0.05 < (-ref['r']).mean() < 0.95
 
 
+@pytest.mark.parametrize('task_replay,ttr,flat', [('replay_task_cp_buffer', 1, False), ('replay_task_cp_buffer', None, False),
+                                                  ('replay_random_task_transition', None, False),
+                                                  ('replay_current_task_transition', None, False), ('', None, True)])
+def test_reward_table_kinds_vs_oracle(task_replay, ttr, flat):
+    """Every rule of the reward table (distance with per-module thresholds, pair = offset between two achieved-goal
+    slices, info passthrough) inside the fused kernel vs the oracle's restatement, all sampler modes; bit-exact.
+    (Rules are restatements: parity with gym_flowers' compute_reward is unpinned)"""
+    from curious_b200 import her
+    from curious_b200.replay_buffer import ReplayBuffer
+    from curious_b200.reward import ModuleRewardTable
+    from oracle import her_oracle, replay_oracle
+    from oracle.reward_oracle import ModuleRewardTable as OracleTable
+    T, E, B, N = 50, 200, 8192, 4
+    dims, ag_ids, g_ids, eps = _arm_setup(N, E, T, seed=21)
+    spec = dict(threshold=[0.05, 0.25, 0.05, 0.12], kinds=['distance', 'pair', 'info', 'distance'],
+                ref_ag_id=[None, [0, 1, 2], None, None], info_keys=[None, None, 'is_success', None], flat_threshold=0.35)
+    shapes = {k: v.shape[1:] for k, v in eps.items()}
+    if flat:
+        o_s = her_oracle.make_sample_her_transitions('her', 4, OracleTable(ag_ids, g_ids, **spec), '', tasks_ag_id=ag_ids,
+                                                     tasks_g_id=g_ids)
+        g_s = her.make_sample_her_transitions('her', 4, ModuleRewardTable(ag_ids, g_ids, **spec), '', tasks_ag_id=ag_ids,
+                                              tasks_g_id=g_ids)
+        kw = {}
+    else:
+        o_s = her_oracle.make_sample_multi_task_her_transitions('her', 4, task_replay, OracleTable(ag_ids, g_ids, **spec),
+                                                                tasks_ag_id=ag_ids, tasks_g_id=g_ids)
+        g_s = her.make_sample_multi_task_her_transitions('her', 4, task_replay, ModuleRewardTable(ag_ids, g_ids, **spec),
+                                                         tasks_ag_id=ag_ids, tasks_g_id=g_ids)
+        kw = dict(task_to_replay=ttr)
+    obuf = replay_oracle.ReplayBufferOracle(shapes, E * T, T, o_s)
+    obuf.store_episode({k: v.copy() for k, v in eps.items()})
+    np.random.seed(5)
+    ref = obuf.sample(B, **kw)
+    gbuf = ReplayBuffer(shapes, E * T, T, g_s)
+    gbuf.store_episode({k: v.copy() for k, v in eps.items()})
+    np.random.seed(5)
+    out = gbuf.sample(B, **kw)
+    for k in ref:
+        assert np.array_equal(out[k], np.asarray(ref[k], np.float64)), k
+    if not flat:
+        mod = np.argmax(ref['task_descr'], axis=1)
+        for m in (range(N) if ttr is None else [ttr]):
+            rows = mod == m
+            assert rows.sum() > 50 and 0.0 < (-ref['r'][rows]).mean() < 1.0, (m, rows.sum(), (-ref['r'][rows]).mean())
+        rows = mod == 2                                              # info rule: r = info_is_success - 1
+        assert np.array_equal(ref['r'][rows, 0], ref['info_is_success'][rows, 0] - 1.0)
+
+
 def test_store_roundtrip_and_overwrite_policy():
     """store_episode -> packed rows -> .buffers gives back what was stored; slots follow the reference's
     sequential-then-random policy with the same np.random seed."""
@@ -161,6 +209,30 @@ def test_philox_draws_and_relabel(mode):
     out = g_s.to_host_dict(res, gbuf.device_view())
     for k in ref:
         assert np.array_equal(out[k], np.asarray(ref[k], np.float64)), k
+
+
+def test_philox_device_known_answers():
+    """Random123 known-answer vectors through the device function the kernels draw with (cur_philox4x32_10), plus random
+    (counter, key) pairs against the oracle restatement."""
+    import ctypes as C
+    import torch
+    from curious_b200 import _lib
+    from oracle import philox_oracle
+    from tests.test_oracle_golden import PHILOX_KAT
+    rng = np.random.RandomState(0)
+    extra = rng.randint(0, 2 ** 32, size=(4096, 6), dtype=np.uint64).astype(np.uint32)
+    inp = np.concatenate([np.array([list(c) + list(k) for c, k, _ in PHILOX_KAT], np.uint32), extra])
+    d_in = torch.from_numpy(inp.view(np.int32)).cuda()
+    d_out = torch.zeros((inp.shape[0], 4), dtype=torch.int32, device='cuda')
+    _lib.check(_lib.load().cur_philox4x32_10(_lib.stream_ptr(), d_in.data_ptr(), inp.shape[0], d_out.data_ptr()),
+               'cur_philox4x32_10')
+    out = d_out.cpu().numpy().view(np.uint32)
+    for i, (_, _, want) in enumerate(PHILOX_KAT):
+        assert tuple(int(x) for x in out[i]) == want
+    for j in range(0, extra.shape[0], 16):                 # the oracle takes one key per call
+        c = extra[j]
+        got = philox_oracle.philox4x32_10(*[np.array([int(x)]) for x in c[:4]], int(c[4]), int(c[5]))
+        assert tuple(int(x[0]) for x in got) == tuple(int(x) for x in out[len(PHILOX_KAT) + j])
 
 
 def test_full_size_properties():

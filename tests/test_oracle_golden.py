@@ -243,3 +243,24 @@ def test_storage_oracle_equals_the_live_reference_on_random_sequences():
             assert any(inc > size_ep for inc in incs) == any(x == ('too large',) for x in la)
     finally:
         np.random.set_state(state)
+
+
+# Random123 (D. E. Shaw Research) known-answer vectors for philox4x32, 10 rounds: (counter, key) -> output
+PHILOX_KAT = [
+    ((0x00000000, 0x00000000, 0x00000000, 0x00000000), (0x00000000, 0x00000000),
+     (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff),
+     (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+def test_philox_oracle_known_answers():
+    """The counter-based generator of the Philox draw mode is Philox4x32-10 as published: the oracle restatement
+    reproduces the three Random123 known-answer vectors (the kernel's device function is checked against the same
+    vectors in tests/test_her_gpu.py::test_philox_device_known_answers)."""
+    from oracle import philox_oracle
+    for ctr, key, want in PHILOX_KAT:
+        got = philox_oracle.philox4x32_10(*[np.array([c]) for c in ctr], *key)
+        assert tuple(int(x[0]) for x in got) == want
