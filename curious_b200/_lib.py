@@ -151,6 +151,12 @@ SIGNATURES = {
                                       C.c_float, C.c_int32]),
     'cur_polyak': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double]),
     'cur_checksum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'cur_ddpg_actions_rows': (C.c_int, [C.c_void_p, C.POINTER(NetDesc), C.c_void_p, C.POINTER(NormStats), C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_uint32]),
+    'cur_host_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    'cur_host_free': (C.c_int, [C.c_void_p]),
+    'cur_copy_h2d': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     'cur_action_noise': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_double,
                                    C.c_uint64, C.c_uint64]),
     'cur_net_param_count': (C.c_int64, [C.POINTER(NetDesc), C.c_int]),
@@ -171,6 +177,9 @@ SIGNATURES = {
     'cur_ddpg_rows_refresh': (C.c_int, [C.c_void_p, C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.c_int64]),
     'cur_ddpg_grads_group': (C.c_int, [C.c_void_p, C.POINTER(NetDesc), C.c_int, C.POINTER(DdpgExpert)]),
     'cur_ddpg_set_tensor_cores': (C.c_int, [C.c_int]),
+    'cur_tc_chain_timeline': (C.c_int, [C.c_void_p]),
+    'cur_ddpg_set_chain': (C.c_int, [C.c_int]),
+    'cur_ddpg_uses_chain': (C.c_int, [C.POINTER(NetDesc), C.c_int64]),
     'cur_ddpg_uses_tensor_cores': (C.c_int, [C.POINTER(NetDesc), C.c_int64]),
     'cur_tc_gemm_timeline': (C.c_int, [C.c_void_p]),
     'cur_tc_gemm_supported': (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
@@ -235,9 +244,15 @@ def ptr(t):
 
 
 def stream_ptr(stream=None):
+    """cudaStream_t of `stream` or of torch's current stream (the raw-handle query: torch.cuda.current_stream() builds a
+    Stream object per call, ~5 us - more than a kernel launch)."""
+    if stream is not None:
+        return stream.cuda_stream
     import torch
-    s = stream if stream is not None else torch.cuda.current_stream()
-    return s.cuda_stream
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    except AttributeError:
+        return torch.cuda.current_stream().cuda_stream
 
 
 def make_layout(T, dimo, dimag, dimg, dimu, dimtd=0, dimchange=0, diminfo=0):

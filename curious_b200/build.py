@@ -12,10 +12,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcurious_b200.so')
-SOURCES = ['her.cu', 'norm_adam.cu', 'ddpg.cu', 'ddpg_rows.cu', 'p2p.cu', 'tc_gemm.cu']
+SOURCES = ['her.cu', 'norm_adam.cu', 'ddpg.cu', 'ddpg_rows.cu', 'p2p.cu', 'tc_gemm.cu', 'tc_chain.cu']
 HEADERS = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'mlp_kernels.cuh'),
            os.path.join(CSRC, 'net_layout.cuh'), os.path.join(CSRC, 'her_device.cuh'),
-           os.path.join(CSRC, 'tc_gemm.cuh'),
+           os.path.join(CSRC, 'tc_gemm.cuh'), os.path.join(CSRC, 'tc_ptx.cuh'),
            os.path.join(os.path.dirname(HERE), 'include', 'curious_b200.h')]
 
 NVCC_FLAGS = [

@@ -31,6 +31,9 @@ struct Workspace {
   float *hp[CUR_MAX_LAYERS], *hq[CUR_MAX_LAYERS], *hqp[CUR_MAX_LAYERS], *ht[CUR_MAX_LAYERS], *htq[CUR_MAX_LAYERS];
   float *Q, *Qt, *dQ, *dQpi, *dy;
   float *dc[2], *da[2], *dp[2];
+  float *dcl[CUR_MAX_LAYERS], *dpl[CUR_MAX_LAYERS];   // chain schedule (tc_chain.cu): one delta buffer per layer
+  float* chain_loss;                                   // ... and its per-tile loss partials [n / 128][4]
+  uint32_t *chain_mp, *chain_mq, *chain_mqp;           // ... ReLU mask words [layers][8][n] (main.pi, main.Q(u), main.Q(pi))
   // tensor-core path (large batch only): split-K partial tiles / partial row reductions, TC_SLOTS problems per level
   float *tc_part, *tc_rowpart;
   int64_t tc_part_stride, tc_rowpart_stride;
@@ -46,7 +49,7 @@ struct Workspace {
 constexpr int64_t TC_MIN_BATCH = 1024;
 constexpr int LOSS_MAX_CTAS = 128;
 constexpr int64_t LOSS_MC_MIN_BATCH = 1024;   // from here the loss / backward-seed kernel runs on several CTAs
-constexpr int TC_SLOTS = 3;          // split-K weight gradients / row reductions per dependency level
+constexpr int TC_SLOTS = 8;          // split-K weight gradients / row reductions per dependency level (chain: per net)
 static int g_tc_mode = -1;          // -1: environment (default on), 0: off, 1: on  (cur_ddpg_set_tensor_cores)
 static bool tc_enabled() {
   if (g_tc_mode >= 0) return g_tc_mode == 1;
@@ -62,6 +65,17 @@ static bool tc_shape_ok(const cur_net_desc& d, int64_t n) { return n >= 256 && (
 static bool use_tc(const cur_net_desc& d, int64_t n) {
   if (!tc_shape_ok(d, n) || !tc_enabled()) return false;
   return g_tc_mode == 1 || n >= TC_MIN_BATCH;
+}
+
+// The fused chain kernel (tc_chain.cu) replaces the forward / loss / dX levels whenever the tensor-core path is on and the
+// shape fits; CUR_DDPG_CHAIN=0 or cur_ddpg_set_chain(0) keeps the level-by-level schedule (A/B measurements, tests).
+static int g_chain_mode = -1;
+static bool use_chain(const cur_net_desc& d, int64_t n) {
+  if (!use_tc(d, n) || !tc_chain_supported(d, n)) return false;
+  if (g_chain_mode >= 0) return g_chain_mode == 1;
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CUR_DDPG_CHAIN"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 static Workspace carve(const cur_net_desc& d, int64_t n, float* base) {
@@ -105,6 +119,16 @@ static Workspace carve(const cur_net_desc& d, int64_t n, float* base) {
   w.loss_part = take(LOSS_MAX_CTAS * 4);
   w.tc_part = w.tc_rowpart = nullptr;
   w.tc_part_stride = w.tc_rowpart_stride = 0;
+  for (int l = 0; l < CUR_MAX_LAYERS; ++l) w.dcl[l] = w.dpl[l] = nullptr;
+  w.chain_loss = nullptr;
+  w.chain_mp = w.chain_mq = w.chain_mqp = nullptr;
+  if (tc_chain_supported(d, n)) {
+    for (int l = 0; l < d.layers; ++l) { w.dcl[l] = take(n * w.H); w.dpl[l] = take(n * w.H); }
+    w.chain_loss = take((n / 128) * 4);
+    w.chain_mp = reinterpret_cast<uint32_t*>(take((int64_t)d.layers * 8 * n));
+    w.chain_mq = reinterpret_cast<uint32_t*>(take((int64_t)d.layers * 8 * n));
+    w.chain_mqp = reinterpret_cast<uint32_t*>(take((int64_t)d.layers * 8 * n));
+  }
   if (tc_shape_ok(d, n)) {      // carved whenever the shape is eligible: the workspace size does not depend on the toggle
     GemmProb dwp = zero_prob();
     dwp.M = w.H; dwp.N = w.H; dwp.K = (int)n; dwp.a_trans = 1;
@@ -417,6 +441,17 @@ extern "C" int cur_ddpg_set_tensor_cores(int mode) {
   return CUR_OK;
 }
 
+extern "C" int cur_ddpg_set_chain(int mode) {
+  CUR_REQUIRE(mode >= -1 && mode <= 1, "mode must be -1 (default), 0 (off) or 1 (on)");
+  g_chain_mode = mode;
+  return CUR_OK;
+}
+
+extern "C" int cur_ddpg_uses_chain(const cur_net_desc* d, int64_t batch) {
+  if (check_desc(d) != CUR_OK || batch <= 0) return 0;
+  return use_chain(*d, batch) ? 1 : 0;
+}
+
 extern "C" int cur_ddpg_uses_tensor_cores(const cur_net_desc* d, int64_t batch) {
   if (check_desc(d) != CUR_OK || batch <= 0) return 0;
   return use_tc(*d, batch) ? 1 : 0;
@@ -546,6 +581,76 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
   GroupBatcher B(s, use_tc(*d, n), E, n_e);
 #define FOR_EXPERTS for (int i = 0; i < n_e; ++i)
 #define ADD(prob) CUR_TRY(B.add(i, (prob)))
+  if (use_chain(*d, n)) {
+    // ---- chain schedule (tc_chain.cu): forward nets, losses and the data-gradient chains of a 128-row tile in one
+    // CTA per chain, then every weight / bias gradient as split-K tensor-core GEMMs + row reductions, one level per net
+    FOR_EXPERTS {
+      Expert& x = E[i]; const Workspace& w = x.w;
+      TcChainIO io;
+      memset(&io, 0, sizeof(io));
+      io.n = n; io.grad_rows = x.h->loss_rows > 0 ? x.h->loss_rows : n;
+      io.mQ = x.mQ; io.mP = x.mP; io.tQ = x.tQ; io.tP = x.tP;
+      io.Xpi = w.Xpi; io.Xg = w.Xg; io.XQu = w.XQu; io.Xpi_t = w.Xpi_t; io.Xg_t = w.Xg_t; io.XQpi = w.XQpi; io.XQ_t = w.XQ_t;
+      io.ld_spi = w.ld_spi; io.ld_sq = w.ld_sq; io.ld_g = w.ld_g; io.lddy = (int)r4(d->dimu);
+      // (the chain keeps hp / hq / dcl / dpl TRANSPOSED, [256][n]: K-major operands of the weight-gradient GEMMs)
+      for (int l = 0; l < L; ++l) { io.hp[l] = w.hp[l]; io.hq[l] = w.hq[l]; io.dc[l] = w.dcl[l]; io.dp[l] = w.dpl[l]; }
+      io.mp = w.chain_mp; io.mq = w.chain_mq; io.mqp = w.chain_mqp;
+      io.Q = w.Q; io.Qt = w.Qt; io.dQ = w.dQ; io.dy = w.dy; io.q_pi = x.q_pi; io.r = x.batch->r;
+      io.gamma = x.h->gamma; io.clip_return = x.h->clip_return; io.action_l2 = x.h->action_l2; io.clip_pos = x.h->clip_pos_returns;
+      io.loss_part = w.chain_loss; io.q_loss = x.q_loss; io.pi_loss = x.pi_loss;
+      io.step_counter = x.h->step_counter; io.loss_ring = x.h->loss_ring;
+      CUR_TRY(tc_chain_launch(s, *d, io));
+    }
+    const int lddy = (int)r4(d->dimu);
+    // dW = X^T dY with both operands K-major (K = batch): A = hT [256][n], B = dT [256][n]; first layers: A = X [n][in]
+    auto dw_t = [&](const float* XT, int m_rows, const float* DT, float* dW) {
+      GemmProb p = zero_prob();
+      p.A = XT; p.lda = (int)n; p.a_trans = 0; p.K = (int)n; p.split_k = 1;
+      p.B = DT; p.ldb = (int)n; p.b_trans = 1;
+      p.C = dW; p.ldc = H; p.M = m_rows; p.N = H;
+      return p;
+    };
+    auto dw_x = [&](const float* X, int ldx, int n_in, const float* DT, float* dW) {
+      GemmProb p = zero_prob();
+      p.A = X; p.lda = ldx; p.a_trans = 1; p.K = (int)n;
+      p.B = DT; p.ldb = (int)n; p.b_trans = 1;
+      p.C = dW; p.ldc = H; p.M = n_in; p.N = H;
+      return p;
+    };
+    FOR_EXPERTS {
+      Expert& x = E[i]; const Workspace& w = x.w;
+      TcRowSumBatch RS;
+      RS.n = 0; RS.rows = n;
+      auto rowsum = [&](const float* XT, int M, const float* Y, int ldy, int NJ, float* out) {
+        TcRowSum& r = RS.p[RS.n++];
+        r.XT = XT; r.ld = n; r.Y = Y; r.ldy = ldy; r.NJ = NJ; r.out = out; r.M = M; r.block_begin = 0;
+      };
+      // main.Q from the critic chain
+      rowsum(w.hq[L - 1], H, w.dQ, 1, 1, x.gQ + LQ.off_Wout);                  // dWout = h^T dQ
+      rowsum(nullptr, 1, w.dQ, 1, 1, x.gQ + LQ.off_bout);                      // dbout = sum dQ
+      for (int l = L - 1; l >= 1; --l) {
+        ADD(dw_t(w.hq[l - 1], H, w.dcl[l], x.gQ + LQ.off_W[l]));
+        rowsum(w.dcl[l], H, nullptr, 0, 1, x.gQ + LQ.off_b[l]);
+      }
+      ADD(dw_x(w.XQu, w.ld_sq, LQ.in_s, w.dcl[0], x.gQ + LQ.off_W0));
+      rowsum(w.dcl[0], H, nullptr, 0, 1, x.gQ + LQ.off_b0);
+      if (LQ.in_g > 0) ADD(dw_x(w.Xg, w.ld_g, LQ.in_g, w.dcl[0], x.gQ + LQ.off_W0g));
+      // main.pi from the actor chain
+      rowsum(w.hp[L - 1], H, w.dy, lddy, d->dimu, x.gP + LP.off_Wout);
+      rowsum(nullptr, 1, w.dy, lddy, d->dimu, x.gP + LP.off_bout);
+      for (int l = L - 1; l >= 1; --l) {
+        ADD(dw_t(w.hp[l - 1], H, w.dpl[l], x.gP + LP.off_W[l]));
+        rowsum(w.dpl[l], H, nullptr, 0, 1, x.gP + LP.off_b[l]);
+      }
+      ADD(dw_x(w.Xpi, w.ld_spi, LP.in_s, w.dpl[0], x.gP + LP.off_W0));
+      rowsum(w.dpl[0], H, nullptr, 0, 1, x.gP + LP.off_b0);
+      if (LP.in_g > 0) ADD(dw_x(w.Xg, w.ld_g, LP.in_g, w.dpl[0], x.gP + LP.off_W0g));
+      CUR_TRY(B.flush());
+      CUR_TRY(tc_chain_rowsums(s, RS));
+    }
+    CUR_TRY(B.B.T.finish(s));
+    return CUR_OK;
+  }
   // ---- fwd-1: main.pi | target.pi | main.Q(o,g,u)
   FOR_EXPERTS {
     Expert& x = E[i]; const Workspace& w = x.w;

@@ -153,6 +153,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_ll(unsigned long long* p, float v, uint32_t flag) {
+  const unsigned long long w = ((unsigned long long)flag << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(S_CONSUMERS) : "memory"); }
 
 struct Ring {
@@ -188,8 +197,8 @@ __device__ __forceinline__ void fma_row(float2 (&acc)[NR / 2][4], const float* _
 }
 
 // acc += sum over this thread's k rows of the next `nchunks` weight chunks of  xT[k][r] * W[k][4cg + c]
-template <int NR>
-__device__ __forceinline__ void gemv_chunks(const StreamParams& P, Ring& rg, int nchunks, const float* __restrict__ xT,
+template <int NR, class PT>
+__device__ __forceinline__ void gemv_chunks(const PT& P, Ring& rg, int nchunks, const float* __restrict__ xT,
                                             float2 (&acc)[NR / 2][4]) {
   const int cg = threadIdx.x & 63, ks = threadIdx.x >> 6;
 #pragma unroll 1
@@ -222,8 +231,8 @@ __device__ __forceinline__ void gemv_chunks(const StreamParams& P, Ring& rg, int
 
 // One dense layer for NR rows: chunks -> split-K partials -> fixed-order sum.  Returns, for the thread's column
 // `col = tid`, the NR pre-activation sums in v[] (without bias).
-template <int NR>
-__device__ __forceinline__ void layer_gemv(const StreamParams& P, Ring& rg, int nchunks, const float* xT, float* red,
+template <int NR, class PT>
+__device__ __forceinline__ void layer_gemv(const PT& P, Ring& rg, int nchunks, const float* xT, float* red,
                                            float (&v)[NR]) {
   float2 acc[NR / 2][4];
 #pragma unroll
@@ -386,8 +395,8 @@ __device__ __forceinline__ float relu_mask(float v, float m) { return m > 0.f ? 
 // One forward net for NR rows: L hidden layers (bias + ReLU) from the first-layer input already in `xa`; optional
 // row-major copies of every hidden activation (rows 0-3 -> h_a, rows 4-7 -> h_b).  Returns the buffer that holds
 // the last hidden activations (transposed).
-template <int NR>
-__device__ __forceinline__ float* forward_net(const StreamParams& P, Ring& rg, int ch0, float* xa, float* xb, float* red,
+template <int NR, class PT>
+__device__ __forceinline__ float* forward_net(const PT& P, Ring& rg, int ch0, float* xa, float* xb, float* red,
                                               const float* const* bias, float* const* h_a, float* const* h_b,
                                               int64_t row0) {
   const int col = threadIdx.x;
@@ -669,6 +678,145 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   S_TL(7);
 }
 
+// ------------------------------------------------------------------------------------------------
+// get_actions as ONE launch (ddpg.py:129-146 with _preprocess_og, :118-127): one CTA per 4 rows walks pi (and, for
+// compute_Q, Q on the noise-free action) with the same weight ring / GEMV core as the update kernel.  Inputs may
+// live in mapped pinned HOST memory (zero-copy over PCIe: a rollout step is n = 2 rows, 0.5 KB) and so may the outputs;
+// the last CTA to finish then stores the call's sequence number into a host-visible word the caller polls - no
+// memcpy calls, no stream synchronisation on the critical path of a rollout step (rollout.py:217,226).
+constexpr int A_MAXCHUNK = 64;          // pi + Q forward chunks (L = 4: 2 * 27)
+
+struct ActParams {
+  cur_net_desc d;
+  int in_sp, in_g, KP, L, nchunks;
+  int dbg_skip_math;         // (read by the shared GEMV core)
+  int ch0[2];                // chunks of the first layer: [0] pi, [1] Q
+  int64_t n;
+  const float *o, *g, *td;
+  const float* ag;           // relative goals: g <- g - ag (ddpg.py:120-125), else NULL
+  const float *o_mean, *o_std, *g_mean, *g_std;
+  float clip;                // clip o, g to +-clip (<= 0: off)
+  uint32_t seq;              // != 0: outputs are 8-byte words {float32 bits | seq << 32} the host polls ("LL" words)
+  const float *bP[S_MAXL], *bQ[S_MAXL];
+  const float *WoutP, *boutP, *WoutQ, *boutQ;
+  void *pi, *q;              // [n][dimu], [n] (or NULL): float32, or LL words when seq != 0
+  long long* tl;
+  SChunk chunks[A_MAXCHUNK];
+};
+
+__device__ __forceinline__ float act_x_elem(const ActParams& P, int64_t row, int r, int k, int act_kind, const float* ths) {
+  const cur_net_desc& d = P.d;
+  const bool nrm = d.normalize_obs != 0;
+  const int in_s = P.in_sp + (act_kind ? d.dimu : 0);
+  const float clip = P.clip;
+  float v = 0.f;
+  int gj = -1, aj = -1;
+  if (k < d.dimo) {
+    v = P.o[row * d.dimo + k];
+    if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+    if (nrm) v = norm1s(v, P.o_mean, P.o_std, k, d.norm_clip);
+  } else if (d.modular) {
+    if (k < d.dimo + d.dimtd) v = P.td[row * d.dimtd + (k - d.dimo)];       // never normalised
+    else if (k < in_s) aj = k - d.dimo - d.dimtd;
+    else if (k < in_s + d.dimg) gj = k - in_s;
+  } else {
+    if (k < d.dimo + d.dimg) gj = k - d.dimo;
+    else if (k < in_s) aj = k - d.dimo - d.dimg;
+  }
+  if (gj >= 0) {
+    v = P.g[row * d.dimg + gj];
+    if (P.ag) v = __fsub_rn(v, P.ag[row * d.dimg + gj]);
+    if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
+    if (nrm) v = norm1s(v, P.g_mean, P.g_std, gj, d.norm_clip);
+  }
+  if (aj >= 0) v = ths[r * S_DU + aj];
+  return v;
+}
+
+// an output element: plain float32, or - seq != 0 - one naturally aligned 8-byte word {value | seq << 32}: a 64-bit
+// store is single-copy atomic (also across PCIe), so the host polls the data words themselves and the kernel needs
+// neither a system fence nor a completion ticket
+__device__ __forceinline__ void put_out(void* base, int64_t i, float v, uint32_t seq) {
+  if (seq == 0) reinterpret_cast<float*>(base)[i] = v;
+  else st_ll(reinterpret_cast<unsigned long long*>(base) + i, v, seq);
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+actions_stream_kernel(const __grid_constant__ ActParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ringf = reinterpret_cast<float*>(smem_raw);
+  float* xa = ringf + S_NSLOT * S_SLOT;
+  float* xb = xa + S_XT;
+  float* red = xb + S_XT;
+  float* misc = red + S_RED;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + S_MISC);
+  float* s_th = misc;                 // [4][8] tanh output
+  float* s_q = misc + 64;             // [4][8]
+  const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * S_ROWS;
+  const cur_net_desc& d = P.d;
+  const uint32_t full = smem_addr(bars), empty = smem_addr(bars + S_NSLOT);
+  if (tid == 0) {
+    for (int i = 0; i < S_NSLOT; ++i) {
+      mbar_init(full + 8 * i, 1);
+      mbar_init(empty + 8 * i, S_CONSUMERS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid >= S_CONSUMERS) {
+    if (tid == S_CONSUMERS) {
+      const uint32_t ring_s = smem_addr(ringf);
+      for (int i = 0; i < P.nchunks; ++i) {
+        const int slot = i % S_NSLOT, round = i / S_NSLOT;
+        if (round > 0) mbar_wait(empty + 8 * slot, (round - 1) & 1);
+        const uint32_t bytes = (uint32_t)P.chunks[i].nrows * S_H * 4;
+        mbar_expect_tx(full + 8 * slot, bytes);
+        bulk_g2s(ring_s + slot * S_SLOT * 4, P.chunks[i].src, bytes, full + 8 * slot);
+      }
+    }
+    return;
+  }
+  Ring rg;
+  rg.chunks = P.chunks; rg.slots = ringf; rg.full = full; rg.empty = empty; rg.cons = 0;
+  const int nr = (int)((P.n - row0 < S_ROWS) ? P.n - row0 : S_ROWS);      // rows of this CTA that exist
+#define A_TL(i)                                                                              \
+  do {                                                                                       \
+    if (P.tl != nullptr && tid == 0 && blockIdx.x == 0) P.tl[i] = (long long)globaltimer_ns(); \
+  } while (0)
+  A_TL(0);
+  auto build = [&](int act_kind) {
+    for (int idx = tid; idx < S_ROWS * P.KP; idx += S_CONSUMERS) {
+      const int k = idx >> 2, r = idx & 3;
+      xa[k * 4 + r] = act_x_elem(P, row0 + (r < nr ? r : nr - 1), r, k, act_kind, s_th);
+    }
+  };
+  build(0);
+  consumer_sync();
+  A_TL(1);
+  float* xl = forward_net<4>(P, rg, P.ch0[0], xa, xb, red, P.bP, nullptr, nullptr, row0);
+  small_out(xl, 4, 0, 4, P.WoutP, d.dimu, 1, d.dimu, P.boutP, s_th);
+  consumer_sync();
+  A_TL(2);
+  if (tid < S_ROWS * S_DU && (tid & (S_DU - 1)) < d.dimu) {
+    const float th = tanhf(s_th[tid]);                                  // actor_critic.py:89
+    s_th[tid] = th;
+    const int r = tid >> 3, j = tid & (S_DU - 1);
+    if (r < nr) put_out(P.pi, (row0 + r) * d.dimu + j, d.max_u * th, P.seq);
+  }
+  consumer_sync();
+  if (P.q != nullptr) {
+    build(2);                                                          // Q(o, g, pi / max_u): the noise-free action
+    consumer_sync();
+    xl = forward_net<4>(P, rg, P.ch0[1], xa, xb, red, P.bQ, nullptr, nullptr, row0);
+    small_out(xl, 4, 0, 4, P.WoutQ, 1, 1, 1, P.boutQ, s_q);
+    consumer_sync();
+    if (tid < nr) put_out(P.q, row0 + tid, s_q[tid * S_DU], P.seq);
+  }
+  A_TL(3);
+#undef A_TL
+}
+
 // W^T of the hidden layers (operands of the backward streams): dst[m][j][i] = src_m[i][j], 256 x 256 each
 struct TransposeParams {
   const float* src[2 * S_MAXL];
@@ -704,19 +852,10 @@ struct XchgDev {
   int* error_flag;
 };
 
-__device__ __forceinline__ void st_ll(unsigned long long* p, float v, uint32_t flag) {
-  const unsigned long long w = ((unsigned long long)flag << 32) | (unsigned long long)__float_as_uint(v);
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
 __device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
 }
 // a peer that does not show up for ~20 s is dead or diverged: fail loudly (the host sees a launch failure)
 __device__ __noinline__ void xchg_timeout_check(unsigned long long t0, int* error_flag) {
@@ -1546,5 +1685,106 @@ extern "C" int cur_ddpg_rows_transposes(const cur_net_desc* d, float* workspace,
     out->begin[out->n] = LQ.off_W[l]; out->dst[out->n++] = w.TQ[l];
     out->begin[out->n] = offP + LP.off_W[l]; out->dst[out->n++] = w.TP[l];
   }
+  return CUR_OK;
+}
+
+
+// One launch for DDPG.get_actions (see actions_stream_kernel).  o / ag / g / td / out_pi / out_q may be device
+// pointers of mapped pinned host memory.  seq != 0: the outputs are 8-byte words {float32 bits | seq << 32}.
+extern "C" int cur_ddpg_actions_rows(void* stream, const cur_net_desc* d, const float* theta, const cur_norm_stats* stats,
+                                     const float* o, const float* ag, const float* g, const float* td, int64_t n,
+                                     float clip_obs, void* out_pi, void* out_q, uint32_t seq) {
+  CUR_TRY(check_desc(d));
+  CUR_REQUIRE(theta && o && g && out_pi, "NULL argument");
+  CUR_REQUIRE(!d->modular || td, "task_descr required for a modular net");
+  CUR_REQUIRE(n > 0 && n <= 4096, "bad row count (the one-launch action path covers up to 4096 rows)");
+  CUR_REQUIRE(rows_supported(d, S_ROWS), "shape not supported by the rows schedule (see cur_ddpg_rows_supported)");
+  if (d->normalize_obs)
+    CUR_REQUIRE(stats && stats->o_mean && stats->o_std && stats->g_mean && stats->g_std, "normalizer stats required");
+  const NetLayout LQ = net_layout(*d, 0), LP = net_layout(*d, 1);
+  const float *thQ = theta, *thP = theta + r4(LQ.total);
+  const int L = d->layers, H = d->hidden;
+  static bool configured = false;
+  static bool tl_on = false;
+  if (!configured) {
+    CUR_CUDA_TRY(cudaFuncSetAttribute(actions_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)S_SMEM_BYTES));
+    tl_on = getenv("CUR_ACTIONS_TIMELINE") != nullptr;
+    configured = true;
+  }
+  ActParams P;
+  P.d = *d;
+  P.in_sp = LP.in_s; P.in_g = LQ.in_g; P.L = L;
+  P.KP = (LQ.in_s + LQ.in_g + 3) / 4 * 4;
+  P.dbg_skip_math = 0;
+  P.n = n;
+  P.o = o; P.g = g; P.td = td; P.ag = ag; P.clip = clip_obs; P.seq = seq;
+  P.o_mean = P.o_std = P.g_mean = P.g_std = nullptr;
+  if (stats) { P.o_mean = stats->o_mean; P.o_std = stats->o_std; P.g_mean = stats->g_mean; P.g_std = stats->g_std; }
+  for (int l = 0; l < S_MAXL; ++l) {
+    P.bP[l] = l < L ? thP + ((l == 0) ? LP.off_b0 : LP.off_b[l]) : nullptr;
+    P.bQ[l] = l < L ? thQ + ((l == 0) ? LQ.off_b0 : LQ.off_b[l]) : nullptr;
+  }
+  P.WoutP = thP + LP.off_Wout; P.boutP = thP + LP.off_bout;
+  P.WoutQ = thQ + LQ.off_Wout; P.boutQ = thQ + LQ.off_bout;
+  P.pi = out_pi; P.q = out_q;
+  int nc = 0;
+  auto rows_of = [&](const float* src, int nrows, int k0) {
+    for (int r = 0; r < nrows; r += S_CK) {
+      SChunk& C = P.chunks[nc++];
+      C.src = src + (int64_t)r * H; C.nrows = (nrows - r < S_CK) ? nrows - r : S_CK; C.k0 = k0 + r;
+    }
+  };
+  auto forward_net = [&](const float* th, const NetLayout& NL) {
+    const int before = nc;
+    rows_of(th + NL.off_W0, NL.in_s, 0);
+    if (NL.in_g > 0) rows_of(th + NL.off_W0g, NL.in_g, NL.in_s);
+    const int first = nc - before;
+    for (int l = 1; l < L; ++l) rows_of(th + NL.off_W[l], H, 0);
+    return first;
+  };
+  CUR_REQUIRE((out_q ? 2 : 1) * (4 + (L - 1) * (H / S_CK)) <= A_MAXCHUNK, "too many weight chunks");
+  P.ch0[0] = forward_net(thP, LP);
+  P.ch0[1] = out_q != nullptr ? forward_net(thQ, LQ) : 0;
+  P.nchunks = nc;
+  static long long* tl_dev = nullptr;
+  static int tl_calls = 0;
+  if (tl_on && tl_dev == nullptr) {
+    CUR_CUDA_TRY(cudaMalloc(&tl_dev, 8 * sizeof(long long)));
+    CUR_CUDA_TRY(cudaMemset(tl_dev, 0, 8 * sizeof(long long)));
+  }
+  P.tl = tl_on ? tl_dev : nullptr;
+  const unsigned blocks = (unsigned)((n + S_ROWS - 1) / S_ROWS);
+  actions_stream_kernel<<<blocks, S_THREADS, S_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+  CUR_CHECK_LAUNCH();
+  if (tl_on && ++tl_calls == 100) {          // debug only: one warmed-up timeline of CTA 0 (%globaltimer, ns)
+    long long t[8];
+    CUR_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    CUR_CUDA_TRY(cudaMemcpy(t, tl_dev, sizeof(t), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[actions timeline] inputs %lld | pi forward %lld | outputs (+ Q) %lld | total %lld ns\n", t[1] - t[0],
+            t[2] - t[1], t[3] - t[2], t[3] - t[0]);
+  }
+  return CUR_OK;
+}
+
+// Mapped pinned host memory for the zero-copy action path: *host_ptr is the CPU address, *dev_ptr the address the
+// kernels use (equal under unified addressing).  Freed with cur_host_free.
+extern "C" int cur_host_alloc(int64_t bytes, void** host_ptr, void** dev_ptr) {
+  CUR_REQUIRE(bytes > 0 && host_ptr && dev_ptr, "bad argument");
+  CUR_CUDA_TRY(cudaHostAlloc(host_ptr, (size_t)bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  CUR_CUDA_TRY(cudaHostGetDevicePointer(dev_ptr, *host_ptr, 0));
+  memset(*host_ptr, 0, (size_t)bytes);
+  return CUR_OK;
+}
+
+// cudaMemcpyAsync(host -> device) on `stream` (`src` from cur_host_alloc, so the copy is asynchronous)
+extern "C" int cur_copy_h2d(void* stream, void* dst, const void* src, int64_t bytes) {
+  CUR_REQUIRE(dst && src && bytes >= 0, "bad argument");
+  CUR_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return CUR_OK;
+}
+
+extern "C" int cur_host_free(void* host_ptr) {
+  if (host_ptr) CUR_CUDA_TRY(cudaFreeHost(host_ptr));
   return CUR_OK;
 }

@@ -48,4 +48,42 @@ struct TcLauncher {
   bool empty() const { return G.n == 0 && R.n == 0 && n_rowred == 0 && n_skinny == 0; }
 };
 
+// ---- the fused actor / critic chain kernel (tc_chain.cu)
+struct TcChainIO {
+  int64_t n, grad_rows;
+  const float *mQ, *mP, *tQ, *tP;                       // parameter blocks of the four nets
+  const float *Xpi, *Xg, *XQu, *Xpi_t, *Xg_t;           // prepared first-layer inputs [n][ld]
+  float *XQpi, *XQ_t;                                   // ... whose action columns the kernel fills
+  int ld_spi, ld_sq, ld_g, lddy;
+  // TRANSPOSED copies [256][n] the weight gradients need: activations (main.pi, main.Q(u)), deltas (critic, actor chain)
+  float *hp[CUR_MAX_LAYERS], *hq[CUR_MAX_LAYERS], *dc[CUR_MAX_LAYERS], *dp[CUR_MAX_LAYERS];
+  uint32_t *mp, *mq, *mqp;                              // ReLU mask words [layers][8][n] of main.pi, main.Q(u), main.Q(pi)
+  float *Q, *Qt, *dQ, *dy, *q_pi;
+  const float* r;
+  float gamma, clip_return, action_l2;
+  int clip_pos;
+  float *loss_part;                                     // [n / 128][4]
+  float *q_loss, *pi_loss;
+  int64_t* step_counter;
+  int loss_ring;
+};
+// bias / output-layer weight gradients from the transposed copies (tc_chain_rowsum_kernel)
+struct TcRowSum {
+  const float* XT; int64_t ld;      // [M][rows] (NULL: ones)
+  const float* Y; int ldy, NJ;      // optional [rows][NJ <= 4]
+  float* out; int M, block_begin;
+};
+struct TcRowSumBatch {
+  TcRowSum p[24];
+  int n;
+  int64_t rows;
+};
+int tc_chain_rowsums(cudaStream_t s, TcRowSumBatch& R);
+bool tc_chain_supported(const cur_net_desc& d, int64_t n);
+int tc_chain_launch(cudaStream_t s, const cur_net_desc& d, const TcChainIO& io);
+void tc_chain_set_timeline(long long* dev);             // 128 x int64 debug stamps (CTA 0 / CTA 1) or NULL
+// row-major [rows][cols] fp32 operand as a TMA tensor map in the layouts the tcgen05 descriptors expect (tc_gemm.cu)
+int tc_make_map(void* map /* CUtensorMap */, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                bool mn_major);
+
 }  // namespace cur

@@ -94,6 +94,9 @@ class DDPG(object):
         self.action_noise = kwargs.get('action_noise', 'host')
         assert self.action_noise in ('host', 'device')
         self._action_calls = 0
+        self.action_path = kwargs.get('action_path', 'auto')   # 'levels': always the multi-launch forward
+        self._action_rows = None
+        self._action_slots = {}
         self.create_actor_critic = import_function(self.network_class)
 
         self.dimo = self.input_dims['o']
@@ -250,13 +253,107 @@ class DDPG(object):
         g = np.clip(g, -self.clip_obs, self.clip_obs)
         return o, g
 
+    def _action_slot(self, n):
+        """Persistent mapped pinned buffers of the one-launch action path for n rows: the inputs, and the outputs as
+        8-byte words {float32 | call number} (cur_ddpg_actions_rows)."""
+        slot = self._action_slots.get(n)
+        if slot is None:
+            lib = _lib.load()
+            sizes = [('o', n * self.dimo), ('g', n * self.dimg)]
+            if self.relative_goals:
+                sizes.append(('ag', n * self.dimag))
+            if self.modular:
+                sizes.append(('td', n * self.dimtd))
+            sizes += [('out', 2 * n * (self.dimu + 1))]           # [pi words | q words]
+            total = sum((sz + 3) // 4 * 4 for _, sz in sizes)
+            hp, dp = C.c_void_p(), C.c_void_p()
+            _lib.check(lib.cur_host_alloc(4 * total, C.byref(hp), C.byref(dp)), 'cur_host_alloc')
+            host = np.ctypeslib.as_array((C.c_float * total).from_address(hp.value))
+            slot = dict(host_ptr=hp.value, seq=0)
+            k = 0
+            for name, sz in sizes:
+                slot[name] = host[k:k + sz]
+                slot['d_' + name] = dp.value + 4 * k
+                k += (sz + 3) // 4 * 4
+            words = slot['out'].reshape(n * (self.dimu + 1), 2)
+            slot['val'] = words[:, 0]                              # float32 values: n * dimu actions, then n Q values
+            slot['tag'] = words[:, 1].view(np.uint32)              # the call number each word was written by
+            slot['d_q'] = slot['d_out'] + 8 * n * self.dimu
+            self._action_slots[n] = slot
+        return slot
+
+    def _actions_one_launch(self, o, ag, g, task_descr, n, theta, compute_Q, device_noise, noise_eps, random_eps):
+        """cur_ddpg_actions_rows: inputs read from / actions written to mapped pinned memory by the kernel; completion =
+        every output word carries this call's number (no copies, no stream synchronisation, no fence).  Returns the flat
+        [pi | q] host array."""
+        lib = _lib.load()
+        slot = self._action_slot(n)
+        np.copyto(slot['o'], o.reshape(-1))
+        np.copyto(slot['g'], g.reshape(-1))
+        if self.relative_goals:
+            np.copyto(slot['ag'], np.asarray(ag, np.float32).reshape(-1))
+        if self.modular:
+            np.copyto(slot['td'], np.asarray(task_descr, np.float32).reshape(-1))
+        n_out = n * (self.dimu + (1 if compute_Q else 0))
+        noisy = device_noise and (noise_eps != 0. or random_eps != 0.)
+        if noisy or n > self.ACTION_ZERO_COPY_MAX:
+            # plain float32 outputs in device memory, one D2H copy: device-side noise works in place on the device array
+            # (Q is evaluated on the noise-free action, like the reference's Q_pi_tf, ddpg.py:138-146), and above a few
+            # dozen rows 4-byte accesses over PCIe cost more than one bulk copy each way
+            out = torch.empty(n * (self.dimu + 1), dtype=torch.float32, device=self.device)
+            base = slot['d_o']
+            if n > self.ACTION_ZERO_COPY_MAX:
+                if 'dev_in' not in slot:
+                    slot['n_in'] = (slot['d_out'] - slot['d_o']) // 4
+                    slot['dev_in'] = torch.empty(slot['n_in'], dtype=torch.float32, device=self.device)
+                _lib.check(lib.cur_copy_h2d(_lib.stream_ptr(), slot['dev_in'].data_ptr(), slot['d_o'], 4 * slot['n_in']),
+                           'cur_copy_h2d')
+                base = slot['dev_in'].data_ptr()
+            rel = lambda name: base + (slot[name] - slot['d_o'])
+            _lib.check(lib.cur_ddpg_actions_rows(
+                _lib.stream_ptr(), C.byref(self.net.desc), theta.data_ptr(), C.byref(self._stats), base,
+                rel('d_ag') if self.relative_goals else None, rel('d_g'), rel('d_td') if self.modular else None, n,
+                float(self.clip_obs), out.data_ptr(), out.data_ptr() + 4 * n * self.dimu if compute_Q else None, 0),
+                'cur_ddpg_actions_rows')
+            if noisy:
+                _lib.check(lib.cur_action_noise(_lib.stream_ptr(), out.data_ptr(), n, self.dimu, float(self.max_u),
+                                                float(noise_eps), float(random_eps), int(self.noise_seed) & (2 ** 64 - 1),
+                                                self._action_calls), 'cur_action_noise')
+            return out[:n_out].cpu().numpy()
+        slot['seq'] = seq = slot['seq'] % 0xFFFFFFF0 + 1
+        _lib.check(lib.cur_ddpg_actions_rows(
+            _lib.stream_ptr(), C.byref(self.net.desc), theta.data_ptr(), C.byref(self._stats), slot['d_o'],
+            slot['d_ag'] if self.relative_goals else None, slot['d_g'], slot['d_td'] if self.modular else None, n,
+            float(self.clip_obs), slot['d_out'], slot['d_q'] if compute_Q else None, seq), 'cur_ddpg_actions_rows')
+        tag = slot['tag'][:n_out]
+        last = n_out - 1
+        spins = 0
+        while tag[last] != seq or not (tag == seq).all():
+            spins += 1
+            if spins > 200000:                     # ~0.1 s without an answer: let a launch failure surface, then give up
+                torch.cuda.current_stream().synchronize()
+                if not (tag == seq).all():
+                    raise RuntimeError('cur_ddpg_actions_rows did not complete')
+        return slot['val'][:n_out].copy()
+
+    ACTION_ROWS_MAX = 512      # rows per call served by the one-launch path (one CTA per 4 rows)
+    ACTION_ZERO_COPY_MAX = 64  # ... of which up to this many rows travel zero-copy (kernel reads / writes host memory)
+
     def get_actions(self, o, ag, g, task_descr=None, noise_eps=0., random_eps=0., use_target_net=False,
                     compute_Q=False):
-        """ddpg.py:129-161.  One H2D blob, prep + MLP kernels, one D2H; exploration noise on the host RNG (default)
-        or on the device (`action_noise='device'`)."""
+        """ddpg.py:129-161.  Up to ACTION_ROWS_MAX rows (the rollout's per-step call): ONE launch that reads the host
+        arrays and writes the host actions itself (`_actions_one_launch`); larger batches: one H2D blob, prep + MLP level
+        kernels, one D2H.  Exploration noise on the host RNG (default) or on the device (`action_noise='device'`)."""
         o = np.asarray(o, np.float32).reshape(-1, self.dimo)
         g = np.asarray(g, np.float32).reshape(-1, self.dimg)
         n = o.shape[0]
+        theta = self.theta_target if use_target_net else self.theta_main
+        device_noise = self.action_noise == 'device'
+        if n <= self.ACTION_ROWS_MAX and self._action_rows_ok():
+            res = self._actions_one_launch(o, ag, g, task_descr, n, theta, compute_Q, device_noise, noise_eps, random_eps)
+            if device_noise:
+                self._action_calls += 1
+            return self._finish_actions(res, n, compute_Q, device_noise, noise_eps, random_eps)
         parts = [o, g]
         if self.relative_goals:
             parts.append(np.asarray(ag, np.float32).reshape(-1, self.dimag))
@@ -283,12 +380,10 @@ class DDPG(object):
             idx += 1
         p_td = ptrs[idx] if self.modular else None
         out = torch.empty(n * (self.dimu + (1 if compute_Q else 0)), dtype=torch.float32, device=self.device)
-        theta = self.theta_target if use_target_net else self.theta_main
         _lib.check(_lib.load().cur_ddpg_actions(
             _lib.stream_ptr(), C.byref(self.net.desc), theta.data_ptr(), C.byref(self._stats), p_o, p_ag, p_g, p_td, n,
             float(self.clip_obs), self._workspace(n).data_ptr(), out.data_ptr(),
             out.data_ptr() + 4 * n * self.dimu if compute_Q else None), 'cur_ddpg_actions')
-        device_noise = self.action_noise == 'device'
         if device_noise:
             # Q above was evaluated on the noise-free action, like the reference's Q_pi_tf (ddpg.py:138-146)
             if noise_eps != 0. or random_eps != 0.:
@@ -296,24 +391,27 @@ class DDPG(object):
                                                         float(noise_eps), float(random_eps), int(self.noise_seed) & (2 ** 64 - 1),
                                                         self._action_calls), 'cur_action_noise')
             self._action_calls += 1
-        res = out.cpu().numpy()
-        ret = [res[:n * self.dimu].reshape(n, self.dimu).copy()]
-        if compute_Q:
-            ret.append(res[n * self.dimu:].reshape(n, 1).copy())
-        # action postprocessing (ddpg.py:147-155), host RNG in reference order
-        u = ret[0]
+        return self._finish_actions(out.cpu().numpy(), n, compute_Q, device_noise, noise_eps, random_eps)
+
+    def _action_rows_ok(self):
+        if self._action_rows is None:
+            self._action_rows = bool(self.action_path != 'levels' and
+                                     _lib.load().cur_ddpg_rows_supported(C.byref(self.net.desc), 4))
+        return self._action_rows
+
+    def _finish_actions(self, res, n, compute_Q, device_noise, noise_eps, random_eps):
+        """Action postprocessing (ddpg.py:147-155) on the flat [pi | q] host array `res` (owned by this call): host RNG
+        consumed in reference order (randn, binomial, uniform - also when the eps are 0, like the reference)."""
+        u = res[:n * self.dimu].reshape(n, self.dimu)
         if not device_noise:
-            noise = noise_eps * self.max_u * np.random.randn(*u.shape)
-            u += noise
-            u = np.clip(u, -self.max_u, self.max_u)
-            u += np.random.binomial(1, random_eps, u.shape[0]).reshape(-1, 1) * (self._random_action(u.shape[0]) - u)
-        if u.shape[0] == 1:
-            u = u[0]
-        u = u.copy()
-        ret[0] = u
-        if len(ret) == 1:
-            return ret[0]
-        return ret
+            u += noise_eps * self.max_u * np.random.randn(n, self.dimu)                    # ddpg.py:148-149
+            lim = self.max_u
+            np.minimum(np.maximum(u, -lim, out=u), lim, out=u)                              # np.clip, ddpg.py:150
+            u += np.random.binomial(1, random_eps, n).reshape(-1, 1) * (self._random_action(n) - u)   # ddpg.py:151
+        u = u[0].copy() if n == 1 else u.copy()                                            # ddpg.py:152-154
+        if not compute_Q:
+            return u
+        return [u, res[n * self.dimu:].reshape(n, 1).copy()]
 
     # ------------------------------------------------------------------------------------------
     def _multi_buffer(self):

@@ -266,6 +266,21 @@ int cur_ddpg_actions(void* stream, const cur_net_desc* d, const float* theta,
                      const float* g, const float* td, int64_t n, float clip_obs, float* workspace,
                      float* out_pi, float* out_q /* or NULL */);
 
+/* The same forward as ONE launch for the rollout's per-step call (rollout.py:217,226: n = rollout_batch_size rows, 50
+ * calls per episode; hidden 256, see cur_ddpg_rows_supported): one CTA per 4 rows streams the net through shared memory.
+ * Every data pointer may address MAPPED PINNED HOST memory (cur_host_alloc) - inputs are then read and actions written
+ * over PCIe by the kernel itself.  seq == 0: out_pi / out_q are float32 arrays.  seq != 0: they are arrays of 8-byte words
+ * {float32 bits | seq << 32}; an aligned 64-bit store is single-copy atomic, so a caller that owns the (host-visible)
+ * buffer polls the words for its call number instead of issuing copies and a stream synchronisation.  n <= 4096. */
+int cur_ddpg_actions_rows(void* stream, const cur_net_desc* d, const float* theta, const cur_norm_stats* stats,
+                          const float* o, const float* ag /* or NULL */, const float* g, const float* td, int64_t n,
+                          float clip_obs, void* out_pi, void* out_q /* or NULL */, uint32_t seq);
+/* cudaHostAlloc(mapped | portable): *host_ptr for the CPU, *dev_ptr for the kernels; zero-filled. */
+int cur_host_alloc(int64_t bytes, void** host_ptr, void** dev_ptr);
+int cur_host_free(void* host_ptr);
+/* cudaMemcpyAsync(host -> device) on `stream`; `src` from cur_host_alloc */
+int cur_copy_h2d(void* stream, void* dst, const void* src, int64_t bytes);
+
 /* Device-side option for the exploration noise of get_actions (ddpg.py:147-152), in place on
  * u [n, dimu] (the out_pi of cur_ddpg_actions): Gaussian noise noise_eps * max_u * N(0,1), clip to +-max_u, then with
  * probability random_eps per row the action is replaced by a uniform one in [-max_u, max_u].  Draws are Philox4x32-10
@@ -491,6 +506,13 @@ int cur_tc_gemm_timeline(long long* device_buffer_128);
  * 1 tensor cores for every eligible shape (batch >= 256, batch % 128 == 0, hidden == 256). */
 int cur_ddpg_set_tensor_cores(int mode);
 int cur_ddpg_uses_tensor_cores(const cur_net_desc* d, int64_t batch);
+/* Large batches (a multiple of 128 rows, hidden 256, 2-4 hidden layers) with the tensor cores on: forward nets, losses
+ * and the data-gradient chains run as ONE launch - a CTA per 128-row tile and chain (csrc/tc_chain.cu) - followed by the
+ * split-K weight-gradient GEMMs.  mode -1: default (on; CUR_DDPG_CHAIN=0 turns it off), 0: level-by-level schedule, 1: on. */
+int cur_ddpg_set_chain(int mode);
+int cur_ddpg_uses_chain(const cur_net_desc* d, int64_t batch);
+/* debug: in-kernel clock64 timeline of the chain kernel's first actor / critic CTA (1024 x int64 device buffer, or NULL) */
+int cur_tc_chain_timeline(long long* device_buffer_1024);
 int64_t cur_tc_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int a_trans);
 int cur_tc_gemm(void* stream, const float* A, int64_t lda, int a_trans, const float* B, int64_t ldb,
                 int b_trans, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,

@@ -219,7 +219,7 @@ def test_get_actions_against_oracle():
     gpu.o_stats.load_state_list([ora.o_stats.sum, ora.o_stats.sumsq, ora.o_stats.count, ora.o_stats.mean, ora.o_stats.std])
     gpu.g_stats.load_state_list([ora.g_stats.sum, ora.g_stats.sumsq, ora.g_stats.count, ora.g_stats.mean, ora.g_stats.std])
     rng = np.random.RandomState(5)
-    for n in (1, 2, 38):
+    for n in (1, 2, 38, 203, 700):               # <= 512 rows: the one-launch path, above: the level kernels
         o = rng.standard_normal((n, dims['o'])).astype(np.float32) * 100
         g = rng.uniform(-1, 1, (n, dims['g'])).astype(np.float32)
         ag = rng.uniform(-1, 1, (n, dims['ag'])).astype(np.float32)
@@ -232,13 +232,59 @@ def test_get_actions_against_oracle():
             u_g, q_g = gpu.get_actions(o, ag, g, task_descr=td, noise_eps=0.2, random_eps=0.3,
                                        use_target_net=use_target, compute_Q=True)
             assert u_g.shape == u_o.shape and (n > 1 or u_g.ndim == 1)
-            assert np.allclose(u_g, u_o, rtol=1e-5, atol=1e-6)
-            assert np.allclose(q_g, q_o, rtol=1e-5, atol=1e-6)
+            assert np.allclose(u_g, u_o, rtol=1e-5, atol=1e-6 if n < 100 else 1e-5)      # (see the note below)
+            assert np.allclose(q_g, q_o, rtol=1e-5, atol=1e-6 if n < 100 else 1e-5)
         np.random.seed(10)
         # raw network output: inputs here are 100x out of distribution (clipped to +-200, normalised,
         # clipped to +-5), so pre-tanh sums of ~45 terms of magnitude ~5; 1e-5 of the action range max_u
         assert np.allclose(gpu.get_actions(o, ag, g, task_descr=td), ora.get_actions(o, ag, g, task_descr=td),
                            rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('structure,relative_goals,normalize_obs,action_noise',
+                         [('curious', False, False, 'host'), ('curious', True, True, 'host'), ('flat', False, True, 'host'),
+                          ('curious', False, True, 'device'), ('task_experts', False, False, 'host')])
+def test_one_launch_actions_equal_the_level_kernels(structure, relative_goals, normalize_obs, action_noise):
+    """The rollout-step path (cur_ddpg_actions_rows: one launch, zero-copy host buffers, polled completion word) against
+    the multi-launch forward of the same library on the same weights: every option that changes the network input, both
+    nets, with and without Q, row counts that are not multiples of the 4-row CTA, repeated calls (buffer reuse)."""
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(4, structure=structure, task_replay='' if structure == 'flat' else
+                                          ('replay_current_task_buffer' if structure == 'task_experts' else
+                                           'replay_task_cp_buffer'), normalize_obs=normalize_obs,
+                                          relative_goals=relative_goals)
+    if structure == 'task_experts':
+        kw['t_id'] = 2
+    a = make_gpu_agent(kw, dims, ag_ids, g_ids, seed=3, action_noise=action_noise)
+    b = make_gpu_agent(kw, dims, ag_ids, g_ids, seed=3, action_noise=action_noise, action_path='levels')
+    assert a._action_rows_ok() and not b._action_rows_ok()
+    for ag_ in (a, b):                                             # non-trivial statistics and a target net that differs
+        ag_.o_stats.load_state_list([np.zeros(dims['o']), np.zeros(dims['o']), np.ones(1),
+                                     np.linspace(-0.5, 0.5, dims['o']), np.linspace(0.5, 2.0, dims['o'])])
+        ag_.g_stats.load_state_list([np.zeros(dims['g']), np.zeros(dims['g']), np.ones(1),
+                                     np.linspace(-0.1, 0.1, dims['g']), np.linspace(0.05, 0.3, dims['g'])])
+        ag_.set_flat('Q', ag_.get_flat('Q') * 1.5, target=True)
+        ag_.set_flat('pi', ag_.get_flat('pi') * 0.5, target=True)
+    rng = np.random.RandomState(11)
+    flat = structure == 'flat'
+    for n in (1, 2, 3, 4, 5, 38, 2, 511, 2):
+        o = rng.standard_normal((n, dims['o'])).astype(np.float32) * 3
+        g = rng.uniform(-0.3, 0.3, (n, dims['g'])).astype(np.float32)
+        ag = rng.uniform(-0.3, 0.3, (n, dims['ag'])).astype(np.float32)
+        td = None if flat else np.eye(4, dtype=np.float32)[rng.randint(0, 4, n)]
+        for use_target in (False, True):
+            for compute_Q in (False, True):
+                outs = []
+                for ag_ in (a, b):
+                    np.random.seed(4)
+                    outs.append(ag_.get_actions(o, ag, g, task_descr=td, noise_eps=0.1, random_eps=0.2,
+                                                use_target_net=use_target, compute_Q=compute_Q))
+                if compute_Q:
+                    (ua, qa), (ub, qb) = outs
+                    assert qa.shape == qb.shape == (n, 1) and np.allclose(qa, qb, rtol=1e-5, atol=2e-6)
+                else:
+                    ua, ub = outs
+                assert ua.shape == ub.shape and np.allclose(ua, ub, rtol=1e-5, atol=2e-6), (n, use_target, compute_Q)
+    assert a._action_calls == b._action_calls
 
 
 def test_device_side_exploration_noise_against_oracle():
@@ -501,11 +547,13 @@ def test_cuda_graph_path_equals_eager_path(task_replay, schedule):
     assert np.array_equal(g.get_flat('Q', True), e.get_flat('Q', True))
 
 
-@pytest.mark.parametrize('batch_size', [1024, 4096])
+@pytest.mark.parametrize('batch_size', [512, 1024, 1280, 2560, 4096, 4864])
 def test_large_batch_tensor_core_update_against_oracle(batch_size):
-    """BASELINE config 5 batch sweep: at batch >= 1024 the hidden-layer GEMMs of cur_ddpg_grads run on tcgen05
-    (3xTF32, csrc/tc_gemm.cu).  Same tolerances as the batch-256 path versus the oracle, and the tensor-core
-    gradients must agree with the FFMA path of the same library on the same batch."""
+    """BASELINE configs 4 / 5 (19 workers x 256 = 4864 rows; batch sweep): at large batch the update runs on tcgen05
+    (3xTF32) - by default as the fused chain kernel (csrc/tc_chain.cu: forward, losses and dX chains of a 128-row tile in
+    one CTA) followed by split-K weight-gradient GEMMs, alternatively level by level (csrc/tc_gemm.cu).  Same tolerances
+    as the batch-256 path versus the oracle for both, and both must agree with the FFMA path of the same library on the
+    same batch."""
     import ctypes as C
     from curious_b200 import _lib
     kw, dims, ag_ids, g_ids = ddpg_kwargs(4, batch_size=batch_size)
@@ -518,6 +566,7 @@ def test_large_batch_tensor_core_update_against_oracle(batch_size):
     np.random.seed(7)
     _fill(gpu, episodes, cp)
     lib = _lib.load()
+    modes = [('chain', 1, 1), ('levels', 1, 0), ('ffma', 0, 0)] if batch_size % 128 == 0 else [('ffma', 0, 0)]
     try:
         for step in range(2):
             np.random.seed(300 + step)
@@ -528,22 +577,26 @@ def test_large_batch_tensor_core_update_against_oracle(batch_size):
                 assert np.array_equal(x, np.asarray(y, np.float64)), key
             ref = ora.grads(ob)
             got = {}
-            for mode in (1, 0):
-                _lib.check(lib.cur_ddpg_set_tensor_cores(mode), 'cur_ddpg_set_tensor_cores')
-                assert lib.cur_ddpg_uses_tensor_cores(C.byref(gpu.net.desc), batch_size) == mode
+            for name, tc, chain in modes:
+                _lib.check(lib.cur_ddpg_set_tensor_cores(tc), 'cur_ddpg_set_tensor_cores')
+                _lib.check(lib.cur_ddpg_set_chain(chain), 'cur_ddpg_set_chain')
+                assert lib.cur_ddpg_uses_tensor_cores(C.byref(gpu.net.desc), batch_size) == tc
+                assert lib.cur_ddpg_uses_chain(C.byref(gpu.net.desc), batch_size) == chain
+                gpu.grads.zero_()
                 gpu.stage_batch(gb)
                 ql, qpi, gq, gp = gpu._grads()
-                got[mode] = (float(ql), float(gpu._pi_loss), qpi.cpu().numpy().copy(), gq.cpu().numpy().copy(),
+                got[name] = (float(ql), float(gpu._pi_loss), qpi.cpu().numpy().copy(), gq.cpu().numpy().copy(),
                              gp.cpu().numpy().copy())
-            for mode in (1, 0):
-                ql, pl, qpi, gq, gp = got[mode]
-                assert abs(ql - ref['Q_loss']) <= LOSS_RTOL * abs(ref['Q_loss']) + 1e-7, mode
-                assert abs(pl - ref['pi_loss']) <= LOSS_RTOL * abs(ref['pi_loss']) + 1e-7, mode
-                assert rel_err(qpi, ref['Q_pi']) <= 1e-5, mode
-                _check_grad(gq, ref['Q_grad'], ref['relu_margin'], 'Q tc=%d' % mode)        # see the module docstring
-                _check_grad(gp, ref['pi_grad'], ref['relu_margin'], 'pi tc=%d' % mode)
-            _check_grad(got[1][3], got[0][3], ref['relu_margin'], 'Q tc vs ffma')
-            _check_grad(got[1][4], got[0][4], ref['relu_margin'], 'pi tc vs ffma')
+            for name, _, _ in modes:
+                ql, pl, qpi, gq, gp = got[name]
+                assert abs(ql - ref['Q_loss']) <= LOSS_RTOL * abs(ref['Q_loss']) + 1e-7, name
+                assert abs(pl - ref['pi_loss']) <= LOSS_RTOL * abs(ref['pi_loss']) + 1e-7, name
+                assert rel_err(qpi, ref['Q_pi']) <= 1e-5, name
+                _check_grad(gq, ref['Q_grad'], ref['relu_margin'], 'Q %s' % name)        # see the module docstring
+                _check_grad(gp, ref['pi_grad'], ref['relu_margin'], 'pi %s' % name)
+            for name in ('chain', 'levels'):
+                _check_grad(got[name][3], got['ffma'][3], ref['relu_margin'], 'Q %s vs ffma' % name)
+                _check_grad(got[name][4], got['ffma'][4], ref['relu_margin'], 'pi %s vs ffma' % name)
             # step both sides with the ORACLE's gradient (Adam's m / sqrt(v) turns last-bit gradient noise into
             # +-lr parameter differences on the first steps, see the module docstring): bit exact
             import torch
@@ -556,6 +609,7 @@ def test_large_batch_tensor_core_update_against_oracle(batch_size):
             assert np.array_equal(gpu.get_flat('pi'), ora.pi_adam.theta)
     finally:
         lib.cur_ddpg_set_tensor_cores(-1)
+        lib.cur_ddpg_set_chain(-1)
 
 
 @pytest.mark.parametrize('batch_size,use_graph', [(256, True), (256, False), (2048, True)])
