@@ -33,6 +33,7 @@ struct Workspace {
   float *dc[2], *da[2], *dp[2];
   float *dcl[CUR_MAX_LAYERS], *dpl[CUR_MAX_LAYERS];   // chain schedule (tc_chain.cu): one delta buffer per layer
   float* chain_loss;                                   // ... and its per-tile loss partials [n / 128][4]
+  float* chain_wsplit;                                 // ... the parameters of both arenas as 3xTF32 halves (4 x arena)
   uint32_t *chain_mp, *chain_mq, *chain_mqp;           // ... ReLU mask words [layers][8][n] (main.pi, main.Q(u), main.Q(pi))
   // tensor-core path (large batch only): split-K partial tiles / partial row reductions, TC_SLOTS problems per level
   float *tc_part, *tc_rowpart;
@@ -122,9 +123,11 @@ static Workspace carve(const cur_net_desc& d, int64_t n, float* base) {
   for (int l = 0; l < CUR_MAX_LAYERS; ++l) w.dcl[l] = w.dpl[l] = nullptr;
   w.chain_loss = nullptr;
   w.chain_mp = w.chain_mq = w.chain_mqp = nullptr;
+  w.chain_wsplit = nullptr;
   if (tc_chain_supported(d, n)) {
     for (int l = 0; l < d.layers; ++l) { w.dcl[l] = take(n * w.H); w.dpl[l] = take(n * w.H); }
     w.chain_loss = take((n / 128) * 4);
+    w.chain_wsplit = take(4 * (r4(q.total) + r4(p.total)));
     w.chain_mp = reinterpret_cast<uint32_t*>(take((int64_t)d.layers * 8 * n));
     w.chain_mq = reinterpret_cast<uint32_t*>(take((int64_t)d.layers * 8 * n));
     w.chain_mqp = reinterpret_cast<uint32_t*>(take((int64_t)d.layers * 8 * n));
@@ -594,7 +597,7 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
       io.ld_spi = w.ld_spi; io.ld_sq = w.ld_sq; io.ld_g = w.ld_g; io.lddy = (int)r4(d->dimu);
       // (the chain keeps hp / hq / dcl / dpl TRANSPOSED, [256][n]: K-major operands of the weight-gradient GEMMs)
       for (int l = 0; l < L; ++l) { io.hp[l] = w.hp[l]; io.hq[l] = w.hq[l]; io.dc[l] = w.dcl[l]; io.dp[l] = w.dpl[l]; }
-      io.mp = w.chain_mp; io.mq = w.chain_mq; io.mqp = w.chain_mqp;
+      io.mp = w.chain_mp; io.mq = w.chain_mq; io.mqp = w.chain_mqp; io.wsplit = w.chain_wsplit;
       io.Q = w.Q; io.Qt = w.Qt; io.dQ = w.dQ; io.dy = w.dy; io.q_pi = x.q_pi; io.r = x.batch->r;
       io.gamma = x.h->gamma; io.clip_return = x.h->clip_return; io.action_l2 = x.h->action_l2; io.clip_pos = x.h->clip_pos_returns;
       io.loss_part = w.chain_loss; io.q_loss = x.q_loss; io.pi_loss = x.pi_loss;
@@ -605,14 +608,14 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
     // dW = X^T dY with both operands K-major (K = batch): A = hT [256][n], B = dT [256][n]; first layers: A = X [n][in]
     auto dw_t = [&](const float* XT, int m_rows, const float* DT, float* dW) {
       GemmProb p = zero_prob();
-      p.A = XT; p.lda = (int)n; p.a_trans = 0; p.K = (int)n; p.split_k = 1;
+      p.A = XT; p.lda = (int)n; p.a_trans = 0; p.K = (int)n; p.split_k = 2;
       p.B = DT; p.ldb = (int)n; p.b_trans = 1;
       p.C = dW; p.ldc = H; p.M = m_rows; p.N = H;
       return p;
     };
     auto dw_x = [&](const float* X, int ldx, int n_in, const float* DT, float* dW) {
       GemmProb p = zero_prob();
-      p.A = X; p.lda = ldx; p.a_trans = 1; p.K = (int)n;
+      p.A = X; p.lda = ldx; p.a_trans = 1; p.K = (int)n; p.split_k = 2;
       p.B = DT; p.ldb = (int)n; p.b_trans = 1;
       p.C = dW; p.ldc = H; p.M = n_in; p.N = H;
       return p;
@@ -645,10 +648,11 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
       ADD(dw_x(w.Xpi, w.ld_spi, LP.in_s, w.dpl[0], x.gP + LP.off_W0));
       rowsum(w.dpl[0], H, nullptr, 0, 1, x.gP + LP.off_b0);
       if (LP.in_g > 0) ADD(dw_x(w.Xg, w.ld_g, LP.in_g, w.dpl[0], x.gP + LP.off_W0g));
+      CUR_TRY(tc_chain_rowsums(s, RS));             // side stream: next to the GEMM launch below
       CUR_TRY(B.flush());
-      CUR_TRY(tc_chain_rowsums(s, RS));
     }
     CUR_TRY(B.B.T.finish(s));
+    CUR_TRY(tc_chain_join(s));
     return CUR_OK;
   }
   // ---- fwd-1: main.pi | target.pi | main.Q(o,g,u)

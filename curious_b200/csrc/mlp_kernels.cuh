@@ -37,7 +37,8 @@ struct GemmProb {
   const float* aux; int ldaux; // RELU_MASK: activation whose sign gates the gradient; ACTOR_DY: tanh output
   int M, N, K, K2;
   int a_trans, b_trans, ones_a;
-  int split_k;                 // tensor-core path: split K over CTAs although A is not transposed (K = batch, K-major operands)
+  int split_k;                 // tensor-core path: split K over CTAs although A is not transposed (K = batch, K-major
+                               // operands); 2: coarse splits (512 rows above batch 2048), see tc_pick_splits
   int accumulate;              // weight-gradient launch of the rows schedule: C += result (micro-batch j > 0)
   int epi;
   float scale2, coef;

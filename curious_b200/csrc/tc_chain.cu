@@ -12,24 +12,25 @@
 // Why: rows of the batch are independent until dW (the insight behind the rows schedule, ddpg_rows.cu), but that
 // schedule re-streams all weights per 4 rows (cost grows linearly with the rows), and the dependency-level schedule
 // (ddpg.cu) pays ~16 us of launch / prologue / epilogue / global round trip per level x 17 levels.  Here a CTA owns 128
-// rows and one chain; per layer it streams the 256 KB weight matrix ONCE (TMA, 32-k blocks, 2-stage ring), splits it in
-// shared memory for 3xTF32 (x = hi + lo; hi*hi + lo*hi + hi*lo, tc_ptx.cuh), and issues tcgen05.mma M=128 N=256 K=8 into
-// a TMEM accumulator; the NEXT layer's A operand is produced straight from that accumulator: four "feeder" warps (one
-// per TMEM lane quarter, thread = batch row) read 32 accumulator columns with tcgen05.ld, apply bias / ReLU (forward)
-// or the ReLU mask (backward), keep the copy the weight-gradient GEMMs need - TRANSPOSED, [256 units][n rows], so that a
-// warp (32 consecutive rows) writes one full 128-byte line per unit instead of 32 partial lines (measured: the
-// row-major 16-byte-per-lane stores cost ~1 k cycles of L1 transactions per chunk) - and the ReLU masks as one 32-bit
-// word per row and chunk, split the
-// values into hi / lo and write them as the next k-block of the A operand in the K-major 128-byte-swizzled layout the
-// MMA descriptors expect.  Layer l + 1 accumulates into the other half of TMEM (2 x 256 columns, ping-pong) while
-// layer l's accumulator is being drained chunk by chunk, so feeder, splitter, TMA and tensor pipe overlap across
-// the layer boundary.  Output layers (N = 1 / dimu), tanh, the TD / actor losses and the backward seeds are per-row
-// dot products inside the feeder threads.
+// rows and one chain.  Per layer it streams the weight matrix ONCE as ready-made 3xTF32 halves (x = hi + lo, split once
+// per update by tc_chain_presplit_kernel: 2 x 32 KB per 32-k block through a 2-stage TMA ring - a first version split the
+// raw tile in shared memory with four warps and sat at the 128 B/clk shared-memory limit, 304 KB of traffic per
+// k-block) and issues tcgen05.mma M=128 N=256 K=8 (hi*hi + lo*hi + hi*lo) into a TMEM accumulator; the NEXT layer's A
+// operand is produced straight from that accumulator: eight "feeder" warps (two per TMEM lane quarter taking alternate
+// 32-column chunks, thread = batch row) read the accumulator with tcgen05.ld, apply bias / ReLU (forward) or the ReLU
+// mask (backward), keep the copy the weight-gradient GEMMs need - TRANSPOSED, [256 units][n rows], so that a warp
+// (32 consecutive rows) writes one full 128-byte line per unit instead of 32 partial lines (measured: row-major
+// 16-byte-per-lane stores cost ~1 k cycles of L1 transactions per chunk) - and the ReLU masks as one 32-bit word per row
+// and chunk, split the values into hi / lo and write them as the next k-block of the A operand in the K-major
+// 128-byte-swizzled layout the MMA descriptors expect.  Layer l + 1 accumulates into the other half of TMEM (2 x 256
+// columns, ping-pong) while layer l's accumulator is being drained chunk by chunk, so feeders, TMA and tensor pipe
+// overlap across the layer boundary.  Output layers (N = 1 / dimu), tanh, the TD / actor losses and the backward seeds
+// are per-row dot products inside the feeder threads (partial over the chunks of a warp pair, combined through 2 KB of
+// shared memory in fixed order).
 //
 //   warp 0      TMA producer (weights, the B operand): cp.async.bulk.tensor.2d into the B ring, mbarrier complete_tx
 //   warp 1      MMA issuer (one lane), owns the TMEM allocation; tcgen05.commit frees A / B stages, publishes accumulators
-//   warps 2-5   B splitters: raw fp32 tile -> hi (in place) | lo, fence.proxy.async
-//   warps 6-9   feeders (A operand + everything row-wise), see above
+//   warps 2-9   feeders (A operand + everything row-wise), see above
 //
 // Even CTAs run the actor chain (main.pi -> main.Q(o,g,pi) -> actor loss -> backward through main.Q and main.pi), odd
 // CTAs the critic chain (target.pi -> target.Q -> main.Q(o,g,u) -> TD loss -> backward through main.Q); nothing is
@@ -49,17 +50,18 @@ constexpr int CH_BM = 128, CH_BN = 256, CH_BK = 32;
 constexpr int CH_A_HALF = CH_BM * CH_BK * 4;              // 16 KB: one k-block of the A operand (hi or lo)
 constexpr int CH_B_HALF = CH_BN * CH_BK * 4;              // 32 KB
 constexpr int CH_A_STAGE = 2 * CH_A_HALF;                 // hi | lo
-constexpr int CH_B_STAGE = 2 * CH_B_HALF;                 // hi | lo (the raw tile lands in the hi slot)
-constexpr int CH_NA = 3, CH_NB = 2;                       // ring depths: 96 KB + 128 KB
+constexpr int CH_B_STAGE = 2 * CH_B_HALF;                 // hi | lo
+constexpr int CH_NA = 2, CH_NB = 2;                       // ring depths: 64 KB + 128 KB (A: one stage per feeder parity)
 constexpr int CH_MNBLK = 32 * 128;                        // bytes of one 32-wide N block of an MN-major weight tile
-constexpr int CH_WARP_SPLIT0 = 2, CH_SPLIT_WARPS = 4, CH_WARP_FEED0 = 6, CH_FEED_WARPS = 4;
+constexpr int CH_WARP_FEED0 = 2, CH_FEED_WARPS = 8;
 constexpr int CH_THREADS = (CH_WARP_FEED0 + CH_FEED_WARPS) * 32;     // 320
 constexpr size_t CH_SMEM_BYTES = (size_t)CH_NA * CH_A_STAGE + (size_t)CH_NB * CH_B_STAGE + 1024 /* alignment */ + 256;
-constexpr int CH_MAX_GEMM = 16, CH_MAX_MAPS = 20;
+constexpr int CH_MAX_GEMM = 16, CH_MAX_MAPS = 40;         // (hi, lo) map pairs
 constexpr int CH_NCH = CH_BN / 32;                        // 32-column chunks of a layer output
+constexpr int CH_VEC_FLOATS = 3 * 4 * CH_BN + 2 * 4 * CH_BN + 2 * CH_BN;   // 3 nets x <= 4 biases, 2 x [256][4], 2 x [256]
 
 struct ChGemm {
-  int map1, nkb1, map2, nkb2;     // weight tensor maps of the (up to two) K segments and their k-block counts
+  int map1, nkb1, map2, nkb2;     // weight tensor maps (hi; lo = + 1) of the (up to two) K segments, their k-block counts
   int b_mn;                       // 1: weights stored [K][N] (forward), 0: stored [N][K] (dX = dY W^T)
 };
 struct ChProg {
@@ -73,8 +75,7 @@ struct __align__(64) ChainParams {
   cur_net_desc d;
   int L, in_sp, in_sq, in_g, ld_spi, ld_sq, ld_g, lddy;
   int64_t n, grad_rows;
-  const float *Xpi, *Xg, *XQu, *Xpi_t, *Xg_t;
-  float *XQpi, *XQ_t;
+  const float *Xpi, *Xg, *XQu, *XQpi, *Xpi_t, *Xg_t, *XQ_t;
   const float *bP[CUR_MAX_LAYERS], *bPT[CUR_MAX_LAYERS], *bQ[CUR_MAX_LAYERS], *bQT[CUR_MAX_LAYERS];
   const float *WoutP, *boutP, *WoutPT, *boutPT, *WoutQ, *boutQ, *WoutQT, *boutQT;
   const float* W0Q_act;           // main.Q first-layer rows of the action inputs: [dimu][256]
@@ -88,22 +89,24 @@ struct __align__(64) ChainParams {
   int clip_pos;
   float* loss_part;               // [tiles][4]: ssq (critic), sum Q_pi, sum th^2 (actor)
   long long* tl;                  // debug timeline (clock64 stamps of CTA 0 / 1), normally NULL
-  int dbg;                        // measurement switches (CUR_CHAIN_DBG): 1 no row-major copies, 2 no mask loads
+  int dbg;                        // measurement switches (CUR_CHAIN_DBG): 1 no transposed copies, 2 masks all ones
 };
 
 // ---------------------------------------------------------------------------------------------------- feeder
 struct Feeder {
   uint8_t* a_gen;                 // generic address of the A ring
+  float (*s_x)[4];                // [128][4] exchange buffer of the warp pairs
   uint32_t a_full, a_empty, acc_full;
   uint32_t tmem_lane;             // TMEM address of this thread's lane, column 0
-  int lane, r;                    // lane in warp, row in tile
+  int lane, r, par;               // lane in warp, row in tile, parity of the k-blocks / chunks this warp takes
   int64_t row;                    // batch row
-  int a_cnt;                      // A stages produced so far
+  int a_cnt;                      // k-blocks of the A operand so far (both parities count all of them)
   long long* tl;                  // debug stamps (first feeder warp, lane 0) or NULL
   int dbg;
-  int n_stamp;                    // debug: extra feeder stamps tl[400 ...]
+  int n_stamp;
   __device__ __forceinline__ void stamp() { if (tl && n_stamp < 100) tl[400 + n_stamp++] = clock64(); }
 
+  __device__ __forceinline__ bool mine() const { return (a_cnt & 1) == par; }
   __device__ __forceinline__ void wait_acc(int g) const {
     tc_bar_wait(acc_full + 8 * (g & 1), (uint32_t)(g >> 1) & 1u);
     tc_fence_after();
@@ -116,7 +119,7 @@ struct Feeder {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(x[i]);
   }
-  // the next k-block of the A operand: this thread's row of 32 values, split, K-major SWIZZLE_128B
+  // the next k-block of the A operand (it must be `mine()`): this thread's row of 32 values, split, K-major SWIZZLE_128B
   __device__ __forceinline__ void push_A(const float (&v)[32]) {
     const int s = a_cnt % CH_NA, round = a_cnt / CH_NA;
     if (round > 0) tc_bar_wait(a_empty + 8 * s, (uint32_t)(round - 1) & 1u);
@@ -137,8 +140,33 @@ struct Feeder {
     if (lane == 0) tc_bar_arrive(a_full + 8 * s);
     ++a_cnt;
   }
+  // Partial per-row sums of the two warps of a lane quarter -> the same total in both (fixed order: parity 0 + parity 1)
+  template <int NJ>
+  __device__ __forceinline__ void combine(float (&out)[NJ]) const {
+    if (par == 1) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) s_x[r][j] = out[j];
+    }
+    asm volatile("bar.sync 3, 256;" ::: "memory");
+    if (par == 0) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { out[j] += s_x[r][j]; s_x[r][j] = out[j]; }
+    }
+    asm volatile("bar.sync 3, 256;" ::: "memory");
+    if (par == 1) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) out[j] = s_x[r][j];
+    }
+  }
 };
 
+__device__ __forceinline__ void ch_load32(const float* src, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 x = *reinterpret_cast<const float4*>(src + 4 * q);
+    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+  }
+}
 // transposed copy: unit 32 c + i of this thread's row -> T[(32 c + i) * n + row]; the 32 lanes of a warp write one line
 __device__ __forceinline__ void ch_store_t(float* T, int64_t n, int64_t row, int c, const float (&v)[32]) {
   float* dst = T + (int64_t)(32 * c) * n + row;
@@ -151,24 +179,14 @@ __device__ __forceinline__ uint32_t ch_mask_word(const float (&v)[32]) {
   for (int i = 0; i < 32; ++i) w |= (v[i] > 0.f ? 1u : 0u) << i;
   return w;
 }
-// the small per-layer vectors (bias, output-layer weights) of the NEXT chunk into L1 while this chunk is processed
-__device__ __forceinline__ void ch_prefetch(const float* p, int lines, int lane) {
-  if (lane < lines) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32 * lane));
-}
-__device__ __forceinline__ void ch_load32(const float* src, float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 x = *reinterpret_cast<const float4*>(src + 4 * q);
-    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-  }
-}
-
-// A operand of a first layer: k-blocks of the thread's row of a prepared input matrix X [n][ld] (columns >= kcols are 0)
-__device__ __forceinline__ void ch_feed_x(Feeder& F, const float* X, int ld, int kcols) {
+// A operand of a first layer: k-blocks of the thread's row of a prepared input matrix X [n][ld] (columns >= kcols are 0);
+// columns [a0, a0 + na) are taken from `act` (the tanh output of the policy net just evaluated) instead
+__device__ __forceinline__ void ch_feed_x(Feeder& F, const float* X, int ld, int kcols, int a0, int na, const float (&act)[4]) {
   const int nkb = (kcols + CH_BK - 1) / CH_BK;
   const float* xr = X + F.row * ld;
 #pragma unroll 1
   for (int kb = 0; kb < nkb; ++kb) {
+    if (!F.mine()) { ++F.a_cnt; continue; }
     float v[32];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -178,19 +196,25 @@ __device__ __forceinline__ void ch_feed_x(Feeder& F, const float* X, int ld, int
       v[4 * q] = k < kcols ? x.x : 0.f; v[4 * q + 1] = k + 1 < kcols ? x.y : 0.f;
       v[4 * q + 2] = k + 2 < kcols ? x.z : 0.f; v[4 * q + 3] = k + 3 < kcols ? x.w : 0.f;
     }
+    if (na > 0 && a0 < (kb + 1) * CH_BK && a0 + na > kb * CH_BK) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < na && kb * CH_BK + i == a0 + j) v[i] = act[j];
+    }
     F.push_A(v);
   }
 }
 
 // Forward hidden layer boundary: h = relu(acc(g) + bias) -> mask word, optional transposed copy -> A operand of the next GEMM
-__device__ __forceinline__ void ch_feed_relu(Feeder& F, int g, const float* __restrict__ bias, float* HT, uint32_t* mask,
+__device__ __forceinline__ void ch_feed_relu(Feeder& F, int g, const float* bias, float* HT, uint32_t* mask,
                                              int64_t n) {
-  ch_prefetch(bias, 1, F.lane);
   F.wait_acc(g);
 #pragma unroll 1
   for (int c = 0; c < CH_NCH; ++c) {
+    if (!F.mine()) { ++F.a_cnt; continue; }
     float v[32], b[32];
-    if (c + 1 < CH_NCH) ch_prefetch(bias + 32 * (c + 1), 1, F.lane);
     ch_load32(bias + 32 * c, b);
     F.ld_chunk(g, c, v);
 #pragma unroll
@@ -202,25 +226,16 @@ __device__ __forceinline__ void ch_feed_relu(Feeder& F, int g, const float* __re
 }
 
 // Output layer on the last hidden activation: h = relu(acc(g) + bias) (mask word, optional transposed copy),
-// out[j] = sum_c h[c] Wout[c][j]
+// out[j] = sum_c h[c] Wout[c][j] (the chunks of this warp's parity, then combined over the warp pair)
 template <int NJMAX>
-__device__ __forceinline__ void ch_out_layer(Feeder& F, int g, const float* __restrict__ bias, float* HT, uint32_t* mask,
-                                             int64_t n, const float* __restrict__ Wout, int nj, float (&out)[NJMAX]) {
+__device__ __forceinline__ void ch_out_layer(Feeder& F, int g, const float* bias, float* HT, uint32_t* mask,
+                                             int64_t n, const float* Wout, int nj, float (&out)[NJMAX]) {
 #pragma unroll
   for (int j = 0; j < NJMAX; ++j) out[j] = 0.f;
-  ch_prefetch(bias, 1, F.lane);
-  ch_prefetch(Wout, nj, F.lane);
-  F.stamp();
   F.wait_acc(g);
-  F.stamp();
 #pragma unroll 1
-  for (int c = 0; c < CH_NCH; ++c) {
+  for (int c = F.par; c < CH_NCH; c += 2) {
     float v[32], b[32];
-    if (c == 1 || c == 7) F.stamp();
-    if (c + 1 < CH_NCH) {
-      ch_prefetch(bias + 32 * (c + 1), 1, F.lane);
-      ch_prefetch(Wout + 32 * (c + 1) * nj, nj, F.lane);
-    }
     ch_load32(bias + 32 * c, b);
     F.ld_chunk(g, c, v);
 #pragma unroll
@@ -236,7 +251,7 @@ __device__ __forceinline__ void ch_out_layer(Feeder& F, int g, const float* __re
       // one broadcast 16-byte load per hidden unit: Wout[c][0..3]
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(Wout) + 32 * c + i);
+        const float4 w = *(reinterpret_cast<const float4*>(Wout) + 32 * c + i);
         out[0] = fmaf(v[i], w.x, out[0]); out[1] = fmaf(v[i], w.y, out[1]);
         out[2] = fmaf(v[i], w.z, out[2]); out[3] = fmaf(v[i], w.w, out[3]);
       }
@@ -245,22 +260,21 @@ __device__ __forceinline__ void ch_out_layer(Feeder& F, int g, const float* __re
       for (int i = 0; i < 32; ++i)
 #pragma unroll
         for (int j = 0; j < NJMAX; ++j)
-          if (j < nj) out[j] = fmaf(v[i], __ldg(Wout + (32 * c + i) * nj + j), out[j]);
+          if (j < nj) out[j] = fmaf(v[i], Wout[(32 * c + i) * nj + j], out[j]);
     }
   }
-  F.stamp();
+  F.combine<NJMAX>(out);
 }
 
 // Backward seed through an output layer: d[c] = (sum_j dout[j] Wout[c][j]) where the mask word says the unit is active
 // -> optional transposed copy -> A
 template <int NJMAX>
-__device__ __forceinline__ void ch_seed(Feeder& F, const float (&dout)[NJMAX], int nj, const float* __restrict__ Wout,
+__device__ __forceinline__ void ch_seed(Feeder& F, const float (&dout)[NJMAX], int nj, const float* Wout,
                                         const uint32_t* mask, float* DT, int64_t n) {
-  ch_prefetch(Wout, nj, F.lane);
 #pragma unroll 1
   for (int c = 0; c < CH_NCH; ++c) {
+    if (!F.mine()) { ++F.a_cnt; continue; }
     float v[32];
-    if (c + 1 < CH_NCH) ch_prefetch(Wout + 32 * (c + 1) * nj, nj, F.lane);
     const uint32_t mw = (F.dbg & 2) ? 0xFFFFFFFFu : mask[(int64_t)c * n + F.row];
     if (NJMAX == 1) {
       float w[32];
@@ -270,7 +284,7 @@ __device__ __forceinline__ void ch_seed(Feeder& F, const float (&dout)[NJMAX], i
     } else if (nj == 4) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(Wout) + 32 * c + i);
+        const float4 w = *(reinterpret_cast<const float4*>(Wout) + 32 * c + i);
         const float s = fmaf(dout[3], w.w, fmaf(dout[2], w.z, fmaf(dout[1], w.y, dout[0] * w.x)));
         v[i] = ((mw >> i) & 1u) ? s : 0.f;
       }
@@ -280,7 +294,7 @@ __device__ __forceinline__ void ch_seed(Feeder& F, const float (&dout)[NJMAX], i
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < NJMAX; ++j)
-          if (j < nj) s = fmaf(dout[j], __ldg(Wout + (32 * c + i) * nj + j), s);
+          if (j < nj) s = fmaf(dout[j], Wout[(32 * c + i) * nj + j], s);
         v[i] = ((mw >> i) & 1u) ? s : 0.f;
       }
     }
@@ -295,6 +309,10 @@ __device__ __forceinline__ void ch_feed_mask(Feeder& F, int g, const uint32_t* m
   F.wait_acc(g);
 #pragma unroll 1
   for (int c = 0; c < CH_NCH; ++c) {
+    if (push ? !F.mine() : ((c & 1) != F.par)) {
+      if (push) ++F.a_cnt;
+      continue;
+    }
     float v[32];
     const uint32_t mw = (F.dbg & 2) ? 0xFFFFFFFFu : mask[(int64_t)c * n + F.row];
     F.ld_chunk(g, c, v);
@@ -305,8 +323,8 @@ __device__ __forceinline__ void ch_feed_mask(Feeder& F, int g, const uint32_t* m
   }
 }
 
-// sum over the 128 feeder threads in fixed order (warp shuffle tree, then the 4 warps in order); result in thread 0 of
-// the feeder group
+// sum over the 128 rows of the tile in fixed order (warp shuffle tree, then the 4 warps of parity 0 in order); called by
+// the parity-0 feeder warps only
 __device__ __forceinline__ float ch_tile_sum(float x, float* s_red, int fw, int lane) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -320,6 +338,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
   extern __shared__ uint8_t ch_smem_raw[];
   __shared__ uint32_t s_tmem;
   __shared__ float s_red[4];
+  __shared__ float s_x[CH_BM][4];
+  __shared__ __align__(16) float s_vec[CH_VEC_FLOATS];   // biases / output-layer weights of this chain (see `stage`)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int role = blockIdx.x & 1;                      // 0: actor chain, 1: critic chain
   const int tile = blockIdx.x >> 1;
@@ -331,16 +351,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
   uint8_t* gen_base = ch_smem_raw + (base - tc_smem(ch_smem_raw));
   const uint32_t a_ring = base, b_ring = base + CH_NA * CH_A_STAGE;
   const uint32_t bars = b_ring + CH_NB * CH_B_STAGE;
-  const uint32_t a_full = bars, a_empty = bars + 8 * CH_NA, b_full = bars + 16 * CH_NA, b_split = b_full + 8 * CH_NB,
-                 b_empty = b_full + 16 * CH_NB, acc_full = b_full + 24 * CH_NB;
+  const uint32_t a_full = bars, a_empty = bars + 8 * CH_NA, b_full = bars + 16 * CH_NA, b_empty = b_full + 8 * CH_NB,
+                 acc_full = b_full + 16 * CH_NB;
   long long* tl = (P.tl != nullptr && tile == 0 && lane == 0) ? P.tl + 512 * role : nullptr;   // [role][512] stamps
   if (tl && warp == 0) tl[0] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < CH_NA; ++s) { tc_bar_init(a_full + 8 * s, CH_FEED_WARPS); tc_bar_init(a_empty + 8 * s, 1); }
-    for (int s = 0; s < CH_NB; ++s) {
-      tc_bar_init(b_full + 8 * s, 1); tc_bar_init(b_split + 8 * s, CH_SPLIT_WARPS); tc_bar_init(b_empty + 8 * s, 1);
-    }
+    for (int s = 0; s < CH_NA; ++s) { tc_bar_init(a_full + 8 * s, CH_FEED_WARPS / 2); tc_bar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < CH_NB; ++s) { tc_bar_init(b_full + 8 * s, 1); tc_bar_init(b_empty + 8 * s, 1); }
     tc_bar_init(acc_full, 1); tc_bar_init(acc_full + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -354,7 +372,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
   const uint32_t tmem = s_tmem;
 
   if (warp == 0) {
-    // =============================================================== TMA producer: the weight tiles of every GEMM
+    // =============================================================== TMA producer: the weight tiles (hi, lo) of every GEMM
     if (lane == 0) {
       int cnt = 0;
       for (int g = 0; g < prog.n; ++g) {
@@ -365,14 +383,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
           if (round > 0) tc_bar_wait(b_empty + 8 * s, (uint32_t)(round - 1) & 1u);
           const uint32_t dst = b_ring + s * CH_B_STAGE;
           const bool seg2 = kb >= G.nkb1;
-          const CUtensorMap* m = &P.maps[role][seg2 ? G.map2 : G.map1];
+          const CUtensorMap* mh = &P.maps[role][seg2 ? G.map2 : G.map1];
+          const CUtensorMap* ml = mh + 1;
           const int k0 = (seg2 ? kb - G.nkb1 : kb) * CH_BK;
           if (tl && cnt < 88) tl[288 + cnt] = clock64();
-          tc_bar_expect_tx(b_full + 8 * s, CH_B_HALF);                 // zero-filled out-of-bounds rows count too
+          tc_bar_expect_tx(b_full + 8 * s, CH_B_STAGE);                // zero-filled out-of-bounds rows count too
           if (G.b_mn) {
-            for (int j = 0; j < CH_BN / 32; ++j) tc_tma_2d(dst + j * CH_MNBLK, m, 32 * j, k0, b_full + 8 * s);   // [32 k][32 n]
+            for (int j = 0; j < CH_BN / 32; ++j) {                                                             // [32 k][32 n]
+              tc_tma_2d(dst + j * CH_MNBLK, mh, 32 * j, k0, b_full + 8 * s);
+              tc_tma_2d(dst + CH_B_HALF + j * CH_MNBLK, ml, 32 * j, k0, b_full + 8 * s);
+            }
           } else {
-            tc_tma_2d(dst, m, k0, 0, b_full + 8 * s);                                                          // [256 n][32 k]
+            tc_tma_2d(dst, mh, k0, 0, b_full + 8 * s);                                                         // [256 n][32 k]
+            tc_tma_2d(dst + CH_B_HALF, ml, k0, 0, b_full + 8 * s);
           }
         }
       }
@@ -390,7 +413,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
       const uint32_t acc = tmem + (uint32_t)((g & 1) * CH_BN);
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
         const int sa = cnt % CH_NA, ra = cnt / CH_NA, sb = cnt % CH_NB, rb = cnt / CH_NB;
-        tc_bar_wait(b_split + 8 * sb, (uint32_t)rb & 1u);
+        tc_bar_wait(b_full + 8 * sb, (uint32_t)rb & 1u);
         tc_bar_wait(a_full + 8 * sa, (uint32_t)ra & 1u);
         tc_fence_after();
         if (lane == 0) {
@@ -412,26 +435,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
         __syncwarp();
       }
     }
-  } else if (warp < CH_WARP_FEED0) {
-    // =============================================================== B splitters
-    const int t = threadIdx.x - CH_WARP_SPLIT0 * 32;
-    int total = 0;
-    for (int g = 0; g < prog.n; ++g) total += prog.g[g].nkb1 + prog.g[g].nkb2;
-    for (int cnt = 0; cnt < total; ++cnt) {
-      const int s = cnt % CH_NB, round = cnt / CH_NB;
-      tc_bar_wait(b_full + 8 * s, (uint32_t)round & 1u);
-      float* st = reinterpret_cast<float*>(gen_base + CH_NA * CH_A_STAGE + s * CH_B_STAGE);
-      tc_split_tile(st, CH_B_HALF / 4, CH_B_HALF / 16, t, CH_SPLIT_WARPS * 32, false);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (tl && warp == CH_WARP_SPLIT0 && cnt < 88) tl[192 + cnt] = clock64();
-      if (lane == 0) tc_bar_arrive(b_split + 8 * s);
-    }
   } else {
-    // =============================================================== feeders: thread = batch row
+    // =============================================================== feeders: thread = batch row, two warps per lane quarter
     Feeder F;
-    const int fw = warp - CH_WARP_FEED0, q = warp & 3;               // a warp may only touch TMEM lanes 32 (warp % 4) .. + 31
+    const int q = warp & 3;                               // a warp may only touch TMEM lanes 32 (warp % 4) .. + 31
+    F.par = (warp - CH_WARP_FEED0) >> 2;
+    const int fw = (warp - CH_WARP_FEED0) & 3;            // index among the warps of its parity
     F.a_gen = gen_base;
+    F.s_x = s_x;
     F.a_full = a_full; F.a_empty = a_empty; F.acc_full = acc_full;
     F.lane = lane; F.r = 32 * q + lane;
     F.tmem_lane = tmem + ((uint32_t)(32 * q) << 16);
@@ -441,37 +452,53 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
     F.n_stamp = 0;
     F.tl = (tl && warp == CH_WARP_FEED0) ? tl : nullptr;
     const int64_t row = F.row, n = P.n;
+    const bool lead = F.par == 0;                         // the warp of a pair that writes the per-row results
     const float inv_n = 1.0f / (float)P.grad_rows;
+    const float none[4] = {0.f, 0.f, 0.f, 0.f};
 #define MW(l) ((int64_t)(l) * CH_NCH * n)            /* mask words of layer l */
-    int g = 0;                                                        // index of the GEMM whose A operand is produced next
+    int g = 0;                                            // index of the GEMM whose accumulator is read next
+    // The small vectors every row needs (biases, output-layer weights) go to shared memory once: read from global per
+    // chunk they cost an exposed L2 round trip each (measured 0.6 - 1.5 k cycles per chunk in the output-layer passes).
+    int v_off = 0;
+    const int ft = threadIdx.x - CH_WARP_FEED0 * 32;
+    auto stage = [&](const float* src, int count) -> const float* {
+      float* dst = s_vec + v_off;
+      for (int i = ft; i < count; i += CH_FEED_WARPS * 32) dst[i] = __ldg(src + i);
+      v_off += (count + 3) & ~3;
+      return dst;
+    };
+    const float *sbA[CUR_MAX_LAYERS], *sbB[CUR_MAX_LAYERS], *sbC[CUR_MAX_LAYERS];
     if (role == 0) {
-      // ---------------- actor chain: main.pi
-      ch_feed_x(F, P.Xpi, P.ld_spi, P.in_sp);
-      if (P.in_g > 0) ch_feed_x(F, P.Xg, P.ld_g, P.in_g);
-      for (int l = 1; l < L; ++l, ++g) ch_feed_relu(F, g, P.bP[l - 1], P.hp[l - 1], P.mp + MW(l - 1), n);
+      // ---------------- actor chain: main.pi (the first A operand goes out before anything else: the tensor pipe starts)
+      ch_feed_x(F, P.Xpi, P.ld_spi, P.in_sp, 0, 0, none);
+      if (P.in_g > 0) ch_feed_x(F, P.Xg, P.ld_g, P.in_g, 0, 0, none);
+      for (int l = 0; l < L; ++l) sbA[l] = stage(P.bP[l], CH_BN);
+      const float* sWoutP = stage(P.WoutP, CH_BN * d.dimu);
+      for (int l = 0; l < L; ++l) sbB[l] = stage(P.bQ[l], CH_BN);
+      const float* sWoutQ = stage(P.WoutQ, CH_BN);
+      const float* sW0act = stage(P.W0Q_act, d.dimu * CH_BN);
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      for (int l = 1; l < L; ++l, ++g) ch_feed_relu(F, g, sbA[l - 1], P.hp[l - 1], P.mp + MW(l - 1), n);
       float th[4];
-      ch_out_layer<4>(F, g, P.bP[L - 1], P.hp[L - 1], P.mp + MW(L - 1), n, P.WoutP, d.dimu, th);
+      ch_out_layer<4>(F, g, sbA[L - 1], P.hp[L - 1], P.mp + MW(L - 1), n, sWoutP, d.dimu, th);
       ++g;
       float sth = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         th[j] = j < d.dimu ? tanhf(th[j] + __ldg(P.boutP + j)) : 0.f;       // actor_critic.py:89 (pi / max_u)
-        if (j < d.dimu) {
-          P.XQpi[row * P.ld_sq + P.in_sp + j] = th[j];                      // action columns of main.Q's input
-          sth += th[j] * th[j];
-        }
+        sth += th[j] * th[j];
       }
-      // ---------------- main.Q(o, g, pi)
-      ch_feed_x(F, P.XQpi, P.ld_sq, P.in_sq);
-      if (P.in_g > 0) ch_feed_x(F, P.Xg, P.ld_g, P.in_g);
-      for (int l = 1; l < L; ++l, ++g) ch_feed_relu(F, g, P.bQ[l - 1], nullptr, P.mqp + MW(l - 1), n);
+      // ---------------- main.Q(o, g, pi): the action columns of the input come from `th`
+      ch_feed_x(F, P.XQpi, P.ld_sq, P.in_sq, P.in_sp, d.dimu, th);
+      if (P.in_g > 0) ch_feed_x(F, P.Xg, P.ld_g, P.in_g, 0, 0, none);
+      for (int l = 1; l < L; ++l, ++g) ch_feed_relu(F, g, sbB[l - 1], nullptr, P.mqp + MW(l - 1), n);
       float qv[1];
-      ch_out_layer<1>(F, g, P.bQ[L - 1], nullptr, P.mqp + MW(L - 1), n, P.WoutQ, 1, qv);
+      ch_out_layer<1>(F, g, sbB[L - 1], nullptr, P.mqp + MW(L - 1), n, sWoutQ, 1, qv);
       ++g;
       const float q_pi = qv[0] + __ldg(P.boutQ);
-      P.q_pi[row] = q_pi;
-      // ---------------- actor loss terms (ddpg.py:440-441), per-tile partial sums in fixed order
-      {
+      if (lead) {
+        P.q_pi[row] = q_pi;
+        // ---------------- actor loss terms (ddpg.py:440-441), per-tile partial sums in fixed order
         const float sq = ch_tile_sum(q_pi, s_red, fw, lane);
         const float st = ch_tile_sum(sth, s_red, fw, lane);
         if (fw == 0 && lane == 0) { P.loss_part[4 * tile + 1] = sq; P.loss_part[4 * tile + 2] = st; }
@@ -479,17 +506,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
       // ---------------- backward through main.Q (actor-through-critic chain, data gradients only)
       {
         float dq[1] = {-inv_n};                                            // d(-mean(Q_pi)) / dQ_pi
-        ch_seed<1>(F, dq, 1, P.WoutQ, P.mqp + MW(L - 1), nullptr, n);
+        ch_seed<1>(F, dq, 1, sWoutQ, P.mqp + MW(L - 1), nullptr, n);
       }
       for (int l = L - 1; l >= 2; --l, ++g) ch_feed_mask(F, g, P.mqp + MW(l - 1), nullptr, n, true);
       // gradient wrt the action inputs: d h0 (masked) . W0[action rows]^T, then through tanh and the action penalty
       float dy[4] = {0.f, 0.f, 0.f, 0.f};
       F.wait_acc(g);
 #pragma unroll 1
-      for (int c = 0; c < CH_NCH; ++c) {
+      for (int c = F.par; c < CH_NCH; c += 2) {
         float v[32];
-        if (c + 1 < CH_NCH) ch_prefetch(P.W0Q_act + 32 * (c + 1), 1, lane), ch_prefetch(P.W0Q_act + CH_BN + 32 * (c + 1), 1, lane),
-                            ch_prefetch(P.W0Q_act + 2 * CH_BN + 32 * (c + 1), 1, lane), ch_prefetch(P.W0Q_act + 3 * CH_BN + 32 * (c + 1), 1, lane);
         const uint32_t mw = (F.dbg & 2) ? 0xFFFFFFFFu : P.mqp[(int64_t)c * n + row];
         F.ld_chunk(g, c, v);
 #pragma unroll
@@ -498,65 +523,70 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
         for (int j = 0; j < 4; ++j) {
           if (j < d.dimu) {
             float w[32];
-            ch_load32(P.W0Q_act + j * CH_BN + 32 * c, w);
+            ch_load32(sW0act + j * CH_BN + 32 * c, w);
 #pragma unroll
             for (int i = 0; i < 32; ++i) dy[j] = fmaf(v[i], w[i], dy[j]);
           }
         }
       }
       ++g;
+      F.combine<4>(dy);
       {
         const float coef = P.action_l2 * 2.0f / (float)(P.grad_rows * d.dimu);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           dy[j] = j < d.dimu ? (dy[j] + coef * th[j]) * (1.f - th[j] * th[j]) : 0.f;
-          if (j < P.lddy) P.dy[row * P.lddy + j] = dy[j];
+          if (lead && j < P.lddy) P.dy[row * P.lddy + j] = dy[j];
         }
       }
       // ---------------- backward through main.pi
-      ch_seed<4>(F, dy, d.dimu, P.WoutP, P.mp + MW(L - 1), P.dp[L - 1], n);
+      ch_seed<4>(F, dy, d.dimu, sWoutP, P.mp + MW(L - 1), P.dp[L - 1], n);
       for (int l = L - 1; l >= 1; --l, ++g) ch_feed_mask(F, g, P.mp + MW(l - 1), P.dp[l - 1], n, l >= 2);
     } else {
       // ---------------- critic chain: target.pi
-      ch_feed_x(F, P.Xpi_t, P.ld_spi, P.in_sp);
-      if (P.in_g > 0) ch_feed_x(F, P.Xg_t, P.ld_g, P.in_g);
-      for (int l = 1; l < L; ++l, ++g) ch_feed_relu(F, g, P.bPT[l - 1], nullptr, nullptr, n);
+      ch_feed_x(F, P.Xpi_t, P.ld_spi, P.in_sp, 0, 0, none);
+      if (P.in_g > 0) ch_feed_x(F, P.Xg_t, P.ld_g, P.in_g, 0, 0, none);
+      for (int l = 0; l < L; ++l) sbA[l] = stage(P.bPT[l], CH_BN);
+      const float* sWoutPT = stage(P.WoutPT, CH_BN * d.dimu);
+      for (int l = 0; l < L; ++l) sbB[l] = stage(P.bQT[l], CH_BN);
+      const float* sWoutQT = stage(P.WoutQT, CH_BN);
+      for (int l = 0; l < L; ++l) sbC[l] = stage(P.bQ[l], CH_BN);
+      const float* sWoutQ = stage(P.WoutQ, CH_BN);
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      for (int l = 1; l < L; ++l, ++g) ch_feed_relu(F, g, sbA[l - 1], nullptr, nullptr, n);
       float th[4];
-      ch_out_layer<4>(F, g, P.bPT[L - 1], nullptr, nullptr, n, P.WoutPT, d.dimu, th);
+      ch_out_layer<4>(F, g, sbA[L - 1], nullptr, nullptr, n, sWoutPT, d.dimu, th);
       ++g;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < d.dimu) P.XQ_t[row * P.ld_sq + P.in_sp + j] = tanhf(th[j] + __ldg(P.boutPT + j));
+      for (int j = 0; j < 4; ++j) th[j] = j < d.dimu ? tanhf(th[j] + __ldg(P.boutPT + j)) : 0.f;
       // ---------------- target.Q(o_2, g_2, pi_target) with the same td (ddpg.py:427-431)
-      ch_feed_x(F, P.XQ_t, P.ld_sq, P.in_sq);
-      if (P.in_g > 0) ch_feed_x(F, P.Xg_t, P.ld_g, P.in_g);
-      for (int l = 1; l < L; ++l, ++g) ch_feed_relu(F, g, P.bQT[l - 1], nullptr, nullptr, n);
+      ch_feed_x(F, P.XQ_t, P.ld_sq, P.in_sq, P.in_sp, d.dimu, th);
+      if (P.in_g > 0) ch_feed_x(F, P.Xg_t, P.ld_g, P.in_g, 0, 0, none);
+      for (int l = 1; l < L; ++l, ++g) ch_feed_relu(F, g, sbB[l - 1], nullptr, nullptr, n);
       float qt[1];
-      ch_out_layer<1>(F, g, P.bQT[L - 1], nullptr, nullptr, n, P.WoutQT, 1, qt);
+      ch_out_layer<1>(F, g, sbB[L - 1], nullptr, nullptr, n, sWoutQT, 1, qt);
       ++g;
       const float q_t = qt[0] + __ldg(P.boutQT);
-      P.Qt[row] = q_t;
       // ---------------- main.Q(o, g, u)
-      ch_feed_x(F, P.XQu, P.ld_sq, P.in_sq);
-      if (P.in_g > 0) ch_feed_x(F, P.Xg, P.ld_g, P.in_g);
-      for (int l = 1; l < L; ++l, ++g) ch_feed_relu(F, g, P.bQ[l - 1], P.hq[l - 1], P.mq + MW(l - 1), n);
+      ch_feed_x(F, P.XQu, P.ld_sq, P.in_sq, 0, 0, none);
+      if (P.in_g > 0) ch_feed_x(F, P.Xg, P.ld_g, P.in_g, 0, 0, none);
+      for (int l = 1; l < L; ++l, ++g) ch_feed_relu(F, g, sbC[l - 1], P.hq[l - 1], P.mq + MW(l - 1), n);
       float qv[1];
-      ch_out_layer<1>(F, g, P.bQ[L - 1], P.hq[L - 1], P.mq + MW(L - 1), n, P.WoutQ, 1, qv);
+      ch_out_layer<1>(F, g, sbC[L - 1], P.hq[L - 1], P.mq + MW(L - 1), n, sWoutQ, 1, qv);
       ++g;
       const float q = qv[0] + __ldg(P.boutQ);
-      P.Q[row] = q;
       // ---------------- TD loss (ddpg.py:436-439) and its backward seed
       const float hi_clip = P.clip_pos ? 0.f : INFINITY;
       const float tgt = fminf(fmaxf(P.r[row] + P.gamma * q_t, -P.clip_return), hi_clip);
       const float diff = tgt - q;
       float dq[1] = {-2.0f * inv_n * diff};                                // d mean((tgt - Q)^2) / dQ
-      P.dQ[row] = dq[0];
-      {
+      if (lead) {
+        P.Qt[row] = q_t; P.Q[row] = q; P.dQ[row] = dq[0];
         const float ssq = ch_tile_sum(diff * diff, s_red, fw, lane);
         if (fw == 0 && lane == 0) P.loss_part[4 * tile] = ssq;
       }
       // ---------------- backward through main.Q (critic chain)
-      ch_seed<1>(F, dq, 1, P.WoutQ, P.mq + MW(L - 1), P.dc[L - 1], n);
+      ch_seed<1>(F, dq, 1, sWoutQ, P.mq + MW(L - 1), P.dc[L - 1], n);
       for (int l = L - 1; l >= 1; --l, ++g) ch_feed_mask(F, g, P.mq + MW(l - 1), P.dc[l - 1], n, l >= 2);
     }
 #undef MW
@@ -570,6 +600,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1) tc_chain_kernel(const __grid_co
   }
 }
 
+// Once per update: every parameter of the four nets as the two TF32 halves of 3xTF32 (tc_ptx.cuh: tc_split1), laid out
+// like the parameter arenas themselves: out = [main hi | main lo | target hi | target lo], `arena` floats each
+__global__ void __launch_bounds__(256) tc_chain_presplit_kernel(const float* __restrict__ theta_main,
+                                                                 const float* __restrict__ theta_target, float* __restrict__ out,
+                                                                 int64_t arena4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * arena4) return;
+  const bool tgt = i >= arena4;
+  const int64_t k = tgt ? i - arena4 : i;
+  const float4 x = reinterpret_cast<const float4*>(tgt ? theta_target : theta_main)[k];
+  float4 h, l;
+  tc_split1(x.x, h.x, l.x); tc_split1(x.y, h.y, l.y); tc_split1(x.z, h.z, l.z); tc_split1(x.w, h.w, l.w);
+  float4* o = reinterpret_cast<float4*>(out) + (tgt ? 2 * arena4 : 0);
+  o[k] = h;
+  o[arena4 + k] = l;
+}
+
 // per-tile loss partials -> Q_loss / pi_loss (ring slot of the device step counter), fixed order; bumps the counter
 struct ChainLossParams {
   const float* part;
@@ -580,9 +627,16 @@ struct ChainLossParams {
   int64_t* step_counter;
 };
 __global__ void __launch_bounds__(32) tc_chain_loss_kernel(const __grid_constant__ ChainLossParams P) {
-  if (threadIdx.x != 0) return;
+  // lane l folds tiles l, l + 32, ... in order, then a fixed shuffle tree
   float ssq = 0.f, sq = 0.f, sth = 0.f;
-  for (int t = 0; t < P.tiles; ++t) { ssq += P.part[4 * t]; sq += P.part[4 * t + 1]; sth += P.part[4 * t + 2]; }
+  for (int t = threadIdx.x; t < P.tiles; t += 32) { ssq += P.part[4 * t]; sq += P.part[4 * t + 1]; sth += P.part[4 * t + 2]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    sth += __shfl_xor_sync(0xffffffffu, sth, o);
+  }
+  if (threadIdx.x != 0) return;
   long long slot = 0;
   if (P.step_counter) {
     const long long st = *P.step_counter;
@@ -606,14 +660,22 @@ __global__ void __launch_bounds__(256) tc_chain_rowsum_kernel(const __grid_const
   const int m = blockIdx.x - P.block_begin;
   const float* x = P.XT ? P.XT + (int64_t)m * P.ld : nullptr;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t r = threadIdx.x; r < R.rows; r += 256) {
-    const float xv = x ? x[r] : 1.f;
-    if (P.Y) {
+  if (x != nullptr && P.Y == nullptr) {
+    // plain row sum: 16-byte loads (rows is a multiple of 128, every row of XT starts 16-byte aligned)
+    for (int64_t r = 4 * (int64_t)threadIdx.x; r < R.rows; r += 1024) {
+      const float4 v = *reinterpret_cast<const float4*>(x + r);
+      acc[0] += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    for (int64_t r = threadIdx.x; r < R.rows; r += 256) {
+      const float xv = x ? x[r] : 1.f;
+      if (P.Y) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < P.NJ) acc[j] = fmaf(xv, P.Y[r * P.ldy + j], acc[j]);
-    } else {
-      acc[0] += xv;
+        for (int j = 0; j < 4; ++j)
+          if (j < P.NJ) acc[j] = fmaf(xv, P.Y[r * P.ldy + j], acc[j]);
+      } else {
+        acc[0] += xv;
+      }
     }
   }
 #pragma unroll
@@ -629,12 +691,52 @@ __global__ void __launch_bounds__(256) tc_chain_rowsum_kernel(const __grid_const
   if ((int)threadIdx.x < P.NJ) P.out[(int64_t)m * P.NJ + threadIdx.x] = red[0][threadIdx.x];
 }
 
+// The row sums only depend on the chain kernel's outputs: they run on a side stream next to the weight-gradient GEMMs
+// (fork / join with events - capturable, inside a CUDA graph the two become parallel branches).
+struct ChainSide {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+  bool pending = false;
+};
+static int chain_side(ChainSide** out) {
+  static thread_local ChainSide ss;
+  int dev = 0;
+  CUR_CUDA_TRY(cudaGetDevice(&dev));
+  if (ss.stream == nullptr || ss.device != dev) {
+    CUR_CUDA_TRY(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
+    CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    ss.device = dev;
+    ss.pending = false;
+  }
+  *out = &ss;
+  return CUR_OK;
+}
+
 int tc_chain_rowsums(cudaStream_t s, TcRowSumBatch& R) {
   if (R.n == 0) return CUR_OK;
   int blocks = 0;
   for (int i = 0; i < R.n; ++i) { R.p[i].block_begin = blocks; blocks += R.p[i].M; }
-  tc_chain_rowsum_kernel<<<blocks, 256, 0, s>>>(R);
+  ChainSide* ss = nullptr;
+  CUR_TRY(chain_side(&ss));
+  CUR_CUDA_TRY(cudaEventRecord(ss->fork, s));
+  CUR_CUDA_TRY(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+  tc_chain_rowsum_kernel<<<blocks, 256, 0, ss->stream>>>(R);
   CUR_CHECK_LAUNCH();
+  CUR_CUDA_TRY(cudaEventRecord(ss->join, ss->stream));
+  ss->pending = true;
+  return CUR_OK;
+}
+
+// the caller's stream waits for the row sums launched since the last join
+int tc_chain_join(cudaStream_t s) {
+  ChainSide* ss = nullptr;
+  CUR_TRY(chain_side(&ss));
+  if (ss->pending) {
+    CUR_CUDA_TRY(cudaStreamWaitEvent(s, ss->join, 0));
+    ss->pending = false;
+  }
   return CUR_OK;
 }
 
@@ -662,7 +764,7 @@ int tc_chain_launch(cudaStream_t s, const cur_net_desc& d, const TcChainIO& io) 
   }
   const NetLayout LQ = net_layout(d, 0), LP = net_layout(d, 1);
   const int L = d.layers, H = d.hidden;
-  static thread_local ChainParams P;                      // 9 KB: kept off the stack; rebuilt on every call
+  static thread_local ChainParams P;                      // 12 KB: kept off the stack; rebuilt on every call
   memset(&P.prog, 0, sizeof(P.prog));
   P.d = d; P.L = L;
   P.in_sp = LP.in_s; P.in_sq = LQ.in_s; P.in_g = LQ.in_g;
@@ -689,23 +791,40 @@ int tc_chain_launch(cudaStream_t s, const cur_net_desc& d, const TcChainIO& io) 
   static const int dbg = getenv("CUR_CHAIN_DBG") ? atoi(getenv("CUR_CHAIN_DBG")) : 0;
   P.dbg = dbg;
 
-  // ---- the GEMM programs and their weight tensor maps
+  // ---- the weights as 3xTF32 halves, once per call (the weights change with every update)
+  const int64_t arena = r4(LQ.total) + r4(LP.total);
+  CUR_REQUIRE(io.wsplit != nullptr && io.mP == io.mQ + r4(LQ.total) && io.tP == io.tQ + r4(LQ.total), "parameter arenas expected");
+  {
+    const int64_t arena4 = arena / 4;
+    tc_chain_presplit_kernel<<<(unsigned)((2 * arena4 + 255) / 256), 256, 0, s>>>(io.mQ, io.tQ, io.wsplit, arena4);
+    CUR_CHECK_LAUNCH();
+  }
+  // ---- the GEMM programs and their weight tensor maps (pairs: hi, lo)
   int n_maps[2] = {0, 0};
+  auto map_pair = [&](int role, const float* w, int64_t rows, int box_rows, bool mn) -> int {
+    const bool is_target = (w >= io.tQ && w < io.tQ + arena);
+    const int64_t off = is_target ? w - io.tQ : w - io.mQ;
+    CUR_REQUIRE(off >= 0 && off < arena && n_maps[role] + 2 <= CH_MAX_MAPS, "bad weight block");
+    const float* hi = io.wsplit + (is_target ? 2 * arena : 0) + off;
+    CUR_TRY(tc_make_map(&P.maps[role][n_maps[role]++], hi, rows, H, H, box_rows, mn));
+    CUR_TRY(tc_make_map(&P.maps[role][n_maps[role]++], hi + arena, rows, H, H, box_rows, mn));
+    return CUR_OK;
+  };
   auto fwd_net = [&](int role, const float* th, const NetLayout& NL) -> int {
     ChProg& pr = P.prog[role];
     ChGemm& g0 = pr.g[pr.n++];
     g0.b_mn = 1;
     g0.map1 = n_maps[role]; g0.nkb1 = (NL.in_s + CH_BK - 1) / CH_BK;
-    CUR_TRY(tc_make_map(&P.maps[role][n_maps[role]++], th + NL.off_W0, NL.in_s, H, H, CH_BK, true));
+    CUR_TRY(map_pair(role, th + NL.off_W0, NL.in_s, CH_BK, true));
     g0.map2 = 0; g0.nkb2 = 0;
     if (NL.in_g > 0) {
       g0.map2 = n_maps[role]; g0.nkb2 = (NL.in_g + CH_BK - 1) / CH_BK;
-      CUR_TRY(tc_make_map(&P.maps[role][n_maps[role]++], th + NL.off_W0g, NL.in_g, H, H, CH_BK, true));
+      CUR_TRY(map_pair(role, th + NL.off_W0g, NL.in_g, CH_BK, true));
     }
     for (int l = 1; l < L; ++l) {
       ChGemm& g = pr.g[pr.n++];
       g.b_mn = 1; g.map1 = n_maps[role]; g.nkb1 = H / CH_BK; g.map2 = 0; g.nkb2 = 0;
-      CUR_TRY(tc_make_map(&P.maps[role][n_maps[role]++], th + NL.off_W[l], H, H, H, CH_BK, true));
+      CUR_TRY(map_pair(role, th + NL.off_W[l], H, CH_BK, true));
     }
     return CUR_OK;
   };
@@ -714,15 +833,14 @@ int tc_chain_launch(cudaStream_t s, const cur_net_desc& d, const TcChainIO& io) 
     for (int l = L - 1; l >= 1; --l) {
       ChGemm& g = pr.g[pr.n++];
       g.b_mn = 0; g.map1 = n_maps[role]; g.nkb1 = H / CH_BK; g.map2 = 0; g.nkb2 = 0;
-      CUR_TRY(tc_make_map(&P.maps[role][n_maps[role]++], th + NL.off_W[l], H, H, H, CH_BN, false));
+      CUR_TRY(map_pair(role, th + NL.off_W[l], H, CH_BN, false));
     }
     return CUR_OK;
   };
-  static_assert(3 * 4 + 3 <= CH_MAX_GEMM && 6 + 4 * 3 <= CH_MAX_MAPS, "programs of up to 4 hidden layers fit");
+  static_assert(3 * 4 + 3 <= CH_MAX_GEMM && 2 * (6 + 4 * 3) <= CH_MAX_MAPS, "programs of up to 4 hidden layers fit");
   CUR_TRY(fwd_net(0, mP, LP)); CUR_TRY(fwd_net(0, mQ, LQ)); CUR_TRY(bwd_net(0, mQ, LQ)); CUR_TRY(bwd_net(0, mP, LP));
   CUR_TRY(fwd_net(1, tP, LP)); CUR_TRY(fwd_net(1, tQ, LQ)); CUR_TRY(fwd_net(1, mQ, LQ)); CUR_TRY(bwd_net(1, mQ, LQ));
-  CUR_REQUIRE(n_maps[0] <= CH_MAX_MAPS && n_maps[1] <= CH_MAX_MAPS && P.prog[0].n <= CH_MAX_GEMM && P.prog[1].n <= CH_MAX_GEMM,
-              "chain program too long");
+  CUR_REQUIRE(P.prog[0].n <= CH_MAX_GEMM && P.prog[1].n <= CH_MAX_GEMM, "chain program too long");
 
   const int tiles = (int)(io.n / CH_BM);
   tc_chain_kernel<<<2 * tiles, CH_THREADS, CH_SMEM_BYTES, s>>>(P);
@@ -738,7 +856,7 @@ int tc_chain_launch(cudaStream_t s, const cur_net_desc& d, const TcChainIO& io) 
 }  // namespace cur
 
 // debug: `device_buffer` = 1024 x int64 (clock64 stamps of the first actor / critic CTA: [role][512] = start, end,
-// [8..) MMA issue, [96..) A stage ready, [192..) B stage split, [288..) TMA issue per k-block), or NULL to switch it off
+// [8..) MMA issue, [96..) A stage ready (first feeder warp: its parity only), [288..) TMA issue per k-block), or NULL
 extern "C" int cur_tc_chain_timeline(long long* device_buffer_1024) {
   cur::tc_chain_set_timeline(device_buffer_1024);
   return CUR_OK;

@@ -626,15 +626,19 @@ bool tc_supported(const GemmProb& p) {
   return true;
 }
 
+// rows of K one CTA of a split weight gradient covers: 256 (8 k-blocks, like every other tile of a dependency level), or -
+// split_k == 2, the weight-gradient launch behind the chain kernel, where nothing else shares the launch - 512 above
+// batch 2048: a CTA pays ~8 k cycles of prologue / epilogue around ~2.6 k per k-block, and at batch 4864 the 19 x 12 tiles of
+// the 256-row split need two waves (41 us) where 10 x 12 tiles of 16 k-blocks fit one (25 us)
+static int tc_k_per_split(const GemmProb& p) { return (p.split_k == 2 && p.K > 2048) ? 512 : 256; }
+
 int tc_pick_splits(const GemmProb& p) {
-  // forward / dX problems have M = batch: plenty of tiles.  Weight gradients (M <= 256, K = batch) split K into
-  // chunks of 256 rows: 8 k-blocks per CTA like every other tile of the level (balanced waves), batch / 256 CTAs per
-  // 128 rows of dW, accumulation chains as short as the forward ones
+  // forward / dX problems have M = batch: plenty of tiles.  Weight gradients (M <= 256, K = batch) split K over CTAs;
+  // the last split may be shorter (the TMA unit zero-fills the rows beyond K)
   if (p.M >= 1024 || !(p.a_trans || p.split_k)) return 1;
-  int s = p.K / 256;
-  if (s < 1) s = 1;
-  while (s > 1 && (p.K % (s * TC_BK)) != 0) --s;
-  return s;
+  const int kps = tc_k_per_split(p);
+  const int s = (p.K + kps - 1) / kps;
+  return s < 1 ? 1 : s;
 }
 
 int64_t tc_partial_floats(const GemmProb& p) {
@@ -654,7 +658,7 @@ int TcLauncher::add(const GemmProb& p, float* partial) {
   q.a_mn = p.a_trans ? 1 : 0;          // A stored [K][M]
   q.b_mn = p.b_trans ? 0 : 1;          // B stored [K][N] is N-major; stored [N][K] is K-major
   q.splits = tc_pick_splits(p);
-  q.k_per_split = (q.splits > 1) ? p.K / q.splits : p.K;
+  q.k_per_split = (q.splits > 1) ? tc_k_per_split(p) : p.K;
   q.nkb1 = (q.k_per_split + TC_BK - 1) / TC_BK;       // a K tail is zero-filled by the TMA unit
   q.nkb2 = (p.K2 + TC_BK - 1) / TC_BK;
   q.bias = p.bias; q.aux = p.aux; q.ldaux = p.ldaux; q.epi = p.epi;

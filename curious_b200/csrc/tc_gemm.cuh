@@ -53,7 +53,8 @@ struct TcChainIO {
   int64_t n, grad_rows;
   const float *mQ, *mP, *tQ, *tP;                       // parameter blocks of the four nets
   const float *Xpi, *Xg, *XQu, *Xpi_t, *Xg_t;           // prepared first-layer inputs [n][ld]
-  float *XQpi, *XQ_t;                                   // ... whose action columns the kernel fills
+  const float *XQpi, *XQ_t;                             // ... (action columns: taken from the policy output in the kernel)
+  float* wsplit;                                        // 4 x arena floats: main hi | main lo | target hi | target lo
   int ld_spi, ld_sq, ld_g, lddy;
   // TRANSPOSED copies [256][n] the weight gradients need: activations (main.pi, main.Q(u)), deltas (critic, actor chain)
   float *hp[CUR_MAX_LAYERS], *hq[CUR_MAX_LAYERS], *dc[CUR_MAX_LAYERS], *dp[CUR_MAX_LAYERS];
@@ -78,7 +79,8 @@ struct TcRowSumBatch {
   int n;
   int64_t rows;
 };
-int tc_chain_rowsums(cudaStream_t s, TcRowSumBatch& R);
+int tc_chain_rowsums(cudaStream_t s, TcRowSumBatch& R);   // on a side stream forked from `s`
+int tc_chain_join(cudaStream_t s);                        // ... which `s` waits for here
 bool tc_chain_supported(const cur_net_desc& d, int64_t n);
 int tc_chain_launch(cudaStream_t s, const cur_net_desc& d, const TcChainIO& io);
 void tc_chain_set_timeline(long long* dev);             // 128 x int64 debug stamps (CTA 0 / CTA 1) or NULL

@@ -225,9 +225,16 @@ class DDPG(object):
     def _use_rows(self, n):
         if self.update_schedule == 'levels':
             return False
-        ok = bool(_lib.load().cur_ddpg_rows_supported(C.byref(self.net.desc), n))
-        if self.update_schedule == 'rows' and not ok:
-            raise ValueError('update_schedule="rows" does not support this network / batch shape')
+        lib = _lib.load()
+        ok = bool(lib.cur_ddpg_rows_supported(C.byref(self.net.desc), n))
+        if self.update_schedule == 'rows':
+            if not ok:
+                raise ValueError('update_schedule="rows" does not support this network / batch shape')
+            return True
+        # auto: from 1024 rows the fused tcgen05 chain kernel (csrc/tc_chain.cu) is faster than re-streaming the weights per
+        # 4 rows (measured us / update, rows vs chain: 512 110 / 165, 768 160 / 166, 1024 208 / 166)
+        if ok and n >= self.CHAIN_MIN_ROWS and lib.cur_ddpg_uses_chain(C.byref(self.net.desc), n):
+            return False
         return ok
 
     def _workspace_rows(self, n):
@@ -336,6 +343,7 @@ class DDPG(object):
                     raise RuntimeError('cur_ddpg_actions_rows did not complete')
         return slot['val'][:n_out].copy()
 
+    CHAIN_MIN_ROWS = 1024      # update_schedule='auto': rows schedule below, tcgen05 chain kernel from here
     ACTION_ROWS_MAX = 512      # rows per call served by the one-launch path (one CTA per 4 rows)
     ACTION_ZERO_COPY_MAX = 64  # ... of which up to this many rows travel zero-copy (kernel reads / writes host memory)
 

@@ -40,6 +40,5 @@ for role, name in ((0, 'actor'), (1, 'critic')):
         print('   kb %2d: tma %7d split %7d A %7d mma %7d' % (i, p[i] - t0, b[i] - t0, a[i] - t0, mma[i] - t0))
     st = r[400:500]
     st = st[st > 0]
-    print('  out-layer stamps (enter, acc ready, chunk 1, chunk 7, done) relative to start:')
-    for i in range(0, len(st) - 4, 5):
-        print('   ', (st[i:i + 5] - t0).tolist(), ' last MMA issue before: %d' % (mma[:k][mma[:k] < st[i + 1]].max() - t0))
+    print('  out-layer stamps: per chunk (start, acc loaded, relu+mask, stored), then (dot done, combined); deltas:')
+    print('   ', np.diff(st).tolist())
