@@ -132,7 +132,7 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm), 'source': self.source}
 
 
-TRAFFIC_FILE = 'profiles/r01_her_traffic.json'
+TRAFFIC_FILE = 'profiles/r02_her_traffic.json'
 
 
 def her_traffic_per_launch(rows_per_step):
@@ -267,6 +267,20 @@ def time_updates(fn, n, torch):
     return e0.elapsed_time(e1) / n
 
 
+def schedule_name(a, rows):
+    """Which implementation of the update DDPG.train() runs at `rows` rows per launch."""
+    import ctypes as C
+    from curious_b200 import _lib
+    if a._use_rows(rows):
+        return 'rows (FFMA2 row clusters)'
+    lib = _lib.load()
+    if lib.cur_ddpg_uses_chain(C.byref(a.net.desc), rows):
+        return 'chain (tcgen05, fused actor / critic chains + split-K weight gradients)'
+    if lib.cur_ddpg_uses_tensor_cores(C.byref(a.net.desc), rows):
+        return 'levels (tcgen05)'
+    return 'levels (FFMA)'
+
+
 def large_batch_sweep(agent, dims, torch):
     """BASELINE config 5: per-GPU batch sweep of the DDPG update through DDPG.train() (HER sample + grads + Adam in
     one CUDA graph) and structure='task_experts' as grouped launches.  At batch >= 1024 the hidden-layer GEMMs run on
@@ -280,13 +294,13 @@ def large_batch_sweep(agent, dims, torch):
     except Exception:
         bf16 = 2250.0 * 0.745
     sweep = []
-    for b in (256, 512, 1024, 2048, 4096, 16384):
+    for b in (256, 512, 1024, 2048, 4096, 4864, 16384):
         a = agent if b == BATCH else agent.make_agent(batch_size=b)
         ms = time_updates(a.train, 200 if b <= 1024 else 40, torch)
         fl = update_flops(dims, N_MODULES, b)
         tc = bool(_lib.load().cur_ddpg_uses_tensor_cores(C.byref(a.net.desc), b)) and not a._use_rows(b)
         sweep.append({'batch': b, 'update_us': 1e3 * ms, 'updates_per_s': 1e3 / ms, 'transitions_per_s': 1e3 * b / ms,
-                      'tflops': fl / (ms * 1e-3) / 1e12, 'schedule': 'rows' if a._use_rows(b) else 'levels',
+                      'tflops': fl / (ms * 1e-3) / 1e12, 'schedule': schedule_name(a, b),
                       'tensor_cores': tc, 'tensor_frac': (3 * fl / (ms * 1e-3) / 1e12) / (bf16 / 2) if tc else None})
         if b != BATCH:
             del a
@@ -549,7 +563,7 @@ def measure_agent(agent, dims, n_modules, world, rank, barrier, torch, dist, dev
     e1.record()
     barrier()
     upd19_ms = e0.elapsed_time(e1)
-    sched19 = 'rows' if agent19._use_rows(agent19._graph_rows) else 'levels (tcgen05)'
+    sched19 = schedule_name(agent19, agent19._graph_rows)
     exch19 = 'tile' if agent19._xchg is not None else ('p2p' if agent19._peer is not None else ('nccl' if world > 1 else None))
     del agent19
     torch.cuda.empty_cache()
@@ -561,7 +575,7 @@ def measure_agent(agent, dims, n_modules, world, rank, barrier, torch, dist, dev
     upd_ms, cyc_s, upd19_ms, rc_s, ga2, ga38 = vals
     res['update_us'] = 1e3 * upd_ms / n_upd
     res['updates_per_s'] = world * n_upd / (upd_ms * 1e-3)
-    res['update_schedule'] = 'rows' if agent._use_rows(BATCH) else 'levels'
+    res['update_schedule'] = schedule_name(agent, BATCH)
     res['grad_exchange'] = ('tile' if getattr(agent, '_xchg', None) is not None else
                             'p2p' if getattr(agent, '_peer', None) is not None else 'nccl') if world > 1 else None
     if getattr(agent, '_xchg', None) is not None:

@@ -584,7 +584,7 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
   GroupBatcher B(s, use_tc(*d, n), E, n_e);
 #define FOR_EXPERTS for (int i = 0; i < n_e; ++i)
 #define ADD(prob) CUR_TRY(B.add(i, (prob)))
-  if (use_chain(*d, n)) {
+  if (n_e == 1 && use_chain(*d, n)) {            // (several experts: the grouped levels below fill the GPU better)
     // ---- chain schedule (tc_chain.cu): forward nets, losses and the data-gradient chains of a 128-row tile in one
     // CTA per chain, then every weight / bias gradient as split-K tensor-core GEMMs + row reductions, one level per net
     FOR_EXPERTS {
