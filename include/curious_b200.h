@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CUR_ABI_VERSION 2
+#define CUR_ABI_VERSION 3
 
 #define CUR_OK 0
 #define CUR_ERR_INVALID 1   /* bad argument (dims, null pointer, table overflow)   */

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
         assert name in _lib.SIGNATURES, 'ctypes signature missing for ' + name
-    assert lib.cur_abi_version() == 2
+    assert lib.cur_abi_version() == 3
 
 
 def test_ctypes_structs_match_header(tmp_path):
