@@ -615,6 +615,68 @@ def test_large_batch_tensor_core_update_against_oracle(batch_size):
         lib.cur_ddpg_set_chain(-1)
 
 
+@pytest.mark.parametrize('structure,n_modules,layers,normalize_obs,relative_goals',
+                         [('flat', 4, 3, False, False), ('curious', 8, 3, True, False), ('curious', 4, 2, False, True),
+                          ('curious', 4, 4, True, False), ('task_experts', 4, 3, False, False)])
+def test_chain_kernel_network_variants(structure, n_modules, layers, normalize_obs, relative_goals):
+    """The fused chain kernel on every network shape it accepts: the flat nets (one K segment in the first layers), the
+    Arm8 dims (three k-blocks of state input), 2 and 4 hidden layers, normalised inputs, relative goals - losses, Q_pi and
+    both gradients at 1024 rows against the oracle and against the FFMA path of the same library."""
+    import ctypes as C
+    from curious_b200 import _lib
+    task_replay = '' if structure == 'flat' else ('replay_current_task_buffer' if structure == 'task_experts'
+                                                   else 'replay_task_cp_buffer')
+    kw, dims, ag_ids, g_ids = ddpg_kwargs(n_modules, structure=structure, task_replay=task_replay, batch_size=1024,
+                                          layers=layers, normalize_obs=normalize_obs, relative_goals=relative_goals)
+    if structure == 'task_experts':
+        kw['t_id'] = 1
+    cp = np.linspace(0.0, 0.3, n_modules)
+    episodes = episode_stream(dims, kw['T'], 12, flat=structure == 'flat')
+    ora = make_oracle_agent(kw, dims, ag_ids, g_ids)
+    gpu = make_gpu_agent(kw, dims, ag_ids, g_ids, her_rng='numpy', update_schedule='levels')
+    np.random.seed(17)
+    _fill(ora, episodes, cp)
+    np.random.seed(17)
+    _fill(gpu, episodes, cp)
+    if normalize_obs:
+        for a, b in ((gpu.o_stats, ora.o_stats), (gpu.g_stats, ora.g_stats)):
+            a.load_state_list([b.sum, b.sumsq, b.count, b.mean, b.std])
+    lib = _lib.load()
+    try:
+        np.random.seed(400)
+        ob = ora.sample_batch()
+        np.random.seed(400)
+        gb = gpu.sample_batch()
+        for key, x, y in zip(ora.stage_keys, gb, ob):
+            if relative_goals and key in ('g', 'g_2'):        # g - ag: float32 on the device, float64 in the reference
+                assert np.allclose(x, np.asarray(y, np.float64), rtol=0, atol=1e-7), key
+            else:
+                assert np.array_equal(x, np.asarray(y, np.float64)), key
+        ref = ora.grads(ob)
+        got = {}
+        for name, tc, chain in (('chain', 1, 1), ('ffma', 0, 0)):
+            _lib.check(lib.cur_ddpg_set_tensor_cores(tc), 'cur_ddpg_set_tensor_cores')
+            _lib.check(lib.cur_ddpg_set_chain(chain), 'cur_ddpg_set_chain')
+            assert lib.cur_ddpg_uses_chain(C.byref(gpu.net.desc), 1024) == chain
+            gpu.grads.zero_()
+            gpu.stage_batch(gb)
+            ql, qpi, gq, gp = gpu._grads()
+            got[name] = (float(ql), float(gpu._pi_loss), qpi.cpu().numpy().copy(), gq.cpu().numpy().copy(),
+                         gp.cpu().numpy().copy())
+        for name in ('chain', 'ffma'):
+            ql, pl, qpi, gq, gp = got[name]
+            assert abs(ql - ref['Q_loss']) <= LOSS_RTOL * abs(ref['Q_loss']) + 1e-7, name
+            assert abs(pl - ref['pi_loss']) <= LOSS_RTOL * abs(ref['pi_loss']) + 1e-7, name
+            assert rel_err(qpi, ref['Q_pi']) <= 1e-5, name
+            _check_grad(gq, ref['Q_grad'], ref['relu_margin'], 'Q %s' % name, 'large')
+            _check_grad(gp, ref['pi_grad'], ref['relu_margin'], 'pi %s' % name, 'large')
+        _check_grad(got['chain'][3], got['ffma'][3], ref['relu_margin'], 'Q chain vs ffma', 'large')
+        _check_grad(got['chain'][4], got['ffma'][4], ref['relu_margin'], 'pi chain vs ffma', 'large')
+    finally:
+        lib.cur_ddpg_set_tensor_cores(-1)
+        lib.cur_ddpg_set_chain(-1)
+
+
 @pytest.mark.parametrize('batch_size,use_graph', [(256, True), (256, False), (2048, True)])
 def test_task_experts_grouped_update_equals_sequential(batch_size, use_graph):
     """structure='task_experts': TaskExperts.train() steps all experts with grouped launches (one launch per
