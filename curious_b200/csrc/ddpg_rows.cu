@@ -162,6 +162,11 @@ __device__ __forceinline__ void st_ll(unsigned long long* p, float v, uint32_t f
   const unsigned long long w = ((unsigned long long)flag << 32) | (unsigned long long)__float_as_uint(v);
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
+// Programmatic dependent launch: the next kernel of the stream may be scheduled while this one still runs (its CTAs
+// take SMs as they free up and park in pdl_wait); pdl_wait returns once the previous kernel has completed and its
+// writes are visible.  Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(S_CONSUMERS) : "memory"); }
 
 struct Ring {
@@ -461,6 +466,8 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  pdl_launch_dependents();
+  pdl_wait();               // everything below reads what the previous kernel (weight gradients + Adam of the last update) wrote
   __syncthreads();          // barriers initialised before the producer / consumers use them
 
   const SChunk* my_chunks = role == 0 ? P.chunks : P.chunks_t;
@@ -1203,6 +1210,8 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     else if (blockIdx.x == gridDim.x - 1) tl = T.tl + 48;
   }
   if (tl) tl[0] = clock64();
+  pdl_launch_dependents();
+  pdl_wait();                                                    // activations / deltas of the stream kernel, the step counter
   const long long st = T.step_counter ? *T.step_counter : 0;     // value BEFORE this update's bump
   // several workers per rank (19-worker-equivalent batches): the device counter counts micro-batches,
   // update u = st / micro, launch j = st % micro of it adds its gradient to the sum of launches 0..j-1
@@ -1379,6 +1388,22 @@ static void build_dw_batch(GemmBatch& G, const NetLayout& LQ, const NetLayout& L
   };
   net_grads(LQ, gQ, w.Xq, w.hq, w.dc, w.dQ, 1);
   net_grads(LP, gP, w.Xp, w.hp, w.dp, w.dy, w.lddy);
+}
+
+// launch configuration; CUR_PDL=1 adds programmatic stream serialisation (measured: batch 256 60.2 us with, 58.3 us
+// without - the early-scheduled CTAs of the next kernel do not pay for what they displace - so it is off by default)
+static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, unsigned grid, unsigned block, size_t smem,
+                       cudaStream_t s) {
+  static const bool on = getenv("CUR_PDL") != nullptr && getenv("CUR_PDL")[0] == '1';
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = on ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = on ? 1 : 0;
 }
 
 }  // namespace cur
@@ -1560,7 +1585,12 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   P.dbg_skip_math = getenv("CUR_ROWS_SKIP_MATH") != nullptr;
 
   const unsigned int n_ctas = (unsigned int)(n / S_ROWS);
-  ddpg_stream_kernel<<<2 * n_ctas, S_THREADS, S_SMEM_BYTES, s>>>(P);      // (main, target) CTA pairs
+  {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[1];
+    pdl_config(cfg, at, 2 * n_ctas, S_THREADS, S_SMEM_BYTES, s);
+    CUR_CUDA_TRY(cudaLaunchKernelEx(&cfg, ddpg_stream_kernel, P));       // (actor, critic) CTA pairs
+  }
   CUR_CHECK_LAUNCH();
   if (tl_on && ++tl_calls == 40) {          // debug only: one warmed-up timeline of CTA 0
     long long t[64];
@@ -1631,7 +1661,12 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     T.tl_skinny_block = 0;
     for (int i = 0; i < G.n; ++i)
       if (G.p[i].variant == DW_FULLK) { T.tl_skinny_block = G.p[i].tile_begin; break; }
-    rows_dw_kernel<<<tiles, GEMM_THREADS, DW_SMEM_BYTES, s>>>(G, T);
+    {
+      cudaLaunchConfig_t cfg;
+      cudaLaunchAttribute at[1];
+      pdl_config(cfg, at, (unsigned)tiles, GEMM_THREADS, DW_SMEM_BYTES, s);
+      CUR_CUDA_TRY(cudaLaunchKernelEx(&cfg, rows_dw_kernel, G, T));
+    }
     CUR_CHECK_LAUNCH();
   }
   if (tl_on && tl_calls == 40) {
