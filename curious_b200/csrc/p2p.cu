@@ -84,7 +84,11 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(const __grid_co
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(P.region[P.rank]);
     long long spins = 0;
     while (ld_acquire_sys(mine + threadIdx.x) < want) {
-      if (++spins > (1ll << 25)) { s_ok = 0; if (P.error_flag) *P.error_flag = 1; break; }
+      if (++spins > (1ll << 25)) {           // a peer that never shows up: fail the launch (no partial update of theta / m / v)
+        if (P.error_flag) *P.error_flag = 1;
+        __threadfence_system();
+        __trap();
+      }
       __nanosleep(64);
     }
   }
@@ -155,7 +159,11 @@ __device__ __forceinline__ bool wait_flags(const unsigned long long* flags, int 
   if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
     long long spins = 0;
     while (ld_acquire_sys(flags + threadIdx.x) < want) {
-      if (++spins > (1ll << 25)) { s_ok2 = 0; if (error_flag) *error_flag = 1; break; }
+      if (++spins > (1ll << 25)) {
+        if (error_flag) *error_flag = 1;
+        __threadfence_system();
+        __trap();
+      }
       __nanosleep(64);
     }
   }

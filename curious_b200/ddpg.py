@@ -928,6 +928,8 @@ class DDPG(object):
                                           self.theta_main.numel(), 0.0), 'cur_polyak')
 
     def update_target_net(self):
+        if getattr(self, '_peer', None) is not None:
+            self._peer.check()              # (once per cycle: a timed-out exchange must not survive into the target net)
         _lib.check(_lib.load().cur_polyak(_lib.stream_ptr(), self.theta_target.data_ptr(), self.theta_main.data_ptr(),
                                           self.theta_main.numel(), float(self.polyak)), 'cur_polyak')
 

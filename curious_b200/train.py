@@ -247,10 +247,11 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
     (`clear_eval_competence=True` restarts them at every evaluation instead)."""
     history = []
     records = None
+    resumed_run = None
     start_epoch = 0
     workers = rollout_worker if isinstance(rollout_worker, list) else [rollout_worker]
     if logdir is not None:
-        resumed = _EpochRecords.load_run_state(logdir, evaluator.rank) if resume else None
+        resumed = resumed_run = _EpochRecords.load_run_state(logdir, evaluator.rank) if resume else None
         if resumed is not None:
             suffix = '' if evaluator.rank == 0 else '_rank%d' % evaluator.rank
             for i, pol in enumerate(policy if isinstance(policy, list) else [policy]):
@@ -261,7 +262,8 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
             start_epoch = resumed['epoch'] + 1
         records = _EpochRecords(logdir, evaluator, params, policy_save_interval, save_policies, checkpoint_interval, echo,
                                 workers=workers, resumed=resumed)
-    if initial_evaluation and start_epoch == 0:
+    if initial_evaluation and start_epoch == 0 and resumed_run is None:   # (a run resumed from its epoch -1 checkpoint
+        # must not evaluate the untrained policy a second time)
         # train.py:62-75 / 125-135: epoch -1.  The experts' branch also restarts the evaluator's competence queues here and
         # logs the LAST expert's worker and policy (i_policy = -1 indexes the lists from the end)
         evaluator.clear_history()
@@ -316,6 +318,8 @@ def train(policy, rollout_worker, evaluator, n_epochs, n_test_rollouts, n_cycles
                 log(rec)
             if records:
                 records.epoch(epoch, rollout_worker[i_policy], policy, i_policy)
+        if records:
+            records.log.close()
         return history
     for epoch in range(start_epoch, n_epochs):                                            # train.py:125-166
         rollout_worker.clear_history()

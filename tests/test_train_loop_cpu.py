@@ -163,3 +163,33 @@ def test_resumed_run_equals_uninterrupted_run(structure, tmp_path):
     # resume=True without checkpoints starts from scratch
     fresh, _ = run(str(tmp_path / 'empty'), 1, seed=3, resume=True)
     assert [h['epoch'] for h in fresh] == [0]
+
+
+def test_resume_from_the_epoch_minus_one_checkpoint(tmp_path):
+    """With checkpoint_interval=1 the evaluation of the untrained policy (epoch -1, train.py:62-75) is checkpointed too; a run
+    killed right after it and resumed must not evaluate the untrained policy a second time: one epoch -1 row, evaluator
+    queues and all later epochs equal to the uninterrupted run."""
+    def run(logdir, n_epochs, seed, resume=False):
+        np.random.seed(seed)
+        policy, rollout, evaluator, _ = _workers('curious')
+        for i, w in enumerate([rollout, evaluator]):
+            w.seed(70 + 10 * i)
+        return train(policy, rollout, evaluator, n_epochs=n_epochs, n_test_rollouts=2, n_cycles=2, n_batches=2,
+                     structure='curious', logdir=logdir, policy_save_interval=0, checkpoint_interval=1, resume=resume,
+                     initial_evaluation=True)
+
+    full = run(str(tmp_path / 'full'), 2, seed=5)
+    first = run(str(tmp_path / 'split'), 0, seed=5)                       # only the epoch -1 evaluation
+    assert first == []                                                      # (epoch -1 goes to the run records only)
+    tail = run(str(tmp_path / 'split'), 2, seed=77, resume=True)
+    assert [h['epoch'] for h in full] == [0, 1] and [h['epoch'] for h in tail] == [0, 1]
+    for a, b in zip(full, tail):
+        for key in a:
+            assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), key
+
+    def epochs(path):
+        lines = open(path).read().splitlines()
+        e = lines[0].split(',').index('epoch')
+        return [line.split(',')[e] for line in lines[1:]]
+    assert epochs(str(tmp_path / 'split' / 'progress.csv')) == epochs(str(tmp_path / 'full' / 'progress.csv')) == ['-1', '0', '1']
+
