@@ -584,9 +584,10 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
   GroupBatcher B(s, use_tc(*d, n), E, n_e);
 #define FOR_EXPERTS for (int i = 0; i < n_e; ++i)
 #define ADD(prob) CUR_TRY(B.add(i, (prob)))
-  if (n_e == 1 && use_chain(*d, n)) {            // (several experts: the grouped levels below fill the GPU better)
+  if (use_chain(*d, n)) {
     // ---- chain schedule (tc_chain.cu): forward nets, losses and the data-gradient chains of a 128-row tile in one
     // CTA per chain, then every weight / bias gradient as split-K tensor-core GEMMs + row reductions, one level per net
+    if (n_e > 1) CUR_TRY(tc_chain_lanes_fork(s));
     FOR_EXPERTS {
       Expert& x = E[i]; const Workspace& w = x.w;
       TcChainIO io;
@@ -602,8 +603,11 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
       io.gamma = x.h->gamma; io.clip_return = x.h->clip_return; io.action_l2 = x.h->action_l2; io.clip_pos = x.h->clip_pos_returns;
       io.loss_part = w.chain_loss; io.q_loss = x.q_loss; io.pi_loss = x.pi_loss;
       io.step_counter = x.h->step_counter; io.loss_ring = x.h->loss_ring;
-      CUR_TRY(tc_chain_launch(s, *d, io));
+      cudaStream_t cs = s;                         // several experts: independent chains on concurrent streams
+      if (n_e > 1) CUR_TRY(tc_chain_lane(i, &cs));
+      CUR_TRY(tc_chain_launch(cs, *d, io));
     }
+    if (n_e > 1) CUR_TRY(tc_chain_lanes_join(s));
     const int lddy = (int)r4(d->dimu);
     // dW = X^T dY with both operands K-major (K = batch): A = hT [256][n], B = dT [256][n]; first layers: A = X [n][in]
     auto dw_t = [&](const float* XT, int m_rows, const float* DT, float* dW) {
@@ -648,9 +652,9 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
       ADD(dw_x(w.Xpi, w.ld_spi, LP.in_s, w.dpl[0], x.gP + LP.off_W0));
       rowsum(w.dpl[0], H, nullptr, 0, 1, x.gP + LP.off_b0);
       if (LP.in_g > 0) ADD(dw_x(w.Xg, w.ld_g, LP.in_g, w.dpl[0], x.gP + LP.off_W0g));
-      CUR_TRY(tc_chain_rowsums(s, RS));             // side stream: next to the GEMM launch below
-      CUR_TRY(B.flush());
+      CUR_TRY(tc_chain_rowsums(s, RS));             // side stream: next to the GEMM launches
     }
+    CUR_TRY(B.flush());                             // (the batcher also flushes whenever a launch is full)
     CUR_TRY(B.B.T.finish(s));
     CUR_TRY(tc_chain_join(s));
     return CUR_OK;

@@ -714,6 +714,61 @@ static int chain_side(ChainSide** out) {
   return CUR_OK;
 }
 
+// Several agents (task_experts): the chain kernels of different experts are independent and one expert's tiles do not
+// fill the GPU, so expert i launches on lane i % 4; fork once before the first, join after the last.
+constexpr int CH_LANES = 4;
+struct ChainLanes {
+  cudaStream_t stream[CH_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, done[CH_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  bool used[CH_LANES] = {false, false, false, false};
+  int device = -1;
+};
+static int chain_lanes(ChainLanes** out) {
+  static thread_local ChainLanes L;
+  int dev = 0;
+  CUR_CUDA_TRY(cudaGetDevice(&dev));
+  if (L.fork == nullptr || L.device != dev) {
+    for (int i = 0; i < CH_LANES; ++i) {
+      CUR_CUDA_TRY(cudaStreamCreateWithFlags(&L.stream[i], cudaStreamNonBlocking));
+      CUR_CUDA_TRY(cudaEventCreateWithFlags(&L.done[i], cudaEventDisableTiming));
+      L.used[i] = false;
+    }
+    CUR_CUDA_TRY(cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
+    L.device = dev;
+  }
+  *out = &L;
+  return CUR_OK;
+}
+int tc_chain_lanes_fork(cudaStream_t s) {
+  ChainLanes* L = nullptr;
+  CUR_TRY(chain_lanes(&L));
+  CUR_CUDA_TRY(cudaEventRecord(L->fork, s));
+  for (int i = 0; i < CH_LANES; ++i) L->used[i] = false;
+  return CUR_OK;
+}
+int tc_chain_lane(int i, cudaStream_t* out) {
+  ChainLanes* L = nullptr;
+  CUR_TRY(chain_lanes(&L));
+  const int k = i % CH_LANES;
+  if (!L->used[k]) {
+    CUR_CUDA_TRY(cudaStreamWaitEvent(L->stream[k], L->fork, 0));
+    L->used[k] = true;
+  }
+  *out = L->stream[k];
+  return CUR_OK;
+}
+int tc_chain_lanes_join(cudaStream_t s) {
+  ChainLanes* L = nullptr;
+  CUR_TRY(chain_lanes(&L));
+  for (int k = 0; k < CH_LANES; ++k) {
+    if (!L->used[k]) continue;
+    CUR_CUDA_TRY(cudaEventRecord(L->done[k], L->stream[k]));
+    CUR_CUDA_TRY(cudaStreamWaitEvent(s, L->done[k], 0));
+    L->used[k] = false;
+  }
+  return CUR_OK;
+}
+
 int tc_chain_rowsums(cudaStream_t s, TcRowSumBatch& R) {
   if (R.n == 0) return CUR_OK;
   int blocks = 0;

@@ -81,6 +81,10 @@ struct TcRowSumBatch {
 };
 int tc_chain_rowsums(cudaStream_t s, TcRowSumBatch& R);   // on a side stream forked from `s`
 int tc_chain_join(cudaStream_t s);                        // ... which `s` waits for here
+// concurrent chain launches of several experts: fork from `s`, expert i's stream, join back into `s`
+int tc_chain_lanes_fork(cudaStream_t s);
+int tc_chain_lane(int i, cudaStream_t* out);
+int tc_chain_lanes_join(cudaStream_t s);
 bool tc_chain_supported(const cur_net_desc& d, int64_t n);
 int tc_chain_launch(cudaStream_t s, const cur_net_desc& d, const TcChainIO& io);
 void tc_chain_set_timeline(long long* dev);             // 128 x int64 debug stamps (CTA 0 / CTA 1) or NULL
