@@ -25,7 +25,7 @@ class Layout(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'T', 'dimo', 'dimag', 'dimg', 'dimu', 'dimtd', 'dimchange', 'diminfo',
         'off_g', 'off_u', 'off_td', 'off_ag', 'off_o', 'row_stride',
-        'off_change', 'off_info', 'cold_stride')]
+        'off_change', 'off_info', 'cold_stride', 'trans_stride', 'off_agc')]
 
 
 class EpisodeSrc(C.Structure):

@@ -286,14 +286,13 @@ __device__ __forceinline__ float x_elem(const StreamParams& P, int64_t row, int 
   const cur_net_desc& d = P.d;
   const bool nrm = d.normalize_obs != 0;
   const int in_s = P.in_sp + (act_kind ? d.dimu : 0);
-  const cur_layout& HL = P.her.L;
   const HerPlan& pl = P.plan;
   const float clip = P.her.clip_obs;
   float v = 0.f;
   int gj = -1, aj = -1;
   if (k < d.dimo) {
     if (st) {
-      v = st[(target ? pl.i0 + HL.off_o : HL.off_o - pl.img_off) + k];
+      v = st[(target ? pl.iO2 : pl.iO) + k];
       if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
     } else {
       v = (target ? P.o_2 : P.o)[row * d.dimo + k];
@@ -302,7 +301,7 @@ __device__ __forceinline__ float x_elem(const StreamParams& P, int64_t row, int 
   } else if (d.modular) {
     if (k < d.dimo + d.dimtd) {
       const int j = k - d.dimo;
-      v = st ? st[pl.i0 + HL.off_td + j] : P.td[row * d.dimtd + j];       // never normalised
+      v = st ? st[pl.iTD + j] : P.td[row * d.dimtd + j];       // never normalised
     } else if (k < in_s) aj = k - d.dimo - d.dimtd;
     else if (k < in_s + d.dimg) gj = k - in_s;
   } else {
@@ -311,8 +310,8 @@ __device__ __forceinline__ float x_elem(const StreamParams& P, int64_t row, int 
   }
   if (gj >= 0) {
     if (st) {
-      v = st[pl.i0 + HL.off_g + gj];
-      if (P.her.relative_goals) v -= st[(target ? pl.i0 + HL.off_ag : HL.off_ag - pl.img_off) + gj];
+      v = st[pl.iG + gj];
+      if (P.her.relative_goals) v -= st[(target ? pl.iAG2 : pl.iAG) + gj];
       if (clip > 0.f) v = fminf(fmaxf(v, -clip), clip);
     } else {
       v = (target ? P.g_2 : P.g)[row * d.dimg + gj];
@@ -320,7 +319,7 @@ __device__ __forceinline__ float x_elem(const StreamParams& P, int64_t row, int 
     if (nrm) v = norm1s(v, P.g_mean, P.g_std, gj, d.norm_clip);
   }
   if (aj >= 0) {
-    if (act_kind == 1) v = __fdiv_rn(st ? st[pl.i0 + HL.off_u + aj] : P.u[row * d.dimu + aj], d.max_u);
+    if (act_kind == 1) v = __fdiv_rn(st ? st[pl.iU + aj] : P.u[row * d.dimu + aj], d.max_u);
     else v = ths[r * S_DU + aj];
   }
   return v;
@@ -354,7 +353,7 @@ __device__ __forceinline__ void sample_rows(const StreamParams& P, int64_t row0,
   if (tid < S_ROWS) her_draw_row(P.her, pl, row0 + tid, row, m_src + 3 * tid);
   consumer_sync();
   if (warp < S_ROWS) {
-    const int per_row = pl.img4 + pl.fut4 + pl.cold4;   // (cold rows only when a module's reward reads `info`)
+    const int per_row = pl.img4 + pl.fut4 + pl.cold4;   // (cold rows only for an `info` reward or relative goals)
     float* dst = stage + warp * pl.stage_stride;
     for (int c = lane; c < per_row; c += 32) {
       int sel = 0, q = c, doff = 4 * c;

@@ -11,8 +11,8 @@
 //   * warp 0 decodes the per-row draws (injected stream or Philox4x32-10), one lane per row, and
 //     publishes three source addresses per row (main span, future achieved goal, cold row);
 //   * all warps then copy global -> shared with per-lane 16-byte cp.async (SASS LDGSTS, L2-only
-//     `.cg`): thanks to the shifted hot-row layout the whole transition is ONE contiguous span, so a
-//     single warp-wide LDGSTS moves an Arm4 transition (28 lanes span + 3 lanes future goal);
+//     `.cg`): a transition is ONE 64-byte aligned row of the transition-major storage, so a
+//     single warp-wide LDGSTS moves an Arm4 transition (28 lanes row + 3 lanes future goal);
 //     no register staging, ~16 KB in flight per CTA, up to 14 CTAs per SM;
 //   * relabel (g, task_descr), the float64 reward and the clip are evaluated straight out of shared
 //     memory and every output array is written as contiguous, fully coalesced 16-byte stores.
@@ -57,11 +57,11 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 __device__ __forceinline__ float clipf(float x, float c) { return fminf(fmaxf(x, -c), c); }
 
-// Cooperative, coalesced write of `nrows` rows of `dim` floats starting at output row j0.
+// Cooperative, coalesced write of `nrows` rows of `dim` floats starting at output row j0 by threads t = 0 .. nt-1.
 // src(tr, k) returns element k of tile-row tr.  The output span is contiguous and 128-byte aligned
 // (j0 is a multiple of TILE), so dim % 4 == 0 takes the 16-byte path.
 template <typename Src4, typename Src1>
-__device__ __forceinline__ void emit(float* __restrict__ out, int dim, int64_t j0, int nrows,
+__device__ __forceinline__ void emit(float* __restrict__ out, int dim, int64_t j0, int nrows, int t, int nt,
                                      Src4 src4, Src1 src1) {
   if (out == nullptr || dim <= 0) return;
   float* dst = out + j0 * (int64_t)dim;
@@ -69,7 +69,7 @@ __device__ __forceinline__ void emit(float* __restrict__ out, int dim, int64_t j
     const int d4 = dim >> 2;
     const float inv = 1.0f / (float)d4;
     const int n4 = nrows * d4;
-    for (int i = threadIdx.x; i < n4; i += HER_THREADS) {
+    for (int i = t; i < n4; i += nt) {
       int tr = __float2int_rz(((float)i + 0.5f) * inv);
       int k4 = i - tr * d4;
       reinterpret_cast<float4*>(dst)[i] = src4(tr, k4 << 2);
@@ -77,7 +77,7 @@ __device__ __forceinline__ void emit(float* __restrict__ out, int dim, int64_t j
   } else {
     const float inv = 1.0f / (float)dim;
     const int n = nrows * dim;
-    for (int i = threadIdx.x; i < n; i += HER_THREADS) {
+    for (int i = t; i < n; i += nt) {
       int tr = __float2int_rz(((float)i + 0.5f) * inv);
       int k = i - tr * dim;
       dst[i] = src1(tr, k);
@@ -88,9 +88,9 @@ __device__ __forceinline__ void emit(float* __restrict__ out, int dim, int64_t j
 // Two outputs of the same width sharing the index arithmetic (o/o_2, g/g_2, ag/ag_2).
 template <typename A4, typename B4, typename A1, typename B1>
 __device__ __forceinline__ void emit2(float* __restrict__ outa, float* __restrict__ outb, int dim, int64_t j0,
-                                      int nrows, A4 a4, B4 b4, A1 a1, B1 b1) {
-  if (outa == nullptr) { emit(outb, dim, j0, nrows, b4, b1); return; }
-  if (outb == nullptr) { emit(outa, dim, j0, nrows, a4, a1); return; }
+                                      int nrows, int t, int nt, A4 a4, B4 b4, A1 a1, B1 b1) {
+  if (outa == nullptr) { emit(outb, dim, j0, nrows, t, nt, b4, b1); return; }
+  if (outb == nullptr) { emit(outa, dim, j0, nrows, t, nt, a4, a1); return; }
   if (dim <= 0) return;
   float* da = outa + j0 * (int64_t)dim;
   float* db = outb + j0 * (int64_t)dim;
@@ -98,7 +98,7 @@ __device__ __forceinline__ void emit2(float* __restrict__ outa, float* __restric
     const int d4 = dim >> 2;
     const float inv = 1.0f / (float)d4;
     const int n4 = nrows * d4;
-    for (int i = threadIdx.x; i < n4; i += HER_THREADS) {
+    for (int i = t; i < n4; i += nt) {
       int tr = __float2int_rz(((float)i + 0.5f) * inv);
       int k = (i - tr * d4) << 2;
       reinterpret_cast<float4*>(da)[i] = a4(tr, k);
@@ -107,7 +107,7 @@ __device__ __forceinline__ void emit2(float* __restrict__ outa, float* __restric
   } else {
     const float inv = 1.0f / (float)dim;
     const int n = nrows * dim;
-    for (int i = threadIdx.x; i < n; i += HER_THREADS) {
+    for (int i = t; i < n; i += nt) {
       int tr = __float2int_rz(((float)i + 0.5f) * inv);
       int k = i - tr * dim;
       da[i] = a1(tr, k);
@@ -116,6 +116,11 @@ __device__ __forceinline__ void emit2(float* __restrict__ outa, float* __restric
   }
 }
 
+// One CTA = one tile of TILE output rows, one shared-memory stage (~16 KB: 12 - 14 CTAs per SM overlap their phases):
+//   draws (warp 0) | gather (all warps, cp.async) | relabel + reward (warp 0) NEXT TO the outputs that do not depend on it
+//   (o, o_2, u, ag, ag_2, change, info: warps 1 - 3) | the relabelled outputs (g, g_2, task_descr: all warps).
+// (A persistent double-buffered variant - draws and gather of tile i+1 issued before tile i is waited for - was measured
+// slower, 70 % vs 81 % of the HBM peak: throughput follows the number of resident tiles per SM, profiles/README.md.)
 __global__ void __launch_bounds__(HER_THREADS)
 her_sample_kernel(const __grid_constant__ HerKernelParams P) {
   const cur_her_args& a = P.a;
@@ -124,12 +129,9 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
 
   float* stage = reinterpret_cast<float*>(smem_raw);                              // TILE * stage_stride
-  // per row: source address of [0] the main span, [1] the future achieved goal (NULL: not a HER
+  // per row: source address of [0] the transition row, [1] the future achieved goal (NULL: not a HER
   // row), [2] the cold row (NULL: not requested)
   const float** m_src = reinterpret_cast<const float**>(stage + TILE * pl.stage_stride);    // TILE * 3
-  float* rew = reinterpret_cast<float*>(m_src + 3 * TILE);                        // TILE
-  int* m_task = reinterpret_cast<int*>(rew + TILE);        // module written to task_descr (-1: keep)
-  int* m_relab = m_task + TILE;                            // module whose goal slice is relabelled (-1: none)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -150,11 +152,11 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
     const int per_row = pl.img4 + pl.fut4 + pl.cold4;
     const uint32_t stage_s = smem_u32(stage);
     for (int c0 = 0; c0 < per_row; c0 += 32) {
-      const int c = c0 + lane;
-      int sel = 0, q = c, doff = 4 * c;
-      if (c >= pl.img4 + pl.fut4) { sel = 2; q = c - pl.img4 - pl.fut4; doff = pl.cold_off + 4 * q; }
-      else if (c >= pl.img4) { sel = 1; q = c - pl.img4; doff = pl.fut_off + 4 * q; }
-      const bool active = c < per_row;
+      const int ch = c0 + lane;
+      int sel = 0, q = ch, doff = 4 * ch;
+      if (ch >= pl.img4 + pl.fut4) { sel = 2; q = ch - pl.img4 - pl.fut4; doff = pl.cold_off + 4 * q; }
+      else if (ch >= pl.img4) { sel = 1; q = ch - pl.img4; doff = pl.fut_off + 4 * q; }
+      const bool active = ch < per_row;
       uint32_t dst = stage_s + 4u * (uint32_t)(warp * ss + doff);
       const uint32_t dstep = 4u * (uint32_t)(HER_WARPS * ss);
       for (int r = warp; r < nrows; r += HER_WARPS, dst += dstep) {
@@ -167,27 +169,8 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
   }
   __syncthreads();
 
-  // ---------------------------------------------------------------- module decisions + reward
-  // image indices: row t sections at (off - img_off); row t+1 sections at (i0 + off);
-  // g/u/td of step t live in row t+1 (shifted layout)
-  const int iG = pl.i0 + L.off_g, iU = pl.i0 + L.off_u, iTD = pl.i0 + L.off_td;
-  const int iAG2 = pl.i0 + L.off_ag, iO2 = pl.i0 + L.off_o;
-  const int iO = L.off_o - pl.img_off, iAG = L.off_ag - pl.img_off;   // iAG valid only if img_off <= off_ag
-  const bool wipe = (a.mode == CUR_MODE_BUFFER || a.mode == CUR_MODE_RANDOM_TASK || a.mode == CUR_MODE_CP_TASK);
-
-  if (warp == 0 && lane < nrows) {
-    int relab_out = -1;
-    const float rew1 = her_relabel_row(a, pl, stage + lane * ss, row, &relab_out);
-    if (a.idx_out) {
-      int32_t* io = a.idx_out + (j0 + lane) * 4;
-      io[0] = row.ep; io[1] = row.t; io[2] = row.ft;
-      io[3] = row.her ? ((a.mode == CUR_MODE_FLAT) ? 0 : relab_out) : -1;
-    }
-    if (a.r != nullptr) a.r[j0 + lane] = rew1;
-  }
-  __syncthreads();
-
-  // ---------------------------------------------------------------- coalesced outputs
+  // image indices (HerPlan): o(t) first, then the step block; ag(t) sits in the cold part of the image
+  const int iG = pl.iG, iU = pl.iU, iTD = pl.iTD, iAG2 = pl.iAG2, iO2 = pl.iO2, iO = pl.iO, iAG = pl.iAG;
   const float c = a.clip_obs;
   const bool do_clip = c > 0.0f;
   auto ld4 = [&](int tr, int off) {
@@ -200,46 +183,65 @@ her_sample_kernel(const __grid_constant__ HerKernelParams P) {
   auto clip1 = [&](float v) { return do_clip ? clipf(v, c) : v; };
   auto sub4 = [&](float4 x, float4 y) { return make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w); };
 
-  emit2(a.o, a.o_2, L.dimo, j0, nrows,
-        [&](int tr, int k) { return clip4(ld4(tr, iO + k)); },
-        [&](int tr, int k) { return clip4(ld4(tr, iO2 + k)); },
-        [&](int tr, int k) { return clip1(stage[tr * ss + iO + k]); },
-        [&](int tr, int k) { return clip1(stage[tr * ss + iO2 + k]); });
-  emit(a.u, L.dimu, j0, nrows,
-       [&](int tr, int k) { return ld4(tr, iU + k); },
-       [&](int tr, int k) { return stage[tr * ss + iU + k]; });
-  emit(a.td, L.dimtd, j0, nrows,
+  if (warp == 0) {
+    // ---------------------------------------------------------------- module decisions + reward (one lane per row)
+    if (lane < nrows) {
+      int relab_out = -1;
+      const float rew1 = her_relabel_row(a, pl, stage + lane * ss, row, &relab_out);
+      if (a.idx_out) {
+        int32_t* io = a.idx_out + (j0 + lane) * 4;
+        io[0] = row.ep; io[1] = row.t; io[2] = row.ft;
+        io[3] = row.her ? ((a.mode == CUR_MODE_FLAT) ? 0 : relab_out) : -1;
+      }
+      if (a.r != nullptr) a.r[j0 + lane] = rew1;
+    }
+  } else {
+    // ---------------------------------------------------------------- outputs the relabelling does not touch
+    const int t = tid - 32, nt = HER_THREADS - 32;
+    emit2(a.o, a.o_2, L.dimo, j0, nrows, t, nt,
+          [&](int tr, int k) { return clip4(ld4(tr, iO + k)); },
+          [&](int tr, int k) { return clip4(ld4(tr, iO2 + k)); },
+          [&](int tr, int k) { return clip1(stage[tr * ss + iO + k]); },
+          [&](int tr, int k) { return clip1(stage[tr * ss + iO2 + k]); });
+    emit(a.u, L.dimu, j0, nrows, t, nt,
+         [&](int tr, int k) { return ld4(tr, iU + k); },
+         [&](int tr, int k) { return stage[tr * ss + iU + k]; });
+    emit2(a.ag, a.ag_2, L.dimag, j0, nrows, t, nt,
+          [&](int tr, int k) { return ld4(tr, iAG + k); },
+          [&](int tr, int k) { return ld4(tr, iAG2 + k); },
+          [&](int tr, int k) { return stage[tr * ss + iAG + k]; },
+          [&](int tr, int k) { return stage[tr * ss + iAG2 + k]; });
+    emit(a.change, L.dimchange, j0, nrows, t, nt,
+         [&](int tr, int k) { return ld4(tr, pl.cold_off + L.off_change + k); },
+         [&](int tr, int k) { return stage[tr * ss + pl.cold_off + L.off_change + k]; });
+    emit(a.info, L.diminfo, j0, nrows, t, nt,
+         [&](int tr, int k) { return ld4(tr, pl.cold_off + L.off_info + k); },
+         [&](int tr, int k) { return stage[tr * ss + pl.cold_off + L.off_info + k]; });
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- the relabelled outputs
+  emit(a.td, L.dimtd, j0, nrows, tid, HER_THREADS,
        [&](int tr, int k) { return ld4(tr, iTD + k); },
        [&](int tr, int k) { return stage[tr * ss + iTD + k]; });
   // g / g_2 (ddpg.py:350-353): optional relative goals, then clip
   if (a.relative_goals) {
-    emit2(a.g, a.g_2, L.dimg, j0, nrows,
+    emit2(a.g, a.g_2, L.dimg, j0, nrows, tid, HER_THREADS,
           [&](int tr, int k) { return clip4(sub4(ld4(tr, iG + k), ld4(tr, iAG + k))); },
           [&](int tr, int k) { return clip4(sub4(ld4(tr, iG + k), ld4(tr, iAG2 + k))); },
           [&](int tr, int k) { return clip1(stage[tr * ss + iG + k] - stage[tr * ss + iAG + k]); },
           [&](int tr, int k) { return clip1(stage[tr * ss + iG + k] - stage[tr * ss + iAG2 + k]); });
   } else {
-    emit2(a.g, a.g_2, L.dimg, j0, nrows,
+    emit2(a.g, a.g_2, L.dimg, j0, nrows, tid, HER_THREADS,
           [&](int tr, int k) { return clip4(ld4(tr, iG + k)); },
           [&](int tr, int k) { return clip4(ld4(tr, iG + k)); },
           [&](int tr, int k) { return clip1(stage[tr * ss + iG + k]); },
           [&](int tr, int k) { return clip1(stage[tr * ss + iG + k]); });
   }
-  emit2(a.ag, a.ag_2, L.dimag, j0, nrows,
-        [&](int tr, int k) { return ld4(tr, iAG + k); },
-        [&](int tr, int k) { return ld4(tr, iAG2 + k); },
-        [&](int tr, int k) { return stage[tr * ss + iAG + k]; },
-        [&](int tr, int k) { return stage[tr * ss + iAG2 + k]; });
-  emit(a.change, L.dimchange, j0, nrows,
-       [&](int tr, int k) { return ld4(tr, pl.cold_off + L.off_change + k); },
-       [&](int tr, int k) { return stage[tr * ss + pl.cold_off + L.off_change + k]; });
-  emit(a.info, L.diminfo, j0, nrows,
-       [&](int tr, int k) { return ld4(tr, pl.cold_off + L.off_info + k); },
-       [&](int tr, int k) { return stage[tr * ss + pl.cold_off + L.off_info + k]; });
 }
 
 // ------------------------------------------------------------------------------------------------
-// store: pack key-major episodes into hot/cold rows, one CTA per (row, copy)
+// store: pack key-major episodes into transition / cold rows, one CTA per (transition, copy)
 // ------------------------------------------------------------------------------------------------
 struct StoreParams {
   cur_layout L;
@@ -253,48 +255,36 @@ struct StoreParams {
 
 __global__ void __launch_bounds__(128) store_episodes_kernel(const __grid_constant__ StoreParams S) {
   const cur_layout& L = S.L;
-  const int r = blockIdx.x;        // hot row 0..T
+  const int t = blockIdx.x;        // transition 0..T-1
   const int cpy = blockIdx.y;
   const int e = S.copy_src[cpy];
-  float* dst = S.copy_hot[cpy] + (S.copy_slot[cpy] * (L.T + 1) + r) * (int64_t)L.row_stride;
-  const int64_t rprev = (int64_t)e * L.T + (r - 1);        // step whose g/u/td live in this row
-  const int64_t rcur = (int64_t)e * (L.T + 1) + r;
-  for (int k = threadIdx.x; k < L.row_stride; k += blockDim.x) {
+  float* dst = S.copy_hot[cpy] + (S.copy_slot[cpy] * L.T + t) * (int64_t)L.trans_stride;
+  const int64_t rt = (int64_t)e * L.T + t;                 // step t of the key-major [n_ep, T, dim] arrays
+  const int64_t rcur = (int64_t)e * (L.T + 1) + t;         // row t of the [n_ep, T+1, dim] arrays
+  const int dimo_pad = round_up4(L.dimo);
+  for (int k = threadIdx.x; k < L.trans_stride; k += blockDim.x) {
     float v = 0.0f;
-    if (k < L.off_ag) {
-      if (r > 0) {
-        if (k < L.off_u) {
-          int j = k - L.off_g;
-          if (j < L.dimg) v = S.src.g[rprev * L.dimg + j];
-        } else if (k < L.off_td) {
-          int j = k - L.off_u;
-          if (j < L.dimu) v = S.src.u[rprev * L.dimu + j];
-        } else {
-          int j = k - L.off_td;
-          if (j < L.dimtd && S.src.td) v = S.src.td[rprev * L.dimtd + j];
-        }
-      }
-    } else if (k < L.off_o) {
-      int j = k - L.off_ag;
-      if (j < L.dimag) v = S.src.ag[rcur * L.dimag + j];
+    if (k < dimo_pad) {
+      if (k < L.dimo) v = S.src.o[rcur * L.dimo + k];
     } else {
-      int j = k - L.off_o;
-      if (j < L.dimo) v = S.src.o[rcur * L.dimo + j];
+      const int b = k - dimo_pad;                          // inside the step block
+      int j;
+      if ((j = b - L.off_g) >= 0 && j < L.dimg) v = S.src.g[rt * L.dimg + j];
+      else if ((j = b - L.off_u) >= 0 && j < L.dimu) v = S.src.u[rt * L.dimu + j];
+      else if ((j = b - L.off_td) >= 0 && j < L.dimtd) { if (S.src.td) v = S.src.td[rt * L.dimtd + j]; }
+      else if ((j = b - L.off_ag) >= 0 && j < L.dimag) v = S.src.ag[(rcur + 1) * L.dimag + j];
+      else if ((j = b - L.off_o) >= 0 && j < L.dimo) v = S.src.o[(rcur + 1) * L.dimo + j];
     }
     dst[k] = v;
   }
-  if (r < L.T && L.cold_stride > 0 && S.copy_cold[cpy] != nullptr) {
-    float* cd = S.copy_cold[cpy] + (S.copy_slot[cpy] * L.T + r) * (int64_t)L.cold_stride;
-    const int64_t rt = (int64_t)e * L.T + r;
+  if (S.copy_cold[cpy] != nullptr) {
+    float* cd = S.copy_cold[cpy] + (S.copy_slot[cpy] * L.T + t) * (int64_t)L.cold_stride;
     for (int k = threadIdx.x; k < L.cold_stride; k += blockDim.x) {
       float v = 0.0f;
-      if (k < L.off_info) {
-        int j = k - L.off_change;
-        if (j < L.dimchange && S.src.change) v = S.src.change[rt * L.dimchange + j];
-      } else {
-        int j = k - L.off_info;
-        if (j < L.diminfo && S.src.info) v = S.src.info[rt * L.diminfo + j];
-      }
+      int j;
+      if ((j = k - L.off_change) >= 0 && j < L.dimchange) { if (S.src.change) v = S.src.change[rt * L.dimchange + j]; }
+      else if ((j = k - L.off_info) >= 0 && j < L.diminfo) { if (S.src.info) v = S.src.info[rt * L.diminfo + j]; }
+      else if ((j = k - L.off_agc) >= 0 && j < L.dimag) v = S.src.ag[rcur * L.dimag + j];
       cd[k] = v;
     }
   }
@@ -325,16 +315,35 @@ extern "C" int cur_layout_init(cur_layout* L, int T, int dimo, int dimag, int di
   L->T = T;
   L->dimo = dimo; L->dimag = dimag; L->dimg = dimg; L->dimu = dimu;
   L->dimtd = dimtd; L->dimchange = dimchange; L->diminfo = diminfo;
+  // Step block: g, u, task_descr, ag(t+1) in the order that makes the ag(t+1) block - the one a HER row of ANOTHER
+  // transition gathers on its own - straddle the fewest 64-byte DRAM atoms of the transition row; o(t+1) stays last.
+  // Ties keep the earliest order in the enumeration below (g, u, td, ag first).
+  const int dimo_pad = round_up4(dimo);
+  const int w[4] = {round_up4(dimg), round_up4(dimu), round_up4(dimtd), round_up4(dimag)};   // g u td ag
+  static const int perms[24][4] = {{0, 1, 2, 3}, {0, 1, 3, 2}, {0, 2, 1, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {0, 3, 2, 1},
+                                   {1, 0, 2, 3}, {1, 0, 3, 2}, {1, 2, 0, 3}, {1, 2, 3, 0}, {1, 3, 0, 2}, {1, 3, 2, 0},
+                                   {2, 0, 1, 3}, {2, 0, 3, 1}, {2, 1, 0, 3}, {2, 1, 3, 0}, {2, 3, 0, 1}, {2, 3, 1, 0},
+                                   {3, 0, 1, 2}, {3, 0, 2, 1}, {3, 1, 0, 2}, {3, 1, 2, 0}, {3, 2, 0, 1}, {3, 2, 1, 0}};
+  int best = 0, best_atoms = 1 << 30;
+  for (int p = 0; p < 24; ++p) {
+    int off = 0, ag_at = 0;
+    for (int i = 0; i < 4; ++i) {
+      if (perms[p][i] == 3) ag_at = off;
+      off += w[perms[p][i]];
+    }
+    const int first = (dimo_pad + ag_at) / 16, last = (dimo_pad + ag_at + w[3] - 1) / 16;
+    if (last - first + 1 < best_atoms) { best_atoms = last - first + 1; best = p; }
+  }
   int off = 0;
-  L->off_g = off; off += round_up4(dimg);
-  L->off_u = off; off += round_up4(dimu);
-  L->off_td = off; off += round_up4(dimtd);
-  L->off_ag = off; off += round_up4(dimag);
-  L->off_o = off; off += round_up4(dimo);
+  int32_t* slot[4] = {&L->off_g, &L->off_u, &L->off_td, &L->off_ag};
+  for (int i = 0; i < 4; ++i) { *slot[perms[best][i]] = off; off += w[perms[best][i]]; }
+  L->off_o = off; off += dimo_pad;
   L->row_stride = off;
+  L->trans_stride = (dimo_pad + off + 15) / 16 * 16;
   off = 0;
   L->off_change = off; off += round_up4(dimchange);
   L->off_info = off; off += round_up4(diminfo);
+  L->off_agc = off; off += round_up4(dimag);
   L->cold_stride = off;
   return CUR_OK;
 }
@@ -345,7 +354,7 @@ extern "C" int cur_store_episodes(void* stream, const cur_layout* L, const cur_e
   CUR_REQUIRE(L && src && copy_src && copy_hot && copy_slot, "NULL argument");
   CUR_REQUIRE(src->o && src->ag && src->g && src->u, "o/ag/g/u sources are required");
   CUR_REQUIRE(n_copies >= 0 && n_ep > 0, "bad counts");
-  CUR_REQUIRE(L->cold_stride == 0 || copy_cold != nullptr, "cold destinations required");
+  CUR_REQUIRE(copy_cold != nullptr, "cold destinations required");
   cudaStream_t s = (cudaStream_t)stream;
   for (int done = 0; done < n_copies; done += CUR_MAX_COPIES) {
     StoreParams S;
@@ -357,10 +366,11 @@ extern "C" int cur_store_episodes(void* stream, const cur_layout* L, const cur_e
       CUR_REQUIRE(copy_hot[done + i] != nullptr && copy_slot[done + i] >= 0, "bad destination");
       S.copy_src[i] = copy_src[done + i];
       S.copy_hot[i] = copy_hot[done + i];
-      S.copy_cold[i] = copy_cold ? copy_cold[done + i] : nullptr;
+      CUR_REQUIRE(copy_cold[done + i] != nullptr, "bad cold destination");
+      S.copy_cold[i] = copy_cold[done + i];
       S.copy_slot[i] = copy_slot[done + i];
     }
-    dim3 grid(L->T + 1, S.n_copies);
+    dim3 grid(L->T, S.n_copies);
     store_episodes_kernel<<<grid, 128, 0, s>>>(S);
     CUR_CHECK_LAUNCH();
   }
@@ -412,8 +422,8 @@ extern "C" int cur_her_sample(void* stream, const cur_her_args* args) {
   make_plan(a, &P.p);
   if (P.p.cold4 > 0)
     for (int i = 0; i < a.n_segments; ++i)
-      CUR_REQUIRE(a.seg[i].count == 0 || a.seg[i].cold != nullptr, "change/info requested but segment has no cold rows");
-  size_t smem = (size_t)TILE * P.p.stage_stride * 4 + 3 * TILE * sizeof(void*) + 3 * TILE * 4 + 16;
+      CUR_REQUIRE(a.seg[i].count == 0 || a.seg[i].cold != nullptr, "change/info/ag requested but segment has no cold rows");
+  size_t smem = (size_t)TILE * P.p.stage_stride * 4 + 3 * TILE * sizeof(void*) + 16;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     CUR_REQUIRE(smem <= 227 * 1024, "row too large for the shared-memory stage");

@@ -10,15 +10,16 @@
 namespace cur {
 
 struct HerPlan {
-  // shared-memory image of one transition = global floats [row t + img_off, row t+1 end), then the
-  // future achieved goal, then (optionally) the cold row
-  int img_off;      // first float of row t that is copied (off_o, or off_ag when ag_t is needed)
-  int i0;           // image index where row t+1 starts (= row_stride - img_off)
-  int img4;         // 16-byte chunks of the image
+  // shared-memory image of one transition = its transition row [o(t) | step block] (without the 64-byte tail padding),
+  // then the future achieved goal, then (optionally) the cold row [change | info | ag(t)]
+  int img4;         // 16-byte chunks of the transition row that are copied
   int fut_off, fut4;
-  int cold_off, cold4;   // cold4 == 0 when change/info are not requested
+  int cold_off, cold4;   // cold4 == 0 when neither change / info / ag(t) are needed
   int stage_stride; // floats per transition in shared memory
   int dimg_pad;
+  // image indices of the sections
+  int iO, iG, iU, iTD, iAG2, iO2;
+  int iAG;          // ag(t): inside the cold part, valid only when cold4 > 0
 };
 
 
@@ -80,10 +81,11 @@ __device__ __forceinline__ void her_draw_row(const cur_her_args& a, const HerPla
   }
   row.her = u_her < a.future_p;                                                   // her.py:115
   row.ft = row.her ? row.t + 1 + (int)(u_off * (double)(L.T - row.t)) : -1;       // her.py:116-118
-  const int64_t off = ((int64_t)row.ep * (L.T + 1) + row.t) * (int64_t)L.row_stride;
-  src[0] = base + off + pl.img_off;
-  src[1] = row.her ? base + ((int64_t)row.ep * (L.T + 1) + row.ft) * (int64_t)L.row_stride + L.off_ag : nullptr;
-  src[2] = (pl.cold4 > 0) ? a.seg[s].cold + ((int64_t)row.ep * L.T + row.t) * (int64_t)L.cold_stride : nullptr;
+  const int64_t tr = (int64_t)row.ep * L.T + row.t;
+  src[0] = base + tr * (int64_t)L.trans_stride;
+  // ag(future_t) is the ag(t+1) block of transition future_t - 1 (future_t >= 1)
+  src[1] = row.her ? base + ((int64_t)row.ep * L.T + (row.ft - 1)) * (int64_t)L.trans_stride + pl.iAG2 : nullptr;
+  src[2] = (pl.cold4 > 0) ? a.seg[s].cold + tr * (int64_t)L.cold_stride : nullptr;
 }
 
 // Squared distance of module m (float64, NumPy's operation order: difference, square, running sum - no FMA
@@ -101,12 +103,11 @@ __device__ __forceinline__ double reward_d2(const cur_task_table& tt, int m, con
 }
 
 // Relabel the staged image of one row in place (g, task_descr) and return its reward.
-// image indices: row t sections at (off - img_off); row t+1 sections at (i0 + off); g/u/td of step t live in
-// row t+1 (shifted layout).  *relab_out receives the module whose goal slice was relabelled (-1: none).
+// image indices come from the plan.  *relab_out receives the module whose goal slice was relabelled (-1: none).
 __device__ __forceinline__ float her_relabel_row(const cur_her_args& a, const HerPlan& pl, float* st, const HerRow& row,
                                                  int* relab_out) {
   const cur_layout& L = a.L;
-  const int iG = pl.i0 + L.off_g, iTD = pl.i0 + L.off_td, iAG2 = pl.i0 + L.off_ag;
+  const int iG = pl.iG, iTD = pl.iTD, iAG2 = pl.iAG2;
   const bool wipe = (a.mode == CUR_MODE_BUFFER || a.mode == CUR_MODE_RANDOM_TASK || a.mode == CUR_MODE_CP_TASK);
   int own = -1;
   for (int k = 0; k < L.dimtd; ++k)
@@ -167,14 +168,20 @@ inline int make_plan(const cur_her_args& a, HerPlan* p) {
   const bool need_ag_t = (a.ag != nullptr) || a.relative_goals;
   const bool need_cold = (a.change != nullptr && L.dimchange > 0) || (a.info != nullptr && L.diminfo > 0) ||
                          (reward_needs_info(a.tasks) && L.diminfo > 0);
-  p->img_off = need_ag_t ? L.off_ag : L.off_o;
-  p->i0 = L.row_stride - p->img_off;
-  p->img4 = (p->i0 + L.row_stride) / 4;
-  p->fut_off = p->i0 + L.row_stride;
+  const int dimo_pad = round_up4(L.dimo);
+  p->img4 = (dimo_pad + L.row_stride) / 4;
+  p->fut_off = dimo_pad + L.row_stride;
   p->fut4 = round_up4(L.dimag) / 4;
   p->cold_off = p->fut_off + 4 * p->fut4;
-  p->cold4 = need_cold ? L.cold_stride / 4 : 0;
+  p->cold4 = (need_cold || need_ag_t) ? L.cold_stride / 4 : 0;
   p->stage_stride = p->cold_off + 4 * p->cold4;
+  // one lane per row walks its image in the draw / relabel passes: an odd number of 16-byte units per row keeps the
+  // rows of a warp off the same shared-memory banks (128 floats per row would be a 32-way conflict)
+  if ((p->stage_stride / 4) % 2 == 0) p->stage_stride += 4;
+  p->iO = 0;
+  p->iG = dimo_pad + L.off_g; p->iU = dimo_pad + L.off_u; p->iTD = dimo_pad + L.off_td;
+  p->iAG2 = dimo_pad + L.off_ag; p->iO2 = dimo_pad + L.off_o;
+  p->iAG = p->cold_off + L.off_agc;
   p->dimg_pad = round_up4(L.dimg);
   return CUR_OK;
 }

@@ -1019,7 +1019,7 @@ class DDPG(object):
                 L, n = b.layout, b.current_size
                 st['buffers'].append(dict(
                     index=i, current_size=n, n_transitions_stored=b.n_transitions_stored, layout=bytes(L),
-                    hot=cpu(b.storage[:n * (L.T + 1) * L.row_stride]),
+                    hot=cpu(b.storage[:n * L.T * L.trans_stride]),
                     cold=None if b.cold is None else cpu(b.cold[:n * L.T * L.cold_stride])))
         torch.save(st, path)
 

@@ -1,8 +1,8 @@
 """Device-resident replay buffer - drop-in for reference baselines/her/replay_buffer.py:6-109.
 
-Storage is two float32 CUDA tensors of packed per-timestep rows (layout in include/curious_b200.h,
-`cur_layout`: "hot" rows [g|u|task_descr|ag|o] and "cold" rows [change|info]) instead of the
-reference's dict of float64 host arrays (replay_buffer.py:23-24).  Everything the reference stores is
+Storage is two float32 CUDA tensors of packed rows (layout in include/curious_b200.h, `cur_layout`:
+"hot" transition rows [o(t) | g u task_descr ag(t+1) o(t+1)], 64-byte aligned, and "cold" rows
+[change|info|ag(t)]) instead of the reference's dict of float64 host arrays (replay_buffer.py:23-24).  Everything the reference stores is
 float32-representable (rollout.py:50-52,194-195 build float32 episodes; `change` is bool), so no
 information is lost; inputs that are not are rounded to float32.
 
@@ -64,11 +64,9 @@ def layout_from_shapes(buffer_shapes):
 
 
 def alloc_storage(layout, n_episodes, device):
-    """(hot, cold) tensors for `n_episodes` episodes; cold is None when there is no change/info."""
-    hot = torch.empty(n_episodes * (layout.T + 1) * layout.row_stride, dtype=torch.float32, device=device)
-    cold = None
-    if layout.cold_stride > 0:
-        cold = torch.empty(n_episodes * layout.T * layout.cold_stride, dtype=torch.float32, device=device)
+    """(hot, cold) tensors for `n_episodes` episodes: transition rows and [change | info | ag(t)] rows."""
+    hot = torch.empty(n_episodes * layout.T * layout.trans_stride, dtype=torch.float32, device=device)
+    cold = torch.empty(n_episodes * layout.T * layout.cold_stride, dtype=torch.float32, device=device)
     return hot, cold
 
 
@@ -272,20 +270,22 @@ class ReplayBuffer:
         """Host copy in the reference's layout {key: float64 [size, T(+1), dim]} (debug / export only)."""
         L, T = self.layout, self.T
         n = self.current_size              # only the filled slots are copied; the rest reads as zeros (np.empty in the reference)
-        rows = np.zeros((self.size, T + 1, L.row_stride), np.float64)
-        rows[:n] = self.storage[:n * (T + 1) * L.row_stride].view(n, T + 1, L.row_stride).cpu().numpy()
-        out = {'o': rows[:, :, L.off_o:L.off_o + L.dimo], 'ag': rows[:, :, L.off_ag:L.off_ag + L.dimag],
-               # g/u/task_descr of step t are stored in hot row t+1 (shifted layout)
-               'g': rows[:, 1:, L.off_g:L.off_g + L.dimg], 'u': rows[:, 1:, L.off_u:L.off_u + L.dimu]}
+        rows = np.zeros((self.size, T, L.trans_stride), np.float64)
+        rows[:n] = self.storage[:n * T * L.trans_stride].view(n, T, L.trans_stride).cpu().numpy()
+        cold = np.zeros((self.size, T, L.cold_stride), np.float64)
+        cold[:n] = self.cold[:n * T * L.cold_stride].view(n, T, L.cold_stride).cpu().numpy()
+        b0 = (L.dimo + 3) // 4 * 4                       # the step block follows o(t)
+        step = lambda off, dim: rows[:, :, b0 + off:b0 + off + dim]
+        # o(t) heads transition t, o(T) is the o(t+1) block of the last transition; ag(t) lives in the cold rows
+        out = {'o': np.concatenate([rows[:, :, :L.dimo], step(L.off_o, L.dimo)[:, -1:]], axis=1),
+               'ag': np.concatenate([cold[:, :, L.off_agc:L.off_agc + L.dimag], step(L.off_ag, L.dimag)[:, -1:]], axis=1),
+               'g': step(L.off_g, L.dimg), 'u': step(L.off_u, L.dimu)}
         if self.has_td:
-            out['task_descr'] = rows[:, 1:, L.off_td:L.off_td + L.dimtd]
-        if self.cold is not None:
-            cold = np.zeros((self.size, T, L.cold_stride), np.float64)
-            cold[:n] = self.cold[:n * T * L.cold_stride].view(n, T, L.cold_stride).cpu().numpy()
-            if self.has_change:
-                out['change'] = cold[:, :, L.off_change:L.off_change + L.dimchange]
-            k0 = L.off_info
-            for key, d in self.info_keys:
-                out[key] = cold[:, :, k0:k0 + d]
-                k0 += d
+            out['task_descr'] = step(L.off_td, L.dimtd)
+        if self.has_change:
+            out['change'] = cold[:, :, L.off_change:L.off_change + L.dimchange]
+        k0 = L.off_info
+        for key, d in self.info_keys:
+            out[key] = cold[:, :, k0:k0 + d]
+            k0 += d
         return out

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CUR_ABI_VERSION 3
+#define CUR_ABI_VERSION 4
 
 #define CUR_OK 0
 #define CUR_ERR_INVALID 1   /* bad argument (dims, null pointer, table overflow)   */
@@ -42,22 +42,29 @@ int cur_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * Replay storage layout.  Replaces the float64 dict-of-arrays storage of
  * baselines/her/replay_buffer.py:23-24 by TWO float32 arrays per buffer:
  *
- *   hot  [E][T+1][row_stride]   row r = [ g(r-1) | u(r-1) | task_descr(r-1) | ag(r) | o(r) ]
- *   cold [E][T][cold_stride]    row t = [ change(t) | info(t) ]
+ *   hot  [E][T][trans_stride]   transition t = [ o(t) | step block ],  step block = g(t), u(t), task_descr(t),
+ *                               ag(t+1), o(t+1) at off_g / off_u / off_td / off_ag / off_o (o(t+1) last)
+ *   cold [E][T][cold_stride]    row t = [ change(t) | info(t) | ag(t) ]
  *
- * Sections are padded to multiples of 4 floats (16-byte aligned).  The per-step arrays g/u/task_descr
- * are stored SHIFTED by one row (row 0 holds zeros there), so everything a training transition
- * (o_t, g_t, u_t, td_t, o_{t+1}, ag_{t+1}) needs is ONE contiguous span: the tail [o] of row t
- * followed by the whole row t+1.  `change`/`info` are only read by the API-parity sampler and the
- * store-time routing; keeping them out of the hot rows keeps that span free of dead bytes.
+ * TRANSITION-major: everything a training transition needs (o_t, g_t, u_t, td_t, ag_{t+1}, o_{t+1}) is ONE row,
+ * padded to a multiple of 64 bytes - the DRAM access granularity - so a sampled transition costs exactly
+ * trans_stride * 4 bytes of DRAM reads (Arm4: 448 B = 7 atoms; the episode-major rows of round 1, 72 floats with the
+ * span starting on a 32-byte boundary, cost 480 B on average), at the price of storing o twice (o(t+1) of transition t
+ * is o(t) of transition t + 1; 1e6 Arm4 transitions: 0.45 GB hot + 0.11 GB cold).  The future achieved goal of a HER
+ * row is the ag(t+1) block of transition future_t - 1; cur_layout_init places that block inside the step block so that
+ * it straddles as few 64-byte atoms as possible (Arm4: one).  Sections are padded to multiples of 4 floats.
+ * `change` / `info` / ag(t) are only read by the API-parity sampler, the store-time routing, relative goals and an
+ * INFO reward rule; keeping them out of the hot rows keeps those free of dead bytes.
  * ------------------------------------------------------------------------------------------ */
 typedef struct cur_layout {
   int32_t T;
   int32_t dimo, dimag, dimg, dimu, dimtd, dimchange, diminfo;
-  int32_t off_g, off_u, off_td, off_ag, off_o; /* floats, inside a hot row  */
-  int32_t row_stride;                          /* floats per hot row, multiple of 4 */
+  int32_t off_g, off_u, off_td, off_ag, off_o; /* floats, inside the step block of a transition row; o last */
+  int32_t row_stride;                          /* floats of the step block, multiple of 4 */
   int32_t off_change, off_info;                /* floats, inside a cold row */
-  int32_t cold_stride;                         /* floats per cold row (0 if no change/info) */
+  int32_t cold_stride;                         /* floats per cold row */
+  int32_t trans_stride;                        /* floats per transition row: round_up16(round_up4(dimo) + row_stride) */
+  int32_t off_agc;                             /* ag(t) inside a cold row */
 } cur_layout;
 
 /* Fills offsets/strides.  dimtd/dimchange/diminfo may be 0 (flat structure). */
@@ -67,7 +74,7 @@ int cur_layout_init(cur_layout* L, int T, int dimo, int dimag, int dimg, int dim
 /* ------------------------------------------------------------------------------------------
  * cur_store_episodes - ReplayBuffer.store_episode (replay_buffer.py:57-72) + the per-module
  * duplication of DDPG.store_episode (ddpg.py:187-197).  Packs `n_ep` episodes given as key-major
- * float32 device arrays ([n_ep,T+1,dimo], [n_ep,T+1,dimag], [n_ep,T,dim*]...) into rows and writes
+ * float32 device arrays ([n_ep,T+1,dimo], [n_ep,T+1,dimag], [n_ep,T,dim*]...) into transition rows and writes
  * copy i of episode copy_src[i] to slot copy_slot[i] of the buffer (copy_hot[i], copy_cold[i]).
  * Slot choice (_get_storage_idx, replay_buffer.py:90-109) stays on the host: it consumes the
  * caller's np.random stream.  copy_* are HOST arrays of length n_copies <= CUR_MAX_COPIES.
@@ -113,8 +120,8 @@ enum {
 };
 
 typedef struct cur_segment {
-  const float* base;      /* hot rows of the buffer                                          */
-  const float* cold;      /* cold rows (needed only when change/info outputs are requested)  */
+  const float* base;      /* transition rows of the buffer                                   */
+  const float* cold;      /* cold rows (read for change / info / ag outputs, relative goals, INFO rewards) */
   int32_t n_episodes;     /* current_size: episodes are drawn from [0, n_episodes)            */
   int32_t count;          /* rows sampled from this buffer (proportions[i], ddpg.py:326-336)  */
   int32_t task_to_replay; /* module forced on HER rows, or -1 for None                        */

@@ -491,7 +491,7 @@ def test_checkpoint_resume_continues_bit_for_bit(use_graph, tmp_path):
     assert torch.equal(a.o_stats._running, b.o_stats._running) and torch.equal(a.g_stats.std, b.g_stats.std)
     for x, y in zip(a.buffer, b.buffer):
         assert x.n_transitions_stored == y.n_transitions_stored
-        n = x.current_size * (x.layout.T + 1) * x.layout.row_stride
+        n = x.current_size * x.layout.T * x.layout.trans_stride
         assert torch.equal(x.storage[:n], y.storage[:n])
     # a checkpoint of another architecture is refused
     kw2, dims2, ag2, g2 = ddpg_kwargs(4, hidden=64)

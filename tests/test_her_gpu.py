@@ -283,10 +283,11 @@ def test_full_size_properties():
     assert 0.02 < (r == 0).mean() < 0.98
     # future_t == T rows must reproduce the final achieved goal exactly -> recomputed reward is 0 there only if
     # the row's ag_2 equals it; check the gather itself on a sample of rows instead
-    host = buf.storage.view(buf.size, T + 1, buf.layout.row_stride)
+    host = buf.storage.view(buf.size, T, buf.layout.trans_stride)
     sel = np.where(her_rows)[0][:4096]
     L = buf.layout
-    fut = host[torch.from_numpy(ep[sel]).long().cuda(), torch.from_numpy(ft[sel]).long().cuda()][:, L.off_ag:L.off_ag + dims['ag']]
+    a0 = (dims['o'] + 3) // 4 * 4 + L.off_ag                  # ag(t+1) block of a transition row; ag(ft) sits in transition ft - 1
+    fut = host[torch.from_numpy(ep[sel]).long().cuda(), torch.from_numpy(ft[sel] - 1).long().cuda()][:, a0:a0 + dims['ag']]
     assert torch.equal(a['g'][torch.from_numpy(sel).cuda()][:, g_ids[2]], fut[:, ag_ids[2]])
 
 

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
         assert name in _lib.SIGNATURES, 'ctypes signature missing for ' + name
-    assert lib.cur_abi_version() == 3
+    assert lib.cur_abi_version() == 4
 
 
 def test_ctypes_structs_match_header(tmp_path):
@@ -43,10 +43,16 @@ def test_ctypes_structs_match_header(tmp_path):
 def test_layout_and_param_counts_without_gpu():
     from curious_b200 import _lib
     L = _lib.make_layout(50, 40, 12, 12, 4, 4, 12, 1)
-    assert (L.off_g, L.off_u, L.off_td, L.off_ag, L.off_o, L.row_stride) == (0, 12, 16, 20, 32, 72)
-    assert (L.off_change, L.off_info, L.cold_stride) == (0, 12, 16)
-    L = _lib.make_layout(10, 25, 3, 3, 4)          # unaligned dims get padded sections; flat: no cold rows
-    assert (L.off_g, L.off_u, L.off_td, L.off_ag, L.off_o, L.row_stride, L.cold_stride) == (0, 4, 8, 8, 12, 40, 0)
+    # Arm4: the transition row is exactly 7 x 64 bytes and the ag(t+1) block (floats 52..63 of it) sits inside ONE
+    # 64-byte atom - the order g, ag, u, td is the first of the enumeration that achieves it
+    assert (L.off_g, L.off_ag, L.off_u, L.off_td, L.off_o, L.row_stride, L.trans_stride) == (0, 12, 24, 28, 32, 72, 112)
+    assert (40 + L.off_ag) // 16 == (40 + L.off_ag + 11) // 16
+    assert (L.off_change, L.off_info, L.off_agc, L.cold_stride) == (0, 12, 16, 28)
+    L = _lib.make_layout(10, 25, 3, 3, 4)          # unaligned dims get padded sections; flat: the cold row is ag(t) alone
+    assert (L.off_g, L.off_u, L.off_td, L.off_ag, L.off_o, L.row_stride, L.trans_stride) == (0, 4, 8, 8, 12, 40, 80)
+    assert (L.off_change, L.off_info, L.off_agc, L.cold_stride) == (0, 0, 0, 4)
+    L = _lib.make_layout(50, 64, 24, 24, 4, 8, 0, 0)   # Arm8: 24 floats of ag(t+1) cannot fit one atom; two is the minimum
+    assert (64 + L.off_ag) // 16 + 1 == (64 + L.off_ag + 23) // 16
     lib = _lib.load()
     d = _lib.NetDesc(1, 40, 12, 4, 4, 256, 3, 1.0, 0, 5.0)
     assert lib.cur_net_param_count(C.byref(d), 0) == 147457
