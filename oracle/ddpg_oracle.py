@@ -7,10 +7,13 @@ Pinning (the reference has no tests for baselines/her/, and TensorFlow 1.x / mpi
     concatenation and shuffle, store_episode routing and its normaliser batch, get_actions post-processing,
     _preprocess_og, Normalizer.update / synchronize / snapshot-and-reset, MpiAdam.update (with NumPy-1 scalar casting
     reproduced at the boundary);
-  * PARITY UNPINNED (restated from the TF1 graph definitions): network forward, losses and gradients, the running-sum /
-    mean / std half of Normalizer, polyak.  tests/test_host_logic.py cross-checks the hand-written
-    backward pass against torch autograd and Adam against the reference's `test_MpiAdam` problem definition
-    (mpi_adam.py:54-63).
+  * PINNED against the reference's own graph code (round 2): the unmodified ddpg.py / actor_critic.py / util.py /
+    normalizer.py / tf_util.py / mpi_adam.py build and run their TF1 graph over oracle/tf1_shim.py (a stand-in `tensorflow`
+    whose primitives are torch CPU ops); oracle/gen_golden_ddpg.py records that agent's losses, gradients, parameters after
+    MpiAdam + polyak updates, get_actions outputs, weight files and whole-agent trajectories as tests/golden/ddpg/*.npz;
+    tests/test_reference_graph.py walks this file through them and runs the reference agent live beside it.
+    tests/test_host_logic.py additionally cross-checks the hand-written backward pass against torch autograd and Adam
+    against the reference's `test_MpiAdam` problem definition (mpi_adam.py:54-63).
 Each function cites the reference lines it restates.
 
 Conventions
