@@ -601,27 +601,40 @@ def measure_agent(agent, dims, n_modules, world, rank, barrier, torch, dist, dev
 
 def exchange_parity(agent, world, rank, torch, dist, device, n_updates=8):
     """Several ranks: the same updates through the in-launch tile exchange and through an all-gather + RANK-ORDERED sum +
-    Adam launch on identical gradients (fresh twin agents: same weights, same replay, same Philox counters) must end on
-    bit-identical parameters on every rank.  Also reports the distance to NCCL's own all-reduce, whose summation order
-    is its algorithm's (equal for 2 ranks, a few ulp otherwise)."""
+    Adam launch on identical gradients (fresh twin agents: same weights, same replay, same Philox counters).  The
+    peer-memory forms of the exchange (modes 0 / 1) sum in rank order: bit-identical parameters on every rank, asserted
+    bit for bit.  The NVLS form (mode 2, the default from 4 ranks) sums in the switch: parameters bit-identical on every
+    rank and within 1e-6 of the rank-ordered result; the mode-1 bit-for-bit check runs beside it.  Also reports the
+    distance to NCCL's own all-reduce, whose summation order is its algorithm's (equal for 2 ranks, a few ulp otherwise)."""
     from curious_b200 import parallel
-    thetas = {}
-    for name, ge, ordered in (('tile', 'auto', False), ('ordered', 'nccl', True), ('nccl', 'nccl', False)):
+    thetas, modes = {}, {}
+    for name, kw, ordered in (('tile', dict(grad_exchange='auto'), False), ('ordered', dict(grad_exchange='nccl'), True),
+                              ('nccl', dict(grad_exchange='nccl'), False), ('mode1', dict(grad_exchange='auto', xchg_mode=1), False)):
+        if name == 'mode1' and modes.get('tile') != 2:
+            continue
         parallel.ORDERED_ALLREDUCE = ordered
-        a = agent.make_agent(grad_exchange=ge)
+        a = agent.make_agent(**kw)
         for _ in range(n_updates):
             a.train()
         a.update_target_net()
         torch.cuda.synchronize()
         thetas[name] = a.theta_main.clone()
         kind = 'tile' if a._xchg is not None else ('p2p' if a._peer is not None else 'nccl')
+        modes[name] = int(a._xchg.mode) if a._xchg is not None else None
         if name == 'tile':
             used = kind
         del a
         torch.cuda.empty_cache()
         dist.barrier()
     parallel.ORDERED_ALLREDUCE = False
-    bad = torch.tensor([0 if torch.equal(thetas['tile'], thetas['ordered']) else 1], device=device)
+    nvls = modes['tile'] == 2
+    d_ord = (thetas['tile'] - thetas['ordered']).abs().max()
+    dist.all_reduce(d_ord, op=dist.ReduceOp.MAX)
+    if nvls:
+        bad = torch.tensor([0 if float(d_ord.item()) <= 1e-6 else 1], device=device)
+        bad += 0 if torch.equal(thetas['mode1'], thetas['ordered']) else 1
+    else:
+        bad = torch.tensor([0 if torch.equal(thetas['tile'], thetas['ordered']) else 1], device=device)
     # ... and every rank holds rank 0's parameters
     ref = thetas['tile'].clone()
     dist.broadcast(ref, src=0)
@@ -629,9 +642,66 @@ def exchange_parity(agent, world, rank, torch, dist, device, n_updates=8):
     dist.all_reduce(bad)
     diff = (thetas['tile'] - thetas['nccl']).abs().max()
     dist.all_reduce(diff, op=dist.ReduceOp.MAX)
-    return {'exchange_parity': int(bad.item()) == 0, 'exchange': used, 'updates': n_updates,
+    return {'exchange_parity': int(bad.item()) == 0, 'exchange': used, 'exchange_mode': modes['tile'], 'updates': n_updates,
+            'exchange_parity_rule': ('parameters bit-identical on every rank and within 1e-6 of the rank-ordered sum (NVLS: '
+                                     'the switch fixes the summation order); the peer-memory mode 1 bit-equal to the '
+                                     'rank-ordered sum in the same run' if nvls else
+                                     'parameters bit-equal to the rank-ordered sum on every rank'),
+            'max_abs_diff_vs_rank_ordered_sum': float(d_ord.item()),
             'max_abs_diff_vs_nccl_allreduce': float(diff.item()),
             'against': 'all-gather + rank-ordered float32 sum + Adam launch (parallel.ORDERED_ALLREDUCE)'}
+
+
+def nvls_exchange(agent, world, torch, dist, device, n_updates=8):
+    """Several ranks: the NVLS form of the tile exchange (cur_xchg_ctx mode 2: multimem.ld_reduce through the NVSwitch,
+    one multicast store for the result) next to the default - per-rank update time, parameters identical on every rank,
+    distance to the rank-ordered sum (the in-switch summation order is the hardware's)."""
+    from curious_b200 import parallel
+    try:
+        a = agent.make_agent(grad_exchange='tile', xchg_mode='nvls')
+    except Exception as e:                      # no multicast support on this system / torch build
+        return {'unavailable': '%s: %s' % (type(e).__name__, str(e)[:200])}
+    for _ in range(n_updates):
+        a.train()
+    a.update_target_net()
+    torch.cuda.synchronize()
+    theta = a.theta_main.clone()
+    parallel.ORDERED_ALLREDUCE = True
+    b = agent.make_agent(grad_exchange='nccl')
+    for _ in range(n_updates):
+        b.train()
+    b.update_target_net()
+    torch.cuda.synchronize()
+    parallel.ORDERED_ALLREDUCE = False
+    diff = (theta - b.theta_main).abs().max()
+    dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    del b
+    ref = theta.clone()
+    dist.broadcast(ref, src=0)
+    bad = torch.tensor([0 if torch.equal(ref, theta) else 1], device=device)
+    dist.all_reduce(bad)
+    for _ in range(5):
+        a.train()
+    ms = time_updates(a.train, 200, torch)
+    tt = torch.tensor([ms], device=device, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    del a
+    torch.cuda.empty_cache()
+    dist.barrier()
+    b = agent.make_agent(grad_exchange='tile', xchg_mode=1 if world > 2 else 0)
+    for _ in range(5):
+        b.train()
+    ms1 = time_updates(b.train, 200, torch)
+    t1 = torch.tensor([ms1], device=device, dtype=torch.float64)
+    dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+    del b
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return {'per_rank_update_us': 1e3 * float(tt.item()), 'peer_memory_mode_per_rank_update_us': 1e3 * float(t1.item()),
+            'identical_on_every_rank': int(bad.item()) == 0,
+            'max_abs_diff_vs_rank_ordered_sum': float(diff.item()), 'updates': n_updates,
+            'what': 'tile exchange mode 2: partials in place, multimem.ld_reduce by the owning rank, Adam, one multicast '
+                    'store of the stepped parameters (csrc/ddpg_rows.cu, parallel.TileGradExchange(mode="nvls"))'}
 
 
 def run_ours(args):
@@ -681,7 +751,7 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     # ---- several ranks: how much one rank's update costs next to a world of one on the same GPU, and the parity check
-    scaling = parity = None
+    scaling = parity = nvls = None
     if world > 1:
         solo = agent.make_agent(comm=False)
         for _ in range(5):
@@ -696,6 +766,7 @@ def run_ours(args):
                    'what': 'device-timed train() of one rank alone (comm=False, same GPU, same run) / the same inside the '
                            '%d-rank job: the weak-scaling efficiency of the path that has a collective' % world}
         parity = exchange_parity(agent, world, rank, torch, dist, device)
+        nvls = nvls_exchange(agent, world, torch, dist, device)
     # ---- BASELINE config 4: the Arm8 shape (dimo 64, dimg 24, N 8, buffers 6..8 aliased), same measurements
     agent8, sampler8, buffers8, dims8, _, _ = build_gpu_workload(device, seed=50 + rank, n_modules=8)
     arm8 = measure_agent(agent8, dims8, 8, world, rank, barrier, torch, dist, device)
@@ -744,6 +815,7 @@ def run_ours(args):
         if scaling is not None:
             line['scaling_e2e'] = scaling
             line.update(parity)
+            line['nvls_exchange'] = nvls
         if her8 is not None:
             line['her_arm8'] = her8
         if world == 1 and not args.no_sweep:

@@ -104,7 +104,7 @@ CUR_MAX_RANKS = 8
 class XchgCtx(C.Structure):
     _fields_ = [('rank', C.c_int32), ('world', C.c_int32), ('mode', C.c_int32), ('_pad', C.c_int32),
                 ('region', C.c_void_p * CUR_MAX_RANKS), ('arena', C.c_int64), ('timeline', C.c_void_p),
-                ('error_flag', C.c_void_p)]
+                ('error_flag', C.c_void_p), ('mc_region', C.c_void_p)]
 
 
 class AdamFused(C.Structure):

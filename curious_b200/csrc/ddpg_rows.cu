@@ -856,6 +856,10 @@ struct XchgDev {
   int64_t arena;
   long long* tl;                             // optional [tiles][4] %globaltimer stamps
   int* error_flag;
+  // mode 2 (NVLS): the regions are ONE symmetric allocation with a multicast mapping - a load from part_mc is reduced by
+  // the NVSwitch over every rank's copy, a store to res_mc lands in every rank's copy
+  const float2* part_mc;                     // multicast alias of the partial slots [arena] {value, update number as float}
+  unsigned long long* res_mc;                // multicast alias of the result slots [arena]
 };
 
 __device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p) {
@@ -979,6 +983,36 @@ __device__ __forceinline__ void xchg_wait_result(const XchgDev& xc, uint32_t fla
     if (ok[e]) th[e] = __uint_as_float((uint32_t)x[e]);
 }
 
+// mode 2, the owner: ONE multimem.ld_reduce per element returns the switch-reduced sum of the world's {value, number}
+// pairs - the value half is the gradient sum, the number half equals world x number exactly once every rank's pair of
+// THIS update has landed (a pair is one naturally aligned 8-byte store; older pairs carry a smaller number).
+template <int NE>
+__device__ __forceinline__ void xchg_reduce_nvls(const XchgDev& xc, float want, const int64_t (&off)[NE],
+                                                 const bool (&ok)[NE], float (&g)[NE]) {
+  float sv[NE], sf[NE];
+  bool all;
+  unsigned int spins = 0;
+  unsigned long long t0 = 0;
+  do {
+    all = true;
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (ok[e])
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v2.f32 {%0, %1}, [%2];"
+                     : "=f"(sv[e]), "=f"(sf[e]) : "l"(xc.part_mc + off[e]) : "memory");
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (ok[e]) all = all && (sf[e] == want);
+    if (!all && (++spins & 0x3FFu) == 0) {
+      if (t0 == 0) t0 = globaltimer_ns();
+      xchg_timeout_check(t0, xc.error_flag);
+    }
+  } while (!all);
+#pragma unroll
+  for (int e = 0; e < NE; ++e)
+    if (ok[e]) g[e] = sv[e];
+}
+
 // The end of every weight-gradient element: local gradient (accumulated over micro-batches / K chunks), exchange with
 // the peers, Adam.  v[e] is the tile value of this launch, c[e] its place in the local gradient arena; th[e] returns
 // the stepped parameter (undefined unless cx.opt).
@@ -1008,6 +1042,14 @@ __device__ __forceinline__ void dw_finish(const DwTail& T, const DwCtx& cx, floa
           for (int e = 0; e < NE; ++e)
             if (ok[e]) st_ll(dst + off[e], v[e], cx.flag);
         }
+    } else if (xc.mode == 2) {
+      // NVLS: every rank (the owner too) publishes its partial in its OWN slots; the number travels as a float so that
+      // the switch can add it up (exact: world x 2^20 < 2^24)
+      const float nf = (float)((cx.flag & 0xFFFFFu) + 1u);
+      unsigned long long* dst = xc.part[xc.rank];
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        if (ok[e]) st_ll(dst + off[e], v[e], __float_as_uint(nf));
     } else if (!cx.own) {
       unsigned long long* dst = xc.part[cx.owner] + (int64_t)xc.rank * xc.arena;
 #pragma unroll
@@ -1015,7 +1057,8 @@ __device__ __forceinline__ void dw_finish(const DwTail& T, const DwCtx& cx, floa
         if (ok[e]) st_ll(dst + off[e], v[e], cx.flag);
     }
     if (cx.own) {
-      xchg_reduce<NE>(xc, cx.flag, off, ok, v);
+      if (xc.mode == 2) xchg_reduce_nvls<NE>(xc, (float)xc.world * (float)((cx.flag & 0xFFFFFu) + 1u), off, ok, v);
+      else xchg_reduce<NE>(xc, cx.flag, off, ok, v);
       if (cx.tl && threadIdx.x == 0) cx.tl[2] = (long long)globaltimer_ns();
     } else {
       xchg_wait_result<NE>(xc, cx.flag, off, ok, th);
@@ -1043,6 +1086,11 @@ __device__ __forceinline__ void dw_finish(const DwTail& T, const DwCtx& cx, floa
         for (int e = 0; e < NE; ++e)
           if (ok[e]) st_ll(xc.res[r] + off[e], th[e], cx.flag);
       }
+  } else if (cx.xc_on && T.xc.mode == 2) {
+    // one store to the multicast alias: the switch delivers the stepped parameter to every rank's result slot
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (ok[e]) st_ll(T.xc.res_mc + off[e], th[e], cx.flag);
   }
 }
 
@@ -1630,7 +1678,8 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   if (adam != nullptr && adam->xchg != nullptr && adam->xchg->world > 1) {
     const cur_xchg_ctx* x = adam->xchg;
     CUR_REQUIRE(x->world <= CUR_MAX_RANKS && x->rank >= 0 && x->rank < x->world, "bad rank / world of the exchange");
-    CUR_REQUIRE(x->mode == 0 || x->mode == 1, "bad exchange mode");
+    CUR_REQUIRE(x->mode >= 0 && x->mode <= 2, "bad exchange mode");
+    CUR_REQUIRE(x->mode != 2 || x->mc_region != nullptr, "exchange mode 2 needs the multicast mapping of the regions");
     CUR_REQUIRE(x->arena >= r4(LQ.total) + r4(LP.total), "exchange arena smaller than the gradient arena");
     T.xc_on = 1;
     T.xc.rank = x->rank; T.xc.world = x->world; T.xc.mode = x->mode; T.xc.arena = x->arena;
@@ -1638,8 +1687,10 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     for (int r = 0; r < x->world; ++r) {
       CUR_REQUIRE(x->region[r] != nullptr, "peer region not mapped");
       T.xc.part[r] = reinterpret_cast<unsigned long long*>(x->region[r]);
-      T.xc.res[r] = T.xc.part[r] + (int64_t)x->world * x->arena;
+      T.xc.res[r] = T.xc.part[r] + (int64_t)(x->mode == 2 ? 1 : x->world) * x->arena;
     }
+    T.xc.part_mc = reinterpret_cast<const float2*>(x->mc_region);
+    T.xc.res_mc = x->mc_region ? reinterpret_cast<unsigned long long*>(x->mc_region) + x->arena : nullptr;
   }
   T.tl = tl_on ? tl_dev : nullptr;
   const AdamCtx ax_full = T.ax;

@@ -75,6 +75,9 @@ class DDPG(object):
         # all-gather by stores, 'nccl' = NCCL all-reduce + Adam launch after the graph, 'auto' = tile when the rows
         # schedule runs on an NCCL (one GPU per rank) group
         self.grad_exchange = kwargs.get('grad_exchange', 'auto')
+        # mode of the in-launch tile exchange: 'auto' (0 for two ranks, 1 above), 0, 1, or 2 / 'nvls' (NVSwitch multicast:
+        # multimem.ld_reduce does the sum; parallel.TileGradExchange)
+        self.xchg_mode = kwargs.get('xchg_mode', 'auto')
         assert self.grad_exchange in ('auto', 'tile', 'p2p', 'p2p_sharded', 'nccl')
         self.xchg_timeline_tiles = int(kwargs.get('xchg_timeline_tiles', 0))      # debug: per-tile %globaltimer stamps
         # reference workers hosted by this rank (the 19 MPI workers become ceil(19 / G) workers per GPU):
@@ -689,7 +692,8 @@ class DDPG(object):
         kind = self._exchange_kind()
         if kind == 'tile':
             from .parallel import TileGradExchange
-            self._xchg = TileGradExchange(self.net.arena, self.comm, timeline_tiles=self.xchg_timeline_tiles)
+            self._xchg = TileGradExchange(self.net.arena, self.comm, mode=self.xchg_mode,
+                                          timeline_tiles=self.xchg_timeline_tiles)
         elif kind is not None:
             from .parallel import PeerGradExchange
             # the sharded exchange moves 8x fewer bytes at 8 GPUs but measured no faster (2 GPUs: 83 us full / 91 us
@@ -988,7 +992,7 @@ class DDPG(object):
         that reduces it: assemble the full vectors on every rank (COLLECTIVE - every rank saves its own checkpoint,
         train.py of this package; also needed before switching to another update path)."""
         x = getattr(self, '_xchg', None)
-        if x is None or x.mode != 1:
+        if x is None or x.mode not in (1, 2):
             return
         owner = np.empty(int(self.net.arena), np.int32)
         _lib.check(_lib.load().cur_ddpg_rows_owner_map(C.byref(self.net.desc), self._graph_rows, x.world,

@@ -390,9 +390,17 @@ int cur_ddpg_grads_group(void* stream, const cur_net_desc* d, int n_experts, con
  *           out per rank and update) and every rank keeps the full Adam state - best for 2 ranks;
  *   mode 1  tile t is reduced by rank t % world, which pushes the stepped parameters back to all peers (two hops,
  *           2 x (W-1)/W x arena x 8 bytes out per rank); Adam moments exist only on the owner of an element
- *           (cur_ddpg_rows_owner_map tells which) - best for 4..8 ranks.
- * Region of a rank (cur_p2p_alloc / cur_p2p_open, zero-initialised, cur_xchg_region_bytes bytes):
+ *           (cur_ddpg_rows_owner_map tells which) - best for 4..8 ranks;
+ *   mode 2  NVLS: as mode 1, but the owner reads the tile with multimem.ld_reduce - the NVSwitch adds the world's partials
+ *           (each rank keeps its partial in its OWN slots, {value, update number as float}: the number half of the reduced
+ *           word equals world x number once every rank's pair has landed) - and publishes the stepped parameters with ONE
+ *           store to the multicast mapping (mc_region).  (W-1)/W x arena x 8 bytes in, arena / W x 8 bytes out per rank
+ *           instead of 2 x (W-1)/W x arena x 8 each way; the order of the in-switch summation is the hardware's, so the
+ *           parameters are identical on every rank but not bit-equal to the rank-ordered sum of modes 0 / 1.
+ * Region of a rank (zero-initialised): modes 0 / 1 (cur_p2p_alloc / cur_p2p_open, cur_xchg_region_bytes bytes)
  *   [ partial slots: world x arena x 8 bytes, block s written by rank s | result slots: arena x 8 bytes ]
+ * mode 2 (symmetric memory with a multicast mapping)
+ *   [ partial slots: arena x 8 bytes, written by the rank itself | result slots: arena x 8 bytes ]
  * The update number travelling with the data is (device step counter / micro_batches) + 1; it never repeats as long
  * as the counter only grows (zero the regions collectively before moving the counter backwards).  A rank that waits
  * longer than ~20 s for a peer sets *error_flag (if given) and traps. */
@@ -405,6 +413,8 @@ typedef struct cur_xchg_ctx {
   int64_t* timeline;           /* optional DEVICE buffer [tiles][4] of %globaltimer stamps (ns): CTA start, tile computed and
                                   pushed, reduced tile available (partials landed / result landed), CTA end */
   int32_t* error_flag;         /* optional device int */
+  void* mc_region;             /* mode 2: the multicast (NVLS) mapping of the regions - one symmetric allocation, e.g.
+                                  torch.distributed._symmetric_memory (rendezvous(...).multicast_ptr); NULL otherwise */
 } cur_xchg_ctx;
 int64_t cur_xchg_region_bytes(int64_t arena_floats, int world);
 
