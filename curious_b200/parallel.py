@@ -237,8 +237,10 @@ class TileGradExchange(object):
             mode = 2
         auto = mode == 'auto'
         if auto:
-            # measured per-rank update (us), modes 0 / 1 / 2: 2 GPUs 68.0 / 71.5 / 70.8, 8 GPUs 99.6 / 74.3 / 71.7
-            mode = 0 if n == 2 else 2
+            # measured per-rank update (us), modes 0 / 1 / 2: 2 GPUs 68.0 / 71.5 / 70.8, 8 GPUs 99.6 / 74.3 / 71.7.  The NVLS
+            # form (2) is the fastest from 4 ranks but stays opt-in (xchg_mode='nvls', CUR_XCHG_MODE=2, CUR_XCHG_AUTO_NVLS=1):
+            # its sum is not in rank order, and its setup depends on the system's multicast support
+            mode = 0 if n == 2 else (2 if os.environ.get('CUR_XCHG_AUTO_NVLS') == '1' else 1)
         assert mode in (0, 1, 2)
         self.mode = mode
         self.ctx = _lib.XchgCtx()

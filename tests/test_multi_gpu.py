@@ -83,7 +83,7 @@ def _worker(rank, world, port, use_graph, out_dir, grad_exchange='auto', workers
             assert (agent._xchg is not None) == (kind == 'tile'), 'wrong gradient exchange path'
             assert (agent._peer is not None) == (kind in ('p2p', 'p2p_sharded')), 'wrong gradient exchange path'
             if agent._xchg is not None:
-                assert agent._xchg.mode == (xchg_mode if xchg_mode is not None else (0 if world == 2 else 2))
+                assert agent._xchg.mode == (xchg_mode if xchg_mode is not None else (0 if world == 2 else 1))
                 assert int(agent._xchg.error_flag.item()) == 0
             if agent._peer is not None:
                 agent._peer.check()
