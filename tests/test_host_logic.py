@@ -322,7 +322,8 @@ def test_host_draws_replay_the_reference_stream():
 def test_library_sass_is_blackwell_native():
     """B200_PROFILING.md "What proves a Blackwell-native kernel": the SASS of the in-tree library holds tcgen05 MMAs
     (UTC*MMA) with TMEM loads (LDTM), TMA tensor and bulk copies (UTMALDG / UBLKCP) with their mbarrier waits (SYNCS), the
-    cta_group::2 commit of the pair kernel (UTCBAR.2CTA) and packed FP32 FMAs (FFMA2) - and no legacy HMMA tensor path."""
+    cta_group::2 commit of the pair kernel (UTCBAR.2CTA), packed FP32 FMAs (FFMA2) and the in-switch reduction of the NVLS
+    gradient exchange (multimem.ld_reduce = LDGMC.E.ADD) inside the weight-gradient kernel - and no legacy HMMA tensor path."""
     import shutil
     import subprocess
     from curious_b200 import _lib
@@ -336,6 +337,7 @@ def test_library_sass_is_blackwell_native():
     assert count(r'\bUTC[A-Z]*MMA') >= 6                 # 3xTF32: three MMAs per k-step, single-CTA and pair kernels
     assert count(r'\bLDTM') >= 8 and count(r'\bUTMALDG') >= 8 and count(r'\bUBLKCP') >= 1
     assert count(r'\bUTCBAR\.2CTA') >= 1 and count(r'\bSYNCS\.') >= 20 and count(r'\bFFMA2\b') >= 500
+    assert count(r'\bLDGMC\.E\.ADD\.F32') >= 3         # FULLK / SKINNY / COLSUM tile epilogues of rows_dw_kernel
     assert count(r'\bHMMA\b') == 0 and count(r'\bHGMMA\b') == 0
 
 
