@@ -223,9 +223,9 @@ def build_gpu_workload(device, seed, n_modules=N_MODULES):
     gamma = 1. - 1. / T
     cp = np.array(CP if n_modules == 4 else CP8)
 
-    def make_agent(batch_size=BATCH, structure='curious', task_replay='replay_task_cp_buffer', **extra):
+    def make_agent(batch_size=BATCH, structure='curious', task_replay='replay_task_cp_buffer', hidden=256, **extra):
         extra.setdefault('grad_exchange', os.environ.get('CUR_GRAD_EXCHANGE', 'auto'))
-        a = DDPG(input_dims=dims, hidden=256, layers=3, network_class='baselines.her.actor_critic:MultiTaskActorCritic',
+        a = DDPG(input_dims=dims, hidden=hidden, layers=3, network_class='baselines.her.actor_critic:MultiTaskActorCritic',
                  polyak=0.95, batch_size=batch_size, Q_lr=0.001, pi_lr=0.001, norm_eps=0.01, norm_clip=5, max_u=1.,
                  action_l2=1.0, clip_obs=200., scope='ddpg', T=T, rollout_batch_size=2,
                  subtract_goals=lambda a, b: a - b, relative_goals=False, clip_pos_returns=True,
@@ -305,6 +305,18 @@ def large_batch_sweep(agent, dims, torch):
         if b != BATCH:
             del a
             torch.cuda.empty_cache()
+    # hidden widths other than the default (config.py:25): zero-padded onto the 256-wide kernels (DDPG pad_hidden) next to
+    # the dependency-level kernels at the true width
+    widths = []
+    for h in (64, 128):
+        rec = {'hidden': h, 'batch': BATCH}
+        for tag, kw in (('padded_rows_update_us', dict(pad_hidden='auto')), ('levels_update_us', dict(pad_hidden=False))):
+            a = agent.make_agent(hidden=h, **kw)
+            rec[tag] = 1e3 * time_updates(a.train, 200, torch)
+            rec[tag.replace('update_us', 'schedule')] = schedule_name(a, BATCH)
+            del a
+            torch.cuda.empty_cache()
+        widths.append(rec)
     experts = []
     for b in (256, 4096):
         ps = [agent.make_agent(batch_size=b, structure='task_experts', task_replay='replay_current_task_buffer', t_id=t,
@@ -317,7 +329,7 @@ def large_batch_sweep(agent, dims, torch):
                         'mode': 'sequential rows' if all(p._use_rows(b) for p in ps) else 'grouped levels'})
         del grp, ps
         torch.cuda.empty_cache()
-    return {'batch_sweep': sweep, 'task_experts': experts, 'tf32_peak_tflops_assumed': bf16 / 2}
+    return {'batch_sweep': sweep, 'hidden_widths': widths, 'task_experts': experts, 'tf32_peak_tflops_assumed': bf16 / 2}
 
 
 def her_step_segments(buffers, rows, cp):

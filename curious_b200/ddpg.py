@@ -68,6 +68,10 @@ class DDPG(object):
         # level) or 'auto' (rows whenever the shape is supported)
         self.update_schedule = kwargs.get('update_schedule', 'auto')
         self.fuse_her = kwargs.get('fuse_her', True)      # rows schedule: sample inside the update kernel
+        # hidden widths below 256 (config.py:25 is a user parameter): 'auto' = run zero-padded to 256 on the hand-written
+        # row / chain / action kernels whenever they take the padded shape (actor_critic._NetSpec; same results, 59 instead
+        # of 140 us per batch-256 update), True = always, False = never (dependency-level kernels at the true width)
+        self.pad_hidden = kwargs.get('pad_hidden', 'auto')
         # several ranks: 'tile' = the gradient tiles are exchanged over NVLink peer memory INSIDE the weight-gradient
         # launch, Adam and W^T stay in its epilogue (csrc/ddpg_rows.cu, parallel.TileGradExchange: 2 launches per update
         # like one rank), 'p2p' = one exchange + Adam kernel after the weight-gradient launch (csrc/p2p.cu: every rank
@@ -142,12 +146,22 @@ class DDPG(object):
     # ------------------------------------------------------------------------------------------
     def _create_network(self, reuse=False):
         dev = self.device
-        self.net = self.create_actor_critic(dimo=self.dimo, dimg=self.dimg, dimu=self.dimu, dimtd=self.dimtd,
-                                            max_u=self.max_u, hidden=self.hidden, layers=self.layers,
-                                            normalize_obs=self.normalize_obs, norm_clip=self.norm_clip)
+        mk = lambda kh: self.create_actor_critic(dimo=self.dimo, dimg=self.dimg, dimu=self.dimu, dimtd=self.dimtd,
+                                                 max_u=self.max_u, hidden=self.hidden, layers=self.layers,
+                                                 normalize_obs=self.normalize_obs, norm_clip=self.norm_clip,
+                                                 kernel_hidden=kh)
+        self.net = mk(None)
+        if self.pad_hidden and self.hidden < self.KERNEL_HIDDEN and self.update_schedule != 'levels':
+            wide = mk(self.KERNEL_HIDDEN)
+            rows = self.batch_size * max(1, int(getattr(self, 'workers_per_rank', 1)))
+            if self.pad_hidden is True or _lib.load().cur_ddpg_rows_supported(C.byref(wide.desc), min(rows, 256)):
+                self.net = wide
         if self.net.modular != self.modular:
             raise ValueError('network_class %s does not fit structure %r' % (self.network_class, self.structure))
         net = self.net
+        self._ref_idx = None
+        if net.padded:
+            self._ref_idx = {w: torch.from_numpy(net.ref_index(w)).to(dev) for w in ('Q', 'pi')}
         # running averages (ddpg.py:402-409)
         # both normalisers accumulate into ONE packed buffer [sum_o|sumsq_o|count_o|sum_g|sumsq_g|count_g]: one collective
         # per store_episode (normalizer.recompute_stats_packed)
@@ -210,13 +224,26 @@ class DDPG(object):
                     chunks.append(np.zeros(s, np.float32))
             self.set_flat(which, np.concatenate(chunks))
 
+    KERNEL_HIDDEN = 256        # width of the hand-written row / chain / action kernels
+
+    def ref_flat(self, arena, which):
+        """The `which` net of an arena-shaped tensor (parameters, gradients, Adam moments) as a device vector in the
+        reference's GetFlat order - a view, or a gather when the net runs zero-padded."""
+        v = self._view(arena, which)
+        return v if self._ref_idx is None else v[self._ref_idx[which]]
+
     # flat parameter access in GetFlat order (tf_util.py:221-244)
     def get_flat(self, which, target=False):
-        return self._view(self.theta_target if target else self.theta_main, which).detach().cpu().numpy().copy()
+        return self.ref_flat(self.theta_target if target else self.theta_main, which).detach().cpu().numpy().copy()
 
     def set_flat(self, which, values, target=False):
-        v = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float32))
-        self._view(self.theta_target if target else self.theta_main, which).copy_(v.to(self.device))
+        v = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float32)).to(self.device)
+        dst = self._view(self.theta_target if target else self.theta_main, which)
+        if self._ref_idx is None:
+            dst.copy_(v)
+        else:
+            dst.zero_()                                   # the padding stays exactly zero
+            dst[self._ref_idx[which]] = v
         self._wT_dirty = True
 
     def _workspace(self, n):
@@ -1009,7 +1036,7 @@ class DDPG(object):
         state, replay data and RNG position are lost on restart.  One torch.save file, tensors on the host."""
         self._gather_adam_state()
         cpu = lambda t: t.detach().cpu().clone()
-        st = dict(format=1, arena=int(self.net.arena), theta_main=cpu(self.theta_main), theta_target=cpu(self.theta_target),
+        st = dict(format=1, arena=int(self.net.arena), net=self._net_signature(), theta_main=cpu(self.theta_main), theta_target=cpu(self.theta_target),
                   adam_m=cpu(self._adam_m), adam_v=cpu(self._adam_v), adam_t=(int(self.Q_adam.t), int(self.pi_adam.t)),
                   step=int(self._step.item()), n_updates=int(self._n_updates),
                   sampler=dict(calls=int(self.sample_transitions.calls), seed=int(self.sample_transitions.seed)),
@@ -1027,12 +1054,20 @@ class DDPG(object):
                     cold=None if b.cold is None else cpu(b.cold[:n * L.T * L.cold_stride])))
         torch.save(st, path)
 
+    def _net_signature(self):
+        """What has to agree between a checkpoint and the agent it is loaded into (a hidden-64 net zero-padded to the
+        kernels' width has the arena size of a hidden-256 one)."""
+        n = self.net
+        return (bool(n.modular), int(n.dimo), int(n.dimg), int(n.dimu), int(n.dimtd), int(n.hidden), int(n.kernel_hidden),
+                int(n.layers))
+
     def load_checkpoint(self, path):
         """Inverse of save_checkpoint on an agent built with the same arguments (checked: arena size, buffer layouts)."""
         st = torch.load(path, map_location='cpu', weights_only=False)
-        if st.get('format') != 1 or st['arena'] != int(self.net.arena):
-            raise ValueError('checkpoint %s does not fit this agent (arena %s vs %d)' % (path, st.get('arena'),
-                                                                                      self.net.arena))
+        if st.get('format') != 1 or st['arena'] != int(self.net.arena) or st.get('net', self._net_signature()) != \
+                self._net_signature():
+            raise ValueError('checkpoint %s does not fit this agent (arena %s vs %d, network %s vs %s)' % (
+                path, st.get('arena'), self.net.arena, st.get('net'), self._net_signature()))
         if getattr(self, '_peer', None) is not None and st['step'] < int(self._step.item()):
             # the peer-memory exchange counts updates in its NVLink flags (csrc/p2p.cu): they cannot run backwards
             raise ValueError('load the checkpoint into a freshly built agent when the peer-memory exchange is active')
