@@ -361,3 +361,33 @@ def test_owner_map_of_the_tile_exchange_covers_every_parameter():
             assert owner[real].max() == world - 1
             counts = np.bincount(owner[real], minlength=world)
             assert counts.min() > 0.8 * counts.mean()
+
+
+def test_zero_padded_network_index_map():
+    """actor_critic._NetSpec(kernel_hidden=256): where every element of the reference's flat vector (hidden wide) sits in
+    the 256-wide kernel-side vector - injective, inside the padded net, rows / columns of every layer preserved."""
+    from curious_b200.actor_critic import ActorCritic, MultiTaskActorCritic
+    for cls, kw in ((MultiTaskActorCritic, dict(dimtd=4)), (ActorCritic, {})):
+        for hidden, layers in ((64, 3), (128, 2), (60, 4)):
+            net = cls(40, 12, 4, 1.0, hidden, layers, kernel_hidden=256, **kw)
+            assert net.padded and net.desc.hidden == 256
+            for which, n_pad in (('Q', net.n_Q), ('pi', net.n_pi)):
+                idx = net.ref_index(which)
+                ref = [int(np.prod(s)) for s in net.var_shapes(which)]
+                assert idx.size == sum(ref) and len(set(idx.tolist())) == idx.size and idx.max() < n_pad
+                # walk the layers: element (i, j) of a [r, c] kernel lands at base + i * padded_c + j
+                flat = np.arange(sum(ref), dtype=np.float64) + 1.0
+                padded = np.zeros(n_pad)
+                padded[idx] = flat
+                k = kp = 0
+                for s, ps in zip(net.var_shapes(which), net.var_shapes(which, 256)):
+                    a = flat[k:k + int(np.prod(s))].reshape(s)
+                    b = padded[kp:kp + int(np.prod(ps))].reshape(ps)
+                    if len(s) == 2:
+                        assert np.array_equal(b[:s[0], :s[1]], a) and b[s[0]:].sum() == 0 and b[:, s[1]:].sum() == 0
+                    else:
+                        assert np.array_equal(b[:s[0]], a) and b[s[0]:].sum() == 0
+                    k += int(np.prod(s))
+                    kp += int(np.prod(ps))
+        same = cls(40, 12, 4, 1.0, 256, 3, kernel_hidden=256, **kw)
+        assert not same.padded and np.array_equal(same.ref_index('Q'), np.arange(same.n_Q))
