@@ -35,9 +35,7 @@ int sm_count() {
   return cached;
 }
 
-constexpr int TILE = 32;         // transitions per CTA
-constexpr int HER_THREADS = 128;
-constexpr int HER_WARPS = HER_THREADS / 32;
+// CTA shape of the sampling kernel: TILE transitions, HER_THREADS threads (template parameters of the kernel)
 
 struct HerKernelParams {
   cur_her_args a;
@@ -121,8 +119,10 @@ __device__ __forceinline__ void emit2(float* __restrict__ outa, float* __restric
 //   (o, o_2, u, ag, ag_2, change, info: warps 1 - 3) | the relabelled outputs (g, g_2, task_descr: all warps).
 // (A persistent double-buffered variant - draws and gather of tile i+1 issued before tile i is waited for - was measured
 // slower, 70 % vs 81 % of the HBM peak: throughput follows the number of resident tiles per SM, profiles/README.md.)
+template <int TILE, int HER_THREADS>
 __global__ void __launch_bounds__(HER_THREADS)
 her_sample_kernel(const __grid_constant__ HerKernelParams P) {
+  constexpr int HER_WARPS = HER_THREADS / 32;
   const cur_her_args& a = P.a;
   const cur_layout& L = a.L;
   const HerPlan& pl = P.p;
@@ -423,17 +423,20 @@ extern "C" int cur_her_sample(void* stream, const cur_her_args* args) {
   if (P.p.cold4 > 0)
     for (int i = 0; i < a.n_segments; ++i)
       CUR_REQUIRE(a.seg[i].count == 0 || a.seg[i].cold != nullptr, "change/info/ag requested but segment has no cold rows");
+  // CTA shape: 32 rows / 128 threads.  16 / 64 and 32 / 64 measured the same (Arm4 0.827 / 0.828 vs 0.830 of the HBM peak),
+  // 16 / 128 slower (0.655): at full size the kernel sits at the DRAM pipe, not at its own latency (profiles/README.md)
+  constexpr int TILE = 32, THREADS = 128;
   size_t smem = (size_t)TILE * P.p.stage_stride * 4 + 3 * TILE * sizeof(void*) + 16;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     CUR_REQUIRE(smem <= 227 * 1024, "row too large for the shared-memory stage");
-    CUR_CUDA_TRY(cudaFuncSetAttribute(her_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUR_CUDA_TRY(cudaFuncSetAttribute(her_sample_kernel<TILE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     configured = smem;
   }
   const int64_t blocks = (a.batch + TILE - 1) / TILE;
   CUR_REQUIRE(blocks <= 0x7fffffff, "batch too large for one launch");
-  her_sample_kernel<<<(unsigned)blocks, HER_THREADS, smem, (cudaStream_t)stream>>>(P);
+  her_sample_kernel<TILE, THREADS><<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(P);
   CUR_CHECK_LAUNCH();
   return CUR_OK;
 }
