@@ -154,6 +154,8 @@ SIGNATURES = {
     'cur_ddpg_actions_rows': (C.c_int, [C.c_void_p, C.POINTER(NetDesc), C.c_void_p, C.POINTER(NormStats), C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
                                         C.c_uint32]),
+    'cur_actions_finish_host': (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int64]),
     'cur_host_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     'cur_host_free': (C.c_int, [C.c_void_p]),
     'cur_copy_h2d': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),

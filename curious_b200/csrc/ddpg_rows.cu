@@ -1873,3 +1873,52 @@ extern "C" int cur_host_free(void* host_ptr) {
   if (host_ptr) CUR_CUDA_TRY(cudaFreeHost(host_ptr));
   return CUR_OK;
 }
+
+static inline float __uint_as_float_host(uint32_t b) {
+  float f;
+  memcpy(&f, &b, sizeof(f));
+  return f;
+}
+
+// Host-side tail of the zero-copy action path (DDPG.get_actions, ddpg.py:147-155): wait until every one of the n_out
+// 8-byte output words {float32 bits | seq << 32} written by actions_stream_kernel carries this call's number, then apply
+// the reference's post-processing with the caller's draws (np.random, taken in reference order while the launch was in
+// flight).  The arithmetic restates NumPy's evaluation of the reference statements, type for type:
+//   u += noise_eps * max_u * randn           float32 array += float64 array: float64 add, rounded to float32
+//   u = clip(u, -max_u, max_u)               float32 (the Python float bound is a weak scalar)
+//   u += explore[:, None] * (u_rand - u)     int64 * (float64 - float32) -> float64 add, rounded to float32
+// Returns CUR_OK, or CUR_ERR_UNSUPPORTED if the words did not arrive within max_spins polls (the caller synchronises the
+// stream to let a launch failure surface and calls again).  No CUDA call is made here.
+extern "C" int cur_actions_finish_host(const void* out_words, int64_t n, int dimu, int with_q, uint32_t seq,
+                                       const double* randn, const int64_t* explore, const double* u_rand, double noise_scale,
+                                       double max_u, float* u_out, float* q_out, int64_t max_spins) {
+  CUR_REQUIRE(out_words && u_out && n > 0 && dimu > 0, "bad argument");
+  CUR_REQUIRE(!with_q || q_out, "q_out required");
+  CUR_REQUIRE((randn == nullptr) == (explore == nullptr) && (randn == nullptr) == (u_rand == nullptr),
+              "the three draws come together");
+  const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(out_words);
+  const int64_t n_pi = n * dimu, n_out = n_pi + (with_q ? n : 0);
+  int64_t spins = 0, done = 0;
+  while (done < n_out) {
+    if ((uint32_t)(w[done] >> 32) == seq) { ++done; continue; }
+    if (++spins > max_spins) return CUR_ERR_UNSUPPORTED;
+  }
+  const float lim = (float)max_u;
+  for (int64_t r = 0; r < n; ++r) {
+    for (int j = 0; j < dimu; ++j) {
+      const int64_t i = r * dimu + j;
+      float u = __uint_as_float_host((uint32_t)w[i]);
+      if (randn != nullptr) {
+        const double noise = noise_scale * randn[i];
+        u = (float)((double)u + noise);
+        if (u < -lim) u = -lim;                       // np.maximum / np.minimum: NaN stays NaN
+        if (u > lim) u = lim;
+        const double step = (double)explore[r] * (u_rand[i] - (double)u);
+        u = (float)((double)u + step);
+      }
+      u_out[i] = u;
+    }
+    if (with_q) q_out[r] = __uint_as_float_host((uint32_t)w[n_pi + r]);
+  }
+  return CUR_OK;
+}

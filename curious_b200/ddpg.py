@@ -316,13 +316,26 @@ class DDPG(object):
             slot['val'] = words[:, 0]                              # float32 values: n * dimu actions, then n Q values
             slot['tag'] = words[:, 1].view(np.uint32)              # the call number each word was written by
             slot['d_q'] = slot['d_out'] + 8 * n * self.dimu
+            slot['h_out'] = hp.value + (slot['d_out'] - dp.value)
+            # host post-processing (cur_actions_finish_host): the caller's draws and the finished float32 [pi | q]
+            slot['randn'] = np.empty((n, self.dimu), np.float64)
+            slot['explore'] = np.empty(n, np.int64)
+            slot['u_rand'] = np.empty((n, self.dimu), np.float64)
+            slot['fin'] = np.empty(n * (self.dimu + 1), np.float32)
+            slot['fin_u'] = slot['fin'][:n * self.dimu].reshape(n, self.dimu)
+            slot['fin_q'] = slot['fin'][n * self.dimu:].reshape(n, 1)
+            for name in ('randn', 'explore', 'u_rand', 'fin'):
+                slot['p_' + name] = slot[name].ctypes.data
+            slot['p_fin_q'] = slot['p_fin'] + 4 * n * self.dimu
+            slot['refs'] = (C.byref(self.net.desc), C.byref(self._stats))
             self._action_slots[n] = slot
         return slot
 
     def _actions_one_launch(self, o, ag, g, task_descr, n, theta, compute_Q, device_noise, noise_eps, random_eps):
         """cur_ddpg_actions_rows: inputs read from / actions written to mapped pinned memory by the kernel; completion =
-        every output word carries this call's number (no copies, no stream synchronisation, no fence).  Returns the flat
-        [pi | q] host array."""
+        every output word carries this call's number (no copies, no stream synchronisation, no fence).  Returns
+        (result, finished): the finished get_actions result on the zero-copy path (post-processing included), else the
+        flat [pi | q] host array that `_finish_actions` still has to post-process."""
         lib = _lib.load()
         slot = self._action_slot(n)
         np.copyto(slot['o'], o.reshape(-1))
@@ -356,22 +369,36 @@ class DDPG(object):
                 _lib.check(lib.cur_action_noise(_lib.stream_ptr(), out.data_ptr(), n, self.dimu, float(self.max_u),
                                                 float(noise_eps), float(random_eps), int(self.noise_seed) & (2 ** 64 - 1),
                                                 self._action_calls), 'cur_action_noise')
-            return out[:n_out].cpu().numpy()
+            return out[:n_out].cpu().numpy(), False
         slot['seq'] = seq = slot['seq'] % 0xFFFFFFF0 + 1
+        desc_ref, stats_ref = slot['refs']
         _lib.check(lib.cur_ddpg_actions_rows(
-            _lib.stream_ptr(), C.byref(self.net.desc), theta.data_ptr(), C.byref(self._stats), slot['d_o'],
+            _lib.stream_ptr(), desc_ref, theta.data_ptr(), stats_ref, slot['d_o'],
             slot['d_ag'] if self.relative_goals else None, slot['d_g'], slot['d_td'] if self.modular else None, n,
             float(self.clip_obs), slot['d_out'], slot['d_q'] if compute_Q else None, seq), 'cur_ddpg_actions_rows')
-        tag = slot['tag'][:n_out]
-        last = n_out - 1
-        spins = 0
-        while tag[last] != seq or not (tag == seq).all():
-            spins += 1
-            if spins > 200000:                     # ~0.1 s without an answer: let a launch failure surface, then give up
-                torch.cuda.current_stream().synchronize()
-                if not (tag == seq).all():
-                    raise RuntimeError('cur_ddpg_actions_rows did not complete')
-        return slot['val'][:n_out].copy()
+        # The host RNG draws of ddpg.py:148-151 do not depend on the kernel's answer: take them (in reference order) while
+        # the launch is in flight - ~10 us of NumPy calls hidden behind ~15 us of launch latency + weight stream.  The
+        # arithmetic on the answer is one C call (cur_actions_finish_host: poll the words, NumPy's own evaluation types).
+        p_randn = p_explore = p_u_rand = None
+        if not device_noise:
+            randn, explore, u_rand = self._draw_action_noise(n, random_eps)
+            np.copyto(slot['randn'], randn)
+            np.copyto(slot['explore'], explore)
+            np.copyto(slot['u_rand'], u_rand)
+            p_randn, p_explore, p_u_rand = slot['p_randn'], slot['p_explore'], slot['p_u_rand']
+        finish = (slot['h_out'], n, self.dimu, 1 if compute_Q else 0, seq, p_randn, p_explore, p_u_rand,
+                  float(noise_eps) * float(self.max_u), float(self.max_u), slot['p_fin'],
+                  slot['p_fin_q'] if compute_Q else None, 20000000)          # ~0.1 s of polls
+        status = lib.cur_actions_finish_host(*finish)
+        if status == 3:                     # no answer: let a launch failure surface, then give up
+            torch.cuda.current_stream().synchronize()
+            status = lib.cur_actions_finish_host(*finish)
+            if status == 3:
+                raise RuntimeError('cur_ddpg_actions_rows did not complete')
+        _lib.check(status, 'cur_actions_finish_host')
+        u = slot['fin_u']
+        u = u[0].copy() if n == 1 else u.copy()                                            # ddpg.py:152-154
+        return ([u, slot['fin_q'].copy()] if compute_Q else u), True
 
     CHAIN_MIN_ROWS = 1024      # update_schedule='auto': rows schedule below, tcgen05 chain kernel from here
     ACTION_ROWS_MAX = 512      # rows per call served by the one-launch path (one CTA per 4 rows)
@@ -388,10 +415,11 @@ class DDPG(object):
         theta = self.theta_target if use_target_net else self.theta_main
         device_noise = self.action_noise == 'device'
         if n <= self.ACTION_ROWS_MAX and self._action_rows_ok():
-            res = self._actions_one_launch(o, ag, g, task_descr, n, theta, compute_Q, device_noise, noise_eps, random_eps)
+            res, finished = self._actions_one_launch(o, ag, g, task_descr, n, theta, compute_Q, device_noise, noise_eps,
+                                                     random_eps)
             if device_noise:
                 self._action_calls += 1
-            return self._finish_actions(res, n, compute_Q, device_noise, noise_eps, random_eps)
+            return res if finished else self._finish_actions(res, n, compute_Q, device_noise, noise_eps, random_eps)
         parts = [o, g]
         if self.relative_goals:
             parts.append(np.asarray(ag, np.float32).reshape(-1, self.dimag))
@@ -437,15 +465,21 @@ class DDPG(object):
                                      _lib.load().cur_ddpg_rows_supported(C.byref(self.net.desc), 4))
         return self._action_rows
 
+    def _draw_action_noise(self, n, random_eps):
+        """The host RNG draws of ddpg.py:148-151 in the order the reference consumes np.random: randn (Gaussian noise),
+        binomial (which rows act randomly), uniform (_random_action) - also when the eps are 0, like the reference."""
+        return np.random.randn(n, self.dimu), np.random.binomial(1, random_eps, n), self._random_action(n)
+
     def _finish_actions(self, res, n, compute_Q, device_noise, noise_eps, random_eps):
-        """Action postprocessing (ddpg.py:147-155) on the flat [pi | q] host array `res` (owned by this call): host RNG
-        consumed in reference order (randn, binomial, uniform - also when the eps are 0, like the reference)."""
+        """Action postprocessing (ddpg.py:147-155) on the flat [pi | q] host array `res` (owned by this call); the
+        zero-copy path does the same arithmetic in cur_actions_finish_host (compared in tests/test_host_logic.py)."""
         u = res[:n * self.dimu].reshape(n, self.dimu)
         if not device_noise:
-            u += noise_eps * self.max_u * np.random.randn(n, self.dimu)                    # ddpg.py:148-149
+            randn, explore, u_rand = self._draw_action_noise(n, random_eps)
+            u += noise_eps * self.max_u * randn                                             # ddpg.py:148-149
             lim = self.max_u
             np.minimum(np.maximum(u, -lim, out=u), lim, out=u)                              # np.clip, ddpg.py:150
-            u += np.random.binomial(1, random_eps, n).reshape(-1, 1) * (self._random_action(n) - u)   # ddpg.py:151
+            u += explore.reshape(-1, 1) * (u_rand - u)                                      # ddpg.py:151
         u = u[0].copy() if n == 1 else u.copy()                                            # ddpg.py:152-154
         if not compute_Q:
             return u

@@ -282,6 +282,17 @@ int cur_ddpg_actions(void* stream, const cur_net_desc* d, const float* theta,
 int cur_ddpg_actions_rows(void* stream, const cur_net_desc* d, const float* theta, const cur_norm_stats* stats,
                           const float* o, const float* ag /* or NULL */, const float* g, const float* td, int64_t n,
                           float clip_obs, void* out_pi, void* out_q /* or NULL */, uint32_t seq);
+/* Host-side tail of a seq != 0 call of cur_ddpg_actions_rows (ddpg.py:147-155): polls the n * dimu (+ n with_q) output
+ * words in the mapped buffer until all carry `seq`, then applies the reference's exploration post-processing with the
+ * caller's np.random draws (randn [n, dimu] float64, explore [n] int64 = binomial(1, random_eps), u_rand [n, dimu] float64 =
+ * uniform(-max_u, max_u); all three NULL: no post-processing, e.g. device-side noise) in NumPy's own evaluation types:
+ *   u = (float)((double)u + noise_scale * randn); u = clip(u, +-(float)max_u); u = (float)((double)u + explore * (u_rand - u))
+ * with noise_scale = noise_eps * max_u.  Writes float32 u_out [n, dimu] and q_out [n].  CUR_ERR_UNSUPPORTED: the words did
+ * not arrive within max_spins polls (synchronise the stream so that a launch failure surfaces, then call again).
+ * Pure host code: no CUDA call, no device work. */
+int cur_actions_finish_host(const void* out_words, int64_t n, int dimu, int with_q, uint32_t seq, const double* randn,
+                            const int64_t* explore, const double* u_rand, double noise_scale, double max_u, float* u_out,
+                            float* q_out /* or NULL */, int64_t max_spins);
 /* cudaHostAlloc(mapped | portable): *host_ptr for the CPU, *dev_ptr for the kernels; zero-filled. */
 int cur_host_alloc(int64_t bytes, void** host_ptr, void** dev_ptr);
 int cur_host_free(void* host_ptr);

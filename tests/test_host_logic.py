@@ -391,3 +391,54 @@ def test_zero_padded_network_index_map():
                     kp += int(np.prod(ps))
         same = cls(40, 12, 4, 1.0, 256, 3, kernel_hidden=256, **kw)
         assert not same.padded and np.array_equal(same.ref_index('Q'), np.arange(same.n_Q))
+
+
+def _reference_action_postprocessing(u, randn, explore, u_rand, noise_eps, max_u):
+    """ddpg.py:147-151 as NumPy evaluates the reference statements on the float32 policy output."""
+    u = u.copy()
+    noise = noise_eps * max_u * randn
+    u += noise
+    u = np.clip(u, -max_u, max_u)
+    u += explore.reshape(-1, 1) * (u_rand - u)
+    return u
+
+
+@pytest.mark.parametrize('n,dimu,with_q', [(1, 4, False), (2, 4, False), (2, 4, True), (38, 4, True), (7, 3, True)])
+def test_host_action_tail_equals_the_reference_statements(n, dimu, with_q):
+    """cur_actions_finish_host (the host tail of the zero-copy get_actions path, pure host code) against the reference's own
+    NumPy statements, bit for bit: float32 += float64, float32 clip, int64 * (float64 - float32)."""
+    from curious_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(n * 10 + dimu)
+    for trial in range(20):
+        seq = 1 + trial
+        max_u = [1.0, 0.7, 2.5][trial % 3]
+        noise_eps = [0.2, 0.0, 1.3][trial % 3]
+        u = (max_u * np.tanh(rng.randn(n, dimu) * 2)).astype(np.float32)
+        q = rng.randn(n).astype(np.float32)
+        words = np.zeros((n * (dimu + 1), 2), np.uint32)
+        words[:n * dimu, 0] = u.reshape(-1).view(np.uint32)
+        words[n * dimu:, 0] = q.view(np.uint32)
+        words[:n * dimu + (n if with_q else 0), 1] = seq
+        randn = rng.randn(n, dimu)
+        explore = rng.binomial(1, 0.3, n).astype(np.int64)
+        u_rand = rng.uniform(-max_u, max_u, (n, dimu))
+        u_out = np.full((n, dimu), np.nan, np.float32)
+        q_out = np.full(n, np.nan, np.float32)
+        rc = lib.cur_actions_finish_host(words.ctypes.data, n, dimu, int(with_q), seq, randn.ctypes.data, explore.ctypes.data,
+                                         u_rand.ctypes.data, float(noise_eps) * float(max_u), float(max_u), u_out.ctypes.data,
+                                         q_out.ctypes.data if with_q else None, 1000)
+        assert rc == 0
+        want = _reference_action_postprocessing(u, randn, explore, u_rand, noise_eps, max_u)
+        assert want.dtype == np.float32 and np.array_equal(u_out, want)
+        if with_q:
+            assert np.array_equal(q_out, q)
+        # no draws (device-side noise or a caller that only wants the policy output): plain copy
+        rc = lib.cur_actions_finish_host(words.ctypes.data, n, dimu, 0, seq, None, None, None, 0.0, float(max_u),
+                                         u_out.ctypes.data, None, 1000)
+        assert rc == 0 and np.array_equal(u_out, u)
+        # one word still carries the previous call's number: the poll gives up after max_spins
+        words[n * dimu - 1, 1] = seq - 1
+        rc = lib.cur_actions_finish_host(words.ctypes.data, n, dimu, 0, seq, None, None, None, 0.0, float(max_u),
+                                         u_out.ctypes.data, None, 1000)
+        assert rc == 3
