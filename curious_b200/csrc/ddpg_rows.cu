@@ -35,6 +35,8 @@
 
 #include "her_device.cuh"
 #include "net_layout.cuh"
+#include "tc_gemm.cuh"
+#include "tc_ptx.cuh"
 
 namespace cur {
 
@@ -345,14 +347,14 @@ __device__ __noinline__ void build_x(const StreamParams& P, float* xT, int NR, i
 // the same per-row device functions as her_sample_kernel (bit-identical batches).  Both CTAs of a pair sample the
 // same rows (a 4 x ~0.5 KB gather).
 __device__ __forceinline__ void sample_rows(const StreamParams& P, int64_t row0, float* stage, const float** m_src,
-                                            float* s_r) {
+                                            float* s_r, int nrows = S_ROWS) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const HerPlan& pl = P.plan;
   HerRow row;
   row.ft = -1; row.choice = -1; row.ep = 0; row.t = 0; row.ttr = -1; row.her = false;
-  if (tid < S_ROWS) her_draw_row(P.her, pl, row0 + tid, row, m_src + 3 * tid);
+  if (tid < nrows) her_draw_row(P.her, pl, row0 + tid, row, m_src + 3 * tid);
   consumer_sync();
-  if (warp < S_ROWS) {
+  if (warp < nrows) {
     const int per_row = pl.img4 + pl.fut4 + pl.cold4;   // (cold rows only for an `info` reward or relative goals)
     float* dst = stage + warp * pl.stage_stride;
     for (int c = lane; c < per_row; c += 32) {
@@ -366,7 +368,7 @@ __device__ __forceinline__ void sample_rows(const StreamParams& P, int64_t row0,
   cp_commit();
   cp_wait0();
   consumer_sync();
-  if (tid < S_ROWS) {
+  if (tid < nrows) {
     int relab;
     s_r[tid] = her_relabel_row(P.her, pl, stage + tid * pl.stage_stride, row, &relab);
   }
@@ -382,11 +384,13 @@ __device__ __noinline__ void small_out(const float* xT, int NR, int roff, int nr
   const bool on = r < nr;
   float acc = 0.f;
   if (on) {
-#pragma unroll 8
-    for (int kk = 0; kk < S_H / 8; ++kk) {
-      const int k = kp + 8 * kk;
-      acc = fmaf(xT[k * NR + roff + r], __ldg(W + (int64_t)k * ldk + (int64_t)j * ldj), acc);
-    }
+    // all 32 weight loads of the thread in flight at once: one exposed L2 round trip instead of four (the loop is on the
+    // critical path of every net: nothing else runs in the CTA meanwhile)
+    float wv[S_H / 8];
+#pragma unroll
+    for (int kk = 0; kk < S_H / 8; ++kk) wv[kk] = __ldg(W + (int64_t)(kp + 8 * kk) * ldk + (int64_t)j * ldj);
+#pragma unroll
+    for (int kk = 0; kk < S_H / 8; ++kk) acc = fmaf(xT[(kp + 8 * kk) * NR + roff + r], wv[kk], acc);
   }
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -408,8 +412,8 @@ __device__ __forceinline__ float* forward_net(const PT& P, Ring& rg, int ch0, fl
   float* xout = xb;
   for (int l = 0; l < P.L; ++l) {
     float v[NR];
+    const float b = bias[l][col];                 // in flight during the layer (an exposed L2 round trip otherwise)
     layer_gemv<NR>(P, rg, l == 0 ? ch0 : S_H / S_CK, xin, red, v);
-    const float b = bias[l][col];
 #pragma unroll
     for (int r = 0; r < NR; ++r) v[r] = fmaxf(v[r] + b, 0.f);
     if (h_a != nullptr) {
@@ -452,6 +456,7 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   float* her_stage = misc + S_STAGE_OFF;                                  // [4][stage_stride]
 
   const int tid = threadIdx.x;
+  if (P.tl != nullptr && tid == 0 && blockIdx.x < 512) P.tl[64 + 2 * blockIdx.x] = (long long)globaltimer_ns();
   const uint32_t role = blockIdx.x & 1;                      // 0: actor chain, 1: critic chain (independent CTAs)
   const int64_t row0 = (int64_t)(blockIdx.x >> 1) * S_ROWS;
   const cur_net_desc& d = P.d;
@@ -563,6 +568,7 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
       consumer_sync();
       float* t = xin; xin = xout; xout = t;
     }
+    if (P.tl != nullptr && tid == 0 && blockIdx.x < 512) P.tl[65 + 2 * blockIdx.x] = (long long)globaltimer_ns();
     return;
   }
 
@@ -682,6 +688,473 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
     }
   }
   S_TL(7);
+  if (P.tl != nullptr && tid == 0 && blockIdx.x < 512) P.tl[65 + 2 * blockIdx.x] = (long long)globaltimer_ns();
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-PAIR form of the stream kernel (batch a multiple of 8): a 2-CTA cluster walks one chain for EIGHT rows, and each CTA
+// owns HALF the output columns of every hidden layer.  An SM then ingests only half of its chain's weights (1.1 MB
+// instead of 2.2 MB - per-SM L2 -> shared bandwidth, ~42 B/clk, is what bounds the 4-row kernel) while doing the same
+// number of FMAs (8 rows x 128 columns; scratch/micro/gemv_micro.cu: 690 cycles per 32 KB chunk against ~780 of ingest).
+// After every layer the two CTAs swap their halves of the activations through distributed shared memory: each thread
+// stores its 16 bytes into both CTAs' transposed activation buffer and arrives on the partner's mbarrier; the next layer
+// starts with the k rows of the CTA's OWN columns (already local) and only then waits for the partner's half, so the
+// exchange latency hides behind half a layer.  Weight chunks are 64 k rows x 128 columns = 32 KB, one 2-D TMA box each
+// (64 bulk copies of 512 bytes per chunk, the first version, ran at ~8 B/clk: 100 us per update).
+constexpr int PR_ROWS = 8;                // batch rows per CTA pair
+constexpr int PR_NC = 128;                // output columns per CTA
+constexpr int PR_CK = 64;                 // k rows per weight chunk (64 x 128 floats = S_SLOT)
+constexpr int PR_MAXCHUNK = 64;           // chunks per (chain, rank): L = 4, 256 first-layer inputs -> 3 * 17 + 12 = 63
+constexpr int PR_MISC = 4096;             // floats of small per-CTA state + the staged HER images of the 8 rows
+constexpr int PR_STAGE_OFF = 512;
+constexpr size_t PR_SMEM_BYTES = (size_t)(S_NSLOT * S_SLOT + 2 * S_XT + S_RED + PR_MISC) * 4 + 128;
+static_assert(PR_CK * PR_NC == S_SLOT && PR_ROWS * S_H == S_XT && 8 * PR_ROWS * PR_NC == S_RED, "pair kernel reuses the ring / xT / partial areas");
+
+constexpr int PR_MAXMAPS = 28;            // weight blocks of the four nets + the transposes (L = 4: 4 * 5 + 2 * 3 = 26)
+
+struct PairChunk {
+  int map;            // tensor map of the weight block [rows][256] this chunk comes from
+  int krow;           // first row of the block
+  short nrows;        // rows of the chunk that exist (<= 64; the TMA unit zero-fills the rest of the box)
+  short wait;         // 1: the first chunk of a layer whose k rows are the PARTNER's columns of the previous layer
+  int k0;             // first k row of the layer this chunk covers
+};
+
+struct PairParams {
+  StreamParams S;
+  int nch[2][2];                          // [role][rank]
+  int pch0[2];                            // chunks of a first layer: [0] pi nets, [1] Q nets
+  PairChunk ch[2][2][PR_MAXCHUNK];        // [role: actor, critic][cluster rank]
+  alignas(64) CUtensorMap maps[PR_MAXMAPS];   // box = 128 columns x 64 rows, dense
+};
+
+struct PairRing {
+  const PairChunk* chunks;
+  const float* slots;
+  uint32_t full, empty;
+  int cons;
+};
+
+// the activation exchange of a CTA pair (see above); every consumer thread holds the same state.  A thread's 16 bytes
+// travel as ONE st.async that also counts its bytes on the receiver's mbarrier (complete_tx, like a TMA copy): no
+// release / acquire round trip and no per-thread arrive (256 remote arrives per layer cost ~4 k cycles, measured).
+struct PairX {
+  uint32_t bar_local[2], bar_remote[2];   // mbarriers (count 1 = the receiver's own expect_tx), alternating per exchange
+  uint32_t x_local, x_remote;             // shared address of xa here / in the partner (xb follows at + S_XT floats)
+  uint32_t word_remote;                   // a scratch word of the partner (payload of a data-less rendezvous)
+  int step;                               // exchanges issued so far
+  bool pending;                           // the partner's half of exchange `step - 1` has not been waited for yet
+  long long* dbg;                         // debug stamps (thread 0 of CTA 0, CUR_ROWS_TIMELINE=1) or nullptr
+  __device__ __forceinline__ void stamp() {
+    if (dbg != nullptr) *dbg++ = clock64();
+  }
+  __device__ __forceinline__ void wait() {
+    if (pending) {
+      const int s = step - 1;
+      stamp();
+      mbar_wait_cluster(bar_local[s & 1], (uint32_t)((s >> 1) & 1));
+      stamp();
+      pending = false;
+    }
+  }
+  // 4 rows (4 * rh ..) of column `gcol` of the layer output: into both CTAs' transposed buffer `xT`
+  __device__ __forceinline__ void put(float* xT, int gcol, int rh, const float (&v)[4]) {
+    float* dst = xT + gcol * PR_ROWS + 4 * rh;
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    const uint32_t ra = x_remote + (smem_addr(dst) - x_local);
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(ra),
+                 "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(bar_remote[step & 1])
+                 : "memory");
+    if (threadIdx.x == 0) mbar_expect_tx(bar_local[step & 1], S_CONSUMERS * 16);     // what the partner sends me
+    ++step;
+    pending = true;
+  }
+  // pair-wide rendezvous of the consumers without data: nobody passes before both CTAs are done with what they read
+  // so far (a first layer / a backward seed does not depend on the partner, so it could otherwise overwrite a buffer the
+  // partner is still reading)
+  __device__ __forceinline__ void sync() {
+    wait();
+    consumer_sync();                      // every thread of this CTA is done reading
+    if (threadIdx.x == 0) {
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(word_remote),
+                   "f"(0.f), "r"(bar_remote[step & 1])
+                   : "memory");
+      mbar_expect_tx(bar_local[step & 1], 4);
+    }
+    ++step;
+    pending = true;
+    wait();
+  }
+};
+
+template <class PT>
+__device__ __forceinline__ void pair_gemv_chunks(const PT& P, PairRing& rg, PairX& X, int nchunks, const float* __restrict__ xT,
+                                                 float2 (&acc)[4][4]) {
+  const int cg = threadIdx.x & 31, ks = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const int slot = rg.cons % S_NSLOT;
+    const int nrows = rg.chunks[rg.cons].nrows, k0 = rg.chunks[rg.cons].k0;
+    if (rg.chunks[rg.cons].wait) X.wait();
+    mbar_wait(rg.full + 8 * slot, (rg.cons / S_NSLOT) & 1);
+    const float* ws = rg.slots + slot * S_SLOT + 4 * cg;
+    const float* xs = xT + (k0 + ks * 8) * PR_ROWS;
+    if (P.dbg_skip_math) {
+    } else if (ks * 8 < nrows) {
+      // a ragged first-layer block: the TMA unit zero-filled the box rows beyond nrows and pair_build_x zeroed the x
+      // rows beyond the fan-in, so a k-slice that starts inside the block runs unguarded (warp-uniform test)
+      float4 w[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) w[kk] = *reinterpret_cast<const float4*>(ws + (ks * 8 + kk) * PR_NC);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) fma_row<PR_ROWS>(acc, xs + kk * PR_ROWS, w[kk]);
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(rg.empty + 8 * slot);
+    ++rg.cons;
+  }
+}
+
+// One dense layer for the pair's 8 rows and this CTA's 128 columns.  Returns, for the thread's column `tid & 127` and
+// its 4 rows 4 * (tid >> 7) .., the pre-activation sums (without bias).
+template <class PT>
+__device__ __forceinline__ void pair_layer_gemv(const PT& P, PairRing& rg, PairX& X, int nchunks, const float* xT, float* red,
+                                                float (&v)[4]) {
+  float2 acc[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[p][c] = make_float2(0.f, 0.f);
+  X.stamp();
+  pair_gemv_chunks(P, rg, X, nchunks, xT, acc);
+  X.stamp();
+  const int cg = threadIdx.x & 31, ks = threadIdx.x >> 5;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    *reinterpret_cast<float4*>(red + (ks * PR_ROWS + 2 * p) * PR_NC + 4 * cg) =
+        make_float4(acc[p][0].x, acc[p][1].x, acc[p][2].x, acc[p][3].x);
+    *reinterpret_cast<float4*>(red + (ks * PR_ROWS + 2 * p + 1) * PR_NC + 4 * cg) =
+        make_float4(acc[p][0].y, acc[p][1].y, acc[p][2].y, acc[p][3].y);
+  }
+  consumer_sync();
+  const int col = threadIdx.x & (PR_NC - 1), rh = threadIdx.x >> 7;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float* p = red + (4 * rh + r) * PR_NC + col;
+    constexpr int SL = PR_ROWS * PR_NC;             // one k-slice of partials
+    v[r] = ((p[0] + p[SL]) + (p[2 * SL] + p[3 * SL])) + ((p[4 * SL] + p[5 * SL]) + (p[6 * SL] + p[7 * SL]));
+  }
+}
+
+// One forward net for the pair's 8 rows (first-layer input already in `xa` of both CTAs).  Returns the buffer that holds
+// the last hidden activations; the partner's half of it is still in flight (X.wait() before reading all of it).
+template <class PT>
+__device__ __forceinline__ float* pair_forward_net(const PT& P, PairRing& rg, PairX& X, int ch0, int L, int gc0, float* xa,
+                                                   float* xb, float* red, const float* const* bias, float* const* h_out,
+                                                   int64_t row0) {
+  const int col = threadIdx.x & (PR_NC - 1), rh = threadIdx.x >> 7, gcol = gc0 + col;
+  float* xin = xa;
+  float* xout = xb;
+  for (int l = 0; l < L; ++l) {
+    float v[4];
+    const float b = bias[l][gcol];                // in flight during the layer (an exposed L2 round trip otherwise)
+    pair_layer_gemv(P, rg, X, l == 0 ? ch0 : S_H / PR_CK, xin, red, v);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[r] = fmaxf(v[r] + b, 0.f);
+    if (h_out != nullptr) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) h_out[l][(row0 + 4 * rh + r) * S_H + gcol] = v[r];
+    }
+    X.put(xout, gcol, rh, v);
+    consumer_sync();
+    X.stamp();
+    float* t = xin; xin = xout; xout = t;
+  }
+  return xin;
+}
+
+// backward through the hidden layers L-1 .. 1 of one net from the seed already exchanged into `xin`: masks from the
+// row-major activations `h`, deltas optionally stored row-major into `dout`
+template <class PT>
+__device__ __forceinline__ float* pair_backward_net(const PT& P, PairRing& rg, PairX& X, int L, int gc0, float* xin, float* xout,
+                                                    float* red, float* const* h, float* const* dout, int64_t row0) {
+  const int col = threadIdx.x & (PR_NC - 1), rh = threadIdx.x >> 7, gcol = gc0 + col;
+  for (int l = L - 1; l >= 1; --l) {
+    float m[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) m[r] = __ldcg(h[l - 1] + (row0 + 4 * rh + r) * S_H + gcol);   // ReLU masks of layer l-1
+    float v[4];
+    pair_layer_gemv(P, rg, X, S_H / PR_CK, xin, red, v);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      v[r] = relu_mask(v[r], m[r]);
+      if (dout != nullptr) dout[l - 1][(row0 + 4 * rh + r) * S_H + gcol] = v[r];
+    }
+    X.put(xout, gcol, rh, v);
+    consumer_sync();
+    float* t = xin; xin = xout; xout = t;
+  }
+  return xin;
+}
+
+// first-layer input of the pair's 8 rows (two 4-row halves of build_x); the row-major global copy only from rank 0
+__device__ __forceinline__ void pair_build_x(const StreamParams& P, float* xT, int64_t row0, bool target, int act_kind,
+                                             const float* ths, float* gout, const float* stage) {
+  const int ss = P.plan.stage_stride;
+  build_x(P, xT, PR_ROWS, 0, row0, target, act_kind, ths, gout, stage);
+  build_x(P, xT, PR_ROWS, 4, row0 + 4, target, act_kind, ths ? ths + 4 * S_DU : nullptr, gout,
+          stage ? stage + 4 * ss : nullptr);
+  // k rows [KP, KP + 64) are multiplied with zero-filled weight rows of the ragged first-layer chunks: keep them finite
+  const int kend = (P.KP + PR_CK < S_H) ? P.KP + PR_CK : S_H;
+  for (int i = P.KP * PR_ROWS + threadIdx.x; i < kend * PR_ROWS; i += S_CONSUMERS) xT[i] = 0.f;
+}
+
+__device__ __forceinline__ void pair_consumer(const PairParams& PP, float* ringf, float* xa, float* xb, float* red,
+                                              float* misc, uint32_t full, uint32_t empty, uint32_t xbar) {
+  const StreamParams& P = PP.S;
+  float* s_th = misc;                 // [8][8] tanh output of this chain's pi net (= pi / max_u)
+  float* s_q = misc + 64;             // [8][8] main.Q of the 8 rows
+  float* s_qt = misc + 128;           // [8][8] target.Q
+  float* s_dq = misc + 192;           // [8] backward seed; [8..16): squared TD error
+  float* s_dy = misc + 256;           // [8][8]
+  float* s_r = misc + 320;            // [8] rewards of the rows (fused HER sampling)
+  const float** m_src = reinterpret_cast<const float**>(misc + 336);     // [8][3] source addresses
+  float* her_stage = misc + PR_STAGE_OFF;                                 // [8][stage_stride]
+
+  const int tid = threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t pair = blockIdx.x >> 1;
+  const uint32_t role = pair & 1;                              // 0: actor chain, 1: critic chain (independent pairs)
+  const int64_t row0 = (int64_t)(pair >> 1) * PR_ROWS;
+  const cur_net_desc& d = P.d;
+  const int L = P.L;
+  const int gc0 = (int)rank * PR_NC, col = tid & (PR_NC - 1), rh = tid >> 7, gcol = gc0 + col;
+  const bool lead = rank == 0;                                 // writes what both CTAs compute redundantly
+
+  PairRing rg;
+  rg.chunks = PP.ch[role][rank]; rg.slots = ringf; rg.full = full; rg.empty = empty; rg.cons = 0;
+  PairX X;
+  X.bar_local[0] = xbar; X.bar_local[1] = xbar + 8;
+  X.bar_remote[0] = map_to_cta(xbar, rank ^ 1u); X.bar_remote[1] = map_to_cta(xbar + 8, rank ^ 1u);
+  X.x_local = smem_addr(xa); X.x_remote = map_to_cta(X.x_local, rank ^ 1u);
+  X.word_remote = map_to_cta(smem_addr(misc + 400), rank ^ 1u);
+  X.step = 0; X.pending = false;
+  X.dbg = nullptr;
+
+  const float inv_n = 1.0f / (float)P.grad_rows;      // scale of the backward seeds
+  const float* stage = nullptr;
+  if (P.fused_her) {
+    sample_rows(P, row0, her_stage, m_src, s_r, PR_ROWS);
+    stage = her_stage;
+  }
+  const float hi_clip = P.clip_pos ? 0.f : INFINITY;
+  const bool tl_on = P.tl != nullptr && blockIdx.x == 0 && tid == 0;
+#define PR_TL(i) do { if (tl_on) P.tl[i] = clock64(); } while (0)
+
+  if (role == 1) {
+    // ===== critic pair: target.pi -> target.Q(o2, g2, pi_target), main.Q(o, g, u), TD loss, the critic's backward chain
+    pair_build_x(P, xa, row0, true, 0, nullptr, nullptr, stage);
+    consumer_sync();
+    float* xl = pair_forward_net(P, rg, X, PP.pch0[0], L, gc0, xa, xb, red, P.bPT, nullptr, row0);
+    X.wait();
+    small_out(xl, PR_ROWS, 0, PR_ROWS, P.WoutPT, d.dimu, 1, d.dimu, P.boutPT, s_th);
+    consumer_sync();
+    if (tid < PR_ROWS * S_DU && (tid & (S_DU - 1)) < d.dimu) s_th[tid] = tanhf(s_th[tid]);
+    X.sync();
+    consumer_sync();
+    pair_build_x(P, xa, row0, true, 2, s_th, nullptr, stage);
+    consumer_sync();
+    xl = pair_forward_net(P, rg, X, PP.pch0[1], L, gc0, xa, xb, red, P.bQT, nullptr, row0);
+    X.wait();
+    small_out(xl, PR_ROWS, 0, PR_ROWS, P.WoutQT, 1, 1, 1, P.boutQT, s_qt);
+    X.sync();
+    consumer_sync();
+    // main.Q(o, g, u)
+    pair_build_x(P, xa, row0, false, 1, nullptr, lead ? P.Xq : nullptr, stage);
+    consumer_sync();
+    xl = pair_forward_net(P, rg, X, PP.pch0[1], L, gc0, xa, xb, red, P.bQ, P.hq, row0);
+    X.wait();
+    small_out(xl, PR_ROWS, 0, PR_ROWS, P.WoutQ, 1, 1, 1, P.boutQ, s_q);
+    consumer_sync();
+    // critic loss (ddpg.py:436-439) and its backward seed
+    if (tid < PR_ROWS) {
+      const int64_t row = row0 + tid;
+      const float rew = stage ? s_r[tid] : P.r[row];
+      const float tgt = fminf(fmaxf(rew + P.gamma * s_qt[tid * S_DU], -P.clip_return), hi_clip);
+      const float diff = tgt - s_q[tid * S_DU];
+      s_dq[tid] = -2.0f * inv_n * diff;          // d mean((tgt - Q)^2) / dQ
+      s_dq[8 + tid] = diff * diff;
+      if (lead) P.dQ[row] = s_dq[tid];
+    }
+    X.sync();
+    consumer_sync();
+    if (lead && tid < 2) {                        // per 4 rows, like the 4-row kernel (same fold in rows_dw_kernel)
+      float ssq = 0.f;
+      for (int r = 0; r < 4; ++r) ssq += s_dq[8 + 4 * tid + r];
+      P.loss_part[((row0 >> 2) + tid) * 4] = ssq;
+    }
+    // backward through main.Q (critic chain): gradient at the last hidden layer is dQ * Wout^T (Wout is [H][1])
+    {
+      const float wq = __ldg(P.WoutQ + gcol);
+      float v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r] = relu_mask(s_dq[4 * rh + r] * wq, __ldcg(P.hq[L - 1] + (row0 + 4 * rh + r) * S_H + gcol));
+        P.dc[L - 1][(row0 + 4 * rh + r) * S_H + gcol] = v[r];
+      }
+      X.put(xa, gcol, rh, v);
+      consumer_sync();
+    }
+    pair_backward_net(P, rg, X, L, gc0, xa, xb, red, P.hq, P.dc, row0);
+    X.wait();
+    return;
+  }
+
+  // ===== actor pair: main.pi -> main.Q(o, g, pi) -> actor loss -> backward through main.Q and main.pi =====
+  PR_TL(0);
+  pair_build_x(P, xa, row0, false, 0, nullptr, lead ? P.Xp : nullptr, stage);
+  consumer_sync();
+  PR_TL(1);
+  {
+    if (tl_on) X.dbg = P.tl + 8;          // main.pi forward in detail: 24 stamps at most
+    X.stamp();
+    float* xl = pair_forward_net(P, rg, X, PP.pch0[0], L, gc0, xa, xb, red, P.bP, P.hp, row0);
+    X.wait();
+    X.dbg = nullptr;
+    small_out(xl, PR_ROWS, 0, PR_ROWS, P.WoutP, d.dimu, 1, d.dimu, P.boutP, s_th);
+    consumer_sync();
+    if (tid < PR_ROWS * S_DU && (tid & (S_DU - 1)) < d.dimu) s_th[tid] = tanhf(s_th[tid]);   // actor_critic.py:89
+    X.sync();
+    consumer_sync();
+  }
+  PR_TL(2);
+  PR_TL(3);
+  pair_build_x(P, xa, row0, false, 2, s_th, nullptr, stage);
+  consumer_sync();
+  {
+    float* xl = pair_forward_net(P, rg, X, PP.pch0[1], L, gc0, xa, xb, red, P.bQ, P.hqp, row0);
+    X.wait();
+    small_out(xl, PR_ROWS, 0, PR_ROWS, P.WoutQ, 1, 1, 1, P.boutQ, s_q);
+    consumer_sync();
+  }
+  PR_TL(4);
+  PR_TL(5);
+  // ===== actor loss terms (ddpg.py:440-441) and backward seed =====
+  if (tid < PR_ROWS) {
+    s_dq[tid] = -inv_n;                        // d (-mean(Q_pi)) / dQ_pi
+    if (lead) P.q_pi[row0 + tid] = s_q[tid * S_DU];
+  }
+  if (lead && tid < 2) {
+    float sq = 0.f, sth = 0.f;
+    for (int r = 4 * tid; r < 4 * tid + 4; ++r) {
+      sq += s_q[r * S_DU];
+      for (int j = 0; j < d.dimu; ++j) sth += s_th[r * S_DU + j] * s_th[r * S_DU + j];
+    }
+    float* lp = P.loss_part + ((row0 >> 2) + tid) * 4;
+    lp[1] = sq; lp[2] = sth; lp[3] = 0.f;
+  }
+  X.sync();
+  consumer_sync();
+  // ===== backward through main.Q, actor-through-critic chain =====
+  {
+    {
+      const float wq = __ldg(P.WoutQ + gcol);
+      float v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        v[r] = relu_mask(s_dq[4 * rh + r] * wq, __ldcg(P.hqp[L - 1] + (row0 + 4 * rh + r) * S_H + gcol));
+      X.put(xa, gcol, rh, v);
+      consumer_sync();
+    }
+    float* xin = pair_backward_net(P, rg, X, L, gc0, xa, xb, red, P.hqp, nullptr, row0);
+    X.wait();
+    // gradient wrt the action inputs of main.Q, then through tanh and the action penalty (ddpg.py:440-441):
+    // d pi_loss/d(pre-tanh) = (dL/d(pi/max_u) + action_l2*2/(B*dimu)*th) * (1 - th^2)
+    small_out(xin, PR_ROWS, 0, PR_ROWS, P.W0Q_act, 1, S_H, d.dimu, nullptr, s_dy);
+    consumer_sync();
+    if (tid < PR_ROWS * S_DU) {
+      const int r = tid >> 3, j = tid & (S_DU - 1);
+      float v = 0.f;
+      if (j < d.dimu) {
+        const float coef = P.action_l2 * 2.0f / (float)(P.grad_rows * d.dimu);
+        const float th = s_th[tid];
+        v = (s_dy[tid] + coef * th) * (1.f - th * th);
+      }
+      s_dy[tid] = v;
+      if (lead && j < P.lddy) P.dy[(row0 + r) * P.lddy + j] = v;
+    }
+    X.sync();
+    consumer_sync();
+  }
+  PR_TL(6);
+  // ===== backward through main.pi =====
+  {
+    {
+      float v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[r] = 0.f;
+      for (int j = 0; j < d.dimu; ++j) {
+        const float wj = __ldg(P.WoutP + (int64_t)gcol * d.dimu + j);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = fmaf(s_dy[(4 * rh + r) * S_DU + j], wj, v[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r] = relu_mask(v[r], __ldcg(P.hp[L - 1] + (row0 + 4 * rh + r) * S_H + gcol));
+        P.dp[L - 1][(row0 + 4 * rh + r) * S_H + gcol] = v[r];
+      }
+      X.put(xa, gcol, rh, v);
+      consumer_sync();
+    }
+    pair_backward_net(P, rg, X, L, gc0, xa, xb, red, P.hp, P.dp, row0);
+    X.wait();
+  }
+  PR_TL(7);
+#undef PR_TL
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S_THREADS, 1)
+ddpg_stream_pair_kernel(const __grid_constant__ PairParams PP) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ringf = reinterpret_cast<float*>(smem_raw);
+  float* xa = ringf + S_NSLOT * S_SLOT;
+  float* xb = xa + S_XT;
+  float* red = xb + S_XT;
+  float* misc = red + S_RED;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + PR_MISC);      // full[4], empty[4], xchg[2]
+  const int tid = threadIdx.x;
+  const uint32_t full = smem_addr(bars), empty = smem_addr(bars + S_NSLOT), xbar = smem_addr(bars + 2 * S_NSLOT);
+  if (tid == 0) {
+    for (int i = 0; i < S_NSLOT; ++i) {
+      mbar_init(full + 8 * i, 1);
+      mbar_init(empty + 8 * i, S_CONSUMERS / 32);
+    }
+    mbar_init(xbar, 1);
+    mbar_init(xbar + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_launch_dependents();
+  pdl_wait();               // everything below reads what the previous kernel (weight gradients + Adam of the last update) wrote
+  cluster_sync_all();       // both CTAs' barriers are initialised before anybody arrives on them (locally or remotely)
+
+  if (tid >= S_CONSUMERS) {
+    // ------------------------------------------------------------ producer warp: stream this CTA's half of every chunk
+    if (tid == S_CONSUMERS) {
+      const uint32_t rank = cluster_ctarank(), role = (blockIdx.x >> 1) & 1;
+      const PairChunk* my = PP.ch[role][rank];
+      const int total = PP.nch[role][rank];
+      const uint32_t ring_s = smem_addr(ringf);
+      for (int i = 0; i < total; ++i) {
+        const int slot = i % S_NSLOT, round = i / S_NSLOT;
+        if (round > 0) mbar_wait(empty + 8 * slot, (round - 1) & 1);
+        mbar_expect_tx(full + 8 * slot, (uint32_t)S_SLOT * 4);          // a box always counts in full (zero-filled rows too)
+        tc_tma_2d(ring_s + slot * S_SLOT * 4, &PP.maps[my[i].map], (int)rank * PR_NC, my[i].krow, full + 8 * slot);
+      }
+    }
+  } else {
+    pair_consumer(PP, ringf, xa, xb, red, misc, full, empty, xbar);
+  }
+  cluster_sync_all();       // neither CTA leaves while the partner may still store into it / arrive on its barriers
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1099,7 +1572,7 @@ __device__ __forceinline__ void dw_finish(const DwTail& T, const DwCtx& cx, floa
 //              cp.async (one L2 round trip instead of a multi-stage pipeline of dependent ones), 4-way split-K
 //              inside the CTA, packed FFMA2; 3 CTAs per SM so that all ~330 tiles are co-resident (one wave)
 //   DW_SKINNY  N <= 4 (output layers): 32 rows of C per tile, 8 k-parts per row
-//   DW_COLSUM  C[n] = sum_k B[k][n] (bias gradients), 256 columns per tile
+//   DW_COLSUM  C[n] = sum_k B[k][n] (bias gradients), 32 columns per tile, 8 k-parts per column
 // (A 64 x 64 / 8 x 8-micro-tile variant, which is not bound by shared-memory wavefronts, measured slower here:
 //  88 fat CTAs leave 60 SMs idle and cannot overlap staging with compute - see profiles/README.md.)
 enum { DW_FULLK = 0, DW_SKINNY = 1, DW_COLSUM = 2 };
@@ -1107,10 +1580,10 @@ constexpr int DW_KMAX = 256;
 constexpr int DW_LD = GT + 4;                                   // row stride of a staged [k][32] tile
 constexpr size_t DW_SMEM_BYTES = (size_t)2 * DW_KMAX * DW_LD * 4;
 
-__device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, float* Bs, int m0, int n0, const DwTail& T,
-                                              const DwCtx& cx) {
+// ---- stage A[k][m0..m0+32) and B[k][n0..n0+32) for every k (zero fill past the edges); issued before anything that
+// depends on the device step counter, so that the two dependent round trips of that setup overlap this one
+__device__ __forceinline__ void dw_stage_fullk(const GemmProb& P, float* As, float* Bs, int m0, int n0) {
   const int tid = threadIdx.x;
-  // ---- stage A[k][m0..m0+32) and B[k][n0..n0+32) for every k (zero fill past the edges)
 #pragma unroll
   for (int j = 0; j < (DW_KMAX * 8) / GEMM_THREADS; ++j) {
     const int f = tid + j * GEMM_THREADS;
@@ -1121,6 +1594,11 @@ __device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, floa
     cp16_zfill(Bs + k * DW_LD + c4, P.B + (okb ? (int64_t)k * P.ldb + (n0 + c4) : 0), okb);
   }
   cp_commit();
+}
+
+__device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, float* Bs, int m0, int n0, const DwTail& T,
+                                              const DwCtx& cx) {
+  const int tid = threadIdx.x;
   cp_wait0();
   __syncthreads();
   const int kg = tid >> 6, lt = tid & 63, ty = lt >> 3, tx = lt & 7;
@@ -1184,29 +1662,51 @@ __device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, floa
   }
 }
 
-// C[m][j] = sum_k A[k][m] * B[k*ldb + j], j < N <= 4, for the 32 rows m0.. of C; 8 interleaved k-parts per row,
-// loads of 8 k steps in flight per thread
-__device__ __forceinline__ void dw_tile_skinny(const GemmProb& P, float* red, int m0, const DwTail& T, const DwCtx& cx) {
-  const int tid = threadIdx.x, m = tid & 31, kp = tid >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool on = m0 + m < P.M;
-  const float* ap = P.A + (on ? m0 + m : 0);
+// C[m][j] = sum_k A[k][m] * B[k*ldb + j], j < N <= 4, for the 32 rows m0.. of C; 8 interleaved k-parts per row.
+// Both operands are staged for the whole K in ONE round trip (A with cp.async like a full-K tile, B with one plain load
+// per thread): the first version took its operands in four dependent batches of loads, each queued behind the 128 KB of
+// staging traffic of the two full-K tiles on the same SM - 18.5 k cycles, the longest tile of the launch.
+__device__ __forceinline__ void dw_stage_skinny(const GemmProb& P, float* As, float* Bs, int m0) {
+  const int tid = threadIdx.x;
   const int N = P.N;
-  for (int kb = kp; kb < P.K; kb += 64) {        // batches of 8 k steps: all loads first, then the FMAs
-    float a8[8], b8[8][4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int k = kb + 8 * u;
-      const bool kin = k < P.K;
-      a8[u] = (on && kin) ? __ldg(ap + (int64_t)k * P.lda) : 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b8[u][j] = (kin && j < N) ? __ldg(P.B + (int64_t)k * P.ldb + j) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(a8[u], b8[u][j], acc[j]);
+  for (int j = 0; j < (DW_KMAX * 8) / GEMM_THREADS; ++j) {
+    const int f = tid + j * GEMM_THREADS;
+    const int k = f >> 3, c4 = (f & 7) << 2;
+    const bool oka = (k < P.K) && (m0 + c4 < P.M) && P.lda % 4 == 0;
+    cp16_zfill(As + k * DW_LD + c4, P.A + (oka ? (int64_t)k * P.lda + (m0 + c4) : 0), oka);
   }
+  cp_commit();
+  {
+    const int k = tid;                                       // GEMM_THREADS == DW_KMAX: one B row per thread
+    float b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = (k < P.K && j < N) ? __ldg(P.B + (int64_t)k * P.ldb + j) : 0.f;
+    *reinterpret_cast<float4*>(Bs + 4 * k) = make_float4(b[0], b[1], b[2], b[3]);
+  }
+  if (P.lda % 4 != 0) {                                      // (never for the shapes of the rows schedule: ld = 256)
+    for (int f = tid; f < DW_KMAX * GT; f += GEMM_THREADS) {
+      const int k = f >> 5, mm = f & 31;
+      As[k * DW_LD + mm] = (k < P.K && m0 + mm < P.M) ? __ldg(P.A + (int64_t)k * P.lda + m0 + mm) : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void dw_tile_skinny(const GemmProb& P, float* As, float* Bs, int m0, const DwTail& T,
+                                               const DwCtx& cx) {
+  const int tid = threadIdx.x, m = tid & 31, kp = tid >> 5;
+  cp_wait0();
+  __syncthreads();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+  for (int t = 0; t < DW_KMAX / 8; ++t) {                    // k = kp, kp + 8, ...: the summation order of the first version
+    const int k = kp + 8 * t;
+    const float a = As[k * DW_LD + m];
+    const float4 b = *reinterpret_cast<const float4*>(Bs + 4 * k);
+    acc[0] = fmaf(a, b.x, acc[0]); acc[1] = fmaf(a, b.y, acc[1]); acc[2] = fmaf(a, b.z, acc[2]); acc[3] = fmaf(a, b.w, acc[3]);
+  }
+  __syncthreads();                                            // everybody is done with the staged operands
+  float* red = As;
 #pragma unroll
   for (int j = 0; j < 4; ++j) red[(kp * 32 + m) * 4 + j] = acc[j];
   __syncthreads();
@@ -1223,23 +1723,31 @@ __device__ __forceinline__ void dw_tile_skinny(const GemmProb& P, float* red, in
   }
 }
 
-// C[n] = sum_k B[k][n] for 256 columns n0.. : one thread per column, 4 independent partial sums
+// C[n] = sum_k B[k][n] for the 32 columns n0.. : 8 k-parts per column, the 32 loads of a thread in flight at once (the
+// first version - one thread per column walking K in steps of 4 - was a chain of 64 dependent round trips: 15 k cycles)
+constexpr int DW_CS_COLS = 32;
 __device__ __forceinline__ void dw_tile_colsum(const GemmProb& P, float* red, int n0, const DwTail& T, const DwCtx& cx) {
-  const int n = n0 + threadIdx.x;
-  if (n >= P.N) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int k = 0;
-  for (; k + 4 <= P.K; k += 4) {
-    s0 += P.B[(int64_t)k * P.ldb + n];
-    s1 += P.B[(int64_t)(k + 1) * P.ldb + n];
-    s2 += P.B[(int64_t)(k + 2) * P.ldb + n];
-    s3 += P.B[(int64_t)(k + 3) * P.ldb + n];
+  const int tid = threadIdx.x, nn = tid & 31, kp = tid >> 5;
+  const int n = n0 + nn;
+  float x[DW_KMAX / 8];
+#pragma unroll
+  for (int t = 0; t < DW_KMAX / 8; ++t) {
+    const int k = kp * (DW_KMAX / 8) + t;
+    x[t] = (n < P.N && k < P.K) ? __ldg(P.B + (int64_t)k * P.ldb + n) : 0.f;
   }
-  for (; k < P.K; ++k) s0 += P.B[(int64_t)k * P.ldb + n];
-  float* c[1] = {P.C + n};
-  const bool ok[1] = {true};
-  float v[1] = {(s0 + s1) + (s2 + s3)}, th[1];
-  dw_finish<1>(T, cx, c, ok, P.accumulate != 0, v, th);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int t = 0; t < DW_KMAX / 8; t += 4) { s0 += x[t]; s1 += x[t + 1]; s2 += x[t + 2]; s3 += x[t + 3]; }
+  red[kp * 32 + nn] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (tid < 32) {
+    float* c[1] = {P.C + n};
+    const bool ok[1] = {n < P.N};
+    float v[1], th[1];
+    v[0] = ((red[nn] + red[32 + nn]) + (red[64 + nn] + red[96 + nn])) +
+           ((red[128 + nn] + red[160 + nn]) + (red[192 + nn] + red[224 + nn]));
+    dw_finish<1>(T, cx, c, ok, P.accumulate != 0, v, th);
+  }
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 3)
@@ -1257,8 +1765,25 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     else if (blockIdx.x == gridDim.x - 1) tl = T.tl + 48;
   }
   if (tl) tl[0] = clock64();
+  if (T.tl != nullptr && threadIdx.x == 0 && blockIdx.x < 512) T.tl[1088 + 2 * blockIdx.x] = (long long)globaltimer_ns();
   pdl_launch_dependents();
   pdl_wait();                                                    // activations / deltas of the stream kernel, the step counter
+  int pi = 0;
+#pragma unroll 1
+  while (pi + 1 < G.n && (int)blockIdx.x >= G.p[pi + 1].tile_begin) ++pi;
+  {
+    const int* src = reinterpret_cast<const int*>(&G.p[pi]);
+    int* dst = reinterpret_cast<int*>(&Ps);
+    for (int i = threadIdx.x; i < (int)(sizeof(GemmProb) / 4); i += GEMM_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const GemmProb& P = Ps;
+  const int tile = blockIdx.x - P.tile_begin;
+  const int tm = (P.variant == DW_FULLK) ? tile / P.tiles_n : 0, tn = tile - tm * P.tiles_n;
+  // ---- the operands first (one round trip) ...
+  if (P.variant == DW_FULLK) dw_stage_fullk(P, As, Bs, tm * GT, tn * GT);
+  else if (P.variant == DW_SKINNY) dw_stage_skinny(P, As, Bs, tile * GT);
+  // ---- ... and what depends on the device step counter (two dependent round trips of thread 0) while they travel
   const long long st = T.step_counter ? *T.step_counter : 0;     // value BEFORE this update's bump
   // several workers per rank (19-worker-equivalent batches): the device counter counts micro-batches,
   // update u = st / micro, launch j = st % micro of it adds its gradient to the sum of launches 0..j-1
@@ -1276,38 +1801,23 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     cx.flag = (uint32_t)(upd + 1);
     cx.tl = (cx.xc_on && T.xc.tl != nullptr) ? T.xc.tl + 4 * (int64_t)blockIdx.x : nullptr;
     if (cx.tl) cx.tl[0] = (long long)globaltimer_ns();
-  }
-  int pi = 0;
-#pragma unroll 1
-  while (pi + 1 < G.n && (int)blockIdx.x >= G.p[pi + 1].tile_begin) ++pi;
-  {
-    const int* src = reinterpret_cast<const int*>(&G.p[pi]);
-    int* dst = reinterpret_cast<int*>(&Ps);
-    for (int i = threadIdx.x; i < (int)(sizeof(GemmProb) / 4); i += GEMM_THREADS) dst[i] = src[i];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
     if (T.parity_stride > 0) Ps.C += ((upd + 1) & 1) * T.parity_stride;
     Ps.accumulate = (mb > 0 || T.chunk > 0) ? 1 : 0;
   }
-  __syncthreads();
-  {
-    const GemmProb& P = Ps;
-    const int tile = blockIdx.x - P.tile_begin;
-    if (tl) tl[1] = clock64();
-    if (P.variant == DW_FULLK) {
-      const int tm = tile / P.tiles_n, tn = tile - tm * P.tiles_n;
-      dw_tile_fullk(P, As, Bs, tm * GT, tn * GT, T, cx);
-    } else if (P.variant == DW_SKINNY) {
-      dw_tile_skinny(P, As, tile * GT, T, cx);
-    } else {
-      dw_tile_colsum(P, As, tile * GEMM_THREADS, T, cx);
-    }
+  if (tl) tl[1] = clock64();
+  // (every tile function starts with a __syncthreads before it reads cx / Ps.C / Ps.accumulate)
+  if (P.variant == DW_FULLK) {
+    dw_tile_fullk(P, As, Bs, tm * GT, tn * GT, T, cx);
+  } else if (P.variant == DW_SKINNY) {
+    dw_tile_skinny(P, As, Bs, tile * GT, T, cx);
+  } else {
+    dw_tile_colsum(P, As, tile * DW_CS_COLS, T, cx);
   }
   // ---- the last CTA to finish folds the loss partials and bumps the step counter
   __syncthreads();
   if (tl) tl[2] = clock64();
   if (cx.tl && threadIdx.x == 0) cx.tl[3] = (long long)globaltimer_ns();
+  if (T.tl != nullptr && threadIdx.x == 0 && blockIdx.x < 512) T.tl[1089 + 2 * blockIdx.x] = (long long)globaltimer_ns();
   if (!T.last_chunk) return;
   if (threadIdx.x == 0) {
     __threadfence();
@@ -1315,12 +1825,19 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     s_last = (t == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
+  if (s_last) {
+    // the partials travel in parallel (one round trip), thread 0 then adds them in the fixed order c = 0, 1, ...
+    float* lp = As;
+    for (int i = threadIdx.x; i < 4 * T.n_clusters; i += GEMM_THREADS) lp[i] = __ldcg(T.loss_part + i);
+    __syncthreads();
+  }
   if (s_last && threadIdx.x == 0) {
+    const float* lp = As;
     float ssq = 0.f, sq = 0.f, sth = 0.f;
     for (int c = 0; c < T.n_clusters; ++c) {
-      ssq += T.loss_part[4 * c + 0];
-      sq += T.loss_part[4 * c + 1];
-      sth += T.loss_part[4 * c + 2];
+      ssq += lp[4 * c + 0];
+      sq += lp[4 * c + 1];
+      sth += lp[4 * c + 2];
     }
     const float inv_n = 1.0f / (float)T.n;
     const long long slot = (T.step_counter && T.ring > 0) ? st % T.ring : 0;
@@ -1340,7 +1857,7 @@ static int plan_dw_batch(GemmBatch& G) {
     GemmProb& P = G.p[i];
     P.tile_begin = t;
     if (P.ones_a) {
-      P.variant = DW_COLSUM; P.tiles_n = (P.N + GEMM_THREADS - 1) / GEMM_THREADS;
+      P.variant = DW_COLSUM; P.tiles_n = (P.N + DW_CS_COLS - 1) / DW_CS_COLS;
       t += P.tiles_n;
     } else if (P.N <= 4) {
       P.variant = DW_SKINNY; P.tiles_n = 1;
@@ -1488,7 +2005,7 @@ extern "C" int cur_ddpg_rows_owner_map(const cur_net_desc* d, int64_t batch, int
         for (int m = t * GT; m < (t + 1) * GT && m < P.M; ++m)
           for (int n = 0; n < P.N; ++n) owner[base + (int64_t)m * P.ldc + n] = own;
       } else {
-        for (int n = t * GEMM_THREADS; n < (t + 1) * GEMM_THREADS && n < P.N; ++n) owner[base + n] = own;
+        for (int n = t * DW_CS_COLS; n < (t + 1) * DW_CS_COLS && n < P.N; ++n) owner[base + n] = own;
       }
     }
   }
@@ -1625,14 +2142,102 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   static int tl_calls = 0;
   const bool tl_on = getenv("CUR_ROWS_TIMELINE") != nullptr;
   if (tl_on && tl_dev == nullptr) {
-    CUR_CUDA_TRY(cudaMalloc(&tl_dev, 64 * sizeof(long long)));
-    CUR_CUDA_TRY(cudaMemset(tl_dev, 0, 64 * sizeof(long long)));
+    CUR_CUDA_TRY(cudaMalloc(&tl_dev, (64 + 2048) * sizeof(long long)));
+    CUR_CUDA_TRY(cudaMemset(tl_dev, 0, (64 + 2048) * sizeof(long long)));
   }
   P.tl = tl_on ? tl_dev : nullptr;
   P.dbg_skip_math = getenv("CUR_ROWS_SKIP_MATH") != nullptr;
 
   const unsigned int n_ctas = (unsigned int)(n / S_ROWS);
-  {
+  // CTA-pair form (column split over a 2-CTA cluster, 8 rows per pair): half the weight bytes per SM
+  static const int pair_mode = getenv("CUR_ROWS_PAIR") ? atoi(getenv("CUR_ROWS_PAIR")) : 0;   // measured slower, see profiles/README.md
+  const bool use_pair = pair_mode != 0 && (n % PR_ROWS) == 0 && d->dimu <= 4 &&
+                        (her == nullptr || PR_ROWS * P.plan.stage_stride <= PR_MISC - PR_STAGE_OFF);
+  if (use_pair) {
+    static bool pair_configured = false;
+    if (!pair_configured) {
+      CUR_CUDA_TRY(cudaFuncSetAttribute(ddpg_stream_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)PR_SMEM_BYTES));
+      pair_configured = true;
+    }
+    static thread_local PairParams PP;                       // ~20 KB: kept off the stack; rebuilt on every call
+    PP.S = P;
+    // one tensor map per weight block (encoded once per address: the arenas and the workspace do not move)
+    struct MapKey { const float* ptr; int rows; };
+    static thread_local MapKey cache_key[256];
+    static thread_local CUtensorMap cache_map[256];
+    static thread_local int cache_n = 0;
+    int n_maps = 0;
+    MapKey used[PR_MAXMAPS];
+    auto map_of = [&](const float* ptr, int rows, int* out) -> int {
+      for (int i = 0; i < n_maps; ++i)
+        if (used[i].ptr == ptr && used[i].rows == rows) { *out = i; return CUR_OK; }
+      CUR_REQUIRE(n_maps < PR_MAXMAPS, "too many weight blocks for the CTA-pair rows schedule");
+      int hit = -1;
+      for (int i = 0; i < cache_n; ++i)
+        if (cache_key[i].ptr == ptr && cache_key[i].rows == rows) { hit = i; break; }
+      if (hit < 0) {
+        hit = cache_n < 256 ? cache_n++ : 0;
+        CUR_TRY(tc_make_plain_map(&cache_map[hit], ptr, rows, H, H, PR_NC, PR_CK));
+        cache_key[hit].ptr = ptr; cache_key[hit].rows = rows;
+      }
+      PP.maps[n_maps] = cache_map[hit];
+      used[n_maps].ptr = ptr; used[n_maps].rows = rows;
+      *out = n_maps++;
+      return CUR_OK;
+    };
+    for (int rank = 0; rank < 2; ++rank) {
+      int m = 0;
+      PairChunk* pl = nullptr;
+      // a row block [nrows][256] as chunks of <= 64 rows of this rank's 128 columns; `exchanged`: the k rows are the
+      // columns of the previous layer's output, so the rank's own half comes first and the partner's half waits
+      auto rows_of = [&](const float* src, int nrows, int k0, bool exchanged) -> int {
+        int mi = 0;
+        CUR_TRY(map_of(src, nrows, &mi));
+        if (!exchanged) {
+          for (int r = 0; r < nrows; r += PR_CK) {
+            CUR_REQUIRE(m < PR_MAXCHUNK, "too many weight chunks for the CTA-pair rows schedule");
+            PairChunk& C = pl[m++];
+            C.map = mi; C.krow = r; C.nrows = (short)((nrows - r < PR_CK) ? nrows - r : PR_CK); C.wait = 0; C.k0 = k0 + r;
+          }
+          return CUR_OK;
+        }
+        for (int half = 0; half < 2; ++half) {
+          const int hk = (half == 0 ? rank : 1 - rank) * PR_NC;          // first k row of this half
+          for (int r = 0; r < PR_NC; r += PR_CK) {
+            CUR_REQUIRE(m < PR_MAXCHUNK, "too many weight chunks for the CTA-pair rows schedule");
+            PairChunk& C = pl[m++];
+            C.map = mi; C.krow = hk + r; C.nrows = PR_CK; C.wait = (short)((half == 1 && r == 0) ? 1 : 0); C.k0 = k0 + hk + r;
+          }
+        }
+        return CUR_OK;
+      };
+      auto forward_net = [&](const float* th, const NetLayout& NL, int* first) -> int {
+        const int before = m;
+        CUR_TRY(rows_of(th + NL.off_W0, NL.in_s, 0, false));
+        if (NL.in_g > 0) CUR_TRY(rows_of(th + NL.off_W0g, NL.in_g, NL.in_s, false));
+        if (first) *first = m - before;
+        for (int l = 1; l < L; ++l) CUR_TRY(rows_of(th + NL.off_W[l], H, 0, true));
+        return CUR_OK;
+      };
+      pl = PP.ch[0][rank]; m = 0;
+      CUR_TRY(forward_net(mP, LP, &PP.pch0[0]));
+      CUR_TRY(forward_net(mQ, LQ, &PP.pch0[1]));
+      for (int l = L - 1; l >= 1; --l) CUR_TRY(rows_of(w.TQ[l], H, 0, true));
+      for (int l = L - 1; l >= 1; --l) CUR_TRY(rows_of(w.TP[l], H, 0, true));
+      PP.nch[0][rank] = m;
+      pl = PP.ch[1][rank]; m = 0;
+      CUR_TRY(forward_net(tP, LP, nullptr));
+      CUR_TRY(forward_net(tQ, LQ, nullptr));
+      CUR_TRY(forward_net(mQ, LQ, nullptr));                                      // critic pair: main.Q(o,g,u) ...
+      for (int l = L - 1; l >= 1; --l) CUR_TRY(rows_of(w.TQ[l], H, 0, true));     // ... and its backward chain
+      PP.nch[1][rank] = m;
+    }
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[1];
+    pdl_config(cfg, at, (unsigned)(n / PR_ROWS) * 4u, S_THREADS, PR_SMEM_BYTES, s);   // (actor, critic) x (rank 0, rank 1)
+    CUR_CUDA_TRY(cudaLaunchKernelEx(&cfg, ddpg_stream_pair_kernel, PP));
+  } else {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
     pdl_config(cfg, at, 2 * n_ctas, S_THREADS, S_SMEM_BYTES, s);
@@ -1646,6 +2251,11 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     fprintf(stderr, "[rows timeline] build %lld | main.pi %lld | main.Q x2 %lld | wait target.Q %lld | "
                     "loss+bwd Q %lld | bwd pi %lld | total %lld cycles\n",
             t[1] - t[0], t[2] - t[1], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6], t[7] - t[0]);
+    if (use_pair) {
+      fprintf(stderr, "[pair main.pi stamps, cycles after build]");
+      for (int i = 8; i < 32 && t[i] != 0; ++i) fprintf(stderr, " %lld", t[i] - t[1]);
+      fprintf(stderr, "\n");
+    }
   }
 
   // ---- launch 2: weight gradients, one launch per 256-row chunk of the batch (K of the tiles)
@@ -1723,6 +2333,25 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     long long t[64];
     CUR_CUDA_TRY(cudaStreamSynchronize(s));
     CUR_CUDA_TRY(cudaMemcpy(t, tl_dev, sizeof(t), cudaMemcpyDeviceToHost));
+    {
+      // wall-clock spans (%globaltimer, ns) of every CTA of the two launches of this update
+      static long long sp[2048];
+      CUR_CUDA_TRY(cudaMemcpy(sp, tl_dev + 64, sizeof(sp), cudaMemcpyDeviceToHost));
+      for (int k = 0; k < 2; ++k) {
+        long long s0 = 0, e1 = 0, dmin = 1LL << 60, dmax = 0, dsum = 0; int cnt = 0;
+        for (int b = 0; b < 512; ++b) {
+          const long long a = sp[1024 * k + 2 * b], e = sp[1024 * k + 2 * b + 1];
+          if (a == 0 || e == 0) continue;
+          if (cnt == 0 || a < s0) s0 = a;
+          if (e > e1) e1 = e;
+          const long long dd = e - a;
+          dmin = dd < dmin ? dd : dmin; dmax = dd > dmax ? dd : dmax; dsum += dd; ++cnt;
+        }
+        if (cnt) fprintf(stderr, "[spans] %s: %d CTAs, CTA span min %lld / mean %lld / max %lld ns, first start -> last end %lld ns%s",
+                         k == 0 ? "stream kernel" : "dw kernel", cnt, dmin, dsum / cnt, dmax, e1 - s0, k == 0 ? "" : "\n");
+        if (k == 0) { fprintf(stderr, ", "); sp[2047] = e1; } else fprintf(stderr, "[spans] stream last end -> dw first start %lld ns\n", s0 - sp[2047]);
+      }
+    }
     for (int b = 0; b < 3; ++b) {
       const long long* q = t + 32 + 8 * b;
       fprintf(stderr, "[dw timeline] %s: prologue %lld | tile %lld | tail %lld | total %lld cycles (start +%lld after block 0)\n",

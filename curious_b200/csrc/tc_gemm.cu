@@ -606,6 +606,26 @@ static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols
   return CUR_OK;
 }
 
+// row-major [rows][cols] fp32 block, box_cols x box_rows tiles delivered dense (no swizzle) - the weight chunks of the
+// CTA-pair rows kernel (ddpg_rows.cu); rows beyond `rows` are zero-filled by the TMA unit
+int tc_make_plain_map(void* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  CUR_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult rc = fn(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled (plain) failed (%d): rows %lld cols %lld ld %lld",
+             (int)rc, (long long)rows, (long long)cols, (long long)ld);
+    return CUR_ERR_CUDA;
+  }
+  return CUR_OK;
+}
+
 int tc_make_map(void* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool mn_major) {
   return make_map(reinterpret_cast<CUtensorMap*>(map), ptr, rows, cols, ld, box_rows, mn_major);
 }
