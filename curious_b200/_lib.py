@@ -180,6 +180,7 @@ SIGNATURES = {
     'cur_ddpg_grads_group': (C.c_int, [C.c_void_p, C.POINTER(NetDesc), C.c_int, C.POINTER(DdpgExpert)]),
     'cur_ddpg_set_tensor_cores': (C.c_int, [C.c_int]),
     'cur_tc_chain_timeline': (C.c_int, [C.c_void_p]),
+    'cur_rows_timeline_dump': (C.c_int, []),
     'cur_ddpg_set_chain': (C.c_int, [C.c_int]),
     'cur_ddpg_uses_chain': (C.c_int, [C.POINTER(NetDesc), C.c_int64]),
     'cur_ddpg_uses_tensor_cores': (C.c_int, [C.POINTER(NetDesc), C.c_int64]),

@@ -84,6 +84,8 @@ struct StreamParams {
   float* q_pi;               // [n]
   long long* tl;             // optional debug timeline (clock64 stamps of CTA 0), CUR_ROWS_TIMELINE=1
   int dbg_skip_math;         // debug: consumers only wait/release (measures the pure streaming rate)
+  const int64_t* tl_step;    // debug: device step counter (update number of the timeline marks) or NULL
+  int pdl_late;              // programmatic dependent launch: trigger the next kernel when this CTA is done (not at its start)
   int fused_her;             // sample the CTA's 4 rows here (her, plan) instead of reading a staged batch
   HerPlan plan;
   cur_her_args her;
@@ -170,6 +172,17 @@ __device__ __forceinline__ void st_ll(unsigned long long* p, float v, uint32_t f
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(S_CONSUMERS) : "memory"); }
+
+
+// debug (CUR_ROWS_TIMELINE=1): first start / last end of the two launches of an update on the %globaltimer clock, in a ring
+// of 8 updates at tl[64 + 2048 + 4 * (update & 7)] = {stream first start, stream last end, dw first start, dw last end}
+constexpr int TL_MARKS = 64 + 2048;
+__device__ __forceinline__ void tl_mark_min(long long* p) {
+  atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)globaltimer_ns());
+}
+__device__ __forceinline__ void tl_mark_max(long long* p) {
+  atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)globaltimer_ns());
+}
 
 struct Ring {
   const SChunk* chunks;     // this CTA's chunk list (kernel-parameter space)
@@ -457,6 +470,7 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
 
   const int tid = threadIdx.x;
   if (P.tl != nullptr && tid == 0 && blockIdx.x < 512) P.tl[64 + 2 * blockIdx.x] = (long long)globaltimer_ns();
+  if (P.tl != nullptr && P.tl_step != nullptr && tid == 0) tl_mark_min(P.tl + TL_MARKS + 4 * (int)(*P.tl_step & 7));
   const uint32_t role = blockIdx.x & 1;                      // 0: actor chain, 1: critic chain (independent CTAs)
   const int64_t row0 = (int64_t)(blockIdx.x >> 1) * S_ROWS;
   const cur_net_desc& d = P.d;
@@ -470,7 +484,7 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  pdl_launch_dependents();
+  if (!P.pdl_late) pdl_launch_dependents();
   pdl_wait();               // everything below reads what the previous kernel (weight gradients + Adam of the last update) wrote
   __syncthreads();          // barriers initialised before the producer / consumers use them
 
@@ -569,6 +583,8 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
       float* t = xin; xin = xout; xout = t;
     }
     if (P.tl != nullptr && tid == 0 && blockIdx.x < 512) P.tl[65 + 2 * blockIdx.x] = (long long)globaltimer_ns();
+    if (P.tl != nullptr && P.tl_step != nullptr && tid == 0) tl_mark_max(P.tl + TL_MARKS + 4 * (int)(*P.tl_step & 7) + 1);
+    pdl_launch_dependents();
     return;
   }
 
@@ -689,6 +705,8 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   }
   S_TL(7);
   if (P.tl != nullptr && tid == 0 && blockIdx.x < 512) P.tl[65 + 2 * blockIdx.x] = (long long)globaltimer_ns();
+  if (P.tl != nullptr && P.tl_step != nullptr && tid == 0) tl_mark_max(P.tl + TL_MARKS + 4 * (int)(*P.tl_step & 7) + 1);
+  pdl_launch_dependents();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1350,6 +1368,7 @@ __device__ __noinline__ void xchg_timeout_check(unsigned long long t0, int* erro
 }
 
 struct DwTail {
+  int pdl_late;                    // trigger the dependent launch when the tile is done (not at the start)
   AdamCtx ax;                      // ax.theta == NULL: gradients only
   const float* neg_a_table;
   int table_len;
@@ -1757,16 +1776,50 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
   float* Bs = dw_smem + DW_KMAX * DW_LD;
   __shared__ GemmProb Ps;
   __shared__ DwCtx cx;
-  __shared__ unsigned int s_last;
+  // The launch that completes an update carries one extra CTA without a tile (the last block): it folds the loss partials
+  // of the stream kernel and bumps the device step counter once every tile CTA has read it.  (First version: every CTA
+  // fenced and took a ticket AFTER its tile and the last one to finish did the fold - ~3 us behind the slowest tile.)
+  const unsigned int n_tile_ctas = gridDim.x - (T.last_chunk ? 1u : 0u);
+  if (blockIdx.x >= n_tile_ctas) {
+    pdl_wait();
+    const long long st = T.step_counter ? *T.step_counter : 0;   // value BEFORE this update's bump
+    float* lp = As;                                              // the partials travel in parallel (one round trip) ...
+    for (int i = threadIdx.x; i < 4 * T.n_clusters; i += GEMM_THREADS) lp[i] = __ldcg(T.loss_part + i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float ssq = 0.f, sq = 0.f, sth = 0.f;                      // ... and are added in the fixed order c = 0, 1, ...
+      for (int c = 0; c < T.n_clusters; ++c) {
+        ssq += lp[4 * c + 0];
+        sq += lp[4 * c + 1];
+        sth += lp[4 * c + 2];
+      }
+      const float inv_n = 1.0f / (float)T.n;
+      const long long slot = (T.step_counter && T.ring > 0) ? st % T.ring : 0;
+      if (T.q_loss) T.q_loss[slot] = ssq * inv_n;                                                   // ddpg.py:439
+      if (T.pi_loss) T.pi_loss[slot] = -sq * inv_n + T.action_l2 * sth / (float)(T.n * T.dimu);     // ddpg.py:440-441
+      if (T.tl != nullptr) {
+        long long* nx = T.tl + TL_MARKS + 4 * (int)((st + 2) & 7);
+        nx[0] = 0x7fffffffffffffffLL; nx[1] = 0; nx[2] = 0x7fffffffffffffffLL; nx[3] = 0;
+      }
+      // a tile CTA takes its ticket after it has read the step counter: only then may the counter move
+      volatile unsigned int* tk = T.ticket;
+      while (*tk < n_tile_ctas) { }
+      if (T.step_counter) *T.step_counter = st + 1;
+      *T.ticket = 0u;
+      __threadfence();
+    }
+    pdl_launch_dependents();
+    return;
+  }
   long long* tl = nullptr;
   if (T.tl != nullptr && threadIdx.x == 0) {
     if (blockIdx.x == 0) tl = T.tl + 32;
     else if ((int)blockIdx.x == T.tl_skinny_block) tl = T.tl + 40;
-    else if (blockIdx.x == gridDim.x - 1) tl = T.tl + 48;
+    else if (blockIdx.x == n_tile_ctas - 1) tl = T.tl + 48;
   }
   if (tl) tl[0] = clock64();
   if (T.tl != nullptr && threadIdx.x == 0 && blockIdx.x < 512) T.tl[1088 + 2 * blockIdx.x] = (long long)globaltimer_ns();
-  pdl_launch_dependents();
+  if (!T.pdl_late) pdl_launch_dependents();
   pdl_wait();                                                    // activations / deltas of the stream kernel, the step counter
   int pi = 0;
 #pragma unroll 1
@@ -1784,11 +1837,13 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
   if (P.variant == DW_FULLK) dw_stage_fullk(P, As, Bs, tm * GT, tn * GT);
   else if (P.variant == DW_SKINNY) dw_stage_skinny(P, As, Bs, tile * GT);
   // ---- ... and what depends on the device step counter (two dependent round trips of thread 0) while they travel
-  const long long st = T.step_counter ? *T.step_counter : 0;     // value BEFORE this update's bump
-  // several workers per rank (19-worker-equivalent batches): the device counter counts micro-batches,
-  // update u = st / micro, launch j = st % micro of it adds its gradient to the sum of launches 0..j-1
-  const long long upd = st / T.micro, mb = st - upd * T.micro;
+  long long st = 0;
   if (threadIdx.x == 0) {
+    st = T.step_counter ? *T.step_counter : 0;                    // value BEFORE this update's bump
+    // several workers per rank (19-worker-equivalent batches): the device counter counts micro-batches,
+    // update u = st / micro, launch j = st % micro of it adds its gradient to the sum of launches 0..j-1
+    const long long upd = st / T.micro, mb = st - upd * T.micro;
+    if (T.tl != nullptr) tl_mark_min(T.tl + TL_MARKS + 4 * (int)(st & 7) + 2);
     cx.ax = T.ax;
     cx.opt = (T.ax.theta != nullptr && T.last_chunk && mb == T.micro - 1) ? 1 : 0;
     if (cx.opt && T.neg_a_table != nullptr) {
@@ -1803,6 +1858,7 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     if (cx.tl) cx.tl[0] = (long long)globaltimer_ns();
     if (T.parity_stride > 0) Ps.C += ((upd + 1) & 1) * T.parity_stride;
     Ps.accumulate = (mb > 0 || T.chunk > 0) ? 1 : 0;
+    if (T.last_chunk) atomicAdd(T.ticket, 1u);                    // the step counter has been read (its value is in use above)
   }
   if (tl) tl[1] = clock64();
   // (every tile function starts with a __syncthreads before it reads cx / Ps.C / Ps.accumulate)
@@ -1813,40 +1869,13 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
   } else {
     dw_tile_colsum(P, As, tile * DW_CS_COLS, T, cx);
   }
-  // ---- the last CTA to finish folds the loss partials and bumps the step counter
-  __syncthreads();
   if (tl) tl[2] = clock64();
   if (cx.tl && threadIdx.x == 0) cx.tl[3] = (long long)globaltimer_ns();
-  if (T.tl != nullptr && threadIdx.x == 0 && blockIdx.x < 512) T.tl[1089 + 2 * blockIdx.x] = (long long)globaltimer_ns();
-  if (!T.last_chunk) return;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int t = atomicAdd(T.ticket, 1u);
-    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+  if (T.tl != nullptr && threadIdx.x == 0) {
+    if (blockIdx.x < 512) T.tl[1089 + 2 * blockIdx.x] = (long long)globaltimer_ns();
+    tl_mark_max(T.tl + TL_MARKS + 4 * (int)(st & 7) + 3);
   }
-  __syncthreads();
-  if (s_last) {
-    // the partials travel in parallel (one round trip), thread 0 then adds them in the fixed order c = 0, 1, ...
-    float* lp = As;
-    for (int i = threadIdx.x; i < 4 * T.n_clusters; i += GEMM_THREADS) lp[i] = __ldcg(T.loss_part + i);
-    __syncthreads();
-  }
-  if (s_last && threadIdx.x == 0) {
-    const float* lp = As;
-    float ssq = 0.f, sq = 0.f, sth = 0.f;
-    for (int c = 0; c < T.n_clusters; ++c) {
-      ssq += lp[4 * c + 0];
-      sq += lp[4 * c + 1];
-      sth += lp[4 * c + 2];
-    }
-    const float inv_n = 1.0f / (float)T.n;
-    const long long slot = (T.step_counter && T.ring > 0) ? st % T.ring : 0;
-    if (T.q_loss) T.q_loss[slot] = ssq * inv_n;                                                   // ddpg.py:439
-    if (T.pi_loss) T.pi_loss[slot] = -sq * inv_n + T.action_l2 * sth / (float)(T.n * T.dimu);     // ddpg.py:440-441
-    if (T.step_counter) *T.step_counter = st + 1;
-    *T.ticket = 0u;
-    __threadfence();
-  }
+  pdl_launch_dependents();
   if (tl) tl[3] = clock64();
 }
 
@@ -1958,7 +1987,7 @@ static void build_dw_batch(GemmBatch& G, const NetLayout& LQ, const NetLayout& L
 // without - the early-scheduled CTAs of the next kernel do not pay for what they displace - so it is off by default)
 static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, unsigned grid, unsigned block, size_t smem,
                        cudaStream_t s) {
-  static const bool on = getenv("CUR_PDL") != nullptr && getenv("CUR_PDL")[0] == '1';
+  static const bool on = getenv("CUR_PDL") != nullptr && (getenv("CUR_PDL")[0] == '1' || getenv("CUR_PDL")[0] == '2');
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid, 1, 1);
   cfg.blockDim = dim3(block, 1, 1);
@@ -1973,6 +2002,32 @@ static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, unsigne
 }  // namespace cur
 
 using namespace cur;
+
+static long long* g_rows_tl = nullptr;     // debug timeline buffer of cur_ddpg_rows_step (CUR_ROWS_TIMELINE=1)
+
+// debug: after a run with CUR_ROWS_TIMELINE=1 (CUDA graph or not), print where the last updates spent their time on the
+// %globaltimer clock: per update the span of the two launches and the gaps between them
+extern "C" int cur_rows_timeline_dump(void) {
+  CUR_REQUIRE(g_rows_tl != nullptr, "no timeline recorded (set CUR_ROWS_TIMELINE=1 before the first update)");
+  CUR_CUDA_TRY(cudaDeviceSynchronize());
+  long long m[32];
+  CUR_CUDA_TRY(cudaMemcpy(m, g_rows_tl + TL_MARKS, sizeof(m), cudaMemcpyDeviceToHost));
+  // order the ring by the stream kernel's start
+  int idx[8], n = 0;
+  for (int i = 0; i < 8; ++i)
+    if (m[4 * i] != 0x7fffffffffffffffLL && m[4 * i + 1] != 0 && m[4 * i + 3] != 0) idx[n++] = i;
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j)
+      if (m[4 * idx[j]] < m[4 * idx[i]]) { int t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
+  for (int i = 0; i < n; ++i) {
+    const long long* q = m + 4 * idx[i];
+    fprintf(stderr, "[update marks] stream %lld ns | gap %lld | dw %lld ns", q[1] - q[0], q[2] - q[1], q[3] - q[2]);
+    if (i + 1 < n) fprintf(stderr, " | gap to the next update's stream kernel %lld ns | update period %lld ns",
+                           m[4 * idx[i + 1]] - q[3], m[4 * idx[i + 1]] - q[0]);
+    fprintf(stderr, "\n");
+  }
+  return CUR_OK;
+}
 
 extern "C" int cur_ddpg_rows_owner_map(const cur_net_desc* d, int64_t batch, int world, int32_t* owner) {
   CUR_TRY(check_desc(d));
@@ -2138,15 +2193,21 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   CUR_REQUIRE(nc <= S_MAXCHUNK_T, "too many weight chunks for the rows schedule");
   P.nchunks_t = nc;
 
-  static long long* tl_dev = nullptr;
+  long long*& tl_dev = g_rows_tl;
   static int tl_calls = 0;
   const bool tl_on = getenv("CUR_ROWS_TIMELINE") != nullptr;
   if (tl_on && tl_dev == nullptr) {
-    CUR_CUDA_TRY(cudaMalloc(&tl_dev, (64 + 2048) * sizeof(long long)));
-    CUR_CUDA_TRY(cudaMemset(tl_dev, 0, (64 + 2048) * sizeof(long long)));
+    CUR_CUDA_TRY(cudaMalloc(&tl_dev, (TL_MARKS + 32) * sizeof(long long)));
+    CUR_CUDA_TRY(cudaMemset(tl_dev, 0, (TL_MARKS + 32) * sizeof(long long)));
+    long long init[32];
+    for (int i = 0; i < 32; ++i) init[i] = (i & 1) ? 0 : 0x7fffffffffffffffLL;
+    CUR_CUDA_TRY(cudaMemcpy(tl_dev + TL_MARKS, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   P.tl = tl_on ? tl_dev : nullptr;
+  P.tl_step = h->step_counter;
   P.dbg_skip_math = getenv("CUR_ROWS_SKIP_MATH") != nullptr;
+  static const int pdl_late = (getenv("CUR_PDL") != nullptr && getenv("CUR_PDL")[0] == '2') ? 1 : 0;
+  P.pdl_late = pdl_late;
 
   const unsigned int n_ctas = (unsigned int)(n / S_ROWS);
   // CTA-pair form (column split over a 2-CTA cluster, 8 rows per pair): half the weight bytes per SM
@@ -2303,6 +2364,7 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     T.xc.res_mc = x->mc_region ? reinterpret_cast<unsigned long long*>(x->mc_region) + x->arena : nullptr;
   }
   T.tl = tl_on ? tl_dev : nullptr;
+  T.pdl_late = pdl_late;
   const AdamCtx ax_full = T.ax;
   const int n_chunks = (int)((n + DW_KMAX - 1) / DW_KMAX);
   for (int c = 0; c < n_chunks; ++c) {
@@ -2314,7 +2376,7 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     const int tiles = plan_dw_batch(G);
     CUR_REQUIRE(tiles > 0, "weight-gradient problems do not fit the rows schedule (unaligned dims)");
     // CTAs of the exchange spin on their peers: every tile of the launch must be resident at once
-    CUR_REQUIRE(!T.xc_on || tiles <= dw_resident, "too many weight-gradient tiles for the in-launch gradient exchange");
+    CUR_REQUIRE(!T.xc_on || tiles + 1 <= dw_resident, "too many weight-gradient tiles for the in-launch gradient exchange");
     T.chunk = c; T.last_chunk = last ? 1 : 0;
     T.ax = ax_full;
     if (!last) T.ax.theta = nullptr;             // the optimiser runs once, on the complete sum
@@ -2324,7 +2386,7 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     {
       cudaLaunchConfig_t cfg;
       cudaLaunchAttribute at[1];
-      pdl_config(cfg, at, (unsigned)tiles, GEMM_THREADS, DW_SMEM_BYTES, s);
+      pdl_config(cfg, at, (unsigned)tiles + (last ? 1u : 0u), GEMM_THREADS, DW_SMEM_BYTES, s);   // + the bookkeeping CTA
       CUR_CUDA_TRY(cudaLaunchKernelEx(&cfg, rows_dw_kernel, G, T));
     }
     CUR_CHECK_LAUNCH();

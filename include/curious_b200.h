@@ -539,6 +539,9 @@ int cur_ddpg_uses_tensor_cores(const cur_net_desc* d, int64_t batch);
  * split-K weight-gradient GEMMs.  mode -1: default (on; CUR_DDPG_CHAIN=0 turns it off), 0: level-by-level schedule, 1: on. */
 int cur_ddpg_set_chain(int mode);
 int cur_ddpg_uses_chain(const cur_net_desc* d, int64_t batch);
+/* debug: after updates run with CUR_ROWS_TIMELINE=1 (rows schedule, CUDA graph or not), print to stderr the %globaltimer
+ * span of the two launches of the last updates and the gaps between them */
+int cur_rows_timeline_dump(void);
 /* debug: in-kernel clock64 timeline of the chain kernel's first actor / critic CTA (1024 x int64 device buffer, or NULL) */
 int cur_tc_chain_timeline(long long* device_buffer_1024);
 int64_t cur_tc_gemm_workspace_floats(int64_t M, int64_t N, int64_t K, int a_trans);

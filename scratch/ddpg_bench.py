@@ -19,3 +19,6 @@ t0 = time.perf_counter(); e0.record()
 for _ in range(N): ag.train()
 e1.record(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
 print('sched=%s ' % sched + 'graph=%s B=%d: device %.1f us/update, host issue %.1f us/update, wall %.1f us/update' % (graph, B, 1e3 * e0.elapsed_time(e1) / N, 1e6 * (t1 - t0) / N, 1e6 * (t2 - t0) / N))
+if os.environ.get('CUR_ROWS_TIMELINE'):
+    from curious_b200 import _lib
+    _lib.load().cur_rows_timeline_dump()
