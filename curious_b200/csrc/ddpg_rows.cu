@@ -45,7 +45,7 @@ constexpr int S_H = 256;                 // hidden units
 constexpr int S_CONSUMERS = 256;         // 8 consumer warps
 constexpr int S_THREADS = S_CONSUMERS + 32;   // + 1 producer warp
 constexpr int S_CK = 32;                 // k rows per weight chunk
-constexpr int S_NSLOT = 4;               // ring slots
+constexpr int S_NSLOT = 4;               // ring slots (a fifth slot - one more chunk in flight while the CTA samples its rows - measured no gain)
 constexpr int S_SLOT = S_CK * S_H;       // floats per slot (32 KB)
 constexpr int S_MAXL = 4;                // hidden layers supported by this schedule
 constexpr int S_MAXCHUNK = 128;          // weight chunks of the main CTA (L = 4: 2 * 33 + 2 * 24 = 114)
@@ -1368,6 +1368,7 @@ __device__ __noinline__ void xchg_timeout_check(unsigned long long t0, int* erro
 }
 
 struct DwTail {
+  int dbg_skip_stage;              // debug (CUR_DW_SKIP_STAGE=1): tiles run on whatever their shared memory holds
   int pdl_late;                    // trigger the dependent launch when the tile is done (not at the start)
   AdamCtx ax;                      // ax.theta == NULL: gradients only
   const float* neg_a_table;
@@ -1400,6 +1401,7 @@ struct DwCtx {
   int owner;                       // the rank that does (mode 1)
   uint32_t flag;                   // update number travelling with the data
   long long* tl;                   // this tile's stamps or NULL
+  long long* dbg;                  // debug: clock64 stamps inside a traced full-K tile ([4..7] of its timeline row) or NULL
 };
 
 // Sum of the world's partial tiles in rank order (bit-identical on every reducer): g[e] holds this rank's partial on
@@ -1601,6 +1603,9 @@ constexpr size_t DW_SMEM_BYTES = (size_t)2 * DW_KMAX * DW_LD * 4;
 
 // ---- stage A[k][m0..m0+32) and B[k][n0..n0+32) for every k (zero fill past the edges); issued before anything that
 // depends on the device step counter, so that the two dependent round trips of that setup overlap this one
+// (Committing the burst as 4 groups of 64 k rows and running the math of a group while the later ones travel was measured
+// SLOWER - 55.3 instead of 53.4 us per update: the last operands land at +12.3 k cycles instead of +8.2 k, the cp.async
+// writes and the LDS of the math share the same shared-memory pipe.)
 __device__ __forceinline__ void dw_stage_fullk(const GemmProb& P, float* As, float* Bs, int m0, int n0) {
   const int tid = threadIdx.x;
 #pragma unroll
@@ -1620,6 +1625,7 @@ __device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, floa
   const int tid = threadIdx.x;
   cp_wait0();
   __syncthreads();
+  if (tid == 0 && cx.dbg) cx.dbg[4] = clock64();
   const int kg = tid >> 6, lt = tid & 63, ty = lt >> 3, tx = lt & 7;
   float2 acc[4][2];
 #pragma unroll
@@ -1641,6 +1647,7 @@ __device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, floa
     acc[3][1] = __ffma2_rn(make_float2(a.w, a.w), b23, acc[3][1]);
   }
   __syncthreads();                       // everybody is done with the staged tiles: reuse them for the partials
+  if (tid == 0 && cx.dbg) cx.dbg[5] = clock64();
   float* red = As;                       // 4 x [32][32]
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -1664,7 +1671,9 @@ __device__ __forceinline__ void dw_tile_fullk(const GemmProb& P, float* As, floa
     c[j] = P.C + (int64_t)gm * P.ldc + gn;
     v[j] = (red[i] + red[GT * GT + i]) + (red[2 * GT * GT + i] + red[3 * GT * GT + i]);
   }
+  if (tid == 0 && cx.dbg) cx.dbg[6] = clock64();
   dw_finish<NE>(T, cx, c, ok, P.accumulate != 0, v, th);
+  if (tid == 0 && cx.dbg) cx.dbg[7] = clock64();
   if (keep_t) {
 #pragma unroll
     for (int j = 0; j < NE; ++j) {
@@ -1822,8 +1831,17 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
   if (!T.pdl_late) pdl_launch_dependents();
   pdl_wait();                                                    // activations / deltas of the stream kernel, the step counter
   int pi = 0;
+  {
+    // the problem of this tile: last p with tile_begin[p] <= blockIdx.x (bisection: a linear walk over the ~30 problems
+    // cost the last blocks of the grid - the ones that finish last - ~2 k cycles of dependent constant-bank reads)
+    int lo = 0, hi = G.n - 1;
 #pragma unroll 1
-  while (pi + 1 < G.n && (int)blockIdx.x >= G.p[pi + 1].tile_begin) ++pi;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((int)blockIdx.x >= G.p[mid].tile_begin) lo = mid; else hi = mid - 1;
+    }
+    pi = lo;
+  }
   {
     const int* src = reinterpret_cast<const int*>(&G.p[pi]);
     int* dst = reinterpret_cast<int*>(&Ps);
@@ -1834,7 +1852,8 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
   const int tile = blockIdx.x - P.tile_begin;
   const int tm = (P.variant == DW_FULLK) ? tile / P.tiles_n : 0, tn = tile - tm * P.tiles_n;
   // ---- the operands first (one round trip) ...
-  if (P.variant == DW_FULLK) dw_stage_fullk(P, As, Bs, tm * GT, tn * GT);
+  if (T.dbg_skip_stage) {                                        // debug: what the launch costs without its operand traffic
+  } else if (P.variant == DW_FULLK) dw_stage_fullk(P, As, Bs, tm * GT, tn * GT);
   else if (P.variant == DW_SKINNY) dw_stage_skinny(P, As, Bs, tile * GT);
   // ---- ... and what depends on the device step counter (two dependent round trips of thread 0) while they travel
   long long st = 0;
@@ -1855,6 +1874,7 @@ rows_dw_kernel(const __grid_constant__ GemmBatch G, const __grid_constant__ DwTa
     cx.own = (!T.xc_on || T.xc.mode == 0 || cx.owner == T.xc.rank) ? 1 : 0;
     cx.flag = (uint32_t)(upd + 1);
     cx.tl = (cx.xc_on && T.xc.tl != nullptr) ? T.xc.tl + 4 * (int64_t)blockIdx.x : nullptr;
+    cx.dbg = tl;
     if (cx.tl) cx.tl[0] = (long long)globaltimer_ns();
     if (T.parity_stride > 0) Ps.C += ((upd + 1) & 1) * T.parity_stride;
     Ps.accumulate = (mb > 0 || T.chunk > 0) ? 1 : 0;
@@ -1986,8 +2006,11 @@ static void build_dw_batch(GemmBatch& G, const NetLayout& LQ, const NetLayout& L
 // launch configuration; CUR_PDL=1 adds programmatic stream serialisation (measured: batch 256 60.2 us with, 58.3 us
 // without - the early-scheduled CTAs of the next kernel do not pay for what they displace - so it is off by default)
 static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, unsigned grid, unsigned block, size_t smem,
-                       cudaStream_t s) {
-  static const bool on = getenv("CUR_PDL") != nullptr && (getenv("CUR_PDL")[0] == '1' || getenv("CUR_PDL")[0] == '2');
+                       cudaStream_t s, int which = 0 /* 0: stream kernel, 1: weight-gradient launch */) {
+  // CUR_PDL: 1 both launches may start early (trigger at the start of the previous kernel), 2 both with the trigger at the
+  // END of the previous kernel's CTAs, 3 only the weight-gradient launch, 4 only the stream kernel
+  static const char mode = getenv("CUR_PDL") != nullptr ? getenv("CUR_PDL")[0] : '0';
+  const bool on = mode == '1' || mode == '2' || (mode == '3' && which == 1) || (mode == '4' && which == 0);
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid, 1, 1);
   cfg.blockDim = dim3(block, 1, 1);
@@ -2365,6 +2388,7 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
   }
   T.tl = tl_on ? tl_dev : nullptr;
   T.pdl_late = pdl_late;
+  T.dbg_skip_stage = getenv("CUR_DW_SKIP_STAGE") != nullptr;
   const AdamCtx ax_full = T.ax;
   const int n_chunks = (int)((n + DW_KMAX - 1) / DW_KMAX);
   for (int c = 0; c < n_chunks; ++c) {
@@ -2386,7 +2410,7 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
     {
       cudaLaunchConfig_t cfg;
       cudaLaunchAttribute at[1];
-      pdl_config(cfg, at, (unsigned)tiles + (last ? 1u : 0u), GEMM_THREADS, DW_SMEM_BYTES, s);   // + the bookkeeping CTA
+      pdl_config(cfg, at, (unsigned)tiles + (last ? 1u : 0u), GEMM_THREADS, DW_SMEM_BYTES, s, 1);   // + the bookkeeping CTA
       CUR_CUDA_TRY(cudaLaunchKernelEx(&cfg, rows_dw_kernel, G, T));
     }
     CUR_CHECK_LAUNCH();
@@ -2419,6 +2443,8 @@ extern "C" int cur_ddpg_rows_step(void* stream, const cur_net_desc* d, float* th
       fprintf(stderr, "[dw timeline] %s: prologue %lld | tile %lld | tail %lld | total %lld cycles (start +%lld after block 0)\n",
               b == 0 ? "block 0 (output-layer tile)" : b == 1 ? "first full-K tile" : "last block", q[1] - q[0], q[2] - q[1],
               q[3] - q[2], q[3] - q[0], q[0] - t[32]);
+      if (b > 0) fprintf(stderr, "              operands landed +%lld | math done +%lld | partials summed +%lld | finish (Adam) done +%lld | end +%lld\n",
+                         q[4] - q[0], q[5] - q[0], q[6] - q[0], q[7] - q[0], q[2] - q[0]);
     }
   }
   CUR_CHECK_LAUNCH();
