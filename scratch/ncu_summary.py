@@ -19,7 +19,7 @@ for r in rows[2:]:
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]; idx = {n: i for i, n in enumerate(h)}
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) == len(h) and r != h and r[idx['# Samples']].strip().isdigit()]   # (several results: later header rows are dropped, the sites of all results are pooled)
 stalls = [n for n in h if n.startswith('stall_') and 'Not Issued' not in n]
 tot = sum(int(r[idx['# Samples']] or 0) for r in data)
 print('SASS instructions: %d, warp stall samples: %d' % (len(data), tot))
