@@ -565,6 +565,9 @@ struct GroupBatcher {
 static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_e, int64_t n) {
   const NetLayout LQ = net_layout(*d, 0), LP = net_layout(*d, 1);
   const int L = d->layers, H = d->hidden;
+  // ---- chain schedule, one agent: the 3xTF32 weight halves are split on a side stream beside the input preparation
+  if (n_e == 1 && use_chain(*d, n))
+    CUR_TRY(tc_chain_presplit_async(s, E[0].mQ, E[0].tQ, E[0].w.chain_wsplit, r4(LQ.total) + r4(LP.total)));
   // ---- inputs
   for (int i = 0; i < n_e; ++i) {
     Expert& x = E[i];
@@ -603,6 +606,7 @@ static int grads_levels(cudaStream_t s, const cur_net_desc* d, Expert* E, int n_
       io.gamma = x.h->gamma; io.clip_return = x.h->clip_return; io.action_l2 = x.h->action_l2; io.clip_pos = x.h->clip_pos_returns;
       io.loss_part = w.chain_loss; io.q_loss = x.q_loss; io.pi_loss = x.pi_loss;
       io.step_counter = x.h->step_counter; io.loss_ring = x.h->loss_ring;
+      io.side_ok = n_e == 1 ? 1 : 0;
       cudaStream_t cs = s;                         // several experts: independent chains on concurrent streams
       if (n_e > 1) CUR_TRY(tc_chain_lane(i, &cs));
       CUR_TRY(tc_chain_launch(cs, *d, io));

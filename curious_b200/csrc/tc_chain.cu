@@ -696,8 +696,12 @@ __global__ void __launch_bounds__(256) tc_chain_rowsum_kernel(const __grid_const
 struct ChainSide {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork0 = nullptr, split_done = nullptr;   // the weight split runs beside the input preparation
   int device = -1;
   bool pending = false;
+  bool split_pending = false;                          // tc_chain_presplit_async ran: tc_chain_launch waits instead of splitting
+  bool loss_deferred = false;                          // the loss fold of the last chain launch goes with the row sums
+  ChainLossParams loss;
 };
 static int chain_side(ChainSide** out) {
   static thread_local ChainSide ss;
@@ -707,8 +711,12 @@ static int chain_side(ChainSide** out) {
     CUR_CUDA_TRY(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
     CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
     CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.fork0, cudaEventDisableTiming));
+    CUR_CUDA_TRY(cudaEventCreateWithFlags(&ss.split_done, cudaEventDisableTiming));
     ss.device = dev;
     ss.pending = false;
+    ss.split_pending = false;
+    ss.loss_deferred = false;
   }
   *out = &ss;
   return CUR_OK;
@@ -777,6 +785,11 @@ int tc_chain_rowsums(cudaStream_t s, TcRowSumBatch& R) {
   CUR_TRY(chain_side(&ss));
   CUR_CUDA_TRY(cudaEventRecord(ss->fork, s));
   CUR_CUDA_TRY(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+  if (ss->loss_deferred) {                       // the loss fold only needs the chain kernel's partials: off the GEMM's path
+    tc_chain_loss_kernel<<<1, 32, 0, ss->stream>>>(ss->loss);
+    CUR_CHECK_LAUNCH();
+    ss->loss_deferred = false;
+  }
   tc_chain_rowsum_kernel<<<blocks, 256, 0, ss->stream>>>(R);
   CUR_CHECK_LAUNCH();
   CUR_CUDA_TRY(cudaEventRecord(ss->join, ss->stream));
@@ -805,6 +818,21 @@ bool tc_chain_supported(const cur_net_desc& d, int64_t n) {
   for (int l = 1; l < d.layers; ++l)
     if ((q.off_W[l] % 4) || (p.off_W[l] % 4)) return false;
   return n / CH_BM <= (1 << 20);
+}
+
+// The 3xTF32 halves of the weights only depend on the previous update: split them on the side stream while the caller's
+// stream prepares the inputs (call before the input preparation is launched; tc_chain_launch then waits for the event).
+int tc_chain_presplit_async(cudaStream_t s, const float* mQ, const float* tQ, float* wsplit, int64_t arena) {
+  ChainSide* ss = nullptr;
+  CUR_TRY(chain_side(&ss));
+  CUR_CUDA_TRY(cudaEventRecord(ss->fork0, s));
+  CUR_CUDA_TRY(cudaStreamWaitEvent(ss->stream, ss->fork0, 0));
+  const int64_t arena4 = arena / 4;
+  tc_chain_presplit_kernel<<<(unsigned)((2 * arena4 + 255) / 256), 256, 0, ss->stream>>>(mQ, tQ, wsplit, arena4);
+  CUR_CHECK_LAUNCH();
+  CUR_CUDA_TRY(cudaEventRecord(ss->split_done, ss->stream));
+  ss->split_pending = true;
+  return CUR_OK;
 }
 
 static long long* g_chain_timeline = nullptr;
@@ -849,7 +877,12 @@ int tc_chain_launch(cudaStream_t s, const cur_net_desc& d, const TcChainIO& io) 
   // ---- the weights as 3xTF32 halves, once per call (the weights change with every update)
   const int64_t arena = r4(LQ.total) + r4(LP.total);
   CUR_REQUIRE(io.wsplit != nullptr && io.mP == io.mQ + r4(LQ.total) && io.tP == io.tQ + r4(LQ.total), "parameter arenas expected");
-  {
+  ChainSide* side = nullptr;
+  CUR_TRY(chain_side(&side));
+  if (io.side_ok && side->split_pending) {
+    CUR_CUDA_TRY(cudaStreamWaitEvent(s, side->split_done, 0));      // split by tc_chain_presplit_async
+    side->split_pending = false;
+  } else {
     const int64_t arena4 = arena / 4;
     tc_chain_presplit_kernel<<<(unsigned)((2 * arena4 + 255) / 256), 256, 0, s>>>(io.mQ, io.tQ, io.wsplit, arena4);
     CUR_CHECK_LAUNCH();
@@ -903,8 +936,13 @@ int tc_chain_launch(cudaStream_t s, const cur_net_desc& d, const TcChainIO& io) 
   ChainLossParams LPm;
   LPm.part = io.loss_part; LPm.tiles = tiles; LPm.dimu = d.dimu; LPm.ring = io.loss_ring; LPm.n = io.n;
   LPm.action_l2 = io.action_l2; LPm.q_loss = io.q_loss; LPm.pi_loss = io.pi_loss; LPm.step_counter = io.step_counter;
-  tc_chain_loss_kernel<<<1, 32, 0, s>>>(LPm);
-  CUR_CHECK_LAUNCH();
+  if (io.side_ok) {                              // one agent on the caller's stream: the fold travels with the row sums
+    side->loss = LPm;
+    side->loss_deferred = true;
+  } else {
+    tc_chain_loss_kernel<<<1, 32, 0, s>>>(LPm);
+    CUR_CHECK_LAUNCH();
+  }
   return CUR_OK;
 }
 

@@ -67,6 +67,8 @@ struct TcChainIO {
   float *q_loss, *pi_loss;
   int64_t* step_counter;
   int loss_ring;
+  int side_ok;                                          // one agent, launched on the caller's stream: the weight split may have run on
+                                                        // the side stream (tc_chain_presplit_async) and the loss fold goes with the row sums
 };
 // bias / output-layer weight gradients from the transposed copies (tc_chain_rowsum_kernel)
 struct TcRowSum {
@@ -87,6 +89,7 @@ int tc_chain_lane(int i, cudaStream_t* out);
 int tc_chain_lanes_join(cudaStream_t s);
 bool tc_chain_supported(const cur_net_desc& d, int64_t n);
 int tc_chain_launch(cudaStream_t s, const cur_net_desc& d, const TcChainIO& io);
+int tc_chain_presplit_async(cudaStream_t s, const float* mQ, const float* tQ, float* wsplit, int64_t arena);
 void tc_chain_set_timeline(long long* dev);             // 128 x int64 debug stamps (CTA 0 / CTA 1) or NULL
 // row-major [rows][cols] fp32 operand as a TMA tensor map in the layouts the tcgen05 descriptors expect (tc_gemm.cu)
 int tc_make_map(void* map /* CUtensorMap */, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
