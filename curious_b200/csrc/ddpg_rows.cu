@@ -360,12 +360,24 @@ __device__ __noinline__ void build_x(const StreamParams& P, float* xT, int NR, i
 // the same per-row device functions as her_sample_kernel (bit-identical batches).  Both CTAs of a pair sample the
 // same rows (a 4 x ~0.5 KB gather).
 __device__ __forceinline__ void sample_rows(const StreamParams& P, int64_t row0, float* stage, const float** m_src,
-                                            float* s_r, int nrows = S_ROWS) {
+                                            float* s_r, float* scratch /* >= 1 KB, 16-byte aligned */, int nrows = S_ROWS) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const HerPlan& pl = P.plan;
   HerRow row;
   row.ft = -1; row.choice = -1; row.ep = 0; row.t = 0; row.ttr = -1; row.her = false;
-  if (tid < nrows) her_draw_row(P.her, pl, row0 + tid, row, m_src + 3 * tid);
+  // the device control block of the sampler (counts, sizes, cdf, the step counter behind a pointer) in TWO round trips: the
+  // draw below used to read it in place, ~7 dependent L2 round trips in front of every chain
+  static_assert(sizeof(cur_her_dyn) % 4 == 0 && sizeof(cur_her_dyn) + 8 <= 4 * 256, "control block copy fits the scratch area");
+  cur_her_dyn* dyn_s = reinterpret_cast<cur_her_dyn*>(scratch);
+  int64_t* step_s = reinterpret_cast<int64_t*>(scratch + sizeof(cur_her_dyn) / 4);
+  if (P.her.dyn != nullptr) {
+    if (tid < (int)(sizeof(cur_her_dyn) / 4))
+      reinterpret_cast<uint32_t*>(dyn_s)[tid] = __ldcg(reinterpret_cast<const uint32_t*>(P.her.dyn) + tid);
+    consumer_sync();
+    if (tid == 0) *step_s = __ldcg(reinterpret_cast<const long long*>(dyn_s->step));
+    consumer_sync();
+  }
+  if (tid < nrows) her_draw_row(P.her, pl, row0 + tid, row, m_src + 3 * tid, dyn_s, step_s);
   consumer_sync();
   if (warp < nrows) {
     const int per_row = pl.img4 + pl.fut4 + pl.cold4;   // (cold rows only for an `info` reward or relative goals)
@@ -512,7 +524,7 @@ ddpg_stream_kernel(const __grid_constant__ StreamParams P) {
   const float inv_n = 1.0f / (float)P.grad_rows;      // scale of the backward seeds
   const float* stage = nullptr;
   if (P.fused_her) {
-    sample_rows(P, row0, her_stage, m_src, s_r);
+    sample_rows(P, row0, her_stage, m_src, s_r, red);
     stage = her_stage;
   }
 
@@ -962,7 +974,7 @@ __device__ __forceinline__ void pair_consumer(const PairParams& PP, float* ringf
   const float inv_n = 1.0f / (float)P.grad_rows;      // scale of the backward seeds
   const float* stage = nullptr;
   if (P.fused_her) {
-    sample_rows(P, row0, her_stage, m_src, s_r, PR_ROWS);
+    sample_rows(P, row0, her_stage, m_src, s_r, red, PR_ROWS);
     stage = her_stage;
   }
   const float hi_clip = P.clip_pos ? 0.f : INFINITY;

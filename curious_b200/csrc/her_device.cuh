@@ -30,13 +30,16 @@ struct HerRow {
 
 // Draws of concat row j (injected stream or Philox), segment lookup, and the three source addresses of the row:
 // src[0] main span, src[1] future achieved goal (NULL: not a HER row), src[2] cold row (NULL: not requested).
+// dyn_copy / step_val (optional): the caller's copy of the device control block and of *dyn->step, fetched up front in two round
+// trips (the rows kernels draw on the critical path of every update; read in place the block costs ~7 dependent ones).
 __device__ __forceinline__ void her_draw_row(const cur_her_args& a, const HerPlan& pl, int64_t j, HerRow& row,
-                                             const float** src) {
+                                             const float** src, const cur_her_dyn* dyn_copy = nullptr,
+                                             const int64_t* step_val = nullptr) {
   const cur_layout& L = a.L;
   const int64_t c = a.perm ? (int64_t)a.perm[j] : j;
   // segment lookup: concat rows are the segments' counts laid end to end (ddpg.py:326-345)
   // (with a device control block - CUDA-graph replays - counts / sizes / counter come from memory)
-  const cur_her_dyn* dyn = a.dyn;
+  const cur_her_dyn* dyn = (a.dyn != nullptr && dyn_copy != nullptr) ? dyn_copy : a.dyn;
   int s = 0;
   int64_t acc = 0;
   while (s + 1 < a.n_segments) {
@@ -49,7 +52,7 @@ __device__ __forceinline__ void her_draw_row(const cur_her_args& a, const HerPla
   const int E = dyn ? dyn->n_episodes[s] : a.seg[s].n_episodes;
   row.ttr = a.seg[s].task_to_replay;
   row.choice = -1;
-  const uint64_t call_offset = a.call_offset + (dyn ? (uint64_t)*dyn->step : 0ull);
+  const uint64_t call_offset = a.call_offset + (dyn ? (uint64_t)(step_val ? *step_val : *dyn->step) : 0ull);
   double u_her, u_off;
   if (a.inj_ep != nullptr) {
     row.ep = a.inj_ep[c];
