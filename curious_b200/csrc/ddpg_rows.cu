@@ -23,12 +23,14 @@
 //             activations as one broadcast LDS.128 per k; activations never leave shared memory between
 //             layers.  History (profiles/README.md): column split over an 8-CTA cluster with a per-layer
 //             exchange (lost to the synchronisation), one CTA for everything, main / target CTA pair with
-//             main.Q streamed once for 8 stacked rows (FFMA-bound passes, idle target CTA), this split.
+//             main.Q streamed once for 8 stacked rows (FFMA-bound passes, idle target CTA), this split; round 2:
+//             ddpg_stream_pair_kernel, the columns of every layer split over a 2-CTA cluster (half the weight
+//             bytes per SM, st.async exchange through distributed shared memory) - correct, slower, opt-in.
 //   launch 2  rows_dw_kernel     every dW = X^T dY and db = 1^T dY of both nets as one grouped GEMM with
 //             the full batch as K (deterministic, no atomics), written into the flat GetFlat-ordered
 //             gradient arena; optionally Adam is applied to the element in the same epilogue (world
-//             size 1: no all-reduce between gradient and step).  The last CTA to finish folds the
-//             per-CTA loss partials and bumps the device step counter.
+//             size 1: no all-reduce between gradient and step).  One extra CTA without a tile folds the
+//             per-CTA loss partials and bumps the device step counter beside the tiles.
 //
 // All arithmetic is FP32 FFMA (IEEE); see DESIGN.md section 4 for why tensor cores do not apply here.
 #include <stdlib.h>
