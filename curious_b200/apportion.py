@@ -65,9 +65,10 @@ def active_modules(change_last, tasks_ag_id, tasks_g_id):
     """Modules whose achieved-goal slice moved by the last step; only j<5 when nb_tasks>=5 (ddpg.py:178-184)."""
     nb = len(tasks_g_id)
     active = []
+    moved = np.asarray(change_last).tolist()          # plain Python truth values: a dozen scalar look-ups beat fancy indexing
     for j in range(nb):
         cols = list(tasks_ag_id[j])[:len(tasks_g_id[j])]
-        if any(change_last[cols]):
+        if any(moved[c] for c in cols):
             if nb < 5 or j < 5:
                 active.append(j)
     return active

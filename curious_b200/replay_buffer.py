@@ -51,8 +51,21 @@ def split_keys(shapes_or_batch):
     return 'task_descr' in shapes_or_batch, 'change' in shapes_or_batch, info
 
 
+_LAYOUTS = {}
+
+
 def layout_from_shapes(buffer_shapes):
-    """buffer_shapes: {key: (T or T+1, dim)} as built by config.configure_buffer (config.py:200-208)."""
+    """buffer_shapes: {key: (T or T+1, dim)} as built by config.configure_buffer (config.py:200-208).  Cached per shape
+    signature (store_episode asks once per call for the normaliser's temporary episodes)."""
+    sig = tuple((k, tuple(int(x) for x in v)) for k, v in buffer_shapes.items())
+    hit = _LAYOUTS.get(sig)
+    if hit is None:
+        hit = _LAYOUTS[sig] = _layout_from_shapes(buffer_shapes)
+    L, info_keys, has_td, has_change = hit
+    return L, list(info_keys), has_td, has_change
+
+
+def _layout_from_shapes(buffer_shapes):
     has_td, has_change, info = split_keys(buffer_shapes)
     T = buffer_shapes['u'][0]
     assert buffer_shapes['o'][0] == T + 1 and buffer_shapes['ag'][0] == T + 1
@@ -258,6 +271,11 @@ class ReplayBuffer:
             overflow = inc - (self.size - self.current_size)
             idx = np.concatenate([np.arange(self.current_size, self.size),
                                   np.random.randint(0, self.current_size, overflow)])
+        elif inc == 1:
+            # one slot of a full buffer (every per-module copy of store_staged): the scalar form draws the same value from the
+            # same stream position as np.random.randint(0, size, 1)[0] at a third of the cost
+            # (tests/test_host_logic.py::test_scalar_randint_is_the_size_one_draw)
+            return np.random.randint(0, self.size)
         else:
             idx = np.random.randint(0, self.size, inc)
         self.current_size = min(self.size, self.current_size + inc)

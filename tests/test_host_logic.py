@@ -442,3 +442,21 @@ def test_host_action_tail_equals_the_reference_statements(n, dimu, with_q):
         rc = lib.cur_actions_finish_host(words.ctypes.data, n, dimu, 0, seq, None, None, None, 0.0, float(max_u),
                                          u_out.ctypes.data, None, 1000)
         assert rc == 3
+
+
+def test_scalar_randint_is_the_size_one_draw():
+    """ReplayBuffer._get_storage_idx draws the slot of a full buffer with the scalar form of np.random.randint: same value,
+    same stream position as the reference's np.random.randint(0, size, 1) (replay_buffer.py:99-102) for every size class."""
+    rng = np.random.RandomState(0)
+    sizes = [1, 2, 3, 5, 8, 9, 255, 256, 257, 1000, 20000, 65535, 65536, 65537, 10 ** 6, 2 ** 31 - 1, 2 ** 31, 2 ** 32 - 1,
+             2 ** 32, 2 ** 32 + 5, 2 ** 40]
+    for _ in range(400):
+        n = int(rng.choice(sizes))
+        seed = int(rng.randint(0, 2 ** 31 - 1))
+        np.random.seed(seed)
+        a = [int(np.random.randint(0, n, 1)[0]) for _ in range(4)]
+        sa = np.random.get_state()
+        np.random.seed(seed)
+        b = [int(np.random.randint(0, n)) for _ in range(4)]
+        sb = np.random.get_state()
+        assert a == b and np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:], (n, seed)
