@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B of two builds of the library on the same box: scratch/ab/lib_head.so vs scratch/ab/lib_new.so (measurement script)
+# A/B of two builds of the library on the same box (measurement script): build the two versions here with
+# `python -m curious_b200.build`, copy curious_b200/libcurious_b200.so to scratch/ab/lib_head.so / scratch/ab/lib_new.so
+# (git-ignored, they travel with the gpurun snapshot), then `gpurun -- ./scratch/ab/ab.sh` (env B = batch rows, PAIR = CUR_ROWS_PAIR)
 for rep in 1 2 3; do
   for v in head new; do
     cp scratch/ab/lib_$v.so curious_b200/libcurious_b200.so
