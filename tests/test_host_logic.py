@@ -460,3 +460,11 @@ def test_scalar_randint_is_the_size_one_draw():
         b = [int(np.random.randint(0, n)) for _ in range(4)]
         sb = np.random.get_state()
         assert a == b and np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:], (n, seed)
+
+
+def test_timeline_dump_without_a_recorded_timeline_is_an_error_not_a_crash():
+    """cur_rows_timeline_dump (debug export) refuses politely when no update ran with CUR_ROWS_TIMELINE=1 (no CUDA call)."""
+    from curious_b200 import _lib
+    lib = _lib.load()
+    assert lib.cur_rows_timeline_dump() == 1                      # CUR_ERR_INVALID
+    assert b'timeline' in (lib.cur_last_error() or b'')
